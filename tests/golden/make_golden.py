@@ -1,0 +1,114 @@
+#!/usr/bin/env python3
+"""Generate the golden fixtures in this directory from the REAL reference implementation.
+
+Run in the build container only (needs `transformers` and /root/reference):
+
+    python tests/golden/make_golden.py
+
+* Mimi encode: ``transformers.MimiModel.encode`` (transformers 5.5.0,
+  models/mimi/modeling_mimi.py:1522-1611), CPU fp32, loaded with the seeded synthetic state dict of
+  ``tokenize_audio_b200.synth.synth_state_dict(0)`` (real kyutai/mimi weights are not available
+  offline). Inputs are stored as int16 PCM (x = pcm / 32768 exactly), outputs as codes [B,K,T]
+  and the pre-quantisation latent [B,512,T].
+* codes -> unicode: ``/root/reference/pretraining-data/converter.py:17-37`` ``codes_to_chars``.
+* feature extractor: ``transformers.EncodecFeatureExtractor`` padding behaviour.
+
+The fixtures travel to the GPU box; this script and /root/reference do not need to.
+"""
+import hashlib
+import importlib.util
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.abspath(os.path.join(HERE, "..", "..")))
+
+from tokenize_audio_b200 import synth  # noqa: E402
+
+
+def pcm16(seed, n):
+    x = synth.synth_speech(seed, n)
+    return np.clip(np.round(x * 32768.0), -32768, 32767).astype(np.int16)
+
+
+def main():
+    from transformers import EncodecFeatureExtractor, MimiConfig, MimiModel
+
+    torch.manual_seed(0)
+    sd = synth.synth_state_dict(0)
+    model = MimiModel(MimiConfig()).eval()
+    missing, unexpected = model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=False)
+    assert not unexpected
+    assert all(k.startswith(("decoder", "upsample")) or "output_proj" in k for k in missing), missing
+    digest = synth.state_dict_digest(sd)
+    fe = EncodecFeatureExtractor()
+
+    def run(name, pcms, K):
+        audio = [p.astype(np.float32) / np.float32(32768.0) for p in pcms]
+        if len(audio) > 1:      # REF/emilia-mimi/process_shard.py:113-118
+            inputs = fe(raw_audio=audio, sampling_rate=24000, return_tensors="pt", padding=True)
+        else:                   # REF/emilia-mimi/process_shard.py:75-79 (padding=None -> True)
+            inputs = fe(raw_audio=audio[0], sampling_rate=24000, return_tensors="pt")
+        iv, pm = inputs["input_values"], inputs["padding_mask"]
+        with torch.no_grad():
+            out = model.encode(iv, pm, num_quantizers=K)
+            emb = model.encoder(iv)
+            z = model.encoder_transformer(emb.transpose(1, 2))[0].transpose(1, 2)
+            latent = model.downsample(z)
+            # the same call without a mask / with None must give the same codes (mask is unused)
+            out2 = model.encode(iv, num_quantizers=K)
+        assert torch.equal(out.audio_codes, out2.audio_codes)
+        codes = out.audio_codes.numpy()
+        assert codes.dtype == np.int64 and codes.max() < 2048
+        n_max = max(len(p) for p in pcms)
+        pcm = np.zeros((len(pcms), n_max), np.int16)
+        for i, p in enumerate(pcms):
+            pcm[i, :len(p)] = p
+        path = os.path.join(HERE, f"{name}.npz")
+        np.savez_compressed(
+            path, pcm=pcm, lengths=np.array([len(p) for p in pcms], np.int64),
+            input_values_sha256=hashlib.sha256(iv.numpy().tobytes()).hexdigest(),
+            padding_mask_sum=pm.sum(-1).numpy().astype(np.int64),
+            codes=codes.astype(np.int16), latent=latent.numpy().astype(np.float32),
+            seanet_out_first=emb.numpy()[0, :, :8].astype(np.float32),
+            num_quantizers=np.int64(K), weights_digest=digest, weights_seed=np.int64(0))
+        print(name, "codes", codes.shape, "latent", tuple(latent.shape), os.path.getsize(path) // 1024, "KiB")
+
+    # C1-like: B=1, ragged tail (N % 1920 != 0), all 32 codebooks
+    run("mimi_b1_k32", [pcm16(101, 24000 + 18000 + 777)], 32)
+    # C2-like: padded batch of 3 with a padding mask, 8 codebooks (odd T25 for the short items)
+    run("mimi_b3_pad_k8", [pcm16(201, 30000), pcm16(202, 47999), pcm16(203, 12345)], 8)
+    # C3-like: T25 = 275 > 250 exercises the sliding window, 8 codebooks
+    run("mimi_long_k8", [pcm16(301, 275 * 960)], 8)
+
+    # get_encoded_length known answers (TF:1490-1503)
+    lens = np.array([240777, 150000, 1, 1919, 1920, 1921, 47999, 12345, 264000], np.int64)
+    enc = model.get_encoded_length(torch.from_numpy(lens)).numpy()
+    np.savez_compressed(os.path.join(HERE, "encoded_length.npz"), lengths=lens, frames=enc.astype(np.int64))
+    print("encoded_length", dict(zip(lens.tolist(), enc.tolist())))
+
+    # codes -> unicode from the reference's own converter (imports numpy+torch only)
+    spec = importlib.util.spec_from_file_location("ref_converter", "/root/reference/pretraining-data/converter.py")
+    conv = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(conv)
+    g = np.random.Generator(np.random.PCG64(7))
+    cases = {}
+    for tag, K, T in (("k8_t375", 8, 375), ("k8_t3", 8, 3), ("k32_t17", 32, 17), ("k1_t5", 1, 5), ("k8_t0", 8, 0)):
+        codes = g.integers(0, 2048, size=(K, T), dtype=np.int64)
+        if T:
+            codes[:, 0] = 0
+            codes[:, -1] = 2047
+        s = conv.codes_to_chars(codes, 2048, copy_before_conversion=True, unicode_offset=0xE000)
+        back = np.array(conv.chars_to_codes(s, K, 2048, unicode_offset=0xE000), np.int64).reshape(K, T) if T else codes
+        assert np.array_equal(back, codes)
+        cases[f"{tag}_codes"] = codes.astype(np.int16)
+        cases[f"{tag}_utf8"] = np.frombuffer(s.encode("utf-8"), np.uint8)
+    np.savez_compressed(os.path.join(HERE, "codes_to_chars.npz"), **cases)
+    print("codes_to_chars", {k: v.shape for k, v in cases.items()})
+
+
+if __name__ == "__main__":
+    main()
