@@ -1,0 +1,165 @@
+/*
+ * mimi_b200.h -- C ABI of the B200-native Mimi encode hot path (waveform -> discrete codes).
+ *
+ * This is the drop-in boundary. The reference (potsawee/tokenize-audio) is pure
+ * Python and reaches the GPU through `transformers.MimiModel.encode`; there is no reference FFI, so
+ * every entry point below cites the reference-side Python interface it stands in for:
+ *
+ *   mimi_b200_encode          <- MimiModel.encode            transformers/models/mimi/modeling_mimi.py:1522-1611
+ *                                called at REF/emilia-mimi/process_shard.py:81-84, :124-127,
+ *                                REF/emilia-mimi/utils.py:63-66 (and the 9 other MimiEncoder copies)
+ *   mimi_b200_load_weights    <- MimiModel.from_pretrained   REF/emilia-mimi/process_shard.py:57-59
+ *                                (+ lazy MimiEuclideanCodebook.embed, modeling_mimi.py:1191-1195)
+ *   mimi_b200_resample        <- utils.resample_audio        REF/emilia-mimi/utils.py:84-87 (librosa.resample)
+ *   mimi_b200_codes_to_utf8   <- utils.codes_to_chars        REF/emilia-mimi/utils.py:18-37,
+ *                                REF/pretraining-data/converter.py:17-37
+ *   mimi_b200_encoded_frames  <- MimiModel.get_encoded_length modeling_mimi.py:1490-1503
+ *
+ * Conventions: plain pointers and sizes only, no C++/torch types, no exceptions across the boundary.
+ * Every function returns an int status (MIMI_B200_OK == 0). `d_` pointers are device memory on the
+ * handle's device, `h_` pointers are host memory. The caller owns inputs, outputs and the workspace;
+ * the library owns its packed weights. Calls are asynchronous on `stream` (a cudaStream_t passed as
+ * void*) and NOT re-entrant per handle. There is no CPU fallback: without a CUDA device every call
+ * fails with MIMI_B200_ERR_CUDA.
+ */
+#ifndef MIMI_B200_H
+#define MIMI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MIMI_B200_ABI_VERSION 1
+
+enum {
+  MIMI_B200_OK = 0,
+  MIMI_B200_ERR_ARG = 1,        /* bad argument (message via mimi_b200_last_error) */
+  MIMI_B200_ERR_CUDA = 2,       /* CUDA runtime / driver error */
+  MIMI_B200_ERR_STATE = 3,      /* e.g. encode before load_weights */
+  MIMI_B200_ERR_WORKSPACE = 4   /* workspace too small */
+};
+
+/* fixed architecture of kyutai/mimi == transformers MimiConfig() defaults */
+#define MIMI_B200_SAMPLE_RATE 24000
+#define MIMI_B200_FRAME_SIZE 1920      /* 24 kHz samples per code frame (12.5 Hz) */
+#define MIMI_B200_HIDDEN 512
+#define MIMI_B200_NUM_CONVS 14
+#define MIMI_B200_NUM_LAYERS 8
+#define MIMI_B200_MAX_QUANTIZERS 32
+#define MIMI_B200_CODEBOOK_SIZE 2048
+#define MIMI_B200_CODEBOOK_DIM 256
+
+typedef struct mimi_b200 mimi_b200_t;
+
+/* One transformer layer, names as in MimiModel.state_dict(): encoder_transformer.layers.{l}.* */
+typedef struct {
+  const float* input_layernorm_weight;          /* [512] */
+  const float* input_layernorm_bias;            /* [512] */
+  const float* q_proj_weight;                   /* [512,512] (out,in) */
+  const float* k_proj_weight;
+  const float* v_proj_weight;
+  const float* o_proj_weight;
+  const float* self_attn_layer_scale;           /* [512] */
+  const float* post_attention_layernorm_weight; /* [512] */
+  const float* post_attention_layernorm_bias;
+  const float* fc1_weight;                      /* [2048,512] */
+  const float* fc2_weight;                      /* [512,2048] */
+  const float* mlp_layer_scale;                 /* [512] */
+} mimi_b200_layer_weights_t;
+
+/* Host fp32 arrays in state-dict layout. The library copies and repacks; the caller keeps ownership. */
+typedef struct {
+  /* encoder.layers.{0, 1.block.1, 1.block.3, 3, 4.block.1, 4.block.3, 6, 7.block.1, 7.block.3, 9,
+     10.block.1, 10.block.3, 12, 14}.conv.{weight [C_out,C_in,k], bias [C_out]} in execution order */
+  const float* conv_weight[MIMI_B200_NUM_CONVS];
+  const float* conv_bias[MIMI_B200_NUM_CONVS];
+  mimi_b200_layer_weights_t layer[MIMI_B200_NUM_LAYERS];
+  const float* downsample_weight;               /* downsample.conv.weight [512,512,4] */
+  const float* semantic_input_proj_weight;      /* quantizer.semantic_...input_proj.weight [256,512,1] */
+  const float* acoustic_input_proj_weight;      /* quantizer.acoustic_...input_proj.weight [256,512,1] */
+  /* index 0 = semantic layer 0, 1..31 = acoustic layers 0..30 */
+  const float* embed_sum[MIMI_B200_MAX_QUANTIZERS];      /* [2048,256] */
+  const float* cluster_usage[MIMI_B200_MAX_QUANTIZERS];  /* [2048] */
+  /* optional [32] rotary inverse frequencies exactly as MimiRotaryEmbedding computes them
+     (modeling_mimi.py:538-560); NULL = computed by the library */
+  const float* rope_inv_freq;
+} mimi_b200_weights_t;
+
+/* Library / ABI identification. */
+int mimi_b200_abi_version(void);
+
+/* Create an engine on CUDA device `device_ordinal`. Fails (no CPU fallback) if there is none. */
+int mimi_b200_create(mimi_b200_t** out, int device_ordinal);
+void mimi_b200_destroy(mimi_b200_t* h);
+
+/* Last error message for this handle (or for create() when h == NULL); owned by the library. */
+const char* mimi_b200_last_error(const mimi_b200_t* h);
+
+int mimi_b200_load_weights(mimi_b200_t* h, const mimi_b200_weights_t* host_weights);
+
+/* T = ceil(N / 1920): frames produced for N input samples (get_encoded_length). */
+int64_t mimi_b200_encoded_frames(int64_t n_samples);
+
+/* Bytes of scratch `mimi_b200_encode` needs for a [B,1,N] batch with K codebooks. */
+int mimi_b200_workspace_bytes(mimi_b200_t* h, int B, int64_t N, int K, size_t* out_bytes);
+
+/*
+ * Encode d_input [B,1,N] fp32 (24 kHz) into d_codes [B,K,T] int64, T = ceil(N/1920).
+ *  h_valid_len  NULL  : strict mode -- every item is encoded over all N samples, exactly what
+ *                       MimiModel.encode does with a padded batch (the padding mask is ignored there).
+ *               [B]   : ragged mode -- item i only needs frames < ceil(h_valid_len[i]/1920) (what
+ *                       MimiEncoder.encode_audio_batch keeps, REF/emilia-mimi/process_shard.py:132-139);
+ *                       work on the padded tail is skipped, kept frames are identical to strict mode
+ *                       (the network is causal), all other frames are written as 0.
+ *  d_latent_opt NULL or [B,512,T] fp32: pre-quantisation latent (downsample conv output) for parity dumps.
+ */
+int mimi_b200_encode(mimi_b200_t* h, const float* d_input, int B, int64_t N,
+                     const int64_t* h_valid_len, int K, int64_t* d_codes, float* d_latent_opt,
+                     void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* Debug/parity taps: copy an internal activation of the LAST encode call into d_out (channels-last
+   [B, rows, C] fp32). `which`: 0..13 = output of SEANet conv i (after residual add for block.3 convs),
+   100+l = transformer layer l output. Returns rows/C through the out params. */
+int mimi_b200_debug_tap(mimi_b200_t* h, int which, float* d_out, size_t out_capacity_floats,
+                        int64_t* rows_per_item, int* channels, void* stream);
+
+/* Debug knobs (parity bisection only): key 0 = number of transformer layers to run (default 8),
+   key 1 = index of the last SEANet conv to run (default 13; smaller values stop the pipeline there and
+   leave d_codes untouched). */
+int mimi_b200_debug_set(mimi_b200_t* h, int key, int value);
+
+/* Output length of the resampler for n input samples: ceil(n * sr_out / sr_in) (librosa fix=True). */
+int64_t mimi_b200_resample_out_len(int64_t n_in, int sr_in, int sr_out);
+
+/*
+ * Polyphase FIR resampler. d_in [B, in_stride] fp32 rows with h_len[i] valid samples each, d_out
+ * [B, out_stride] fp32; row i gets resample_out_len(h_len[i]) samples followed by zeros up to
+ * out_stride (so the result is directly the zero-right-padded [B,1,N] batch the encoder takes).
+ * sr_in == sr_out copies.
+ */
+int mimi_b200_resample(mimi_b200_t* h, const float* d_in, int64_t in_stride, const int64_t* h_len, int B,
+                       int sr_in, int sr_out, float* d_out, int64_t out_stride, void* stream);
+
+/* Bytes of UTF-8 one frame of K codebooks takes (e.g. 28 for K=8, offset 0xE000, size 2048);
+   returns -1 for an offset whose range touches the surrogates U+D800..DFFF (converter.py:68-81). */
+int64_t mimi_b200_utf8_bytes_per_frame(int K, uint32_t unicode_offset, int codebook_size);
+
+/*
+ * codes -> UTF-8 of codes_to_chars: item i, frame t < h_frames[i] (NULL = all T), codebook k becomes
+ * code point unicode_offset + k*codebook_size + d_codes[i,k,t], frame-major / codebook-minor.
+ * d_out is [B, out_stride] bytes; h_out_len_opt[i] (host, may be NULL) receives the byte length of row i.
+ */
+int mimi_b200_codes_to_utf8(mimi_b200_t* h, const int64_t* d_codes, int B, int K, int64_t T,
+                            const int64_t* h_frames, uint32_t unicode_offset, int codebook_size,
+                            uint8_t* d_out, int64_t out_stride, int64_t* h_out_len_opt, void* stream);
+
+/* Number of kernels this handle has launched since creation (bench.py reports it as gpu_launches). */
+int64_t mimi_b200_launch_count(const mimi_b200_t* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MIMI_B200_H */

@@ -1,0 +1,58 @@
+"""Host-side logic that needs no GPU: feature-extractor mirror, bucketing/sharding, product hygiene."""
+import hashlib
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, golden_input, load_golden
+from tokenize_audio_b200 import sharding
+from tokenize_audio_b200.encoder import EncodecFeatureExtractorLite, MimiEncoderOutput
+
+
+def test_feature_extractor_mirror_reproduces_reference_padding():
+    g = load_golden("mimi_b3_pad_k8")
+    lens = g["lengths"].tolist()
+    audio = [golden_input(g)[i, 0, :n] for i, n in enumerate(lens)]
+    out = EncodecFeatureExtractorLite()(raw_audio=audio, sampling_rate=24000, return_tensors="np", padding=True)
+    assert out["input_values"].shape == (3, 1, max(lens)) and out["input_values"].dtype == np.float32
+    assert hashlib.sha256(out["input_values"].tobytes()).hexdigest() == str(g["input_values_sha256"])
+    assert out["padding_mask"].sum(-1).tolist() == g["padding_mask_sum"].tolist() == lens
+    with pytest.raises(ValueError, match="sampling rate"):
+        EncodecFeatureExtractorLite()(raw_audio=audio[0], sampling_rate=16000)
+
+
+def test_single_item_keeps_batch_dim_and_float64_is_downcast():
+    out = EncodecFeatureExtractorLite()(raw_audio=np.zeros(100, np.float64), sampling_rate=24000, return_tensors="np")
+    assert out["input_values"].shape == (1, 1, 100) and out["input_values"].dtype == np.float32
+    assert out["padding_mask"].shape == (1, 100)
+
+
+def test_encoder_output_is_tuple_compatible():
+    o = MimiEncoderOutput("codes")
+    assert o.audio_codes == "codes" and o[0] == "codes" and o.padding_cache is None and len(o) == 3
+
+
+def test_bucket_batches_and_sharding():
+    rng = np.random.default_rng(0)
+    lens = rng.integers(2 * 24000, 20 * 24000, size=256).tolist()
+    batches = sharding.bucket_batches(lens, 64)
+    assert sorted(i for b in batches for i in b) == list(range(256))
+    assert all(len(b) <= 64 for b in batches)
+    file_order = [list(range(i, i + 64)) for i in range(0, 256, 64)]
+    assert sharding.padding_waste(lens, batches) < 0.5 * sharding.padding_waste(lens, file_order)
+    assert sharding.bucket_batches([], 8) == []
+    parts = [sharding.shard_for_rank(10, r, 4) for r in range(4)]
+    assert sorted(i for p in parts for i in p) == list(range(10))
+    assert sharding.reduce_counters({"a": 1.0, "t_max": 2.0}) == {"a": 1.0, "t_max": 2.0}
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "tokenize_audio_b200")
+    for dirpath, _d, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f"{f} imports the oracle"
+                assert "import transformers" not in src and "from transformers" not in src, f"{f} imports transformers"

@@ -1,0 +1,44 @@
+"""The resampler specification (oracle/resample_oracle.py). The reference's librosa/soxr output is
+unpinned (not installed, nothing in the reference tests it), so the oracle is cross-checked for indexing
+against scipy.signal.resample_poly with the same taps and for quality against an ideal band-limited
+signal and torchaudio."""
+import numpy as np
+import pytest
+
+from oracle import resample_oracle as R
+
+
+def tone(sr, n, freqs=(440.0, 3100.0)):
+    t = np.arange(n) / sr
+    return sum(a * np.sin(2 * np.pi * f * t + p) for f, a, p in zip(freqs, (0.5, 0.3), (0.0, 1.0)))
+
+
+@pytest.mark.parametrize("sr_in", [16000, 48000, 44100, 8000, 22050])
+def test_matches_scipy_resample_poly_with_same_taps(sr_in):
+    ss = pytest.importorskip("scipy.signal")
+    n = sr_in // 5 + 13
+    x = tone(sr_in, n).astype(np.float32)
+    h, L, M, c = R.design_taps(sr_in, 24000)
+    y = R.resample(x, sr_in, 24000)
+    assert len(y) == R.out_len(n, sr_in, 24000) == int(np.ceil(n * 24000 / sr_in))
+    ys = ss.resample_poly(x.astype(np.float64), L, M, window=h.astype(np.float64) / L)   # scipy multiplies by L
+    m = min(len(y), len(ys))
+    assert np.abs(y[:m] - ys[:m]).max() < 2e-6
+
+
+@pytest.mark.parametrize("sr_in", [16000, 48000, 44100])
+def test_quality_against_ideal_signal(sr_in):
+    n = sr_in // 2
+    y = R.resample(tone(sr_in, n).astype(np.float32), sr_in, 24000)
+    ideal = tone(24000, len(y))
+    mid = slice(600, len(y) - 600)
+    snr = 10 * np.log10((ideal[mid] ** 2).sum() / ((y[mid] - ideal[mid]) ** 2).sum())
+    assert snr > 120.0, f"SNR {snr:.1f} dB"      # limited by fp32 rounding of taps/output, not the filter
+
+
+def test_same_rate_is_identity_and_lengths():
+    x = np.arange(10, dtype=np.float32)
+    assert R.resample(x, 24000, 24000) is x
+    assert R.out_len(160000, 16000, 24000) == 240000
+    assert R.out_len(1, 16000, 24000) == 2
+    assert len(R.resample(np.zeros(0, np.float32), 16000, 24000)) == 0

@@ -1,0 +1,41 @@
+// Shared helpers for the mimi_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mimi {
+
+constexpr int kHidden = 512;
+constexpr int kHeads = 8;
+constexpr int kHeadDim = 64;
+constexpr int kWindow = 250;      // MimiConfig.sliding_window (modeling_mimi.py:1096-1102)
+constexpr int kFfn = 2048;
+constexpr int kCodebookSize = 2048;
+constexpr int kCodeDim = 256;
+
+// nn.ELU(alpha=1): x > 0 ? x : exp(x) - 1   (modeling_mimi.py:428,473,478)
+__device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : expm1f(x); }
+
+// exact (erf) GELU, ACT2FN["gelu"] used by MimiMLP (modeling_mimi.py:614-627)
+__device__ __forceinline__ float gelu_erf(float x) {
+  return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
+}
+
+__device__ __forceinline__ float4 ld_nc_f4(const float* p) {
+  return __ldg(reinterpret_cast<const float4*>(p));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__host__ __device__ __forceinline__ int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace mimi

@@ -1,0 +1,735 @@
+// mimi_b200: C-ABI engine for the Mimi encode hot path on B200 (sm_100a). See include/mimi_b200.h for the
+// boundary and DESIGN.md for the layout / kernel notes. No CPU fallback anywhere in this file.
+#include "../../include/mimi_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "gemm_simt.cuh"
+#include "io_kernels.cuh"
+#include "rvq.cuh"
+#include "transformer.cuh"
+
+using namespace mimi;
+
+namespace {
+
+struct ConvGeom { int cin, cout, k, stride; };
+// SEANet convs in execution order (MimiEncoder.__init__, modeling_mimi.py:454-488)
+const ConvGeom kConv[MIMI_B200_NUM_CONVS] = {
+    {1, 64, 7, 1},    {64, 32, 3, 1},   {32, 64, 1, 1},   {64, 128, 8, 4},   {128, 64, 3, 1},
+    {64, 128, 1, 1},  {128, 256, 10, 5}, {256, 128, 3, 1}, {128, 256, 1, 1},  {256, 512, 12, 6},
+    {512, 256, 3, 1}, {256, 512, 1, 1}, {512, 1024, 16, 8}, {1024, 512, 3, 1}};
+const int kLevelStride[5] = {4, 5, 6, 8, 2};   // level l+1 = ceil(level l / stride)
+constexpr int kRopeMaxPos = 16384;             // 25 Hz positions (10.9 min); reference chunks are <= 60 s
+constexpr int kStageSlots = 4;
+
+struct LayerDev {
+  float *ln1_w, *ln1_b, *qkv_wt, *o_wt, *ls1, *ln2_w, *ln2_b, *fc1_wt, *fc2_wt, *ls2;
+};
+
+// float offsets of every activation buffer inside the caller's workspace (channels-last, dense
+// [B][rows_max(level)][C])
+struct Plan {
+  int B = 0, K = 0;
+  long long N = 0;
+  int rows[6] = {0, 0, 0, 0, 0, 0};           // max rows per level: N, /4, /20, /120, T25, T
+  long long a0, r1, d1, r2, d2, r3, d3, r4, d4, z, y, qkv, att, ffn, e, rp;   // float offsets
+  long long ints;                              // byte offset of the int region (lens[6][B], prefix[B+1])
+  size_t bytes = 0;
+};
+
+struct TapInfo { long long off; int level; int C; };
+
+}  // namespace
+
+struct mimi_b200 {
+  int device = -1;
+  std::string err;
+  bool loaded = false;
+  long long launches = 0;
+  // weights (device)
+  float* conv_wt[MIMI_B200_NUM_CONVS] = {};    // [K = k*Cin][Cout]; conv 0 keeps [64][7]
+  float* conv_b[MIMI_B200_NUM_CONVS] = {};
+  LayerDev layer[MIMI_B200_NUM_LAYERS] = {};
+  float* down_wt = nullptr;                    // [2048][512]
+  float* proj_wt = nullptr;                    // [512][512]: cols 0..255 semantic, 256..511 acoustic
+  float* embed = nullptr;                      // [32][2048][256]
+  float* embed_t = nullptr;                    // [32][256][2048]
+  float* enorm = nullptr;                      // [32][2048]
+  float* rope_cos = nullptr;                   // [kRopeMaxPos][32]
+  float* rope_sin = nullptr;
+  std::vector<void*> allocs;
+  // pinned staging ring for small host->device int arrays
+  int* stage[kStageSlots] = {};
+  size_t stage_cap = 0;                        // ints per slot
+  cudaEvent_t stage_ev[kStageSlots] = {};
+  int stage_next = 0;
+  // scratch for resample / utf8 length arrays (device)
+  int* dev_ints = nullptr;
+  size_t dev_ints_cap = 0;
+  // resampler taps cache: key (sr_in << 32 | sr_out)
+  struct Taps { float* d; int c, L, M; };
+  std::map<unsigned long long, Taps> taps;
+  // debug knobs and last plan
+  int dbg_layers = MIMI_B200_NUM_LAYERS;
+  int dbg_last_conv = MIMI_B200_NUM_CONVS - 1;
+  Plan last;
+  void* last_ws = nullptr;
+};
+
+static std::string g_create_err;
+
+#define CUDA_TRY(h, expr)                                                                     \
+  do {                                                                                        \
+    cudaError_t e__ = (expr);                                                                 \
+    if (e__ != cudaSuccess) {                                                                 \
+      (h)->err = std::string(#expr) + ": " + cudaGetErrorString(e__);                         \
+      return MIMI_B200_ERR_CUDA;                                                              \
+    }                                                                                         \
+  } while (0)
+
+static int fail(mimi_b200* h, int code, const std::string& msg) {
+  if (h) h->err = msg; else g_create_err = msg;
+  return code;
+}
+
+static int dev_upload(mimi_b200* h, float** dst, const std::vector<float>& src) {
+  void* p = nullptr;
+  CUDA_TRY(h, cudaMalloc(&p, src.size() * sizeof(float)));
+  h->allocs.push_back(p);
+  CUDA_TRY(h, cudaMemcpy(p, src.data(), src.size() * sizeof(float), cudaMemcpyHostToDevice));
+  *dst = static_cast<float*>(p);
+  return MIMI_B200_OK;
+}
+
+// [N][K] (out, in) -> [K][N]
+static std::vector<float> transpose_nk(const float* w, int N, int K) {
+  std::vector<float> t((size_t)N * K);
+  for (int n = 0; n < N; ++n)
+    for (int k = 0; k < K; ++k) t[(size_t)k * N + n] = w[(size_t)n * K + k];
+  return t;
+}
+
+// conv weight [Cout][Cin][k] -> Wt[(tau*Cin + ci)][Cout]
+static std::vector<float> pack_conv(const float* w, int cout, int cin, int k) {
+  std::vector<float> t((size_t)cout * cin * k);
+  for (int co = 0; co < cout; ++co)
+    for (int ci = 0; ci < cin; ++ci)
+      for (int tau = 0; tau < k; ++tau)
+        t[((size_t)tau * cin + ci) * cout + co] = w[((size_t)co * cin + ci) * k + tau];
+  return t;
+}
+
+static void free_weights(mimi_b200* h) {
+  for (void* p : h->allocs) cudaFree(p);
+  h->allocs.clear();
+  h->loaded = false;
+}
+
+static int stage_ints(mimi_b200* h, const std::vector<int>& v, int* d_dst, cudaStream_t st) {
+  if (v.size() > h->stage_cap) {
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    for (int i = 0; i < kStageSlots; ++i) {
+      if (h->stage[i]) cudaFreeHost(h->stage[i]);
+      h->stage[i] = nullptr;
+    }
+    h->stage_cap = std::max<size_t>(4096, v.size() * 2);
+    for (int i = 0; i < kStageSlots; ++i) CUDA_TRY(h, cudaMallocHost((void**)&h->stage[i], h->stage_cap * sizeof(int)));
+  }
+  const int s = h->stage_next;
+  h->stage_next = (s + 1) % kStageSlots;
+  CUDA_TRY(h, cudaEventSynchronize(h->stage_ev[s]));
+  std::memcpy(h->stage[s], v.data(), v.size() * sizeof(int));
+  CUDA_TRY(h, cudaMemcpyAsync(d_dst, h->stage[s], v.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(h, cudaEventRecord(h->stage_ev[s], st));
+  return MIMI_B200_OK;
+}
+
+static int ensure_dev_ints(mimi_b200* h, size_t n) {
+  if (n <= h->dev_ints_cap) return MIMI_B200_OK;
+  CUDA_TRY(h, cudaDeviceSynchronize());
+  if (h->dev_ints) cudaFree(h->dev_ints);
+  h->dev_ints_cap = std::max<size_t>(4096, n * 2);
+  CUDA_TRY(h, cudaMalloc((void**)&h->dev_ints, h->dev_ints_cap * sizeof(int)));
+  return MIMI_B200_OK;
+}
+
+static Plan make_plan(int B, long long N, int K) {
+  Plan p;
+  p.B = B; p.K = K; p.N = N;
+  long long L = N;
+  p.rows[0] = (int)L;
+  for (int l = 0; l < 5; ++l) { L = (L + kLevelStride[l] - 1) / kLevelStride[l]; p.rows[l + 1] = (int)L; }
+  long long off = 0;
+  auto take = [&](int level, int C) {
+    const long long o = off;
+    long long n = (long long)B * p.rows[level] * C;
+    n = (n + 63) / 64 * 64;                  // keep every buffer 256-byte aligned
+    off += n;
+    return o;
+  };
+  p.a0 = take(0, 64);  p.r1 = take(0, 32);
+  p.d1 = take(1, 128); p.r2 = take(1, 64);
+  p.d2 = take(2, 256); p.r3 = take(2, 128);
+  p.d3 = take(3, 512); p.r4 = take(3, 256);
+  p.d4 = take(4, 1024);
+  p.z = take(4, 512);  p.y = take(4, 512);  p.qkv = take(4, 1536);  p.att = take(4, 512);  p.ffn = take(4, 2048);
+  p.e = take(5, 512);  p.rp = take(5, 512);
+  p.ints = off * (long long)sizeof(float);
+  p.bytes = (size_t)p.ints + sizeof(int) * (size_t)(7 * B + 1 + 64);
+  return p;
+}
+
+template <int BM, int BN, int TN>
+static void launch_gemm_t(const GemmParams& p, int B, int lout_max, cudaStream_t st) {
+  dim3 grid((lout_max + BM - 1) / BM, p.N / BN, B);
+  gemm_f32_kernel<BM, BN, TN><<<grid, 256, 0, st>>>(p);
+}
+
+static int launch_gemm(mimi_b200* h, const GemmParams& p, int B, int max_len_in, cudaStream_t st) {
+  const int lout_max = (max_len_in + p.stride - 1) / p.stride;
+  if (lout_max <= 0 || B <= 0) return MIMI_B200_OK;
+  if (p.K % 16 || p.Cin % 16 || p.N % 32) return fail(h, MIMI_B200_ERR_ARG, "gemm: unsupported shape");
+  if (p.N % 128 == 0) launch_gemm_t<128, 128, 8>(p, B, lout_max, st);
+  else if (p.N % 64 == 0) launch_gemm_t<128, 64, 4>(p, B, lout_max, st);
+  else launch_gemm_t<256, 32, 4>(p, B, lout_max, st);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  return MIMI_B200_OK;
+}
+
+// ---- resampler taps (same design as oracle/resample_oracle.py: Kaiser-windowed sinc) -----------------
+static double bessel_i0(double x) {
+  double sum = 1.0, term = 1.0;
+  const double q = x * x / 4.0;
+  for (int k = 1; k < 500; ++k) {
+    term *= q / ((double)k * (double)k);
+    sum += term;
+    if (term < 1e-20 * sum) break;
+  }
+  return sum;
+}
+
+static void design_taps(int sr_in, int sr_out, std::vector<float>& taps, int& c, int& L, int& M) {
+  long long a = sr_in, b = sr_out;
+  while (b) { const long long t = a % b; a = b; b = t; }
+  L = (int)(sr_out / a); M = (int)(sr_in / a);
+  const double kZeros = 32.0, kRolloff = 0.945, kBeta = 14.769656459379492;
+  const double fc = kRolloff * 0.5 / std::max(L, M);
+  c = (int)std::ceil(kZeros / (2.0 * fc));
+  const int n = 2 * c + 1;
+  std::vector<double> hcoef(n);
+  const double i0b = bessel_i0(kBeta);
+  double sum = 0.0;
+  for (int i = 0; i < n; ++i) {
+    const double t = (double)(i - c);
+    const double xx = 2.0 * fc * t;
+    const double sinc = (t == 0.0) ? 1.0 : std::sin(M_PI * xx) / (M_PI * xx);
+    const double r = (double)(i - c) / (double)c;
+    const double w = bessel_i0(kBeta * std::sqrt(std::max(0.0, 1.0 - r * r))) / i0b;
+    hcoef[i] = 2.0 * fc * sinc * w;
+    sum += hcoef[i];
+  }
+  taps.resize(n);
+  for (int i = 0; i < n; ++i) taps[i] = (float)(hcoef[i] * (double)L / sum);
+}
+
+static int utf8_len(unsigned cp) { return cp < 0x80u ? 1 : cp < 0x800u ? 2 : cp < 0x10000u ? 3 : 4; }
+
+// =====================================================================================================
+extern "C" {
+
+int mimi_b200_abi_version(void) { return MIMI_B200_ABI_VERSION; }
+
+const char* mimi_b200_last_error(const mimi_b200_t* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+int64_t mimi_b200_launch_count(const mimi_b200_t* h) { return h ? h->launches : 0; }
+
+int64_t mimi_b200_encoded_frames(int64_t n) {
+  for (int l = 0; l < 5; ++l) n = (n + kLevelStride[l] - 1) / kLevelStride[l];
+  return n;
+}
+
+int mimi_b200_create(mimi_b200_t** out, int device_ordinal) {
+  if (!out) return fail(nullptr, MIMI_B200_ERR_ARG, "create: out is NULL");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(nullptr, MIMI_B200_ERR_CUDA,
+                std::string("create: no CUDA device (") + cudaGetErrorString(e) + "); there is no CPU fallback");
+  if (device_ordinal < 0 || device_ordinal >= n) return fail(nullptr, MIMI_B200_ERR_ARG, "create: bad device ordinal");
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device_ordinal)) != cudaSuccess)
+    return fail(nullptr, MIMI_B200_ERR_CUDA, cudaGetErrorString(e));
+  if (prop.major != 10)
+    return fail(nullptr, MIMI_B200_ERR_CUDA, "create: this library is built for sm_100a (B200) only");
+  mimi_b200* h = new mimi_b200();
+  h->device = device_ordinal;
+  if ((e = cudaSetDevice(device_ordinal)) != cudaSuccess) { delete h; return fail(nullptr, MIMI_B200_ERR_CUDA, cudaGetErrorString(e)); }
+  for (int i = 0; i < kStageSlots; ++i) cudaEventCreateWithFlags(&h->stage_ev[i], cudaEventDisableTiming);
+  cudaFuncSetAttribute(swa_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttSmemBytes);
+  cudaFuncSetAttribute(rvq_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRvqSmemBytes);
+  if ((e = cudaGetLastError()) != cudaSuccess) { delete h; return fail(nullptr, MIMI_B200_ERR_CUDA, cudaGetErrorString(e)); }
+  *out = h;
+  return MIMI_B200_OK;
+}
+
+void mimi_b200_destroy(mimi_b200_t* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  free_weights(h);
+  for (int i = 0; i < kStageSlots; ++i) {
+    if (h->stage[i]) cudaFreeHost(h->stage[i]);
+    if (h->stage_ev[i]) cudaEventDestroy(h->stage_ev[i]);
+  }
+  if (h->dev_ints) cudaFree(h->dev_ints);
+  for (auto& kv : h->taps) cudaFree(kv.second.d);
+  delete h;
+}
+
+int mimi_b200_debug_set(mimi_b200_t* h, int key, int value) {
+  if (!h) return MIMI_B200_ERR_ARG;
+  if (key == 0) h->dbg_layers = std::min(std::max(value, 0), MIMI_B200_NUM_LAYERS);
+  else if (key == 1) h->dbg_last_conv = std::min(std::max(value, 0), MIMI_B200_NUM_CONVS - 1);
+  else return fail(h, MIMI_B200_ERR_ARG, "debug_set: unknown key");
+  return MIMI_B200_OK;
+}
+
+int mimi_b200_load_weights(mimi_b200_t* h, const mimi_b200_weights_t* w) {
+  if (!h || !w) return fail(h, MIMI_B200_ERR_ARG, "load_weights: NULL argument");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  free_weights(h);
+  for (int i = 0; i < MIMI_B200_NUM_CONVS; ++i)
+    if (!w->conv_weight[i] || !w->conv_bias[i]) return fail(h, MIMI_B200_ERR_ARG, "load_weights: missing SEANet conv tensor");
+  int rc;
+  for (int i = 0; i < MIMI_B200_NUM_CONVS; ++i) {
+    const ConvGeom& g = kConv[i];
+    std::vector<float> wt = (i == 0) ? std::vector<float>(w->conv_weight[0], w->conv_weight[0] + 64 * 7)
+                                     : pack_conv(w->conv_weight[i], g.cout, g.cin, g.k);
+    if ((rc = dev_upload(h, &h->conv_wt[i], wt))) return rc;
+    if ((rc = dev_upload(h, &h->conv_b[i], std::vector<float>(w->conv_bias[i], w->conv_bias[i] + g.cout)))) return rc;
+  }
+  for (int l = 0; l < MIMI_B200_NUM_LAYERS; ++l) {
+    const mimi_b200_layer_weights_t& s = w->layer[l];
+    const float* need[] = {s.input_layernorm_weight, s.input_layernorm_bias, s.q_proj_weight, s.k_proj_weight,
+                           s.v_proj_weight, s.o_proj_weight, s.self_attn_layer_scale, s.post_attention_layernorm_weight,
+                           s.post_attention_layernorm_bias, s.fc1_weight, s.fc2_weight, s.mlp_layer_scale};
+    for (const float* q : need) if (!q) return fail(h, MIMI_B200_ERR_ARG, "load_weights: missing transformer tensor");
+    LayerDev& d = h->layer[l];
+    auto vec = [](const float* p, size_t n) { return std::vector<float>(p, p + n); };
+    if ((rc = dev_upload(h, &d.ln1_w, vec(s.input_layernorm_weight, 512)))) return rc;
+    if ((rc = dev_upload(h, &d.ln1_b, vec(s.input_layernorm_bias, 512)))) return rc;
+    if ((rc = dev_upload(h, &d.ln2_w, vec(s.post_attention_layernorm_weight, 512)))) return rc;
+    if ((rc = dev_upload(h, &d.ln2_b, vec(s.post_attention_layernorm_bias, 512)))) return rc;
+    if ((rc = dev_upload(h, &d.ls1, vec(s.self_attn_layer_scale, 512)))) return rc;
+    if ((rc = dev_upload(h, &d.ls2, vec(s.mlp_layer_scale, 512)))) return rc;
+    // fused QKV: Wt [512][1536], columns [q | k | v]
+    std::vector<float> qkv((size_t)512 * 1536);
+    const float* src[3] = {s.q_proj_weight, s.k_proj_weight, s.v_proj_weight};
+    for (int part = 0; part < 3; ++part)
+      for (int n = 0; n < 512; ++n)
+        for (int k = 0; k < 512; ++k) qkv[(size_t)k * 1536 + part * 512 + n] = src[part][(size_t)n * 512 + k];
+    if ((rc = dev_upload(h, &d.qkv_wt, qkv))) return rc;
+    if ((rc = dev_upload(h, &d.o_wt, transpose_nk(s.o_proj_weight, 512, 512)))) return rc;
+    if ((rc = dev_upload(h, &d.fc1_wt, transpose_nk(s.fc1_weight, 2048, 512)))) return rc;
+    if ((rc = dev_upload(h, &d.fc2_wt, transpose_nk(s.fc2_weight, 512, 2048)))) return rc;
+  }
+  if (!w->downsample_weight || !w->semantic_input_proj_weight || !w->acoustic_input_proj_weight)
+    return fail(h, MIMI_B200_ERR_ARG, "load_weights: missing downsample / input_proj tensor");
+  if ((rc = dev_upload(h, &h->down_wt, pack_conv(w->downsample_weight, 512, 512, 4)))) return rc;
+  {
+    std::vector<float> pj((size_t)512 * 512);
+    for (int n = 0; n < 256; ++n)
+      for (int k = 0; k < 512; ++k) {
+        pj[(size_t)k * 512 + n] = w->semantic_input_proj_weight[(size_t)n * 512 + k];
+        pj[(size_t)k * 512 + 256 + n] = w->acoustic_input_proj_weight[(size_t)n * 512 + k];
+      }
+    if ((rc = dev_upload(h, &h->proj_wt, pj))) return rc;
+  }
+  {
+    // MimiEuclideanCodebook.embed (modeling_mimi.py:1191-1195): embed_sum / clamp(cluster_usage, 1e-5)
+    const size_t per = (size_t)kCodebookSize * kCodeDim;
+    std::vector<float> E(32 * per), Et(32 * per), En((size_t)32 * kCodebookSize);
+    for (int s = 0; s < MIMI_B200_MAX_QUANTIZERS; ++s) {
+      if (!w->embed_sum[s] || !w->cluster_usage[s]) return fail(h, MIMI_B200_ERR_ARG, "load_weights: missing codebook tensor");
+      for (int c = 0; c < kCodebookSize; ++c) {
+        const float u = std::max(w->cluster_usage[s][c], 1e-5f);
+        double nrm = 0.0;
+        for (int k = 0; k < kCodeDim; ++k) {
+          const float v = w->embed_sum[s][(size_t)c * kCodeDim + k] / u;
+          E[s * per + (size_t)c * kCodeDim + k] = v;
+          Et[s * per + (size_t)k * kCodebookSize + c] = v;
+          nrm += (double)v * (double)v;
+        }
+        En[(size_t)s * kCodebookSize + c] = (float)nrm;
+      }
+    }
+    if ((rc = dev_upload(h, &h->embed, E))) return rc;
+    if ((rc = dev_upload(h, &h->embed_t, Et))) return rc;
+    if ((rc = dev_upload(h, &h->enorm, En))) return rc;
+  }
+  {
+    // MimiRotaryEmbedding (modeling_mimi.py:538-577): angle = float(pos) * inv_freq[i] in fp32
+    std::vector<float> cs((size_t)kRopeMaxPos * 32), sn((size_t)kRopeMaxPos * 32);
+    float inv[32];
+    for (int i = 0; i < 32; ++i)
+      inv[i] = w->rope_inv_freq ? w->rope_inv_freq[i] : 1.0f / powf(10000.0f, (float)(2 * i) / 64.0f);
+    for (int pos = 0; pos < kRopeMaxPos; ++pos)
+      for (int i = 0; i < 32; ++i) {
+        const float ang = (float)pos * inv[i];
+        cs[(size_t)pos * 32 + i] = cosf(ang);
+        sn[(size_t)pos * 32 + i] = sinf(ang);
+      }
+    if ((rc = dev_upload(h, &h->rope_cos, cs))) return rc;
+    if ((rc = dev_upload(h, &h->rope_sin, sn))) return rc;
+  }
+  h->loaded = true;
+  return MIMI_B200_OK;
+}
+
+int mimi_b200_workspace_bytes(mimi_b200_t* h, int B, int64_t N, int K, size_t* out_bytes) {
+  if (!h || !out_bytes) return fail(h, MIMI_B200_ERR_ARG, "workspace_bytes: NULL argument");
+  if (B < 0 || N < 0 || N > (1ll << 30) || K < 1 || K > MIMI_B200_MAX_QUANTIZERS)
+    return fail(h, MIMI_B200_ERR_ARG, "workspace_bytes: bad B/N/K");
+  *out_bytes = make_plan(B, N, K).bytes + 256;
+  return MIMI_B200_OK;
+}
+
+int mimi_b200_encode(mimi_b200_t* h, const float* d_input, int B, int64_t N, const int64_t* h_valid_len, int K,
+                     int64_t* d_codes, float* d_latent_opt, void* d_workspace, size_t workspace_bytes, void* stream) {
+  if (!h) return MIMI_B200_ERR_ARG;
+  if (!h->loaded) return fail(h, MIMI_B200_ERR_STATE, "encode: weights not loaded");
+  if (K > MIMI_B200_MAX_QUANTIZERS)
+    return fail(h, MIMI_B200_ERR_ARG,
+                "The number of quantizers (i.e codebooks) asked should be lower than the total number of quantizers 32, "
+                "but is currently " + std::to_string(K) + ".");
+  if (K < 1)
+    return fail(h, MIMI_B200_ERR_ARG,
+                "The number of quantizers (i.e codebooks) asked should be higher than the number of semantic quantizers 1, "
+                "but is currently " + std::to_string(K) + ".");
+  if (B < 0 || N < 0 || N > (1ll << 30)) return fail(h, MIMI_B200_ERR_ARG, "encode: bad B/N");
+  if (B == 0 || N == 0) return MIMI_B200_OK;
+  if (!d_input || !d_codes || !d_workspace) return fail(h, MIMI_B200_ERR_ARG, "encode: NULL device pointer");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+  const Plan p = make_plan(B, N, K);
+  // align the workspace base to 256 bytes
+  uintptr_t base = (reinterpret_cast<uintptr_t>(d_workspace) + 255) & ~uintptr_t(255);
+  if (base + p.bytes > reinterpret_cast<uintptr_t>(d_workspace) + workspace_bytes)
+    return fail(h, MIMI_B200_ERR_WORKSPACE, "encode: workspace too small, need " + std::to_string(p.bytes + 256));
+  if (p.rows[4] > kRopeMaxPos) return fail(h, MIMI_B200_ERR_ARG, "encode: more than 16384 25-Hz positions per item");
+  float* ws = reinterpret_cast<float*>(base);
+  int* dints = reinterpret_cast<int*>(base + p.ints);
+  h->last = p;
+  h->last_ws = ws;
+
+  // per-level lengths. strict: uniform (no arrays). ragged: item i is encoded over
+  // min(N, ceil(len_i/1920)*1920) samples (identical kept frames, see mimi_b200.h).
+  const int* dlen[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  const int* dprefix = nullptr;
+  int maxlen[6];
+  for (int l = 0; l < 6; ++l) maxlen[l] = p.rows[l];
+  int total_frames = B * p.rows[5];
+  if (h_valid_len) {
+    std::vector<int> v((size_t)7 * B + 1);
+    int mx[6] = {0, 0, 0, 0, 0, 0};
+    int acc = 0;
+    for (int b = 0; b < B; ++b) {
+      long long len = h_valid_len[b];
+      if (len < 0 || len > N) return fail(h, MIMI_B200_ERR_ARG, "encode: valid_len out of range");
+      long long L = std::min<long long>(N, (len + MIMI_B200_FRAME_SIZE - 1) / MIMI_B200_FRAME_SIZE * MIMI_B200_FRAME_SIZE);
+      for (int l = 0; l < 6; ++l) {
+        v[(size_t)l * B + b] = (int)L;
+        mx[l] = std::max(mx[l], (int)L);
+        if (l < 5) L = (L + kLevelStride[l] - 1) / kLevelStride[l];
+      }
+      v[(size_t)6 * B + b] = acc;
+      acc += v[(size_t)5 * B + b];
+    }
+    v[(size_t)7 * B] = acc;
+    total_frames = acc;
+    int rc = stage_ints(h, v, dints, st);
+    if (rc) return rc;
+    for (int l = 0; l < 6; ++l) { dlen[l] = dints + (size_t)l * B; maxlen[l] = mx[l]; }
+    dprefix = dints + (size_t)6 * B;
+    const long long ncodes = (long long)B * K * p.rows[5];
+    fill_codes_zero_kernel<<<(unsigned)((ncodes + 255) / 256), 256, 0, st>>>(reinterpret_cast<long long*>(d_codes), ncodes);
+    h->launches++;
+  }
+
+  auto istride = [&](int level, int C) { return (long long)p.rows[level] * C; };
+  int rc;
+
+  // ---- SEANet encoder (MimiEncoder.forward, modeling_mimi.py:490-496) ------------------------------
+  {
+    dim3 grid((maxlen[0] + 127) / 128, B);
+    if (maxlen[0] > 0) {
+      conv0_kernel<<<grid, 256, 0, st>>>(d_input, N, h->conv_wt[0], h->conv_b[0], ws + p.a0, istride(0, 64), dlen[0], maxlen[0]);
+      h->launches++;
+      CUDA_TRY(h, cudaGetLastError());
+    }
+  }
+  struct Stage { long long h_off, r_off; int level, C; };
+  const Stage stages[4] = {{p.a0, p.r1, 0, 64}, {p.d1, p.r2, 1, 128}, {p.d2, p.r3, 2, 256}, {p.d3, p.r4, 3, 512}};
+  const long long down_off[4] = {p.d1, p.d2, p.d3, p.d4};
+  bool stop = h->dbg_last_conv < 1;
+  for (int s = 0; s < 4 && !stop; ++s) {
+    const Stage& sg = stages[s];
+    const int ia = 1 + 3 * s, ib = 2 + 3 * s, id = 3 + 3 * s;
+    GemmParams g{};
+    // resblock conv a: ELU -> C -> C/2, k3
+    g.A = ws + sg.h_off; g.Wt = h->conv_wt[ia]; g.bias = h->conv_b[ia]; g.out = ws + sg.r_off;
+    g.len_in = dlen[sg.level]; g.uniform_len_in = maxlen[sg.level];
+    g.a_item_stride = istride(sg.level, sg.C); g.out_item_stride = istride(sg.level, sg.C / 2);
+    g.Cin = sg.C; g.stride = 1; g.pad_left = 2; g.K = 3 * sg.C; g.N = sg.C / 2; g.elu_in = 1;
+    if ((rc = launch_gemm(h, g, B, maxlen[sg.level], st))) return rc;
+    if (h->dbg_last_conv <= ia) { stop = true; break; }
+    // resblock conv b: ELU -> C/2 -> C, k1, + skip (in place on h)
+    g = GemmParams{};
+    g.A = ws + sg.r_off; g.Wt = h->conv_wt[ib]; g.bias = h->conv_b[ib]; g.res = ws + sg.h_off; g.out = ws + sg.h_off;
+    g.len_in = dlen[sg.level]; g.uniform_len_in = maxlen[sg.level];
+    g.a_item_stride = istride(sg.level, sg.C / 2); g.out_item_stride = istride(sg.level, sg.C);
+    g.Cin = sg.C / 2; g.stride = 1; g.pad_left = 0; g.K = sg.C / 2; g.N = sg.C; g.elu_in = 1;
+    if ((rc = launch_gemm(h, g, B, maxlen[sg.level], st))) return rc;
+    if (h->dbg_last_conv <= ib) { stop = true; break; }
+    // strided down conv: ELU -> C -> 2C, k = 2*ratio, stride = ratio
+    const ConvGeom& cg = kConv[id];
+    g = GemmParams{};
+    g.A = ws + sg.h_off; g.Wt = h->conv_wt[id]; g.bias = h->conv_b[id]; g.out = ws + down_off[s];
+    g.len_in = dlen[sg.level]; g.uniform_len_in = maxlen[sg.level];
+    g.a_item_stride = istride(sg.level, sg.C); g.out_item_stride = istride(sg.level + 1, 2 * sg.C);
+    g.Cin = sg.C; g.stride = cg.stride; g.pad_left = cg.k - cg.stride; g.K = cg.k * sg.C; g.N = 2 * sg.C; g.elu_in = 1;
+    if ((rc = launch_gemm(h, g, B, maxlen[sg.level], st))) return rc;
+    if (h->dbg_last_conv <= id) { stop = true; break; }
+  }
+  if (stop) return MIMI_B200_OK;
+  {
+    GemmParams g{};   // final conv: ELU -> 1024 -> 512, k3
+    g.A = ws + p.d4; g.Wt = h->conv_wt[13]; g.bias = h->conv_b[13]; g.out = ws + p.z;
+    g.len_in = dlen[4]; g.uniform_len_in = maxlen[4];
+    g.a_item_stride = istride(4, 1024); g.out_item_stride = istride(4, 512);
+    g.Cin = 1024; g.stride = 1; g.pad_left = 2; g.K = 3072; g.N = 512; g.elu_in = 1;
+    if ((rc = launch_gemm(h, g, B, maxlen[4], st))) return rc;
+  }
+
+  // ---- encoder transformer (MimiTransformerModel.forward, modeling_mimi.py:1015-1140) ---------------
+  const int T25 = maxlen[4];
+  for (int l = 0; l < h->dbg_layers; ++l) {
+    const LayerDev& d = h->layer[l];
+    dim3 lgrid((T25 + 7) / 8, B);
+    layernorm512_kernel<<<lgrid, 256, 0, st>>>(ws + p.z, ws + p.y, d.ln1_w, d.ln1_b, istride(4, 512), dlen[4], T25);
+    h->launches++;
+    GemmParams g{};
+    g.A = ws + p.y; g.Wt = d.qkv_wt; g.out = ws + p.qkv; g.len_in = dlen[4]; g.uniform_len_in = T25;
+    g.a_item_stride = istride(4, 512); g.out_item_stride = istride(4, 1536);
+    g.Cin = 512; g.stride = 1; g.K = 512; g.N = 1536;
+    if ((rc = launch_gemm(h, g, B, T25, st))) return rc;
+    dim3 agrid((T25 + kAttQT - 1) / kAttQT, kHeads, B);
+    swa_attention_kernel<<<agrid, 256, kAttSmemBytes, st>>>(ws + p.qkv, istride(4, 1536), ws + p.att, istride(4, 512),
+                                                            h->rope_cos, h->rope_sin, dlen[4], T25);
+    h->launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    g = GemmParams{};   // o_proj + LayerScale + residual (in place on z)
+    g.A = ws + p.att; g.Wt = d.o_wt; g.scale = d.ls1; g.res = ws + p.z; g.out = ws + p.z;
+    g.len_in = dlen[4]; g.uniform_len_in = T25; g.a_item_stride = istride(4, 512); g.out_item_stride = istride(4, 512);
+    g.Cin = 512; g.stride = 1; g.K = 512; g.N = 512;
+    if ((rc = launch_gemm(h, g, B, T25, st))) return rc;
+    layernorm512_kernel<<<lgrid, 256, 0, st>>>(ws + p.z, ws + p.y, d.ln2_w, d.ln2_b, istride(4, 512), dlen[4], T25);
+    h->launches++;
+    g = GemmParams{};   // fc1 + GELU(erf)
+    g.A = ws + p.y; g.Wt = d.fc1_wt; g.out = ws + p.ffn; g.len_in = dlen[4]; g.uniform_len_in = T25;
+    g.a_item_stride = istride(4, 512); g.out_item_stride = istride(4, 2048);
+    g.Cin = 512; g.stride = 1; g.K = 512; g.N = 2048; g.act = 1;
+    if ((rc = launch_gemm(h, g, B, T25, st))) return rc;
+    g = GemmParams{};   // fc2 + LayerScale + residual (in place on z)
+    g.A = ws + p.ffn; g.Wt = d.fc2_wt; g.scale = d.ls2; g.res = ws + p.z; g.out = ws + p.z;
+    g.len_in = dlen[4]; g.uniform_len_in = T25; g.a_item_stride = istride(4, 2048); g.out_item_stride = istride(4, 512);
+    g.Cin = 2048; g.stride = 1; g.K = 2048; g.N = 512;
+    if ((rc = launch_gemm(h, g, B, T25, st))) return rc;
+  }
+
+  // ---- stride-2 downsample conv, replicate padding (modeling_mimi.py:1422-1431,1484) ----------------
+  {
+    GemmParams g{};
+    g.A = ws + p.z; g.Wt = h->down_wt; g.out = ws + p.e; g.len_in = dlen[4]; g.uniform_len_in = T25;
+    g.a_item_stride = istride(4, 512); g.out_item_stride = istride(5, 512);
+    g.Cin = 512; g.stride = 2; g.pad_left = 2; g.K = 2048; g.N = 512; g.replicate = 1;
+    if ((rc = launch_gemm(h, g, B, T25, st))) return rc;
+  }
+  const int T = maxlen[5];
+  if (d_latent_opt) {
+    const long long n = (long long)kHidden * p.rows[5];
+    dim3 tgrid((unsigned)((n + 255) / 256), B);
+    latent_transpose_kernel<<<tgrid, 256, 0, st>>>(ws + p.e, istride(5, 512), d_latent_opt, p.rows[5], dlen[5], T);
+    h->launches++;
+  }
+  // ---- split RVQ (modeling_mimi.py:1311-1338): both input_proj as one GEMM, then the fused chain -----
+  {
+    GemmParams g{};
+    g.A = ws + p.e; g.Wt = h->proj_wt; g.out = ws + p.rp; g.len_in = dlen[5]; g.uniform_len_in = T;
+    g.a_item_stride = istride(5, 512); g.out_item_stride = istride(5, 512);
+    g.Cin = 512; g.stride = 1; g.K = 512; g.N = 512;
+    if ((rc = launch_gemm(h, g, B, T, st))) return rc;
+    RvqParams r{};
+    r.rproj = ws + p.rp; r.item_stride = istride(5, 512);
+    r.embed = h->embed; r.embed_t = h->embed_t; r.enorm = h->enorm;
+    r.codes = reinterpret_cast<long long*>(d_codes); r.K = K; r.T_out = p.rows[5];
+    r.len = dlen[5]; r.uniform_len = T; r.B = B; r.total_frames = total_frames; r.frame_prefix = dprefix;
+    if (total_frames > 0) {
+      rvq_encode_kernel<<<(total_frames + kRvqFM - 1) / kRvqFM, 256, kRvqSmemBytes, st>>>(r);
+      h->launches++;
+    }
+  }
+  CUDA_TRY(h, cudaGetLastError());
+  return MIMI_B200_OK;
+}
+
+int mimi_b200_debug_tap(mimi_b200_t* h, int which, float* d_out, size_t cap, int64_t* rows_per_item, int* channels,
+                        void* stream) {
+  if (!h || !h->last_ws) return fail(h, MIMI_B200_ERR_STATE, "debug_tap: no encode call yet");
+  const Plan& p = h->last;
+  TapInfo t{};
+  switch (which) {
+    case 0: case 2: t = {p.a0, 0, 64}; break;
+    case 1: t = {p.r1, 0, 32}; break;
+    case 3: case 5: t = {p.d1, 1, 128}; break;
+    case 4: t = {p.r2, 1, 64}; break;
+    case 6: case 8: t = {p.d2, 2, 256}; break;
+    case 7: t = {p.r3, 2, 128}; break;
+    case 9: case 11: t = {p.d3, 3, 512}; break;
+    case 10: t = {p.r4, 3, 256}; break;
+    case 12: t = {p.d4, 4, 1024}; break;
+    case 13: t = {p.z, 4, 512}; break;
+    case 200: t = {p.e, 5, 512}; break;
+    case 201: t = {p.rp, 5, 512}; break;
+    default:
+      if (which >= 100 && which < 100 + MIMI_B200_NUM_LAYERS) t = {p.z, 4, 512};
+      else return fail(h, MIMI_B200_ERR_ARG, "debug_tap: unknown tap");
+  }
+  const size_t n = (size_t)p.B * p.rows[t.level] * t.C;
+  if (rows_per_item) *rows_per_item = p.rows[t.level];
+  if (channels) *channels = t.C;
+  if (!d_out) return MIMI_B200_OK;
+  if (cap < n) return fail(h, MIMI_B200_ERR_ARG, "debug_tap: output too small");
+  CUDA_TRY(h, cudaMemcpyAsync(d_out, static_cast<float*>(h->last_ws) + t.off, n * sizeof(float), cudaMemcpyDeviceToDevice,
+                              static_cast<cudaStream_t>(stream)));
+  return MIMI_B200_OK;
+}
+
+int64_t mimi_b200_resample_out_len(int64_t n_in, int sr_in, int sr_out) {
+  if (sr_in <= 0 || sr_out <= 0 || n_in < 0) return -1;
+  if (sr_in == sr_out) return n_in;
+  return (int64_t)std::ceil((double)n_in * (double)sr_out / (double)sr_in);
+}
+
+int mimi_b200_resample(mimi_b200_t* h, const float* d_in, int64_t in_stride, const int64_t* h_len, int B, int sr_in,
+                       int sr_out, float* d_out, int64_t out_stride, void* stream) {
+  if (!h || !d_in || !d_out || !h_len) return fail(h, MIMI_B200_ERR_ARG, "resample: NULL argument");
+  if (B <= 0) return MIMI_B200_OK;
+  if (sr_in <= 0 || sr_out <= 0) return fail(h, MIMI_B200_ERR_ARG, "resample: bad sample rate");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  std::vector<int> v((size_t)2 * B);
+  for (int b = 0; b < B; ++b) {
+    if (h_len[b] < 0 || h_len[b] > in_stride || h_len[b] > (1ll << 30)) return fail(h, MIMI_B200_ERR_ARG, "resample: bad length");
+    const int64_t ol = mimi_b200_resample_out_len(h_len[b], sr_in, sr_out);
+    if (ol > out_stride) return fail(h, MIMI_B200_ERR_ARG, "resample: out_stride too small");
+    v[b] = (int)h_len[b];
+    v[(size_t)B + b] = (int)ol;
+  }
+  mimi_b200::Taps tp;
+  if (sr_in == sr_out) {
+    // identity filter: L = M = 1, single tap 1.0 (REF/*/utils.py:85-86 returns the input unchanged)
+    sr_in = sr_out = 1;
+  }
+  const unsigned long long key = ((unsigned long long)(unsigned)sr_in << 32) | (unsigned)sr_out;
+  auto it = h->taps.find(key);
+  if (it == h->taps.end()) {
+    std::vector<float> taps;
+    int c, L, M;
+    if (sr_in == sr_out) { taps.assign(1, 1.0f); c = 0; L = 1; M = 1; }
+    else design_taps(sr_in, sr_out, taps, c, L, M);
+    float* d = nullptr;
+    CUDA_TRY(h, cudaMalloc((void**)&d, taps.size() * sizeof(float)));
+    CUDA_TRY(h, cudaMemcpy(d, taps.data(), taps.size() * sizeof(float), cudaMemcpyHostToDevice));
+    tp = {d, c, L, M};
+    h->taps[key] = tp;
+  } else {
+    tp = it->second;
+  }
+  int rc;
+  if ((rc = ensure_dev_ints(h, v.size()))) return rc;
+  if ((rc = stage_ints(h, v, h->dev_ints, st))) return rc;
+  dim3 grid((unsigned)((out_stride + 255) / 256), B);
+  resample_kernel<<<grid, 256, 0, st>>>(d_in, in_stride, h->dev_ints, h->dev_ints + B, tp.d, tp.c, tp.L, tp.M, d_out, out_stride);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  return MIMI_B200_OK;
+}
+
+int64_t mimi_b200_utf8_bytes_per_frame(int K, uint32_t off, int cbs) {
+  if (K < 1 || K > 32 || cbs < 1) return -1;
+  const unsigned long long lower = off, upper = (unsigned long long)off + (unsigned long long)K * cbs;
+  if (lower < 0xDFFFull && upper > 0xD800ull) return -1;     // converter.py:68-81
+  if (upper > 0x110000ull) return -1;
+  int64_t n = 0;
+  for (int k = 0; k < K; ++k) {
+    const unsigned lo = off + (unsigned)k * cbs, hi = lo + cbs - 1;
+    if (utf8_len(lo) != utf8_len(hi)) return -1;             // variable width inside one codebook: unsupported
+    n += utf8_len(lo);
+  }
+  return n;
+}
+
+int mimi_b200_codes_to_utf8(mimi_b200_t* h, const int64_t* d_codes, int B, int K, int64_t T, const int64_t* h_frames,
+                            uint32_t off, int cbs, uint8_t* d_out, int64_t out_stride, int64_t* h_out_len_opt, void* stream) {
+  if (!h) return MIMI_B200_ERR_ARG;
+  const int64_t bpf = mimi_b200_utf8_bytes_per_frame(K, off, cbs);
+  if (bpf < 0) return fail(h, MIMI_B200_ERR_ARG, "codes_to_utf8: unicode offset / codebook range not representable");
+  if (B <= 0 || T < 0) return fail(h, MIMI_B200_ERR_ARG, "codes_to_utf8: bad B/T");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Utf8Params p{};
+  p.codes = reinterpret_cast<const long long*>(d_codes); p.B = B; p.K = K; p.T = T; p.offset = off; p.codebook_size = cbs;
+  p.bytes_per_frame = (int)bpf; p.out = d_out; p.out_stride = out_stride; p.frames = nullptr;
+  int o = 0;
+  for (int k = 0; k < K; ++k) { p.byte_off[k] = (unsigned char)o; o += utf8_len(off + (unsigned)k * cbs); }
+  int64_t maxfr = T;
+  if (h_frames) {
+    std::vector<int> v(B);
+    maxfr = 0;
+    for (int b = 0; b < B; ++b) {
+      if (h_frames[b] < 0 || h_frames[b] > T) return fail(h, MIMI_B200_ERR_ARG, "codes_to_utf8: frames out of range");
+      v[b] = (int)h_frames[b];
+      maxfr = std::max<int64_t>(maxfr, h_frames[b]);
+    }
+    int rc;
+    if ((rc = ensure_dev_ints(h, v.size()))) return rc;
+    if ((rc = stage_ints(h, v, h->dev_ints, st))) return rc;
+    p.frames = h->dev_ints;
+  }
+  if (maxfr * bpf > out_stride) return fail(h, MIMI_B200_ERR_ARG, "codes_to_utf8: out_stride too small");
+  if (h_out_len_opt)
+    for (int b = 0; b < B; ++b) h_out_len_opt[b] = (h_frames ? h_frames[b] : T) * bpf;
+  if (maxfr == 0) return MIMI_B200_OK;
+  if (!d_codes || !d_out) return fail(h, MIMI_B200_ERR_ARG, "codes_to_utf8: NULL device pointer");
+  dim3 grid((unsigned)((maxfr * K + 255) / 256), B);
+  codes_to_utf8_kernel<<<grid, 256, 0, st>>>(p);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  return MIMI_B200_OK;
+}
+
+}  // extern "C"

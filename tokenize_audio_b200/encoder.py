@@ -1,0 +1,331 @@
+"""Host-side mirror of the reference interface for the Mimi encode path.
+
+* :class:`MimiB200Model` keeps the call signature of ``transformers.MimiModel.encode``
+  (transformers/models/mimi/modeling_mimi.py:1522-1531): ``encode(input_values[B,1,N], padding_mask=None,
+  num_quantizers=None, ...) -> MimiEncoderOutput`` with ``audio_codes`` int64 ``[B,K,T]``, T = ceil(N/1920).
+* :class:`MimiEncoder` mirrors the wrapper class every ``*-mimi/process_*.py`` script copies
+  (REF/emilia-mimi/process_shard.py:50-140): ``encode_audio_chunk`` / ``encode_audio_batch``.
+* :class:`EncodecFeatureExtractorLite` mirrors what those scripts use of ``EncodecFeatureExtractor``
+  (transformers/models/encodec/feature_extraction_encodec.py:81-202): fp32 cast, zero right-padding to the
+  longest item, ``padding_mask``.
+
+PyTorch is only the plumbing here (device memory, streams); all arithmetic is in libmimi_b200.so, and
+nothing in this module falls back to the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+from typing import Dict, List, Optional, Sequence, Union
+
+import numpy as np
+import torch
+
+from . import _lib
+from .synth import SEANET_CONVS
+
+FRAME_SIZE = 1920
+NUM_QUANTIZERS = 32
+NUM_SEMANTIC_QUANTIZERS = 1
+
+
+class MimiEncoderOutput(tuple):
+    """Tuple-compatible stand-in for transformers' ``MimiEncoderOutput`` (modeling_mimi.py:60-75):
+    ``out.audio_codes``, ``out[0]``, ``out.encoder_past_key_values``, ``out.padding_cache``."""
+
+    def __new__(cls, audio_codes, encoder_past_key_values=None, padding_cache=None):
+        return super().__new__(cls, (audio_codes, encoder_past_key_values, padding_cache))
+
+    audio_codes = property(lambda self: self[0])
+    encoder_past_key_values = property(lambda self: self[1])
+    padding_cache = property(lambda self: self[2])
+
+
+def _as_f32(a) -> np.ndarray:
+    if isinstance(a, torch.Tensor):
+        a = a.detach().cpu().numpy()
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float32))
+
+
+def _rope_inv_freq() -> np.ndarray:
+    # MimiRotaryEmbedding.compute_default_rope_parameters (modeling_mimi.py:538-560), same torch ops
+    inv = 1.0 / (10000.0 ** (torch.arange(0, 64, 2, dtype=torch.int64).to(dtype=torch.float) / 64))
+    return np.ascontiguousarray(inv.numpy().astype(np.float32))
+
+
+class MimiB200Model:
+    """B200-native drop-in for the encode half of ``transformers.MimiModel``."""
+
+    def __init__(self, state_dict: Dict[str, Union[np.ndarray, torch.Tensor]], device: Union[str, int, torch.device] = "cuda"):
+        if not torch.cuda.is_available():
+            raise _lib.MimiB200Error("MimiB200Model needs a CUDA device (B200); there is no CPU fallback")
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise _lib.MimiB200Error(f"MimiB200Model only runs on CUDA devices, got {dev}")
+        self.device = torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
+        self._lib = _lib.load_library()
+        self._lock = threading.Lock()
+        self._workspace: Optional[torch.Tensor] = None
+        self.ragged_from_mask = False     # True: use padding_mask row sums as valid lengths (ragged mode)
+        h = C.c_void_p()
+        rc = self._lib.mimi_b200_create(C.byref(h), self.device.index)
+        _lib.check(self._lib, None, rc, "mimi_b200_create")
+        self._h = h
+        self._load(state_dict)
+
+    # -- construction helpers ---------------------------------------------------------------------
+    @classmethod
+    def from_transformers(cls, model, device="cuda") -> "MimiB200Model":
+        """Build from a loaded ``transformers.MimiModel`` (e.g. ``MimiModel.from_pretrained("kyutai/mimi")``)."""
+        return cls(model.state_dict(), device=device)
+
+    @classmethod
+    def from_pretrained(cls, path: str, device="cuda") -> "MimiB200Model":
+        """Load a local ``kyutai/mimi`` checkpoint: a ``.safetensors`` file, or a directory holding
+        ``model.safetensors`` (the layout ``MimiModel.from_pretrained`` reads, REF/emilia-mimi/process_shard.py:58)."""
+        import os
+        from safetensors.numpy import load_file
+        if os.path.isdir(path):
+            path = os.path.join(path, "model.safetensors")
+        return cls(load_file(path), device=device)
+
+    def _load(self, sd) -> None:
+        keep: List[np.ndarray] = []
+
+        def ptr(name: str, shape) -> C.c_void_p:
+            if name not in sd:
+                raise KeyError(f"state dict is missing '{name}'")
+            a = _as_f32(sd[name])
+            if tuple(a.shape) != tuple(shape):
+                raise ValueError(f"'{name}' has shape {tuple(a.shape)}, expected {tuple(shape)}")
+            keep.append(a)
+            return C.c_void_p(a.ctypes.data)
+
+        w = _lib.Weights()
+        for i, (name, cin, cout, k, _s) in enumerate(SEANET_CONVS):
+            w.conv_weight[i] = ptr(f"{name}.conv.weight", (cout, cin, k))
+            w.conv_bias[i] = ptr(f"{name}.conv.bias", (cout,))
+        for l in range(8):
+            p = f"encoder_transformer.layers.{l}"
+            lw = w.layer[l]
+            lw.input_layernorm_weight = ptr(f"{p}.input_layernorm.weight", (512,))
+            lw.input_layernorm_bias = ptr(f"{p}.input_layernorm.bias", (512,))
+            lw.q_proj_weight = ptr(f"{p}.self_attn.q_proj.weight", (512, 512))
+            lw.k_proj_weight = ptr(f"{p}.self_attn.k_proj.weight", (512, 512))
+            lw.v_proj_weight = ptr(f"{p}.self_attn.v_proj.weight", (512, 512))
+            lw.o_proj_weight = ptr(f"{p}.self_attn.o_proj.weight", (512, 512))
+            lw.self_attn_layer_scale = ptr(f"{p}.self_attn_layer_scale.scale", (512,))
+            lw.post_attention_layernorm_weight = ptr(f"{p}.post_attention_layernorm.weight", (512,))
+            lw.post_attention_layernorm_bias = ptr(f"{p}.post_attention_layernorm.bias", (512,))
+            lw.fc1_weight = ptr(f"{p}.mlp.fc1.weight", (2048, 512))
+            lw.fc2_weight = ptr(f"{p}.mlp.fc2.weight", (512, 2048))
+            lw.mlp_layer_scale = ptr(f"{p}.mlp_layer_scale.scale", (512,))
+        w.downsample_weight = ptr("downsample.conv.weight", (512, 512, 4))
+        w.semantic_input_proj_weight = ptr("quantizer.semantic_residual_vector_quantizer.input_proj.weight", (256, 512, 1))
+        w.acoustic_input_proj_weight = ptr("quantizer.acoustic_residual_vector_quantizer.input_proj.weight", (256, 512, 1))
+        for s in range(32):
+            which, idx = ("semantic", 0) if s == 0 else ("acoustic", s - 1)
+            q = f"quantizer.{which}_residual_vector_quantizer.layers.{idx}.codebook"
+            w.embed_sum[s] = ptr(f"{q}.embed_sum", (2048, 256))
+            w.cluster_usage[s] = ptr(f"{q}.cluster_usage", (2048,))
+        inv = _rope_inv_freq()
+        keep.append(inv)
+        w.rope_inv_freq = C.c_void_p(inv.ctypes.data)
+        with torch.cuda.device(self.device):
+            rc = self._lib.mimi_b200_load_weights(self._h, C.byref(w))
+        _lib.check(self._lib, self._h, rc, "mimi_b200_load_weights")
+        del keep
+
+    # -- nn.Module-flavoured no-ops so reference scripts keep working -----------------------------------
+    def to(self, device):
+        if torch.device(device).type != "cuda":
+            raise _lib.MimiB200Error("MimiB200Model cannot move to a non-CUDA device (no CPU fallback)")
+        return self
+
+    def eval(self):
+        return self
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.mimi_b200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- the hot path --------------------------------------------------------------------------------
+    def get_encoded_length(self, input_length):
+        """MimiModel.get_encoded_length (modeling_mimi.py:1490-1503)."""
+        if isinstance(input_length, torch.Tensor):
+            return torch.div(input_length + (FRAME_SIZE - 1), FRAME_SIZE, rounding_mode="floor")
+        return int(self._lib.mimi_b200_encoded_frames(int(input_length)))
+
+    def _ws(self, nbytes: int) -> torch.Tensor:
+        if self._workspace is None or self._workspace.numel() < nbytes:
+            self._workspace = None
+            self._workspace = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+        return self._workspace
+
+    def encode(self, input_values: torch.Tensor, padding_mask: Optional[torch.Tensor] = None,
+               num_quantizers: Optional[float] = None, encoder_past_key_values=None, padding_cache=None,
+               use_streaming: Optional[bool] = None, return_dict: Optional[bool] = None,
+               valid_lengths: Optional[Sequence[int]] = None, return_latent: bool = False):
+        """Same contract as ``MimiModel.encode``. Extras (keyword-only in spirit): ``valid_lengths`` switches
+        on ragged mode (skip work past each item's last kept frame), ``return_latent`` also returns the
+        pre-quantisation latent ``[B,512,T]`` for parity checks."""
+        if encoder_past_key_values is not None or padding_cache is not None or use_streaming:
+            raise NotImplementedError("streaming / cache arguments are not supported (the reference scripts never pass them)")
+        K = NUM_QUANTIZERS if num_quantizers is None else num_quantizers
+        if K > NUM_QUANTIZERS:   # modeling_mimi.py:1562-1565
+            raise ValueError(
+                f"The number of quantizers (i.e codebooks) asked should be lower than the total number of quantizers {NUM_QUANTIZERS}, but is currently {K}.")
+        if input_values.dim() != 3:
+            raise ValueError(f"input_values must be [batch, channels, length], got {tuple(input_values.shape)}")
+        B, channels, N = input_values.shape
+        if channels < 1 or channels > 2:   # modeling_mimi.py:1569-1570
+            raise ValueError(f"Number of audio channels must be 1 or 2, but got {channels}")
+        if channels != 1:
+            # MimiConfig.audio_channels == 1: the first conv takes one channel (torch would raise here too)
+            raise RuntimeError("expected input_values with 1 audio channel (kyutai/mimi is mono)")
+        if K < NUM_SEMANTIC_QUANTIZERS:    # modeling_mimi.py:1324-1327
+            raise ValueError(
+                f"The number of quantizers (i.e codebooks) asked should be higher than the number of semantic quantizers {NUM_SEMANTIC_QUANTIZERS}, but is currently {K}.")
+        K = int(K)
+        if not input_values.is_cuda:
+            raise _lib.MimiB200Error("input_values must live on the CUDA device (no CPU fallback)")
+        if input_values.device != self.device:
+            raise _lib.MimiB200Error(f"input_values is on {input_values.device}, model on {self.device}")
+        x = input_values.detach()
+        if x.dtype != torch.float32:
+            x = x.float()
+        x = x.contiguous()
+        T = -(-N // FRAME_SIZE)
+        if valid_lengths is None and self.ragged_from_mask and padding_mask is not None:
+            valid_lengths = padding_mask.reshape(B, -1, N)[:, 0].sum(-1).tolist()
+        vl = None
+        if valid_lengths is not None:
+            vl = (C.c_int64 * B)(*[int(v) for v in valid_lengths])
+        codes = torch.empty((B, K, T), dtype=torch.int64, device=self.device)
+        latent = torch.empty((B, 512, T), dtype=torch.float32, device=self.device) if return_latent else None
+        self._last_B = B
+        if B > 0 and N > 0:
+            with self._lock, torch.cuda.device(self.device):
+                nbytes = C.c_size_t()
+                rc = self._lib.mimi_b200_workspace_bytes(self._h, B, N, K, C.byref(nbytes))
+                _lib.check(self._lib, self._h, rc, "mimi_b200_workspace_bytes")
+                ws = self._ws(nbytes.value)
+                stream = torch.cuda.current_stream(self.device).cuda_stream
+                rc = self._lib.mimi_b200_encode(
+                    self._h, x.data_ptr(), B, N, vl, K, codes.data_ptr(),
+                    latent.data_ptr() if latent is not None else None, ws.data_ptr(), ws.numel(), stream)
+                _lib.check(self._lib, self._h, rc, "mimi_b200_encode")
+        out = MimiEncoderOutput(codes, None, None)
+        if return_latent:
+            return out, latent
+        if return_dict is False:
+            return tuple(out)
+        return out
+
+    # -- parity helpers --------------------------------------------------------------------------------
+    def debug_set(self, key: int, value: int) -> None:
+        _lib.check(self._lib, self._h, self._lib.mimi_b200_debug_set(self._h, key, value), "mimi_b200_debug_set")
+
+    def debug_tap(self, which: int) -> torch.Tensor:
+        """Channels-last ``[B, rows, C]`` copy of an internal activation of the last encode call."""
+        rows, ch = C.c_int64(), C.c_int()
+        rc = self._lib.mimi_b200_debug_tap(self._h, which, None, 0, C.byref(rows), C.byref(ch), None)
+        _lib.check(self._lib, self._h, rc, "mimi_b200_debug_tap")
+        B = self._last_B
+        out = torch.empty((B, rows.value, ch.value), dtype=torch.float32, device=self.device)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        rc = self._lib.mimi_b200_debug_tap(self._h, which, out.data_ptr(), out.numel(), None, None, stream)
+        _lib.check(self._lib, self._h, rc, "mimi_b200_debug_tap")
+        return out
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.mimi_b200_launch_count(self._h))
+
+
+class EncodecFeatureExtractorLite:
+    """The part of ``EncodecFeatureExtractor.__call__`` the reference scripts use: fp32 cast, zero
+    right-padding to the longest item, int32 ``padding_mask``; ``ValueError`` on a wrong sampling rate
+    (feature_extraction_encodec.py:122-128)."""
+
+    sampling_rate = 24000
+    padding_value = 0.0
+
+    def __call__(self, raw_audio, sampling_rate: Optional[int] = None, return_tensors: Optional[str] = "pt",
+                 padding=None):
+        if sampling_rate is not None and sampling_rate != self.sampling_rate:
+            raise ValueError(
+                f"The model corresponding to this feature extractor: {self} was trained using a sampling rate of"
+                f" {self.sampling_rate}. Please make sure that the provided audio input was sampled with"
+                f" {self.sampling_rate} and not {sampling_rate}.")
+        batched = isinstance(raw_audio, (list, tuple)) and len(raw_audio) > 0 and isinstance(raw_audio[0], (np.ndarray, list, tuple))
+        items = [np.asarray(a, dtype=np.float32) for a in (raw_audio if batched else [raw_audio])]
+        for a in items:
+            if a.ndim != 1:
+                raise ValueError(f"Expected mono audio but example has {a.shape[-1]} channels")
+        n = max(len(a) for a in items)
+        iv = np.zeros((len(items), 1, n), np.float32)
+        pm = np.zeros((len(items), n), np.int32)
+        for i, a in enumerate(items):
+            iv[i, 0, : len(a)] = a
+            pm[i, : len(a)] = 1
+        if return_tensors == "pt":
+            return {"input_values": torch.from_numpy(iv), "padding_mask": torch.from_numpy(pm)}
+        return {"input_values": iv, "padding_mask": pm}
+
+
+class MimiEncoder:
+    """Same methods as the reference's ``MimiEncoder`` wrapper (REF/emilia-mimi/process_shard.py:50-140).
+
+    ``model`` may be a :class:`MimiB200Model`, a state dict, a checkpoint path, or a loaded
+    ``transformers.MimiModel`` whose weights are taken over."""
+
+    def __init__(self, model, device: str = "cuda", ragged: bool = True):
+        self.device = device
+        self.feature_extractor = EncodecFeatureExtractorLite()
+        if isinstance(model, MimiB200Model):
+            self.model = model
+        elif isinstance(model, str):
+            self.model = MimiB200Model.from_pretrained(model, device=device)
+        elif isinstance(model, dict):
+            self.model = MimiB200Model(model, device=device)
+        else:
+            self.model = MimiB200Model.from_transformers(model, device=device)
+        self.ragged = ragged
+        self._pinned: Optional[torch.Tensor] = None
+
+    def _to_device(self, t: torch.Tensor) -> torch.Tensor:
+        return t.to(self.model.device, non_blocking=True)
+
+    def encode_audio_chunk(self, audio_array: np.ndarray, sample_rate: int = 24000) -> np.ndarray:
+        """REF/emilia-mimi/process_shard.py:63-86: one utterance -> codes ``[32, T]`` (numpy int64)."""
+        with torch.no_grad():
+            inputs = self.feature_extractor(raw_audio=audio_array, sampling_rate=sample_rate, return_tensors="pt")
+            inputs = {k: self._to_device(v) for k, v in inputs.items()}
+            out = self.model.encode(inputs["input_values"], inputs["padding_mask"])
+            return out.audio_codes.cpu().numpy()[0]
+
+    def encode_audio_batch(self, audio_arrays: List[np.ndarray], sample_rate: int = 24000) -> List[np.ndarray]:
+        """REF/emilia-mimi/process_shard.py:88-140: pad to the longest, encode, trim item i to
+        ceil(len_i / 1920) frames. With ``ragged=True`` (default) the padded tails are not computed; the kept
+        frames are the same either way. One device->host copy per batch instead of one per item."""
+        if len(audio_arrays) == 0:
+            return []
+        if len(audio_arrays) == 1:
+            return [self.encode_audio_chunk(audio_arrays[0], sample_rate)]
+        with torch.no_grad():
+            original_lengths = [len(a) for a in audio_arrays]
+            inputs = self.feature_extractor(raw_audio=audio_arrays, sampling_rate=sample_rate, return_tensors="pt", padding=True)
+            inputs = {k: self._to_device(v) for k, v in inputs.items()}
+            out = self.model.encode(input_values=inputs["input_values"], padding_mask=inputs["padding_mask"],
+                                    valid_lengths=original_lengths if self.ragged else None)
+            codes = out.audio_codes.cpu().numpy()
+            frame_rate = sample_rate / 12.5
+            return [codes[i, :, : int(np.ceil(n / frame_rate))] for i, n in enumerate(original_lengths)]
