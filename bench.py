@@ -1,0 +1,335 @@
+#!/usr/bin/env python3
+"""Benchmark of the Mimi encode hot path (BASELINE.json metric: audio-seconds encoded per second).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
+
+Workload (config.workload = "c2"): BASELINE.json configs[1] -- Mimi encode, 8 codebooks, batch 64 of 2-20 s
+utterances, length-bucketed (2 s buckets), padded to the longest item of the batch. A pool of 512 synthetic
+speech-shaped utterances (durations U(2,20) s, fixed seed) is bucketed into 8 batches of 64; step i encodes
+batch i % 8. One "step" = one batch. Every rank works on its own shard (same length multiset, different
+audio), no collective on the data path (weak scaling); counters meet in one all_reduce at the end.
+
+Printed JSON (rank 0, one line):
+  value   audio-seconds per second with the padded batches already resident in HBM (device timed)
+  e2e     the same through the reference-facing wrapper MimiEncoder.encode_audio_batch with HOST numpy
+          inputs: pinned staging + H2D + encode + D2H of the codes inside the timed region
+  roofline      dominant kernel, timed live with CUDA events inside the timed region
+  cpu_baseline  transformers.MimiModel (the reference's own implementation) on this box's host cores on a
+                bounded sample of the same workload (rank 0, N=1 only)
+
+--impl reference times that CPU implementation as its own arm (bounded sample per step).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from tokenize_audio_b200 import sharding, synth  # noqa: E402
+
+SR = 24000
+K_CODEBOOKS = 8
+BATCH = 64
+POOL = 512
+N_BATCHES = POOL // BATCH
+SEED = 1234 + 2000            # seed = 1234 + config_id*1000 (+ item index)
+REF_ITEMS_PER_STEP = 8        # bounded CPU sample per step for the reference arm
+CPU_BASELINE_ITEMS = 24       # bounded CPU sample for the cpu_baseline leg
+
+# algorithmic MACs per audio-second of each launch kind (K = 8 codebooks)
+MMAC_PER_AUDIO_S = {
+    "conv0": 10.752, "seanet_conv1": 147.456, "seanet_conv2": 49.152, "seanet_conv3": 393.216,
+    "seanet_conv4": 147.456, "seanet_conv5": 49.152, "seanet_conv6": 393.216, "seanet_conv7": 117.965,
+    "seanet_conv8": 39.322, "seanet_conv9": 314.573, "seanet_conv10": 78.643, "seanet_conv11": 26.214,
+    "seanet_conv12": 209.715, "seanet_conv13": 39.322, "qkv_gemm": 157.286, "o_proj": 52.429,
+    "fc1_gelu": 209.715, "fc2": 209.715, "attention": 51.2, "downsample_conv": 13.107,
+    "rvq_input_proj": 3.277, "rvq_fused": 6.5536 * K_CODEBOOKS,
+}
+# algorithmic HBM bytes per audio-second for the bandwidth-bound kinds (fp32, channels-last)
+HBM_BYTES_PER_AUDIO_S = {
+    "conv0": 24000 * 4 + 24000 * 64 * 4,
+    "layernorm": 25 * 512 * 4 * 2 * 16,
+}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": float(d["hbm_gbs"]), "tflops": float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "src": "measured"}
+    return {"hbm_gbs": 6650.0, "tflops": 1400.0, "src": "fallback"}
+
+
+def make_workload(rank: int):
+    """512 utterance lengths U(2,20) s -> 8 length-bucketed batches of 64 (lists of numpy clips)."""
+    rng = np.random.Generator(np.random.PCG64(SEED))
+    lengths = [int(v) for v in rng.uniform(2.0, 20.0, size=POOL) * SR]
+    batches = sharding.bucket_batches(lengths, BATCH)
+    # 12 base clips of 20 s per rank; utterance i = a crop of base clip i % 12 (content does not affect timing)
+    base = [synth.synth_speech(SEED + 100 * rank + j, 20 * SR) for j in range(12)]
+    clips = []
+    for b in batches:
+        clips.append([base[i % 12][: lengths[i]] if (i // 12) % 2 == 0 else base[i % 12][20 * SR - lengths[i]:] for i in b])
+    return clips, lengths, batches
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def reference_encoder(sd):
+    """The reference path unchanged: transformers.MimiModel fp32 on the host CPU, driven the way
+    MimiEncoder.encode_audio_batch does (REF/emilia-mimi/process_shard.py:88-140)."""
+    from transformers import EncodecFeatureExtractor, MimiConfig, MimiModel
+    torch.set_num_threads(os.cpu_count() or 1)
+    model = MimiModel(MimiConfig()).eval()
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=False)
+    fe = EncodecFeatureExtractor()
+
+    def encode_batch(clips):
+        with torch.no_grad():
+            inputs = fe(raw_audio=clips, sampling_rate=SR, return_tensors="pt", padding=True)
+            codes = model.encode(input_values=inputs["input_values"], padding_mask=inputs["padding_mask"],
+                                 num_quantizers=K_CODEBOOKS).audio_codes
+            return [codes[i, :, : int(np.ceil(len(c) / 1920.0))].numpy() for i, c in enumerate(clips)]
+    return encode_batch
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    sd = synth.synth_state_dict(0)
+    clips, lengths, batches = make_workload(0)
+    try:
+        enc = reference_encoder(sd)
+    except Exception as e:  # transformers missing on this box
+        print(json.dumps({"impl": "reference", "unavailable": f"transformers MimiModel not importable: {e}"}))
+        return
+    cores = os.cpu_count() or 1
+
+    def step(i):
+        sample = clips[i % N_BATCHES][:REF_ITEMS_PER_STEP]
+        enc(sample)
+        return sum(len(c) for c in sample) / SR
+    for i in range(args.warmup):
+        step(i)
+    t0 = time.perf_counter()
+    audio = sum(step(i) for i in range(args.steps))
+    dt = time.perf_counter() - t0
+    val = audio / dt
+    print(json.dumps({
+        "impl": "reference", "metric": "audio_seconds_encoded_per_sec", "value": val, "unit": "x_realtime",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "c2", "codebooks": K_CODEBOOKS, "batch": BATCH, "durations_s": "U(2,20) length-bucketed",
+                   "weights": "synthetic seed 0 (kyutai/mimi architecture)"},
+        "cpu_baseline": {"value": val, "unit": "x_realtime", "cores": cores, "kind": "reference",
+                         "sample": f"first {REF_ITEMS_PER_STEP} items of each step's 64-item batch, transformers.MimiModel fp32 CPU, {cores} torch threads"},
+        "e2e": {"value": val, "unit": "x_realtime", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def run_b200(args, rank, world, local_rank):
+    from tokenize_audio_b200.encoder import MimiB200Model, MimiEncoder
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    sd = synth.synth_state_dict(0)
+    model = MimiB200Model(sd, device=dev)
+    wrapper = MimiEncoder(model, device=str(dev), ragged=True, num_quantizers=K_CODEBOOKS)
+    clips, lengths, batches = make_workload(rank)
+    peaks = load_peaks()
+
+    # resident inputs: padded [64,1,N] batches already in HBM
+    dev_batches = []
+    for b, cl in zip(batches, clips):
+        n = max(len(c) for c in cl)
+        x = torch.zeros((len(cl), 1, n), dtype=torch.float32)
+        for i, c in enumerate(cl):
+            x[i, 0, : len(c)] = torch.from_numpy(c)
+        dev_batches.append((x.to(dev), [len(c) for c in cl]))
+    audio_s = [sum(l) / SR for _, l in dev_batches]
+    computed_s = [sum(min(x.shape[2], -(-n // 1920) * 1920) for n in l) / SR for x, l in dev_batches]
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize(dev)
+
+    def resident_step(i):
+        x, l = dev_batches[i % N_BATCHES]
+        return model.encode(x, num_quantizers=K_CODEBOOKS, valid_lengths=l).audio_codes
+
+    def e2e_step(i):
+        return wrapper.encode_audio_batch(clips[i % N_BATCHES])
+
+    # ---- device-timed, inputs resident ---------------------------------------------------------------
+    for i in range(args.warmup):
+        resident_step(i)
+    barrier()
+    model.profile(True)
+    launches0 = model.launch_count
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        resident_step(i)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    prof = model.profile_read()
+    model.profile(False)
+    launches = model.launch_count - launches0
+    total_audio = sum(audio_s[i % N_BATCHES] for i in range(args.steps))
+    total_computed = sum(computed_s[i % N_BATCHES] for i in range(args.steps))
+
+    # ---- end to end through the wrapper with host buffers ---------------------------------------------
+    for i in range(min(args.warmup, 3)):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        e2e_step(i)
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop() if sampler else None
+    h2d = float(np.mean([dev_batches[i % N_BATCHES][0].numel() * 4 for i in range(args.steps)]))
+    d2h = float(np.mean([BATCH * K_CODEBOOKS * (-(-dev_batches[i % N_BATCHES][0].shape[2] // 1920)) * 8 for i in range(args.steps)]))
+
+    red = sharding.reduce_counters({"audio": total_audio, "ms_max": ms, "e2e_s_max": e2e_s, "launches": launches}, device=dev)
+    if rank != 0:
+        return
+    value = red["audio"] / (red["ms_max"] / 1e3)
+    e2e_value = red["audio"] / red["e2e_s_max"]
+
+    # ---- roofline of the dominant kernel (live CUDA-event durations from the timed region) --------------
+    kind, (kms, kcnt) = max(prof.items(), key=lambda kv: kv[1][0])
+    per_launch_s = kms / 1e3 / kcnt
+    launches_per_step = kcnt / args.steps
+    audio_per_launch = total_computed / args.steps / launches_per_step
+    if kind in MMAC_PER_AUDIO_S and kind != "conv0":
+        achieved = 2 * MMAC_PER_AUDIO_S[kind] * 1e6 * audio_per_launch / per_launch_s / 1e12
+        roof = {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
+                "frac": achieved / peaks["tflops"]}
+    else:
+        achieved = HBM_BYTES_PER_AUDIO_S.get(kind, 0.0) * audio_per_launch / per_launch_s / 1e9
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"]}
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(kind)
+    roof.update({"traffic": traffic, "kernel": kind, "share_of_step": kms / sum(v[0] for v in prof.values()),
+                 "avg_launch_ms": 1e3 * per_launch_s, "peak_source": peaks["src"],
+                 "precision": "fp32 FFMA (exact-fp32 path); peak is the dense bf16 tensor figure"})
+    breakdown = {k: round(v[0] / args.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
+
+    # ---- CPU baseline beside it (rank 0, N=1 only): the reference implementation on host cores -----------
+    cpu = None
+    agreement = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            enc = reference_encoder(sd)
+            mid = N_BATCHES // 2
+            sample = clips[mid][:CPU_BASELINE_ITEMS]
+            t0 = time.perf_counter()
+            ref_codes = []
+            for j in range(0, len(sample), 8):
+                ref_codes += enc(sample[j:j + 8])
+            dt = time.perf_counter() - t0
+            cores = os.cpu_count() or 1
+            cpu = {"value": sum(len(c) for c in sample) / SR / dt, "unit": "x_realtime", "cores": cores, "kind": "reference",
+                   "sample": f"{len(sample)} items of batch {mid} ({sum(len(c) for c in sample) / SR:.0f} audio-s) in sub-batches of 8, transformers.MimiModel fp32 CPU, {cores} torch threads, {dt:.1f} s"}
+            got = []
+            for j in range(0, len(sample), 8):
+                got += wrapper.encode_audio_batch(sample[j:j + 8])
+            same = sum(int((a == b).sum()) for a, b in zip(got, ref_codes))
+            tot = sum(a.size for a in ref_codes)
+            agreement = {"codes_equal_frac": same / tot, "slots": tot, "vs": "transformers.MimiModel CPU fp32, same items, same sub-batches"}
+        except Exception as e:
+            cpu = {"value": None, "unit": "x_realtime", "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {e}"}
+
+    print(json.dumps({
+        "metric": "audio_seconds_encoded_per_sec", "value": value, "unit": "x_realtime", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": red["ms_max"] / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "c2", "codebooks": K_CODEBOOKS, "batch": BATCH, "durations_s": "U(2,20) length-bucketed, 8 batches cycled",
+                   "mode": "ragged (padded tails skipped, kept frames identical)", "l2": "inputs+activations per step >> 126 MB L2",
+                   "weights": "synthetic seed 0 (kyutai/mimi architecture)", "audio_s_per_step": total_audio / args.steps},
+        "audio_hours_per_sec": value / 3600.0,
+        "e2e": {"value": e2e_value, "unit": "x_realtime", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "api": "MimiEncoder.encode_audio_batch(list[np.ndarray]) -> list[np.ndarray]"},
+        "gpu_launches": int(red["launches"]), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+        "agreement": agreement, "ms_per_step_by_kernel": breakdown,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=16)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_b200(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -128,8 +128,15 @@ int mimi_b200_debug_tap(mimi_b200_t* h, int which, float* d_out, size_t out_capa
 
 /* Debug knobs (parity bisection only): key 0 = number of transformer layers to run (default 8),
    key 1 = index of the last SEANet conv to run (default 13; smaller values stop the pipeline there and
-   leave d_codes untouched). */
+   leave d_codes untouched), key 2 = per-launch CUDA-event profiling on/off (resets the profile). */
 int mimi_b200_debug_set(mimi_b200_t* h, int key, int value);
+
+/* Read and reset the per-launch profile gathered since profiling was switched on: for launch kind
+   id < max_ids, sum_ms[id] = total device time between the previous launch's end and this launch's end on
+   the encode stream, count[id] = launches. Kinds: 0 conv0; 1..13 SEANet conv i (gather-GEMM); 14
+   LayerNorm; 15 QKV; 16 attention; 17 o_proj; 18 fc1; 19 fc2; 20 downsample conv; 21 RVQ input_proj;
+   22 fused RVQ; 23 latent transpose; 24 code fill. Synchronises with the last recorded launch. */
+int mimi_b200_profile_read(mimi_b200_t* h, int max_ids, double* sum_ms, int64_t* count);
 
 /* Output length of the resampler for n input samples: ceil(n * sr_out / sr_in) (librosa fix=True). */
 int64_t mimi_b200_resample_out_len(int64_t n_in, int sr_in, int sr_out);

@@ -82,6 +82,11 @@ struct mimi_b200 {
   // debug knobs and last plan
   int dbg_layers = MIMI_B200_NUM_LAYERS;
   int dbg_last_conv = MIMI_B200_NUM_CONVS - 1;
+  // optional per-launch CUDA-event profile (debug_set key 2): events[i] closes launch prof_ids[i]
+  bool prof_on = false;
+  std::vector<cudaEvent_t> prof_pool;
+  std::vector<int> prof_ids;           // -1 = "begin" marker
+  size_t prof_n = 0;
   Plan last;
   void* last_ws = nullptr;
 };
@@ -100,6 +105,20 @@ static std::string g_create_err;
 static int fail(mimi_b200* h, int code, const std::string& msg) {
   if (h) h->err = msg; else g_create_err = msg;
   return code;
+}
+
+// record "launch `id` just ended" on the stream (profiling only)
+static void mark(mimi_b200* h, int id, cudaStream_t st) {
+  if (!h->prof_on) return;
+  if (h->prof_n == h->prof_pool.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    h->prof_pool.push_back(e);
+    h->prof_ids.push_back(0);
+  }
+  h->prof_ids[h->prof_n] = id;
+  cudaEventRecord(h->prof_pool[h->prof_n], st);
+  h->prof_n++;
 }
 
 static int dev_upload(mimi_b200* h, float** dst, const std::vector<float>& src) {
@@ -195,7 +214,7 @@ static void launch_gemm_t(const GemmParams& p, int B, int lout_max, cudaStream_t
   gemm_f32_kernel<BM, BN, TN><<<grid, 256, 0, st>>>(p);
 }
 
-static int launch_gemm(mimi_b200* h, const GemmParams& p, int B, int max_len_in, cudaStream_t st) {
+static int launch_gemm(mimi_b200* h, const GemmParams& p, int B, int max_len_in, cudaStream_t st, int prof_id) {
   const int lout_max = (max_len_in + p.stride - 1) / p.stride;
   if (lout_max <= 0 || B <= 0) return MIMI_B200_OK;
   if (p.K % 16 || p.Cin % 16 || p.N % 32) return fail(h, MIMI_B200_ERR_ARG, "gemm: unsupported shape");
@@ -203,6 +222,7 @@ static int launch_gemm(mimi_b200* h, const GemmParams& p, int B, int max_len_in,
   else if (p.N % 64 == 0) launch_gemm_t<128, 64, 4>(p, B, lout_max, st);
   else launch_gemm_t<256, 32, 4>(p, B, lout_max, st);
   h->launches++;
+  mark(h, prof_id, st);
   CUDA_TRY(h, cudaGetLastError());
   return MIMI_B200_OK;
 }
@@ -294,6 +314,7 @@ void mimi_b200_destroy(mimi_b200_t* h) {
     if (h->stage_ev[i]) cudaEventDestroy(h->stage_ev[i]);
   }
   if (h->dev_ints) cudaFree(h->dev_ints);
+  for (cudaEvent_t e : h->prof_pool) cudaEventDestroy(e);
   for (auto& kv : h->taps) cudaFree(kv.second.d);
   delete h;
 }
@@ -302,7 +323,25 @@ int mimi_b200_debug_set(mimi_b200_t* h, int key, int value) {
   if (!h) return MIMI_B200_ERR_ARG;
   if (key == 0) h->dbg_layers = std::min(std::max(value, 0), MIMI_B200_NUM_LAYERS);
   else if (key == 1) h->dbg_last_conv = std::min(std::max(value, 0), MIMI_B200_NUM_CONVS - 1);
+  else if (key == 2) { h->prof_on = value != 0; h->prof_n = 0; }
   else return fail(h, MIMI_B200_ERR_ARG, "debug_set: unknown key");
+  return MIMI_B200_OK;
+}
+
+int mimi_b200_profile_read(mimi_b200_t* h, int max_ids, double* sum_ms, int64_t* count) {
+  if (!h || !sum_ms || !count || max_ids <= 0) return fail(h, MIMI_B200_ERR_ARG, "profile_read: bad argument");
+  for (int i = 0; i < max_ids; ++i) { sum_ms[i] = 0.0; count[i] = 0; }
+  if (h->prof_n == 0) return MIMI_B200_OK;
+  CUDA_TRY(h, cudaEventSynchronize(h->prof_pool[h->prof_n - 1]));
+  for (size_t i = 1; i < h->prof_n; ++i) {
+    const int id = h->prof_ids[i];
+    if (id < 0 || id >= max_ids) continue;            // -1 = begin marker of an encode call
+    float ms = 0.f;
+    CUDA_TRY(h, cudaEventElapsedTime(&ms, h->prof_pool[i - 1], h->prof_pool[i]));
+    sum_ms[id] += ms;
+    count[id] += 1;
+  }
+  h->prof_n = 0;
   return MIMI_B200_OK;
 }
 
@@ -434,6 +473,7 @@ int mimi_b200_encode(mimi_b200_t* h, const float* d_input, int B, int64_t N, con
   int* dints = reinterpret_cast<int*>(base + p.ints);
   h->last = p;
   h->last_ws = ws;
+  mark(h, -1, st);
 
   // per-level lengths. strict: uniform (no arrays). ragged: item i is encoded over
   // min(N, ceil(len_i/1920)*1920) samples (identical kept frames, see mimi_b200.h).
@@ -466,7 +506,7 @@ int mimi_b200_encode(mimi_b200_t* h, const float* d_input, int B, int64_t N, con
     dprefix = dints + (size_t)6 * B;
     const long long ncodes = (long long)B * K * p.rows[5];
     fill_codes_zero_kernel<<<(unsigned)((ncodes + 255) / 256), 256, 0, st>>>(reinterpret_cast<long long*>(d_codes), ncodes);
-    h->launches++;
+    h->launches++; mark(h, 24, st);
   }
 
   auto istride = [&](int level, int C) { return (long long)p.rows[level] * C; };
@@ -477,7 +517,7 @@ int mimi_b200_encode(mimi_b200_t* h, const float* d_input, int B, int64_t N, con
     dim3 grid((maxlen[0] + 127) / 128, B);
     if (maxlen[0] > 0) {
       conv0_kernel<<<grid, 256, 0, st>>>(d_input, N, h->conv_wt[0], h->conv_b[0], ws + p.a0, istride(0, 64), dlen[0], maxlen[0]);
-      h->launches++;
+      h->launches++; mark(h, 0, st);
       CUDA_TRY(h, cudaGetLastError());
     }
   }
@@ -494,7 +534,7 @@ int mimi_b200_encode(mimi_b200_t* h, const float* d_input, int B, int64_t N, con
     g.len_in = dlen[sg.level]; g.uniform_len_in = maxlen[sg.level];
     g.a_item_stride = istride(sg.level, sg.C); g.out_item_stride = istride(sg.level, sg.C / 2);
     g.Cin = sg.C; g.stride = 1; g.pad_left = 2; g.K = 3 * sg.C; g.N = sg.C / 2; g.elu_in = 1;
-    if ((rc = launch_gemm(h, g, B, maxlen[sg.level], st))) return rc;
+    if ((rc = launch_gemm(h, g, B, maxlen[sg.level], st, ia))) return rc;
     if (h->dbg_last_conv <= ia) { stop = true; break; }
     // resblock conv b: ELU -> C/2 -> C, k1, + skip (in place on h)
     g = GemmParams{};
@@ -502,7 +542,7 @@ int mimi_b200_encode(mimi_b200_t* h, const float* d_input, int B, int64_t N, con
     g.len_in = dlen[sg.level]; g.uniform_len_in = maxlen[sg.level];
     g.a_item_stride = istride(sg.level, sg.C / 2); g.out_item_stride = istride(sg.level, sg.C);
     g.Cin = sg.C / 2; g.stride = 1; g.pad_left = 0; g.K = sg.C / 2; g.N = sg.C; g.elu_in = 1;
-    if ((rc = launch_gemm(h, g, B, maxlen[sg.level], st))) return rc;
+    if ((rc = launch_gemm(h, g, B, maxlen[sg.level], st, ib))) return rc;
     if (h->dbg_last_conv <= ib) { stop = true; break; }
     // strided down conv: ELU -> C -> 2C, k = 2*ratio, stride = ratio
     const ConvGeom& cg = kConv[id];
@@ -511,7 +551,7 @@ int mimi_b200_encode(mimi_b200_t* h, const float* d_input, int B, int64_t N, con
     g.len_in = dlen[sg.level]; g.uniform_len_in = maxlen[sg.level];
     g.a_item_stride = istride(sg.level, sg.C); g.out_item_stride = istride(sg.level + 1, 2 * sg.C);
     g.Cin = sg.C; g.stride = cg.stride; g.pad_left = cg.k - cg.stride; g.K = cg.k * sg.C; g.N = 2 * sg.C; g.elu_in = 1;
-    if ((rc = launch_gemm(h, g, B, maxlen[sg.level], st))) return rc;
+    if ((rc = launch_gemm(h, g, B, maxlen[sg.level], st, id))) return rc;
     if (h->dbg_last_conv <= id) { stop = true; break; }
   }
   if (stop) return MIMI_B200_OK;
@@ -521,7 +561,7 @@ int mimi_b200_encode(mimi_b200_t* h, const float* d_input, int B, int64_t N, con
     g.len_in = dlen[4]; g.uniform_len_in = maxlen[4];
     g.a_item_stride = istride(4, 1024); g.out_item_stride = istride(4, 512);
     g.Cin = 1024; g.stride = 1; g.pad_left = 2; g.K = 3072; g.N = 512; g.elu_in = 1;
-    if ((rc = launch_gemm(h, g, B, maxlen[4], st))) return rc;
+    if ((rc = launch_gemm(h, g, B, maxlen[4], st, 13))) return rc;
   }
 
   // ---- encoder transformer (MimiTransformerModel.forward, modeling_mimi.py:1015-1140) ---------------
@@ -530,34 +570,34 @@ int mimi_b200_encode(mimi_b200_t* h, const float* d_input, int B, int64_t N, con
     const LayerDev& d = h->layer[l];
     dim3 lgrid((T25 + 7) / 8, B);
     layernorm512_kernel<<<lgrid, 256, 0, st>>>(ws + p.z, ws + p.y, d.ln1_w, d.ln1_b, istride(4, 512), dlen[4], T25);
-    h->launches++;
+    h->launches++; mark(h, 14, st);
     GemmParams g{};
     g.A = ws + p.y; g.Wt = d.qkv_wt; g.out = ws + p.qkv; g.len_in = dlen[4]; g.uniform_len_in = T25;
     g.a_item_stride = istride(4, 512); g.out_item_stride = istride(4, 1536);
     g.Cin = 512; g.stride = 1; g.K = 512; g.N = 1536;
-    if ((rc = launch_gemm(h, g, B, T25, st))) return rc;
+    if ((rc = launch_gemm(h, g, B, T25, st, 15))) return rc;
     dim3 agrid((T25 + kAttQT - 1) / kAttQT, kHeads, B);
     swa_attention_kernel<<<agrid, 256, kAttSmemBytes, st>>>(ws + p.qkv, istride(4, 1536), ws + p.att, istride(4, 512),
                                                             h->rope_cos, h->rope_sin, dlen[4], T25);
-    h->launches++;
+    h->launches++; mark(h, 16, st);
     CUDA_TRY(h, cudaGetLastError());
     g = GemmParams{};   // o_proj + LayerScale + residual (in place on z)
     g.A = ws + p.att; g.Wt = d.o_wt; g.scale = d.ls1; g.res = ws + p.z; g.out = ws + p.z;
     g.len_in = dlen[4]; g.uniform_len_in = T25; g.a_item_stride = istride(4, 512); g.out_item_stride = istride(4, 512);
     g.Cin = 512; g.stride = 1; g.K = 512; g.N = 512;
-    if ((rc = launch_gemm(h, g, B, T25, st))) return rc;
+    if ((rc = launch_gemm(h, g, B, T25, st, 17))) return rc;
     layernorm512_kernel<<<lgrid, 256, 0, st>>>(ws + p.z, ws + p.y, d.ln2_w, d.ln2_b, istride(4, 512), dlen[4], T25);
-    h->launches++;
+    h->launches++; mark(h, 14, st);
     g = GemmParams{};   // fc1 + GELU(erf)
     g.A = ws + p.y; g.Wt = d.fc1_wt; g.out = ws + p.ffn; g.len_in = dlen[4]; g.uniform_len_in = T25;
     g.a_item_stride = istride(4, 512); g.out_item_stride = istride(4, 2048);
     g.Cin = 512; g.stride = 1; g.K = 512; g.N = 2048; g.act = 1;
-    if ((rc = launch_gemm(h, g, B, T25, st))) return rc;
+    if ((rc = launch_gemm(h, g, B, T25, st, 18))) return rc;
     g = GemmParams{};   // fc2 + LayerScale + residual (in place on z)
     g.A = ws + p.ffn; g.Wt = d.fc2_wt; g.scale = d.ls2; g.res = ws + p.z; g.out = ws + p.z;
     g.len_in = dlen[4]; g.uniform_len_in = T25; g.a_item_stride = istride(4, 2048); g.out_item_stride = istride(4, 512);
     g.Cin = 2048; g.stride = 1; g.K = 2048; g.N = 512;
-    if ((rc = launch_gemm(h, g, B, T25, st))) return rc;
+    if ((rc = launch_gemm(h, g, B, T25, st, 19))) return rc;
   }
 
   // ---- stride-2 downsample conv, replicate padding (modeling_mimi.py:1422-1431,1484) ----------------
@@ -566,14 +606,14 @@ int mimi_b200_encode(mimi_b200_t* h, const float* d_input, int B, int64_t N, con
     g.A = ws + p.z; g.Wt = h->down_wt; g.out = ws + p.e; g.len_in = dlen[4]; g.uniform_len_in = T25;
     g.a_item_stride = istride(4, 512); g.out_item_stride = istride(5, 512);
     g.Cin = 512; g.stride = 2; g.pad_left = 2; g.K = 2048; g.N = 512; g.replicate = 1;
-    if ((rc = launch_gemm(h, g, B, T25, st))) return rc;
+    if ((rc = launch_gemm(h, g, B, T25, st, 20))) return rc;
   }
   const int T = maxlen[5];
   if (d_latent_opt) {
     const long long n = (long long)kHidden * p.rows[5];
     dim3 tgrid((unsigned)((n + 255) / 256), B);
     latent_transpose_kernel<<<tgrid, 256, 0, st>>>(ws + p.e, istride(5, 512), d_latent_opt, p.rows[5], dlen[5], T);
-    h->launches++;
+    h->launches++; mark(h, 23, st);
   }
   // ---- split RVQ (modeling_mimi.py:1311-1338): both input_proj as one GEMM, then the fused chain -----
   {
@@ -581,7 +621,7 @@ int mimi_b200_encode(mimi_b200_t* h, const float* d_input, int B, int64_t N, con
     g.A = ws + p.e; g.Wt = h->proj_wt; g.out = ws + p.rp; g.len_in = dlen[5]; g.uniform_len_in = T;
     g.a_item_stride = istride(5, 512); g.out_item_stride = istride(5, 512);
     g.Cin = 512; g.stride = 1; g.K = 512; g.N = 512;
-    if ((rc = launch_gemm(h, g, B, T, st))) return rc;
+    if ((rc = launch_gemm(h, g, B, T, st, 21))) return rc;
     RvqParams r{};
     r.rproj = ws + p.rp; r.item_stride = istride(5, 512);
     r.embed = h->embed; r.embed_t = h->embed_t; r.enorm = h->enorm;
@@ -589,7 +629,7 @@ int mimi_b200_encode(mimi_b200_t* h, const float* d_input, int B, int64_t N, con
     r.len = dlen[5]; r.uniform_len = T; r.B = B; r.total_frames = total_frames; r.frame_prefix = dprefix;
     if (total_frames > 0) {
       rvq_encode_kernel<<<(total_frames + kRvqFM - 1) / kRvqFM, 256, kRvqSmemBytes, st>>>(r);
-      h->launches++;
+      h->launches++; mark(h, 22, st);
     }
   }
   CUDA_TRY(h, cudaGetLastError());

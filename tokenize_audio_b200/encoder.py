@@ -245,6 +245,21 @@ class MimiB200Model:
         _lib.check(self._lib, self._h, rc, "mimi_b200_debug_tap")
         return out
 
+    LAUNCH_KINDS = (["conv0"] + [f"seanet_conv{i}" for i in range(1, 14)] +
+                    ["layernorm", "qkv_gemm", "attention", "o_proj", "fc1_gelu", "fc2", "downsample_conv",
+                     "rvq_input_proj", "rvq_fused", "latent_transpose", "code_fill"])
+
+    def profile(self, on: bool) -> None:
+        """Switch per-launch CUDA-event profiling on/off (resets the counters)."""
+        self.debug_set(2, 1 if on else 0)
+
+    def profile_read(self) -> Dict[str, "tuple[float, int]"]:
+        """{launch kind: (total ms, launches)} since the last read; synchronises."""
+        n = len(self.LAUNCH_KINDS)
+        ms, cnt = (C.c_double * n)(), (C.c_int64 * n)()
+        _lib.check(self._lib, self._h, self._lib.mimi_b200_profile_read(self._h, n, ms, cnt), "mimi_b200_profile_read")
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.LAUNCH_KINDS) if cnt[i]}
+
     @property
     def launch_count(self) -> int:
         return int(self._lib.mimi_b200_launch_count(self._h))
@@ -285,9 +300,10 @@ class MimiEncoder:
     """Same methods as the reference's ``MimiEncoder`` wrapper (REF/emilia-mimi/process_shard.py:50-140).
 
     ``model`` may be a :class:`MimiB200Model`, a state dict, a checkpoint path, or a loaded
-    ``transformers.MimiModel`` whose weights are taken over."""
+    ``transformers.MimiModel`` whose weights are taken over. ``num_quantizers=None`` returns all 32
+    codebooks like the reference (whose callers then slice ``[:8]``); pass 8 to compute only those."""
 
-    def __init__(self, model, device: str = "cuda", ragged: bool = True):
+    def __init__(self, model, device: str = "cuda", ragged: bool = True, num_quantizers: Optional[int] = None):
         self.device = device
         self.feature_extractor = EncodecFeatureExtractorLite()
         if isinstance(model, MimiB200Model):
@@ -299,17 +315,36 @@ class MimiEncoder:
         else:
             self.model = MimiB200Model.from_transformers(model, device=device)
         self.ragged = ragged
+        self.num_quantizers = num_quantizers
         self._pinned: Optional[torch.Tensor] = None
 
-    def _to_device(self, t: torch.Tensor) -> torch.Tensor:
-        return t.to(self.model.device, non_blocking=True)
+    def _stage(self, audio_arrays: Sequence[np.ndarray], sample_rate: int) -> torch.Tensor:
+        """What ``feature_extractor(..., padding=True)`` + ``.to(device)`` do in the reference
+        (REF/emilia-mimi/process_shard.py:113-121), as one pinned staging buffer and one H2D copy: fp32
+        cast, zero right-padding to the longest item -> ``input_values [B,1,N]`` on the device. The
+        ``padding_mask`` is never shipped: the model ignores it and the lengths are known here."""
+        if sample_rate != self.feature_extractor.sampling_rate:
+            self.feature_extractor(raw_audio=np.zeros(1, np.float32), sampling_rate=sample_rate)   # raises ValueError
+        B = len(audio_arrays)
+        N = max(len(a) for a in audio_arrays)
+        if self._pinned is None or self._pinned.numel() < B * N:
+            self._pinned = torch.empty(max(B * N, 1), dtype=torch.float32).pin_memory()
+        buf = self._pinned[: B * N].view(B, 1, N)
+        for i, a in enumerate(audio_arrays):
+            a = np.asarray(a)
+            if a.ndim != 1:
+                raise ValueError(f"Expected mono audio but example has {a.shape[-1]} channels")
+            n = a.shape[0]
+            buf[i, 0, :n].copy_(torch.from_numpy(np.ascontiguousarray(a)))       # casts float64 -> float32
+            if n < N:
+                buf[i, 0, n:].zero_()
+        return buf.to(self.model.device, non_blocking=True)
 
     def encode_audio_chunk(self, audio_array: np.ndarray, sample_rate: int = 24000) -> np.ndarray:
-        """REF/emilia-mimi/process_shard.py:63-86: one utterance -> codes ``[32, T]`` (numpy int64)."""
+        """REF/emilia-mimi/process_shard.py:63-86: one utterance -> codes ``[K, T]`` (numpy int64)."""
         with torch.no_grad():
-            inputs = self.feature_extractor(raw_audio=audio_array, sampling_rate=sample_rate, return_tensors="pt")
-            inputs = {k: self._to_device(v) for k, v in inputs.items()}
-            out = self.model.encode(inputs["input_values"], inputs["padding_mask"])
+            x = self._stage([audio_array], sample_rate)
+            out = self.model.encode(x, None, num_quantizers=self.num_quantizers)
             return out.audio_codes.cpu().numpy()[0]
 
     def encode_audio_batch(self, audio_arrays: List[np.ndarray], sample_rate: int = 24000) -> List[np.ndarray]:
@@ -322,9 +357,8 @@ class MimiEncoder:
             return [self.encode_audio_chunk(audio_arrays[0], sample_rate)]
         with torch.no_grad():
             original_lengths = [len(a) for a in audio_arrays]
-            inputs = self.feature_extractor(raw_audio=audio_arrays, sampling_rate=sample_rate, return_tensors="pt", padding=True)
-            inputs = {k: self._to_device(v) for k, v in inputs.items()}
-            out = self.model.encode(input_values=inputs["input_values"], padding_mask=inputs["padding_mask"],
+            x = self._stage(audio_arrays, sample_rate)
+            out = self.model.encode(input_values=x, padding_mask=None, num_quantizers=self.num_quantizers,
                                     valid_lengths=original_lengths if self.ragged else None)
             codes = out.audio_codes.cpu().numpy()
             frame_rate = sample_rate / 12.5
