@@ -128,15 +128,22 @@ int mimi_b200_debug_tap(mimi_b200_t* h, int which, float* d_out, size_t out_capa
 
 /* Debug knobs (parity bisection only): key 0 = number of transformer layers to run (default 8),
    key 1 = index of the last SEANet conv to run (default 13; smaller values stop the pipeline there and
-   leave d_codes untouched), key 2 = per-launch CUDA-event profiling on/off (resets the profile). */
+   leave d_codes untouched), key 2 = per-launch CUDA-event profiling on/off (resets the profile), key 3 =
+   compute mode: 1 (default) wide layers on tcgen05 3xTF32 tensor cores, 0 all-fp32 FFMA. */
 int mimi_b200_debug_set(mimi_b200_t* h, int key, int value);
 
 /* Read and reset the per-launch profile gathered since profiling was switched on: for launch kind
    id < max_ids, sum_ms[id] = total device time between the previous launch's end and this launch's end on
    the encode stream, count[id] = launches. Kinds: 0 conv0; 1..13 SEANet conv i (gather-GEMM); 14
    LayerNorm; 15 QKV; 16 attention; 17 o_proj; 18 fc1; 19 fc2; 20 downsample conv; 21 RVQ input_proj;
-   22 fused RVQ; 23 latent transpose; 24 code fill. Synchronises with the last recorded launch. */
+   22 fused RVQ; 23 latent transpose; 24 code fill; 25 halo zeroing; 26 replicate-pad + split. Synchronises with the last recorded launch. */
 int mimi_b200_profile_read(mimi_b200_t* h, int max_ids, double* sum_ms, int64_t* count);
+
+/* Unit-test hook for the tensor-core GEMM kernel: d_out[M][N] = act(d_a[M][K] * h_w[N][K]^T + bias) through the
+   encoder's own TF32 hi/lo split + TMA + tcgen05 path (N % 64 == 0, K % 32 == 0; act 1 = GELU(erf)).
+   Synchronises the stream. */
+int mimi_b200_debug_tc_gemm(mimi_b200_t* h, const float* d_a, const float* h_w, const float* d_bias_opt, int M,
+                            int N, int K, int act, float* d_out, void* stream);
 
 /* Output length of the resampler for n input samples: ceil(n * sr_out / sr_in) (librosa fix=True). */
 int64_t mimi_b200_resample_out_len(int64_t n_in, int sr_in, int sr_out);

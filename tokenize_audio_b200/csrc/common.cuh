@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 namespace mimi {
 
@@ -34,6 +35,27 @@ __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
+}
+
+// fp32 -> (hi, lo) for the 3xTF32 tensor-core path: hi keeps the 10-bit TF32 mantissa (round to nearest on
+// the dropped 13 bits), lo = x - hi exactly. hi is exactly TF32-representable, so whatever rounding the
+// tensor core applies to its fp32 inputs cannot change it.
+__host__ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+#ifdef __CUDA_ARCH__
+  hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+#else
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  u = (u + 0x1000u) & 0xFFFFE000u;
+  memcpy(&hi, &u, 4);
+#endif
+  lo = x - hi;
+}
+__device__ __forceinline__ void store_split4(float* hi, float* lo, float4 v) {
+  float4 h4, l4;
+  split_tf32(v.x, h4.x, l4.x); split_tf32(v.y, h4.y, l4.y); split_tf32(v.z, h4.z, l4.z); split_tf32(v.w, h4.w, l4.w);
+  *reinterpret_cast<float4*>(hi) = h4;
+  *reinterpret_cast<float4*>(lo) = l4;
 }
 
 __host__ __device__ __forceinline__ int ceil_div(int a, int b) { return (a + b - 1) / b; }

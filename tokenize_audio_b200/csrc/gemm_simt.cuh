@@ -31,6 +31,13 @@ struct GemmParams {
   int replicate;              // 1: clamp rows (replicate padding) instead of zero fill
   int elu_in;                 // 1: ELU applied to A while loading
   int act;                    // 0 none, 1 GELU(erf) after bias
+  // optional hi/lo split output for a tensor-core consumer (out may then be nullptr): row j of item b at
+  // b*split_item_stride + (split_front + j)*N; ELU applied first when elu_split
+  float* out_hi;
+  float* out_lo;
+  long long split_item_stride;
+  int split_front;
+  int elu_split;
 };
 
 template <int BM, int BN, int TN>
@@ -175,7 +182,12 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmParams p) {
         const float4 rv = *reinterpret_cast<const float4*>(p.res + o);   // may alias out: plain load
         v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
       }
-      *reinterpret_cast<float4*>(p.out + o) = v;
+      if (p.out) *reinterpret_cast<float4*>(p.out + o) = v;
+      if (p.out_hi) {
+        if (p.elu_split) { v.x = elu1(v.x); v.y = elu1(v.y); v.z = elu1(v.z); v.w = elu1(v.w); }
+        const long long so = (long long)b * p.split_item_stride + (long long)(p.split_front + j) * p.N + c;
+        store_split4(p.out_hi + so, p.out_lo + so, v);
+      }
     }
   }
 }

@@ -2,11 +2,14 @@
 // boundary and DESIGN.md for the layout / kernel notes. No CPU fallback anywhere in this file.
 #include "../../include/mimi_b200.h"
 
+#include <cuda.h>
+#include <cudaTypedefs.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -16,6 +19,7 @@
 #include "gemm_simt.cuh"
 #include "io_kernels.cuh"
 #include "rvq.cuh"
+#include "tc_gemm.cuh"
 #include "transformer.cuh"
 
 using namespace mimi;
@@ -48,6 +52,38 @@ struct Plan {
 };
 
 struct TapInfo { long long off; int level; int C; };
+
+// ---- tensor-core (tcgen05 3xTF32) path ---------------------------------------------------------------
+// A weight matrix [N][K] (K-major) pre-split into TF32 hi / lo parts with its two TMA maps (box 32 x BN)
+struct TcWeight {
+  float* hi = nullptr;
+  float* lo = nullptr;
+  CUtensorMap map_hi, map_lo;
+  int N = 0, K = 0, BN = 0;
+};
+// hi/lo activation pair, channels-last with `front` zero halo rows before row 0 of every item
+struct SplitBuf { long long hi = 0, lo = 0, item_stride = 0; int front = 0, back = 0, C = 0, level = 0; };
+constexpr int kHalo = 8;     // >= max(k - stride) = 8 (front) and >= max(stride) - 1 = 7 (back)
+
+struct PlanTC {
+  int B = 0, K = 0;
+  long long N = 0;
+  int rows[6] = {0, 0, 0, 0, 0, 0};
+  long long a0, r1, d1, d2, d3, z, qkv, e, rp;                 // raw fp32 buffers (float offsets)
+  SplitBuf s_h1, s_d1, s_r2, s_h2, s_d2, s_r3, s_h3, s_d3, s_r4, s_h4, s_d4, s_y, s_att, s_ffn, s_zp, s_e;
+  long long ints;
+  size_t bytes = 0;
+};
+
+struct MapSet { std::vector<CUtensorMap> maps; uint64_t built = 0; };
+struct MapKey {
+  const void* ws; int B; long long N;
+  bool operator<(const MapKey& o) const {
+    if (ws != o.ws) return ws < o.ws;
+    if (B != o.B) return B < o.B;
+    return N < o.N;
+  }
+};
 
 }  // namespace
 
@@ -83,12 +119,23 @@ struct mimi_b200 {
   int dbg_layers = MIMI_B200_NUM_LAYERS;
   int dbg_last_conv = MIMI_B200_NUM_CONVS - 1;
   // optional per-launch CUDA-event profile (debug_set key 2): events[i] closes launch prof_ids[i]
+  bool sync_debug = false;             // MIMI_B200_SYNC=1: synchronise after every launch, report the first failure
+  std::string sync_err;
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_pool;
   std::vector<int> prof_ids;           // -1 = "begin" marker
   size_t prof_n = 0;
   Plan last;
   void* last_ws = nullptr;
+  // tensor-core path
+  int mode = 1;                                // 1 = tcgen05 3xTF32 for the wide layers, 0 = all-fp32 SIMT
+  PFN_cuTensorMapEncodeTiled_v12000 encode_tiled = nullptr;
+  TcWeight tc_conv[MIMI_B200_NUM_CONVS];       // convs 3..13 (0..2 stay SIMT)
+  TcWeight tc_qkv[MIMI_B200_NUM_LAYERS], tc_o[MIMI_B200_NUM_LAYERS], tc_fc1[MIMI_B200_NUM_LAYERS], tc_fc2[MIMI_B200_NUM_LAYERS];
+  TcWeight tc_down, tc_proj;
+  std::map<MapKey, MapSet> amap_cache;   // activation maps per (workspace, B, N)
+  PlanTC last_tc;
+  bool last_was_tc = false;
 };
 
 static std::string g_create_err;
@@ -97,7 +144,7 @@ static std::string g_create_err;
   do {                                                                                        \
     cudaError_t e__ = (expr);                                                                 \
     if (e__ != cudaSuccess) {                                                                 \
-      (h)->err = std::string(#expr) + ": " + cudaGetErrorString(e__);                         \
+      (h)->err = std::string(#expr) + ": " + cudaGetErrorString(e__) + " " + (h)->sync_err;   \
       return MIMI_B200_ERR_CUDA;                                                              \
     }                                                                                         \
   } while (0)
@@ -109,6 +156,10 @@ static int fail(mimi_b200* h, int code, const std::string& msg) {
 
 // record "launch `id` just ended" on the stream (profiling only)
 static void mark(mimi_b200* h, int id, cudaStream_t st) {
+  if (h->sync_debug && id >= 0 && h->sync_err.empty()) {
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) h->sync_err = "launch kind " + std::to_string(id) + " (#" + std::to_string(h->launches) + "): " + cudaGetErrorString(e);
+  }
   if (!h->prof_on) return;
   if (h->prof_n == h->prof_pool.size()) {
     cudaEvent_t e;
@@ -263,6 +314,8 @@ static void design_taps(int sr_in, int sr_out, std::vector<float>& taps, int& c,
   for (int i = 0; i < n; ++i) taps[i] = (float)(hcoef[i] * (double)L / sum);
 }
 
+#include "tc_host.inl"
+
 static int utf8_len(unsigned cp) { return cp < 0x80u ? 1 : cp < 0x800u ? 2 : cp < 0x10000u ? 3 : 4; }
 
 // =====================================================================================================
@@ -295,10 +348,13 @@ int mimi_b200_create(mimi_b200_t** out, int device_ordinal) {
     return fail(nullptr, MIMI_B200_ERR_CUDA, "create: this library is built for sm_100a (B200) only");
   mimi_b200* h = new mimi_b200();
   h->device = device_ordinal;
+  h->sync_debug = getenv("MIMI_B200_SYNC") != nullptr;
   if ((e = cudaSetDevice(device_ordinal)) != cudaSuccess) { delete h; return fail(nullptr, MIMI_B200_ERR_CUDA, cudaGetErrorString(e)); }
   for (int i = 0; i < kStageSlots; ++i) cudaEventCreateWithFlags(&h->stage_ev[i], cudaEventDisableTiming);
   cudaFuncSetAttribute(swa_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttSmemBytes);
   cudaFuncSetAttribute(rvq_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRvqSmemBytes);
+  cudaFuncSetAttribute(tc::tc_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::smem_bytes(128));
+  cudaFuncSetAttribute(tc::tc_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::smem_bytes(64));
   if ((e = cudaGetLastError()) != cudaSuccess) { delete h; return fail(nullptr, MIMI_B200_ERR_CUDA, cudaGetErrorString(e)); }
   *out = h;
   return MIMI_B200_OK;
@@ -324,6 +380,7 @@ int mimi_b200_debug_set(mimi_b200_t* h, int key, int value) {
   if (key == 0) h->dbg_layers = std::min(std::max(value, 0), MIMI_B200_NUM_LAYERS);
   else if (key == 1) h->dbg_last_conv = std::min(std::max(value, 0), MIMI_B200_NUM_CONVS - 1);
   else if (key == 2) { h->prof_on = value != 0; h->prof_n = 0; }
+  else if (key == 3) h->mode = value ? 1 : 0;
   else return fail(h, MIMI_B200_ERR_ARG, "debug_set: unknown key");
   return MIMI_B200_OK;
 }
@@ -433,6 +490,8 @@ int mimi_b200_load_weights(mimi_b200_t* h, const mimi_b200_weights_t* w) {
     if ((rc = dev_upload(h, &h->rope_cos, cs))) return rc;
     if ((rc = dev_upload(h, &h->rope_sin, sn))) return rc;
   }
+  if ((rc = tc_load_weights(h, w))) return rc;
+  h->amap_cache.clear();
   h->loaded = true;
   return MIMI_B200_OK;
 }
@@ -441,7 +500,7 @@ int mimi_b200_workspace_bytes(mimi_b200_t* h, int B, int64_t N, int K, size_t* o
   if (!h || !out_bytes) return fail(h, MIMI_B200_ERR_ARG, "workspace_bytes: NULL argument");
   if (B < 0 || N < 0 || N > (1ll << 30) || K < 1 || K > MIMI_B200_MAX_QUANTIZERS)
     return fail(h, MIMI_B200_ERR_ARG, "workspace_bytes: bad B/N/K");
-  *out_bytes = make_plan(B, N, K).bytes + 256;
+  *out_bytes = std::max(make_plan(B, N, K).bytes, make_plan_tc(B, N, K).bytes) + 256;
   return MIMI_B200_OK;
 }
 
@@ -463,15 +522,20 @@ int mimi_b200_encode(mimi_b200_t* h, const float* d_input, int B, int64_t N, con
   CUDA_TRY(h, cudaSetDevice(h->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 
+  const bool use_tc = h->mode == 1 && h->dbg_last_conv == MIMI_B200_NUM_CONVS - 1;
   const Plan p = make_plan(B, N, K);
+  const PlanTC pt = make_plan_tc(B, N, K);
+  const size_t need = use_tc ? pt.bytes : p.bytes;
   // align the workspace base to 256 bytes
   uintptr_t base = (reinterpret_cast<uintptr_t>(d_workspace) + 255) & ~uintptr_t(255);
-  if (base + p.bytes > reinterpret_cast<uintptr_t>(d_workspace) + workspace_bytes)
-    return fail(h, MIMI_B200_ERR_WORKSPACE, "encode: workspace too small, need " + std::to_string(p.bytes + 256));
+  if (base + need > reinterpret_cast<uintptr_t>(d_workspace) + workspace_bytes)
+    return fail(h, MIMI_B200_ERR_WORKSPACE, "encode: workspace too small, need " + std::to_string(need + 256));
   if (p.rows[4] > kRopeMaxPos) return fail(h, MIMI_B200_ERR_ARG, "encode: more than 16384 25-Hz positions per item");
   float* ws = reinterpret_cast<float*>(base);
-  int* dints = reinterpret_cast<int*>(base + p.ints);
+  int* dints = reinterpret_cast<int*>(base + (use_tc ? pt.ints : p.ints));
   h->last = p;
+  h->last_tc = pt;
+  h->last_was_tc = use_tc;
   h->last_ws = ws;
   mark(h, -1, st);
 
@@ -507,6 +571,12 @@ int mimi_b200_encode(mimi_b200_t* h, const float* d_input, int B, int64_t N, con
     const long long ncodes = (long long)B * K * p.rows[5];
     fill_codes_zero_kernel<<<(unsigned)((ncodes + 255) / 256), 256, 0, st>>>(reinterpret_cast<long long*>(d_codes), ncodes);
     h->launches++; mark(h, 24, st);
+  }
+
+  if (use_tc) {
+    int rc_tc = encode_tc(h, d_input, B, N, K, pt, ws, dlen, maxlen, dprefix, total_frames, d_codes, d_latent_opt, st);
+    if (rc_tc == MIMI_B200_OK && !h->sync_err.empty()) return fail(h, MIMI_B200_ERR_CUDA, h->sync_err);
+    return rc_tc;
   }
 
   auto istride = [&](int level, int C) { return (long long)p.rows[level] * C; };
@@ -569,7 +639,7 @@ int mimi_b200_encode(mimi_b200_t* h, const float* d_input, int B, int64_t N, con
   for (int l = 0; l < h->dbg_layers; ++l) {
     const LayerDev& d = h->layer[l];
     dim3 lgrid((T25 + 7) / 8, B);
-    layernorm512_kernel<<<lgrid, 256, 0, st>>>(ws + p.z, ws + p.y, d.ln1_w, d.ln1_b, istride(4, 512), dlen[4], T25);
+    layernorm512_kernel<<<lgrid, 256, 0, st>>>(ws + p.z, ws + p.y, d.ln1_w, d.ln1_b, istride(4, 512), dlen[4], T25, nullptr);
     h->launches++; mark(h, 14, st);
     GemmParams g{};
     g.A = ws + p.y; g.Wt = d.qkv_wt; g.out = ws + p.qkv; g.len_in = dlen[4]; g.uniform_len_in = T25;
@@ -578,7 +648,7 @@ int mimi_b200_encode(mimi_b200_t* h, const float* d_input, int B, int64_t N, con
     if ((rc = launch_gemm(h, g, B, T25, st, 15))) return rc;
     dim3 agrid((T25 + kAttQT - 1) / kAttQT, kHeads, B);
     swa_attention_kernel<<<agrid, 256, kAttSmemBytes, st>>>(ws + p.qkv, istride(4, 1536), ws + p.att, istride(4, 512),
-                                                            h->rope_cos, h->rope_sin, dlen[4], T25);
+                                                            h->rope_cos, h->rope_sin, dlen[4], T25, nullptr);
     h->launches++; mark(h, 16, st);
     CUDA_TRY(h, cudaGetLastError());
     g = GemmParams{};   // o_proj + LayerScale + residual (in place on z)
@@ -586,7 +656,7 @@ int mimi_b200_encode(mimi_b200_t* h, const float* d_input, int B, int64_t N, con
     g.len_in = dlen[4]; g.uniform_len_in = T25; g.a_item_stride = istride(4, 512); g.out_item_stride = istride(4, 512);
     g.Cin = 512; g.stride = 1; g.K = 512; g.N = 512;
     if ((rc = launch_gemm(h, g, B, T25, st, 17))) return rc;
-    layernorm512_kernel<<<lgrid, 256, 0, st>>>(ws + p.z, ws + p.y, d.ln2_w, d.ln2_b, istride(4, 512), dlen[4], T25);
+    layernorm512_kernel<<<lgrid, 256, 0, st>>>(ws + p.z, ws + p.y, d.ln2_w, d.ln2_b, istride(4, 512), dlen[4], T25, nullptr);
     h->launches++; mark(h, 14, st);
     g = GemmParams{};   // fc1 + GELU(erf)
     g.A = ws + p.y; g.Wt = d.fc1_wt; g.out = ws + p.ffn; g.len_in = dlen[4]; g.uniform_len_in = T25;
@@ -641,6 +711,22 @@ int mimi_b200_debug_tap(mimi_b200_t* h, int which, float* d_out, size_t cap, int
   if (!h || !h->last_ws) return fail(h, MIMI_B200_ERR_STATE, "debug_tap: no encode call yet");
   const Plan& p = h->last;
   TapInfo t{};
+  if (h->last_was_tc) {
+    const PlanTC& q = h->last_tc;
+    switch (which) {
+      case 0: t = {q.a0, 0, 64}; break;
+      case 1: t = {q.r1, 0, 32}; break;
+      case 3: t = {q.d1, 1, 128}; break;
+      case 6: t = {q.d2, 2, 256}; break;
+      case 9: t = {q.d3, 3, 512}; break;
+      case 13: t = {q.z, 4, 512}; break;
+      case 200: t = {q.e, 5, 512}; break;
+      case 201: t = {q.rp, 5, 512}; break;
+      default:
+        if (which >= 100 && which < 100 + MIMI_B200_NUM_LAYERS) t = {q.z, 4, 512};
+        else return fail(h, MIMI_B200_ERR_ARG, "debug_tap: tap not materialised on the tensor-core path");
+    }
+  } else
   switch (which) {
     case 0: case 2: t = {p.a0, 0, 64}; break;
     case 1: t = {p.r1, 0, 32}; break;
@@ -665,6 +751,47 @@ int mimi_b200_debug_tap(mimi_b200_t* h, int which, float* d_out, size_t cap, int
   if (cap < n) return fail(h, MIMI_B200_ERR_ARG, "debug_tap: output too small");
   CUDA_TRY(h, cudaMemcpyAsync(d_out, static_cast<float*>(h->last_ws) + t.off, n * sizeof(float), cudaMemcpyDeviceToDevice,
                               static_cast<cudaStream_t>(stream)));
+  return MIMI_B200_OK;
+}
+
+// Unit-test hook for the tensor-core GEMM: out[M][N] = epilogue(A[M][K] * W[N][K]^T) through the same split /
+// TMA / tcgen05 path the encoder uses (A is split on the device, W on the host).
+__global__ void debug_split_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) split_tf32(x[i], hi[i], lo[i]);
+}
+
+int mimi_b200_debug_tc_gemm(mimi_b200_t* h, const float* d_a, const float* h_w, const float* d_bias_opt, int M, int N,
+                            int K, int act, float* d_out, void* stream) {
+  if (!h || !d_a || !h_w || !d_out) return fail(h, MIMI_B200_ERR_ARG, "debug_tc_gemm: NULL argument");
+  if (M <= 0 || N % 64 || K % 32) return fail(h, MIMI_B200_ERR_ARG, "debug_tc_gemm: need N % 64 == 0 and K % 32 == 0");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc;
+  if ((rc = tc_init_driver(h))) return rc;
+  TcWeight w;
+  if ((rc = tc_make_weight(h, &w, std::vector<float>(h_w, h_w + (size_t)N * K), N, K))) return rc;
+  float *hi = nullptr, *lo = nullptr;
+  const long long n = (long long)M * K;
+  CUDA_TRY(h, cudaMalloc((void**)&hi, n * sizeof(float)));
+  CUDA_TRY(h, cudaMalloc((void**)&lo, n * sizeof(float)));
+  debug_split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_a, hi, lo, n);
+  CUtensorMap ma_hi, ma_lo;
+  const cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)M, 1};
+  const cuuint64_t strides[2] = {(cuuint64_t)K * sizeof(float), (cuuint64_t)n * sizeof(float)};
+  if ((rc = tc_make_map(h, &ma_hi, hi, 3, dims, strides, tc::kBM))) return rc;
+  if ((rc = tc_make_map(h, &ma_lo, lo, 3, dims, strides, tc::kBM))) return rc;
+  tc::Epilogue ep{};
+  ep.bias = d_bias_opt; ep.out_raw = d_out; ep.raw_item_stride = (long long)M * N; ep.act = act;
+  ep.uniform_len_in = M; ep.conv_stride = 1; ep.N = N;
+  dim3 grid((M + tc::kBM - 1) / tc::kBM, N / w.BN, 1);
+  if (w.BN == 128) tc::tc_gemm_kernel<128><<<grid, tc::kThreads, tc::smem_bytes(128), st>>>(ma_hi, ma_lo, w.map_hi, w.map_lo, K, ep);
+  else tc::tc_gemm_kernel<64><<<grid, tc::kThreads, tc::smem_bytes(64), st>>>(ma_hi, ma_lo, w.map_hi, w.map_lo, K, ep);
+  h->launches += 2;
+  cudaError_t e = cudaStreamSynchronize(st);
+  cudaFree(hi);
+  cudaFree(lo);
+  if (e != cudaSuccess) return fail(h, MIMI_B200_ERR_CUDA, std::string("debug_tc_gemm: ") + cudaGetErrorString(e));
   return MIMI_B200_OK;
 }
 

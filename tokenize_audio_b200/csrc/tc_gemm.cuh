@@ -1,0 +1,336 @@
+// tcgen05 implicit-GEMM for the wide layers: 3xTF32 split precision, TMA-fed, accumulators in TMEM.
+//
+//   D[128 x BN] (fp32, TMEM) = A_hi*W_hi + A_hi*W_lo + A_lo*W_hi        (kind::tf32, UMMA 128 x BN x 8)
+//
+// A is the channels-last activation seen through a 3-D TMA tensor map whose row stride is
+// conv_stride*C_in floats and whose inner extent is k*C_in floats (overlapping rows: the im2col matrix is
+// never materialised; the causal left pad and the right "extra" pad are zero halo rows of the buffer).
+// Both operands are stored pre-split: hi = fp32 rounded to the 10-bit TF32 mantissa, lo = x - hi (exact), so
+// the three passes recover ~2^-22 relative accuracy per product whatever rounding the tensor core applies.
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA issuer,
+// warps 2..5 = epilogue (tcgen05.ld -> bias / GELU / LayerScale / residual / ELU / hi-lo split -> global).
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace mimi {
+namespace tc {
+
+constexpr int kBM = 128;
+constexpr int kBK = 32;                       // fp32 elements per k-block = one 128-byte swizzle row
+constexpr int kUmmaK = 8;                     // tf32 MMA K
+constexpr int kThreads = 192;
+constexpr int kSmemBudget = 196608;           // operand ring bytes (192 KB)
+
+__host__ __device__ constexpr int stage_bytes(int bn) { return 2 * kBM * kBK * 4 + 2 * bn * kBK * 4; }
+__host__ __device__ constexpr int num_stages(int bn) { return kSmemBudget / stage_bytes(bn); }
+__host__ __device__ constexpr int smem_bytes(int bn) { return num_stages(bn) * stage_bytes(bn) + 1024 + 256; }
+
+struct Epilogue {
+  const float* bias;            // [N] or nullptr
+  const float* scale;           // [N] LayerScale or nullptr
+  const float* res;             // raw residual rows of N floats (may alias out_raw) or nullptr
+  float* out_raw;               // raw output rows of N floats, or nullptr
+  float* out_hi;                // split output (with halo rows), or nullptr
+  float* out_lo;
+  long long raw_item_stride;    // floats between items in res / out_raw
+  long long split_item_stride;  // floats between items in out_hi / out_lo
+  int split_front;              // halo rows in front of row 0 of each item in the split buffers
+  int act;                      // 1: GELU(erf) after bias
+  int elu_split;                // 1: ELU applied before the hi/lo split (next conv's input activation)
+  const int* len_in;            // device [B] input rows per item or nullptr -> uniform_len_in
+  int uniform_len_in;
+  int conv_stride;              // Lout = ceil(len_in / conv_stride)
+  int N;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp):
+// start address >> 4 in [0,14), LBO in [16,30) (unused for swizzled K-major), SBO >> 4 in [32,46) = 1024 B
+// (8 rows x 128 B), version = 1 at [46,48), layout type SWIZZLE_128B = 2 at [61,64).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (1 @ bit 4), A = B = TF32 (2 @ bits 7, 10),
+// both K-major, N >> 3 @ bit 17, M >> 4 @ bit 24.
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+constexpr int kChunkKB = 4;                   // k-blocks (of 32) accumulated inside TMEM before a drain: K = 128
+
+// Accuracy note. The tensor core adds into its fp32 accumulator with truncation, so a long K loop drifts by
+// ~0.3 ulp per MMA (measured: 3e-6 relative at K=512 growing to 1e-4 by K=8192, far above the 3e-5 the codes
+// tolerate). Hence: (1) only hi*hi goes to the main accumulator, and only for kChunkKB k-blocks (16 MMAs) at
+// a time -- the epilogue warps drain each chunk from TMEM (double-buffered) and add it to per-thread fp32
+// running sums with round-to-nearest FADDs while the next chunk is being computed; (2) the two small cross
+// terms lo*hi + hi*lo (2^-11 of the main term, so their own drift is irrelevant) accumulate over the whole K
+// in a third TMEM region that is drained once.
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+               const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo, int K,
+               const Epilogue ep) {
+  constexpr int STAGES = num_stages(BN);
+  constexpr int A_BYTES = kBM * kBK * 4;           // 16 KB
+  constexpr int W_BYTES = BN * kBK * 4;
+  constexpr int STAGE = stage_bytes(BN);
+  constexpr int TMEM_COLS = (BN == 128) ? 512 : 256;   // main[0] | main[1] | small  (3*BN, power of two)
+  static_assert(BN == 64 || BN == 128, "BN");
+
+  const int b = blockIdx.z;
+  const int Lin = ep.len_in ? ep.len_in[b] : ep.uniform_len_in;
+  const int Lout = (Lin + ep.conv_stride - 1) / ep.conv_stride;
+  const int m0 = blockIdx.x * kBM;
+  if (m0 >= Lout) return;                          // whole CTA leaves before any barrier exists
+  const int n0 = blockIdx.y * BN;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* acc_full = empty_bar + STAGES;         // [2] chunk accumulator ready (MMA -> epilogue)
+  uint64_t* acc_empty = acc_full + 2;              // [2] chunk accumulator drained (epilogue -> MMA)
+  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb = K / kBK;
+  const int nchunks = (nkb + kChunkKB - 1) / kChunkKB;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA_hi); prefetch_tmap(&tmA_lo); prefetch_tmap(&tmW_hi); prefetch_tmap(&tmW_lo);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_ptr)), "r"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_base_ptr;
+  const uint32_t tmem_small = tmem_base + 2 * BN;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        uint8_t* st = smem + s * STAGE;
+        mbar_expect_tx(&full_bar[s], STAGE);
+        tma_load_3d(st, &tmA_hi, &full_bar[s], kb * kBK, m0, b);
+        tma_load_3d(st + A_BYTES, &tmA_lo, &full_bar[s], kb * kBK, m0, b);
+        tma_load_2d(st + 2 * A_BYTES, &tmW_hi, &full_bar[s], kb * kBK, n0);
+        tma_load_2d(st + 2 * A_BYTES + W_BYTES, &tmW_lo, &full_bar[s], kb * kBK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(kBM, BN);
+      for (int c = 0; c < nchunks; ++c) {
+        const int buf = c & 1;
+        mbar_wait(&acc_empty[buf], ((uint32_t)(c >> 1) & 1u) ^ 1u);      // drained two chunks ago
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tmem_main = tmem_base + buf * BN;
+        const int kb_end = min(nkb, (c + 1) * kChunkKB);
+        for (int kb = c * kChunkKB; kb < kb_end; ++kb) {
+          const int s = kb % STAGES;
+          const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+          mbar_wait(&full_bar[s], ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a_hi = smem_u32(smem + s * STAGE);
+          const uint32_t a_lo = a_hi + A_BYTES;
+          const uint32_t w_hi = a_hi + 2 * A_BYTES;
+          const uint32_t w_lo = w_hi + W_BYTES;
+          const bool first_in_chunk = kb == c * kChunkKB;
+#pragma unroll
+          for (int k = 0; k < kBK / kUmmaK; ++k)
+            umma_tf32(tmem_main, make_smem_desc(a_hi + k * 32), make_smem_desc(w_hi + k * 32), idesc, !(first_in_chunk && k == 0));
+#pragma unroll
+          for (int k = 0; k < kBK / kUmmaK; ++k)
+            umma_tf32(tmem_small, make_smem_desc(a_lo + k * 32), make_smem_desc(w_hi + k * 32), idesc, (kb | k) != 0);
+#pragma unroll
+          for (int k = 0; k < kBK / kUmmaK; ++k)
+            umma_tf32(tmem_small, make_smem_desc(a_hi + k * 32), make_smem_desc(w_lo + k * 32), idesc, 1u);
+          umma_commit(&empty_bar[s]);             // frees the smem slot once these MMAs have read it
+        }
+        umma_commit(&acc_full[buf]);              // chunk (and, after the last one, the small terms) complete
+      }
+    }
+  } else {
+    // ---- epilogue warps: warp w may touch TMEM lanes [32*(w%4), +32); thread = one output row -------------
+    const int quarter = warp & 3;
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    float acc[BN];
+#pragma unroll
+    for (int i = 0; i < BN; ++i) acc[i] = 0.f;
+    for (int c = 0; c < nchunks; ++c) {
+      const int buf = c & 1;
+      mbar_wait(&acc_full[buf], (uint32_t)(c >> 1) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t taddr = tmem_base + lane_off + (uint32_t)(buf * BN);
+#pragma unroll
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr + (uint32_t)c0, r);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[c0 + i] += __uint_as_float(r[i]);
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+    }
+    // the last acc_full commit also covers every small-term MMA
+#pragma unroll
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      uint32_t r[16];
+      tmem_ld16(tmem_small + lane_off + (uint32_t)c0, r);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc[c0 + i] += __uint_as_float(r[i]);
+    }
+    // ---- all TMEM traffic is done: per-thread math (may diverge freely) and stores --------------------------
+    const int row = m0 + quarter * 32 + lane;
+    if (row < Lout) {
+      const long long raw_off = (long long)b * ep.raw_item_stride + (long long)row * ep.N + n0;
+      const long long split_off = (long long)b * ep.split_item_stride + (long long)(ep.split_front + row) * ep.N + n0;
+#pragma unroll
+      for (int c0 = 0; c0 < BN; c0 += 4) {
+        float4 v = make_float4(acc[c0], acc[c0 + 1], acc[c0 + 2], acc[c0 + 3]);
+        if (ep.bias) {
+          const float4 t = ld_nc_f4(ep.bias + n0 + c0);
+          v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+        }
+        if (ep.act == 1) { v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w); }
+        if (ep.scale) {
+          const float4 t = ld_nc_f4(ep.scale + n0 + c0);
+          v.x *= t.x; v.y *= t.y; v.z *= t.z; v.w *= t.w;
+        }
+        if (ep.res) {
+          const float4 t = *reinterpret_cast<const float4*>(ep.res + raw_off + c0);
+          v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+        }
+        if (ep.out_raw) *reinterpret_cast<float4*>(ep.out_raw + raw_off + c0) = v;
+        if (ep.out_hi) {
+          if (ep.elu_split) { v.x = elu1(v.x); v.y = elu1(v.y); v.z = elu1(v.z); v.w = elu1(v.w); }
+          store_split4(ep.out_hi + split_off + c0, ep.out_lo + split_off + c0, v);
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+  }
+}
+
+// Zero the halo rows of one split buffer pair: rows [0, front) and [front + L_b, front + L_b + back) of every
+// item (the causal left pad and the right "extra" pad of the consuming conv).
+__global__ void zero_halo_kernel(float* hi, float* lo, long long item_stride, int C, int front, int back,
+                                 const int* __restrict__ len, int uniform_len) {
+  const int b = blockIdx.y;
+  const int L = len ? len[b] : uniform_len;
+  const int per = (front + back) * C;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < per; i += gridDim.x * blockDim.x) {
+    int r = i / C;
+    const int c = i - r * C;
+    if (r >= front) r = front + L + (r - front);
+    const long long o = (long long)b * item_stride + (long long)r * C + c;
+    hi[o] = 0.f;
+    lo[o] = 0.f;
+  }
+}
+
+// z [B][rows][512] raw -> replicate-padded split copy for the stride-2 downsample conv
+// (pad_mode="replicate", modeling_mimi.py:1422-1431): zp row 0,1 = z row 0; zp row 2+t = z row t;
+// zp row 2+T = z row T-1.  One warp per zp row.
+__global__ void __launch_bounds__(256) pad_replicate_split_kernel(const float* __restrict__ z, long long z_item_stride,
+                                                                  float* __restrict__ hi, float* __restrict__ lo,
+                                                                  long long split_item_stride,
+                                                                  const int* __restrict__ len, int uniform_len) {
+  const int b = blockIdx.y;
+  const int T = len ? len[b] : uniform_len;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 8 + warp;            // zp row
+  if (T <= 0 || r >= T + 3) return;
+  const int src = min(max(r - 2, 0), T - 1);
+  const float* zr = z + (long long)b * z_item_stride + (long long)src * kHidden;
+  const long long o = (long long)b * split_item_stride + (long long)r * kHidden;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    const float4 v = ld_nc_f4(zr + c);
+    float4 h4, l4;
+    split_tf32(v.x, h4.x, l4.x); split_tf32(v.y, h4.y, l4.y); split_tf32(v.z, h4.z, l4.z); split_tf32(v.w, h4.w, l4.w);
+    *reinterpret_cast<float4*>(hi + o + c) = h4;
+    *reinterpret_cast<float4*>(lo + o + c) = l4;
+  }
+}
+
+}  // namespace tc
+}  // namespace mimi

@@ -1,0 +1,330 @@
+// Host side of the tensor-core path (included by mimi_b200.cu after the handle definition): TMA tensor
+// maps, TF32 hi/lo weight packs, the split-buffer workspace plan and the encode pipeline that runs the wide
+// layers on tcgen05 (tc_gemm.cuh) and the narrow / non-GEMM ones on the SIMT kernels.
+
+static int tc_init_driver(mimi_b200* h) {
+  if (h->encode_tiled) return MIMI_B200_OK;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  CUDA_TRY(h, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+  if (!fn || q != cudaDriverEntryPointSuccess) return fail(h, MIMI_B200_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  h->encode_tiled = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  return MIMI_B200_OK;
+}
+
+// fp32 tensor map, SWIZZLE_128B, inner box = 32 floats (128 B). rank 2: {K, rows}; rank 3: {K, rows, items}.
+static int tc_make_map(mimi_b200* h, CUtensorMap* out, const float* base, int rank, const cuuint64_t* dims,
+                       const cuuint64_t* strides_bytes, int box_rows) {
+  cuuint32_t box[3] = {(cuuint32_t)tc::kBK, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = h->encode_tiled(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float*>(base), dims,
+                               strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(h, MIMI_B200_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r) + " (dims " +
+                                           std::to_string(dims[0]) + "," + std::to_string(dims[1]) + " stride " +
+                                           std::to_string(strides_bytes[0]) + ")");
+  return MIMI_B200_OK;
+}
+
+// w_nk: host [N][K] K-major. Splits into TF32 hi/lo, uploads, builds the two weight maps.
+static int tc_make_weight(mimi_b200* h, TcWeight* w, const std::vector<float>& w_nk, int N, int K) {
+  std::vector<float> hi(w_nk.size()), lo(w_nk.size());
+  for (size_t i = 0; i < w_nk.size(); ++i) split_tf32(w_nk[i], hi[i], lo[i]);
+  int rc;
+  if ((rc = dev_upload(h, &w->hi, hi))) return rc;
+  if ((rc = dev_upload(h, &w->lo, lo))) return rc;
+  w->N = N; w->K = K; w->BN = (N % 128 == 0) ? 128 : 64;
+  const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
+  const cuuint64_t strides[1] = {(cuuint64_t)K * sizeof(float)};
+  if ((rc = tc_make_map(h, &w->map_hi, w->hi, 2, dims, strides, w->BN))) return rc;
+  if ((rc = tc_make_map(h, &w->map_lo, w->lo, 2, dims, strides, w->BN))) return rc;
+  return MIMI_B200_OK;
+}
+
+// conv weight [Cout][Cin][k] -> [Cout][k*Cin] with K index = tau*Cin + ci (K-major rows)
+static std::vector<float> pack_conv_nk(const float* w, int cout, int cin, int k) {
+  std::vector<float> t((size_t)cout * cin * k);
+  for (int co = 0; co < cout; ++co)
+    for (int ci = 0; ci < cin; ++ci)
+      for (int tau = 0; tau < k; ++tau) t[((size_t)co * k + tau) * cin + ci] = w[((size_t)co * cin + ci) * k + tau];
+  return t;
+}
+
+static int tc_load_weights(mimi_b200* h, const mimi_b200_weights_t* w) {
+  int rc;
+  if ((rc = tc_init_driver(h))) return rc;
+  for (int i = 3; i < MIMI_B200_NUM_CONVS; ++i) {
+    const ConvGeom& g = kConv[i];
+    if ((rc = tc_make_weight(h, &h->tc_conv[i], pack_conv_nk(w->conv_weight[i], g.cout, g.cin, g.k), g.cout, g.cin * g.k))) return rc;
+  }
+  for (int l = 0; l < MIMI_B200_NUM_LAYERS; ++l) {
+    const mimi_b200_layer_weights_t& s = w->layer[l];
+    std::vector<float> qkv((size_t)1536 * 512);
+    std::memcpy(qkv.data(), s.q_proj_weight, sizeof(float) * 512 * 512);
+    std::memcpy(qkv.data() + 512 * 512, s.k_proj_weight, sizeof(float) * 512 * 512);
+    std::memcpy(qkv.data() + 2 * 512 * 512, s.v_proj_weight, sizeof(float) * 512 * 512);
+    if ((rc = tc_make_weight(h, &h->tc_qkv[l], qkv, 1536, 512))) return rc;
+    if ((rc = tc_make_weight(h, &h->tc_o[l], std::vector<float>(s.o_proj_weight, s.o_proj_weight + 512 * 512), 512, 512))) return rc;
+    if ((rc = tc_make_weight(h, &h->tc_fc1[l], std::vector<float>(s.fc1_weight, s.fc1_weight + 2048 * 512), 2048, 512))) return rc;
+    if ((rc = tc_make_weight(h, &h->tc_fc2[l], std::vector<float>(s.fc2_weight, s.fc2_weight + 512 * 2048), 512, 2048))) return rc;
+  }
+  if ((rc = tc_make_weight(h, &h->tc_down, pack_conv_nk(w->downsample_weight, 512, 512, 4), 512, 2048))) return rc;
+  std::vector<float> pj((size_t)512 * 512);
+  std::memcpy(pj.data(), w->semantic_input_proj_weight, sizeof(float) * 256 * 512);
+  std::memcpy(pj.data() + 256 * 512, w->acoustic_input_proj_weight, sizeof(float) * 256 * 512);
+  if ((rc = tc_make_weight(h, &h->tc_proj, pj, 512, 512))) return rc;
+  return MIMI_B200_OK;
+}
+
+static PlanTC make_plan_tc(int B, long long N, int K) {
+  PlanTC p;
+  p.B = B; p.K = K; p.N = N;
+  long long L = N;
+  p.rows[0] = (int)L;
+  for (int l = 0; l < 5; ++l) { L = (L + kLevelStride[l] - 1) / kLevelStride[l]; p.rows[l + 1] = (int)L; }
+  long long off = 0;
+  auto take = [&](long long n) { const long long o = off; off += (n + 63) / 64 * 64; return o; };
+  auto raw = [&](int level, int C) { return take((long long)B * p.rows[level] * C); };
+  auto split = [&](int level, int C, int front, int back) {
+    SplitBuf s;
+    s.level = level; s.C = C; s.front = front; s.back = back;
+    s.item_stride = (long long)(front + p.rows[level] + back) * C;
+    s.hi = take((long long)B * s.item_stride + 64);
+    s.lo = take((long long)B * s.item_stride + 64);
+    return s;
+  };
+  p.a0 = raw(0, 64);   p.r1 = raw(0, 32);
+  p.s_h1 = split(0, 64, kHalo, kHalo);
+  p.d1 = raw(1, 128);  p.s_d1 = split(1, 128, kHalo, kHalo);  p.s_r2 = split(1, 64, 0, 0);  p.s_h2 = split(1, 128, kHalo, kHalo);
+  p.d2 = raw(2, 256);  p.s_d2 = split(2, 256, kHalo, kHalo);  p.s_r3 = split(2, 128, 0, 0); p.s_h3 = split(2, 256, kHalo, kHalo);
+  p.d3 = raw(3, 512);  p.s_d3 = split(3, 512, kHalo, kHalo);  p.s_r4 = split(3, 256, 0, 0); p.s_h4 = split(3, 512, kHalo, kHalo);
+  p.s_d4 = split(4, 1024, kHalo, kHalo);
+  p.z = raw(4, 512);   p.s_y = split(4, 512, 0, 0);  p.qkv = raw(4, 1536);  p.s_att = split(4, 512, 0, 0);
+  p.s_ffn = split(4, 2048, 0, 0);
+  p.s_zp = split(4, 512, 0, 3);          // rows: [z0, z0, z0..z(T-1), z(T-1)] = T + 3
+  p.e = raw(5, 512);   p.s_e = split(5, 512, 0, 0);  p.rp = raw(5, 512);
+  p.ints = off * (long long)sizeof(float);
+  p.bytes = (size_t)p.ints + sizeof(int) * (size_t)(7 * B + 1 + 64);
+  return p;
+}
+
+namespace {
+struct TcCtx {
+  mimi_b200* h;
+  const PlanTC* p;
+  float* ws;
+  int B;
+  cudaStream_t st;
+  const int* const* dlen;     // [6] device length arrays (or nullptr entries)
+  const int* maxlen;          // [6]
+  std::vector<CUtensorMap>* maps;   // 2 maps (hi, lo) per GEMM site, indexed by a fixed slot id
+  uint64_t* built;                  // bit `slot` set once that site's maps are encoded
+};
+constexpr int kTcSlots = 48;
+}  // namespace
+
+// activation maps for a conv/linear that reads SplitBuf `a` with kernel k, stride s, left pad `pad`
+static int tc_amaps(TcCtx& c, int slot, const SplitBuf& a, int k, int s, int pad, const CUtensorMap** hi, const CUtensorMap** lo) {
+  CUtensorMap* mh = &(*c.maps)[2 * slot];
+  CUtensorMap* ml = mh + 1;
+  if (!((*c.built >> slot) & 1ull)) {
+    const PlanTC& p = *c.p;
+    const int rows_out = (p.rows[a.level] + s - 1) / s;
+    const cuuint64_t dims[3] = {(cuuint64_t)k * a.C, (cuuint64_t)std::max(rows_out, 1), (cuuint64_t)c.B};
+    const cuuint64_t strides[2] = {(cuuint64_t)s * a.C * sizeof(float), (cuuint64_t)a.item_stride * sizeof(float)};
+    const long long base_off = (long long)(a.front - pad) * a.C;
+    if (a.front < pad) return fail(c.h, MIMI_B200_ERR_ARG, "tc: halo smaller than conv padding");
+    int rc;
+    if ((rc = tc_make_map(c.h, mh, c.ws + a.hi + base_off, 3, dims, strides, tc::kBM))) return rc;
+    if ((rc = tc_make_map(c.h, ml, c.ws + a.lo + base_off, 3, dims, strides, tc::kBM))) return rc;
+    *c.built |= 1ull << slot;
+  }
+  *hi = mh;
+  *lo = ml;
+  return MIMI_B200_OK;
+}
+
+struct TcOut {
+  float* raw = nullptr;            // raw output buffer (rows of N), item stride = rows[level]*N
+  const float* res = nullptr;      // residual (same geometry as raw)
+  long long raw_item_stride = 0;
+  const SplitBuf* split = nullptr; // split output
+  int elu_split = 0;
+  const float* bias = nullptr;
+  const float* scale = nullptr;
+  int act = 0;
+};
+
+static int tc_gemm(TcCtx& c, int slot, const SplitBuf& a, int k, int s, int pad, const TcWeight& w, const TcOut& o, int prof_id) {
+  const CUtensorMap *ahi, *alo;
+  int rc;
+  if (slot < 0 || slot >= kTcSlots) return fail(c.h, MIMI_B200_ERR_ARG, "tc: bad map slot");
+  if ((rc = tc_amaps(c, slot, a, k, s, pad, &ahi, &alo))) return rc;
+  if (w.K != k * a.C) return fail(c.h, MIMI_B200_ERR_ARG, "tc: weight K mismatch");
+  tc::Epilogue ep{};
+  ep.bias = o.bias; ep.scale = o.scale; ep.res = o.res; ep.out_raw = o.raw; ep.raw_item_stride = o.raw_item_stride;
+  if (o.split) {
+    if (o.split->C != w.N) return fail(c.h, MIMI_B200_ERR_ARG, "tc: split output width mismatch");
+    ep.out_hi = c.ws + o.split->hi; ep.out_lo = c.ws + o.split->lo;
+    ep.split_item_stride = o.split->item_stride; ep.split_front = o.split->front;
+  }
+  ep.act = o.act; ep.elu_split = o.elu_split;
+  ep.len_in = c.dlen[a.level]; ep.uniform_len_in = c.maxlen[a.level]; ep.conv_stride = s; ep.N = w.N;
+  const int lout_max = (c.maxlen[a.level] + s - 1) / s;
+  if (lout_max <= 0) return MIMI_B200_OK;
+  dim3 grid((lout_max + tc::kBM - 1) / tc::kBM, w.N / w.BN, c.B);
+  if (w.BN == 128)
+    tc::tc_gemm_kernel<128><<<grid, tc::kThreads, tc::smem_bytes(128), c.st>>>(*ahi, *alo, w.map_hi, w.map_lo, w.K, ep);
+  else
+    tc::tc_gemm_kernel<64><<<grid, tc::kThreads, tc::smem_bytes(64), c.st>>>(*ahi, *alo, w.map_hi, w.map_lo, w.K, ep);
+  c.h->launches++;
+  mark(c.h, prof_id, c.st);
+  CUDA_TRY(c.h, cudaGetLastError());
+  return MIMI_B200_OK;
+}
+
+static int tc_zero_halo(TcCtx& c, const SplitBuf& s) {
+  if (s.front + s.back == 0 || c.B == 0) return MIMI_B200_OK;
+  const int per = (s.front + s.back) * s.C;
+  dim3 grid((per + 255) / 256, c.B);
+  tc::zero_halo_kernel<<<grid, 256, 0, c.st>>>(c.ws + s.hi, c.ws + s.lo, s.item_stride, s.C, s.front, s.back,
+                                               c.dlen[s.level], c.maxlen[s.level]);
+  c.h->launches++;
+  mark(c.h, 25, c.st);
+  return MIMI_B200_OK;
+}
+
+// The encode pipeline with the wide layers on tensor cores. Same contract as the SIMT pipeline.
+static int encode_tc(mimi_b200* h, const float* d_input, int B, long long N, int K, const PlanTC& p, float* ws,
+                     const int* const* dlen, const int* maxlen, const int* dprefix, int total_frames,
+                     int64_t* d_codes, float* d_latent_opt, cudaStream_t st) {
+  int rc;
+  const MapKey key{ws, B, N};
+  auto it = h->amap_cache.find(key);
+  TcCtx c{h, &p, ws, B, st, dlen, maxlen, nullptr, nullptr};
+  if (it == h->amap_cache.end()) {
+    if (h->amap_cache.size() >= 64) h->amap_cache.clear();
+    it = h->amap_cache.emplace(key, MapSet()).first;
+    it->second.maps.resize(2 * kTcSlots);
+  }
+  c.maps = &it->second.maps;
+  c.built = &it->second.built;
+  auto rstride = [&](int level, int C) { return (long long)p.rows[level] * C; };
+
+  // halo rows of every conv-consumed split buffer (producers only ever write rows [0, L))
+  const SplitBuf* halos[] = {&p.s_h1, &p.s_d1, &p.s_h2, &p.s_d2, &p.s_h3, &p.s_d3, &p.s_h4, &p.s_d4};
+  for (const SplitBuf* s : halos)
+    if ((rc = tc_zero_halo(c, *s))) return rc;
+
+  // ---- level 0 on CUDA cores: L0 (1->64 k7), R1a (64->32 k3), R1b (32->64 k1 + skip) ---------------------
+  if (maxlen[0] > 0) {
+    dim3 grid((maxlen[0] + 127) / 128, B);
+    conv0_kernel<<<grid, 256, 0, st>>>(d_input, N, h->conv_wt[0], h->conv_b[0], ws + p.a0, rstride(0, 64), dlen[0], maxlen[0]);
+    h->launches++; mark(h, 0, st);
+    CUDA_TRY(h, cudaGetLastError());
+  }
+  {
+    GemmParams g{};
+    g.A = ws + p.a0; g.Wt = h->conv_wt[1]; g.bias = h->conv_b[1]; g.out = ws + p.r1;
+    g.len_in = dlen[0]; g.uniform_len_in = maxlen[0]; g.a_item_stride = rstride(0, 64); g.out_item_stride = rstride(0, 32);
+    g.Cin = 64; g.stride = 1; g.pad_left = 2; g.K = 192; g.N = 32; g.elu_in = 1;
+    if ((rc = launch_gemm(h, g, B, maxlen[0], st, 1))) return rc;
+    g = GemmParams{};
+    g.A = ws + p.r1; g.Wt = h->conv_wt[2]; g.bias = h->conv_b[2]; g.res = ws + p.a0; g.out = nullptr;
+    g.len_in = dlen[0]; g.uniform_len_in = maxlen[0]; g.a_item_stride = rstride(0, 32); g.out_item_stride = rstride(0, 64);
+    g.Cin = 32; g.stride = 1; g.pad_left = 0; g.K = 32; g.N = 64; g.elu_in = 1;
+    g.out_hi = ws + p.s_h1.hi; g.out_lo = ws + p.s_h1.lo; g.split_item_stride = p.s_h1.item_stride;
+    g.split_front = p.s_h1.front; g.elu_split = 1;
+    if ((rc = launch_gemm(h, g, B, maxlen[0], st, 2))) return rc;
+  }
+  // ---- D1 .. R4b on tensor cores ----------------------------------------------------------------------------
+  struct Lvl { const SplitBuf* in; long long d_raw; const SplitBuf *s_d, *s_r, *s_h; int C; };   // C = channels after the down conv
+  const Lvl lv[3] = {{&p.s_h1, p.d1, &p.s_d1, &p.s_r2, &p.s_h2, 128},
+                     {&p.s_h2, p.d2, &p.s_d2, &p.s_r3, &p.s_h3, 256},
+                     {&p.s_h3, p.d3, &p.s_d3, &p.s_r4, &p.s_h4, 512}};
+  for (int s = 0; s < 3; ++s) {
+    const Lvl& L = lv[s];
+    const int id = 3 + 3 * s, ia = 4 + 3 * s, ib = 5 + 3 * s;
+    const ConvGeom& gd = kConv[id];
+    TcOut o;   // down conv: raw (skip) + ELU'd split (resblock conv a)
+    o.raw = ws + L.d_raw; o.raw_item_stride = rstride(s + 1, L.C); o.split = L.s_d; o.elu_split = 1; o.bias = h->conv_b[id];
+    if ((rc = tc_gemm(c, id, *L.in, gd.k, gd.stride, gd.k - gd.stride, h->tc_conv[id], o, id))) return rc;
+    o = TcOut{};   // resblock conv a: C -> C/2, k3
+    o.split = L.s_r; o.elu_split = 1; o.bias = h->conv_b[ia];
+    if ((rc = tc_gemm(c, ia, *L.s_d, 3, 1, 2, h->tc_conv[ia], o, ia))) return rc;
+    o = TcOut{};   // resblock conv b: C/2 -> C, k1, + skip; only ELU(h) is needed downstream
+    o.res = ws + L.d_raw; o.raw_item_stride = rstride(s + 1, L.C); o.split = L.s_h; o.elu_split = 1; o.bias = h->conv_b[ib];
+    if ((rc = tc_gemm(c, ib, *L.s_r, 1, 1, 0, h->tc_conv[ib], o, ib))) return rc;
+  }
+  {
+    TcOut o;   // D4: 512 -> 1024, k16 s8
+    o.split = &p.s_d4; o.elu_split = 1; o.bias = h->conv_b[12];
+    if ((rc = tc_gemm(c, 12, p.s_h4, 16, 8, 8, h->tc_conv[12], o, 12))) return rc;
+    o = TcOut{};   // F: 1024 -> 512, k3 -> transformer stream z (raw)
+    o.raw = ws + p.z; o.raw_item_stride = rstride(4, 512); o.bias = h->conv_b[13];
+    if ((rc = tc_gemm(c, 13, p.s_d4, 3, 1, 2, h->tc_conv[13], o, 13))) return rc;
+  }
+  // ---- encoder transformer -------------------------------------------------------------------------------------
+  const int T25 = maxlen[4];
+  for (int l = 0; l < h->dbg_layers && T25 > 0; ++l) {
+    const LayerDev& d = h->layer[l];
+    dim3 lgrid((T25 + 7) / 8, B);
+    layernorm512_kernel<<<lgrid, 256, 0, st>>>(ws + p.z, ws + p.s_y.hi, d.ln1_w, d.ln1_b, rstride(4, 512), dlen[4], T25, ws + p.s_y.lo);
+    h->launches++; mark(h, 14, st);
+    TcOut o;
+    o.raw = ws + p.qkv; o.raw_item_stride = rstride(4, 1536);
+    if ((rc = tc_gemm(c, 0, p.s_y, 1, 1, 0, h->tc_qkv[l], o, 15))) return rc;
+    dim3 agrid((T25 + kAttQT - 1) / kAttQT, kHeads, B);
+    swa_attention_kernel<<<agrid, 256, kAttSmemBytes, st>>>(ws + p.qkv, rstride(4, 1536), ws + p.s_att.hi, rstride(4, 512),
+                                                            h->rope_cos, h->rope_sin, dlen[4], T25, ws + p.s_att.lo);
+    h->launches++; mark(h, 16, st);
+    CUDA_TRY(h, cudaGetLastError());
+    o = TcOut{};   // o_proj + LayerScale + residual, in place on z
+    o.raw = ws + p.z; o.res = ws + p.z; o.raw_item_stride = rstride(4, 512); o.scale = d.ls1;
+    if ((rc = tc_gemm(c, 1, p.s_att, 1, 1, 0, h->tc_o[l], o, 17))) return rc;
+    layernorm512_kernel<<<lgrid, 256, 0, st>>>(ws + p.z, ws + p.s_y.hi, d.ln2_w, d.ln2_b, rstride(4, 512), dlen[4], T25, ws + p.s_y.lo);
+    h->launches++; mark(h, 14, st);
+    o = TcOut{};   // fc1 + GELU(erf) -> split
+    o.split = &p.s_ffn; o.act = 1;
+    if ((rc = tc_gemm(c, 0, p.s_y, 1, 1, 0, h->tc_fc1[l], o, 18))) return rc;
+    o = TcOut{};   // fc2 + LayerScale + residual, in place on z
+    o.raw = ws + p.z; o.res = ws + p.z; o.raw_item_stride = rstride(4, 512); o.scale = d.ls2;
+    if ((rc = tc_gemm(c, 2, p.s_ffn, 1, 1, 0, h->tc_fc2[l], o, 19))) return rc;
+  }
+  // ---- stride-2 downsample (replicate pad materialised as 3 extra rows), RVQ input projections ------------------
+  const int T = maxlen[5];
+  if (T25 > 0) {
+    dim3 pgrid((T25 + 3 + 7) / 8, B);
+    tc::pad_replicate_split_kernel<<<pgrid, 256, 0, st>>>(ws + p.z, rstride(4, 512), ws + p.s_zp.hi, ws + p.s_zp.lo,
+                                                          p.s_zp.item_stride, dlen[4], T25);
+    h->launches++; mark(h, 26, st);
+    TcOut o;
+    o.raw = ws + p.e; o.raw_item_stride = rstride(5, 512); o.split = &p.s_e;
+    // the downsample conv reads s_zp rows 2j .. 2j+3: k=4, stride 2, no further padding. Lout must come from
+    // the T25 lengths (ceil(T25/2)), which is what tc_gemm derives from level-4 lengths with s = 2.
+    if ((rc = tc_gemm(c, 14, p.s_zp, 4, 2, 0, h->tc_down, o, 20))) return rc;
+  }
+  if (d_latent_opt && T > 0) {
+    const long long n = (long long)kHidden * p.rows[5];
+    dim3 tgrid((unsigned)((n + 255) / 256), B);
+    latent_transpose_kernel<<<tgrid, 256, 0, st>>>(ws + p.e, rstride(5, 512), d_latent_opt, p.rows[5], dlen[5], T);
+    h->launches++; mark(h, 23, st);
+  }
+  if (T > 0) {
+    TcOut o;
+    o.raw = ws + p.rp; o.raw_item_stride = rstride(5, 512);
+    if ((rc = tc_gemm(c, 15, p.s_e, 1, 1, 0, h->tc_proj, o, 21))) return rc;
+    RvqParams r{};
+    r.rproj = ws + p.rp; r.item_stride = rstride(5, 512);
+    r.embed = h->embed; r.embed_t = h->embed_t; r.enorm = h->enorm;
+    r.codes = reinterpret_cast<long long*>(d_codes); r.K = K; r.T_out = p.rows[5];
+    r.len = dlen[5]; r.uniform_len = T; r.B = B; r.total_frames = total_frames; r.frame_prefix = dprefix;
+    if (total_frames > 0) {
+      rvq_encode_kernel<<<(total_frames + kRvqFM - 1) / kRvqFM, 256, kRvqSmemBytes, st>>>(r);
+      h->launches++; mark(h, 22, st);
+    }
+  }
+  CUDA_TRY(h, cudaGetLastError());
+  return MIMI_B200_OK;
+}

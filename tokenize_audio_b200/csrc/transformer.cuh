@@ -11,7 +11,8 @@ __global__ void __launch_bounds__(256) layernorm512_kernel(const float* __restri
                                                            const float* __restrict__ gamma,
                                                            const float* __restrict__ beta,
                                                            long long item_stride, const int* __restrict__ len,
-                                                           int uniform_len) {
+                                                           int uniform_len, float* __restrict__ y_lo) {
+  // y_lo != nullptr: write the hi/lo TF32 split of the result into (y, y_lo) for a tensor-core consumer
   const int b = blockIdx.y;
   const int L = len ? len[b] : uniform_len;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -43,7 +44,8 @@ __global__ void __launch_bounds__(256) layernorm512_kernel(const float* __restri
     o.y = v[i].y * rstd * g.y + bt.y;
     o.z = v[i].z * rstd * g.z + bt.z;
     o.w = v[i].w * rstd * g.w + bt.w;
-    *reinterpret_cast<float4*>(yr + c) = o;
+    if (y_lo) store_split4(yr + c, y_lo + (long long)b * item_stride + (long long)t * kHidden + c, o);
+    else *reinterpret_cast<float4*>(yr + c) = o;
   }
 }
 
@@ -64,7 +66,9 @@ __global__ void __launch_bounds__(256) swa_attention_kernel(const float* __restr
                                                             float* __restrict__ out, long long out_stride,
                                                             const float* __restrict__ rope_cos,
                                                             const float* __restrict__ rope_sin,
-                                                            const int* __restrict__ len, int uniform_len) {
+                                                            const int* __restrict__ len, int uniform_len,
+                                                            float* __restrict__ out_lo) {
+  // out_lo != nullptr: (out, out_lo) receive the hi/lo TF32 split of the result
   extern __shared__ __align__(16) float smem[];
   float* Vs = smem;                                  // [281][64]  (float4 stores: 16-byte aligned)
   float* Qs = Vs + kAttKeys * kHeadDim;              // [32][64]
@@ -167,8 +171,15 @@ __global__ void __launch_bounds__(256) swa_attention_kernel(const float* __restr
       o1 = fmaf(pj, vr[lane + 32], o1);
     }
     float* orow = out + (long long)b * out_stride + (long long)i * kHidden + h * kHeadDim;
-    orow[lane] = o0;
-    orow[lane + 32] = o1;
+    if (out_lo) {
+      float* lrow = out_lo + (long long)b * out_stride + (long long)i * kHidden + h * kHeadDim;
+      float hi, lo;
+      split_tf32(o0, hi, lo); orow[lane] = hi; lrow[lane] = lo;
+      split_tf32(o1, hi, lo); orow[lane + 32] = hi; lrow[lane + 32] = lo;
+    } else {
+      orow[lane] = o0;
+      orow[lane + 32] = o1;
+    }
     __syncwarp();
   }
 }

@@ -247,7 +247,11 @@ class MimiB200Model:
 
     LAUNCH_KINDS = (["conv0"] + [f"seanet_conv{i}" for i in range(1, 14)] +
                     ["layernorm", "qkv_gemm", "attention", "o_proj", "fc1_gelu", "fc2", "downsample_conv",
-                     "rvq_input_proj", "rvq_fused", "latent_transpose", "code_fill"])
+                     "rvq_input_proj", "rvq_fused", "latent_transpose", "code_fill", "halo_zero", "pad_split"])
+
+    def set_mode(self, tensor_cores: bool) -> None:
+        """True (default): wide layers on tcgen05 3xTF32 tensor cores; False: all-fp32 FFMA path."""
+        self.debug_set(3, 1 if tensor_cores else 0)
 
     def profile(self, on: bool) -> None:
         """Switch per-launch CUDA-event profiling on/off (resets the counters)."""

@@ -28,6 +28,40 @@ def main():
     taps, margins = {}, []
     codes_o = O.encode(sd, x, 32, taps=taps, margins=margins)
     xd = torch.from_numpy(x).cuda()
+    if "--tc" in sys.argv:
+        # tensor-core path: raw taps that exist there (down convs 3/6/9, stream z), then the tail
+        m.set_mode(True)
+        m.debug_set(0, 0)
+        m.encode(xd, num_quantizers=32)
+        torch.cuda.synchronize()
+        for ci, nm in {0: "seanet.l0", 3: "seanet.down3", 6: "seanet.down6", 9: "seanet.down9", 13: "seanet.out"}.items():
+            t = m.debug_tap(ci).cpu().numpy()
+            ref = np.stack([a.T for a in taps[nm]])
+            t = t[:, : ref.shape[1]]
+            print(f"[tc] conv {ci:2d} {nm:14s} rel {rel(t, ref):.3e} maxabs {np.abs(t - ref).max():.3e} shape {t.shape}", flush=True)
+        for l in range(8):
+            m.debug_set(0, l + 1)
+            m.encode(xd, num_quantizers=32)
+            torch.cuda.synchronize()
+            t = m.debug_tap(100 + l).cpu().numpy()
+            ref = np.stack(taps[f"transformer.layer{l}"])
+            print(f"[tc] transformer layer {l} rel {rel(t[:, :ref.shape[1]], ref):.3e}", flush=True)
+        m.debug_set(0, 8)
+        out, lat = m.encode(xd, num_quantizers=32, return_latent=True)
+        torch.cuda.synchronize()
+        lat = lat.cpu().numpy()
+        ref = np.stack(taps["latent"])
+        print(f"[tc] latent rel {rel(lat, ref):.3e} maxabs {np.abs(lat - ref).max():.3e}")
+        codes = out.audio_codes.cpu().numpy()
+        agree = codes == codes_o
+        print("[tc] codes agree all %.5f first8 %.5f" % (agree.mean(), agree[:, :8].mean()))
+        print("[tc] per-codebook", np.round(agree.mean(axis=(0, 2)), 3))
+        mg = np.stack(margins).reshape(2, 32, -1)
+        for b, k, t in np.argwhere(~agree)[:20]:
+            print("  mismatch item %d cb %d frame %d: gpu %d oracle %d  oracle top-2 rel margin %.2e" %
+                  (b, k, t, codes[b, k, t], codes_o[b, k, t], mg[b, k, t]))
+        return
+    m.set_mode(False)
     # SEANet taps: run with the pipeline stopped after each conv so in-place buffers hold that conv's output
     names = {0: "seanet.l0", 2: "seanet.res1", 3: "seanet.down3", 5: "seanet.res4", 6: "seanet.down6",
              8: "seanet.res7", 9: "seanet.down9", 11: "seanet.res10", 12: "seanet.down12", 13: "seanet.out"}
