@@ -129,7 +129,8 @@ int mimi_b200_debug_tap(mimi_b200_t* h, int which, float* d_out, size_t out_capa
 /* Debug knobs (parity bisection only): key 0 = number of transformer layers to run (default 8),
    key 1 = index of the last SEANet conv to run (default 13; smaller values stop the pipeline there and
    leave d_codes untouched), key 2 = per-launch CUDA-event profiling on/off (resets the profile), key 3 =
-   compute mode: 1 (default) wide layers on tcgen05 3xTF32 tensor cores, 0 all-fp32 FFMA. */
+   compute mode: 2 (default) every GEMM-shaped layer on the persistent tcgen05 3xTF32 kernel (tc_gemm2.cuh),
+   1 = first-generation tcgen05 kernel for the wide layers (level 0 on FFMA), 0 = all-fp32 FFMA. */
 int mimi_b200_debug_set(mimi_b200_t* h, int key, int value);
 
 /* Read and reset the per-launch profile gathered since profiling was switched on: for launch kind
@@ -140,10 +141,18 @@ int mimi_b200_debug_set(mimi_b200_t* h, int key, int value);
 int mimi_b200_profile_read(mimi_b200_t* h, int max_ids, double* sum_ms, int64_t* count);
 
 /* Unit-test hook for the tensor-core GEMM kernel: d_out[M][N] = act(d_a[M][K] * h_w[N][K]^T + bias) through the
-   encoder's own TF32 hi/lo split + TMA + tcgen05 path (N % 64 == 0, K % 32 == 0; act 1 = GELU(erf)).
-   Synchronises the stream. */
+   encoder's own TF32 hi/lo split + TMA + tcgen05 path (N % 32 == 0 in mode 2, N % 64 == 0 in mode 1;
+   K % 32 == 0; act 1 = GELU(erf)). Uses the kernel generation selected by debug_set key 3. Synchronises
+   the stream. */
 int mimi_b200_debug_tc_gemm(mimi_b200_t* h, const float* d_a, const float* h_w, const float* d_bias_opt, int M,
                             int N, int K, int act, float* d_out, void* stream);
+
+/* Hardware probe (unit test only): one 128 x 64 single-pass TF32 tile whose SWIZZLE_128B A-operand
+   descriptor starts `shift` rows (0..8) into the staged tile: d_out[m][n] = sum_k d_a[m + shift][k] * h_w[n][k].
+   d_a has 136 rows of K floats (K % 32 == 0), h_w 64 rows. base_mode 1 also sets the descriptor's
+   base-offset field to (start >> 7) & 7. Synchronises the stream. */
+int mimi_b200_debug_shift_probe(mimi_b200_t* h, const float* d_a, const float* h_w, int K, int shift, int base_mode,
+                                float* d_out, void* stream);
 
 /* Output length of the resampler for n input samples: ceil(n * sr_out / sr_in) (librosa fix=True). */
 int64_t mimi_b200_resample_out_len(int64_t n_in, int sr_in, int sr_out);

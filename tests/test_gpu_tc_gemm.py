@@ -20,12 +20,17 @@ def engine():
     lib.mimi_b200_destroy(h)
 
 
+@pytest.mark.parametrize("mode", [2, 1])
 @pytest.mark.parametrize("M,N,K,act,bias", [
     (128, 128, 32, 0, False), (300, 128, 512, 0, True), (77, 64, 384, 0, True), (1000, 256, 1280, 0, False),
     (60, 2048, 512, 1, False), (130, 512, 2048, 0, True), (257, 1024, 8192, 0, True), (64, 1536, 512, 0, False),
+    (40000, 128, 64, 0, True), (25000, 64, 96, 0, False), (30000, 32, 192, 0, True), (129, 32, 32, 1, True),
 ])
-def test_tc_gemm_matches_float64(engine, M, N, K, act, bias):
+def test_tc_gemm_matches_float64(engine, M, N, K, act, bias, mode):
     lib, h = engine
+    if mode == 1 and N % 64:
+        pytest.skip("first-generation kernel has no BN=32 instance")
+    _lib.check(lib, h, lib.mimi_b200_debug_set(h, 3, mode), "debug_set")
     g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
     a = torch.randn(M, K, generator=g) * 2.0
     w = torch.randn(N, K, generator=g) / K ** 0.5

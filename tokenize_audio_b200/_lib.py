@@ -50,6 +50,7 @@ SYMBOLS = {
     "mimi_b200_profile_read": (C.c_int, [c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "mimi_b200_debug_tc_gemm": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                           c_void_p, c_void_p]),
+    "mimi_b200_debug_shift_probe": (C.c_int, [c_void_p, c_void_p, c_void_p, C.c_int, C.c_int, C.c_int, c_void_p, c_void_p]),
     "mimi_b200_resample_out_len": (C.c_int64, [C.c_int64, C.c_int, C.c_int]),
     "mimi_b200_resample": (C.c_int, [c_void_p, c_void_p, C.c_int64, c_void_p, C.c_int, C.c_int, C.c_int,
                                      c_void_p, C.c_int64, c_void_p]),

@@ -198,7 +198,11 @@ __global__ void __launch_bounds__(256) conv0_kernel(const float* __restrict__ x,
                                                     const float* __restrict__ w,     // [64][7]
                                                     const float* __restrict__ bias,  // [64]
                                                     float* __restrict__ out, long long out_item_stride,
-                                                    const int* __restrict__ len_in, int uniform_len) {
+                                                    const int* __restrict__ len_in, int uniform_len,
+                                                    float* __restrict__ out_hi, float* __restrict__ out_lo,
+                                                    long long split_item_stride, int split_front) {
+  // out_hi != nullptr: also write the TF32 hi/lo split of ELU(out) (the input of ResBlock-1's first conv) at
+  // row split_front + t of the halo'd split buffers
   constexpr int TT = 128;                     // time steps per CTA
   __shared__ float xs[TT + 6];
   const int b = blockIdx.y;
@@ -234,8 +238,13 @@ __global__ void __launch_bounds__(256) conv0_kernel(const float* __restrict__ x,
 #pragma unroll
       for (int c = 0; c < 4; ++c) v[c] = fmaf(wr[c][k], xv, v[c]);
     }
-    *reinterpret_cast<float4*>(ob + (long long)t * 64 + cg * 4) =
-        make_float4(v[0] + br[0], v[1] + br[1], v[2] + br[2], v[3] + br[3]);
+    float4 o = make_float4(v[0] + br[0], v[1] + br[1], v[2] + br[2], v[3] + br[3]);
+    *reinterpret_cast<float4*>(ob + (long long)t * 64 + cg * 4) = o;
+    if (out_hi) {
+      o.x = elu1(o.x); o.y = elu1(o.y); o.z = elu1(o.z); o.w = elu1(o.w);
+      const long long so = (long long)b * split_item_stride + (long long)(split_front + t) * 64 + cg * 4;
+      store_split4(out_hi + so, out_lo + so, o);
+    }
   }
 }
 

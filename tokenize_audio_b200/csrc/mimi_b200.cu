@@ -20,6 +20,7 @@
 #include "io_kernels.cuh"
 #include "rvq.cuh"
 #include "tc_gemm.cuh"
+#include "tc_gemm2.cuh"
 #include "transformer.cuh"
 
 using namespace mimi;
@@ -70,6 +71,7 @@ struct PlanTC {
   long long N = 0;
   int rows[6] = {0, 0, 0, 0, 0, 0};
   long long a0, r1, d1, d2, d3, z, qkv, e, rp;                 // raw fp32 buffers (float offsets)
+  SplitBuf s_a0, s_r1;                                         // mode 2: level 0 on tensor cores too
   SplitBuf s_h1, s_d1, s_r2, s_h2, s_d2, s_r3, s_h3, s_d3, s_r4, s_h4, s_d4, s_y, s_att, s_ffn, s_zp, s_e;
   long long ints;
   size_t bytes = 0;
@@ -128,9 +130,11 @@ struct mimi_b200 {
   Plan last;
   void* last_ws = nullptr;
   // tensor-core path
-  int mode = 1;                                // 1 = tcgen05 3xTF32 for the wide layers, 0 = all-fp32 SIMT
+  int mode = 2;                                // 2 = persistent tcgen05 3xTF32 kernel for every GEMM-shaped layer,
+                                               // 1 = first-generation tcgen05 kernel (level 0 on FFMA), 0 = all-fp32 SIMT
+  int num_sms = 148;
   PFN_cuTensorMapEncodeTiled_v12000 encode_tiled = nullptr;
-  TcWeight tc_conv[MIMI_B200_NUM_CONVS];       // convs 3..13 (0..2 stay SIMT)
+  TcWeight tc_conv[MIMI_B200_NUM_CONVS];       // convs 1..13 (conv 0 is a direct SIMT conv)
   TcWeight tc_qkv[MIMI_B200_NUM_LAYERS], tc_o[MIMI_B200_NUM_LAYERS], tc_fc1[MIMI_B200_NUM_LAYERS], tc_fc2[MIMI_B200_NUM_LAYERS];
   TcWeight tc_down, tc_proj;
   std::map<MapKey, MapSet> amap_cache;   // activation maps per (workspace, B, N)
@@ -348,6 +352,7 @@ int mimi_b200_create(mimi_b200_t** out, int device_ordinal) {
     return fail(nullptr, MIMI_B200_ERR_CUDA, "create: this library is built for sm_100a (B200) only");
   mimi_b200* h = new mimi_b200();
   h->device = device_ordinal;
+  h->num_sms = prop.multiProcessorCount;
   h->sync_debug = getenv("MIMI_B200_SYNC") != nullptr;
   if ((e = cudaSetDevice(device_ordinal)) != cudaSuccess) { delete h; return fail(nullptr, MIMI_B200_ERR_CUDA, cudaGetErrorString(e)); }
   for (int i = 0; i < kStageSlots; ++i) cudaEventCreateWithFlags(&h->stage_ev[i], cudaEventDisableTiming);
@@ -355,6 +360,10 @@ int mimi_b200_create(mimi_b200_t** out, int device_ordinal) {
   cudaFuncSetAttribute(rvq_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRvqSmemBytes);
   cudaFuncSetAttribute(tc::tc_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::smem_bytes(128));
   cudaFuncSetAttribute(tc::tc_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::smem_bytes(64));
+  cudaFuncSetAttribute(tc2::tc2_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::Cfg<128>::SMEM);
+  cudaFuncSetAttribute(tc2::tc2_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::Cfg<64>::SMEM);
+  cudaFuncSetAttribute(tc2::tc2_gemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::Cfg<32>::SMEM);
+  cudaFuncSetAttribute(tc2::tc_shift_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 40960);
   if ((e = cudaGetLastError()) != cudaSuccess) { delete h; return fail(nullptr, MIMI_B200_ERR_CUDA, cudaGetErrorString(e)); }
   *out = h;
   return MIMI_B200_OK;
@@ -380,7 +389,7 @@ int mimi_b200_debug_set(mimi_b200_t* h, int key, int value) {
   if (key == 0) h->dbg_layers = std::min(std::max(value, 0), MIMI_B200_NUM_LAYERS);
   else if (key == 1) h->dbg_last_conv = std::min(std::max(value, 0), MIMI_B200_NUM_CONVS - 1);
   else if (key == 2) { h->prof_on = value != 0; h->prof_n = 0; }
-  else if (key == 3) h->mode = value ? 1 : 0;
+  else if (key == 3) h->mode = std::min(std::max(value, 0), 2);
   else return fail(h, MIMI_B200_ERR_ARG, "debug_set: unknown key");
   return MIMI_B200_OK;
 }
@@ -522,7 +531,7 @@ int mimi_b200_encode(mimi_b200_t* h, const float* d_input, int B, int64_t N, con
   CUDA_TRY(h, cudaSetDevice(h->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 
-  const bool use_tc = h->mode == 1 && h->dbg_last_conv == MIMI_B200_NUM_CONVS - 1;
+  const bool use_tc = h->mode >= 1 && h->dbg_last_conv == MIMI_B200_NUM_CONVS - 1;
   const Plan p = make_plan(B, N, K);
   const PlanTC pt = make_plan_tc(B, N, K);
   const size_t need = use_tc ? pt.bytes : p.bytes;
@@ -586,7 +595,8 @@ int mimi_b200_encode(mimi_b200_t* h, const float* d_input, int B, int64_t N, con
   {
     dim3 grid((maxlen[0] + 127) / 128, B);
     if (maxlen[0] > 0) {
-      conv0_kernel<<<grid, 256, 0, st>>>(d_input, N, h->conv_wt[0], h->conv_b[0], ws + p.a0, istride(0, 64), dlen[0], maxlen[0]);
+      conv0_kernel<<<grid, 256, 0, st>>>(d_input, N, h->conv_wt[0], h->conv_b[0], ws + p.a0, istride(0, 64), dlen[0], maxlen[0],
+                                         nullptr, nullptr, 0, 0);
       h->launches++; mark(h, 0, st);
       CUDA_TRY(h, cudaGetLastError());
     }
@@ -764,7 +774,8 @@ __global__ void debug_split_kernel(const float* __restrict__ x, float* __restric
 int mimi_b200_debug_tc_gemm(mimi_b200_t* h, const float* d_a, const float* h_w, const float* d_bias_opt, int M, int N,
                             int K, int act, float* d_out, void* stream) {
   if (!h || !d_a || !h_w || !d_out) return fail(h, MIMI_B200_ERR_ARG, "debug_tc_gemm: NULL argument");
-  if (M <= 0 || N % 64 || K % 32) return fail(h, MIMI_B200_ERR_ARG, "debug_tc_gemm: need N % 64 == 0 and K % 32 == 0");
+  if (M <= 0 || N % 32 || K % 32 || (h->mode != 2 && N % 64))
+    return fail(h, MIMI_B200_ERR_ARG, "debug_tc_gemm: need N % 32 == 0 (mode 2) / N % 64 == 0 (mode 1) and K % 32 == 0");
   CUDA_TRY(h, cudaSetDevice(h->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int rc;
@@ -784,14 +795,44 @@ int mimi_b200_debug_tc_gemm(mimi_b200_t* h, const float* d_a, const float* h_w, 
   tc::Epilogue ep{};
   ep.bias = d_bias_opt; ep.out_raw = d_out; ep.raw_item_stride = (long long)M * N; ep.act = act;
   ep.uniform_len_in = M; ep.conv_stride = 1; ep.N = N;
-  dim3 grid((M + tc::kBM - 1) / tc::kBM, N / w.BN, 1);
-  if (w.BN == 128) tc::tc_gemm_kernel<128><<<grid, tc::kThreads, tc::smem_bytes(128), st>>>(ma_hi, ma_lo, w.map_hi, w.map_lo, K, ep);
-  else tc::tc_gemm_kernel<64><<<grid, tc::kThreads, tc::smem_bytes(64), st>>>(ma_hi, ma_lo, w.map_hi, w.map_lo, K, ep);
+  if (h->mode == 2) {
+    launch_tc2(h, ma_hi, ma_lo, w, ep, 1, (M + tc::kBM - 1) / tc::kBM, st);
+  } else {
+    dim3 grid((M + tc::kBM - 1) / tc::kBM, N / w.BN, 1);
+    if (w.BN == 128) tc::tc_gemm_kernel<128><<<grid, tc::kThreads, tc::smem_bytes(128), st>>>(ma_hi, ma_lo, w.map_hi, w.map_lo, K, ep);
+    else if (w.BN == 64) tc::tc_gemm_kernel<64><<<grid, tc::kThreads, tc::smem_bytes(64), st>>>(ma_hi, ma_lo, w.map_hi, w.map_lo, K, ep);
+    else return fail(h, MIMI_B200_ERR_ARG, "debug_tc_gemm: mode 1 has no BN=32 kernel");
+  }
   h->launches += 2;
   cudaError_t e = cudaStreamSynchronize(st);
   cudaFree(hi);
   cudaFree(lo);
   if (e != cudaSuccess) return fail(h, MIMI_B200_ERR_CUDA, std::string("debug_tc_gemm: ") + cudaGetErrorString(e));
+  return MIMI_B200_OK;
+}
+
+int mimi_b200_debug_shift_probe(mimi_b200_t* h, const float* d_a, const float* h_w, int K, int shift, int base_mode,
+                                float* d_out, void* stream) {
+  if (!h || !d_a || !h_w || !d_out) return fail(h, MIMI_B200_ERR_ARG, "debug_shift_probe: NULL argument");
+  if (K <= 0 || K % 32 || shift < 0 || shift > 8) return fail(h, MIMI_B200_ERR_ARG, "debug_shift_probe: bad K / shift");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc;
+  if ((rc = tc_init_driver(h))) return rc;
+  float* dw = nullptr;
+  CUDA_TRY(h, cudaMalloc((void**)&dw, (size_t)64 * K * sizeof(float)));
+  CUDA_TRY(h, cudaMemcpy(dw, h_w, (size_t)64 * K * sizeof(float), cudaMemcpyHostToDevice));
+  CUtensorMap ma, mw;
+  const cuuint64_t adims[2] = {(cuuint64_t)K, 136};
+  const cuuint64_t wdims[2] = {(cuuint64_t)K, 64};
+  const cuuint64_t strides[1] = {(cuuint64_t)K * sizeof(float)};
+  if ((rc = tc_make_map(h, &ma, d_a, 2, adims, strides, 136))) { cudaFree(dw); return rc; }
+  if ((rc = tc_make_map(h, &mw, dw, 2, wdims, strides, 64))) { cudaFree(dw); return rc; }
+  tc2::tc_shift_probe_kernel<<<1, 128, 40960, st>>>(ma, mw, K, shift, base_mode, d_out);
+  h->launches++;
+  cudaError_t e = cudaStreamSynchronize(st);
+  cudaFree(dw);
+  if (e != cudaSuccess) return fail(h, MIMI_B200_ERR_CUDA, std::string("debug_shift_probe: ") + cudaGetErrorString(e));
   return MIMI_B200_OK;
 }
 

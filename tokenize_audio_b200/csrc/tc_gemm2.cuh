@@ -1,0 +1,385 @@
+// tcgen05 implicit-GEMM, second generation: PERSISTENT, with the tile epilogue overlapped with the next
+// tile's main loop and coalesced global I/O. Same arithmetic as tc_gemm.cuh (3xTF32, chunked fp32
+// accumulation, separate accumulator for the two small cross terms), same operands (pre-split hi/lo
+// activations seen through overlapping-row TMA maps, pre-split K-major weights), same Epilogue contract.
+//
+//   grid   = min(#virtual tiles, #SMs) CTAs of 320 threads, one per SM, static round-robin over
+//            virtual tiles id -> (m-tile, item, n-tile); tiles past an item's length are skipped by all roles.
+//   warp 0 = TMA producer (runs ahead across tile boundaries through a 3..5-stage ring)
+//   warp 1 = TMEM owner + single-thread tcgen05.mma issuer
+//   warps 2..9 = epilogue: two warps per TMEM lane quarter, each owning half of the BN columns. They drain
+//            every K=128 chunk of hi*hi from TMEM (double-buffered) into fp32 registers (round-to-nearest
+//            adds), then the cross-term accumulator (double-buffered per tile parity), then finish the tile:
+//            bias / GELU / LayerScale per thread = per row, a 32-column transpose through a swizzled smem
+//            staging tile, and row-contiguous float4 residual loads and raw / hi / lo stores (128 B segments).
+//   TMEM   = main[2] | small[2], 4*BN columns (BN <= 128).
+#pragma once
+#include "tc_gemm.cuh"
+
+namespace mimi {
+namespace tc2 {
+
+using tc::Epilogue;
+using tc::kBK;
+using tc::kBM;
+using tc::kChunkKB;
+using tc::kUmmaK;
+
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 64 + 32 * kEpiWarps;       // 320
+constexpr int kSmemMax = 232448;                    // 227 KB opt-in limit per CTA
+
+struct Sched {
+  int B;            // items
+  int mt_max;       // m-tiles per item at the longest item
+  int ntn;          // n-tiles = N / BN
+};
+
+template <int BN>
+struct Cfg {
+  static constexpr int A_BYTES = kBM * kBK * 4;                      // 16 KB
+  static constexpr int W_BYTES = BN * kBK * 4;
+  static constexpr int STAGE = 2 * A_BYTES + 2 * W_BYTES;
+  static constexpr int PC = (BN / 2 >= 32) ? 32 : BN / 2;            // staging piece width (columns)
+  static constexpr int STG_WARP = 32 * PC * 4;                       // staging bytes per epilogue warp
+  static constexpr int STG = kEpiWarps * STG_WARP;
+  static constexpr int BAR_BYTES = 512;
+  static constexpr int STAGES_RAW = (kSmemMax - 1024 - STG - BAR_BYTES) / STAGE;
+  static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
+  static constexpr int SMEM = 1024 + STAGES * STAGE + STG + BAR_BYTES;
+  static constexpr int TMEM_COLS = (4 * BN <= 32) ? 32 : (4 * BN <= 64) ? 64 : (4 * BN <= 128) ? 128 : (4 * BN <= 256) ? 256 : 512;
+  static_assert(BN == 32 || BN == 64 || BN == 128, "BN");
+  static_assert(STAGES >= 3, "ring too shallow");
+};
+
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// acc[0 .. NCOL) += TMEM[taddr .. taddr + NCOL) for this thread's lane; two loads in flight
+template <int NCOL>
+__device__ __forceinline__ void drain_add(uint32_t taddr, float (&acc)[NCOL]) {
+  static_assert(NCOL % 16 == 0, "NCOL");
+  if constexpr (NCOL == 16) {
+    uint32_t r[16];
+    tmem_ld16_nowait(taddr, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] += __uint_as_float(r[i]);
+  } else {
+#pragma unroll
+    for (int c0 = 0; c0 < NCOL; c0 += 32) {
+      uint32_t r0[16], r1[16];
+      tmem_ld16_nowait(taddr + (uint32_t)c0, r0);
+      tmem_ld16_nowait(taddr + (uint32_t)c0 + 16u, r1);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc[c0 + i] += __uint_as_float(r0[i]);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc[c0 + 16 + i] += __uint_as_float(r1[i]);
+    }
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+tc2_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo, int K,
+                const Epilogue ep, const Sched sc) {
+  using C = Cfg<BN>;
+  constexpr int STAGES = C::STAGES;
+  constexpr int STAGE = C::STAGE;
+  constexpr int A_BYTES = C::A_BYTES;
+  constexpr int W_BYTES = C::W_BYTES;
+  constexpr int HALF = BN / 2;                     // columns per epilogue thread
+  constexpr int PC = C::PC;
+  constexpr int NP = HALF / PC;                    // staging pieces per tile
+  constexpr int LPR = PC / 4;                      // lanes (float4) per row in the coalesced phase
+  constexpr int RPI = 32 / LPR;                    // rows per warp instruction
+  constexpr int IT = 32 / RPI;                     // instructions per 32-row piece
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stg_base = smem + STAGES * STAGE;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg_base + C::STG);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* acc_full = empty_bar + STAGES;         // [2] main chunk ready        (MMA -> epilogue)
+  uint64_t* acc_empty = acc_full + 2;              // [2] main chunk drained      (epilogue -> MMA)
+  uint64_t* small_empty = acc_empty + 2;           // [2] cross-term acc drained  (epilogue -> MMA)
+  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(small_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb = K / kBK;
+  const int nchunks = (nkb + kChunkKB - 1) / kChunkKB;
+  const int vtiles = sc.mt_max * sc.B * sc.ntn;
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&tmA_hi); tc::prefetch_tmap(&tmA_lo); tc::prefetch_tmap(&tmW_hi); tc::prefetch_tmap(&tmW_lo);
+    for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) {
+      tc::mbar_init(&acc_full[s], 1);
+      tc::mbar_init(&acc_empty[s], kEpiWarps);
+      tc::mbar_init(&small_empty[s], kEpiWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(tmem_base_ptr)), "r"(C::TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_base_ptr;
+
+  // virtual tile id -> (n-tile, item, m-tile); returns false for tiles past the item's length
+  auto decode = [&](int id, int& b, int& m0, int& n0, int& Lout) {
+    const int nt = id % sc.ntn;
+    const int t = id / sc.ntn;
+    b = t % sc.B;
+    m0 = (t / sc.B) * kBM;
+    n0 = nt * BN;
+    const int Lin = ep.len_in ? __ldg(ep.len_in + b) : ep.uniform_len_in;
+    Lout = (Lin + ep.conv_stride - 1) / ep.conv_stride;
+    return m0 < Lout;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t kbc = 0;
+      for (int id = blockIdx.x; id < vtiles; id += gridDim.x) {
+        int b, m0, n0, Lout;
+        if (!decode(id, b, m0, n0, Lout)) continue;
+        for (int kb = 0; kb < nkb; ++kb, ++kbc) {
+          const uint32_t s = kbc % STAGES;
+          const uint32_t ph = (kbc / STAGES) & 1u;
+          tc::mbar_wait(&empty_bar[s], ph ^ 1u);
+          uint8_t* st = smem + s * STAGE;
+          tc::mbar_expect_tx(&full_bar[s], STAGE);
+          tc::tma_load_3d(st, &tmA_hi, &full_bar[s], kb * kBK, m0, b);
+          tc::tma_load_3d(st + A_BYTES, &tmA_lo, &full_bar[s], kb * kBK, m0, b);
+          tc::tma_load_2d(st + 2 * A_BYTES, &tmW_hi, &full_bar[s], kb * kBK, n0);
+          tc::tma_load_2d(st + 2 * A_BYTES + W_BYTES, &tmW_lo, &full_bar[s], kb * kBK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::make_idesc(kBM, BN);
+      uint32_t kbc = 0, cc = 0, lt = 0;
+      for (int id = blockIdx.x; id < vtiles; id += gridDim.x) {
+        int b, m0, n0, Lout;
+        if (!decode(id, b, m0, n0, Lout)) continue;
+        const uint32_t tp = lt & 1u;
+        tc::mbar_wait(&small_empty[tp], ((lt >> 1) & 1u) ^ 1u);          // cross-term acc of tile lt-2 drained
+        const uint32_t tmem_small = tmem_base + (2u + tp) * BN;
+        for (int c = 0; c < nchunks; ++c, ++cc) {
+          const uint32_t buf = cc & 1u;
+          tc::mbar_wait(&acc_empty[buf], ((cc >> 1) & 1u) ^ 1u);         // drained two chunks ago
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t tmem_main = tmem_base + buf * BN;
+          const int kb_end = min(nkb, (c + 1) * kChunkKB);
+          for (int kb = c * kChunkKB; kb < kb_end; ++kb, ++kbc) {
+            const uint32_t s = kbc % STAGES;
+            const uint32_t ph = (kbc / STAGES) & 1u;
+            tc::mbar_wait(&full_bar[s], ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a_hi = tc::smem_u32(smem + s * STAGE);
+            const uint32_t a_lo = a_hi + A_BYTES;
+            const uint32_t w_hi = a_hi + 2 * A_BYTES;
+            const uint32_t w_lo = w_hi + W_BYTES;
+            const bool first_in_chunk = kb == c * kChunkKB;
+#pragma unroll
+            for (int k = 0; k < kBK / kUmmaK; ++k)
+              tc::umma_tf32(tmem_main, tc::make_smem_desc(a_hi + k * 32), tc::make_smem_desc(w_hi + k * 32), idesc,
+                            !(first_in_chunk && k == 0));
+#pragma unroll
+            for (int k = 0; k < kBK / kUmmaK; ++k)
+              tc::umma_tf32(tmem_small, tc::make_smem_desc(a_lo + k * 32), tc::make_smem_desc(w_hi + k * 32), idesc,
+                            (uint32_t)((kb | k) != 0));
+#pragma unroll
+            for (int k = 0; k < kBK / kUmmaK; ++k)
+              tc::umma_tf32(tmem_small, tc::make_smem_desc(a_hi + k * 32), tc::make_smem_desc(w_lo + k * 32), idesc, 1u);
+            tc::umma_commit(&empty_bar[s]);
+          }
+          tc::umma_commit(&acc_full[buf]);       // after the tile's last chunk this also covers the cross terms
+        }
+        ++lt;
+      }
+    }
+  } else {
+    // ---- epilogue warps ------------------------------------------------------------------------------------
+    const int ew = warp - 2;
+    const int quarter = warp & 3;                  // TMEM lanes [32*quarter, +32) are the ones this warp may read
+    const int half = ew >> 2;                      // which half of the BN columns
+    const int col0 = half * HALF;
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    float4* stg = reinterpret_cast<float4*>(stg_base + ew * C::STG_WARP);   // [32 rows][LPR float4], swizzled
+    const int rr = lane / LPR;                     // coalesced phase: row within an RPI-row group
+    const int cj = lane % LPR;                     //                  float4 index inside the PC-wide piece
+    uint32_t cc = 0, lt = 0;
+    for (int id = blockIdx.x; id < vtiles; id += gridDim.x) {
+      int b, m0, n0, Lout;
+      if (!decode(id, b, m0, n0, Lout)) continue;
+      float acc[HALF];
+#pragma unroll
+      for (int i = 0; i < HALF; ++i) acc[i] = 0.f;
+      for (int c = 0; c < nchunks; ++c, ++cc) {
+        const uint32_t buf = cc & 1u;
+        tc::mbar_wait(&acc_full[buf], (cc >> 1) & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        drain_add<HALF>(tmem_base + lane_off + buf * BN + (uint32_t)col0, acc);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&acc_empty[buf]);
+      }
+      {
+        const uint32_t tp = lt & 1u;
+        drain_add<HALF>(tmem_base + lane_off + (2u + tp) * BN + (uint32_t)col0, acc);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&small_empty[tp]);
+        ++lt;
+      }
+      // ---- finish the tile: rows m0 + 32*quarter + [0,32), columns n0 + col0 + [0,HALF) ---------------------
+      const int row_base = m0 + quarter * 32;
+      const int ncol0 = n0 + col0;
+      const long long raw_base = (long long)b * ep.raw_item_stride + ncol0;
+      const long long split_base = (long long)b * ep.split_item_stride + (long long)ep.split_front * ep.N + ncol0;
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+        float4 resv[IT];
+        if (ep.res) {
+#pragma unroll
+          for (int it = 0; it < IT; ++it) {
+            const int row = row_base + it * RPI + rr;
+            resv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row < Lout) resv[it] = *reinterpret_cast<const float4*>(ep.res + raw_base + (long long)row * ep.N + p * PC + cj * 4);
+          }
+        }
+        const int wkey = (LPR == 8) ? (lane & 7) : ((lane >> 1) & (LPR - 1));
+#pragma unroll
+        for (int j = 0; j < LPR; ++j) {
+          float4 v = make_float4(acc[p * PC + 4 * j], acc[p * PC + 4 * j + 1], acc[p * PC + 4 * j + 2], acc[p * PC + 4 * j + 3]);
+          const int c = ncol0 + p * PC + 4 * j;
+          if (ep.bias) {
+            const float4 t = ld_nc_f4(ep.bias + c);
+            v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+          }
+          if (ep.act == 1) { v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w); }
+          if (ep.scale) {
+            const float4 t = ld_nc_f4(ep.scale + c);
+            v.x *= t.x; v.y *= t.y; v.z *= t.z; v.w *= t.w;
+          }
+          stg[lane * LPR + (j ^ wkey)] = v;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < IT; ++it) {
+          const int r = it * RPI + rr;               // row within this warp's 32
+          const int rkey = (LPR == 8) ? (r & 7) : ((r >> 1) & (LPR - 1));
+          float4 v = stg[r * LPR + (cj ^ rkey)];
+          const int row = row_base + r;
+          if (row < Lout) {
+            const long long o = (long long)row * ep.N + p * PC + cj * 4;
+            if (ep.res) { v.x += resv[it].x; v.y += resv[it].y; v.z += resv[it].z; v.w += resv[it].w; }
+            if (ep.out_raw) *reinterpret_cast<float4*>(ep.out_raw + raw_base + o) = v;
+            if (ep.out_hi) {
+              if (ep.elu_split) { v.x = elu1(v.x); v.y = elu1(v.y); v.z = elu1(v.z); v.w = elu1(v.w); }
+              store_split4(ep.out_hi + split_base + o, ep.out_lo + split_base + o, v);
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS));
+  }
+}
+
+// ---- probe: does a SWIZZLE_128B K-major operand descriptor work when its start address is shifted by a whole
+// number of 128-byte rows (not a multiple of 8)? One CTA, one 128 x 64 tile, plain single-pass TF32:
+//   out[m][n] = sum_k A[m + shift][k] * W[n][k],   m in [0,128), K % 32 == 0, A has >= 128 + 8 rows.
+// base_mode 0: descriptor base_offset field left 0; 1: base_offset = (start >> 7) & 7.
+__global__ void __launch_bounds__(128, 1)
+tc_shift_probe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, int K, int shift,
+                      int base_mode, float* __restrict__ out) {
+  constexpr int BN = 64;
+  constexpr int A_ROWS = kBM + 8;                  // 136 rows x 128 B = 17 KB (a multiple of 1024)
+  constexpr int A_BYTES = A_ROWS * kBK * 4;
+  constexpr int W_BYTES = BN * kBK * 4;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + A_BYTES + W_BYTES);
+  uint64_t* done = bar + 1;
+  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(done + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    tc::mbar_init(bar, 1);
+    tc::mbar_init(done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(tmem_base_ptr)), "r"(64));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_base_ptr;
+  if (threadIdx.x == 0) {
+    constexpr uint32_t idesc = tc::make_idesc(kBM, BN);
+    const int nkb = K / kBK;
+    for (int kb = 0; kb < nkb; ++kb) {
+      if (kb > 0) tc::mbar_wait(done, (uint32_t)(kb - 1) & 1u);     // previous MMAs have read the single stage
+      tc::mbar_expect_tx(bar, A_BYTES + W_BYTES);
+      tc::tma_load_2d(smem, &tmA, bar, kb * kBK, 0);
+      tc::tma_load_2d(smem + A_BYTES, &tmW, bar, kb * kBK, 0);
+      tc::mbar_wait(bar, (uint32_t)kb & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t a0 = tc::smem_u32(smem) + (uint32_t)shift * 128u;
+      const uint32_t w0 = tc::smem_u32(smem + A_BYTES);
+#pragma unroll
+      for (int k = 0; k < kBK / kUmmaK; ++k) {
+        uint64_t ad = tc::make_smem_desc(a0 + k * 32);
+        if (base_mode == 1) ad |= (uint64_t)(((a0 + k * 32) >> 7) & 7u) << 49;
+        tc::umma_tf32(tmem_base, ad, tc::make_smem_desc(w0 + k * 32), idesc, (uint32_t)((kb | k) != 0));
+      }
+      tc::umma_commit(done);
+    }
+    tc::mbar_wait(done, (uint32_t)(nkb - 1) & 1u);
+  }
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  {
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const int row = warp * 32 + lane;
+#pragma unroll
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      uint32_t r[16];
+      tc::tmem_ld16(tmem_base + lane_off + (uint32_t)c0, r);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int i = 0; i < 16; ++i) out[(long long)row * BN + c0 + i] = __uint_as_float(r[i]);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(64));
+  }
+}
+
+}  // namespace tc2
+}  // namespace mimi

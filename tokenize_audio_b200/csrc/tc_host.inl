@@ -34,7 +34,7 @@ static int tc_make_weight(mimi_b200* h, TcWeight* w, const std::vector<float>& w
   int rc;
   if ((rc = dev_upload(h, &w->hi, hi))) return rc;
   if ((rc = dev_upload(h, &w->lo, lo))) return rc;
-  w->N = N; w->K = K; w->BN = (N % 128 == 0) ? 128 : 64;
+  w->N = N; w->K = K; w->BN = (N % 128 == 0) ? 128 : (N % 64 == 0) ? 64 : 32;
   const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
   const cuuint64_t strides[1] = {(cuuint64_t)K * sizeof(float)};
   if ((rc = tc_make_map(h, &w->map_hi, w->hi, 2, dims, strides, w->BN))) return rc;
@@ -54,7 +54,7 @@ static std::vector<float> pack_conv_nk(const float* w, int cout, int cin, int k)
 static int tc_load_weights(mimi_b200* h, const mimi_b200_weights_t* w) {
   int rc;
   if ((rc = tc_init_driver(h))) return rc;
-  for (int i = 3; i < MIMI_B200_NUM_CONVS; ++i) {
+  for (int i = 1; i < MIMI_B200_NUM_CONVS; ++i) {
     const ConvGeom& g = kConv[i];
     if ((rc = tc_make_weight(h, &h->tc_conv[i], pack_conv_nk(w->conv_weight[i], g.cout, g.cin, g.k), g.cout, g.cin * g.k))) return rc;
   }
@@ -95,6 +95,7 @@ static PlanTC make_plan_tc(int B, long long N, int K) {
     return s;
   };
   p.a0 = raw(0, 64);   p.r1 = raw(0, 32);
+  p.s_a0 = split(0, 64, kHalo, 0);  p.s_r1 = split(0, 32, 0, 0);
   p.s_h1 = split(0, 64, kHalo, kHalo);
   p.d1 = raw(1, 128);  p.s_d1 = split(1, 128, kHalo, kHalo);  p.s_r2 = split(1, 64, 0, 0);  p.s_h2 = split(1, 128, kHalo, kHalo);
   p.d2 = raw(2, 256);  p.s_d2 = split(2, 256, kHalo, kHalo);  p.s_r3 = split(2, 128, 0, 0); p.s_h3 = split(2, 256, kHalo, kHalo);
@@ -156,6 +157,21 @@ struct TcOut {
   int act = 0;
 };
 
+// persistent second-generation kernel: one CTA per SM over mt_max * B * (N / BN) virtual tiles
+static void launch_tc2(mimi_b200* h, const CUtensorMap& ahi, const CUtensorMap& alo, const TcWeight& w, const tc::Epilogue& ep,
+                       int B, int mt_max, cudaStream_t st) {
+  tc2::Sched sc{B, mt_max, w.N / w.BN};
+  const long long vt = (long long)mt_max * B * sc.ntn;
+  const int grid = (int)std::min<long long>(vt, h->num_sms);
+  if (grid <= 0) return;
+  if (w.BN == 128)
+    tc2::tc2_gemm_kernel<128><<<grid, tc2::kThreads, tc2::Cfg<128>::SMEM, st>>>(ahi, alo, w.map_hi, w.map_lo, w.K, ep, sc);
+  else if (w.BN == 64)
+    tc2::tc2_gemm_kernel<64><<<grid, tc2::kThreads, tc2::Cfg<64>::SMEM, st>>>(ahi, alo, w.map_hi, w.map_lo, w.K, ep, sc);
+  else
+    tc2::tc2_gemm_kernel<32><<<grid, tc2::kThreads, tc2::Cfg<32>::SMEM, st>>>(ahi, alo, w.map_hi, w.map_lo, w.K, ep, sc);
+}
+
 static int tc_gemm(TcCtx& c, int slot, const SplitBuf& a, int k, int s, int pad, const TcWeight& w, const TcOut& o, int prof_id) {
   const CUtensorMap *ahi, *alo;
   int rc;
@@ -173,11 +189,17 @@ static int tc_gemm(TcCtx& c, int slot, const SplitBuf& a, int k, int s, int pad,
   ep.len_in = c.dlen[a.level]; ep.uniform_len_in = c.maxlen[a.level]; ep.conv_stride = s; ep.N = w.N;
   const int lout_max = (c.maxlen[a.level] + s - 1) / s;
   if (lout_max <= 0) return MIMI_B200_OK;
-  dim3 grid((lout_max + tc::kBM - 1) / tc::kBM, w.N / w.BN, c.B);
-  if (w.BN == 128)
-    tc::tc_gemm_kernel<128><<<grid, tc::kThreads, tc::smem_bytes(128), c.st>>>(*ahi, *alo, w.map_hi, w.map_lo, w.K, ep);
-  else
-    tc::tc_gemm_kernel<64><<<grid, tc::kThreads, tc::smem_bytes(64), c.st>>>(*ahi, *alo, w.map_hi, w.map_lo, w.K, ep);
+  if (c.h->mode == 2) {
+    launch_tc2(c.h, *ahi, *alo, w, ep, c.B, (lout_max + tc::kBM - 1) / tc::kBM, c.st);
+  } else {
+    dim3 grid((lout_max + tc::kBM - 1) / tc::kBM, w.N / w.BN, c.B);
+    if (w.BN == 128)
+      tc::tc_gemm_kernel<128><<<grid, tc::kThreads, tc::smem_bytes(128), c.st>>>(*ahi, *alo, w.map_hi, w.map_lo, w.K, ep);
+    else if (w.BN == 64)
+      tc::tc_gemm_kernel<64><<<grid, tc::kThreads, tc::smem_bytes(64), c.st>>>(*ahi, *alo, w.map_hi, w.map_lo, w.K, ep);
+    else
+      return fail(c.h, MIMI_B200_ERR_ARG, "tc: mode 1 has no BN=32 kernel");
+  }
   c.h->launches++;
   mark(c.h, prof_id, c.st);
   CUDA_TRY(c.h, cudaGetLastError());
@@ -216,15 +238,25 @@ static int encode_tc(mimi_b200* h, const float* d_input, int B, long long N, int
   const SplitBuf* halos[] = {&p.s_h1, &p.s_d1, &p.s_h2, &p.s_d2, &p.s_h3, &p.s_d3, &p.s_h4, &p.s_d4};
   for (const SplitBuf* s : halos)
     if ((rc = tc_zero_halo(c, *s))) return rc;
+  if (h->mode == 2 && (rc = tc_zero_halo(c, p.s_a0))) return rc;
 
   // ---- level 0 on CUDA cores: L0 (1->64 k7), R1a (64->32 k3), R1b (32->64 k1 + skip) ---------------------
   if (maxlen[0] > 0) {
     dim3 grid((maxlen[0] + 127) / 128, B);
-    conv0_kernel<<<grid, 256, 0, st>>>(d_input, N, h->conv_wt[0], h->conv_b[0], ws + p.a0, rstride(0, 64), dlen[0], maxlen[0]);
+    const bool sp = h->mode == 2;
+    conv0_kernel<<<grid, 256, 0, st>>>(d_input, N, h->conv_wt[0], h->conv_b[0], ws + p.a0, rstride(0, 64), dlen[0], maxlen[0],
+                                       sp ? ws + p.s_a0.hi : nullptr, sp ? ws + p.s_a0.lo : nullptr, p.s_a0.item_stride, p.s_a0.front);
     h->launches++; mark(h, 0, st);
     CUDA_TRY(h, cudaGetLastError());
   }
-  {
+  if (h->mode == 2) {
+    TcOut o;   // R1a: ELU -> 64 -> 32, k3 (ELU was applied by conv0's split store)
+    o.split = &p.s_r1; o.elu_split = 1; o.bias = h->conv_b[1];
+    if ((rc = tc_gemm(c, 16, p.s_a0, 3, 1, 2, h->tc_conv[1], o, 1))) return rc;
+    o = TcOut{};   // R1b: ELU -> 32 -> 64, k1, + skip (raw a0); only ELU(h) is needed downstream
+    o.res = ws + p.a0; o.raw_item_stride = rstride(0, 64); o.split = &p.s_h1; o.elu_split = 1; o.bias = h->conv_b[2];
+    if ((rc = tc_gemm(c, 17, p.s_r1, 1, 1, 0, h->tc_conv[2], o, 2))) return rc;
+  } else {
     GemmParams g{};
     g.A = ws + p.a0; g.Wt = h->conv_wt[1]; g.bias = h->conv_b[1]; g.out = ws + p.r1;
     g.len_in = dlen[0]; g.uniform_len_in = maxlen[0]; g.a_item_stride = rstride(0, 64); g.out_item_stride = rstride(0, 32);

@@ -169,6 +169,17 @@ class MimiB200Model:
             self._workspace = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
         return self._workspace
 
+    def reserve_workspace(self, batch: int, num_samples: int, num_quantizers: int = NUM_QUANTIZERS) -> int:
+        """Pre-size the activation workspace for the largest ``[batch, 1, num_samples]`` input that will be
+        encoded, so no later call has to grow it (a multi-GB device allocation in the middle of a shard).
+        Returns the size in bytes."""
+        with self._lock, torch.cuda.device(self.device):
+            nbytes = C.c_size_t()
+            rc = self._lib.mimi_b200_workspace_bytes(self._h, int(batch), int(num_samples), int(num_quantizers), C.byref(nbytes))
+            _lib.check(self._lib, self._h, rc, "mimi_b200_workspace_bytes")
+            self._ws(nbytes.value)
+        return int(nbytes.value)
+
     def encode(self, input_values: torch.Tensor, padding_mask: Optional[torch.Tensor] = None,
                num_quantizers: Optional[float] = None, encoder_past_key_values=None, padding_cache=None,
                use_streaming: Optional[bool] = None, return_dict: Optional[bool] = None,
@@ -249,9 +260,11 @@ class MimiB200Model:
                     ["layernorm", "qkv_gemm", "attention", "o_proj", "fc1_gelu", "fc2", "downsample_conv",
                      "rvq_input_proj", "rvq_fused", "latent_transpose", "code_fill", "halo_zero", "pad_split"])
 
-    def set_mode(self, tensor_cores: bool) -> None:
-        """True (default): wide layers on tcgen05 3xTF32 tensor cores; False: all-fp32 FFMA path."""
-        self.debug_set(3, 1 if tensor_cores else 0)
+    def set_mode(self, tensor_cores) -> None:
+        """True / 2 (default): every GEMM-shaped layer on the persistent tcgen05 3xTF32 kernel; 1: the
+        first-generation tcgen05 kernel for the wide layers (level 0 on FFMA); False / 0: all-fp32 FFMA."""
+        mode = (2 if tensor_cores else 0) if isinstance(tensor_cores, bool) else int(tensor_cores)
+        self.debug_set(3, mode)
 
     def profile(self, on: bool) -> None:
         """Switch per-launch CUDA-event profiling on/off (resets the counters)."""

@@ -28,9 +28,9 @@ def main():
     taps, margins = {}, []
     codes_o = O.encode(sd, x, 32, taps=taps, margins=margins)
     xd = torch.from_numpy(x).cuda()
-    if "--tc" in sys.argv:
+    if "--tc" in sys.argv or "--tc1" in sys.argv:
         # tensor-core path: raw taps that exist there (down convs 3/6/9, stream z), then the tail
-        m.set_mode(True)
+        m.set_mode(1 if "--tc1" in sys.argv else 2)
         m.debug_set(0, 0)
         m.encode(xd, num_quantizers=32)
         torch.cuda.synchronize()
