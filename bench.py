@@ -55,6 +55,7 @@ MMAC_PER_AUDIO_S = {
     "seanet_conv12": 209.715, "seanet_conv13": 39.322, "qkv_gemm": 157.286, "o_proj": 52.429,
     "fc1_gelu": 209.715, "fc2": 209.715, "attention": 51.2, "downsample_conv": 13.107,
     "rvq_input_proj": 3.277, "rvq_fused": 6.5536 * K_CODEBOOKS,
+    "front_fused": 10.752 + 147.456 + 49.152,
 }
 # algorithmic HBM bytes per audio-second for the bandwidth-bound kinds (fp32, channels-last)
 HBM_BYTES_PER_AUDIO_S = {

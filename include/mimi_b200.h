@@ -129,7 +129,8 @@ int mimi_b200_debug_tap(mimi_b200_t* h, int which, float* d_out, size_t out_capa
 /* Debug knobs (parity bisection only): key 0 = number of transformer layers to run (default 8),
    key 1 = index of the last SEANet conv to run (default 13; smaller values stop the pipeline there and
    leave d_codes untouched), key 2 = per-launch CUDA-event profiling on/off (resets the profile), key 3 =
-   compute mode: 2 (default) every GEMM-shaped layer on the persistent tcgen05 3xTF32 kernel (tc_gemm2.cuh),
+   compute mode: 3 (default) = mode 2 plus the fused 24 kHz front end (front_fused.cuh: L0 + ResBlock 1 in one
+   kernel); 2 = every GEMM-shaped layer on the persistent tcgen05 3xTF32 kernel (tc_gemm2.cuh),
    1 = first-generation tcgen05 kernel for the wide layers (level 0 on FFMA), 0 = all-fp32 FFMA. */
 int mimi_b200_debug_set(mimi_b200_t* h, int key, int value);
 
@@ -137,7 +138,7 @@ int mimi_b200_debug_set(mimi_b200_t* h, int key, int value);
    id < max_ids, sum_ms[id] = total device time between the previous launch's end and this launch's end on
    the encode stream, count[id] = launches. Kinds: 0 conv0; 1..13 SEANet conv i (gather-GEMM); 14
    LayerNorm; 15 QKV; 16 attention; 17 o_proj; 18 fc1; 19 fc2; 20 downsample conv; 21 RVQ input_proj;
-   22 fused RVQ; 23 latent transpose; 24 code fill; 25 halo zeroing; 26 replicate-pad + split. Synchronises with the last recorded launch. */
+   22 fused RVQ; 23 latent transpose; 24 code fill; 25 halo zeroing; 26 replicate-pad + split; 27 fused front end. Synchronises with the last recorded launch. */
 int mimi_b200_profile_read(mimi_b200_t* h, int max_ids, double* sum_ms, int64_t* count);
 
 /* Unit-test hook for the tensor-core GEMM kernel: d_out[M][N] = act(d_a[M][K] * h_w[N][K]^T + bias) through the

@@ -1,0 +1,320 @@
+// Fused SEANet front end at 24 kHz: waveform -> L0 (conv 1->64, k7) -> ELU -> R1a (64->32, k3) -> ELU ->
+// R1b (32->64, k1) + skip -> ELU -> TF32 hi/lo split, written once as the operand of the first strided conv
+// (MimiEncoder layers 0, 1.block.1, 1.block.3; modeling_mimi.py:412-451,454-496). The 64-channel 24 kHz
+// activations (6.1 MB per audio-second in fp32) never touch HBM: per audio-second the kernel reads 96 KB
+// and writes the 12.3 MB split operand.
+//
+//   One persistent CTA per SM, 8 warps = two warpgroups (warps 0-3, 4-7) that ping-pong over time tiles; thread m
+//   of a warpgroup owns tile row m in every phase, so the raw L0 output needed by the skip stays in its
+//   registers (256 threads -> 255 registers each; a ninth warp would cap them at 168 and spill). Thread 0 of
+//   each warpgroup issues that warpgroup's tcgen05.mma after a 128-thread named barrier.
+//     front  L0 on CUDA cores (weights as kernel-parameter constants -> FFMA with constant-bank operands,
+//            no loads), ELU, hi/lo split, stored straight into the SWIZZLE_128B K-major operand layout;
+//     R1a    3 taps x 2 channel panels = 6 k-blocks; tap tau reads the SAME staged rows through a descriptor
+//            whose start address is shifted by tau 128-byte rows (im2col never exists, not even in smem);
+//     mid    TMEM -> bias, ELU, split -> operand of R1b (aliases the dead R1a operand);
+//     R1b    one k-block;
+//     final  TMEM -> bias + skip -> ELU -> split -> 32-column transposes through this warp's own (dead)
+//            operand rows -> row-contiguous float4 stores.
+//   A tile stages 128 rows (times t0-2 .. t0+125) and keeps the 126 outputs t0 .. t0+125: the two leading
+//   rows are the causal halo of the k=3 conv, recomputed instead of carried, so tiles are independent.
+//   Arithmetic is 3xTF32 as in tc_gemm2.cuh; K is at most 192 so a single accumulation chunk is used.
+#pragma once
+#include "tc_gemm.cuh"
+
+namespace mimi {
+namespace f0 {
+
+constexpr int kAdv = 126;                        // outputs kept per tile
+constexpr int kPanelRows = 136;
+constexpr int kPanelBytes = kPanelRows * 128;    // 17408 = 17 KB, keeps every panel 1024-byte aligned
+constexpr int kTileBuf = 4 * kPanelBytes;        // hi panel 0 | hi panel 1 | lo panel 0 | lo panel 1
+constexpr int kW1Block = 32 * 128;               // one k-block of W1 (32 output channels x 32 floats)
+constexpr int kW1Bytes = 6 * kW1Block;           // per hi / lo
+constexpr int kW2Bytes = 64 * 128;               // per hi / lo
+constexpr int kThreads = 256;
+constexpr int kSmem = 1024 + 2 * kTileBuf + 2 * kW1Bytes + 2 * kW2Bytes + 256;
+constexpr int kTmemCols = 512;                   // 2 warpgroups x (32 + 32 + 64 + 64) columns
+
+struct Consts {
+  float w0[64 * 7];     // L0 weight [64][7]
+  float b0[64];
+  float b1[32];         // R1a bias
+  float b2[64];         // R1b bias
+};
+
+struct Params {
+  const float* x;            // [B][x_stride] waveform
+  long long x_stride;
+  const int* len;            // device [B] valid samples per item or nullptr -> uniform_len
+  int uniform_len;
+  int B;
+  int mt_max;                // tiles per item at the longest item
+  float* out_hi;             // split output, channels-last rows of 64, halo rows in front
+  float* out_lo;
+  long long split_item_stride;
+  int split_front;
+};
+
+// exp(x) - 1 for x <= 0 through ex2.approx (abs error ~1e-7, far below the TF32-split granularity downstream)
+__device__ __forceinline__ float elu_fast(float x) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 1.4426950408889634f));
+  return x > 0.f ? x : e - 1.f;
+}
+
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+front_fused_kernel(const __grid_constant__ CUtensorMap tmW1_hi, const __grid_constant__ CUtensorMap tmW1_lo,
+                   const __grid_constant__ CUtensorMap tmW2_hi, const __grid_constant__ CUtensorMap tmW2_lo,
+                   const __grid_constant__ Consts cst, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* w1_hi = smem + 2 * kTileBuf;
+  uint8_t* w1_lo = w1_hi + kW1Bytes;
+  uint8_t* w2_hi = w1_lo + kW1Bytes;
+  uint8_t* w2_lo = w2_hi + kW2Bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(w2_lo + kW2Bytes);
+  uint64_t* acc1_full = bars;           // [2] R1a accumulators of warpgroup g complete (tcgen05.commit)
+  uint64_t* acc2_full = bars + 2;       // [2] R1b accumulators complete
+  uint64_t* w_ready = bars + 4;         // weights landed (TMA)
+  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(bars + 5);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int vtiles = p.mt_max * p.B;
+
+  if (threadIdx.x == 0) {
+    for (int g = 0; g < 2; ++g) {
+      tc::mbar_init(&acc1_full[g], 1);
+      tc::mbar_init(&acc2_full[g], 1);
+    }
+    tc::mbar_init(w_ready, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // rows 0,1 and 130..135 of every panel are never written by the front phase; they only feed discarded
+  // output rows, but keep them finite
+  for (int i = threadIdx.x; i < 2 * 4 * 8 * 32; i += kThreads) {
+    const int buf = i / (4 * 8 * 32), rem = i % (4 * 8 * 32);
+    const int panel = rem / (8 * 32), r8 = (rem / 32) % 8, col = rem % 32;
+    const int row = r8 < 2 ? r8 : 128 + r8;
+    reinterpret_cast<float*>(smem + buf * kTileBuf + panel * kPanelBytes + row * 128)[col] = 0.f;
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(tmem_base_ptr)), "r"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  fence_async_smem();
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_base_ptr;
+
+  auto item_len = [&](int b) { return p.len ? __ldg(p.len + b) : p.uniform_len; };
+
+  if (threadIdx.x == 0) {
+    // resident weights: W1 [32][192] as 6 k-blocks, W2 [64][32]
+    tc::prefetch_tmap(&tmW1_hi); tc::prefetch_tmap(&tmW1_lo); tc::prefetch_tmap(&tmW2_hi); tc::prefetch_tmap(&tmW2_lo);
+    tc::mbar_expect_tx(w_ready, 2 * kW1Bytes + 2 * kW2Bytes);
+    for (int kb = 0; kb < 6; ++kb) {
+      tc::tma_load_2d(w1_hi + kb * kW1Block, &tmW1_hi, w_ready, kb * 32, 0);
+      tc::tma_load_2d(w1_lo + kb * kW1Block, &tmW1_lo, w_ready, kb * 32, 0);
+    }
+    tc::tma_load_2d(w2_hi, &tmW2_hi, w_ready, 0, 0);
+    tc::tma_load_2d(w2_lo, &tmW2_lo, w_ready, 0, 0);
+  }
+  {
+    // ---- compute warpgroups ------------------------------------------------------------------------------------
+    const int g = warp >> 2;                       // warpgroup
+    const int wq = warp & 3;                       // TMEM lane quarter == warp index inside the warpgroup
+    const int m = wq * 32 + lane;                  // tile row owned by this thread
+    const bool issuer = m == 0;                    // issues this warpgroup's MMAs
+    constexpr uint32_t idesc1 = tc::make_idesc(128, 32);
+    constexpr uint32_t idesc2 = tc::make_idesc(128, 64);
+    auto wg_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory"); };
+    if (issuer) tc::mbar_wait(w_ready, 0);
+    uint8_t* buf = smem + g * kTileBuf;
+    const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
+    const uint32_t tm1 = tmem_base + lane_off + g * 192;           // acc1 main | small (32 + 32 columns)
+    const uint32_t tm2 = tm1 + 64;                                  // acc2 main | small (64 + 64 columns)
+    float4* stg_hi = reinterpret_cast<float4*>(buf + 2 * kPanelBytes + (wq * 32 + 2) * 128);   // this warp's own rows
+    float4* stg_lo = reinterpret_cast<float4*>(buf + 3 * kPanelBytes + (wq * 32 + 2) * 128);
+    uint32_t it = 0;
+    for (int id = blockIdx.x + g * gridDim.x; id < vtiles; id += 2 * gridDim.x) {
+      const int b = id % p.B;
+      const int t0 = (id / p.B) * kAdv;
+      const int L = item_len(b);
+      if (t0 >= L) continue;
+      const int t = t0 - 2 + m;                    // time of this thread's row
+      // ---- front: L0 + ELU + split -> operand rows (buffer row m + 2) ---------------------------------------
+      float a0[64];
+      {
+        const float* xb = p.x + (long long)b * p.x_stride;
+        float xv[7];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+          const int tt = t - 6 + k;
+          xv[k] = (tt >= 0 && tt < L) ? __ldg(xb + tt) : 0.f;
+        }
+#pragma unroll
+        for (int c = 0; c < 64; ++c) {
+          float s = cst.b0[c];
+#pragma unroll
+          for (int k = 0; k < 7; ++k) s = fmaf(cst.w0[c * 7 + k], xv[k], s);
+          a0[c] = s;
+        }
+        const int row = m + 2;
+        const int key = row & 7;
+        const bool live = t >= 0;                  // rows before the item start are the conv's zero padding
+#pragma unroll
+        for (int pn = 0; pn < 2; ++pn)
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float4 h4, l4;
+            const int c = pn * 32 + q * 4;
+            split_tf32(live ? elu_fast(a0[c + 0]) : 0.f, h4.x, l4.x);
+            split_tf32(live ? elu_fast(a0[c + 1]) : 0.f, h4.y, l4.y);
+            split_tf32(live ? elu_fast(a0[c + 2]) : 0.f, h4.z, l4.z);
+            split_tf32(live ? elu_fast(a0[c + 3]) : 0.f, h4.w, l4.w);
+            const int off = row * 128 + ((q ^ key) << 4);
+            *reinterpret_cast<float4*>(buf + pn * kPanelBytes + off) = h4;
+            *reinterpret_cast<float4*>(buf + (2 + pn) * kPanelBytes + off) = l4;
+          }
+        fence_async_smem();
+        wg_sync();
+        if (issuer) {
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t bufa = tc::smem_u32(buf);
+          const uint32_t main1 = tmem_base + g * 192, small1 = main1 + 32;
+#pragma unroll
+          for (int kb = 0; kb < 6; ++kb) {
+            const int tau = kb >> 1, pn = kb & 1;
+            const uint32_t a_hi = bufa + pn * kPanelBytes + tau * 128;
+            const uint32_t a_lo = a_hi + 2 * kPanelBytes;
+            const uint32_t b_hi = tc::smem_u32(w1_hi) + kb * kW1Block;
+            const uint32_t b_lo = tc::smem_u32(w1_lo) + kb * kW1Block;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              tc::umma_tf32(main1, tc::make_smem_desc(a_hi + k * 32), tc::make_smem_desc(b_hi + k * 32), idesc1, (uint32_t)((kb | k) != 0));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              tc::umma_tf32(small1, tc::make_smem_desc(a_lo + k * 32), tc::make_smem_desc(b_hi + k * 32), idesc1, (uint32_t)((kb | k) != 0));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              tc::umma_tf32(small1, tc::make_smem_desc(a_hi + k * 32), tc::make_smem_desc(b_lo + k * 32), idesc1, 1u);
+          }
+          tc::umma_commit(&acc1_full[g]);
+        }
+        __syncwarp();
+      }
+      // ---- mid: R1a accumulators -> bias, ELU, split -> R1b operand (row m of hi panel 0 / hi panel 1) -----------
+      {
+        tc::mbar_wait(&acc1_full[g], it & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint32_t rm[32], rs[32];
+        tmem_ld32(tm1, rm);
+        tmem_ld32(tm1 + 32, rs);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const int key = m & 7;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float4 h4, l4;
+          float v[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            v[j] = elu_fast(__uint_as_float(rm[q * 4 + j]) + __uint_as_float(rs[q * 4 + j]) + cst.b1[q * 4 + j]);
+          split_tf32(v[0], h4.x, l4.x); split_tf32(v[1], h4.y, l4.y); split_tf32(v[2], h4.z, l4.z); split_tf32(v[3], h4.w, l4.w);
+          const int off = m * 128 + ((q ^ key) << 4);
+          *reinterpret_cast<float4*>(buf + off) = h4;
+          *reinterpret_cast<float4*>(buf + kPanelBytes + off) = l4;
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        fence_async_smem();
+        wg_sync();
+        if (issuer) {
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a_hi = tc::smem_u32(buf);                       // R1 operand aliases hi panel 0 / hi panel 1
+          const uint32_t a_lo = a_hi + kPanelBytes;
+          const uint32_t b_hi = tc::smem_u32(w2_hi), b_lo = tc::smem_u32(w2_lo);
+          const uint32_t main2 = tmem_base + g * 192 + 64, small2 = main2 + 64;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            tc::umma_tf32(main2, tc::make_smem_desc(a_hi + k * 32), tc::make_smem_desc(b_hi + k * 32), idesc2, (uint32_t)(k != 0));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            tc::umma_tf32(small2, tc::make_smem_desc(a_lo + k * 32), tc::make_smem_desc(b_hi + k * 32), idesc2, (uint32_t)(k != 0));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            tc::umma_tf32(small2, tc::make_smem_desc(a_hi + k * 32), tc::make_smem_desc(b_lo + k * 32), idesc2, 1u);
+          tc::umma_commit(&acc2_full[g]);
+        }
+        __syncwarp();
+      }
+      // ---- final: R1b accumulators + bias + skip -> ELU -> split -> coalesced stores ----------------------------
+      {
+        tc::mbar_wait(&acc2_full[g], it & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const long long obase = (long long)b * p.split_item_stride + (long long)p.split_front * 64;
+#pragma unroll
+        for (int pc = 0; pc < 2; ++pc) {
+          uint32_t rm[32], rs[32];
+          tmem_ld32(tm2 + pc * 32, rm);
+          tmem_ld32(tm2 + 64 + pc * 32, rs);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          const int key = lane & 7;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float4 h4, l4;
+            float v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int c = pc * 32 + q * 4 + j;
+              v[j] = elu_fast((__uint_as_float(rm[q * 4 + j]) + __uint_as_float(rs[q * 4 + j])) + cst.b2[c] + a0[c]);
+            }
+            split_tf32(v[0], h4.x, l4.x); split_tf32(v[1], h4.y, l4.y); split_tf32(v[2], h4.z, l4.z); split_tf32(v[3], h4.w, l4.w);
+            stg_hi[lane * 8 + (q ^ key)] = h4;
+            stg_lo[lane * 8 + (q ^ key)] = l4;
+          }
+          __syncwarp();
+#pragma unroll
+          for (int i8 = 0; i8 < 8; ++i8) {
+            const int r = i8 * 4 + (lane >> 3);        // row inside this warp's 32
+            const int cj = lane & 7;
+            const float4 h4 = stg_hi[r * 8 + (cj ^ (r & 7))];
+            const float4 l4 = stg_lo[r * 8 + (cj ^ (r & 7))];
+            const int mm = wq * 32 + r;
+            const int tt = t0 - 2 + mm;
+            if (mm >= 2 && tt < L) {
+              const long long o = obase + (long long)tt * 64 + pc * 32 + cj * 4;
+              *reinterpret_cast<float4*>(p.out_hi + o) = h4;
+              *reinterpret_cast<float4*>(p.out_lo + o) = l4;
+            }
+          }
+          __syncwarp();
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      }
+      ++it;
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+  }
+}
+
+}  // namespace f0
+}  // namespace mimi

@@ -21,6 +21,7 @@
 #include "rvq.cuh"
 #include "tc_gemm.cuh"
 #include "tc_gemm2.cuh"
+#include "front_fused.cuh"
 #include "transformer.cuh"
 
 using namespace mimi;
@@ -130,8 +131,11 @@ struct mimi_b200 {
   Plan last;
   void* last_ws = nullptr;
   // tensor-core path
-  int mode = 2;                                // 2 = persistent tcgen05 3xTF32 kernel for every GEMM-shaped layer,
+  int mode = 3;                                // 3 = mode 2 + fused 24 kHz front end (front_fused.cuh),
+                                               // 2 = persistent tcgen05 3xTF32 kernel for every GEMM-shaped layer,
                                                // 1 = first-generation tcgen05 kernel (level 0 on FFMA), 0 = all-fp32 SIMT
+  int last_mode = 0;
+  f0::Consts f0_consts;
   int num_sms = 148;
   PFN_cuTensorMapEncodeTiled_v12000 encode_tiled = nullptr;
   TcWeight tc_conv[MIMI_B200_NUM_CONVS];       // convs 1..13 (conv 0 is a direct SIMT conv)
@@ -363,6 +367,7 @@ int mimi_b200_create(mimi_b200_t** out, int device_ordinal) {
   cudaFuncSetAttribute(tc2::tc2_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::Cfg<128>::SMEM);
   cudaFuncSetAttribute(tc2::tc2_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::Cfg<64>::SMEM);
   cudaFuncSetAttribute(tc2::tc2_gemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::Cfg<32>::SMEM);
+  cudaFuncSetAttribute(f0::front_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, f0::kSmem);
   cudaFuncSetAttribute(tc2::tc_shift_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 40960);
   if ((e = cudaGetLastError()) != cudaSuccess) { delete h; return fail(nullptr, MIMI_B200_ERR_CUDA, cudaGetErrorString(e)); }
   *out = h;
@@ -389,7 +394,7 @@ int mimi_b200_debug_set(mimi_b200_t* h, int key, int value) {
   if (key == 0) h->dbg_layers = std::min(std::max(value, 0), MIMI_B200_NUM_LAYERS);
   else if (key == 1) h->dbg_last_conv = std::min(std::max(value, 0), MIMI_B200_NUM_CONVS - 1);
   else if (key == 2) { h->prof_on = value != 0; h->prof_n = 0; }
-  else if (key == 3) h->mode = std::min(std::max(value, 0), 2);
+  else if (key == 3) h->mode = std::min(std::max(value, 0), 3);
   else return fail(h, MIMI_B200_ERR_ARG, "debug_set: unknown key");
   return MIMI_B200_OK;
 }
@@ -499,6 +504,10 @@ int mimi_b200_load_weights(mimi_b200_t* h, const mimi_b200_weights_t* w) {
     if ((rc = dev_upload(h, &h->rope_cos, cs))) return rc;
     if ((rc = dev_upload(h, &h->rope_sin, sn))) return rc;
   }
+  std::memcpy(h->f0_consts.w0, w->conv_weight[0], sizeof(float) * 64 * 7);
+  std::memcpy(h->f0_consts.b0, w->conv_bias[0], sizeof(float) * 64);
+  std::memcpy(h->f0_consts.b1, w->conv_bias[1], sizeof(float) * 32);
+  std::memcpy(h->f0_consts.b2, w->conv_bias[2], sizeof(float) * 64);
   if ((rc = tc_load_weights(h, w))) return rc;
   h->amap_cache.clear();
   h->loaded = true;
@@ -545,6 +554,7 @@ int mimi_b200_encode(mimi_b200_t* h, const float* d_input, int B, int64_t N, con
   h->last = p;
   h->last_tc = pt;
   h->last_was_tc = use_tc;
+  h->last_mode = h->mode;
   h->last_ws = ws;
   mark(h, -1, st);
 
@@ -723,6 +733,7 @@ int mimi_b200_debug_tap(mimi_b200_t* h, int which, float* d_out, size_t cap, int
   TapInfo t{};
   if (h->last_was_tc) {
     const PlanTC& q = h->last_tc;
+    if (h->last_mode == 3 && which < 3) return fail(h, MIMI_B200_ERR_ARG, "debug_tap: level-0 activations stay on chip in mode 3");
     switch (which) {
       case 0: t = {q.a0, 0, 64}; break;
       case 1: t = {q.r1, 0, 32}; break;
@@ -774,7 +785,7 @@ __global__ void debug_split_kernel(const float* __restrict__ x, float* __restric
 int mimi_b200_debug_tc_gemm(mimi_b200_t* h, const float* d_a, const float* h_w, const float* d_bias_opt, int M, int N,
                             int K, int act, float* d_out, void* stream) {
   if (!h || !d_a || !h_w || !d_out) return fail(h, MIMI_B200_ERR_ARG, "debug_tc_gemm: NULL argument");
-  if (M <= 0 || N % 32 || K % 32 || (h->mode != 2 && N % 64))
+  if (M <= 0 || N % 32 || K % 32 || (h->mode < 2 && N % 64))
     return fail(h, MIMI_B200_ERR_ARG, "debug_tc_gemm: need N % 32 == 0 (mode 2) / N % 64 == 0 (mode 1) and K % 32 == 0");
   CUDA_TRY(h, cudaSetDevice(h->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -795,7 +806,7 @@ int mimi_b200_debug_tc_gemm(mimi_b200_t* h, const float* d_a, const float* h_w, 
   tc::Epilogue ep{};
   ep.bias = d_bias_opt; ep.out_raw = d_out; ep.raw_item_stride = (long long)M * N; ep.act = act;
   ep.uniform_len_in = M; ep.conv_stride = 1; ep.N = N;
-  if (h->mode == 2) {
+  if (h->mode >= 2) {
     launch_tc2(h, ma_hi, ma_lo, w, ep, 1, (M + tc::kBM - 1) / tc::kBM, st);
   } else {
     dim3 grid((M + tc::kBM - 1) / tc::kBM, N / w.BN, 1);

@@ -189,7 +189,7 @@ static int tc_gemm(TcCtx& c, int slot, const SplitBuf& a, int k, int s, int pad,
   ep.len_in = c.dlen[a.level]; ep.uniform_len_in = c.maxlen[a.level]; ep.conv_stride = s; ep.N = w.N;
   const int lout_max = (c.maxlen[a.level] + s - 1) / s;
   if (lout_max <= 0) return MIMI_B200_OK;
-  if (c.h->mode == 2) {
+  if (c.h->mode >= 2) {
     launch_tc2(c.h, *ahi, *alo, w, ep, c.B, (lout_max + tc::kBM - 1) / tc::kBM, c.st);
   } else {
     dim3 grid((lout_max + tc::kBM - 1) / tc::kBM, w.N / w.BN, c.B);
@@ -241,7 +241,21 @@ static int encode_tc(mimi_b200* h, const float* d_input, int B, long long N, int
   if (h->mode == 2 && (rc = tc_zero_halo(c, p.s_a0))) return rc;
 
   // ---- level 0 on CUDA cores: L0 (1->64 k7), R1a (64->32 k3), R1b (32->64 k1 + skip) ---------------------
-  if (maxlen[0] > 0) {
+  if (h->mode == 3) {
+    // fused front end: waveform -> L0 -> R1a -> R1b (+skip) -> ELU -> split, 24 kHz activations stay on chip
+    if (maxlen[0] > 0) {
+      f0::Params fp{};
+      fp.x = d_input; fp.x_stride = N; fp.len = dlen[0]; fp.uniform_len = maxlen[0]; fp.B = B;
+      fp.mt_max = (maxlen[0] + f0::kAdv - 1) / f0::kAdv;
+      fp.out_hi = ws + p.s_h1.hi; fp.out_lo = ws + p.s_h1.lo; fp.split_item_stride = p.s_h1.item_stride; fp.split_front = p.s_h1.front;
+      const long long vt = (long long)fp.mt_max * B;
+      const int grid = (int)std::min<long long>(vt, h->num_sms);
+      f0::front_fused_kernel<<<grid, f0::kThreads, f0::kSmem, st>>>(h->tc_conv[1].map_hi, h->tc_conv[1].map_lo, h->tc_conv[2].map_hi,
+                                                                    h->tc_conv[2].map_lo, h->f0_consts, fp);
+      h->launches++; mark(h, 27, st);
+      CUDA_TRY(h, cudaGetLastError());
+    }
+  } else if (maxlen[0] > 0) {
     dim3 grid((maxlen[0] + 127) / 128, B);
     const bool sp = h->mode == 2;
     conv0_kernel<<<grid, 256, 0, st>>>(d_input, N, h->conv_wt[0], h->conv_b[0], ws + p.a0, rstride(0, 64), dlen[0], maxlen[0],
@@ -249,7 +263,8 @@ static int encode_tc(mimi_b200* h, const float* d_input, int B, long long N, int
     h->launches++; mark(h, 0, st);
     CUDA_TRY(h, cudaGetLastError());
   }
-  if (h->mode == 2) {
+  if (h->mode == 3) {
+  } else if (h->mode == 2) {
     TcOut o;   // R1a: ELU -> 64 -> 32, k3 (ELU was applied by conv0's split store)
     o.split = &p.s_r1; o.elu_split = 1; o.bias = h->conv_b[1];
     if ((rc = tc_gemm(c, 16, p.s_a0, 3, 1, 2, h->tc_conv[1], o, 1))) return rc;

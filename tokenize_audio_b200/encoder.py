@@ -258,12 +258,14 @@ class MimiB200Model:
 
     LAUNCH_KINDS = (["conv0"] + [f"seanet_conv{i}" for i in range(1, 14)] +
                     ["layernorm", "qkv_gemm", "attention", "o_proj", "fc1_gelu", "fc2", "downsample_conv",
-                     "rvq_input_proj", "rvq_fused", "latent_transpose", "code_fill", "halo_zero", "pad_split"])
+                     "rvq_input_proj", "rvq_fused", "latent_transpose", "code_fill", "halo_zero", "pad_split",
+                     "front_fused"])
 
     def set_mode(self, tensor_cores) -> None:
-        """True / 2 (default): every GEMM-shaped layer on the persistent tcgen05 3xTF32 kernel; 1: the
-        first-generation tcgen05 kernel for the wide layers (level 0 on FFMA); False / 0: all-fp32 FFMA."""
-        mode = (2 if tensor_cores else 0) if isinstance(tensor_cores, bool) else int(tensor_cores)
+        """True / 3 (default): fused 24 kHz front end + persistent tcgen05 3xTF32 kernel for every other
+        GEMM-shaped layer; 2: the same without the front-end fusion; 1: the first-generation tcgen05 kernel
+        for the wide layers (level 0 on FFMA); False / 0: all-fp32 FFMA."""
+        mode = (3 if tensor_cores else 0) if isinstance(tensor_cores, bool) else int(tensor_cores)
         self.debug_set(3, mode)
 
     def profile(self, on: bool) -> None:

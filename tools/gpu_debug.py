@@ -28,13 +28,16 @@ def main():
     taps, margins = {}, []
     codes_o = O.encode(sd, x, 32, taps=taps, margins=margins)
     xd = torch.from_numpy(x).cuda()
-    if "--tc" in sys.argv or "--tc1" in sys.argv:
+    if "--tc" in sys.argv or "--tc1" in sys.argv or "--tc2" in sys.argv:
         # tensor-core path: raw taps that exist there (down convs 3/6/9, stream z), then the tail
-        m.set_mode(1 if "--tc1" in sys.argv else 2)
+        mode = 1 if "--tc1" in sys.argv else 2 if "--tc2" in sys.argv else 3
+        m.set_mode(mode)
         m.debug_set(0, 0)
         m.encode(xd, num_quantizers=32)
         torch.cuda.synchronize()
         for ci, nm in {0: "seanet.l0", 3: "seanet.down3", 6: "seanet.down6", 9: "seanet.down9", 13: "seanet.out"}.items():
+            if mode == 3 and ci == 0:
+                continue
             t = m.debug_tap(ci).cpu().numpy()
             ref = np.stack([a.T for a in taps[nm]])
             t = t[:, : ref.shape[1]]
