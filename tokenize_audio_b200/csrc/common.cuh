@@ -58,6 +58,18 @@ __device__ __forceinline__ void store_split4(float* hi, float* lo, float4 v) {
   *reinterpret_cast<float4*>(lo) = l4;
 }
 
+// explicit shared-space 16-byte accesses (a pointer into dynamic shared memory that went through integer
+// arithmetic is otherwise compiled as a generic LD/ST, which the compiler cannot reorder against global
+// stores and which pays the generic-address check)
+__device__ __forceinline__ void sts128(uint32_t saddr, const float4& v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+
 __host__ __device__ __forceinline__ int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 }  // namespace mimi

@@ -29,9 +29,9 @@ constexpr int kAdv = 126;                        // outputs kept per tile
 constexpr int kPanelRows = 136;
 constexpr int kPanelBytes = kPanelRows * 128;    // 17408 = 17 KB, keeps every panel 1024-byte aligned
 constexpr int kTileBuf = 4 * kPanelBytes;        // hi panel 0 | hi panel 1 | lo panel 0 | lo panel 1
-constexpr int kW1Block = 32 * 128;               // one k-block of W1 (32 output channels x 32 floats)
-constexpr int kW1Bytes = 6 * kW1Block;           // per hi / lo
-constexpr int kW2Bytes = 64 * 128;               // per hi / lo
+constexpr int kW1Block = 32 * 128;               // one k-block of W1 (32 output channels x 32 floats), hi or lo
+constexpr int kW1Bytes = 6 * kW1Block;           // per hi / lo; stored stacked per k-block: [hi kb | lo kb]
+constexpr int kW2Bytes = 64 * 128;               // per hi / lo; stored stacked: [hi | lo]
 constexpr int kThreads = 256;
 constexpr int kSmem = 1024 + 2 * kTileBuf + 2 * kW1Bytes + 2 * kW2Bytes + 256;
 constexpr int kTmemCols = 512;                   // 2 warpgroups x (32 + 32 + 64 + 64) columns
@@ -82,11 +82,11 @@ front_fused_kernel(const __grid_constant__ CUtensorMap tmW1_hi, const __grid_con
                    const __grid_constant__ Consts cst, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* w1_hi = smem + 2 * kTileBuf;
-  uint8_t* w1_lo = w1_hi + kW1Bytes;
-  uint8_t* w2_hi = w1_lo + kW1Bytes;
-  uint8_t* w2_lo = w2_hi + kW2Bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(w2_lo + kW2Bytes);
+  // B operands are stored "stacked": k-block kb of W1 is [hi (32 rows) | lo (32 rows)] so that ONE N=64 MMA with
+  // A_hi produces the main term (columns 0..31) and the A_hi*W_lo cross term (columns 32..63) together
+  uint8_t* w1 = smem + 2 * kTileBuf;               // 6 x (hi 4 KB | lo 4 KB)
+  uint8_t* w2 = w1 + 2 * kW1Bytes;                 // hi 8 KB | lo 8 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(w2 + 2 * kW2Bytes);
   uint64_t* acc1_full = bars;           // [2] R1a accumulators of warpgroup g complete (tcgen05.commit)
   uint64_t* acc2_full = bars + 2;       // [2] R1b accumulators complete
   uint64_t* w_ready = bars + 4;         // weights landed (TMA)
@@ -128,11 +128,11 @@ front_fused_kernel(const __grid_constant__ CUtensorMap tmW1_hi, const __grid_con
     tc::prefetch_tmap(&tmW1_hi); tc::prefetch_tmap(&tmW1_lo); tc::prefetch_tmap(&tmW2_hi); tc::prefetch_tmap(&tmW2_lo);
     tc::mbar_expect_tx(w_ready, 2 * kW1Bytes + 2 * kW2Bytes);
     for (int kb = 0; kb < 6; ++kb) {
-      tc::tma_load_2d(w1_hi + kb * kW1Block, &tmW1_hi, w_ready, kb * 32, 0);
-      tc::tma_load_2d(w1_lo + kb * kW1Block, &tmW1_lo, w_ready, kb * 32, 0);
+      tc::tma_load_2d(w1 + (2 * kb) * kW1Block, &tmW1_hi, w_ready, kb * 32, 0);
+      tc::tma_load_2d(w1 + (2 * kb + 1) * kW1Block, &tmW1_lo, w_ready, kb * 32, 0);
     }
-    tc::tma_load_2d(w2_hi, &tmW2_hi, w_ready, 0, 0);
-    tc::tma_load_2d(w2_lo, &tmW2_lo, w_ready, 0, 0);
+    tc::tma_load_2d(w2, &tmW2_hi, w_ready, 0, 0);
+    tc::tma_load_2d(w2 + kW2Bytes, &tmW2_lo, w_ready, 0, 0);
   }
   {
     // ---- compute warpgroups ------------------------------------------------------------------------------------
@@ -140,16 +140,18 @@ front_fused_kernel(const __grid_constant__ CUtensorMap tmW1_hi, const __grid_con
     const int wq = warp & 3;                       // TMEM lane quarter == warp index inside the warpgroup
     const int m = wq * 32 + lane;                  // tile row owned by this thread
     const bool issuer = m == 0;                    // issues this warpgroup's MMAs
-    constexpr uint32_t idesc1 = tc::make_idesc(128, 32);
-    constexpr uint32_t idesc2 = tc::make_idesc(128, 64);
+    constexpr uint32_t idesc32 = tc::make_idesc(128, 32);
+    constexpr uint32_t idesc64 = tc::make_idesc(128, 64);
+    constexpr uint32_t idesc128 = tc::make_idesc(128, 128);
     auto wg_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory"); };
     if (issuer) tc::mbar_wait(w_ready, 0);
     uint8_t* buf = smem + g * kTileBuf;
+    const uint32_t bufa = tc::smem_u32(buf);
     const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
     const uint32_t tm1 = tmem_base + lane_off + g * 192;           // acc1 main | small (32 + 32 columns)
     const uint32_t tm2 = tm1 + 64;                                  // acc2 main | small (64 + 64 columns)
-    float4* stg_hi = reinterpret_cast<float4*>(buf + 2 * kPanelBytes + (wq * 32 + 2) * 128);   // this warp's own rows
-    float4* stg_lo = reinterpret_cast<float4*>(buf + 3 * kPanelBytes + (wq * 32 + 2) * 128);
+    const uint32_t stg_hi = tc::smem_u32(buf) + 2 * kPanelBytes + (wq * 32 + 2) * 128;   // this warp's own rows
+    const uint32_t stg_lo = stg_hi + kPanelBytes;
     uint32_t it = 0;
     for (int id = blockIdx.x + g * gridDim.x; id < vtiles; id += 2 * gridDim.x) {
       const int b = id % p.B;
@@ -166,6 +168,14 @@ front_fused_kernel(const __grid_constant__ CUtensorMap tmW1_hi, const __grid_con
         for (int k = 0; k < 7; ++k) {
           const int tt = t - 6 + k;
           xv[k] = (tt >= 0 && tt < L) ? __ldg(xb + tt) : 0.f;
+        }
+        {   // pull the next tile's samples towards L1 while this tile computes
+          const int nid = id + 2 * gridDim.x;
+          if (nid < vtiles) {
+            const int nt = (nid / p.B) * kAdv - 2 + m;
+            if (nt >= 0 && nt < p.uniform_len)
+              asm volatile("prefetch.global.L1 [%0];" ::"l"(p.x + (long long)(nid % p.B) * p.x_stride + nt));
+          }
         }
 #pragma unroll
         for (int c = 0; c < 64; ++c) {
@@ -187,32 +197,27 @@ front_fused_kernel(const __grid_constant__ CUtensorMap tmW1_hi, const __grid_con
             split_tf32(live ? elu_fast(a0[c + 1]) : 0.f, h4.y, l4.y);
             split_tf32(live ? elu_fast(a0[c + 2]) : 0.f, h4.z, l4.z);
             split_tf32(live ? elu_fast(a0[c + 3]) : 0.f, h4.w, l4.w);
-            const int off = row * 128 + ((q ^ key) << 4);
-            *reinterpret_cast<float4*>(buf + pn * kPanelBytes + off) = h4;
-            *reinterpret_cast<float4*>(buf + (2 + pn) * kPanelBytes + off) = l4;
+            const uint32_t off = bufa + (uint32_t)(row * 128 + ((q ^ key) << 4));
+            sts128(off + pn * kPanelBytes, h4);
+            sts128(off + (2 + pn) * kPanelBytes, l4);
           }
         fence_async_smem();
         wg_sync();
         if (issuer) {
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t bufa = tc::smem_u32(buf);
           const uint32_t main1 = tmem_base + g * 192, small1 = main1 + 32;
 #pragma unroll
           for (int kb = 0; kb < 6; ++kb) {
             const int tau = kb >> 1, pn = kb & 1;
             const uint32_t a_hi = bufa + pn * kPanelBytes + tau * 128;
             const uint32_t a_lo = a_hi + 2 * kPanelBytes;
-            const uint32_t b_hi = tc::smem_u32(w1_hi) + kb * kW1Block;
-            const uint32_t b_lo = tc::smem_u32(w1_lo) + kb * kW1Block;
+            const uint32_t b_st = tc::smem_u32(w1) + (2 * kb) * kW1Block;      // [hi | lo] stacked, N = 64
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              tc::umma_tf32(main1, tc::make_smem_desc(a_hi + k * 32), tc::make_smem_desc(b_hi + k * 32), idesc1, (uint32_t)((kb | k) != 0));
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              tc::umma_tf32(small1, tc::make_smem_desc(a_lo + k * 32), tc::make_smem_desc(b_hi + k * 32), idesc1, (uint32_t)((kb | k) != 0));
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              tc::umma_tf32(small1, tc::make_smem_desc(a_hi + k * 32), tc::make_smem_desc(b_lo + k * 32), idesc1, 1u);
+            for (int k = 0; k < 4; ++k) {
+              // columns [0,32) += A_hi W_hi^T (main), columns [32,64) += A_hi W_lo^T; then [32,64) += A_lo W_hi^T
+              tc::umma_tf32(main1, tc::make_smem_desc(a_hi + k * 32), tc::make_smem_desc(b_st + k * 32), idesc64, (uint32_t)((kb | k) != 0));
+              tc::umma_tf32(small1, tc::make_smem_desc(a_lo + k * 32), tc::make_smem_desc(b_st + k * 32), idesc32, 1u);
+            }
           }
           tc::umma_commit(&acc1_full[g]);
         }
@@ -235,28 +240,24 @@ front_fused_kernel(const __grid_constant__ CUtensorMap tmW1_hi, const __grid_con
           for (int j = 0; j < 4; ++j)
             v[j] = elu_fast(__uint_as_float(rm[q * 4 + j]) + __uint_as_float(rs[q * 4 + j]) + cst.b1[q * 4 + j]);
           split_tf32(v[0], h4.x, l4.x); split_tf32(v[1], h4.y, l4.y); split_tf32(v[2], h4.z, l4.z); split_tf32(v[3], h4.w, l4.w);
-          const int off = m * 128 + ((q ^ key) << 4);
-          *reinterpret_cast<float4*>(buf + off) = h4;
-          *reinterpret_cast<float4*>(buf + kPanelBytes + off) = l4;
+          const uint32_t off = bufa + (uint32_t)(m * 128 + ((q ^ key) << 4));
+          sts128(off, h4);
+          sts128(off + kPanelBytes, l4);
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         fence_async_smem();
         wg_sync();
         if (issuer) {
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t a_hi = tc::smem_u32(buf);                       // R1 operand aliases hi panel 0 / hi panel 1
+          const uint32_t a_hi = bufa;                                    // R1 operand aliases hi panel 0 / hi panel 1
           const uint32_t a_lo = a_hi + kPanelBytes;
-          const uint32_t b_hi = tc::smem_u32(w2_hi), b_lo = tc::smem_u32(w2_lo);
+          const uint32_t b_st = tc::smem_u32(w2);                        // [hi | lo] stacked, N = 128
           const uint32_t main2 = tmem_base + g * 192 + 64, small2 = main2 + 64;
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            tc::umma_tf32(main2, tc::make_smem_desc(a_hi + k * 32), tc::make_smem_desc(b_hi + k * 32), idesc2, (uint32_t)(k != 0));
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            tc::umma_tf32(small2, tc::make_smem_desc(a_lo + k * 32), tc::make_smem_desc(b_hi + k * 32), idesc2, (uint32_t)(k != 0));
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            tc::umma_tf32(small2, tc::make_smem_desc(a_hi + k * 32), tc::make_smem_desc(b_lo + k * 32), idesc2, 1u);
+          for (int k = 0; k < 4; ++k) {
+            tc::umma_tf32(main2, tc::make_smem_desc(a_hi + k * 32), tc::make_smem_desc(b_st + k * 32), idesc128, (uint32_t)(k != 0));
+            tc::umma_tf32(small2, tc::make_smem_desc(a_lo + k * 32), tc::make_smem_desc(b_st + k * 32), idesc64, 1u);
+          }
           tc::umma_commit(&acc2_full[g]);
         }
         __syncwarp();
@@ -283,16 +284,24 @@ front_fused_kernel(const __grid_constant__ CUtensorMap tmW1_hi, const __grid_con
               v[j] = elu_fast((__uint_as_float(rm[q * 4 + j]) + __uint_as_float(rs[q * 4 + j])) + cst.b2[c] + a0[c]);
             }
             split_tf32(v[0], h4.x, l4.x); split_tf32(v[1], h4.y, l4.y); split_tf32(v[2], h4.z, l4.z); split_tf32(v[3], h4.w, l4.w);
-            stg_hi[lane * 8 + (q ^ key)] = h4;
-            stg_lo[lane * 8 + (q ^ key)] = l4;
+            sts128(stg_hi + (uint32_t)(lane * 8 + (q ^ key)) * 16u, h4);
+            sts128(stg_lo + (uint32_t)(lane * 8 + (q ^ key)) * 16u, l4);
           }
           __syncwarp();
+          float4 hv[8], lv[8];
 #pragma unroll
           for (int i8 = 0; i8 < 8; ++i8) {
             const int r = i8 * 4 + (lane >> 3);        // row inside this warp's 32
             const int cj = lane & 7;
-            const float4 h4 = stg_hi[r * 8 + (cj ^ (r & 7))];
-            const float4 l4 = stg_lo[r * 8 + (cj ^ (r & 7))];
+            hv[i8] = lds128(stg_hi + (uint32_t)(r * 8 + (cj ^ (r & 7))) * 16u);
+            lv[i8] = lds128(stg_lo + (uint32_t)(r * 8 + (cj ^ (r & 7))) * 16u);
+          }
+#pragma unroll
+          for (int i8 = 0; i8 < 8; ++i8) {
+            const int r = i8 * 4 + (lane >> 3);
+            const int cj = lane & 7;
+            const float4 h4 = hv[i8];
+            const float4 l4 = lv[i8];
             const int mm = wq * 32 + r;
             const int tt = t0 - 2 + mm;
             if (mm >= 2 && tt < L) {

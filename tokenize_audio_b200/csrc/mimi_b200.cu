@@ -361,6 +361,7 @@ int mimi_b200_create(mimi_b200_t** out, int device_ordinal) {
   if ((e = cudaSetDevice(device_ordinal)) != cudaSuccess) { delete h; return fail(nullptr, MIMI_B200_ERR_CUDA, cudaGetErrorString(e)); }
   for (int i = 0; i < kStageSlots; ++i) cudaEventCreateWithFlags(&h->stage_ev[i], cudaEventDisableTiming);
   cudaFuncSetAttribute(swa_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttSmemBytes);
+  cudaFuncSetAttribute(swa_attention2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAtt2SmemBytes);
   cudaFuncSetAttribute(rvq_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRvqSmemBytes);
   cudaFuncSetAttribute(tc::tc_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::smem_bytes(128));
   cudaFuncSetAttribute(tc::tc_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::smem_bytes(64));

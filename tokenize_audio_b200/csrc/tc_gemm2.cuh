@@ -219,7 +219,7 @@ tc2_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     const int half = ew >> 2;                      // which half of the BN columns
     const int col0 = half * HALF;
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-    float4* stg = reinterpret_cast<float4*>(stg_base + ew * C::STG_WARP);   // [32 rows][LPR float4], swizzled
+    const uint32_t stg = tc::smem_u32(stg_base + ew * C::STG_WARP);         // [32 rows][LPR float4], swizzled
     const int rr = lane / LPR;                     // coalesced phase: row within an RPI-row group
     const int cj = lane % LPR;                     //                  float4 index inside the PC-wide piece
     uint32_t cc = 0, lt = 0;
@@ -276,14 +276,20 @@ tc2_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
             const float4 t = ld_nc_f4(ep.scale + c);
             v.x *= t.x; v.y *= t.y; v.z *= t.z; v.w *= t.w;
           }
-          stg[lane * LPR + (j ^ wkey)] = v;
+          sts128(stg + (uint32_t)(lane * LPR + (j ^ wkey)) * 16u, v);
         }
         __syncwarp();
+        float4 tv[IT];
 #pragma unroll
         for (int it = 0; it < IT; ++it) {
           const int r = it * RPI + rr;               // row within this warp's 32
           const int rkey = (LPR == 8) ? (r & 7) : ((r >> 1) & (LPR - 1));
-          float4 v = stg[r * LPR + (cj ^ rkey)];
+          tv[it] = lds128(stg + (uint32_t)(r * LPR + (cj ^ rkey)) * 16u);
+        }
+#pragma unroll
+        for (int it = 0; it < IT; ++it) {
+          const int r = it * RPI + rr;
+          float4 v = tv[it];
           const int row = row_base + r;
           if (row < Lout) {
             const long long o = (long long)row * ep.N + p * PC + cj * 4;
