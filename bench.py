@@ -194,6 +194,7 @@ def run_b200(args, rank, world, local_rank):
         dev_batches.append((x.to(dev), [len(c) for c in cl]))
     # one workspace sized for the longest batch up front (a shard driver knows its longest bucket too)
     model.reserve_workspace(BATCH, max(x.shape[2] for x, _ in dev_batches), K_CODEBOOKS)
+    wrapper.reserve(BATCH, max(x.shape[2] for x, _ in dev_batches))
     audio_s = [sum(l) / SR for _, l in dev_batches]
     computed_s = [sum(min(x.shape[2], -(-n // 1920) * 1920) for n in l) / SR for x, l in dev_batches]
 

@@ -322,7 +322,8 @@ class MimiEncoder:
     ``transformers.MimiModel`` whose weights are taken over. ``num_quantizers=None`` returns all 32
     codebooks like the reference (whose callers then slice ``[:8]``); pass 8 to compute only those."""
 
-    def __init__(self, model, device: str = "cuda", ragged: bool = True, num_quantizers: Optional[int] = None):
+    def __init__(self, model, device: str = "cuda", ragged: bool = True, num_quantizers: Optional[int] = None,
+                 chunk_items: int = 16, stage_threads: int = 1):
         self.device = device
         self.feature_extractor = EncodecFeatureExtractorLite()
         if isinstance(model, MimiB200Model):
@@ -335,29 +336,73 @@ class MimiEncoder:
             self.model = MimiB200Model.from_transformers(model, device=device)
         self.ragged = ragged
         self.num_quantizers = num_quantizers
+        # ragged mode encodes a batch as sub-batches of `chunk_items` items so that host staging of the next
+        # sub-batch overlaps the GPU work of the previous one (items are independent, results identical)
+        self.chunk_items = max(1, int(chunk_items))
         self._pinned: Optional[torch.Tensor] = None
+        self._dev_in: Optional[torch.Tensor] = None
+        self._pinned_codes: Optional[torch.Tensor] = None
+        self._copy_stream: Optional[torch.cuda.Stream] = None
+        self._pool = None
+        if stage_threads > 1:
+            from concurrent.futures import ThreadPoolExecutor
+            self._pool = ThreadPoolExecutor(max_workers=int(stage_threads), thread_name_prefix="mimi-stage")
 
-    def _stage(self, audio_arrays: Sequence[np.ndarray], sample_rate: int) -> torch.Tensor:
-        """What ``feature_extractor(..., padding=True)`` + ``.to(device)`` do in the reference
-        (REF/emilia-mimi/process_shard.py:113-121), as one pinned staging buffer and one H2D copy: fp32
-        cast, zero right-padding to the longest item -> ``input_values [B,1,N]`` on the device. The
-        ``padding_mask`` is never shipped: the model ignores it and the lengths are known here."""
+    def reserve(self, batch: int, max_samples: int) -> None:
+        """Pre-size the pinned staging buffers (and the model workspace) for batches of up to ``batch`` items
+        of up to ``max_samples`` samples, so that no later call has to pin fresh host memory (tens of ms)."""
+        K = NUM_QUANTIZERS if self.num_quantizers is None else int(self.num_quantizers)
+        self._grow_pinned(batch * max_samples, batch * K * (-(-max_samples // FRAME_SIZE)))
+        self.model.reserve_workspace(min(batch, self.chunk_items) if self.ragged else batch, max_samples, K)
+
+    def _grow_pinned(self, samples: int, codes: int) -> None:
+        if self._pinned is None or self._pinned.numel() < samples:
+            self._pinned = self._dev_in = None
+            self._pinned = torch.empty(max(int(samples * 1.25), 1), dtype=torch.float32).pin_memory()
+            # device-side landing buffer of the same size: no allocator traffic on the hot path
+            self._dev_in = torch.empty(self._pinned.numel(), dtype=torch.float32, device=self.model.device)
+        if self._pinned_codes is None or self._pinned_codes.numel() < codes:
+            self._pinned_codes = None
+            self._pinned_codes = torch.empty(max(int(codes * 1.25), 1), dtype=torch.int64).pin_memory()
+
+    def _check_rate(self, sample_rate: int) -> None:
         if sample_rate != self.feature_extractor.sampling_rate:
             self.feature_extractor(raw_audio=np.zeros(1, np.float32), sampling_rate=sample_rate)   # raises ValueError
-        B = len(audio_arrays)
-        N = max(len(a) for a in audio_arrays)
-        if self._pinned is None or self._pinned.numel() < B * N:
-            self._pinned = torch.empty(max(B * N, 1), dtype=torch.float32).pin_memory()
-        buf = self._pinned[: B * N].view(B, 1, N)
-        for i, a in enumerate(audio_arrays):
-            a = np.asarray(a)
+
+    def _pinned_view(self, offset: int, B: int, N: int) -> torch.Tensor:
+        return self._pinned[offset: offset + B * N].view(B, 1, N)
+
+    def _fill(self, buf: torch.Tensor, audio_arrays: Sequence[np.ndarray], zero_to: Sequence[int]) -> None:
+        """fp32 cast + right zero-padding of every item into the pinned ``[B,1,N]`` view (what
+        ``feature_extractor(..., padding=True)`` does, REF/emilia-mimi/process_shard.py:113-118). ``zero_to[i]``
+        is how far item i's padding has to be materialised (N in strict mode; the end of its last kept frame
+        in ragged mode, nothing beyond that is ever read)."""
+        def one(i):
+            a = np.asarray(audio_arrays[i])
             if a.ndim != 1:
                 raise ValueError(f"Expected mono audio but example has {a.shape[-1]} channels")
             n = a.shape[0]
             buf[i, 0, :n].copy_(torch.from_numpy(np.ascontiguousarray(a)))       # casts float64 -> float32
-            if n < N:
-                buf[i, 0, n:].zero_()
-        return buf.to(self.model.device, non_blocking=True)
+            if n < zero_to[i]:
+                buf[i, 0, n:zero_to[i]].zero_()
+        if self._pool is None or len(audio_arrays) < 4:
+            for i in range(len(audio_arrays)):
+                one(i)
+        else:
+            list(self._pool.map(one, range(len(audio_arrays))))
+
+    def _stage(self, audio_arrays: Sequence[np.ndarray], sample_rate: int) -> torch.Tensor:
+        """One pinned staging buffer and one H2D copy -> ``input_values [B,1,N]`` on the device. The
+        ``padding_mask`` is never shipped: the model ignores it and the lengths are known here."""
+        self._check_rate(sample_rate)
+        B = len(audio_arrays)
+        N = max(len(a) for a in audio_arrays)
+        self._grow_pinned(B * N, 0)
+        buf = self._pinned_view(0, B, N)
+        self._fill(buf, audio_arrays, [N] * B)
+        x = self._dev_in[: B * N].view(B, 1, N)
+        x.copy_(buf, non_blocking=True)
+        return x
 
     def encode_audio_chunk(self, audio_array: np.ndarray, sample_rate: int = 24000) -> np.ndarray:
         """REF/emilia-mimi/process_shard.py:63-86: one utterance -> codes ``[K, T]`` (numpy int64)."""
@@ -368,17 +413,64 @@ class MimiEncoder:
 
     def encode_audio_batch(self, audio_arrays: List[np.ndarray], sample_rate: int = 24000) -> List[np.ndarray]:
         """REF/emilia-mimi/process_shard.py:88-140: pad to the longest, encode, trim item i to
-        ceil(len_i / 1920) frames. With ``ragged=True`` (default) the padded tails are not computed; the kept
-        frames are the same either way. One device->host copy per batch instead of one per item."""
+        ceil(len_i / 1920) frames. With ``ragged=True`` (default) the padded tails are not computed and the
+        batch goes through the GPU as sub-batches of ``chunk_items`` items (staging of sub-batch j+1 overlaps
+        the encode of sub-batch j); the kept frames are the same either way. One device->host copy per
+        sub-batch instead of one per item."""
         if len(audio_arrays) == 0:
             return []
         if len(audio_arrays) == 1:
             return [self.encode_audio_chunk(audio_arrays[0], sample_rate)]
+        frame_rate = sample_rate / 12.5
+        original_lengths = [len(a) for a in audio_arrays]
         with torch.no_grad():
-            original_lengths = [len(a) for a in audio_arrays]
-            x = self._stage(audio_arrays, sample_rate)
-            out = self.model.encode(input_values=x, padding_mask=None, num_quantizers=self.num_quantizers,
-                                    valid_lengths=original_lengths if self.ragged else None)
-            codes = out.audio_codes.cpu().numpy()
-            frame_rate = sample_rate / 12.5
-            return [codes[i, :, : int(np.ceil(n / frame_rate))] for i, n in enumerate(original_lengths)]
+            if not self.ragged:
+                x = self._stage(audio_arrays, sample_rate)
+                out = self.model.encode(input_values=x, padding_mask=None, num_quantizers=self.num_quantizers)
+                codes = out.audio_codes.cpu().numpy()
+                return [codes[i, :, : int(np.ceil(n / frame_rate))] for i, n in enumerate(original_lengths)]
+            self._check_rate(sample_rate)
+            B = len(audio_arrays)
+            K = NUM_QUANTIZERS if self.num_quantizers is None else int(self.num_quantizers)
+            # a small first sub-batch gets the GPU going while the rest is still being staged
+            bounds = [0, min(B, max(1, self.chunk_items // 2))]
+            while bounds[-1] < B:
+                bounds.append(min(B, bounds[-1] + max(self.chunk_items, (B - bounds[1] + 1) // 2)))
+            chunks = [list(range(a, b)) for a, b in zip(bounds[:-1], bounds[1:])]
+            n_max = [max(original_lengths[i] for i in ch) for ch in chunks]
+            total = sum(len(ch) * n for ch, n in zip(chunks, n_max))
+            t_max = [-(-n // FRAME_SIZE) for n in n_max]
+            total_codes = sum(len(ch) * K * t for ch, t in zip(chunks, t_max))
+            self._grow_pinned(total, total_codes)
+            off = coff = 0
+            host_codes = []
+            dev = self.model.device
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream(device=dev)
+            main = torch.cuda.current_stream(dev)
+            self._copy_stream.wait_stream(main)
+            for ch, N, T in zip(chunks, n_max, t_max):
+                buf = self._pinned_view(off, len(ch), N)
+                off += len(ch) * N
+                lens = [original_lengths[i] for i in ch]
+                self._fill(buf, [audio_arrays[i] for i in ch], [min(N, -(-n // FRAME_SIZE) * FRAME_SIZE) for n in lens])
+                # H2D on its own stream: the copy of sub-batch j+1 runs under the kernels of sub-batch j
+                x = self._dev_in[off - len(ch) * N: off].view(len(ch), 1, N)
+                with torch.cuda.stream(self._copy_stream):
+                    x.copy_(buf, non_blocking=True)
+                    landed = torch.cuda.Event()
+                    landed.record(self._copy_stream)
+                main.wait_event(landed)
+                out = self.model.encode(input_values=x, padding_mask=None, num_quantizers=self.num_quantizers,
+                                        valid_lengths=lens)
+                hc = self._pinned_codes[coff: coff + len(ch) * K * T].view(len(ch), K, T)
+                coff += len(ch) * K * T
+                hc.copy_(out.audio_codes, non_blocking=True)
+                host_codes.append(hc)
+            torch.cuda.current_stream(self.model.device).synchronize()
+            result: List[np.ndarray] = []
+            for ch, hc in zip(chunks, host_codes):
+                arr = hc.numpy()
+                for j, i in enumerate(ch):
+                    result.append(arr[j, :, : int(np.ceil(original_lengths[i] / frame_rate))].copy())
+            return result
