@@ -180,6 +180,8 @@ def run_b200(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     sd = synth.synth_state_dict(0)
     model = MimiB200Model(sd, device=dev)
+    if args.mode is not None:
+        model.set_mode(args.mode)
     wrapper = MimiEncoder(model, device=str(dev), ragged=True, num_quantizers=K_CODEBOOKS)
     clips, lengths, batches = make_workload(rank)
     peaks = load_peaks()
@@ -318,6 +320,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", type=int, default=None, help="debug: kernel generation (see MimiB200Model.set_mode)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

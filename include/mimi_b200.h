@@ -131,7 +131,9 @@ int mimi_b200_debug_tap(mimi_b200_t* h, int which, float* d_out, size_t out_capa
    leave d_codes untouched), key 2 = per-launch CUDA-event profiling on/off (resets the profile), key 3 =
    compute mode: 3 (default) = mode 2 plus the fused 24 kHz front end (front_fused.cuh: L0 + ResBlock 1 in one
    kernel); 2 = every GEMM-shaped layer on the persistent tcgen05 3xTF32 kernel (tc_gemm2.cuh),
-   1 = first-generation tcgen05 kernel for the wide layers (level 0 on FFMA), 0 = all-fp32 FFMA. */
+   1 = first-generation tcgen05 kernel for the wide layers (level 0 on FFMA), 0 = all-fp32 FFMA;
+   key 4 / key 5 = accuracy experiments on the persistent kernel: cross terms into the main accumulator (0/1),
+   k-blocks per accumulation chunk (0 = default 4). */
 int mimi_b200_debug_set(mimi_b200_t* h, int key, int value);
 
 /* Read and reset the per-launch profile gathered since profiling was switched on: for launch kind

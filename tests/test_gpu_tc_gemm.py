@@ -20,7 +20,7 @@ def engine():
     lib.mimi_b200_destroy(h)
 
 
-@pytest.mark.parametrize("mode", [2, 1])
+@pytest.mark.parametrize("mode", [4, 2, 1])
 @pytest.mark.parametrize("M,N,K,act,bias", [
     (128, 128, 32, 0, False), (300, 128, 512, 0, True), (77, 64, 384, 0, True), (1000, 256, 1280, 0, False),
     (60, 2048, 512, 1, False), (130, 512, 2048, 0, True), (257, 1024, 8192, 0, True), (64, 1536, 512, 0, False),
@@ -28,8 +28,8 @@ def engine():
 ])
 def test_tc_gemm_matches_float64(engine, M, N, K, act, bias, mode):
     lib, h = engine
-    if mode == 1 and N % 64:
-        pytest.skip("first-generation kernel has no BN=32 instance")
+    if mode in (1, 4) and N % 64:
+        pytest.skip("only the second-generation kernel has a BN=32 instance")
     _lib.check(lib, h, lib.mimi_b200_debug_set(h, 3, mode), "debug_set")
     g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
     a = torch.randn(M, K, generator=g) * 2.0
@@ -48,4 +48,5 @@ def test_tc_gemm_matches_float64(engine, M, N, K, act, bias, mode):
     if act:
         ref = torch.nn.functional.gelu(ref)
     err = (out.cpu().double() - ref).norm() / ref.norm()
-    assert err <= 1e-6, f"relative error {err:.2e}"
+    tol = 1.5e-6 if mode == 4 else 1e-6     # mode 4 folds the cross terms into the main accumulator (chunks of K=64)
+    assert err <= tol, f"relative error {err:.2e}"

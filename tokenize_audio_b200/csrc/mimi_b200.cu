@@ -22,6 +22,7 @@
 #include "tc_gemm.cuh"
 #include "tc_gemm2.cuh"
 #include "front_fused.cuh"
+#include "tc_gemm3.cuh"
 #include "transformer.cuh"
 
 using namespace mimi;
@@ -60,7 +61,8 @@ struct TapInfo { long long off; int level; int C; };
 struct TcWeight {
   float* hi = nullptr;
   float* lo = nullptr;
-  CUtensorMap map_hi, map_lo;
+  CUtensorMap map_hi, map_lo;              // box 32 x BN
+  CUtensorMap map64_hi, map64_lo;          // box 32 x 64 (tc_gemm3 when BN would be 32... or N % 128 != 0)
   int N = 0, K = 0, BN = 0;
 };
 // hi/lo activation pair, channels-last with `front` zero halo rows before row 0 of every item
@@ -78,7 +80,7 @@ struct PlanTC {
   size_t bytes = 0;
 };
 
-struct MapSet { std::vector<CUtensorMap> maps; uint64_t built = 0; };
+struct MapSet { std::vector<CUtensorMap> maps, maps3; uint64_t built = 0, built3 = 0; };
 struct MapKey {
   const void* ws; int B; long long N;
   bool operator<(const MapKey& o) const {
@@ -131,10 +133,12 @@ struct mimi_b200 {
   Plan last;
   void* last_ws = nullptr;
   // tensor-core path
-  int mode = 3;                                // 3 = mode 2 + fused 24 kHz front end (front_fused.cuh),
+  int mode = 3;                                // 4 = mode 3 with the experimental third-generation GEMM (tc_gemm3.cuh),
+                                               // 3 = mode 2 + fused 24 kHz front end (front_fused.cuh),
                                                // 2 = persistent tcgen05 3xTF32 kernel for every GEMM-shaped layer,
                                                // 1 = first-generation tcgen05 kernel (level 0 on FFMA), 0 = all-fp32 SIMT
   int last_mode = 0;
+  int exp_single_acc = 0, exp_chunk_kb = 0;    // accuracy experiments (debug_set keys 4, 5)
   f0::Consts f0_consts;
   int num_sms = 148;
   PFN_cuTensorMapEncodeTiled_v12000 encode_tiled = nullptr;
@@ -368,6 +372,8 @@ int mimi_b200_create(mimi_b200_t** out, int device_ordinal) {
   cudaFuncSetAttribute(tc2::tc2_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::Cfg<128>::SMEM);
   cudaFuncSetAttribute(tc2::tc2_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::Cfg<64>::SMEM);
   cudaFuncSetAttribute(tc2::tc2_gemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::Cfg<32>::SMEM);
+  cudaFuncSetAttribute(tc3::tc3_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc3::Cfg<128>::SMEM);
+  cudaFuncSetAttribute(tc3::tc3_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc3::Cfg<64>::SMEM);
   cudaFuncSetAttribute(f0::front_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, f0::kSmem);
   cudaFuncSetAttribute(tc2::tc_shift_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 40960);
   if ((e = cudaGetLastError()) != cudaSuccess) { delete h; return fail(nullptr, MIMI_B200_ERR_CUDA, cudaGetErrorString(e)); }
@@ -395,7 +401,9 @@ int mimi_b200_debug_set(mimi_b200_t* h, int key, int value) {
   if (key == 0) h->dbg_layers = std::min(std::max(value, 0), MIMI_B200_NUM_LAYERS);
   else if (key == 1) h->dbg_last_conv = std::min(std::max(value, 0), MIMI_B200_NUM_CONVS - 1);
   else if (key == 2) { h->prof_on = value != 0; h->prof_n = 0; }
-  else if (key == 3) h->mode = std::min(std::max(value, 0), 3);
+  else if (key == 3) h->mode = std::min(std::max(value, 0), 4);
+  else if (key == 4) h->exp_single_acc = value != 0;
+  else if (key == 5) h->exp_chunk_kb = std::max(value, 0);
   else return fail(h, MIMI_B200_ERR_ARG, "debug_set: unknown key");
   return MIMI_B200_OK;
 }
@@ -734,7 +742,7 @@ int mimi_b200_debug_tap(mimi_b200_t* h, int which, float* d_out, size_t cap, int
   TapInfo t{};
   if (h->last_was_tc) {
     const PlanTC& q = h->last_tc;
-    if (h->last_mode == 3 && which < 3) return fail(h, MIMI_B200_ERR_ARG, "debug_tap: level-0 activations stay on chip in mode 3");
+    if (h->last_mode >= 3 && which < 3) return fail(h, MIMI_B200_ERR_ARG, "debug_tap: level-0 activations stay on chip in mode 3");
     switch (which) {
       case 0: t = {q.a0, 0, 64}; break;
       case 1: t = {q.r1, 0, 32}; break;
@@ -786,7 +794,7 @@ __global__ void debug_split_kernel(const float* __restrict__ x, float* __restric
 int mimi_b200_debug_tc_gemm(mimi_b200_t* h, const float* d_a, const float* h_w, const float* d_bias_opt, int M, int N,
                             int K, int act, float* d_out, void* stream) {
   if (!h || !d_a || !h_w || !d_out) return fail(h, MIMI_B200_ERR_ARG, "debug_tc_gemm: NULL argument");
-  if (M <= 0 || N % 32 || K % 32 || (h->mode < 2 && N % 64))
+  if (M <= 0 || N % 32 || K % 32 || ((h->mode < 2 || h->mode >= 4) && N % 64))
     return fail(h, MIMI_B200_ERR_ARG, "debug_tc_gemm: need N % 32 == 0 (mode 2) / N % 64 == 0 (mode 1) and K % 32 == 0");
   CUDA_TRY(h, cudaSetDevice(h->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -807,7 +815,13 @@ int mimi_b200_debug_tc_gemm(mimi_b200_t* h, const float* d_a, const float* h_w, 
   tc::Epilogue ep{};
   ep.bias = d_bias_opt; ep.out_raw = d_out; ep.raw_item_stride = (long long)M * N; ep.act = act;
   ep.uniform_len_in = M; ep.conv_stride = 1; ep.N = N;
-  if (h->mode >= 2) {
+  ep.single_acc = h->exp_single_acc; ep.chunk_kb = h->exp_chunk_kb;
+  if (h->mode >= 4) {
+    CUtensorMap m4[4];
+    for (int i = 0; i < 4; ++i)
+      if ((rc = tc_make_map4(h, &m4[i], (i & 1) ? lo : hi, K, 1, M, 1, n, 128))) return rc;
+    if ((rc = launch_tc3(h, m4, w, ep, 1, M, K, 1, 1, st))) return rc;
+  } else if (h->mode >= 2) {
     launch_tc2(h, ma_hi, ma_lo, w, ep, 1, (M + tc::kBM - 1) / tc::kBM, st);
   } else {
     dim3 grid((M + tc::kBM - 1) / tc::kBM, N / w.BN, 1);

@@ -43,6 +43,8 @@ struct Epilogue {
   int uniform_len_in;
   int conv_stride;              // Lout = ceil(len_in / conv_stride)
   int N;
+  int single_acc;               // experiment (tc_gemm2 only): cross terms accumulate into the main accumulator
+  int chunk_kb;                 // experiment (tc_gemm2 only): k-blocks per accumulation chunk (0 -> kChunkKB)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

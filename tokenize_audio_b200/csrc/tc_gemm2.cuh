@@ -115,7 +115,8 @@ tc2_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = K / kBK;
-  const int nchunks = (nkb + kChunkKB - 1) / kChunkKB;
+  const int ckb = ep.chunk_kb > 0 ? ep.chunk_kb : kChunkKB;
+  const int nchunks = (nkb + ckb - 1) / ckb;
   const int vtiles = sc.mt_max * sc.B * sc.ntn;
 
   if (warp == 0 && lane == 0) {
@@ -183,8 +184,8 @@ tc2_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
           tc::mbar_wait(&acc_empty[buf], ((cc >> 1) & 1u) ^ 1u);         // drained two chunks ago
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t tmem_main = tmem_base + buf * BN;
-          const int kb_end = min(nkb, (c + 1) * kChunkKB);
-          for (int kb = c * kChunkKB; kb < kb_end; ++kb, ++kbc) {
+          const int kb_end = min(nkb, (c + 1) * ckb);
+          for (int kb = c * ckb; kb < kb_end; ++kb, ++kbc) {
             const uint32_t s = kbc % STAGES;
             const uint32_t ph = (kbc / STAGES) & 1u;
             tc::mbar_wait(&full_bar[s], ph);
@@ -193,18 +194,20 @@ tc2_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
             const uint32_t a_lo = a_hi + A_BYTES;
             const uint32_t w_hi = a_hi + 2 * A_BYTES;
             const uint32_t w_lo = w_hi + W_BYTES;
-            const bool first_in_chunk = kb == c * kChunkKB;
+            const bool first_in_chunk = kb == c * ckb;
+            const uint32_t tmem_x = ep.single_acc ? tmem_main : tmem_small;
+            const uint32_t xacc = ep.single_acc ? 1u : (uint32_t)(kb != 0);
 #pragma unroll
             for (int k = 0; k < kBK / kUmmaK; ++k)
               tc::umma_tf32(tmem_main, tc::make_smem_desc(a_hi + k * 32), tc::make_smem_desc(w_hi + k * 32), idesc,
                             !(first_in_chunk && k == 0));
 #pragma unroll
             for (int k = 0; k < kBK / kUmmaK; ++k)
-              tc::umma_tf32(tmem_small, tc::make_smem_desc(a_lo + k * 32), tc::make_smem_desc(w_hi + k * 32), idesc,
-                            (uint32_t)((kb | k) != 0));
+              tc::umma_tf32(tmem_x, tc::make_smem_desc(a_lo + k * 32), tc::make_smem_desc(w_hi + k * 32), idesc,
+                            k != 0 ? 1u : xacc);
 #pragma unroll
             for (int k = 0; k < kBK / kUmmaK; ++k)
-              tc::umma_tf32(tmem_small, tc::make_smem_desc(a_hi + k * 32), tc::make_smem_desc(w_lo + k * 32), idesc, 1u);
+              tc::umma_tf32(tmem_x, tc::make_smem_desc(a_hi + k * 32), tc::make_smem_desc(w_lo + k * 32), idesc, 1u);
             tc::umma_commit(&empty_bar[s]);
           }
           tc::umma_commit(&acc_full[buf]);       // after the tile's last chunk this also covers the cross terms
@@ -240,7 +243,7 @@ tc2_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       }
       {
         const uint32_t tp = lt & 1u;
-        drain_add<HALF>(tmem_base + lane_off + (2u + tp) * BN + (uint32_t)col0, acc);
+        if (!ep.single_acc) drain_add<HALF>(tmem_base + lane_off + (2u + tp) * BN + (uint32_t)col0, acc);
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&small_empty[tp]);

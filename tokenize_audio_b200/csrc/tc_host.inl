@@ -27,6 +27,23 @@ static int tc_make_map(mimi_b200* h, CUtensorMap* out, const float* base, int ra
   return MIMI_B200_OK;
 }
 
+// activation "plane" map for tc_gemm3: dims {C, stride, q, item}, element (c, ph, q, b) = row q*stride + ph, channel c of
+// item b (row 0 = first padded row); box {32, 1, box_rows, 1}, SWIZZLE_128B
+static int tc_make_map4(mimi_b200* h, CUtensorMap* out, const float* base, int C, int stride, long long q_rows, int B,
+                        long long item_stride_floats, int box_rows) {
+  const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)stride, (cuuint64_t)std::max<long long>(q_rows, 1), (cuuint64_t)B};
+  const cuuint64_t strides[3] = {(cuuint64_t)C * sizeof(float), (cuuint64_t)stride * C * sizeof(float),
+                                 (cuuint64_t)item_stride_floats * sizeof(float)};
+  cuuint32_t box[4] = {(cuuint32_t)tc::kBK, 1, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = h->encode_tiled(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(h, MIMI_B200_ERR_CUDA, "cuTensorMapEncodeTiled (4-D plane map) failed with CUresult " + std::to_string((int)r));
+  return MIMI_B200_OK;
+}
+
 // w_nk: host [N][K] K-major. Splits into TF32 hi/lo, uploads, builds the two weight maps.
 static int tc_make_weight(mimi_b200* h, TcWeight* w, const std::vector<float>& w_nk, int N, int K) {
   std::vector<float> hi(w_nk.size()), lo(w_nk.size());
@@ -39,6 +56,10 @@ static int tc_make_weight(mimi_b200* h, TcWeight* w, const std::vector<float>& w
   const cuuint64_t strides[1] = {(cuuint64_t)K * sizeof(float)};
   if ((rc = tc_make_map(h, &w->map_hi, w->hi, 2, dims, strides, w->BN))) return rc;
   if ((rc = tc_make_map(h, &w->map_lo, w->lo, 2, dims, strides, w->BN))) return rc;
+  if (N % 64 == 0) {   // tc_gemm3 has no BN = 32 instance: an extra 64-row box for it
+    if ((rc = tc_make_map(h, &w->map64_hi, w->hi, 2, dims, strides, 64))) return rc;
+    if ((rc = tc_make_map(h, &w->map64_lo, w->lo, 2, dims, strides, 64))) return rc;
+  }
   return MIMI_B200_OK;
 }
 
@@ -121,9 +142,51 @@ struct TcCtx {
   const int* maxlen;          // [6]
   std::vector<CUtensorMap>* maps;   // 2 maps (hi, lo) per GEMM site, indexed by a fixed slot id
   uint64_t* built;                  // bit `slot` set once that site's maps are encoded
+  std::vector<CUtensorMap>* maps3;  // 4 plane maps per GEMM site (tc_gemm3)
+  uint64_t* built3;
 };
 constexpr int kTcSlots = 48;
 }  // namespace
+
+// third-generation kernel: 256-row tiles, plane-staged activations (4 maps per site: hi/lo x first/second box)
+static int launch_tc3(mimi_b200* h, const CUtensorMap* m4, const TcWeight& w, const tc::Epilogue& ep, int B, int lout_max,
+                      int C, int k, int s, cudaStream_t st) {
+  tc3::Geom gm{};
+  gm.G = k / s; gm.s = s; gm.cpanels = C / 32; gm.B = B; gm.mt_max = (lout_max + tc3::kBM - 1) / tc3::kBM;
+  const int bn = (w.N % 128 == 0) ? 128 : 64;
+  gm.ntn = w.N / bn; gm.chunk_kb = h->exp_chunk_kb;
+  const long long vt = (long long)gm.mt_max * B * gm.ntn;
+  const int grid = (int)std::min<long long>(vt, h->num_sms);
+  if (grid <= 0) return MIMI_B200_OK;
+  if (k % s || C % 32 || gm.G > 3) return fail(h, MIMI_B200_ERR_ARG, "tc3: unsupported conv geometry");
+  const CUtensorMap& wh = (bn == w.BN) ? w.map_hi : w.map64_hi;
+  const CUtensorMap& wl = (bn == w.BN) ? w.map_lo : w.map64_lo;
+  if (bn == 128)
+    tc3::tc3_gemm_kernel<128><<<grid, tc3::kThreads, tc3::Cfg<128>::SMEM, st>>>(m4[0], m4[1], m4[2], m4[3], wh, wl, ep, gm);
+  else
+    tc3::tc3_gemm_kernel<64><<<grid, tc3::kThreads, tc3::Cfg<64>::SMEM, st>>>(m4[0], m4[1], m4[2], m4[3], wh, wl, ep, gm);
+  return MIMI_B200_OK;
+}
+
+// plane maps of a conv/linear that reads SplitBuf `a` (kernel k, stride s, left pad `pad`): [hi box1, lo box1, hi box2, lo box2]
+static int tc_amaps3(TcCtx& c, int slot, const SplitBuf& a, int k, int s, int pad, const CUtensorMap** out4) {
+  CUtensorMap* m = &(*c.maps3)[4 * slot];
+  if (!((*c.built3 >> slot) & 1ull)) {
+    const PlanTC& p = *c.p;
+    const int G = k / s;
+    const long long rows_out = (p.rows[a.level] + s - 1) / s;
+    if (a.front < pad) return fail(c.h, MIMI_B200_ERR_ARG, "tc: halo smaller than conv padding");
+    const long long base_off = (long long)(a.front - pad) * a.C;
+    int rc;
+    for (int i = 0; i < 4; ++i) {
+      const float* base = c.ws + ((i & 1) ? a.lo : a.hi) + base_off;
+      if ((rc = tc_make_map4(c.h, &m[i], base, a.C, s, rows_out + G - 1, c.B, a.item_stride, (i < 2) ? 128 : 128 + G - 1))) return rc;
+    }
+    *c.built3 |= 1ull << slot;
+  }
+  *out4 = m;
+  return MIMI_B200_OK;
+}
 
 // activation maps for a conv/linear that reads SplitBuf `a` with kernel k, stride s, left pad `pad`
 static int tc_amaps(TcCtx& c, int slot, const SplitBuf& a, int k, int s, int pad, const CUtensorMap** hi, const CUtensorMap** lo) {
@@ -173,10 +236,12 @@ static void launch_tc2(mimi_b200* h, const CUtensorMap& ahi, const CUtensorMap& 
 }
 
 static int tc_gemm(TcCtx& c, int slot, const SplitBuf& a, int k, int s, int pad, const TcWeight& w, const TcOut& o, int prof_id) {
-  const CUtensorMap *ahi, *alo;
+  const CUtensorMap *ahi = nullptr, *alo = nullptr, *m4 = nullptr;
   int rc;
   if (slot < 0 || slot >= kTcSlots) return fail(c.h, MIMI_B200_ERR_ARG, "tc: bad map slot");
-  if ((rc = tc_amaps(c, slot, a, k, s, pad, &ahi, &alo))) return rc;
+  const bool v3 = c.h->mode >= 4;
+  if (v3) { if ((rc = tc_amaps3(c, slot, a, k, s, pad, &m4))) return rc; }
+  else if ((rc = tc_amaps(c, slot, a, k, s, pad, &ahi, &alo))) return rc;
   if (w.K != k * a.C) return fail(c.h, MIMI_B200_ERR_ARG, "tc: weight K mismatch");
   tc::Epilogue ep{};
   ep.bias = o.bias; ep.scale = o.scale; ep.res = o.res; ep.out_raw = o.raw; ep.raw_item_stride = o.raw_item_stride;
@@ -186,10 +251,13 @@ static int tc_gemm(TcCtx& c, int slot, const SplitBuf& a, int k, int s, int pad,
     ep.split_item_stride = o.split->item_stride; ep.split_front = o.split->front;
   }
   ep.act = o.act; ep.elu_split = o.elu_split;
+  ep.single_acc = c.h->exp_single_acc; ep.chunk_kb = c.h->exp_chunk_kb;
   ep.len_in = c.dlen[a.level]; ep.uniform_len_in = c.maxlen[a.level]; ep.conv_stride = s; ep.N = w.N;
   const int lout_max = (c.maxlen[a.level] + s - 1) / s;
   if (lout_max <= 0) return MIMI_B200_OK;
-  if (c.h->mode >= 2) {
+  if (v3) {
+    if ((rc = launch_tc3(c.h, m4, w, ep, c.B, lout_max, a.C, k, s, c.st))) return rc;
+  } else if (c.h->mode >= 2) {
     launch_tc2(c.h, *ahi, *alo, w, ep, c.B, (lout_max + tc::kBM - 1) / tc::kBM, c.st);
   } else {
     dim3 grid((lout_max + tc::kBM - 1) / tc::kBM, w.N / w.BN, c.B);
@@ -224,14 +292,17 @@ static int encode_tc(mimi_b200* h, const float* d_input, int B, long long N, int
   int rc;
   const MapKey key{ws, B, N};
   auto it = h->amap_cache.find(key);
-  TcCtx c{h, &p, ws, B, st, dlen, maxlen, nullptr, nullptr};
+  TcCtx c{h, &p, ws, B, st, dlen, maxlen, nullptr, nullptr, nullptr, nullptr};
   if (it == h->amap_cache.end()) {
     if (h->amap_cache.size() >= 64) h->amap_cache.clear();
     it = h->amap_cache.emplace(key, MapSet()).first;
     it->second.maps.resize(2 * kTcSlots);
+    it->second.maps3.resize(4 * kTcSlots);
   }
   c.maps = &it->second.maps;
   c.built = &it->second.built;
+  c.maps3 = &it->second.maps3;
+  c.built3 = &it->second.built3;
   auto rstride = [&](int level, int C) { return (long long)p.rows[level] * C; };
 
   // halo rows of every conv-consumed split buffer (producers only ever write rows [0, L))
@@ -241,7 +312,7 @@ static int encode_tc(mimi_b200* h, const float* d_input, int B, long long N, int
   if (h->mode == 2 && (rc = tc_zero_halo(c, p.s_a0))) return rc;
 
   // ---- level 0 on CUDA cores: L0 (1->64 k7), R1a (64->32 k3), R1b (32->64 k1 + skip) ---------------------
-  if (h->mode == 3) {
+  if (h->mode >= 3) {
     // fused front end: waveform -> L0 -> R1a -> R1b (+skip) -> ELU -> split, 24 kHz activations stay on chip
     if (maxlen[0] > 0) {
       f0::Params fp{};
@@ -263,7 +334,7 @@ static int encode_tc(mimi_b200* h, const float* d_input, int B, long long N, int
     h->launches++; mark(h, 0, st);
     CUDA_TRY(h, cudaGetLastError());
   }
-  if (h->mode == 3) {
+  if (h->mode >= 3) {
   } else if (h->mode == 2) {
     TcOut o;   // R1a: ELU -> 64 -> 32, k3 (ELU was applied by conv0's split store)
     o.split = &p.s_r1; o.elu_split = 1; o.bias = h->conv_b[1];

@@ -262,8 +262,9 @@ class MimiB200Model:
                      "front_fused"])
 
     def set_mode(self, tensor_cores) -> None:
-        """True / 3 (default): fused 24 kHz front end + persistent tcgen05 3xTF32 kernel for every other
-        GEMM-shaped layer; 2: the same without the front-end fusion; 1: the first-generation tcgen05 kernel
+        """True / 3 (default): fused 24 kHz front end + persistent tcgen05 3xTF32 GEMM for every other
+        GEMM-shaped layer; 4: the same with the experimental third-generation GEMM (256-row tiles, plane-staged
+        activations, single accumulator); 2: mode 3 without the front-end fusion; 1: the first-generation tcgen05 kernel
         for the wide layers (level 0 on FFMA); False / 0: all-fp32 FFMA."""
         mode = (3 if tensor_cores else 0) if isinstance(tensor_cores, bool) else int(tensor_cores)
         self.debug_set(3, mode)

@@ -30,13 +30,13 @@ def main():
     xd = torch.from_numpy(x).cuda()
     if "--tc" in sys.argv or "--tc1" in sys.argv or "--tc2" in sys.argv:
         # tensor-core path: raw taps that exist there (down convs 3/6/9, stream z), then the tail
-        mode = 1 if "--tc1" in sys.argv else 2 if "--tc2" in sys.argv else 3
+        mode = 1 if "--tc1" in sys.argv else 2 if "--tc2" in sys.argv else 3 if "--tc3" in sys.argv else 4
         m.set_mode(mode)
         m.debug_set(0, 0)
         m.encode(xd, num_quantizers=32)
         torch.cuda.synchronize()
         for ci, nm in {0: "seanet.l0", 3: "seanet.down3", 6: "seanet.down6", 9: "seanet.down9", 13: "seanet.out"}.items():
-            if mode == 3 and ci == 0:
+            if mode >= 3 and ci == 0:
                 continue
             t = m.debug_tap(ci).cpu().numpy()
             ref = np.stack([a.T for a in taps[nm]])
