@@ -17,6 +17,14 @@ constexpr int kCodeDim = 256;
 // nn.ELU(alpha=1): x > 0 ? x : exp(x) - 1   (modeling_mimi.py:428,473,478)
 __device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : expm1f(x); }
 
+// ELU for the tensor-core epilogues: exp(x) - 1 through ex2.approx (absolute error ~1e-7, below the fp32 rounding
+// of the activations it feeds; end-to-end latent error is unchanged, see tests/test_gpu_parity.py)
+__device__ __forceinline__ float elu_fast(float x) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 1.4426950408889634f));
+  return x > 0.f ? x : e - 1.f;
+}
+
 // exact (erf) GELU, ACT2FN["gelu"] used by MimiMLP (modeling_mimi.py:614-627)
 __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));

@@ -56,13 +56,6 @@ struct Params {
   int split_front;
 };
 
-// exp(x) - 1 for x <= 0 through ex2.approx (abs error ~1e-7, far below the TF32-split granularity downstream)
-__device__ __forceinline__ float elu_fast(float x) {
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 1.4426950408889634f));
-  return x > 0.f ? x : e - 1.f;
-}
-
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {

@@ -23,6 +23,7 @@
 #include "tc_gemm2.cuh"
 #include "front_fused.cuh"
 #include "tc_gemm3.cuh"
+#include "rvq_tc.cuh"
 #include "transformer.cuh"
 
 using namespace mimi;
@@ -145,6 +146,8 @@ struct mimi_b200 {
   TcWeight tc_conv[MIMI_B200_NUM_CONVS];       // convs 1..13 (conv 0 is a direct SIMT conv)
   TcWeight tc_qkv[MIMI_B200_NUM_LAYERS], tc_o[MIMI_B200_NUM_LAYERS], tc_fc1[MIMI_B200_NUM_LAYERS], tc_fc2[MIMI_B200_NUM_LAYERS];
   TcWeight tc_down, tc_proj;
+  float *embed_hi = nullptr, *embed_lo = nullptr;   // TF32 split of the materialised codebooks (rvq_tc.cuh)
+  CUtensorMap map_embed_hi, map_embed_lo;
   std::map<MapKey, MapSet> amap_cache;   // activation maps per (workspace, B, N)
   PlanTC last_tc;
   bool last_was_tc = false;
@@ -374,6 +377,7 @@ int mimi_b200_create(mimi_b200_t** out, int device_ordinal) {
   cudaFuncSetAttribute(tc2::tc2_gemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::Cfg<32>::SMEM);
   cudaFuncSetAttribute(tc3::tc3_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc3::Cfg<128>::SMEM);
   cudaFuncSetAttribute(tc3::tc3_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc3::Cfg<64>::SMEM);
+  cudaFuncSetAttribute(rvqtc::rvq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, rvqtc::kSmem);
   cudaFuncSetAttribute(f0::front_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, f0::kSmem);
   cudaFuncSetAttribute(tc2::tc_shift_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 40960);
   if ((e = cudaGetLastError()) != cudaSuccess) { delete h; return fail(nullptr, MIMI_B200_ERR_CUDA, cudaGetErrorString(e)); }
@@ -497,6 +501,9 @@ int mimi_b200_load_weights(mimi_b200_t* h, const mimi_b200_weights_t* w) {
     if ((rc = dev_upload(h, &h->embed, E))) return rc;
     if ((rc = dev_upload(h, &h->embed_t, Et))) return rc;
     if ((rc = dev_upload(h, &h->enorm, En))) return rc;
+    for (size_t i = 0; i < E.size(); ++i) { float hi, lo; split_tf32(E[i], hi, lo); E[i] = hi; Et[i] = lo; }   // reuse as hi / lo
+    if ((rc = dev_upload(h, &h->embed_hi, E))) return rc;
+    if ((rc = dev_upload(h, &h->embed_lo, Et))) return rc;
   }
   {
     // MimiRotaryEmbedding (modeling_mimi.py:538-577): angle = float(pos) * inv_freq[i] in fp32
@@ -518,6 +525,12 @@ int mimi_b200_load_weights(mimi_b200_t* h, const mimi_b200_weights_t* w) {
   std::memcpy(h->f0_consts.b1, w->conv_bias[1], sizeof(float) * 32);
   std::memcpy(h->f0_consts.b2, w->conv_bias[2], sizeof(float) * 64);
   if ((rc = tc_load_weights(h, w))) return rc;
+  {
+    const cuuint64_t dims[2] = {(cuuint64_t)kCodeDim, (cuuint64_t)MIMI_B200_MAX_QUANTIZERS * kCodebookSize};
+    const cuuint64_t strides[1] = {(cuuint64_t)kCodeDim * sizeof(float)};
+    if ((rc = tc_make_map(h, &h->map_embed_hi, h->embed_hi, 2, dims, strides, rvqtc::kCodesPerBlock))) return rc;
+    if ((rc = tc_make_map(h, &h->map_embed_lo, h->embed_lo, 2, dims, strides, rvqtc::kCodesPerBlock))) return rc;
+  }
   h->amap_cache.clear();
   h->loaded = true;
   return MIMI_B200_OK;

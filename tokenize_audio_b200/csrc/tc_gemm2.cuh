@@ -232,6 +232,17 @@ tc2_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       float acc[HALF];
 #pragma unroll
       for (int i = 0; i < HALF; ++i) acc[i] = 0.f;
+      if (ep.res && cj == 0) {
+        // pull this tile's residual rows towards L2 while the MMAs run (the loads below then miss only L1)
+        const float* rp = ep.res + (long long)b * ep.raw_item_stride + n0 + col0;
+#pragma unroll
+        for (int p = 0; p < NP; ++p)
+#pragma unroll
+          for (int it = 0; it < IT; ++it) {
+            const int row = m0 + quarter * 32 + it * RPI + rr;
+            if (row < Lout) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + (long long)row * ep.N + p * PC));
+          }
+      }
       for (int c = 0; c < nchunks; ++c, ++cc) {
         const uint32_t buf = cc & 1u;
         tc::mbar_wait(&acc_full[buf], (cc >> 1) & 1u);
@@ -299,7 +310,7 @@ tc2_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
             if (ep.res) { v.x += resv[it].x; v.y += resv[it].y; v.z += resv[it].z; v.w += resv[it].w; }
             if (ep.out_raw) *reinterpret_cast<float4*>(ep.out_raw + raw_base + o) = v;
             if (ep.out_hi) {
-              if (ep.elu_split) { v.x = elu1(v.x); v.y = elu1(v.y); v.z = elu1(v.z); v.w = elu1(v.w); }
+              if (ep.elu_split) { v.x = elu_fast(v.x); v.y = elu_fast(v.y); v.z = elu_fast(v.z); v.w = elu_fast(v.w); }
               store_split4(ep.out_hi + split_base + o, ep.out_lo + split_base + o, v);
             }
           }

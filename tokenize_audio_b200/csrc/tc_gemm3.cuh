@@ -308,7 +308,7 @@ tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
             if (ep.res) { v.x += resv[it].x; v.y += resv[it].y; v.z += resv[it].z; v.w += resv[it].w; }
             if (ep.out_raw) *reinterpret_cast<float4*>(ep.out_raw + raw_base + o) = v;
             if (ep.out_hi) {
-              if (ep.elu_split) { v.x = elu1(v.x); v.y = elu1(v.y); v.z = elu1(v.z); v.w = elu1(v.w); }
+              if (ep.elu_split) { v.x = elu_fast(v.x); v.y = elu_fast(v.y); v.z = elu_fast(v.z); v.w = elu_fast(v.w); }
               store_split4(ep.out_hi + split_base + o, ep.out_lo + split_base + o, v);
             }
           }

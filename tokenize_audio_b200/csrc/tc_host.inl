@@ -447,7 +447,15 @@ static int encode_tc(mimi_b200* h, const float* d_input, int B, long long N, int
     r.embed = h->embed; r.embed_t = h->embed_t; r.enorm = h->enorm;
     r.codes = reinterpret_cast<long long*>(d_codes); r.K = K; r.T_out = p.rows[5];
     r.len = dlen[5]; r.uniform_len = T; r.B = B; r.total_frames = total_frames; r.frame_prefix = dprefix;
-    if (total_frames > 0) {
+    if (total_frames > 0 && h->mode >= 3) {
+      rvqtc::Params q{};
+      q.rproj = r.rproj; q.item_stride = r.item_stride; q.embed = h->embed; q.enorm = h->enorm; q.codes = r.codes;
+      q.K = K; q.T_out = r.T_out; q.len = r.len; q.uniform_len = r.uniform_len; q.B = B; q.total_frames = total_frames;
+      q.frame_prefix = dprefix;
+      rvqtc::rvq_tc_kernel<<<(total_frames + rvqtc::kFrames - 1) / rvqtc::kFrames, rvqtc::kThreads, rvqtc::kSmem, st>>>(
+          h->map_embed_hi, h->map_embed_lo, q);
+      h->launches++; mark(h, 22, st);
+    } else if (total_frames > 0) {
       rvq_encode_kernel<<<(total_frames + kRvqFM - 1) / kRvqFM, 256, kRvqSmemBytes, st>>>(r);
       h->launches++; mark(h, 22, st);
     }
