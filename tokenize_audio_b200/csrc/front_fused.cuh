@@ -4,10 +4,11 @@
 // activations (6.1 MB per audio-second in fp32) never touch HBM: per audio-second the kernel reads 96 KB
 // and writes the 12.3 MB split operand.
 //
-//   One persistent CTA per SM, 8 warps = two warpgroups (warps 0-3, 4-7) that ping-pong over time tiles; thread m
-//   of a warpgroup owns tile row m in every phase, so the raw L0 output needed by the skip stays in its
-//   registers (256 threads -> 255 registers each; a ninth warp would cap them at 168 and spill). Thread 0 of
-//   each warpgroup issues that warpgroup's tcgen05.mma after a 128-thread named barrier.
+//   One persistent CTA per SM, 16 warps = two groups of 8 warps (256 threads) that ping-pong over time tiles. Inside
+//   a group thread (m, ch) owns tile row m and one half of the channels in every phase, so the raw L0 output needed
+//   by the skip stays in its registers, and every SM sub-partition has four warps to hide TMEM / barrier / global
+//   latencies behind (the first version had one thread per row and two warps per sub-partition: 25 % issue
+//   utilisation). Thread 0 of each group issues that group's tcgen05.mma after a 256-thread named barrier.
 //     front  L0 on CUDA cores (weights as kernel-parameter constants -> FFMA with constant-bank operands,
 //            no loads), ELU, hi/lo split, stored straight into the SWIZZLE_128B K-major operand layout;
 //     R1a    3 taps x 2 channel panels = 6 k-blocks; tap tau reads the SAME staged rows through a descriptor
@@ -20,7 +21,7 @@
 //   rows are the causal halo of the k=3 conv, recomputed instead of carried, so tiles are independent.
 //   Arithmetic is 3xTF32 as in tc_gemm2.cuh; K is at most 192 so a single accumulation chunk is used.
 #pragma once
-#include "tc_gemm.cuh"
+#include "tc_gemm2.cuh"
 
 namespace mimi {
 namespace f0 {
@@ -32,7 +33,7 @@ constexpr int kTileBuf = 4 * kPanelBytes;        // hi panel 0 | hi panel 1 | lo
 constexpr int kW1Block = 32 * 128;               // one k-block of W1 (32 output channels x 32 floats), hi or lo
 constexpr int kW1Bytes = 6 * kW1Block;           // per hi / lo; stored stacked per k-block: [hi kb | lo kb]
 constexpr int kW2Bytes = 64 * 128;               // per hi / lo; stored stacked: [hi | lo]
-constexpr int kThreads = 256;
+constexpr int kThreads = 512;
 constexpr int kSmem = 1024 + 2 * kTileBuf + 2 * kW1Bytes + 2 * kW2Bytes + 256;
 constexpr int kTmemCols = 512;                   // 2 warpgroups x (32 + 32 + 64 + 64) columns
 
@@ -128,23 +129,23 @@ front_fused_kernel(const __grid_constant__ CUtensorMap tmW1_hi, const __grid_con
     tc::tma_load_2d(w2 + kW2Bytes, &tmW2_lo, w_ready, 0, 0);
   }
   {
-    // ---- compute warpgroups ------------------------------------------------------------------------------------
-    const int g = warp >> 2;                       // warpgroup
-    const int wq = warp & 3;                       // TMEM lane quarter == warp index inside the warpgroup
+    // ---- compute warpgroups: 8 warps each; thread = (tile row m, channel half ch) --------------------------------
+    const int g = warp >> 3;                       // warpgroup
+    const int wq = warp & 3;                       // TMEM lane quarter
+    const int ch = (warp >> 2) & 1;                // channel half: L0 / R1b channels [32ch, +32), R1a channels [16ch, +16)
     const int m = wq * 32 + lane;                  // tile row owned by this thread
-    const bool issuer = m == 0;                    // issues this warpgroup's MMAs
+    const bool issuer = (m == 0) && (ch == 0);     // issues this warpgroup's MMAs
     constexpr uint32_t idesc32 = tc::make_idesc(128, 32);
     constexpr uint32_t idesc64 = tc::make_idesc(128, 64);
     constexpr uint32_t idesc128 = tc::make_idesc(128, 128);
-    auto wg_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory"); };
+    auto wg_sync = [&]() { asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory"); };
     if (issuer) tc::mbar_wait(w_ready, 0);
     uint8_t* buf = smem + g * kTileBuf;
     const uint32_t bufa = tc::smem_u32(buf);
     const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
     const uint32_t tm1 = tmem_base + lane_off + g * 192;           // acc1 main | small (32 + 32 columns)
     const uint32_t tm2 = tm1 + 64;                                  // acc2 main | small (64 + 64 columns)
-    const uint32_t stg_hi = tc::smem_u32(buf) + 2 * kPanelBytes + (wq * 32 + 2) * 128;   // this warp's own rows
-    const uint32_t stg_lo = stg_hi + kPanelBytes;
+    const uint32_t stg = bufa + (2 + ch) * kPanelBytes + (wq * 32 + 2) * 128;   // this warp's own rows of lo panel ch
     uint32_t it = 0;
     for (int id = blockIdx.x + g * gridDim.x; id < vtiles; id += 2 * gridDim.x) {
       const int b = id % p.B;
@@ -152,8 +153,8 @@ front_fused_kernel(const __grid_constant__ CUtensorMap tmW1_hi, const __grid_con
       const int L = item_len(b);
       if (t0 >= L) continue;
       const int t = t0 - 2 + m;                    // time of this thread's row
-      // ---- front: L0 + ELU + split -> operand rows (buffer row m + 2) ---------------------------------------
-      float a0[64];
+      // ---- front: L0 (this thread's 32 channels) + ELU + split -> operand row m + 2 of panel ch ------------------
+      float a0[32];
       {
         const float* xb = p.x + (long long)b * p.x_stride;
         float xv[7];
@@ -162,7 +163,7 @@ front_fused_kernel(const __grid_constant__ CUtensorMap tmW1_hi, const __grid_con
           const int tt = t - 6 + k;
           xv[k] = (tt >= 0 && tt < L) ? __ldg(xb + tt) : 0.f;
         }
-        {   // pull the next tile's samples towards L1 while this tile computes
+        if (ch == 0) {   // pull the next tile's samples towards L1 while this tile computes
           const int nid = id + 2 * gridDim.x;
           if (nid < vtiles) {
             const int nt = (nid / p.B) * kAdv - 2 + m;
@@ -170,70 +171,81 @@ front_fused_kernel(const __grid_constant__ CUtensorMap tmW1_hi, const __grid_con
               asm volatile("prefetch.global.L1 [%0];" ::"l"(p.x + (long long)(nid % p.B) * p.x_stride + nt));
           }
         }
+        // two copies so that every weight is a compile-time constant-bank operand of its FFMA
+        if (ch == 0) {
 #pragma unroll
-        for (int c = 0; c < 64; ++c) {
-          float s = cst.b0[c];
+          for (int c = 0; c < 32; ++c) {
+            float s0 = cst.b0[c];
 #pragma unroll
-          for (int k = 0; k < 7; ++k) s = fmaf(cst.w0[c * 7 + k], xv[k], s);
-          a0[c] = s;
+            for (int k = 0; k < 7; ++k) s0 = fmaf(cst.w0[c * 7 + k], xv[k], s0);
+            a0[c] = s0;
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            float s0 = cst.b0[32 + c];
+#pragma unroll
+            for (int k = 0; k < 7; ++k) s0 = fmaf(cst.w0[(32 + c) * 7 + k], xv[k], s0);
+            a0[c] = s0;
+          }
         }
         const int row = m + 2;
         const int key = row & 7;
         const bool live = t >= 0;                  // rows before the item start are the conv's zero padding
 #pragma unroll
-        for (int pn = 0; pn < 2; ++pn)
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            float4 h4, l4;
-            const int c = pn * 32 + q * 4;
-            split_tf32(live ? elu_fast(a0[c + 0]) : 0.f, h4.x, l4.x);
-            split_tf32(live ? elu_fast(a0[c + 1]) : 0.f, h4.y, l4.y);
-            split_tf32(live ? elu_fast(a0[c + 2]) : 0.f, h4.z, l4.z);
-            split_tf32(live ? elu_fast(a0[c + 3]) : 0.f, h4.w, l4.w);
-            const uint32_t off = bufa + (uint32_t)(row * 128 + ((q ^ key) << 4));
-            sts128(off + pn * kPanelBytes, h4);
-            sts128(off + (2 + pn) * kPanelBytes, l4);
-          }
+        for (int q = 0; q < 8; ++q) {
+          float4 h4, l4;
+          split_tf32(live ? elu_fast(a0[q * 4 + 0]) : 0.f, h4.x, l4.x);
+          split_tf32(live ? elu_fast(a0[q * 4 + 1]) : 0.f, h4.y, l4.y);
+          split_tf32(live ? elu_fast(a0[q * 4 + 2]) : 0.f, h4.z, l4.z);
+          split_tf32(live ? elu_fast(a0[q * 4 + 3]) : 0.f, h4.w, l4.w);
+          const uint32_t off = bufa + (uint32_t)(row * 128 + ((q ^ key) << 4));
+          sts128(off + ch * kPanelBytes, h4);
+          sts128(off + (2 + ch) * kPanelBytes, l4);
+        }
         fence_async_smem();
         wg_sync();
         if (issuer) {
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t main1 = tmem_base + g * 192, small1 = main1 + 32;
+          const uint32_t d_buf = tc::desc_lo(bufa), d_w1 = tc::desc_lo(tc::smem_u32(w1));
 #pragma unroll
           for (int kb = 0; kb < 6; ++kb) {
             const int tau = kb >> 1, pn = kb & 1;
-            const uint32_t a_hi = bufa + pn * kPanelBytes + tau * 128;
-            const uint32_t a_lo = a_hi + 2 * kPanelBytes;
-            const uint32_t b_st = tc::smem_u32(w1) + (2 * kb) * kW1Block;      // [hi | lo] stacked, N = 64
+            const uint32_t a_hi = d_buf + ((pn * kPanelBytes + tau * 128) >> 4);
+            const uint32_t a_lo = a_hi + ((2 * kPanelBytes) >> 4);
+            const uint32_t b_st = d_w1 + (((2 * kb) * kW1Block) >> 4);        // [hi | lo] stacked, N = 64
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               // columns [0,32) += A_hi W_hi^T (main), columns [32,64) += A_hi W_lo^T; then [32,64) += A_lo W_hi^T
-              tc::umma_tf32(main1, tc::make_smem_desc(a_hi + k * 32), tc::make_smem_desc(b_st + k * 32), idesc64, (uint32_t)((kb | k) != 0));
-              tc::umma_tf32(small1, tc::make_smem_desc(a_lo + k * 32), tc::make_smem_desc(b_st + k * 32), idesc32, 1u);
+              tc::umma_tf32_lo(main1, a_hi + 2 * k, b_st + 2 * k, idesc64, (uint32_t)((kb | k) != 0));
+              tc::umma_tf32_lo(small1, a_lo + 2 * k, b_st + 2 * k, idesc32, 1u);
             }
           }
           tc::umma_commit(&acc1_full[g]);
         }
         __syncwarp();
       }
-      // ---- mid: R1a accumulators -> bias, ELU, split -> R1b operand (row m of hi panel 0 / hi panel 1) -----------
+      // ---- mid: R1a accumulators (this thread's 16 channels) -> bias, ELU, split -> R1b operand row m -----------------
       {
         tc::mbar_wait(&acc1_full[g], it & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        uint32_t rm[32], rs[32];
-        tmem_ld32(tm1, rm);
-        tmem_ld32(tm1 + 32, rs);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        uint32_t rm[16], rs[16];
+        tc2::tmem_ld16_nowait(tm1 + ch * 16, rm);
+        tc2::tmem_ld16_nowait(tm1 + 32 + ch * 16, rs);
+        tc2::tmem_ld_wait();
         const int key = m & 7;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
+        for (int q = 0; q < 4; ++q) {
           float4 h4, l4;
           float v[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            v[j] = elu_fast(__uint_as_float(rm[q * 4 + j]) + __uint_as_float(rs[q * 4 + j]) + cst.b1[q * 4 + j]);
+          for (int j = 0; j < 4; ++j) {
+            const float bias = ch == 0 ? cst.b1[q * 4 + j] : cst.b1[16 + q * 4 + j];
+            v[j] = elu_fast(__uint_as_float(rm[q * 4 + j]) + __uint_as_float(rs[q * 4 + j]) + bias);
+          }
           split_tf32(v[0], h4.x, l4.x); split_tf32(v[1], h4.y, l4.y); split_tf32(v[2], h4.z, l4.z); split_tf32(v[3], h4.w, l4.w);
-          const uint32_t off = bufa + (uint32_t)(m * 128 + ((q ^ key) << 4));
+          const uint32_t off = bufa + (uint32_t)(m * 128 + (((ch * 4 + q) ^ key) << 4));
           sts128(off, h4);
           sts128(off + kPanelBytes, l4);
         }
@@ -242,70 +254,68 @@ front_fused_kernel(const __grid_constant__ CUtensorMap tmW1_hi, const __grid_con
         wg_sync();
         if (issuer) {
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t a_hi = bufa;                                    // R1 operand aliases hi panel 0 / hi panel 1
-          const uint32_t a_lo = a_hi + kPanelBytes;
-          const uint32_t b_st = tc::smem_u32(w2);                        // [hi | lo] stacked, N = 128
+          const uint32_t a_hi = tc::desc_lo(bufa);                       // R1 operand aliases hi panel 0 / hi panel 1
+          const uint32_t a_lo = a_hi + (kPanelBytes >> 4);
+          const uint32_t b_st = tc::desc_lo(tc::smem_u32(w2));           // [hi | lo] stacked, N = 128
           const uint32_t main2 = tmem_base + g * 192 + 64, small2 = main2 + 64;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            tc::umma_tf32(main2, tc::make_smem_desc(a_hi + k * 32), tc::make_smem_desc(b_st + k * 32), idesc128, (uint32_t)(k != 0));
-            tc::umma_tf32(small2, tc::make_smem_desc(a_lo + k * 32), tc::make_smem_desc(b_st + k * 32), idesc64, 1u);
+            tc::umma_tf32_lo(main2, a_hi + 2 * k, b_st + 2 * k, idesc128, (uint32_t)(k != 0));
+            tc::umma_tf32_lo(small2, a_lo + 2 * k, b_st + 2 * k, idesc64, 1u);
           }
           tc::umma_commit(&acc2_full[g]);
         }
         __syncwarp();
       }
-      // ---- final: R1b accumulators + bias + skip -> ELU -> split -> coalesced stores ----------------------------
+      // ---- final: R1b accumulators (this thread's 32 channels) + bias + skip -> ELU -> split -> coalesced stores ----
       {
         tc::mbar_wait(&acc2_full[g], it & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const long long obase = (long long)b * p.split_item_stride + (long long)p.split_front * 64;
+        const long long obase = (long long)b * p.split_item_stride + (long long)p.split_front * 64 + ch * 32;
+        uint32_t rm[32], rs[32];
+        tmem_ld32(tm2 + ch * 32, rm);
+        tmem_ld32(tm2 + 64 + ch * 32, rs);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        const int key = lane & 7;
+        float4 lq[8];
 #pragma unroll
-        for (int pc = 0; pc < 2; ++pc) {
-          uint32_t rm[32], rs[32];
-          tmem_ld32(tm2 + pc * 32, rm);
-          tmem_ld32(tm2 + 64 + pc * 32, rs);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          const int key = lane & 7;
+        for (int q = 0; q < 8; ++q) {
+          float4 h4;
+          float v[4];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            float4 h4, l4;
-            float v[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int c = pc * 32 + q * 4 + j;
-              v[j] = elu_fast((__uint_as_float(rm[q * 4 + j]) + __uint_as_float(rs[q * 4 + j])) + cst.b2[c] + a0[c]);
-            }
-            split_tf32(v[0], h4.x, l4.x); split_tf32(v[1], h4.y, l4.y); split_tf32(v[2], h4.z, l4.z); split_tf32(v[3], h4.w, l4.w);
-            sts128(stg_hi + (uint32_t)(lane * 8 + (q ^ key)) * 16u, h4);
-            sts128(stg_lo + (uint32_t)(lane * 8 + (q ^ key)) * 16u, l4);
+          for (int j = 0; j < 4; ++j) {
+            const int c = q * 4 + j;
+            const float bias = ch == 0 ? cst.b2[c] : cst.b2[32 + c];
+            v[j] = elu_fast((__uint_as_float(rm[c]) + __uint_as_float(rs[c])) + bias + a0[c]);
           }
+          split_tf32(v[0], h4.x, lq[q].x); split_tf32(v[1], h4.y, lq[q].y); split_tf32(v[2], h4.z, lq[q].z); split_tf32(v[3], h4.w, lq[q].w);
+          sts128(stg + (uint32_t)(lane * 8 + (q ^ key)) * 16u, h4);
+        }
+        // hi piece, then lo piece, through the same 4 KB of this warp's own (dead) operand rows
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
           __syncwarp();
-          float4 hv[8], lv[8];
+          float4 tv[8];
 #pragma unroll
           for (int i8 = 0; i8 < 8; ++i8) {
             const int r = i8 * 4 + (lane >> 3);        // row inside this warp's 32
-            const int cj = lane & 7;
-            hv[i8] = lds128(stg_hi + (uint32_t)(r * 8 + (cj ^ (r & 7))) * 16u);
-            lv[i8] = lds128(stg_lo + (uint32_t)(r * 8 + (cj ^ (r & 7))) * 16u);
+            tv[i8] = lds128(stg + (uint32_t)(r * 8 + ((lane & 7) ^ (r & 7))) * 16u);
           }
+          float* outp = pass == 0 ? p.out_hi : p.out_lo;
 #pragma unroll
           for (int i8 = 0; i8 < 8; ++i8) {
             const int r = i8 * 4 + (lane >> 3);
-            const int cj = lane & 7;
-            const float4 h4 = hv[i8];
-            const float4 l4 = lv[i8];
             const int mm = wq * 32 + r;
             const int tt = t0 - 2 + mm;
-            if (mm >= 2 && tt < L) {
-              const long long o = obase + (long long)tt * 64 + pc * 32 + cj * 4;
-              *reinterpret_cast<float4*>(p.out_hi + o) = h4;
-              *reinterpret_cast<float4*>(p.out_lo + o) = l4;
-            }
+            if (mm >= 2 && tt < L) *reinterpret_cast<float4*>(outp + obase + (long long)tt * 64 + (lane & 7) * 4) = tv[i8];
           }
           __syncwarp();
+          if (pass == 0) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) sts128(stg + (uint32_t)(lane * 8 + (q ^ key)) * 16u, lq[q]);
+          }
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       }
       ++it;
     }

@@ -132,7 +132,7 @@ rvq_tc_kernel(const __grid_constant__ CUtensorMap tmE_hi, const __grid_constant_
     if (lane == 0) {
       constexpr uint32_t idesc128 = tc::make_idesc(128, 128);
       constexpr uint32_t idesc64 = tc::make_idesc(128, 64);
-      const uint32_t rop = tc::smem_u32(r_op);
+      const uint32_t d_rop = tc::desc_lo(tc::smem_u32(r_op));
       uint32_t c = 0, bc = 0;
       for (int stage = 0; stage < p.K; ++stage) {
         tc::mbar_wait(r_ready, (uint32_t)stage & 1u);
@@ -145,13 +145,13 @@ rvq_tc_kernel(const __grid_constant__ CUtensorMap tmE_hi, const __grid_constant_
             const uint32_t s = c % kAStages;
             tc::mbar_wait(&full_bar[s], (c / kAStages) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t e_hi = tc::smem_u32(a_ring + s * kAStage);
-            const uint32_t e_lo = e_hi + kAStage / 2;
-            const uint32_t r_st = rop + kb * kRKb;             // [r_hi (64 rows) | r_lo (64 rows)] stacked: N = 128
+            const uint32_t e_hi = tc::desc_lo(tc::smem_u32(a_ring) + s * kAStage);
+            const uint32_t e_lo = e_hi + ((kAStage / 2) >> 4);
+            const uint32_t r_st = d_rop + ((kb * kRKb) >> 4);   // [r_hi (64 rows) | r_lo (64 rows)] stacked: N = 128
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              tc::umma_tf32(acc, tc::make_smem_desc(e_hi + k * 32), tc::make_smem_desc(r_st + k * 32), idesc128, (uint32_t)((kb | k) != 0));
-              tc::umma_tf32(acc + 64, tc::make_smem_desc(e_lo + k * 32), tc::make_smem_desc(r_st + k * 32), idesc64, 1u);
+              tc::umma_tf32_lo(acc, e_hi + 2 * k, r_st + 2 * k, idesc128, (uint32_t)((kb | k) != 0));
+              tc::umma_tf32_lo(acc + 64, e_lo + 2 * k, r_st + 2 * k, idesc64, 1u);
             }
             tc::umma_commit(&empty_bar[s]);
           }

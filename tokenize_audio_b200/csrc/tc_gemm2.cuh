@@ -172,6 +172,7 @@ tc2_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = tc::make_idesc(kBM, BN);
+      const uint32_t smem_base_u32 = tc::smem_u32(smem);
       uint32_t kbc = 0, cc = 0, lt = 0;
       for (int id = blockIdx.x; id < vtiles; id += gridDim.x) {
         int b, m0, n0, Lout;
@@ -190,24 +191,21 @@ tc2_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
             const uint32_t ph = (kbc / STAGES) & 1u;
             tc::mbar_wait(&full_bar[s], ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t a_hi = tc::smem_u32(smem + s * STAGE);
-            const uint32_t a_lo = a_hi + A_BYTES;
-            const uint32_t w_hi = a_hi + 2 * A_BYTES;
-            const uint32_t w_lo = w_hi + W_BYTES;
+            // descriptor low words: one encode per stage, then constant adds (16-byte units)
+            const uint32_t d_ahi = tc::desc_lo(smem_base_u32 + s * STAGE);
+            constexpr uint32_t kAlo = A_BYTES >> 4, kWhi = (2 * A_BYTES) >> 4, kWlo = (2 * A_BYTES + W_BYTES) >> 4;
             const bool first_in_chunk = kb == c * ckb;
             const uint32_t tmem_x = ep.single_acc ? tmem_main : tmem_small;
             const uint32_t xacc = ep.single_acc ? 1u : (uint32_t)(kb != 0);
 #pragma unroll
             for (int k = 0; k < kBK / kUmmaK; ++k)
-              tc::umma_tf32(tmem_main, tc::make_smem_desc(a_hi + k * 32), tc::make_smem_desc(w_hi + k * 32), idesc,
-                            !(first_in_chunk && k == 0));
+              tc::umma_tf32_lo(tmem_main, d_ahi + 2 * k, d_ahi + kWhi + 2 * k, idesc, !(first_in_chunk && k == 0));
 #pragma unroll
             for (int k = 0; k < kBK / kUmmaK; ++k)
-              tc::umma_tf32(tmem_x, tc::make_smem_desc(a_lo + k * 32), tc::make_smem_desc(w_hi + k * 32), idesc,
-                            k != 0 ? 1u : xacc);
+              tc::umma_tf32_lo(tmem_x, d_ahi + kAlo + 2 * k, d_ahi + kWhi + 2 * k, idesc, k != 0 ? 1u : xacc);
 #pragma unroll
             for (int k = 0; k < kBK / kUmmaK; ++k)
-              tc::umma_tf32(tmem_x, tc::make_smem_desc(a_hi + k * 32), tc::make_smem_desc(w_lo + k * 32), idesc, 1u);
+              tc::umma_tf32_lo(tmem_x, d_ahi + 2 * k, d_ahi + kWlo + 2 * k, idesc, 1u);
             tc::umma_commit(&empty_bar[s]);
           }
           tc::umma_commit(&acc_full[buf]);       // after the tile's last chunk this also covers the cross terms
