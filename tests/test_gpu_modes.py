@@ -1,0 +1,113 @@
+"""Every kernel generation of the CUDA path against the oracle and against each other (needs a B200).
+
+mode 0 = all-fp32 FFMA (the exact-fp32 baseline), 2 = persistent tcgen05 3xTF32 GEMM + SIMT RVQ, 3 = default
+(+ fused 24 kHz front end, attention v2, tensor-core RVQ), 4 = experimental third-generation GEMM.
+Tolerances as in test_gpu_parity.py: codes >= 99.9 % identical to the oracle, latent relative L2 <= 2e-5.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import chars_oracle as CO
+from oracle import mimi_oracle as O
+from tokenize_audio_b200 import _lib, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30))
+
+
+@pytest.fixture(scope="module")
+def case(state_dict):
+    # two ragged items, T25 = 302 > 250-frame window on the long one; 32 codebooks
+    lens = [289234, 61111]
+    x = np.zeros((2, 1, lens[0]), np.float32)
+    for i, n in enumerate(lens):
+        x[i, 0, :n] = synth.synth_speech(800 + i, n)
+    taps = {}
+    ref = O.encode(state_dict, x, 32, taps=taps)
+    return x, lens, ref, np.stack(taps["latent"])
+
+
+@pytest.mark.parametrize("mode", [0, 2, 3, 4])
+def test_every_mode_matches_the_oracle(b200_model, case, mode):
+    x, lens, ref, lat_ref = case
+    b200_model.set_mode(mode)
+    try:
+        out, lat = b200_model.encode(torch.from_numpy(x).cuda(), num_quantizers=32, return_latent=True)
+        codes = out.audio_codes.cpu().numpy()
+        rag = b200_model.encode(torch.from_numpy(x).cuda(), num_quantizers=32, valid_lengths=lens).audio_codes.cpu().numpy()
+    finally:
+        b200_model.set_mode(True)
+    assert _rel(lat.cpu().numpy(), lat_ref) <= 2e-5
+    assert (codes == ref).mean() >= 0.999, f"mode {mode}: {(codes == ref).mean():.5f}"
+    for i, n in enumerate(lens):
+        t = -(-n // 1920)
+        assert np.array_equal(rag[i, :, :t], codes[i, :, :t])          # ragged == strict on kept frames, every mode
+
+
+def test_tensor_core_rvq_matches_simt_rvq(b200_model):
+    """mode 2 (fused SIMT RVQ, exact fp32 FFMA distances) vs mode 3 (tensor-core RVQ) from the same latent path up to
+    the RVQ input: the codes may differ only through near-ties (<= 0.1 % of slots)."""
+    x = np.stack([synth.synth_speech(900 + i, 20 * 1920) for i in range(6)])[:, None, :]
+    xd = torch.from_numpy(x).cuda()
+    b200_model.set_mode(2)
+    a = b200_model.encode(xd, num_quantizers=32).audio_codes
+    b200_model.set_mode(True)
+    b = b200_model.encode(xd, num_quantizers=32).audio_codes
+    assert a.shape == b.shape == (6, 32, 20)
+    assert float((a == b).float().mean()) >= 0.999
+    assert torch.equal(a[:, 0], b[:, 0])
+
+
+def test_wrapper_sub_batching_is_invisible(b200_model):
+    """The pipelined sub-batches of encode_audio_batch (ragged mode) return exactly what one big batch returns."""
+    from tokenize_audio_b200.encoder import MimiEncoder
+    rng = np.random.default_rng(7)
+    clips = [synth.synth_speech(1000 + i, int(n)) for i, n in enumerate(rng.integers(3000, 60000, size=21))]
+    one = MimiEncoder(b200_model, num_quantizers=8, chunk_items=64).encode_audio_batch(clips)
+    many = MimiEncoder(b200_model, num_quantizers=8, chunk_items=4).encode_audio_batch(clips)
+    assert len(one) == len(many) == 21
+    for a, b, c in zip(one, many, clips):
+        assert a.shape == (8, -(-len(c) // 1920)) and np.array_equal(a, b)
+
+
+def test_config5_codes_to_unicode_after_encode(b200_model):
+    """BASELINE config 5: 30 s segments -> 8 codebooks -> unicode string (375 frames = 3000 chars = 10 500 bytes)."""
+    from tokenize_audio_b200 import utils
+    x = torch.from_numpy(np.stack([synth.synth_speech(1100 + i, 720000) for i in range(2)])[:, None, :]).cuda()
+    codes = b200_model.encode(x, num_quantizers=8).audio_codes
+    got = utils.codes_to_utf8_batch(codes, [375, 375])
+    host = codes.cpu().numpy()
+    for i in range(2):
+        assert len(got[i]) == 10500 and got[i] == CO.codes_to_utf8(host[i], 2048)
+        assert len(got[i].decode("utf-8")) == 3000
+
+
+def test_sw128_descriptor_row_shift_property():
+    """The hardware property front_fused.cuh / tc_gemm3.cuh rely on: a SWIZZLE_128B K-major operand descriptor may
+    start at any whole 128-byte row of a staged tile when its base-offset field is 0."""
+    lib = _lib.load_library()
+    h = C.c_void_p()
+    _lib.check(lib, None, lib.mimi_b200_create(C.byref(h), 0), "create")
+    try:
+        g = torch.Generator().manual_seed(1)
+        K = 96
+        a = torch.randn(136, K, generator=g)
+        w = torch.randn(64, K, generator=g)
+        ad = a.cuda()
+        wn = np.ascontiguousarray(w.numpy())
+        for shift in (0, 1, 2, 3, 7, 8):
+            out = torch.zeros(128, 64, device="cuda")
+            rc = lib.mimi_b200_debug_shift_probe(h, ad.data_ptr(), wn.ctypes.data, K, shift, 0, out.data_ptr(),
+                                                 torch.cuda.current_stream().cuda_stream)
+            _lib.check(lib, h, rc, "shift_probe")
+            ref = a[shift:shift + 128].double() @ w.double().T
+            err = float((out.cpu().double() - ref).norm() / ref.norm())
+            assert err < 2e-3, f"shift {shift}: {err:.2e}"          # single-pass TF32
+    finally:
+        lib.mimi_b200_destroy(h)

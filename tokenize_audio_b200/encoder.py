@@ -438,7 +438,10 @@ class MimiEncoder:
             while bounds[-1] < B:
                 bounds.append(min(B, bounds[-1] + max(self.chunk_items, (B - bounds[1] + 1) // 2)))
             chunks = [list(range(a, b)) for a, b in zip(bounds[:-1], bounds[1:])]
-            n_max = [max(original_lengths[i] for i in ch) for ch in chunks]
+            # a sub-batch is padded to whole frames (but never beyond the full batch length): every item then sees the
+            # same zeros behind its last kept frame as in the reference's single padded batch
+            n_full = max(original_lengths)
+            n_max = [min(n_full, -(-max(original_lengths[i] for i in ch) // FRAME_SIZE) * FRAME_SIZE) for ch in chunks]
             total = sum(len(ch) * n for ch, n in zip(chunks, n_max))
             t_max = [-(-n // FRAME_SIZE) for n in n_max]
             total_codes = sum(len(ch) * K * t for ch, t in zip(chunks, t_max))
