@@ -61,7 +61,10 @@ MMAC_PER_AUDIO_S = {
 HBM_BYTES_PER_AUDIO_S = {
     "conv0": 24000 * 4 + 24000 * 64 * 4,
     "layernorm": 25 * 512 * 4 * 2 * 16,
+    # fused 24 kHz front end: waveform in, TF32 hi/lo split of the 64-channel activation out
+    "front_fused": 24000 * 4 + 24000 * 64 * 8,
 }
+HBM_BOUND_KINDS = ("conv0", "layernorm", "front_fused")
 
 
 def load_peaks():
@@ -256,17 +259,21 @@ def run_b200(args, rank, world, local_rank):
     per_launch_s = kms / 1e3 / kcnt
     launches_per_step = kcnt / args.steps
     audio_per_launch = total_computed / args.steps / launches_per_step
-    if kind in MMAC_PER_AUDIO_S and kind != "conv0":
+    if kind in MMAC_PER_AUDIO_S and kind not in HBM_BOUND_KINDS:
         achieved = 2 * MMAC_PER_AUDIO_S[kind] * 1e6 * audio_per_launch / per_launch_s / 1e12
         roof = {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["tflops"]}
     else:
         achieved = HBM_BYTES_PER_AUDIO_S.get(kind, 0.0) * audio_per_launch / per_launch_s / 1e9
         roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"]}
+    # measured DRAM traffic (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum) per audio-second of the
+    # profiled launch, scaled to this launch's audio
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(kind)
+        per_s = json.load(open(tpath)).get(kind, {}).get("dram_bytes_per_audio_s")
+        if per_s is not None:
+            traffic = per_s * audio_per_launch
     roof.update({"traffic": traffic, "kernel": kind, "share_of_step": kms / sum(v[0] for v in prof.values()),
                  "avg_launch_ms": 1e3 * per_launch_s, "peak_source": peaks["src"],
                  "precision": "3xTF32 on tcgen05 (fp32-equivalent; 3 tensor passes per MAC) or fp32 FFMA for the SIMT kernels; "
@@ -330,6 +337,7 @@ def main():
         return
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # keep stdout to the one JSON line
         torch.cuda.set_device(local_rank)
         torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
