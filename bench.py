@@ -185,6 +185,8 @@ def run_b200(args, rank, world, local_rank):
     model = MimiB200Model(sd, device=dev)
     if args.mode is not None:
         model.set_mode(args.mode)
+    if args.planes is not None:
+        model.debug_set(6, args.planes)
     wrapper = MimiEncoder(model, device=str(dev), ragged=True, num_quantizers=K_CODEBOOKS)
     clips, lengths, batches = make_workload(rank)
     peaks = load_peaks()
@@ -328,6 +330,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mode", type=int, default=None, help="debug: kernel generation (see MimiB200Model.set_mode)")
+    ap.add_argument("--planes", type=int, default=None, help="debug: plane-staged conv activations on/off")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -140,6 +140,8 @@ struct mimi_b200 {
                                                // 1 = first-generation tcgen05 kernel (level 0 on FFMA), 0 = all-fp32 SIMT
   int last_mode = 0;
   int exp_single_acc = 0, exp_chunk_kb = 0;    // accuracy experiments (debug_set keys 4, 5)
+  int use_planes = 0;                          // plane-staged activations for k = G*stride convs (debug_set key 6); off:
+                                               // fewer L2 bytes but not faster (shared-memory bandwidth binds)
   f0::Consts f0_consts;
   int num_sms = 148;
   PFN_cuTensorMapEncodeTiled_v12000 encode_tiled = nullptr;
@@ -375,6 +377,8 @@ int mimi_b200_create(mimi_b200_t** out, int device_ordinal) {
   cudaFuncSetAttribute(tc2::tc2_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::Cfg<128>::SMEM);
   cudaFuncSetAttribute(tc2::tc2_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::Cfg<64>::SMEM);
   cudaFuncSetAttribute(tc2::tc2_gemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::Cfg<32>::SMEM);
+  cudaFuncSetAttribute(tc2::tc2p_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::CfgP<128>::SMEM);
+  cudaFuncSetAttribute(tc2::tc2p_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::CfgP<64>::SMEM);
   cudaFuncSetAttribute(tc3::tc3_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc3::Cfg<128>::SMEM);
   cudaFuncSetAttribute(tc3::tc3_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc3::Cfg<64>::SMEM);
   cudaFuncSetAttribute(rvqtc::rvq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, rvqtc::kSmem);
@@ -408,6 +412,7 @@ int mimi_b200_debug_set(mimi_b200_t* h, int key, int value) {
   else if (key == 3) h->mode = std::min(std::max(value, 0), 4);
   else if (key == 4) h->exp_single_acc = value != 0;
   else if (key == 5) h->exp_chunk_kb = std::max(value, 0);
+  else if (key == 6) h->use_planes = value != 0;
   else return fail(h, MIMI_B200_ERR_ARG, "debug_set: unknown key");
   return MIMI_B200_OK;
 }

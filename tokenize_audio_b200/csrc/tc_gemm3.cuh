@@ -66,12 +66,7 @@ struct Cfg {
   static_assert(W_STAGES >= 2, "weight ring too shallow");
 };
 
-__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(tc::smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(tc::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
+using tc2::tma_load_4d;
 
 // tmA_*: 4-D maps {C, stride, q, item}, box {32, 1, 128 (+G-1 for the second box), 1}: see tc_host.inl
 template <int BN>

@@ -228,11 +228,11 @@ static void launch_tc2(mimi_b200* h, const CUtensorMap& ahi, const CUtensorMap& 
   const int grid = (int)std::min<long long>(vt, h->num_sms);
   if (grid <= 0) return;
   if (w.BN == 128)
-    tc2::tc2_gemm_kernel<128><<<grid, tc2::kThreads, tc2::Cfg<128>::SMEM, st>>>(ahi, alo, w.map_hi, w.map_lo, w.K, ep, sc);
+    tc2::tc2_gemm_kernel<128><<<grid, tc2::threads(128), tc2::Cfg<128>::SMEM, st>>>(ahi, alo, w.map_hi, w.map_lo, w.K, ep, sc);
   else if (w.BN == 64)
-    tc2::tc2_gemm_kernel<64><<<grid, tc2::kThreads, tc2::Cfg<64>::SMEM, st>>>(ahi, alo, w.map_hi, w.map_lo, w.K, ep, sc);
+    tc2::tc2_gemm_kernel<64><<<grid, tc2::threads(64), tc2::Cfg<64>::SMEM, st>>>(ahi, alo, w.map_hi, w.map_lo, w.K, ep, sc);
   else
-    tc2::tc2_gemm_kernel<32><<<grid, tc2::kThreads, tc2::Cfg<32>::SMEM, st>>>(ahi, alo, w.map_hi, w.map_lo, w.K, ep, sc);
+    tc2::tc2_gemm_kernel<32><<<grid, tc2::threads(32), tc2::Cfg<32>::SMEM, st>>>(ahi, alo, w.map_hi, w.map_lo, w.K, ep, sc);
 }
 
 static int tc_gemm(TcCtx& c, int slot, const SplitBuf& a, int k, int s, int pad, const TcWeight& w, const TcOut& o, int prof_id) {
@@ -240,7 +240,9 @@ static int tc_gemm(TcCtx& c, int slot, const SplitBuf& a, int k, int s, int pad,
   int rc;
   if (slot < 0 || slot >= kTcSlots) return fail(c.h, MIMI_B200_ERR_ARG, "tc: bad map slot");
   const bool v3 = c.h->mode >= 4;
-  if (v3) { if ((rc = tc_amaps3(c, slot, a, k, s, pad, &m4))) return rc; }
+  const bool planes = !v3 && c.h->mode >= 2 && c.h->use_planes && s > 0 && k % s == 0 && k / s >= 2 && k / s <= 3 &&
+                      a.C % 32 == 0 && w.N % 64 == 0;
+  if (v3 || planes) { if ((rc = tc_amaps3(c, slot, a, k, s, pad, &m4))) return rc; }
   else if ((rc = tc_amaps(c, slot, a, k, s, pad, &ahi, &alo))) return rc;
   if (w.K != k * a.C) return fail(c.h, MIMI_B200_ERR_ARG, "tc: weight K mismatch");
   tc::Epilogue ep{};
@@ -257,6 +259,15 @@ static int tc_gemm(TcCtx& c, int slot, const SplitBuf& a, int k, int s, int pad,
   if (lout_max <= 0) return MIMI_B200_OK;
   if (v3) {
     if ((rc = launch_tc3(c.h, m4, w, ep, c.B, lout_max, a.C, k, s, c.st))) return rc;
+  } else if (planes) {
+    tc2::Sched sc{c.B, (lout_max + tc::kBM - 1) / tc::kBM, w.N / w.BN};
+    tc2::PlaneGeom gm{k / s, s, a.C / 32};
+    const long long vt = (long long)sc.mt_max * c.B * sc.ntn;
+    const int grid = (int)std::min<long long>(vt, c.h->num_sms);
+    if (w.BN == 128)
+      tc2::tc2p_gemm_kernel<128><<<grid, tc2::threads(128), tc2::CfgP<128>::SMEM, c.st>>>(m4[2], m4[3], w.map_hi, w.map_lo, ep, sc, gm);
+    else
+      tc2::tc2p_gemm_kernel<64><<<grid, tc2::threads(64), tc2::CfgP<64>::SMEM, c.st>>>(m4[2], m4[3], w.map_hi, w.map_lo, ep, sc, gm);
   } else if (c.h->mode >= 2) {
     launch_tc2(c.h, *ahi, *alo, w, ep, c.B, (lout_max + tc::kBM - 1) / tc::kBM, c.st);
   } else {
