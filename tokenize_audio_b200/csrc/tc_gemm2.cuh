@@ -14,7 +14,7 @@
 //            adds), then the cross-term accumulator (double-buffered per tile parity), then finish the tile:
 //            bias / GELU / LayerScale per thread = per row, a 32-column transpose through a swizzled smem
 //            staging tile, and row-contiguous float4 residual loads and raw / hi / lo stores (128 B segments).
-//   TMEM   = main[2] | small[2], 4*BN columns (BN <= 128).
+//   TMEM   = 2 chunk buffers x [main | cross terms], 4*BN columns (BN <= 128).
 #pragma once
 #include "tc_gemm.cuh"
 
@@ -93,7 +93,7 @@ __device__ __forceinline__ void drain_add(uint32_t taddr, float (&acc)[NCOL]) {
 // (tc2p_gemm_kernel): drain every accumulation chunk, add the cross-term accumulator, finish the tile.
 template <int BN, int PC_, int EPIW>
 __device__ __forceinline__ void epilogue_role(const Epilogue& ep, const Sched& sc, uint8_t* stg_base, uint64_t* acc_full,
-                                              uint64_t* acc_empty, uint64_t* small_empty, uint32_t tmem_base, int nchunks,
+                                              uint64_t* acc_empty, uint32_t tmem_base, int nchunks,
                                               int warp, int lane) {
   constexpr int HALF = BN / (EPIW / 4);            // columns per epilogue thread
   constexpr int PC = PC_;
@@ -123,7 +123,7 @@ __device__ __forceinline__ void epilogue_role(const Epilogue& ep, const Sched& s
     const uint32_t stg = tc::smem_u32(stg_base + ew * STG_WARP);         // [32 rows][LPR float4], swizzled
     const int rr = lane / LPR;                     // coalesced phase: row within an RPI-row group
     const int cj = lane % LPR;                     //                  float4 index inside the PC-wide piece
-    uint32_t cc = 0, lt = 0;
+    uint32_t cc = 0;
     for (int id = blockIdx.x; id < vtiles; id += gridDim.x) {
       int b, m0, n0, Lout;
       if (!decode(id, b, m0, n0, Lout)) continue;
@@ -145,18 +145,12 @@ __device__ __forceinline__ void epilogue_role(const Epilogue& ep, const Sched& s
         const uint32_t buf = cc & 1u;
         tc::mbar_wait(&acc_full[buf], (cc >> 1) & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        drain_add<HALF>(tmem_base + lane_off + buf * BN + (uint32_t)col0, acc);
+        // buffer layout per chunk: [main (BN columns) | cross terms (BN columns)], see the MMA issuer
+        drain_add<HALF>(tmem_base + lane_off + buf * (2 * BN) + (uint32_t)col0, acc);
+        drain_add<HALF>(tmem_base + lane_off + buf * (2 * BN) + BN + (uint32_t)col0, acc);
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&acc_empty[buf]);
-      }
-      {
-        const uint32_t tp = lt & 1u;
-        if (!ep.single_acc) drain_add<HALF>(tmem_base + lane_off + (2u + tp) * BN + (uint32_t)col0, acc);
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) tc::mbar_arrive(&small_empty[tp]);
-        ++lt;
       }
       // ---- finish the tile: rows m0 + 32*quarter + [0,32), columns n0 + col0 + [0,HALF) ---------------------
       const int row_base = m0 + quarter * 32;
@@ -236,8 +230,7 @@ tc2_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* acc_full = empty_bar + STAGES;         // [2] main chunk ready        (MMA -> epilogue)
   uint64_t* acc_empty = acc_full + 2;              // [2] main chunk drained      (epilogue -> MMA)
-  uint64_t* small_empty = acc_empty + 2;           // [2] cross-term acc drained  (epilogue -> MMA)
-  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(small_empty + 2);
+  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = K / kBK;
@@ -251,7 +244,6 @@ tc2_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     for (int s = 0; s < 2; ++s) {
       tc::mbar_init(&acc_full[s], 1);
       tc::mbar_init(&acc_empty[s], C::EPIW);
-      tc::mbar_init(&small_empty[s], C::EPIW);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -297,50 +289,44 @@ tc2_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     }
   } else if (warp == 1) {
     if (lane == 0) {
+      // Two MMAs per k-step instead of three: the stage keeps W_hi and W_lo adjacent, so ONE N = 2*BN MMA with A_hi
+      // yields A_hi W_hi^T (columns [0,BN): main) and A_hi W_lo^T (columns [BN,2BN): cross), and an N = BN MMA adds
+      // A_lo W_hi^T to the cross columns. A_hi is read from shared memory once instead of twice -- operand reads
+      // (128 B/clk/SM for three 128x128x8 MMAs) plus the TMA fills are what saturates shared memory here.
       constexpr uint32_t idesc = tc::make_idesc(kBM, BN);
+      constexpr uint32_t idesc2 = tc::make_idesc(kBM, 2 * BN);
       const uint32_t smem_base_u32 = tc::smem_u32(smem);
-      uint32_t kbc = 0, cc = 0, lt = 0;
+      uint32_t kbc = 0, cc = 0;
       for (int id = blockIdx.x; id < vtiles; id += gridDim.x) {
         int b, m0, n0, Lout;
         if (!decode(id, b, m0, n0, Lout)) continue;
-        const uint32_t tp = lt & 1u;
-        tc::mbar_wait(&small_empty[tp], ((lt >> 1) & 1u) ^ 1u);          // cross-term acc of tile lt-2 drained
-        const uint32_t tmem_small = tmem_base + (2u + tp) * BN;
         for (int c = 0; c < nchunks; ++c, ++cc) {
           const uint32_t buf = cc & 1u;
           tc::mbar_wait(&acc_empty[buf], ((cc >> 1) & 1u) ^ 1u);         // drained two chunks ago
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t tmem_main = tmem_base + buf * BN;
+          const uint32_t tmem_main = tmem_base + buf * (2 * BN);
           const int kb_end = min(nkb, (c + 1) * ckb);
           for (int kb = c * ckb; kb < kb_end; ++kb, ++kbc) {
             const uint32_t s = kbc % STAGES;
             const uint32_t ph = (kbc / STAGES) & 1u;
             tc::mbar_wait(&full_bar[s], ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            // descriptor low words: one encode per stage, then constant adds (16-byte units)
             const uint32_t d_ahi = tc::desc_lo(smem_base_u32 + s * STAGE);
-            constexpr uint32_t kAlo = A_BYTES >> 4, kWhi = (2 * A_BYTES) >> 4, kWlo = (2 * A_BYTES + W_BYTES) >> 4;
+            constexpr uint32_t kAlo = A_BYTES >> 4, kWhi = (2 * A_BYTES) >> 4;
             const bool first_in_chunk = kb == c * ckb;
-            const uint32_t tmem_x = ep.single_acc ? tmem_main : tmem_small;
-            const uint32_t xacc = ep.single_acc ? 1u : (uint32_t)(kb != 0);
 #pragma unroll
-            for (int k = 0; k < kBK / kUmmaK; ++k)
-              tc::umma_tf32_lo(tmem_main, d_ahi + 2 * k, d_ahi + kWhi + 2 * k, idesc, !(first_in_chunk && k == 0));
-#pragma unroll
-            for (int k = 0; k < kBK / kUmmaK; ++k)
-              tc::umma_tf32_lo(tmem_x, d_ahi + kAlo + 2 * k, d_ahi + kWhi + 2 * k, idesc, k != 0 ? 1u : xacc);
-#pragma unroll
-            for (int k = 0; k < kBK / kUmmaK; ++k)
-              tc::umma_tf32_lo(tmem_x, d_ahi + 2 * k, d_ahi + kWlo + 2 * k, idesc, 1u);
+            for (int k = 0; k < kBK / kUmmaK; ++k) {
+              tc::umma_tf32_lo(tmem_main, d_ahi + 2 * k, d_ahi + kWhi + 2 * k, idesc2, !(first_in_chunk && k == 0));
+              tc::umma_tf32_lo(tmem_main + BN, d_ahi + kAlo + 2 * k, d_ahi + kWhi + 2 * k, idesc, 1u);
+            }
             tc::umma_commit(&empty_bar[s]);
           }
-          tc::umma_commit(&acc_full[buf]);       // after the tile's last chunk this also covers the cross terms
+          tc::umma_commit(&acc_full[buf]);
         }
-        ++lt;
       }
     }
   } else {
-    epilogue_role<BN, C::PC, C::EPIW>(ep, sc, stg_base, acc_full, acc_empty, small_empty, tmem_base, nchunks, warp, lane);
+    epilogue_role<BN, C::PC, C::EPIW>(ep, sc, stg_base, acc_full, acc_empty, tmem_base, nchunks, warp, lane);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -407,8 +393,7 @@ tc2p_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   uint64_t* w_empty = w_full + NW;
   uint64_t* acc_full = w_empty + NW;
   uint64_t* acc_empty = acc_full + 2;
-  uint64_t* small_empty = acc_empty + 2;
-  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(small_empty + 2);
+  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nplanes = gm.s * gm.cpanels;
@@ -425,7 +410,6 @@ tc2p_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     for (int s = 0; s < 2; ++s) {
       tc::mbar_init(&acc_full[s], 1);
       tc::mbar_init(&acc_empty[s], C::EPIW);
-      tc::mbar_init(&small_empty[s], C::EPIW);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -478,14 +462,12 @@ tc2p_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = tc::make_idesc(kBM, BN);
+      constexpr uint32_t idesc2 = tc::make_idesc(kBM, 2 * BN);
       const uint32_t smem_base_u32 = tc::smem_u32(smem), w_base_u32 = tc::smem_u32(w_base);
-      uint32_t ac = 0, wc = 0, cc = 0, lt = 0;
+      uint32_t ac = 0, wc = 0, cc = 0;
       for (int id = blockIdx.x; id < vtiles; id += gridDim.x) {
         int b, m0, n0, Lout;
         if (!decode(id, b, m0, n0, Lout)) continue;
-        const uint32_t tp = lt & 1u;
-        tc::mbar_wait(&small_empty[tp], ((lt >> 1) & 1u) ^ 1u);
-        const uint32_t tmem_small = tmem_base + (2u + tp) * BN;
         int kb = 0;
         for (int pi = 0; pi < nplanes; ++pi, ++ac) {
           const uint32_t as = ac % NA;
@@ -498,32 +480,24 @@ tc2p_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             const uint32_t ws = wc % NW;
             tc::mbar_wait(&w_full[ws], (wc / NW) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t tmem_main = tmem_base + buf * BN;
+            const uint32_t tmem_main = tmem_base + buf * (2 * BN);
             const uint32_t d_ahi = d_a0 + (uint32_t)(dq * 8);                 // dq rows of 128 B, in 16-byte units
             const uint32_t d_alo = d_ahi + (A_HALF >> 4);
-            const uint32_t d_whi = tc::desc_lo(w_base_u32 + ws * W_STAGE);
-            const uint32_t d_wlo = d_whi + (W_BYTES >> 4);
+            const uint32_t d_whi = tc::desc_lo(w_base_u32 + ws * W_STAGE);    // [W_hi | W_lo] adjacent: N = 2*BN
 #pragma unroll
-            for (int k = 0; k < kBK / kUmmaK; ++k)
-              tc::umma_tf32_lo(tmem_main, d_ahi + 2 * k, d_whi + 2 * k, idesc, !(first_in_chunk && k == 0));
-#pragma unroll
-            for (int k = 0; k < kBK / kUmmaK; ++k)
-              tc::umma_tf32_lo(tmem_small, d_alo + 2 * k, d_whi + 2 * k, idesc, (uint32_t)((kb | k) != 0));
-#pragma unroll
-            for (int k = 0; k < kBK / kUmmaK; ++k)
-              tc::umma_tf32_lo(tmem_small, d_ahi + 2 * k, d_wlo + 2 * k, idesc, 1u);
+            for (int k = 0; k < kBK / kUmmaK; ++k) {
+              tc::umma_tf32_lo(tmem_main, d_ahi + 2 * k, d_whi + 2 * k, idesc2, !(first_in_chunk && k == 0));
+              tc::umma_tf32_lo(tmem_main + BN, d_alo + 2 * k, d_whi + 2 * k, idesc, 1u);
+            }
             tc::umma_commit(&w_empty[ws]);
             if ((kb + 1) % ckb == 0 || kb + 1 == nkb) { tc::umma_commit(&acc_full[buf]); ++cc; }
           }
           tc::umma_commit(&a_empty[as]);
         }
-        ++lt;
       }
     }
   } else {
-    Epilogue ep2 = ep;
-    ep2.single_acc = 0;
-    epilogue_role<BN, C::PC, C::EPIW>(ep2, sc, stg_base, acc_full, acc_empty, small_empty, tmem_base, nchunks, warp, lane);
+    epilogue_role<BN, C::PC, C::EPIW>(ep, sc, stg_base, acc_full, acc_empty, tmem_base, nchunks, warp, lane);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
