@@ -86,7 +86,7 @@ front_fused_kernel(const __grid_constant__ CUtensorMap tmW1_hi, const __grid_con
   uint64_t* w_ready = bars + 4;         // weights landed (TMA)
   uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(bars + 5);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = tc::uniform_warp_idx(), lane = threadIdx.x & 31;
   const int vtiles = p.mt_max * p.B;
 
   if (threadIdx.x == 0) {
@@ -134,12 +134,12 @@ front_fused_kernel(const __grid_constant__ CUtensorMap tmW1_hi, const __grid_con
     const int wq = warp & 3;                       // TMEM lane quarter
     const int ch = (warp >> 2) & 1;                // channel half: L0 / R1b channels [32ch, +32), R1a channels [16ch, +16)
     const int m = wq * 32 + lane;                  // tile row owned by this thread
-    const bool issuer = (m == 0) && (ch == 0);     // issues this warpgroup's MMAs
+    const bool issue_warp = (wq == 0) && (ch == 0);   // one elected lane of this warp issues the group's MMAs
     constexpr uint32_t idesc32 = tc::make_idesc(128, 32);
     constexpr uint32_t idesc64 = tc::make_idesc(128, 64);
     constexpr uint32_t idesc128 = tc::make_idesc(128, 128);
     auto wg_sync = [&]() { asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory"); };
-    if (issuer) tc::mbar_wait(w_ready, 0);
+    if (issue_warp) tc::mbar_wait(w_ready, 0);
     uint8_t* buf = smem + g * kTileBuf;
     const uint32_t bufa = tc::smem_u32(buf);
     const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
@@ -205,7 +205,7 @@ front_fused_kernel(const __grid_constant__ CUtensorMap tmW1_hi, const __grid_con
         }
         fence_async_smem();
         wg_sync();
-        if (issuer) {
+        if (issue_warp && tc::elect_one()) {
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t main1 = tmem_base + g * 192, small1 = main1 + 32;
           const uint32_t d_buf = tc::desc_lo(bufa), d_w1 = tc::desc_lo(tc::smem_u32(w1));
@@ -252,7 +252,7 @@ front_fused_kernel(const __grid_constant__ CUtensorMap tmW1_hi, const __grid_con
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         fence_async_smem();
         wg_sync();
-        if (issuer) {
+        if (issue_warp && tc::elect_one()) {
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t a_hi = tc::desc_lo(bufa);                       // R1 operand aliases hi panel 0 / hi panel 1
           const uint32_t a_lo = a_hi + (kPanelBytes >> 4);

@@ -140,6 +140,7 @@ struct mimi_b200 {
                                                // 1 = first-generation tcgen05 kernel (level 0 on FFMA), 0 = all-fp32 SIMT
   int last_mode = 0;
   int exp_single_acc = 0, exp_chunk_kb = 0;    // accuracy experiments (debug_set keys 4, 5)
+  int exp_prefetch = 0;                        // L2 prefetch of the next tile's activation boxes (debug_set key 7)
   int use_planes = 0;                          // plane-staged activations for k = G*stride convs (debug_set key 6); off:
                                                // fewer L2 bytes but not faster (shared-memory bandwidth binds)
   f0::Consts f0_consts;
@@ -413,6 +414,7 @@ int mimi_b200_debug_set(mimi_b200_t* h, int key, int value) {
   else if (key == 4) h->exp_single_acc = value != 0;
   else if (key == 5) h->exp_chunk_kb = std::max(value, 0);
   else if (key == 6) h->use_planes = value != 0;
+  else if (key == 7) h->exp_prefetch = value != 0;
   else return fail(h, MIMI_B200_ERR_ARG, "debug_set: unknown key");
   return MIMI_B200_OK;
 }

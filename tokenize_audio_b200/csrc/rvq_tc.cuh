@@ -76,7 +76,7 @@ rvq_tc_kernel(const __grid_constant__ CUtensorMap tmE_hi, const __grid_constant_
   uint64_t* r_ready = acc_empty + 2;                         // residual operand of this stage staged (8 warps)
   uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(r_ready + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = tc::uniform_warp_idx(), lane = threadIdx.x & 31;
   const int f0 = blockIdx.x * kFrames;
   const int nf = min(kFrames, p.total_frames - f0);
 
@@ -129,7 +129,7 @@ rvq_tc_kernel(const __grid_constant__ CUtensorMap tmE_hi, const __grid_constant_
           }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc128 = tc::make_idesc(128, 128);
       constexpr uint32_t idesc64 = tc::make_idesc(128, 64);
       const uint32_t d_rop = tc::desc_lo(tc::smem_u32(r_op));
@@ -148,14 +148,17 @@ rvq_tc_kernel(const __grid_constant__ CUtensorMap tmE_hi, const __grid_constant_
             const uint32_t e_hi = tc::desc_lo(tc::smem_u32(a_ring) + s * kAStage);
             const uint32_t e_lo = e_hi + ((kAStage / 2) >> 4);
             const uint32_t r_st = d_rop + ((kb * kRKb) >> 4);   // [r_hi (64 rows) | r_lo (64 rows)] stacked: N = 128
+            if (tc::elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              tc::umma_tf32_lo(acc, e_hi + 2 * k, r_st + 2 * k, idesc128, (uint32_t)((kb | k) != 0));
-              tc::umma_tf32_lo(acc + 64, e_lo + 2 * k, r_st + 2 * k, idesc64, 1u);
+              for (int k = 0; k < 4; ++k) {
+                tc::umma_tf32_lo(acc, e_hi + 2 * k, r_st + 2 * k, idesc128, (uint32_t)((kb | k) != 0));
+                tc::umma_tf32_lo(acc + 64, e_lo + 2 * k, r_st + 2 * k, idesc64, 1u);
+              }
+              tc::umma_commit(&empty_bar[s]);
+              if (kb + 1 == kKB) tc::umma_commit(&acc_full[buf]);
             }
-            tc::umma_commit(&empty_bar[s]);
+            __syncwarp();
           }
-          tc::umma_commit(&acc_full[buf]);
         }
       }
     }

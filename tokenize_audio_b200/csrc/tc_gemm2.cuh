@@ -232,7 +232,7 @@ tc2_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   uint64_t* acc_empty = acc_full + 2;              // [2] main chunk drained      (epilogue -> MMA)
   uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = tc::uniform_warp_idx(), lane = threadIdx.x & 31;
   const int nkb = K / kBK;
   const int ckb = ep.chunk_kb > 0 ? ep.chunk_kb : kChunkKB;
   const int nchunks = (nkb + ckb - 1) / ckb;
@@ -274,7 +274,17 @@ tc2_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       for (int id = blockIdx.x; id < vtiles; id += gridDim.x) {
         int b, m0, n0, Lout;
         if (!decode(id, b, m0, n0, Lout)) continue;
+        // the activation rows of this CTA's NEXT tile are pulled towards L2 one tile ahead, k-block by k-block, so
+        // that their TMA loads hit L2 instead of paying the DRAM latency with only three stages in flight
+        int pb = 0, pm0 = 0, pn0 = 0, pL = 0;
+        bool pf = false;
+        if (ep.prefetch_next)
+          for (int nid = id + gridDim.x; nid < vtiles && !pf; nid += gridDim.x) pf = decode(nid, pb, pm0, pn0, pL);
         for (int kb = 0; kb < nkb; ++kb, ++kbc) {
+          if (pf) {
+            tc::tma_prefetch_3d(&tmA_hi, kb * kBK, pm0, pb);
+            tc::tma_prefetch_3d(&tmA_lo, kb * kBK, pm0, pb);
+          }
           const uint32_t s = kbc % STAGES;
           const uint32_t ph = (kbc / STAGES) & 1u;
           tc::mbar_wait(&empty_bar[s], ph ^ 1u);
@@ -288,7 +298,9 @@ tc2_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
+      // The whole warp walks the loop and waits on the barriers (converged), one elected lane issues: this keeps
+      // descriptor arithmetic on the uniform datapath (no per-instruction divergence loop around tcgen05.mma).
       // Two MMAs per k-step instead of three: the stage keeps W_hi and W_lo adjacent, so ONE N = 2*BN MMA with A_hi
       // yields A_hi W_hi^T (columns [0,BN): main) and A_hi W_lo^T (columns [BN,2BN): cross), and an N = BN MMA adds
       // A_lo W_hi^T to the cross columns. A_hi is read from shared memory once instead of twice -- operand reads
@@ -314,14 +326,17 @@ tc2_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
             const uint32_t d_ahi = tc::desc_lo(smem_base_u32 + s * STAGE);
             constexpr uint32_t kAlo = A_BYTES >> 4, kWhi = (2 * A_BYTES) >> 4;
             const bool first_in_chunk = kb == c * ckb;
+            if (tc::elect_one()) {
 #pragma unroll
-            for (int k = 0; k < kBK / kUmmaK; ++k) {
-              tc::umma_tf32_lo(tmem_main, d_ahi + 2 * k, d_ahi + kWhi + 2 * k, idesc2, !(first_in_chunk && k == 0));
-              tc::umma_tf32_lo(tmem_main + BN, d_ahi + kAlo + 2 * k, d_ahi + kWhi + 2 * k, idesc, 1u);
+              for (int k = 0; k < kBK / kUmmaK; ++k) {
+                tc::umma_tf32_lo(tmem_main, d_ahi + 2 * k, d_ahi + kWhi + 2 * k, idesc2, !(first_in_chunk && k == 0));
+                tc::umma_tf32_lo(tmem_main + BN, d_ahi + kAlo + 2 * k, d_ahi + kWhi + 2 * k, idesc, 1u);
+              }
+              tc::umma_commit(&empty_bar[s]);
+              if (kb + 1 == kb_end) tc::umma_commit(&acc_full[buf]);
             }
-            tc::umma_commit(&empty_bar[s]);
+            __syncwarp();
           }
-          tc::umma_commit(&acc_full[buf]);
         }
       }
     }
@@ -395,7 +410,7 @@ tc2p_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = tc::uniform_warp_idx(), lane = threadIdx.x & 31;
   const int nplanes = gm.s * gm.cpanels;
   const int nkb = nplanes * gm.G;
   const int ckb = ep.chunk_kb > 0 ? ep.chunk_kb : kChunkKB;
@@ -460,7 +475,7 @@ tc2p_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc = tc::make_idesc(kBM, BN);
       constexpr uint32_t idesc2 = tc::make_idesc(kBM, 2 * BN);
       const uint32_t smem_base_u32 = tc::smem_u32(smem), w_base_u32 = tc::smem_u32(w_base);
@@ -484,15 +499,20 @@ tc2p_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             const uint32_t d_ahi = d_a0 + (uint32_t)(dq * 8);                 // dq rows of 128 B, in 16-byte units
             const uint32_t d_alo = d_ahi + (A_HALF >> 4);
             const uint32_t d_whi = tc::desc_lo(w_base_u32 + ws * W_STAGE);    // [W_hi | W_lo] adjacent: N = 2*BN
+            const bool chunk_end = (kb + 1) % ckb == 0 || kb + 1 == nkb;
+            if (tc::elect_one()) {
 #pragma unroll
-            for (int k = 0; k < kBK / kUmmaK; ++k) {
-              tc::umma_tf32_lo(tmem_main, d_ahi + 2 * k, d_whi + 2 * k, idesc2, !(first_in_chunk && k == 0));
-              tc::umma_tf32_lo(tmem_main + BN, d_alo + 2 * k, d_whi + 2 * k, idesc, 1u);
+              for (int k = 0; k < kBK / kUmmaK; ++k) {
+                tc::umma_tf32_lo(tmem_main, d_ahi + 2 * k, d_whi + 2 * k, idesc2, !(first_in_chunk && k == 0));
+                tc::umma_tf32_lo(tmem_main + BN, d_alo + 2 * k, d_whi + 2 * k, idesc, 1u);
+              }
+              tc::umma_commit(&w_empty[ws]);
+              if (chunk_end) tc::umma_commit(&acc_full[buf]);
+              if (dq + 1 == gm.G) tc::umma_commit(&a_empty[as]);
             }
-            tc::umma_commit(&w_empty[ws]);
-            if ((kb + 1) % ckb == 0 || kb + 1 == nkb) { tc::umma_commit(&acc_full[buf]); ++cc; }
+            __syncwarp();
+            if (chunk_end) ++cc;
           }
-          tc::umma_commit(&a_empty[as]);
         }
       }
     }
@@ -523,7 +543,7 @@ tc_shift_probe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + A_BYTES + W_BYTES);
   uint64_t* done = bar + 1;
   uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(done + 1);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = tc::uniform_warp_idx(), lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     tc::mbar_init(bar, 1);
     tc::mbar_init(done, 1);

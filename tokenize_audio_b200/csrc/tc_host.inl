@@ -254,6 +254,7 @@ static int tc_gemm(TcCtx& c, int slot, const SplitBuf& a, int k, int s, int pad,
   }
   ep.act = o.act; ep.elu_split = o.elu_split;
   ep.single_acc = c.h->exp_single_acc; ep.chunk_kb = c.h->exp_chunk_kb;
+  ep.prefetch_next = c.h->exp_prefetch && w.N / w.BN == 1;      // with several n-tiles the rows are in L2 already
   ep.len_in = c.dlen[a.level]; ep.uniform_len_in = c.maxlen[a.level]; ep.conv_stride = s; ep.N = w.N;
   const int lout_max = (c.maxlen[a.level] + s - 1) / s;
   if (lout_max <= 0) return MIMI_B200_OK;
