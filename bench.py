@@ -300,9 +300,12 @@ def run_b200(args, rank, world, local_rank):
         if per_s is not None:
             traffic = per_s * audio_per_launch
     roof.update({"traffic": traffic, "kernel": kind, "share_of_step": kms / sum(v[0] for v in prof.values()),
-                 "avg_launch_ms": 1e3 * per_launch_s, "peak_source": peaks["src"],
-                 "precision": "3xTF32 on tcgen05 (fp32-equivalent; 3 tensor passes per MAC) or fp32 FFMA for the SIMT kernels; "
-                              "achieved counts algorithmic FLOPs once; peak is the measured dense bf16 figure"})
+                 "avg_launch_ms": 1e3 * per_launch_s, "peak_source": peaks["src"]})
+    if roof["bound"] == "tensor":
+        roof["precision"] = ("3xTF32 on tcgen05 (fp32-equivalent; 3 tensor passes per MAC); achieved counts algorithmic "
+                             "FLOPs once; peak is the measured dense bf16 figure")
+    else:
+        roof["note"] = "achieved = algorithmic bytes of the launch / CUDA-event duration; peak = measured copy bandwidth"
     breakdown = {k: round(v[0] / args.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
 
     # ---- CPU baseline beside it (rank 0, N=1 only): the reference implementation on host cores -----------
