@@ -111,3 +111,23 @@ def test_sw128_descriptor_row_shift_property():
             assert err < 2e-3, f"shift {shift}: {err:.2e}"          # single-pass TF32
     finally:
         lib.mimi_b200_destroy(h)
+
+
+def test_front_door_and_string_outputs(b200_model):
+    """SURVEY.md 8(f) ranks 1-2: native-rate clips resampled on the GPU then encoded == resample_audio + encode;
+    encode_to_strings == encode + codes_to_chars per item."""
+    from tokenize_audio_b200 import utils
+    from tokenize_audio_b200.encoder import MimiEncoder
+    enc = MimiEncoder(b200_model, num_quantizers=8)
+    clips16 = [synth.synth_speech(1200 + i, n, sr=16000) for i, n in enumerate([16000, 23456, 9000])]
+    got = enc.encode_native_rate_batch(clips16, 16000)
+    clips24 = [utils.resample_audio(c, 16000, 24000) for c in clips16]
+    want = enc.encode_audio_batch(clips24)
+    assert [g.shape for g in got] == [w.shape for w in want]
+    same = sum(int((g == w).sum()) for g, w in zip(got, want)) / sum(w.size for w in want)
+    assert same >= 0.999          # same kernel, same filter: only the batch padding differs
+    strs = enc.encode_to_strings(clips24)
+    for s_, w in zip(strs, want):
+        assert s_ == utils.codes_to_chars(w, 2048)
+        assert len(s_) == w.size
+    assert enc.encode_native_rate_batch([], 16000) == [] and enc.encode_to_strings([]) == []

@@ -56,3 +56,15 @@ def test_product_never_imports_the_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f"{f} imports the oracle"
                 assert "import transformers" not in src and "from transformers" not in src, f"{f} imports transformers"
+
+
+def test_sub_batch_schedule_covers_every_item_once():
+    from tokenize_audio_b200.encoder import MimiEncoder
+    for B in (2, 3, 8, 9, 16, 24, 64, 100, 257):
+        for chunk in (1, 4, 16, 64):
+            parts = MimiEncoder._sub_batches(B, chunk)
+            flat = [i for p in parts for i in p]
+            assert flat == list(range(B))
+            assert all(len(p) > 0 for p in parts)
+            assert len(parts) <= 3 or chunk < B // 4        # a small head, then at most two big launches
+    assert [len(p) for p in MimiEncoder._sub_batches(64, 16)] == [8, 28, 28]

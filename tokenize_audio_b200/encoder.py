@@ -366,6 +366,16 @@ class MimiEncoder:
             self._pinned_codes = None
             self._pinned_codes = torch.empty(max(int(codes * 1.25), 1), dtype=torch.int64).pin_memory()
 
+    @staticmethod
+    def _sub_batches(B: int, chunk_items: int) -> List[List[int]]:
+        """Item indices of the pipelined sub-batches of one ``encode_audio_batch`` call: a small first one gets the
+        GPU going while the rest is still being staged, then at most two large ones (fewer, larger launches keep the
+        persistent kernels efficient)."""
+        bounds = [0, min(B, max(1, chunk_items // 2))]
+        while bounds[-1] < B:
+            bounds.append(min(B, bounds[-1] + max(chunk_items, (B - bounds[1] + 1) // 2)))
+        return [list(range(a, b)) for a, b in zip(bounds[:-1], bounds[1:])]
+
     def _check_rate(self, sample_rate: int) -> None:
         if sample_rate != self.feature_extractor.sampling_rate:
             self.feature_extractor(raw_audio=np.zeros(1, np.float32), sampling_rate=sample_rate)   # raises ValueError
@@ -433,11 +443,7 @@ class MimiEncoder:
             self._check_rate(sample_rate)
             B = len(audio_arrays)
             K = NUM_QUANTIZERS if self.num_quantizers is None else int(self.num_quantizers)
-            # a small first sub-batch gets the GPU going while the rest is still being staged
-            bounds = [0, min(B, max(1, self.chunk_items // 2))]
-            while bounds[-1] < B:
-                bounds.append(min(B, bounds[-1] + max(self.chunk_items, (B - bounds[1] + 1) // 2)))
-            chunks = [list(range(a, b)) for a, b in zip(bounds[:-1], bounds[1:])]
+            chunks = self._sub_batches(B, self.chunk_items)
             # a sub-batch is padded to whole frames (but never beyond the full batch length): every item then sees the
             # same zeros behind its last kept frame as in the reference's single padded batch
             n_full = max(original_lengths)
@@ -478,3 +484,40 @@ class MimiEncoder:
                 for j, i in enumerate(ch):
                     result.append(arr[j, :, : int(np.ceil(original_lengths[i] / frame_rate))].copy())
             return result
+
+    # -- the callers and data formats either side of the path ---------------------------------
+    def encode_native_rate_batch(self, audio_arrays: List[np.ndarray], sample_rate: int) -> List[np.ndarray]:
+        """GPU front door (8f rank 1): what the reference scripts do with ``librosa.resample`` on the CPU before
+        calling the wrapper (REF/librispeech-mimi/process_librispeech_train.py:189-192, REF/*/utils.py:84-87) --
+        clips at their native rate go to the GPU as they are (16 kHz audio is 1.5x fewer H2D bytes), are resampled
+        to 24 kHz by the polyphase kernel straight into the zero-padded ``[B,1,N]`` layout, and encoded ragged.
+        Returns what ``encode_audio_batch`` returns for the resampled clips."""
+        from . import utils
+        if len(audio_arrays) == 0:
+            return []
+        if sample_rate == self.feature_extractor.sampling_rate:
+            return self.encode_audio_batch(audio_arrays, sample_rate)
+        K = self.num_quantizers
+        with torch.no_grad():
+            x, lens = utils.resample_batch(audio_arrays, sample_rate, self.feature_extractor.sampling_rate,
+                                           device=self.model.device)
+            out = self.model.encode(x, None, num_quantizers=K, valid_lengths=lens if self.ragged else None)
+            codes = out.audio_codes.cpu().numpy()
+        return [codes[i, :, : -(-n // FRAME_SIZE)].copy() for i, n in enumerate(lens)]
+
+    def encode_to_strings(self, audio_arrays: List[np.ndarray], sample_rate: int = 24000, num_codebooks: int = 8,
+                          codebook_size: int = 2048, unicode_offset: int = 0xE000) -> List[str]:
+        """Codes -> storage format on the GPU (8f rank 2): the ``audio_codes[:8]`` + ``codes_to_chars`` step every
+        script performs per item on the host (REF/emilia-mimi/process_shard.py:505-506), as one UTF-8 kernel and
+        one device->host copy per batch. Returns the unicode strings ``codes_to_chars`` would build."""
+        from . import utils
+        if len(audio_arrays) == 0:
+            return []
+        self._check_rate(sample_rate)
+        lens = [len(a) for a in audio_arrays]
+        with torch.no_grad():
+            x = self._stage(audio_arrays, sample_rate)
+            out = self.model.encode(x, None, num_quantizers=num_codebooks, valid_lengths=lens if self.ragged else None)
+            frames = [-(-n // FRAME_SIZE) for n in lens]
+            raw = utils.codes_to_utf8_batch(out.audio_codes, frames, codebook_size, unicode_offset)
+        return [r.decode("utf-8") for r in raw]
