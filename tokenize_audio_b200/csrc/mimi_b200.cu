@@ -83,11 +83,12 @@ struct PlanTC {
 
 struct MapSet { std::vector<CUtensorMap> maps, maps3; uint64_t built = 0, built3 = 0; };
 struct MapKey {
-  const void* ws; int B; long long N;
+  const void* ws; int B; long long N; int layout;     // layout: which workspace plan the offsets come from
   bool operator<(const MapKey& o) const {
     if (ws != o.ws) return ws < o.ws;
     if (B != o.B) return B < o.B;
-    return N < o.N;
+    if (N != o.N) return N < o.N;
+    return layout < o.layout;
   }
 };
 
@@ -547,7 +548,10 @@ int mimi_b200_workspace_bytes(mimi_b200_t* h, int B, int64_t N, int K, size_t* o
   if (!h || !out_bytes) return fail(h, MIMI_B200_ERR_ARG, "workspace_bytes: NULL argument");
   if (B < 0 || N < 0 || N > (1ll << 30) || K < 1 || K > MIMI_B200_MAX_QUANTIZERS)
     return fail(h, MIMI_B200_ERR_ARG, "workspace_bytes: bad B/N/K");
-  *out_bytes = std::max(make_plan(B, N, K).bytes, make_plan_tc(B, N, K).bytes) + 256;
+  // sized for the compute mode in force (debug_set key 3): the fp32 FFMA plan only in mode 0, level-0 buffers only
+  // in the unfused tensor-core modes
+  const bool simt = h->mode == 0 || h->dbg_last_conv != MIMI_B200_NUM_CONVS - 1;
+  *out_bytes = (simt ? make_plan(B, N, K).bytes : make_plan_tc(B, N, K, h->mode < 3).bytes) + 256;
   return MIMI_B200_OK;
 }
 
@@ -571,7 +575,7 @@ int mimi_b200_encode(mimi_b200_t* h, const float* d_input, int B, int64_t N, con
 
   const bool use_tc = h->mode >= 1 && h->dbg_last_conv == MIMI_B200_NUM_CONVS - 1;
   const Plan p = make_plan(B, N, K);
-  const PlanTC pt = make_plan_tc(B, N, K);
+  const PlanTC pt = make_plan_tc(B, N, K, h->mode < 3);
   const size_t need = use_tc ? pt.bytes : p.bytes;
   // align the workspace base to 256 bytes
   uintptr_t base = (reinterpret_cast<uintptr_t>(d_workspace) + 255) & ~uintptr_t(255);

@@ -98,7 +98,9 @@ static int tc_load_weights(mimi_b200* h, const mimi_b200_weights_t* w) {
   return MIMI_B200_OK;
 }
 
-static PlanTC make_plan_tc(int B, long long N, int K) {
+// `level0` = also lay out the level-0 buffers the unfused modes (1, 2) need; the default path keeps the 24 kHz
+// activations on chip, which saves 27.6 MB of workspace per audio-second
+static PlanTC make_plan_tc(int B, long long N, int K, bool level0) {
   PlanTC p;
   p.B = B; p.K = K; p.N = N;
   long long L = N;
@@ -115,8 +117,11 @@ static PlanTC make_plan_tc(int B, long long N, int K) {
     s.lo = take((long long)B * s.item_stride + 64);
     return s;
   };
-  p.a0 = raw(0, 64);   p.r1 = raw(0, 32);
-  p.s_a0 = split(0, 64, kHalo, 0);  p.s_r1 = split(0, 32, 0, 0);
+  p.a0 = p.r1 = 0;
+  if (level0) {
+    p.a0 = raw(0, 64);   p.r1 = raw(0, 32);
+    p.s_a0 = split(0, 64, kHalo, 0);  p.s_r1 = split(0, 32, 0, 0);
+  }
   p.s_h1 = split(0, 64, kHalo, kHalo);
   p.d1 = raw(1, 128);  p.s_d1 = split(1, 128, kHalo, kHalo);  p.s_r2 = split(1, 64, 0, 0);  p.s_h2 = split(1, 128, kHalo, kHalo);
   p.d2 = raw(2, 256);  p.s_d2 = split(2, 256, kHalo, kHalo);  p.s_r3 = split(2, 128, 0, 0); p.s_h3 = split(2, 256, kHalo, kHalo);
@@ -302,7 +307,7 @@ static int encode_tc(mimi_b200* h, const float* d_input, int B, long long N, int
                      const int* const* dlen, const int* maxlen, const int* dprefix, int total_frames,
                      int64_t* d_codes, float* d_latent_opt, cudaStream_t st) {
   int rc;
-  const MapKey key{ws, B, N};
+  const MapKey key{ws, B, N, h->mode < 3 ? 1 : 0};
   auto it = h->amap_cache.find(key);
   TcCtx c{h, &p, ws, B, st, dlen, maxlen, nullptr, nullptr, nullptr, nullptr};
   if (it == h->amap_cache.end()) {
