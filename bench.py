@@ -210,6 +210,8 @@ def run_b200(args, rank, world, local_rank):
         model.debug_set(6, args.planes)
     if args.prefetch is not None:
         model.debug_set(7, args.prefetch)
+    if args.att is not None:
+        model.debug_set(8, args.att)
     wrapper = MimiEncoder(model, device=str(dev), ragged=True, num_quantizers=K_CODEBOOKS)
     clips, lengths, batches = make_workload(rank)
     peaks = load_peaks()
@@ -358,6 +360,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS), help="c2 = the metric's config (default)")
     ap.add_argument("--mode", type=int, default=None, help="debug: kernel generation (see MimiB200Model.set_mode)")
     ap.add_argument("--planes", type=int, default=None, help="debug: plane-staged conv activations on/off")
+    ap.add_argument("--att", type=int, default=None, help="debug: attention kernel variant (2 or 3)")
     ap.add_argument("--prefetch", type=int, default=None, help="debug: next-tile L2 prefetch in the GEMM producer on/off")
     args = ap.parse_args()
     select_workload(args.workload)

@@ -134,7 +134,8 @@ int mimi_b200_debug_tap(mimi_b200_t* h, int which, float* d_out, size_t out_capa
    1 = first-generation tcgen05 kernel for the wide layers (level 0 on FFMA), 0 = all-fp32 FFMA;
    key 4 / key 5 = accuracy experiments on the persistent kernel: cross terms into the main accumulator (0/1),
    k-blocks per accumulation chunk (0 = default 4); key 6 = plane-staged activations for k = G*stride convs
-   (tc2p_gemm_kernel; default 0). */
+   (tc2p_gemm_kernel; default 0); key 7 = next-tile L2 prefetch in the GEMM producer (default 0); key 8 = attention
+   kernel variant (2 = 8 warps x 4 queries, default; 3 = 16 warps x 2 queries). */
 int mimi_b200_debug_set(mimi_b200_t* h, int key, int value);
 
 /* Read and reset the per-launch profile gathered since profiling was switched on: for launch kind

@@ -141,6 +141,8 @@ struct mimi_b200 {
                                                // 1 = first-generation tcgen05 kernel (level 0 on FFMA), 0 = all-fp32 SIMT
   int last_mode = 0;
   int exp_single_acc = 0, exp_chunk_kb = 0;    // accuracy experiments (debug_set keys 4, 5)
+  int att_variant = 2;                         // 2 = 8 warps x 4 queries (default), 3 = 16 warps x 2 queries: 12 % slower, the
+                                               // kernel is bound by shared-memory reads per FMA, not by latency (debug_set key 8)
   int exp_prefetch = 0;                        // L2 prefetch of the next tile's activation boxes (debug_set key 7)
   int use_planes = 0;                          // plane-staged activations for k = G*stride convs (debug_set key 6); off:
                                                // fewer L2 bytes but not faster (shared-memory bandwidth binds)
@@ -373,6 +375,7 @@ int mimi_b200_create(mimi_b200_t** out, int device_ordinal) {
   for (int i = 0; i < kStageSlots; ++i) cudaEventCreateWithFlags(&h->stage_ev[i], cudaEventDisableTiming);
   cudaFuncSetAttribute(swa_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttSmemBytes);
   cudaFuncSetAttribute(swa_attention2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAtt2SmemBytes);
+  cudaFuncSetAttribute(swa_attention3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAtt2SmemBytes);
   cudaFuncSetAttribute(rvq_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRvqSmemBytes);
   cudaFuncSetAttribute(tc::tc_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::smem_bytes(128));
   cudaFuncSetAttribute(tc::tc_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::smem_bytes(64));
@@ -416,6 +419,7 @@ int mimi_b200_debug_set(mimi_b200_t* h, int key, int value) {
   else if (key == 5) h->exp_chunk_kb = std::max(value, 0);
   else if (key == 6) h->use_planes = value != 0;
   else if (key == 7) h->exp_prefetch = value != 0;
+  else if (key == 8) h->att_variant = value == 2 ? 2 : 3;
   else return fail(h, MIMI_B200_ERR_ARG, "debug_set: unknown key");
   return MIMI_B200_OK;
 }

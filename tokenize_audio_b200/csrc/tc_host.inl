@@ -415,8 +415,12 @@ static int encode_tc(mimi_b200* h, const float* d_input, int B, long long N, int
       const int nsplit = std::max(1, std::min(ntiles, (4 * h->num_sms + kHeads * B - 1) / (kHeads * B)));
       const int tps = (ntiles + nsplit - 1) / nsplit;
       dim3 agrid((ntiles + tps - 1) / tps, kHeads, B);
-      swa_attention2_kernel<<<agrid, 256, kAtt2SmemBytes, st>>>(ws + p.qkv, rstride(4, 1536), ws + p.s_att.hi, rstride(4, 512),
-                                                                h->rope_cos, h->rope_sin, dlen[4], T25, ws + p.s_att.lo, tps);
+      if (h->att_variant == 3)
+        swa_attention3_kernel<<<agrid, 512, kAtt2SmemBytes, st>>>(ws + p.qkv, rstride(4, 1536), ws + p.s_att.hi, rstride(4, 512),
+                                                                  h->rope_cos, h->rope_sin, dlen[4], T25, ws + p.s_att.lo, tps);
+      else
+        swa_attention2_kernel<<<agrid, 256, kAtt2SmemBytes, st>>>(ws + p.qkv, rstride(4, 1536), ws + p.s_att.hi, rstride(4, 512),
+                                                                  h->rope_cos, h->rope_sin, dlen[4], T25, ws + p.s_att.lo, tps);
     } else {
       dim3 agrid((T25 + kAttQT - 1) / kAttQT, kHeads, B);
       swa_attention_kernel<<<agrid, 256, kAttSmemBytes, st>>>(ws + p.qkv, rstride(4, 1536), ws + p.s_att.hi, rstride(4, 512),
