@@ -24,6 +24,7 @@
 #include "front_fused.cuh"
 #include "tc_gemm3.cuh"
 #include "rvq_tc.cuh"
+#include "tc_gemm4.cuh"
 #include "transformer.cuh"
 
 using namespace mimi;
@@ -78,6 +79,17 @@ struct PlanTC {
   SplitBuf s_a0, s_r1;                                         // mode 2: level 0 on tensor cores too
   SplitBuf s_h1, s_d1, s_r2, s_h2, s_d2, s_r3, s_h3, s_d3, s_r4, s_h4, s_d4, s_y, s_att, s_ffn, s_zp, s_e;
   long long ints;
+  size_t bytes = 0;
+};
+
+// mode 5: one fp32 buffer per activation (front/back zero halo rows where a conv pads)
+struct RawBuf { long long off = 0, item_stride = 0; int front = 0, back = 0, C = 0, level = 0; };
+struct PlanR {
+  int B = 0, K = 0;
+  long long N = 0;
+  int rows[6] = {0, 0, 0, 0, 0, 0};
+  RawBuf h1, d1, r2, h2, d2, r3, h3, d3, r4, h4, d4, z, y, qkv, att, ffn, zp, e, rp;
+  long long ints = 0;
   size_t bytes = 0;
 };
 
@@ -156,6 +168,7 @@ struct mimi_b200 {
   CUtensorMap map_embed_hi, map_embed_lo;
   std::map<MapKey, MapSet> amap_cache;   // activation maps per (workspace, B, N)
   PlanTC last_tc;
+  PlanR last_r;
   bool last_was_tc = false;
 };
 
@@ -336,6 +349,7 @@ static void design_taps(int sr_in, int sr_out, std::vector<float>& taps, int& c,
 }
 
 #include "tc_host.inl"
+#include "tc5_host.inl"
 
 static int utf8_len(unsigned cp) { return cp < 0x80u ? 1 : cp < 0x800u ? 2 : cp < 0x10000u ? 3 : 4; }
 
@@ -384,6 +398,9 @@ int mimi_b200_create(mimi_b200_t** out, int device_ordinal) {
   cudaFuncSetAttribute(tc2::tc2_gemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::Cfg<32>::SMEM);
   cudaFuncSetAttribute(tc2::tc2p_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::CfgP<128>::SMEM);
   cudaFuncSetAttribute(tc2::tc2p_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::CfgP<64>::SMEM);
+  cudaFuncSetAttribute(tc4::tc4_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc4::Cfg<128>::SMEM);
+  cudaFuncSetAttribute(tc4::tc4_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc4::Cfg<64>::SMEM);
+  cudaFuncSetAttribute(tc4::tc4_gemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc4::Cfg<32>::SMEM);
   cudaFuncSetAttribute(tc3::tc3_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc3::Cfg<128>::SMEM);
   cudaFuncSetAttribute(tc3::tc3_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc3::Cfg<64>::SMEM);
   cudaFuncSetAttribute(rvqtc::rvq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, rvqtc::kSmem);
@@ -414,7 +431,7 @@ int mimi_b200_debug_set(mimi_b200_t* h, int key, int value) {
   if (key == 0) h->dbg_layers = std::min(std::max(value, 0), MIMI_B200_NUM_LAYERS);
   else if (key == 1) h->dbg_last_conv = std::min(std::max(value, 0), MIMI_B200_NUM_CONVS - 1);
   else if (key == 2) { h->prof_on = value != 0; h->prof_n = 0; }
-  else if (key == 3) h->mode = std::min(std::max(value, 0), 4);
+  else if (key == 3) h->mode = std::min(std::max(value, 0), 5);
   else if (key == 4) h->exp_single_acc = value != 0;
   else if (key == 5) h->exp_chunk_kb = std::max(value, 0);
   else if (key == 6) h->use_planes = value != 0;
@@ -555,7 +572,7 @@ int mimi_b200_workspace_bytes(mimi_b200_t* h, int B, int64_t N, int K, size_t* o
   // sized for the compute mode in force (debug_set key 3): the fp32 FFMA plan only in mode 0, level-0 buffers only
   // in the unfused tensor-core modes
   const bool simt = h->mode == 0 || h->dbg_last_conv != MIMI_B200_NUM_CONVS - 1;
-  *out_bytes = (simt ? make_plan(B, N, K).bytes : make_plan_tc(B, N, K, h->mode < 3).bytes) + 256;
+  *out_bytes = (simt ? make_plan(B, N, K).bytes : h->mode == 5 ? make_plan_r(B, N, K).bytes : make_plan_tc(B, N, K, h->mode < 3).bytes) + 256;
   return MIMI_B200_OK;
 }
 
@@ -580,16 +597,19 @@ int mimi_b200_encode(mimi_b200_t* h, const float* d_input, int B, int64_t N, con
   const bool use_tc = h->mode >= 1 && h->dbg_last_conv == MIMI_B200_NUM_CONVS - 1;
   const Plan p = make_plan(B, N, K);
   const PlanTC pt = make_plan_tc(B, N, K, h->mode < 3);
-  const size_t need = use_tc ? pt.bytes : p.bytes;
+  const PlanR pr = make_plan_r(B, N, K);
+  const bool use_r5 = use_tc && h->mode == 5;
+  const size_t need = use_r5 ? pr.bytes : use_tc ? pt.bytes : p.bytes;
   // align the workspace base to 256 bytes
   uintptr_t base = (reinterpret_cast<uintptr_t>(d_workspace) + 255) & ~uintptr_t(255);
   if (base + need > reinterpret_cast<uintptr_t>(d_workspace) + workspace_bytes)
     return fail(h, MIMI_B200_ERR_WORKSPACE, "encode: workspace too small, need " + std::to_string(need + 256));
   if (p.rows[4] > kRopeMaxPos) return fail(h, MIMI_B200_ERR_ARG, "encode: more than 16384 25-Hz positions per item");
   float* ws = reinterpret_cast<float*>(base);
-  int* dints = reinterpret_cast<int*>(base + (use_tc ? pt.ints : p.ints));
+  int* dints = reinterpret_cast<int*>(base + (use_r5 ? pr.ints : use_tc ? pt.ints : p.ints));
   h->last = p;
   h->last_tc = pt;
+  h->last_r = pr;
   h->last_was_tc = use_tc;
   h->last_mode = h->mode;
   h->last_ws = ws;
@@ -629,6 +649,11 @@ int mimi_b200_encode(mimi_b200_t* h, const float* d_input, int B, int64_t N, con
     h->launches++; mark(h, 24, st);
   }
 
+  if (use_r5) {
+    int rc5 = encode_tc5(h, d_input, B, N, K, pr, ws, dlen, maxlen, dprefix, total_frames, d_codes, d_latent_opt, st);
+    if (rc5 == MIMI_B200_OK && !h->sync_err.empty()) return fail(h, MIMI_B200_ERR_CUDA, h->sync_err);
+    return rc5;
+  }
   if (use_tc) {
     int rc_tc = encode_tc(h, d_input, B, N, K, pt, ws, dlen, maxlen, dprefix, total_frames, d_codes, d_latent_opt, st);
     if (rc_tc == MIMI_B200_OK && !h->sync_err.empty()) return fail(h, MIMI_B200_ERR_CUDA, h->sync_err);
@@ -768,6 +793,31 @@ int mimi_b200_debug_tap(mimi_b200_t* h, int which, float* d_out, size_t cap, int
   if (!h || !h->last_ws) return fail(h, MIMI_B200_ERR_STATE, "debug_tap: no encode call yet");
   const Plan& p = h->last;
   TapInfo t{};
+  if (h->last_was_tc && h->last_mode == 5) {
+    const PlanR& q = h->last_r;
+    const RawBuf* rb = nullptr;
+    switch (which) {
+      case 3: rb = &q.d1; break;
+      case 6: rb = &q.d2; break;
+      case 9: rb = &q.d3; break;
+      case 13: rb = &q.z; break;
+      case 200: rb = &q.e; break;
+      case 201: rb = &q.rp; break;
+      default:
+        if (which >= 100 && which < 100 + MIMI_B200_NUM_LAYERS) rb = &q.z;
+        else return fail(h, MIMI_B200_ERR_ARG, "debug_tap: tap not materialised in mode 5");
+    }
+    const size_t row_floats = (size_t)q.rows[rb->level] * rb->C;
+    if (rows_per_item) *rows_per_item = q.rows[rb->level];
+    if (channels) *channels = rb->C;
+    if (!d_out) return MIMI_B200_OK;
+    if (cap < row_floats * q.B) return fail(h, MIMI_B200_ERR_ARG, "debug_tap: output too small");
+    CUDA_TRY(h, cudaMemcpy2DAsync(d_out, row_floats * sizeof(float),
+                                  static_cast<float*>(h->last_ws) + rb->off + (long long)rb->front * rb->C,
+                                  (size_t)rb->item_stride * sizeof(float), row_floats * sizeof(float), (size_t)q.B,
+                                  cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+    return MIMI_B200_OK;
+  }
   if (h->last_was_tc) {
     const PlanTC& q = h->last_tc;
     if (h->last_mode >= 3 && which < 3) return fail(h, MIMI_B200_ERR_ARG, "debug_tap: level-0 activations stay on chip in mode 3");

@@ -91,7 +91,7 @@ __device__ __forceinline__ void drain_add(uint32_t taddr, float (&acc)[NCOL]) {
 
 // The epilogue role shared by the k-block-ring kernel (tc2_gemm_kernel) and the plane-staged kernel
 // (tc2p_gemm_kernel): drain every accumulation chunk, add the cross-term accumulator, finish the tile.
-template <int BN, int PC_, int EPIW>
+template <int BN, int PC_, int EPIW, int EW0 = 2>
 __device__ __forceinline__ void epilogue_role(const Epilogue& ep, const Sched& sc, uint8_t* stg_base, uint64_t* acc_full,
                                               uint64_t* acc_empty, uint32_t tmem_base, int nchunks,
                                               int warp, int lane) {
@@ -115,7 +115,7 @@ __device__ __forceinline__ void epilogue_role(const Epilogue& ep, const Sched& s
   };
   {
     // ---- epilogue warps ------------------------------------------------------------------------------------
-    const int ew = warp - 2;
+    const int ew = warp - EW0;                     // EW0 = index of the first epilogue warp (a multiple of 4 or 2)
     const int quarter = warp & 3;                  // TMEM lanes [32*quarter, +32) are the ones this warp may read
     const int half = ew >> 2;                      // which slice of the BN columns
     const int col0 = half * HALF;

@@ -28,9 +28,9 @@ def main():
     taps, margins = {}, []
     codes_o = O.encode(sd, x, 32, taps=taps, margins=margins)
     xd = torch.from_numpy(x).cuda()
-    if "--tc" in sys.argv or "--tc1" in sys.argv or "--tc2" in sys.argv:
+    if any(a.startswith("--tc") for a in sys.argv):
         # tensor-core path: raw taps that exist there (down convs 3/6/9, stream z), then the tail
-        mode = 1 if "--tc1" in sys.argv else 2 if "--tc2" in sys.argv else 4 if "--tc4" in sys.argv else 3
+        mode = 1 if "--tc1" in sys.argv else 2 if "--tc2" in sys.argv else 4 if "--tc4" in sys.argv else 5 if "--tc5" in sys.argv else 3
         m.set_mode(mode)
         m.debug_set(0, 0)
         m.encode(xd, num_quantizers=32)
