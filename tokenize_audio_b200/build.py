@@ -37,7 +37,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libmimi_b200.so (and there is no CPU fallback)")
     tmp = LIB_PATH + ".tmp"
-    cmd = [nvcc, *NVCC_FLAGS, "-o", tmp, os.path.join(CSRC, "mimi_b200.cu")]
+    extra = os.environ.get("MIMI_B200_NVCC_EXTRA", "").split()       # e.g. -DMIMI_TCP_DEBUG for tools/gpu_tcp_hang.py
+    cmd = [nvcc, *NVCC_FLAGS, *extra, "-o", tmp, os.path.join(CSRC, "mimi_b200.cu")]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)

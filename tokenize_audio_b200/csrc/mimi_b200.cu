@@ -25,6 +25,7 @@
 #include "tc_gemm3.cuh"
 #include "rvq_tc.cuh"
 #include "tc_gemm4.cuh"
+#include "tc_gemm5.cuh"
 #include "transformer.cuh"
 
 using namespace mimi;
@@ -160,6 +161,8 @@ struct mimi_b200 {
                                                // fewer L2 bytes but not faster (shared-memory bandwidth binds)
   f0::Consts f0_consts;
   int num_sms = 148;
+  int num_clusters = 74;                       // co-resident CTA pairs of the cta_group::2 GEMM (tc_gemm5.cuh, mode 6)
+  int exp_pair_n128 = 0;                       // pair tiles of 128 instead of 256 columns (debug_set key 9)
   PFN_cuTensorMapEncodeTiled_v12000 encode_tiled = nullptr;
   TcWeight tc_conv[MIMI_B200_NUM_CONVS];       // convs 1..13 (conv 0 is a direct SIMT conv)
   TcWeight tc_qkv[MIMI_B200_NUM_LAYERS], tc_o[MIMI_B200_NUM_LAYERS], tc_fc1[MIMI_B200_NUM_LAYERS], tc_fc2[MIMI_B200_NUM_LAYERS];
@@ -401,6 +404,20 @@ int mimi_b200_create(mimi_b200_t** out, int device_ordinal) {
   cudaFuncSetAttribute(tc4::tc4_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc4::Cfg<128>::SMEM);
   cudaFuncSetAttribute(tc4::tc4_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc4::Cfg<64>::SMEM);
   cudaFuncSetAttribute(tc4::tc4_gemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc4::Cfg<32>::SMEM);
+  cudaFuncSetAttribute(tcp::tcp_gemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcp::Cfg<256>::SMEM);
+  cudaFuncSetAttribute(tcp::tcp_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcp::Cfg<128>::SMEM);
+  {
+    // how many CTA pairs of the widest instance fit at once (one per TPC unless the device says otherwise)
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * (h->num_sms / 2)); cfg.blockDim = dim3(tcp::kThreads); cfg.dynamicSmemBytes = tcp::Cfg<256>::SMEM;
+    cudaLaunchAttribute at{};
+    at.id = cudaLaunchAttributeClusterDimension; at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+    cfg.attrs = &at; cfg.numAttrs = 1;
+    int ncl = 0;
+    if (cudaOccupancyMaxActiveClusters(&ncl, tcp::tcp_gemm_kernel<256>, &cfg) == cudaSuccess && ncl > 0)
+      h->num_clusters = std::min(ncl, h->num_sms / 2);
+    else { cudaGetLastError(); h->num_clusters = h->num_sms / 2; }
+  }
   cudaFuncSetAttribute(tc3::tc3_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc3::Cfg<128>::SMEM);
   cudaFuncSetAttribute(tc3::tc3_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc3::Cfg<64>::SMEM);
   cudaFuncSetAttribute(rvqtc::rvq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, rvqtc::kSmem);
@@ -431,12 +448,13 @@ int mimi_b200_debug_set(mimi_b200_t* h, int key, int value) {
   if (key == 0) h->dbg_layers = std::min(std::max(value, 0), MIMI_B200_NUM_LAYERS);
   else if (key == 1) h->dbg_last_conv = std::min(std::max(value, 0), MIMI_B200_NUM_CONVS - 1);
   else if (key == 2) { h->prof_on = value != 0; h->prof_n = 0; }
-  else if (key == 3) h->mode = std::min(std::max(value, 0), 5);
+  else if (key == 3) h->mode = std::min(std::max(value, 0), 6);
   else if (key == 4) h->exp_single_acc = value != 0;
   else if (key == 5) h->exp_chunk_kb = std::max(value, 0);
   else if (key == 6) h->use_planes = value != 0;
   else if (key == 7) h->exp_prefetch = value != 0;
   else if (key == 8) h->att_variant = value == 2 ? 2 : 3;
+  else if (key == 9) h->exp_pair_n128 = value != 0;
   else return fail(h, MIMI_B200_ERR_ARG, "debug_set: unknown key");
   return MIMI_B200_OK;
 }
@@ -872,7 +890,7 @@ __global__ void debug_split_kernel(const float* __restrict__ x, float* __restric
 int mimi_b200_debug_tc_gemm(mimi_b200_t* h, const float* d_a, const float* h_w, const float* d_bias_opt, int M, int N,
                             int K, int act, float* d_out, void* stream) {
   if (!h || !d_a || !h_w || !d_out) return fail(h, MIMI_B200_ERR_ARG, "debug_tc_gemm: NULL argument");
-  if (M <= 0 || N % 32 || K % 32 || ((h->mode < 2 || h->mode >= 4) && N % 64))
+  if (M <= 0 || N % 32 || K % 32 || ((h->mode < 2 || h->mode == 4) && N % 64))
     return fail(h, MIMI_B200_ERR_ARG, "debug_tc_gemm: need N % 32 == 0 (mode 2) / N % 64 == 0 (mode 1) and K % 32 == 0");
   CUDA_TRY(h, cudaSetDevice(h->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -894,7 +912,9 @@ int mimi_b200_debug_tc_gemm(mimi_b200_t* h, const float* d_a, const float* h_w, 
   ep.bias = d_bias_opt; ep.out_raw = d_out; ep.raw_item_stride = (long long)M * N; ep.act = act;
   ep.uniform_len_in = M; ep.conv_stride = 1; ep.N = N;
   ep.single_acc = h->exp_single_acc; ep.chunk_kb = h->exp_chunk_kb;
-  if (h->mode >= 4) {
+  if (tcp_applies(h, w)) {
+    launch_tcp(h, ma_hi, ma_lo, w, ep, 1, (M + tc::kBM - 1) / tc::kBM, st);
+  } else if (h->mode == 4) {
     CUtensorMap m4[4];
     for (int i = 0; i < 4; ++i)
       if ((rc = tc_make_map4(h, &m4[i], (i & 1) ? lo : hi, K, 1, M, 1, n, 128))) return rc;
@@ -939,6 +959,19 @@ int mimi_b200_debug_shift_probe(mimi_b200_t* h, const float* d_a, const float* h
   if (e != cudaSuccess) return fail(h, MIMI_B200_ERR_CUDA, std::string("debug_shift_probe: ") + cudaGetErrorString(e));
   return MIMI_B200_OK;
 }
+
+#ifdef MIMI_TCP_DEBUG
+// debug builds only: 64 progress marks of the pair GEMM in mapped host memory (readable while a kernel hangs)
+extern "C" unsigned* mimi_b200_debug_marks_init() {
+  unsigned* hp = nullptr;
+  if (cudaHostAlloc((void**)&hp, 64 * sizeof(unsigned), cudaHostAllocMapped) != cudaSuccess) return nullptr;
+  memset(hp, 0, 64 * sizeof(unsigned));
+  unsigned* dp = nullptr;
+  if (cudaHostGetDevicePointer((void**)&dp, hp, 0) != cudaSuccess) return nullptr;
+  if (cudaMemcpyToSymbol(tcp::g_tcp_marks, &dp, sizeof(dp)) != cudaSuccess) return nullptr;
+  return hp;
+}
+#endif
 
 int64_t mimi_b200_resample_out_len(int64_t n_in, int sr_in, int sr_out) {
   if (sr_in <= 0 || sr_out <= 0 || n_in < 0) return -1;

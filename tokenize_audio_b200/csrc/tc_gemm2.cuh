@@ -89,6 +89,99 @@ __device__ __forceinline__ void drain_add(uint32_t taddr, float (&acc)[NCOL]) {
   }
 }
 
+// Epilogue geometry of one thread: HALF accumulator columns, finished in pieces of PC columns that go through a
+// swizzled 32 x PC staging tile of the warp (transpose: thread = row  ->  lane = float4 of a row).
+template <int HALF, int PC>
+struct EpiGeom {
+  static constexpr int NP = HALF / PC;
+  static constexpr int LPR = PC / 4;
+  static constexpr int RPI = 32 / LPR;
+  static constexpr int IT = 32 / RPI;
+};
+
+// pull this thread's residual rows towards L2 while the MMAs run (the loads in finish_tile then miss only L1)
+template <int HALF, int PC>
+__device__ __forceinline__ void prefetch_residual(const Epilogue& ep, int b, int row_base, int ncol0, int Lout, int lane) {
+  using G = EpiGeom<HALF, PC>;
+  const int rr = lane / G::LPR, cj = lane % G::LPR;
+  if (ep.res && cj == 0) {
+    const float* rp = ep.res + (long long)b * ep.raw_item_stride + ncol0;
+#pragma unroll
+    for (int p = 0; p < G::NP; ++p)
+#pragma unroll
+      for (int it = 0; it < G::IT; ++it) {
+        const int row = row_base + it * G::RPI + rr;
+        if (row < Lout) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + (long long)row * ep.N + p * PC));
+      }
+  }
+}
+
+// Finish a tile: thread (lane) holds acc[0, HALF) = columns ncol0 + [0, HALF) of row row_base + lane. Bias / GELU /
+// LayerScale per thread = per row, transpose through the warp's staging tile `stg`, then row-contiguous float4 residual
+// loads and raw / hi / lo stores (128-byte segments).
+template <int HALF, int PC>
+__device__ __forceinline__ void finish_tile(const Epilogue& ep, float (&acc)[HALF], int b, int row_base, int ncol0, int Lout,
+                                            uint32_t stg, int lane) {
+  using G = EpiGeom<HALF, PC>;
+  constexpr int NP = G::NP, LPR = G::LPR, RPI = G::RPI, IT = G::IT;
+  const int rr = lane / LPR;                     // coalesced phase: row within an RPI-row group
+  const int cj = lane % LPR;                     //                  float4 index inside the PC-wide piece
+  const long long raw_base = (long long)b * ep.raw_item_stride + ncol0;
+  const long long split_base = (long long)b * ep.split_item_stride + (long long)ep.split_front * ep.N + ncol0;
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    float4 resv[IT];
+    if (ep.res) {
+#pragma unroll
+      for (int it = 0; it < IT; ++it) {
+        const int row = row_base + it * RPI + rr;
+        resv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < Lout) resv[it] = *reinterpret_cast<const float4*>(ep.res + raw_base + (long long)row * ep.N + p * PC + cj * 4);
+      }
+    }
+    const int wkey = (LPR == 8) ? (lane & 7) : ((lane >> 1) & (LPR - 1));
+#pragma unroll
+    for (int j = 0; j < LPR; ++j) {
+      float4 v = make_float4(acc[p * PC + 4 * j], acc[p * PC + 4 * j + 1], acc[p * PC + 4 * j + 2], acc[p * PC + 4 * j + 3]);
+      const int c = ncol0 + p * PC + 4 * j;
+      if (ep.bias) {
+        const float4 t = ld_nc_f4(ep.bias + c);
+        v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+      }
+      if (ep.act == 1) { v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w); }
+      if (ep.scale) {
+        const float4 t = ld_nc_f4(ep.scale + c);
+        v.x *= t.x; v.y *= t.y; v.z *= t.z; v.w *= t.w;
+      }
+      sts128(stg + (uint32_t)(lane * LPR + (j ^ wkey)) * 16u, v);
+    }
+    __syncwarp();
+    float4 tv[IT];
+#pragma unroll
+    for (int it = 0; it < IT; ++it) {
+      const int r = it * RPI + rr;               // row within this warp's 32
+      const int rkey = (LPR == 8) ? (r & 7) : ((r >> 1) & (LPR - 1));
+      tv[it] = lds128(stg + (uint32_t)(r * LPR + (cj ^ rkey)) * 16u);
+    }
+#pragma unroll
+    for (int it = 0; it < IT; ++it) {
+      const int r = it * RPI + rr;
+      float4 v = tv[it];
+      const int row = row_base + r;
+      if (row < Lout) {
+        const long long o = (long long)row * ep.N + p * PC + cj * 4;
+        if (ep.res) { v.x += resv[it].x; v.y += resv[it].y; v.z += resv[it].z; v.w += resv[it].w; }
+        if (ep.out_raw) *reinterpret_cast<float4*>(ep.out_raw + raw_base + o) = v;
+        if (ep.out_hi) {
+          if (ep.elu_split) { v.x = elu_fast(v.x); v.y = elu_fast(v.y); v.z = elu_fast(v.z); v.w = elu_fast(v.w); }
+          store_split4(ep.out_hi + split_base + o, ep.out_lo + split_base + o, v);
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
 // The epilogue role shared by the k-block-ring kernel (tc2_gemm_kernel) and the plane-staged kernel
 // (tc2p_gemm_kernel): drain every accumulation chunk, add the cross-term accumulator, finish the tile.
 template <int BN, int PC_, int EPIW, int EW0 = 2>
@@ -97,10 +190,6 @@ __device__ __forceinline__ void epilogue_role(const Epilogue& ep, const Sched& s
                                               int warp, int lane) {
   constexpr int HALF = BN / (EPIW / 4);            // columns per epilogue thread
   constexpr int PC = PC_;
-  constexpr int NP = HALF / PC;
-  constexpr int LPR = PC / 4;
-  constexpr int RPI = 32 / LPR;
-  constexpr int IT = 32 / RPI;
   constexpr int STG_WARP = 32 * PC * 4;
   const int vtiles = sc.mt_max * sc.B * sc.ntn;
   auto decode = [&](int id, int& b, int& m0, int& n0, int& Lout) {
@@ -113,103 +202,34 @@ __device__ __forceinline__ void epilogue_role(const Epilogue& ep, const Sched& s
     Lout = (Lin + ep.conv_stride - 1) / ep.conv_stride;
     return m0 < Lout;
   };
-  {
-    // ---- epilogue warps ------------------------------------------------------------------------------------
-    const int ew = warp - EW0;                     // EW0 = index of the first epilogue warp (a multiple of 4 or 2)
-    const int quarter = warp & 3;                  // TMEM lanes [32*quarter, +32) are the ones this warp may read
-    const int half = ew >> 2;                      // which slice of the BN columns
-    const int col0 = half * HALF;
-    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-    const uint32_t stg = tc::smem_u32(stg_base + ew * STG_WARP);         // [32 rows][LPR float4], swizzled
-    const int rr = lane / LPR;                     // coalesced phase: row within an RPI-row group
-    const int cj = lane % LPR;                     //                  float4 index inside the PC-wide piece
-    uint32_t cc = 0;
-    for (int id = blockIdx.x; id < vtiles; id += gridDim.x) {
-      int b, m0, n0, Lout;
-      if (!decode(id, b, m0, n0, Lout)) continue;
-      float acc[HALF];
+  // ---- epilogue warps --------------------------------------------------------------------------------------
+  const int ew = warp - EW0;                     // EW0 = index of the first epilogue warp (a multiple of 4 or 2)
+  const int quarter = warp & 3;                  // TMEM lanes [32*quarter, +32) are the ones this warp may read
+  const int half = ew >> 2;                      // which slice of the BN columns
+  const int col0 = half * HALF;
+  const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+  const uint32_t stg = tc::smem_u32(stg_base + ew * STG_WARP);         // [32 rows][LPR float4], swizzled
+  uint32_t cc = 0;
+  for (int id = blockIdx.x; id < vtiles; id += gridDim.x) {
+    int b, m0, n0, Lout;
+    if (!decode(id, b, m0, n0, Lout)) continue;
+    float acc[HALF];
 #pragma unroll
-      for (int i = 0; i < HALF; ++i) acc[i] = 0.f;
-      if (ep.res && cj == 0) {
-        // pull this tile's residual rows towards L2 while the MMAs run (the loads below then miss only L1)
-        const float* rp = ep.res + (long long)b * ep.raw_item_stride + n0 + col0;
-#pragma unroll
-        for (int p = 0; p < NP; ++p)
-#pragma unroll
-          for (int it = 0; it < IT; ++it) {
-            const int row = m0 + quarter * 32 + it * RPI + rr;
-            if (row < Lout) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + (long long)row * ep.N + p * PC));
-          }
-      }
-      for (int c = 0; c < nchunks; ++c, ++cc) {
-        const uint32_t buf = cc & 1u;
-        tc::mbar_wait(&acc_full[buf], (cc >> 1) & 1u);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // buffer layout per chunk: [main (BN columns) | cross terms (BN columns)], see the MMA issuer
-        drain_add<HALF>(tmem_base + lane_off + buf * (2 * BN) + (uint32_t)col0, acc);
-        drain_add<HALF>(tmem_base + lane_off + buf * (2 * BN) + BN + (uint32_t)col0, acc);
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) tc::mbar_arrive(&acc_empty[buf]);
-      }
-      // ---- finish the tile: rows m0 + 32*quarter + [0,32), columns n0 + col0 + [0,HALF) ---------------------
-      const int row_base = m0 + quarter * 32;
-      const int ncol0 = n0 + col0;
-      const long long raw_base = (long long)b * ep.raw_item_stride + ncol0;
-      const long long split_base = (long long)b * ep.split_item_stride + (long long)ep.split_front * ep.N + ncol0;
-#pragma unroll
-      for (int p = 0; p < NP; ++p) {
-        float4 resv[IT];
-        if (ep.res) {
-#pragma unroll
-          for (int it = 0; it < IT; ++it) {
-            const int row = row_base + it * RPI + rr;
-            resv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (row < Lout) resv[it] = *reinterpret_cast<const float4*>(ep.res + raw_base + (long long)row * ep.N + p * PC + cj * 4);
-          }
-        }
-        const int wkey = (LPR == 8) ? (lane & 7) : ((lane >> 1) & (LPR - 1));
-#pragma unroll
-        for (int j = 0; j < LPR; ++j) {
-          float4 v = make_float4(acc[p * PC + 4 * j], acc[p * PC + 4 * j + 1], acc[p * PC + 4 * j + 2], acc[p * PC + 4 * j + 3]);
-          const int c = ncol0 + p * PC + 4 * j;
-          if (ep.bias) {
-            const float4 t = ld_nc_f4(ep.bias + c);
-            v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
-          }
-          if (ep.act == 1) { v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w); }
-          if (ep.scale) {
-            const float4 t = ld_nc_f4(ep.scale + c);
-            v.x *= t.x; v.y *= t.y; v.z *= t.z; v.w *= t.w;
-          }
-          sts128(stg + (uint32_t)(lane * LPR + (j ^ wkey)) * 16u, v);
-        }
-        __syncwarp();
-        float4 tv[IT];
-#pragma unroll
-        for (int it = 0; it < IT; ++it) {
-          const int r = it * RPI + rr;               // row within this warp's 32
-          const int rkey = (LPR == 8) ? (r & 7) : ((r >> 1) & (LPR - 1));
-          tv[it] = lds128(stg + (uint32_t)(r * LPR + (cj ^ rkey)) * 16u);
-        }
-#pragma unroll
-        for (int it = 0; it < IT; ++it) {
-          const int r = it * RPI + rr;
-          float4 v = tv[it];
-          const int row = row_base + r;
-          if (row < Lout) {
-            const long long o = (long long)row * ep.N + p * PC + cj * 4;
-            if (ep.res) { v.x += resv[it].x; v.y += resv[it].y; v.z += resv[it].z; v.w += resv[it].w; }
-            if (ep.out_raw) *reinterpret_cast<float4*>(ep.out_raw + raw_base + o) = v;
-            if (ep.out_hi) {
-              if (ep.elu_split) { v.x = elu_fast(v.x); v.y = elu_fast(v.y); v.z = elu_fast(v.z); v.w = elu_fast(v.w); }
-              store_split4(ep.out_hi + split_base + o, ep.out_lo + split_base + o, v);
-            }
-          }
-        }
-        __syncwarp();
-      }
+    for (int i = 0; i < HALF; ++i) acc[i] = 0.f;
+    prefetch_residual<HALF, PC>(ep, b, m0 + quarter * 32, n0 + col0, Lout, lane);
+    for (int c = 0; c < nchunks; ++c, ++cc) {
+      const uint32_t buf = cc & 1u;
+      tc::mbar_wait(&acc_full[buf], (cc >> 1) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      // buffer layout per chunk: [main (BN columns) | cross terms (BN columns)], see the MMA issuer
+      drain_add<HALF>(tmem_base + lane_off + buf * (2 * BN) + (uint32_t)col0, acc);
+      drain_add<HALF>(tmem_base + lane_off + buf * (2 * BN) + BN + (uint32_t)col0, acc);
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&acc_empty[buf]);
     }
+    // ---- finish the tile: rows m0 + 32*quarter + [0,32), columns n0 + col0 + [0,HALF) -----------------------
+    finish_tile<HALF, PC>(ep, acc, b, m0 + quarter * 32, n0 + col0, Lout, stg, lane);
   }
 }
 

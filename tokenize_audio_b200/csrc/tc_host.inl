@@ -240,11 +240,26 @@ static void launch_tc2(mimi_b200* h, const CUtensorMap& ahi, const CUtensorMap& 
     tc2::tc2_gemm_kernel<32><<<grid, tc2::threads(32), tc2::Cfg<32>::SMEM, st>>>(ahi, alo, w.map_hi, w.map_lo, w.K, ep, sc);
 }
 
+// fifth-generation kernel: CTA pairs (cta_group::2), pair tiles of 2 x 128 rows x BNP columns
+static bool tcp_applies(const mimi_b200* h, const TcWeight& w) { return h->mode == 6 && w.N % 128 == 0 && w.BN == 128; }
+static void launch_tcp(mimi_b200* h, const CUtensorMap& ahi, const CUtensorMap& alo, const TcWeight& w, const tc::Epilogue& ep,
+                       int B, int mt_max, cudaStream_t st) {
+  const int bnp = (w.N % 256 == 0 && !h->exp_pair_n128) ? 256 : 128;
+  tcp::Sched sc{B, mt_max, w.N / bnp};
+  const long long npairs = (((long long)mt_max * B + 1) / 2) * sc.ntn;
+  const int ncl = (int)std::min<long long>(npairs, h->num_clusters);
+  if (ncl <= 0) return;
+  if (bnp == 256)
+    tcp::tcp_gemm_kernel<256><<<2 * ncl, tcp::kThreads, tcp::Cfg<256>::SMEM, st>>>(ahi, alo, w.map_hi, w.map_lo, w.K, ep, sc);
+  else
+    tcp::tcp_gemm_kernel<128><<<2 * ncl, tcp::kThreads, tcp::Cfg<128>::SMEM, st>>>(ahi, alo, w.map64_hi, w.map64_lo, w.K, ep, sc);
+}
+
 static int tc_gemm(TcCtx& c, int slot, const SplitBuf& a, int k, int s, int pad, const TcWeight& w, const TcOut& o, int prof_id) {
   const CUtensorMap *ahi = nullptr, *alo = nullptr, *m4 = nullptr;
   int rc;
   if (slot < 0 || slot >= kTcSlots) return fail(c.h, MIMI_B200_ERR_ARG, "tc: bad map slot");
-  const bool v3 = c.h->mode >= 4;
+  const bool v3 = c.h->mode == 4;
   const bool planes = !v3 && c.h->mode >= 2 && c.h->use_planes && s > 0 && k % s == 0 && k / s >= 2 && k / s <= 3 &&
                       a.C % 32 == 0 && w.N % 64 == 0;
   if (v3 || planes) { if ((rc = tc_amaps3(c, slot, a, k, s, pad, &m4))) return rc; }
@@ -274,6 +289,8 @@ static int tc_gemm(TcCtx& c, int slot, const SplitBuf& a, int k, int s, int pad,
       tc2::tc2p_gemm_kernel<128><<<grid, tc2::threads(128), tc2::CfgP<128>::SMEM, c.st>>>(m4[2], m4[3], w.map_hi, w.map_lo, ep, sc, gm);
     else
       tc2::tc2p_gemm_kernel<64><<<grid, tc2::threads(64), tc2::CfgP<64>::SMEM, c.st>>>(m4[2], m4[3], w.map_hi, w.map_lo, ep, sc, gm);
+  } else if (tcp_applies(c.h, w)) {
+    launch_tcp(c.h, *ahi, *alo, w, ep, c.B, (lout_max + tc::kBM - 1) / tc::kBM, c.st);
   } else if (c.h->mode >= 2) {
     launch_tc2(c.h, *ahi, *alo, w, ep, c.B, (lout_max + tc::kBM - 1) / tc::kBM, c.st);
   } else {
