@@ -212,6 +212,9 @@ def run_b200(args, rank, world, local_rank):
         model.debug_set(7, args.prefetch)
     if args.att is not None:
         model.debug_set(8, args.att)
+    for kv in args.dbg:
+        k, v = kv.split("=")
+        model.debug_set(int(k), int(v))
     wrapper = MimiEncoder(model, device=str(dev), ragged=True, num_quantizers=K_CODEBOOKS)
     clips, lengths, batches = make_workload(rank)
     peaks = load_peaks()
@@ -361,6 +364,7 @@ def main():
     ap.add_argument("--mode", type=int, default=None, help="debug: kernel generation (see MimiB200Model.set_mode)")
     ap.add_argument("--planes", type=int, default=None, help="debug: plane-staged conv activations on/off")
     ap.add_argument("--att", type=int, default=None, help="debug: attention kernel variant (2 or 3)")
+    ap.add_argument("--dbg", action="append", default=[], help="debug: KEY=VALUE for mimi_b200_debug_set (A/B knobs)")
     ap.add_argument("--prefetch", type=int, default=None, help="debug: next-tile L2 prefetch in the GEMM producer on/off")
     args = ap.parse_args()
     select_workload(args.workload)

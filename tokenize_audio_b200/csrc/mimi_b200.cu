@@ -148,7 +148,9 @@ struct mimi_b200 {
   Plan last;
   void* last_ws = nullptr;
   // tensor-core path
-  int mode = 3;                                // 4 = mode 3 with the experimental third-generation GEMM (tc_gemm3.cuh),
+  int mode = 6;                                // 6 = mode 3 with the CTA-pair GEMM (tc_gemm5.cuh) where N % 128 == 0 (default),
+                                               // 5 = raw fp32 activations split inside the GEMM (tc_gemm4.cuh),
+                                               // 4 = mode 3 with the experimental third-generation GEMM (tc_gemm3.cuh),
                                                // 3 = mode 2 + fused 24 kHz front end (front_fused.cuh),
                                                // 2 = persistent tcgen05 3xTF32 kernel for every GEMM-shaped layer,
                                                // 1 = first-generation tcgen05 kernel (level 0 on FFMA), 0 = all-fp32 SIMT
@@ -161,6 +163,9 @@ struct mimi_b200 {
                                                // fewer L2 bytes but not faster (shared-memory bandwidth binds)
   f0::Consts f0_consts;
   int num_sms = 148;
+  long long item_tiles[6] = {0, 0, 0, 0, 0, 0};   // sum over items of ceil(rows_at_level / 128) for the call in flight
+  int exp_linear_k = 0;                        // debug_set key 11: k-blocks in linear order (no tap grouping)
+  int exp_no_flat = 0;                         // debug_set key 10: never flatten the linears' row dimension across items
   int num_clusters = 74;                       // co-resident CTA pairs of the cta_group::2 GEMM (tc_gemm5.cuh, mode 6)
   int exp_pair_n128 = 0;                       // pair tiles of 128 instead of 256 columns (debug_set key 9)
   PFN_cuTensorMapEncodeTiled_v12000 encode_tiled = nullptr;
@@ -455,6 +460,8 @@ int mimi_b200_debug_set(mimi_b200_t* h, int key, int value) {
   else if (key == 7) h->exp_prefetch = value != 0;
   else if (key == 8) h->att_variant = value == 2 ? 2 : 3;
   else if (key == 9) h->exp_pair_n128 = value != 0;
+  else if (key == 10) h->exp_no_flat = value != 0;
+  else if (key == 11) h->exp_linear_k = value != 0;
   else return fail(h, MIMI_B200_ERR_ARG, "debug_set: unknown key");
   return MIMI_B200_OK;
 }
@@ -640,7 +647,9 @@ int mimi_b200_encode(mimi_b200_t* h, const float* d_input, int B, int64_t N, con
   int maxlen[6];
   for (int l = 0; l < 6; ++l) maxlen[l] = p.rows[l];
   int total_frames = B * p.rows[5];
+  for (int l = 0; l < 6; ++l) h->item_tiles[l] = (long long)B * ((p.rows[l] + 127) / 128);
   if (h_valid_len) {
+    for (int l = 0; l < 6; ++l) h->item_tiles[l] = 0;
     std::vector<int> v((size_t)7 * B + 1);
     int mx[6] = {0, 0, 0, 0, 0, 0};
     int acc = 0;
@@ -651,6 +660,7 @@ int mimi_b200_encode(mimi_b200_t* h, const float* d_input, int B, int64_t N, con
       for (int l = 0; l < 6; ++l) {
         v[(size_t)l * B + b] = (int)L;
         mx[l] = std::max(mx[l], (int)L);
+        h->item_tiles[l] += (L + 127) / 128;
         if (l < 5) L = (L + kLevelStride[l] - 1) / kLevelStride[l];
       }
       v[(size_t)6 * B + b] = acc;

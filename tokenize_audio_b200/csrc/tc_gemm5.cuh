@@ -211,10 +211,11 @@ tcp_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
             if (rank == 0) tc::mbar_expect_tx(&full_bar[s], 2 * STAGE);
             const uint32_t st = smem_u + s * STAGE;
             const uint32_t fb = full_leader + 8u * s;
-            tma_load_3d_pair(st, &tmA_hi, fb, kb * kBK, m0, b);
-            tma_load_3d_pair(st + A_BYTES, &tmA_lo, fb, kb * kBK, m0, b);
-            tma_load_2d_pair(st + 2 * A_BYTES, &tmW_hi, fb, kb * kBK, wrow);
-            tma_load_2d_pair(st + 2 * A_BYTES + W_BYTES, &tmW_lo, fb, kb * kBK, wrow);
+            const int kx = tc2::kblock_order(sc, kb) * kBK;
+            tma_load_3d_pair(st, &tmA_hi, fb, kx, m0, b);
+            tma_load_3d_pair(st + A_BYTES, &tmA_lo, fb, kx, m0, b);
+            tma_load_2d_pair(st + 2 * A_BYTES, &tmW_hi, fb, kx, wrow);
+            tma_load_2d_pair(st + 2 * A_BYTES + W_BYTES, &tmW_lo, fb, kx, wrow);
           }
         }
       }

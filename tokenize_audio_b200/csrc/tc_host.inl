@@ -150,7 +150,7 @@ struct TcCtx {
   std::vector<CUtensorMap>* maps3;  // 4 plane maps per GEMM site (tc_gemm3)
   uint64_t* built3;
 };
-constexpr int kTcSlots = 48;
+constexpr int kTcSlots = 24;          // GEMM sites; slots [kTcSlots, 2*kTcSlots) hold the flattened-rows maps
 }  // namespace
 
 // third-generation kernel: 256-row tiles, plane-staged activations (4 maps per site: hi/lo x first/second box)
@@ -193,15 +193,20 @@ static int tc_amaps3(TcCtx& c, int slot, const SplitBuf& a, int k, int s, int pa
   return MIMI_B200_OK;
 }
 
-// activation maps for a conv/linear that reads SplitBuf `a` with kernel k, stride s, left pad `pad`
-static int tc_amaps(TcCtx& c, int slot, const SplitBuf& a, int k, int s, int pad, const CUtensorMap** hi, const CUtensorMap** lo) {
+// activation maps for a conv/linear that reads SplitBuf `a` with kernel k, stride s, left pad `pad`. `flat`: the
+// items' rows are one contiguous [B * rows][C] matrix (k = 1, no halo) seen as a single item.
+static int tc_amaps(TcCtx& c, int slot, const SplitBuf& a, int k, int s, int pad, bool flat, const CUtensorMap** hi,
+                    const CUtensorMap** lo) {
+  if (flat) slot += kTcSlots;
   CUtensorMap* mh = &(*c.maps)[2 * slot];
   CUtensorMap* ml = mh + 1;
   if (!((*c.built >> slot) & 1ull)) {
     const PlanTC& p = *c.p;
     const int rows_out = (p.rows[a.level] + s - 1) / s;
-    const cuuint64_t dims[3] = {(cuuint64_t)k * a.C, (cuuint64_t)std::max(rows_out, 1), (cuuint64_t)c.B};
-    const cuuint64_t strides[2] = {(cuuint64_t)s * a.C * sizeof(float), (cuuint64_t)a.item_stride * sizeof(float)};
+    const cuuint64_t dims[3] = {(cuuint64_t)k * a.C, (cuuint64_t)std::max(flat ? rows_out * c.B : rows_out, 1),
+                                (cuuint64_t)(flat ? 1 : c.B)};
+    const cuuint64_t strides[2] = {(cuuint64_t)s * a.C * sizeof(float),
+                                   (cuuint64_t)a.item_stride * (flat ? c.B : 1) * sizeof(float)};
     const long long base_off = (long long)(a.front - pad) * a.C;
     if (a.front < pad) return fail(c.h, MIMI_B200_ERR_ARG, "tc: halo smaller than conv padding");
     int rc;
@@ -225,10 +230,18 @@ struct TcOut {
   int act = 0;
 };
 
+// k-block order of a conv with k taps, stride s over C_in channels (tc2::Sched): taps grouped by tau mod s
+static void tc_korder(const mimi_b200* h, tc2::Sched& sc, int k, int s, int cin) {
+  sc.G = 0; sc.s = 0; sc.cp = 0;
+  if (h->exp_linear_k || s <= 1 || k <= s || k % s || cin % 32) return;   // s = 1 (k = 3): taps are 1 row apart, L2 hits anyway
+  sc.G = k / s; sc.s = s; sc.cp = cin / 32;
+}
+
 // persistent second-generation kernel: one CTA per SM over mt_max * B * (N / BN) virtual tiles
 static void launch_tc2(mimi_b200* h, const CUtensorMap& ahi, const CUtensorMap& alo, const TcWeight& w, const tc::Epilogue& ep,
-                       int B, int mt_max, cudaStream_t st) {
+                       int B, int mt_max, cudaStream_t st, int k = 1, int s = 1, int cin = 0) {
   tc2::Sched sc{B, mt_max, w.N / w.BN};
+  tc_korder(h, sc, k, s, cin);
   const long long vt = (long long)mt_max * B * sc.ntn;
   const int grid = (int)std::min<long long>(vt, h->num_sms);
   if (grid <= 0) return;
@@ -243,9 +256,10 @@ static void launch_tc2(mimi_b200* h, const CUtensorMap& ahi, const CUtensorMap& 
 // fifth-generation kernel: CTA pairs (cta_group::2), pair tiles of 2 x 128 rows x BNP columns
 static bool tcp_applies(const mimi_b200* h, const TcWeight& w) { return h->mode == 6 && w.N % 128 == 0 && w.BN == 128; }
 static void launch_tcp(mimi_b200* h, const CUtensorMap& ahi, const CUtensorMap& alo, const TcWeight& w, const tc::Epilogue& ep,
-                       int B, int mt_max, cudaStream_t st) {
+                       int B, int mt_max, cudaStream_t st, int k = 1, int s = 1, int cin = 0) {
   const int bnp = (w.N % 256 == 0 && !h->exp_pair_n128) ? 256 : 128;
   tcp::Sched sc{B, mt_max, w.N / bnp};
+  tc_korder(h, sc, k, s, cin);
   const long long npairs = (((long long)mt_max * B + 1) / 2) * sc.ntn;
   const int ncl = (int)std::min<long long>(npairs, h->num_clusters);
   if (ncl <= 0) return;
@@ -262,8 +276,16 @@ static int tc_gemm(TcCtx& c, int slot, const SplitBuf& a, int k, int s, int pad,
   const bool v3 = c.h->mode == 4;
   const bool planes = !v3 && c.h->mode >= 2 && c.h->use_planes && s > 0 && k % s == 0 && k / s >= 2 && k / s <= 3 &&
                       a.C % 32 == 0 && w.N % 64 == 0;
+  // Linears (k = 1) over buffers without halo rows: the B items are one contiguous [B * rows][C] matrix. When whole
+  // 128-row tiles of that matrix are fewer than the per-item tiles (each item rounds up on its own), run it as ONE item:
+  // rows past an item's length are computed and stored but never read (every consumer is row-wise and length-bound).
+  const int rows_lvl = c.p->rows[a.level];
+  const bool flat = !c.h->exp_no_flat && !v3 && !planes && k == 1 && s == 1 && pad == 0 && a.front == 0 && a.back == 0 &&
+                    c.B > 1 && (!o.raw && !o.res || o.raw_item_stride == (long long)rows_lvl * w.N) &&
+                    (!o.split || (o.split->front == 0 && o.split->back == 0 && o.split->level == a.level)) &&
+                    ((long long)c.B * rows_lvl + 127) / 128 < c.h->item_tiles[a.level];
   if (v3 || planes) { if ((rc = tc_amaps3(c, slot, a, k, s, pad, &m4))) return rc; }
-  else if ((rc = tc_amaps(c, slot, a, k, s, pad, &ahi, &alo))) return rc;
+  else if ((rc = tc_amaps(c, slot, a, k, s, pad, flat, &ahi, &alo))) return rc;
   if (w.K != k * a.C) return fail(c.h, MIMI_B200_ERR_ARG, "tc: weight K mismatch");
   tc::Epilogue ep{};
   ep.bias = o.bias; ep.scale = o.scale; ep.res = o.res; ep.out_raw = o.raw; ep.raw_item_stride = o.raw_item_stride;
@@ -276,25 +298,27 @@ static int tc_gemm(TcCtx& c, int slot, const SplitBuf& a, int k, int s, int pad,
   ep.single_acc = c.h->exp_single_acc; ep.chunk_kb = c.h->exp_chunk_kb;
   ep.prefetch_next = c.h->exp_prefetch && w.N / w.BN == 1;      // with several n-tiles the rows are in L2 already
   ep.len_in = c.dlen[a.level]; ep.uniform_len_in = c.maxlen[a.level]; ep.conv_stride = s; ep.N = w.N;
-  const int lout_max = (c.maxlen[a.level] + s - 1) / s;
+  int lout_max = (c.maxlen[a.level] + s - 1) / s;
   if (lout_max <= 0) return MIMI_B200_OK;
+  int nb = c.B;
+  if (flat) { ep.len_in = nullptr; ep.uniform_len_in = c.B * rows_lvl; lout_max = c.B * rows_lvl; nb = 1; }
   if (v3) {
-    if ((rc = launch_tc3(c.h, m4, w, ep, c.B, lout_max, a.C, k, s, c.st))) return rc;
+    if ((rc = launch_tc3(c.h, m4, w, ep, nb, lout_max, a.C, k, s, c.st))) return rc;
   } else if (planes) {
-    tc2::Sched sc{c.B, (lout_max + tc::kBM - 1) / tc::kBM, w.N / w.BN};
+    tc2::Sched sc{nb, (lout_max + tc::kBM - 1) / tc::kBM, w.N / w.BN};
     tc2::PlaneGeom gm{k / s, s, a.C / 32};
-    const long long vt = (long long)sc.mt_max * c.B * sc.ntn;
+    const long long vt = (long long)sc.mt_max * nb * sc.ntn;
     const int grid = (int)std::min<long long>(vt, c.h->num_sms);
     if (w.BN == 128)
       tc2::tc2p_gemm_kernel<128><<<grid, tc2::threads(128), tc2::CfgP<128>::SMEM, c.st>>>(m4[2], m4[3], w.map_hi, w.map_lo, ep, sc, gm);
     else
       tc2::tc2p_gemm_kernel<64><<<grid, tc2::threads(64), tc2::CfgP<64>::SMEM, c.st>>>(m4[2], m4[3], w.map_hi, w.map_lo, ep, sc, gm);
   } else if (tcp_applies(c.h, w)) {
-    launch_tcp(c.h, *ahi, *alo, w, ep, c.B, (lout_max + tc::kBM - 1) / tc::kBM, c.st);
+    launch_tcp(c.h, *ahi, *alo, w, ep, nb, (lout_max + tc::kBM - 1) / tc::kBM, c.st, k, s, a.C);
   } else if (c.h->mode >= 2) {
-    launch_tc2(c.h, *ahi, *alo, w, ep, c.B, (lout_max + tc::kBM - 1) / tc::kBM, c.st);
+    launch_tc2(c.h, *ahi, *alo, w, ep, nb, (lout_max + tc::kBM - 1) / tc::kBM, c.st, k, s, a.C);
   } else {
-    dim3 grid((lout_max + tc::kBM - 1) / tc::kBM, w.N / w.BN, c.B);
+    dim3 grid((lout_max + tc::kBM - 1) / tc::kBM, w.N / w.BN, nb);
     if (w.BN == 128)
       tc::tc_gemm_kernel<128><<<grid, tc::kThreads, tc::smem_bytes(128), c.st>>>(*ahi, *alo, w.map_hi, w.map_lo, w.K, ep);
     else if (w.BN == 64)
@@ -330,7 +354,7 @@ static int encode_tc(mimi_b200* h, const float* d_input, int B, long long N, int
   if (it == h->amap_cache.end()) {
     if (h->amap_cache.size() >= 64) h->amap_cache.clear();
     it = h->amap_cache.emplace(key, MapSet()).first;
-    it->second.maps.resize(2 * kTcSlots);
+    it->second.maps.resize(4 * kTcSlots);
     it->second.maps3.resize(4 * kTcSlots);
   }
   c.maps = &it->second.maps;

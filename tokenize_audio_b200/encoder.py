@@ -261,11 +261,12 @@ class MimiB200Model:
                      "rvq_input_proj", "rvq_fused", "latent_transpose", "code_fill", "halo_zero", "pad_split",
                      "front_fused"])
 
-    DEFAULT_MODE = 3
+    DEFAULT_MODE = 6
 
     def set_mode(self, tensor_cores) -> None:
-        """True / 3 (default): fused 24 kHz front end + persistent tcgen05 3xTF32 GEMM for every other
-        GEMM-shaped layer; 4: the same with the experimental third-generation GEMM (256-row tiles, plane-staged
+        """True / 6 (default): fused 24 kHz front end + CTA-pair (cta_group::2) tcgen05 3xTF32 GEMM for every layer with
+        N % 128 == 0, the single-CTA persistent kernel for the rest; 3: the single-CTA kernel everywhere; 5: activations
+        stored as raw fp32 and split inside the GEMM; 4: the same with the experimental third-generation GEMM (256-row tiles, plane-staged
         activations, single accumulator); 2: mode 3 without the front-end fusion; 1: the first-generation tcgen05 kernel
         for the wide layers (level 0 on FFMA); False / 0: all-fp32 FFMA."""
         mode = (self.DEFAULT_MODE if tensor_cores else 0) if isinstance(tensor_cores, bool) else int(tensor_cores)
