@@ -1,7 +1,8 @@
 """Every kernel generation of the CUDA path against the oracle and against each other (needs a B200).
 
-mode 0 = all-fp32 FFMA (the exact-fp32 baseline), 2 = persistent tcgen05 3xTF32 GEMM + SIMT RVQ, 3 = default
-(+ fused 24 kHz front end, attention v2, tensor-core RVQ), 4 = experimental third-generation GEMM.
+mode 0 = all-fp32 FFMA (the exact-fp32 baseline), 2 = persistent tcgen05 3xTF32 GEMM + SIMT RVQ + SIMT attention,
+3 = + fused 24 kHz front end, tensor-core attention and RVQ, 4 = experimental third-generation GEMM, 5 = raw fp32
+activations split inside the GEMM, 6 = default: mode 3 with the CTA-pair (cta_group::2) GEMM.
 Tolerances as in test_gpu_parity.py: codes >= 99.9 % identical to the oracle, latent relative L2 <= 2e-5.
 """
 import ctypes as C
@@ -62,6 +63,31 @@ def test_tensor_core_rvq_matches_simt_rvq(b200_model):
     assert a.shape == b.shape == (6, 32, 20)
     assert float((a == b).float().mean()) >= 0.999
     assert torch.equal(a[:, 0], b[:, 0])
+
+
+def test_tensor_core_attention_matches_simt_attention(b200_model):
+    """attention variant 4 (tcgen05, attention_tc.cuh) vs variant 2 (fp32 SIMT, validated against the oracle above) on
+    ragged long-form items: 30 s = 750 positions = 6 query tiles with full 250-key windows, one item ending inside a
+    tile, one shorter than a key chunk. Same GEMMs on both sides, so the latents may differ only by the attention
+    arithmetic (3xTF32 + ex2.approx vs FFMA + expf): relative L2 <= 5e-6, codes >= 99.9 % identical."""
+    lens = [720000, 531777, 100000, 40000]
+    x = np.zeros((4, 1, lens[0]), np.float32)
+    for i, n in enumerate(lens):
+        x[i, 0, :n] = synth.synth_speech(1300 + i, n)
+    xd = torch.from_numpy(x).cuda()
+    res = {}
+    try:
+        for variant in (2, 4):
+            b200_model.debug_set(8, variant)
+            out, lat = b200_model.encode(xd, num_quantizers=32, valid_lengths=lens, return_latent=True)
+            res[variant] = (out.audio_codes.cpu().numpy(), lat.cpu().numpy())
+    finally:
+        b200_model.debug_set(8, 4)
+    for i, n in enumerate(lens):
+        t = -(-n // 1920)
+        a, b = res[2][1][i, :, :t], res[4][1][i, :, :t]
+        assert _rel(b, a) <= 5e-6, f"item {i}: {_rel(b, a):.2e}"
+        assert (res[2][0][i, :, :t] == res[4][0][i, :, :t]).mean() >= 0.999
 
 
 def test_wrapper_sub_batching_is_invisible(b200_model):

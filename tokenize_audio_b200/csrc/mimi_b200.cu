@@ -27,6 +27,7 @@
 #include "tc_gemm4.cuh"
 #include "tc_gemm5.cuh"
 #include "transformer.cuh"
+#include "attention_tc.cuh"
 
 using namespace mimi;
 
@@ -156,8 +157,9 @@ struct mimi_b200 {
                                                // 1 = first-generation tcgen05 kernel (level 0 on FFMA), 0 = all-fp32 SIMT
   int last_mode = 0;
   int exp_single_acc = 0, exp_chunk_kb = 0;    // accuracy experiments (debug_set keys 4, 5)
-  int att_variant = 2;                         // 2 = 8 warps x 4 queries (default), 3 = 16 warps x 2 queries: 12 % slower, the
-                                               // kernel is bound by shared-memory reads per FMA, not by latency (debug_set key 8)
+  int att_variant = 4;                         // 4 = tcgen05 attention (attention_tc.cuh, default in modes >= 3), 2 = SIMT, 8 warps x
+                                               // 4 queries, 3 = SIMT, 16 warps x 2 queries (12 % slower than 2: bound by
+                                               // shared-memory reads per FMA, not by latency) (debug_set key 8)
   int exp_prefetch = 0;                        // L2 prefetch of the next tile's activation boxes (debug_set key 7)
   int use_planes = 0;                          // plane-staged activations for k = G*stride convs (debug_set key 6); off:
                                                // fewer L2 bytes but not faster (shared-memory bandwidth binds)
@@ -423,6 +425,7 @@ int mimi_b200_create(mimi_b200_t** out, int device_ordinal) {
       h->num_clusters = std::min(ncl, h->num_sms / 2);
     else { cudaGetLastError(); h->num_clusters = h->num_sms / 2; }
   }
+  cudaFuncSetAttribute(atc::swa_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, atc::kSmem);
   cudaFuncSetAttribute(tc3::tc3_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc3::Cfg<128>::SMEM);
   cudaFuncSetAttribute(tc3::tc3_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc3::Cfg<64>::SMEM);
   cudaFuncSetAttribute(rvqtc::rvq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, rvqtc::kSmem);
@@ -458,7 +461,7 @@ int mimi_b200_debug_set(mimi_b200_t* h, int key, int value) {
   else if (key == 5) h->exp_chunk_kb = std::max(value, 0);
   else if (key == 6) h->use_planes = value != 0;
   else if (key == 7) h->exp_prefetch = value != 0;
-  else if (key == 8) h->att_variant = value == 2 ? 2 : 3;
+  else if (key == 8) h->att_variant = (value >= 2 && value <= 4) ? value : 2;
   else if (key == 9) h->exp_pair_n128 = value != 0;
   else if (key == 10) h->exp_no_flat = value != 0;
   else if (key == 11) h->exp_linear_k = value != 0;

@@ -451,7 +451,15 @@ static int encode_tc(mimi_b200* h, const float* d_input, int B, long long N, int
     TcOut o;
     o.raw = ws + p.qkv; o.raw_item_stride = rstride(4, 1536);
     if ((rc = tc_gemm(c, 0, p.s_y, 1, 1, 0, h->tc_qkv[l], o, 15))) return rc;
-    if (h->mode >= 2) {
+    if (h->mode >= 3 && h->att_variant == 4) {
+      // tensor-core attention: persistent CTAs over (128-query tile, head, item) units
+      atc::Params ap{};
+      ap.qkv = ws + p.qkv; ap.item_stride = rstride(4, 1536); ap.out_hi = ws + p.s_att.hi; ap.out_lo = ws + p.s_att.lo;
+      ap.out_stride = rstride(4, 512); ap.rope_cos = h->rope_cos; ap.rope_sin = h->rope_sin; ap.len = dlen[4];
+      ap.uniform_len = T25; ap.B = B; ap.mt_max = (T25 + atc::kQT - 1) / atc::kQT;
+      const long long units = (long long)ap.mt_max * B * kHeads;
+      atc::swa_attention_tc_kernel<<<(int)std::min<long long>(units, h->num_sms), atc::kThreads, atc::kSmem, st>>>(ap);
+    } else if (h->mode >= 2) {
       const int ntiles = (T25 + kAttQT - 1) / kAttQT;
       const int nsplit = std::max(1, std::min(ntiles, (4 * h->num_sms + kHeads * B - 1) / (kHeads * B)));
       const int tps = (ntiles + nsplit - 1) / nsplit;

@@ -32,6 +32,10 @@ def main():
         # tensor-core path: raw taps that exist there (down convs 3/6/9, stream z), then the tail
         mode = 1 if "--tc1" in sys.argv else 2 if "--tc2" in sys.argv else 4 if "--tc4" in sys.argv else 5 if "--tc5" in sys.argv else 6 if "--tc6" in sys.argv else 3
         m.set_mode(mode)
+        for a in sys.argv:
+            if a.startswith("--dbg="):          # --dbg=KEY:VALUE
+                k, v = a[6:].split(":")
+                m.debug_set(int(k), int(v))
         m.debug_set(0, 0)
         m.encode(xd, num_quantizers=32)
         torch.cuda.synchronize()
