@@ -120,6 +120,24 @@ int mimi_b200_encode(mimi_b200_t* h, const float* d_input, int B, int64_t N,
                      const int64_t* h_valid_len, int K, int64_t* d_codes, float* d_latent_opt,
                      void* d_workspace, size_t workspace_bytes, void* stream);
 
+/*
+ * The same encode in phases, so that a host that stages its batch group by group (fill pinned memory -> H2D) can start
+ * the GPU on the first group while it is still staging the others. Items are independent only in the 24 kHz front end
+ * (everything after it runs once over the whole batch), so the phases are:
+ *   MIMI_B200_PHASE_BEGIN   lengths to the device, halo rows, zeroed codes (needs no input samples);
+ *   MIMI_B200_PHASE_FRONT   fused front end for items [b0, b1) -- their samples must have landed in d_input;
+ *   MIMI_B200_PHASE_FINISH  the rest of the pipeline for the whole batch.
+ * Every phase takes the arguments of mimi_b200_encode, identical from call to call; BEGIN, FRONT over a partition of
+ * [0, B), FINISH on one stream is exactly mimi_b200_encode. This is what MimiEncoder.encode_audio_batch
+ * (REF/emilia-mimi/process_shard.py:88-140) does with its pinned staging buffer. Needs the default kernel generation.
+ */
+#define MIMI_B200_PHASE_BEGIN 1
+#define MIMI_B200_PHASE_FRONT 2
+#define MIMI_B200_PHASE_FINISH 3
+int mimi_b200_encode_phase(mimi_b200_t* h, int phase, int b0, int b1, const float* d_input, int B, int64_t N,
+                           const int64_t* h_valid_len, int K, int64_t* d_codes, float* d_latent_opt,
+                           void* d_workspace, size_t workspace_bytes, void* stream);
+
 /* Debug/parity taps: copy an internal activation of the LAST encode call into d_out (channels-last
    [B, rows, C] fp32). `which`: 0..13 = output of SEANet conv i (after residual add for block.3 convs),
    100+l = transformer layer l output. Returns rows/C through the out params. */
@@ -183,6 +201,16 @@ int64_t mimi_b200_utf8_bytes_per_frame(int K, uint32_t unicode_offset, int codeb
 int mimi_b200_codes_to_utf8(mimi_b200_t* h, const int64_t* d_codes, int B, int K, int64_t T,
                             const int64_t* h_frames, uint32_t unicode_offset, int codebook_size,
                             uint8_t* d_out, int64_t out_stride, int64_t* h_out_len_opt, void* stream);
+
+/*
+ * Host-side staging helper of the wrapper (no device work): gathers n ragged fp32 clips into the rows of a (pinned)
+ * [n, dst_stride] buffer -- row i = h_src[i][0 .. h_len[i]) followed by zeros up to h_zero_to[i] (<= dst_stride) -- with a
+ * small pool of memcpy threads. This is the right-zero-padding of EncodecFeatureExtractor.__call__
+ * (feature_extraction_encodec.py:81-202) as REF/emilia-mimi/process_shard.py:113-118 uses it, minus the Python loop;
+ * a single core's memcpy (~10 GB/s) would otherwise bound the end-to-end rate.
+ */
+int mimi_b200_host_pack(float* h_dst, int64_t dst_stride, const float* const* h_src, const int64_t* h_len,
+                        const int64_t* h_zero_to, int n, int n_threads);
 
 /* Number of kernels this handle has launched since creation (bench.py reports it as gpu_launches). */
 int64_t mimi_b200_launch_count(const mimi_b200_t* h);

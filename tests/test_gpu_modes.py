@@ -90,16 +90,29 @@ def test_tensor_core_attention_matches_simt_attention(b200_model):
         assert (res[2][0][i, :, :t] == res[4][0][i, :, :t]).mean() >= 0.999
 
 
-def test_wrapper_sub_batching_is_invisible(b200_model):
-    """The pipelined sub-batches of encode_audio_batch (ragged mode) return exactly what one big batch returns."""
+def test_wrapper_staging_schedules_are_invisible(b200_model):
+    """encode_audio_batch (ragged mode) returns the same codes whether the batch is staged group by group under the
+    running front end (mimi_b200_encode_phase, any group sizes), as independent sub-batches, or in one plain call."""
     from tokenize_audio_b200.encoder import MimiEncoder
     rng = np.random.default_rng(7)
     clips = [synth.synth_speech(1000 + i, int(n)) for i, n in enumerate(rng.integers(3000, 60000, size=21))]
-    one = MimiEncoder(b200_model, num_quantizers=8, chunk_items=64).encode_audio_batch(clips)
-    many = MimiEncoder(b200_model, num_quantizers=8, chunk_items=4).encode_audio_batch(clips)
-    assert len(one) == len(many) == 21
-    for a, b, c in zip(one, many, clips):
-        assert a.shape == (8, -(-len(c) // 1920)) and np.array_equal(a, b)
+    n = max(len(c) for c in clips)
+    x = np.zeros((21, 1, n), np.float32)
+    for i, c in enumerate(clips):
+        x[i, 0, : len(c)] = c
+    plain = b200_model.encode(torch.from_numpy(x).cuda(), num_quantizers=8, valid_lengths=[len(c) for c in clips]).audio_codes.cpu().numpy()
+    results = []
+    for first in (1, 4, 64):
+        results.append(MimiEncoder(b200_model, num_quantizers=8, first_items=first).encode_audio_batch(clips))
+    for chunk in (64, 4):
+        w = MimiEncoder(b200_model, num_quantizers=8, chunk_items=chunk)
+        w.phased = False
+        results.append(w.encode_audio_batch(clips))
+    for res in results:
+        assert len(res) == 21
+        for i, (a, c) in enumerate(zip(res, clips)):
+            t = -(-len(c) // 1920)
+            assert a.shape == (8, t) and np.array_equal(a, plain[i, :, :t])
 
 
 def test_config5_codes_to_unicode_after_encode(b200_model):

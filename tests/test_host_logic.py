@@ -68,3 +68,39 @@ def test_sub_batch_schedule_covers_every_item_once():
             assert all(len(p) > 0 for p in parts)
             assert len(parts) <= 3 or chunk < B // 4        # a small head, then at most two big launches
     assert [len(p) for p in MimiEncoder._sub_batches(64, 16)] == [8, 28, 28]
+
+
+def test_front_groups_partition_the_batch_in_order():
+    from tokenize_audio_b200.encoder import MimiEncoder
+    for B in (1, 2, 3, 8, 9, 64, 100, 257):
+        for first in (1, 4, 8, 1000):
+            parts = MimiEncoder._front_groups(B, first)
+            assert [i for p in parts for i in p] == list(range(B))
+            assert all(len(p) > 0 for p in parts)
+            assert all(len(b) <= 2 * len(a) for a, b in zip(parts[:-1], parts[1:]))
+    assert [len(p) for p in MimiEncoder._front_groups(64, 8)] == [8, 16, 32, 8]
+
+
+def test_host_pack_gathers_and_zero_pads():
+    """mimi_b200_host_pack (host-only entry point of the C-ABI): ragged clips -> rows of the staging buffer, zeros up to
+    zero_to[i], nothing written beyond; any thread count gives the same bytes."""
+    import ctypes as C
+    import torch
+    from tokenize_audio_b200 import _lib
+    lib = _lib.load_library()
+    rng = np.random.default_rng(3)
+    arrs = [rng.standard_normal(int(n)).astype(np.float32) for n in (0, 1, 1919, 1920, 1921, 300000, 77777, 262144, 262145)]
+    B, N = len(arrs), max(a.shape[0] for a in arrs)
+    zto = [min(N, -(-a.shape[0] // 1920) * 1920) for a in arrs]
+    src = (C.c_void_p * B)(*[a.ctypes.data for a in arrs])
+    lens = (C.c_int64 * B)(*[a.shape[0] for a in arrs])
+    z = (C.c_int64 * B)(*zto)
+    for threads in (1, 3, 8):
+        buf = torch.full((B, 1, N), 7.0)
+        assert lib.mimi_b200_host_pack(buf.data_ptr(), buf.stride(0), src, lens, z, B, threads) == 0
+        for i, a in enumerate(arrs):
+            n = a.shape[0]
+            assert np.array_equal(buf[i, 0, :n].numpy(), a)
+            assert bool((buf[i, 0, n:zto[i]] == 0).all()) and bool((buf[i, 0, zto[i]:] == 7).all())
+    bad = (C.c_int64 * B)(*[N + 1] * B)
+    assert lib.mimi_b200_host_pack(buf.data_ptr(), buf.stride(0), src, bad, z, B, 2) != 0

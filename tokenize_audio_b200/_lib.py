@@ -33,6 +33,8 @@ class Weights(C.Structure):
     ]
 
 
+PHASE_BEGIN, PHASE_FRONT, PHASE_FINISH = 1, 2, 3      # MIMI_B200_PHASE_* (include/mimi_b200.h)
+
 # every symbol include/mimi_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "mimi_b200_abi_version": (C.c_int, []),
@@ -44,6 +46,9 @@ SYMBOLS = {
     "mimi_b200_workspace_bytes": (C.c_int, [c_void_p, C.c_int, C.c_int64, C.c_int, C.POINTER(C.c_size_t)]),
     "mimi_b200_encode": (C.c_int, [c_void_p, c_void_p, C.c_int, C.c_int64, c_void_p, C.c_int, c_void_p,
                                    c_void_p, c_void_p, C.c_size_t, c_void_p]),
+    "mimi_b200_encode_phase": (C.c_int, [c_void_p, C.c_int, C.c_int, C.c_int, c_void_p, C.c_int, C.c_int64, c_void_p, C.c_int,
+                                         c_void_p, c_void_p, c_void_p, C.c_size_t, c_void_p]),
+    "mimi_b200_host_pack": (C.c_int, [c_void_p, C.c_int64, c_void_p, c_void_p, c_void_p, C.c_int, C.c_int]),
     "mimi_b200_debug_tap": (C.c_int, [c_void_p, C.c_int, c_void_p, C.c_size_t, C.POINTER(C.c_int64),
                                       C.POINTER(C.c_int), c_void_p]),
     "mimi_b200_debug_set": (C.c_int, [c_void_p, C.c_int, C.c_int]),

@@ -11,7 +11,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
 #include <map>
+#include <memory>
+#include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -166,6 +170,8 @@ struct mimi_b200 {
   f0::Consts f0_consts;
   int num_sms = 148;
   long long item_tiles[6] = {0, 0, 0, 0, 0, 0};   // sum over items of ceil(rows_at_level / 128) for the call in flight
+  int phase = 0, front_b0 = 0, front_b1 = 0;   // mimi_b200_encode_phase: which part of the pipeline the call in flight runs
+  int exp_raw_h1 = 0;                          // debug_set key 12: h1 crosses HBM as raw fp32 (front_fused raw_out + tc_gemm4 for D1)
   int exp_linear_k = 0;                        // debug_set key 11: k-blocks in linear order (no tap grouping)
   int exp_no_flat = 0;                         // debug_set key 10: never flatten the linears' row dimension across items
   int num_clusters = 74;                       // co-resident CTA pairs of the cta_group::2 GEMM (tc_gemm5.cuh, mode 6)
@@ -465,6 +471,7 @@ int mimi_b200_debug_set(mimi_b200_t* h, int key, int value) {
   else if (key == 9) h->exp_pair_n128 = value != 0;
   else if (key == 10) h->exp_no_flat = value != 0;
   else if (key == 11) h->exp_linear_k = value != 0;
+  else if (key == 12) h->exp_raw_h1 = value != 0;
   else return fail(h, MIMI_B200_ERR_ARG, "debug_set: unknown key");
   return MIMI_B200_OK;
 }
@@ -604,8 +611,32 @@ int mimi_b200_workspace_bytes(mimi_b200_t* h, int B, int64_t N, int K, size_t* o
   return MIMI_B200_OK;
 }
 
+static int encode_impl(mimi_b200_t* h, const float* d_input, int B, int64_t N, const int64_t* h_valid_len, int K,
+                       int64_t* d_codes, float* d_latent_opt, void* d_workspace, size_t workspace_bytes, void* stream);
+
 int mimi_b200_encode(mimi_b200_t* h, const float* d_input, int B, int64_t N, const int64_t* h_valid_len, int K,
                      int64_t* d_codes, float* d_latent_opt, void* d_workspace, size_t workspace_bytes, void* stream) {
+  if (!h) return MIMI_B200_ERR_ARG;
+  h->phase = 0; h->front_b0 = 0; h->front_b1 = B;
+  return encode_impl(h, d_input, B, N, h_valid_len, K, d_codes, d_latent_opt, d_workspace, workspace_bytes, stream);
+}
+
+int mimi_b200_encode_phase(mimi_b200_t* h, int phase, int b0, int b1, const float* d_input, int B, int64_t N,
+                           const int64_t* h_valid_len, int K, int64_t* d_codes, float* d_latent_opt, void* d_workspace,
+                           size_t workspace_bytes, void* stream) {
+  if (!h) return MIMI_B200_ERR_ARG;
+  if (phase < MIMI_B200_PHASE_BEGIN || phase > MIMI_B200_PHASE_FINISH) return fail(h, MIMI_B200_ERR_ARG, "encode_phase: bad phase");
+  if (h->mode < 3 || h->mode == 5 || h->dbg_last_conv != MIMI_B200_NUM_CONVS - 1)
+    return fail(h, MIMI_B200_ERR_STATE, "encode_phase: needs the fused front end (modes 3, 4, 6)");
+  if (phase == MIMI_B200_PHASE_FRONT && (b0 < 0 || b1 > B || b0 > b1)) return fail(h, MIMI_B200_ERR_ARG, "encode_phase: bad item range");
+  h->phase = phase; h->front_b0 = b0; h->front_b1 = b1;
+  const int rc = encode_impl(h, d_input, B, N, h_valid_len, K, d_codes, d_latent_opt, d_workspace, workspace_bytes, stream);
+  h->phase = 0;
+  return rc;
+}
+
+static int encode_impl(mimi_b200_t* h, const float* d_input, int B, int64_t N, const int64_t* h_valid_len, int K,
+                       int64_t* d_codes, float* d_latent_opt, void* d_workspace, size_t workspace_bytes, void* stream) {
   if (!h) return MIMI_B200_ERR_ARG;
   if (!h->loaded) return fail(h, MIMI_B200_ERR_STATE, "encode: weights not loaded");
   if (K > MIMI_B200_MAX_QUANTIZERS)
@@ -671,13 +702,17 @@ int mimi_b200_encode(mimi_b200_t* h, const float* d_input, int B, int64_t N, con
     }
     v[(size_t)7 * B] = acc;
     total_frames = acc;
-    int rc = stage_ints(h, v, dints, st);
-    if (rc) return rc;
+    if (h->phase <= MIMI_B200_PHASE_BEGIN) {       // the later phases of a phased call find the lengths in the workspace
+      int rc = stage_ints(h, v, dints, st);
+      if (rc) return rc;
+    }
     for (int l = 0; l < 6; ++l) { dlen[l] = dints + (size_t)l * B; maxlen[l] = mx[l]; }
     dprefix = dints + (size_t)6 * B;
-    const long long ncodes = (long long)B * K * p.rows[5];
-    fill_codes_zero_kernel<<<(unsigned)((ncodes + 255) / 256), 256, 0, st>>>(reinterpret_cast<long long*>(d_codes), ncodes);
-    h->launches++; mark(h, 24, st);
+    if (h->phase <= MIMI_B200_PHASE_BEGIN) {
+      const long long ncodes = (long long)B * K * p.rows[5];
+      fill_codes_zero_kernel<<<(unsigned)((ncodes + 255) / 256), 256, 0, st>>>(reinterpret_cast<long long*>(d_codes), ncodes);
+      h->launches++; mark(h, 24, st);
+    }
   }
 
   if (use_r5) {
@@ -985,6 +1020,98 @@ extern "C" unsigned* mimi_b200_debug_marks_init() {
   return hp;
 }
 #endif
+
+// ---- host staging: a tiny persistent pool of memcpy threads --------------------------------------------------------------
+namespace {
+struct PackJob { float* dst; const float* src; size_t copy_floats, zero_floats; };
+class PackPool {
+ public:
+  explicit PackPool(int n) {
+    for (int i = 0; i < n; ++i) workers_.emplace_back([this] { loop(); });
+  }
+  ~PackPool() {
+    { std::lock_guard<std::mutex> g(m_); stop_ = true; }
+    cv_.notify_all();
+    for (auto& t : workers_) t.join();
+  }
+  int size() const { return (int)workers_.size(); }
+  // runs the jobs on the workers and the calling thread; returns when all are done
+  void run(std::vector<PackJob>& jobs) {
+    {
+      std::lock_guard<std::mutex> g(m_);
+      jobs_ = &jobs; next_ = 0; pending_ = jobs.size(); ++epoch_;
+    }
+    cv_.notify_all();
+    work();
+    std::unique_lock<std::mutex> g(m_);
+    done_.wait(g, [this] { return pending_ == 0; });
+    jobs_ = nullptr;
+  }
+
+ private:
+  static void exec(const PackJob& j) {
+    if (j.copy_floats) memcpy(j.dst, j.src, j.copy_floats * sizeof(float));
+    if (j.zero_floats) memset(j.dst + j.copy_floats, 0, j.zero_floats * sizeof(float));
+  }
+  void work() {
+    for (;;) {
+      PackJob j;
+      {
+        std::lock_guard<std::mutex> g(m_);
+        if (!jobs_ || next_ >= jobs_->size()) return;
+        j = (*jobs_)[next_++];
+      }
+      exec(j);
+      std::lock_guard<std::mutex> g(m_);
+      if (--pending_ == 0) done_.notify_all();
+    }
+  }
+  void loop() {
+    uint64_t seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> g(m_);
+        cv_.wait(g, [&] { return stop_ || epoch_ != seen; });
+        if (stop_) return;
+        seen = epoch_;
+      }
+      work();
+    }
+  }
+  std::vector<std::thread> workers_;
+  std::mutex m_;
+  std::condition_variable cv_, done_;
+  std::vector<PackJob>* jobs_ = nullptr;
+  size_t next_ = 0, pending_ = 0;
+  uint64_t epoch_ = 0;
+  bool stop_ = false;
+};
+std::mutex g_pack_mutex;
+std::unique_ptr<PackPool> g_pack_pool;
+}  // namespace
+
+int mimi_b200_host_pack(float* h_dst, int64_t dst_stride, const float* const* h_src, const int64_t* h_len,
+                        const int64_t* h_zero_to, int n, int n_threads) {
+  if (n < 0 || (n > 0 && (!h_dst || !h_src || !h_len || !h_zero_to))) return MIMI_B200_ERR_ARG;
+  constexpr size_t kPiece = 1 << 18;                       // 1 MB pieces: a long clip is shared by several threads
+  std::vector<PackJob> jobs;
+  for (int i = 0; i < n; ++i) {
+    if (h_len[i] < 0 || h_len[i] > dst_stride || h_zero_to[i] > dst_stride || (h_len[i] > 0 && !h_src[i])) return MIMI_B200_ERR_ARG;
+    float* row = h_dst + (size_t)i * dst_stride;
+    const size_t len = (size_t)h_len[i], end = (size_t)std::max<int64_t>(h_len[i], h_zero_to[i]);
+    for (size_t o = 0; o < end; o += kPiece) {
+      const size_t hi = std::min(end, o + kPiece);
+      const size_t c = o < len ? std::min(len, hi) - o : 0;
+      jobs.push_back({row + o, h_src[i] ? h_src[i] + o : nullptr, c, hi - o - c});
+    }
+  }
+  if (jobs.empty()) return MIMI_B200_OK;
+  std::lock_guard<std::mutex> g(g_pack_mutex);            // one pack at a time per process
+  const int want = std::max(1, std::min(n_threads, 16)) - 1;           // the caller is a worker too
+  if (!g_pack_pool || g_pack_pool->size() != want) g_pack_pool.reset(new PackPool(want));
+  g_pack_pool->run(jobs);
+  return MIMI_B200_OK;
+}
 
 int64_t mimi_b200_resample_out_len(int64_t n_in, int sr_in, int sr_out) {
   if (sr_in <= 0 || sr_out <= 0 || n_in < 0) return -1;

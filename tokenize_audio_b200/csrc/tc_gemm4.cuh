@@ -114,9 +114,10 @@ tc4_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             tc::mbar_wait(&empty_bar[s], ((kbc / STAGES) & 1u) ^ 1u);
             uint8_t* st = smem + s * STAGE;
             tc::mbar_expect_tx(&raw_full[s], C::LOAD_BYTES);
-            tc::tma_load_3d(st, &tmA, &raw_full[s], kb * kBK, m0, b);
-            tc::tma_load_2d(st + 2 * A_BYTES, &tmW_hi, &raw_full[s], kb * kBK, n0);
-            tc::tma_load_2d(st + 2 * A_BYTES + W_BYTES, &tmW_lo, &raw_full[s], kb * kBK, n0);
+            const int kx = tc2::kblock_order(sc, kb) * kBK;
+            tc::tma_load_3d(st, &tmA, &raw_full[s], kx, m0, b);
+            tc::tma_load_2d(st + 2 * A_BYTES, &tmW_hi, &raw_full[s], kx, n0);
+            tc::tma_load_2d(st + 2 * A_BYTES + W_BYTES, &tmW_lo, &raw_full[s], kx, n0);
           }
         }
       }

@@ -228,6 +228,8 @@ struct TcOut {
   const float* bias = nullptr;
   const float* scale = nullptr;
   int act = 0;
+  int raw_in = 0;                  // 1: the input buffer's `hi` array holds RAW fp32 (pre-ELU); the GEMM applies ELU and the
+                                   // hi/lo split itself in shared memory (tc_gemm4.cuh) -- half the HBM bytes on that edge
 };
 
 // k-block order of a conv with k taps, stride s over C_in channels (tc2::Sched): taps grouped by tau mod s
@@ -302,7 +304,19 @@ static int tc_gemm(TcCtx& c, int slot, const SplitBuf& a, int k, int s, int pad,
   if (lout_max <= 0) return MIMI_B200_OK;
   int nb = c.B;
   if (flat) { ep.len_in = nullptr; ep.uniform_len_in = c.B * rows_lvl; lout_max = c.B * rows_lvl; nb = 1; }
-  if (v3) {
+  if (o.raw_in) {
+    if (flat || planes || v3) return fail(c.h, MIMI_B200_ERR_ARG, "tc: raw input only for the k-block ring kernels");
+    tc2::Sched sc{nb, (lout_max + tc::kBM - 1) / tc::kBM, w.N / w.BN};
+    tc_korder(c.h, sc, k, s, a.C);
+    const long long vt = (long long)sc.mt_max * nb * sc.ntn;
+    const int grid = (int)std::min<long long>(vt, c.h->num_sms);
+    if (w.BN == 128)
+      tc4::tc4_gemm_kernel<128><<<grid, tc4::kThreads, tc4::Cfg<128>::SMEM, c.st>>>(*ahi, w.map_hi, w.map_lo, w.K, 1, ep, sc);
+    else if (w.BN == 64)
+      tc4::tc4_gemm_kernel<64><<<grid, tc4::kThreads, tc4::Cfg<64>::SMEM, c.st>>>(*ahi, w.map_hi, w.map_lo, w.K, 1, ep, sc);
+    else
+      tc4::tc4_gemm_kernel<32><<<grid, tc4::kThreads, tc4::Cfg<32>::SMEM, c.st>>>(*ahi, w.map_hi, w.map_lo, w.K, 1, ep, sc);
+  } else if (v3) {
     if ((rc = launch_tc3(c.h, m4, w, ep, nb, lout_max, a.C, k, s, c.st))) return rc;
   } else if (planes) {
     tc2::Sched sc{nb, (lout_max + tc::kBM - 1) / tc::kBM, w.N / w.BN};
@@ -365,19 +379,33 @@ static int encode_tc(mimi_b200* h, const float* d_input, int B, long long N, int
 
   // halo rows of every conv-consumed split buffer (producers only ever write rows [0, L))
   const SplitBuf* halos[] = {&p.s_h1, &p.s_d1, &p.s_h2, &p.s_d2, &p.s_h3, &p.s_d3, &p.s_h4, &p.s_d4};
-  for (const SplitBuf* s : halos)
-    if ((rc = tc_zero_halo(c, *s))) return rc;
-  if (h->mode == 2 && (rc = tc_zero_halo(c, p.s_a0))) return rc;
+  if (h->phase <= MIMI_B200_PHASE_BEGIN) {
+    for (const SplitBuf* s : halos)
+      if ((rc = tc_zero_halo(c, *s))) return rc;
+    if (h->mode == 2 && (rc = tc_zero_halo(c, p.s_a0))) return rc;
+  }
+  if (h->phase == MIMI_B200_PHASE_BEGIN) return MIMI_B200_OK;
 
+  // the 24 kHz activation h1 (64 channels, the largest tensor of the pipeline) crosses HBM once as raw fp32 instead of as
+  // an ELU'd hi/lo pair: the front end stores it raw, the first strided conv splits it in shared memory (tc_gemm4.cuh)
+  const int raw_h1 = h->mode >= 3 && h->mode != 4 && h->exp_raw_h1;
   // ---- level 0 on CUDA cores: L0 (1->64 k7), R1a (64->32 k3), R1b (32->64 k1 + skip) ---------------------
-  if (h->mode >= 3) {
-    // fused front end: waveform -> L0 -> R1a -> R1b (+skip) -> ELU -> split, 24 kHz activations stay on chip
-    if (maxlen[0] > 0) {
+  if (h->mode >= 3 && h->phase == MIMI_B200_PHASE_FINISH) {
+    // phased call: the front end already ran, item group by item group (mimi_b200_encode_phase)
+  } else if (h->mode >= 3) {
+    // fused front end: waveform -> L0 -> R1a -> R1b (+skip) -> ELU -> split, 24 kHz activations stay on chip.
+    // Items [b0, b1) only in a phased call (every item is independent here).
+    const int b0 = h->phase == MIMI_B200_PHASE_FRONT ? h->front_b0 : 0;
+    const int nb = (h->phase == MIMI_B200_PHASE_FRONT ? h->front_b1 : B) - b0;
+    if (maxlen[0] > 0 && nb > 0) {
       f0::Params fp{};
-      fp.x = d_input; fp.x_stride = N; fp.len = dlen[0]; fp.uniform_len = maxlen[0]; fp.B = B;
+      fp.x = d_input + (long long)b0 * N; fp.x_stride = N; fp.len = dlen[0] ? dlen[0] + b0 : nullptr; fp.uniform_len = maxlen[0];
+      fp.B = nb;
       fp.mt_max = (maxlen[0] + f0::kAdv - 1) / f0::kAdv;
-      fp.out_hi = ws + p.s_h1.hi; fp.out_lo = ws + p.s_h1.lo; fp.split_item_stride = p.s_h1.item_stride; fp.split_front = p.s_h1.front;
-      const long long vt = (long long)fp.mt_max * B;
+      fp.out_hi = ws + p.s_h1.hi + (long long)b0 * p.s_h1.item_stride; fp.out_lo = ws + p.s_h1.lo + (long long)b0 * p.s_h1.item_stride;
+      fp.split_item_stride = p.s_h1.item_stride; fp.split_front = p.s_h1.front;
+      fp.raw_out = raw_h1;
+      const long long vt = (long long)fp.mt_max * nb;
       const int grid = (int)std::min<long long>(vt, h->num_sms);
       f0::front_fused_kernel<<<grid, f0::kThreads, f0::kSmem, st>>>(h->tc_conv[1].map_hi, h->tc_conv[1].map_lo, h->tc_conv[2].map_hi,
                                                                     h->tc_conv[2].map_lo, h->f0_consts, fp);
@@ -392,6 +420,7 @@ static int encode_tc(mimi_b200* h, const float* d_input, int B, long long N, int
     h->launches++; mark(h, 0, st);
     CUDA_TRY(h, cudaGetLastError());
   }
+  if (h->phase == MIMI_B200_PHASE_FRONT) return MIMI_B200_OK;
   if (h->mode >= 3) {
   } else if (h->mode == 2) {
     TcOut o;   // R1a: ELU -> 64 -> 32, k3 (ELU was applied by conv0's split store)
@@ -425,6 +454,7 @@ static int encode_tc(mimi_b200* h, const float* d_input, int B, long long N, int
     const ConvGeom& gd = kConv[id];
     TcOut o;   // down conv: raw (skip) + ELU'd split (resblock conv a)
     o.raw = ws + L.d_raw; o.raw_item_stride = rstride(s + 1, L.C); o.split = L.s_d; o.elu_split = 1; o.bias = h->conv_b[id];
+    o.raw_in = (s == 0) ? raw_h1 : 0;
     if ((rc = tc_gemm(c, id, *L.in, gd.k, gd.stride, gd.k - gd.stride, h->tc_conv[id], o, id))) return rc;
     o = TcOut{};   // resblock conv a: C -> C/2, k3
     o.split = L.s_r; o.elu_split = 1; o.bias = h->conv_b[ia];

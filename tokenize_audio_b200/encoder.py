@@ -15,6 +15,7 @@ nothing in this module falls back to the CPU.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import threading
 from typing import Dict, List, Optional, Sequence, Union
 
@@ -66,6 +67,7 @@ class MimiB200Model:
         self._lib = _lib.load_library()
         self._lock = threading.Lock()
         self._workspace: Optional[torch.Tensor] = None
+        self._mode = self.DEFAULT_MODE
         self.ragged_from_mask = False     # True: use padding_mask row sums as valid lengths (ragged mode)
         h = C.c_void_p()
         rc = self._lib.mimi_b200_create(C.byref(h), self.device.index)
@@ -183,10 +185,15 @@ class MimiB200Model:
     def encode(self, input_values: torch.Tensor, padding_mask: Optional[torch.Tensor] = None,
                num_quantizers: Optional[float] = None, encoder_past_key_values=None, padding_cache=None,
                use_streaming: Optional[bool] = None, return_dict: Optional[bool] = None,
-               valid_lengths: Optional[Sequence[int]] = None, return_latent: bool = False):
+               valid_lengths: Optional[Sequence[int]] = None, return_latent: bool = False,
+               staged_groups=None):
         """Same contract as ``MimiModel.encode``. Extras (keyword-only in spirit): ``valid_lengths`` switches
         on ragged mode (skip work past each item's last kept frame), ``return_latent`` also returns the
-        pre-quantisation latent ``[B,512,T]`` for parity checks."""
+        pre-quantisation latent ``[B,512,T]`` for parity checks. ``staged_groups`` = iterable of ``(b0, b1, land)``
+        partitioning ``[0, B)`` in order: ``input_values`` is a device buffer still being filled, and ``land()`` is
+        called right before the front end of items ``[b0, b1)`` is launched -- it stages those items (fill, H2D, make the
+        current stream wait for the copy). The GPU then works on the first groups while the host stages the later
+        ones (``mimi_b200_encode_phase``); the result is that of a plain call on the complete buffer."""
         if encoder_past_key_values is not None or padding_cache is not None or use_streaming:
             raise NotImplementedError("streaming / cache arguments are not supported (the reference scripts never pass them)")
         K = NUM_QUANTIZERS if num_quantizers is None else num_quantizers
@@ -229,10 +236,27 @@ class MimiB200Model:
                 _lib.check(self._lib, self._h, rc, "mimi_b200_workspace_bytes")
                 ws = self._ws(nbytes.value)
                 stream = torch.cuda.current_stream(self.device).cuda_stream
-                rc = self._lib.mimi_b200_encode(
-                    self._h, x.data_ptr(), B, N, vl, K, codes.data_ptr(),
-                    latent.data_ptr() if latent is not None else None, ws.data_ptr(), ws.numel(), stream)
-                _lib.check(self._lib, self._h, rc, "mimi_b200_encode")
+                lat_ptr = latent.data_ptr() if latent is not None else None
+                if staged_groups is None:
+                    rc = self._lib.mimi_b200_encode(self._h, x.data_ptr(), B, N, vl, K, codes.data_ptr(), lat_ptr,
+                                                    ws.data_ptr(), ws.numel(), stream)
+                    _lib.check(self._lib, self._h, rc, "mimi_b200_encode")
+                else:
+                    def phase(ph, b0, b1):
+                        rc = self._lib.mimi_b200_encode_phase(self._h, ph, b0, b1, x.data_ptr(), B, N, vl, K, codes.data_ptr(),
+                                                              lat_ptr, ws.data_ptr(), ws.numel(), stream)
+                        _lib.check(self._lib, self._h, rc, "mimi_b200_encode_phase")
+                    phase(_lib.PHASE_BEGIN, 0, 0)
+                    nxt = 0
+                    for b0, b1, land in staged_groups:
+                        if b0 != nxt or b1 <= b0 or b1 > B:
+                            raise ValueError("staged_groups must partition [0, B) in order")
+                        land()
+                        phase(_lib.PHASE_FRONT, b0, b1)
+                        nxt = b1
+                    if nxt != B:
+                        raise ValueError("staged_groups must partition [0, B) in order")
+                    phase(_lib.PHASE_FINISH, 0, 0)
         out = MimiEncoderOutput(codes, None, None)
         if return_latent:
             return out, latent
@@ -241,7 +265,14 @@ class MimiB200Model:
         return out
 
     # -- parity helpers --------------------------------------------------------------------------------
+    @property
+    def supports_phased(self) -> bool:
+        """mimi_b200_encode_phase needs the fused front end (kernel generations 3, 4, 6)."""
+        return self._mode in (3, 4, 6)
+
     def debug_set(self, key: int, value: int) -> None:
+        if key == 3:
+            self._mode = int(value)
         _lib.check(self._lib, self._h, self._lib.mimi_b200_debug_set(self._h, key, value), "mimi_b200_debug_set")
 
     def debug_tap(self, which: int) -> torch.Tensor:
@@ -327,7 +358,7 @@ class MimiEncoder:
     codebooks like the reference (whose callers then slice ``[:8]``); pass 8 to compute only those."""
 
     def __init__(self, model, device: str = "cuda", ragged: bool = True, num_quantizers: Optional[int] = None,
-                 chunk_items: int = 16, stage_threads: int = 1):
+                 chunk_items: int = 16, stage_threads: int = 1, first_items: Optional[int] = None):
         self.device = device
         self.feature_extractor = EncodecFeatureExtractorLite()
         if isinstance(model, MimiB200Model):
@@ -343,6 +374,11 @@ class MimiEncoder:
         # ragged mode encodes a batch as sub-batches of `chunk_items` items so that host staging of the next
         # sub-batch overlaps the GPU work of the previous one (items are independent, results identical)
         self.chunk_items = max(1, int(chunk_items))
+        self.first_items = max(1, self.chunk_items // 2) if first_items is None else max(1, int(first_items))
+        # phased=True: one padded batch staged group by group under the running front end (mimi_b200_encode_phase);
+        # False: independent sub-batches (the only choice for kernel generations without the fused front end)
+        self.phased = True
+        self.pack_threads = min(8, os.cpu_count() or 1)      # memcpy threads of mimi_b200_host_pack (1: torch copies)
         self._pinned: Optional[torch.Tensor] = None
         self._dev_in: Optional[torch.Tensor] = None
         self._pinned_codes: Optional[torch.Tensor] = None
@@ -357,7 +393,7 @@ class MimiEncoder:
         of up to ``max_samples`` samples, so that no later call has to pin fresh host memory (tens of ms)."""
         K = NUM_QUANTIZERS if self.num_quantizers is None else int(self.num_quantizers)
         self._grow_pinned(batch * max_samples, batch * K * (-(-max_samples // FRAME_SIZE)))
-        self.model.reserve_workspace(min(batch, self.chunk_items) if self.ragged else batch, max_samples, K)
+        self.model.reserve_workspace(batch, max_samples, K)
 
     def _grow_pinned(self, samples: int, codes: int) -> None:
         if self._pinned is None or self._pinned.numel() < samples:
@@ -370,11 +406,11 @@ class MimiEncoder:
             self._pinned_codes = torch.empty(max(int(codes * 1.25), 1), dtype=torch.int64).pin_memory()
 
     @staticmethod
-    def _sub_batches(B: int, chunk_items: int) -> List[List[int]]:
+    def _sub_batches(B: int, chunk_items: int, first_items: Optional[int] = None) -> List[List[int]]:
         """Item indices of the pipelined sub-batches of one ``encode_audio_batch`` call: a small first one gets the
         GPU going while the rest is still being staged, then at most two large ones (fewer, larger launches keep the
         persistent kernels efficient)."""
-        bounds = [0, min(B, max(1, chunk_items // 2))]
+        bounds = [0, min(B, max(1, chunk_items // 2 if first_items is None else first_items))]
         while bounds[-1] < B:
             bounds.append(min(B, bounds[-1] + max(chunk_items, (B - bounds[1] + 1) // 2)))
         return [list(range(a, b)) for a, b in zip(bounds[:-1], bounds[1:])]
@@ -391,6 +427,20 @@ class MimiEncoder:
         ``feature_extractor(..., padding=True)`` does, REF/emilia-mimi/process_shard.py:113-118). ``zero_to[i]``
         is how far item i's padding has to be materialised (N in strict mode; the end of its last kept frame
         in ragged mode, nothing beyond that is ever read)."""
+        B = len(audio_arrays)
+        arrs = [np.asarray(a) for a in audio_arrays]
+        if self.pack_threads > 1 and B > 0 and all(a.ndim == 1 and a.dtype == np.float32 and a.flags.c_contiguous for a in arrs):
+            # native gather: memcpy threads of the extension (the GIL is released for the duration of the call)
+            N = buf.shape[-1]
+            if any(a.shape[0] > N for a in arrs):
+                raise ValueError("clip longer than the staging row")
+            src = (C.c_void_p * B)(*[a.ctypes.data for a in arrs])
+            lens = (C.c_int64 * B)(*[a.shape[0] for a in arrs])
+            zto = (C.c_int64 * B)(*[int(z) for z in zero_to])
+            rc = self.model._lib.mimi_b200_host_pack(buf.data_ptr(), buf.stride(0), src, lens, zto, B, self.pack_threads)
+            _lib.check(self.model._lib, None, rc, "mimi_b200_host_pack")
+            return
+
         def one(i):
             a = np.asarray(audio_arrays[i])
             if a.ndim != 1:
@@ -446,47 +496,95 @@ class MimiEncoder:
             self._check_rate(sample_rate)
             B = len(audio_arrays)
             K = NUM_QUANTIZERS if self.num_quantizers is None else int(self.num_quantizers)
-            chunks = self._sub_batches(B, self.chunk_items)
-            # a sub-batch is padded to whole frames (but never beyond the full batch length): every item then sees the
-            # same zeros behind its last kept frame as in the reference's single padded batch
-            n_full = max(original_lengths)
-            n_max = [min(n_full, -(-max(original_lengths[i] for i in ch) // FRAME_SIZE) * FRAME_SIZE) for ch in chunks]
-            total = sum(len(ch) * n for ch, n in zip(chunks, n_max))
-            t_max = [-(-n // FRAME_SIZE) for n in n_max]
-            total_codes = sum(len(ch) * K * t for ch, t in zip(chunks, t_max))
-            self._grow_pinned(total, total_codes)
-            off = coff = 0
-            host_codes = []
+            if not (self.phased and self.model.supports_phased):
+                return self._encode_sub_batched(audio_arrays, original_lengths, K, frame_rate)
+            # One padded [B,1,N] batch, exactly the reference's, staged group by group: the 24 kHz front end (the only
+            # part where items are independent) starts on group g as soon as its samples have landed while the host is
+            # still filling group g+1; everything after the front end runs once over the whole batch.
+            N = max(original_lengths)
+            T = -(-N // FRAME_SIZE)
+            self._grow_pinned(B * N, B * K * T)
+            buf = self._pinned_view(0, B, N)
+            x = self._dev_in[: B * N].view(B, 1, N)
             dev = self.model.device
             if self._copy_stream is None:
                 self._copy_stream = torch.cuda.Stream(device=dev)
             main = torch.cuda.current_stream(dev)
-            self._copy_stream.wait_stream(main)
-            for ch, N, T in zip(chunks, n_max, t_max):
-                buf = self._pinned_view(off, len(ch), N)
-                off += len(ch) * N
-                lens = [original_lengths[i] for i in ch]
-                self._fill(buf, [audio_arrays[i] for i in ch], [min(N, -(-n // FRAME_SIZE) * FRAME_SIZE) for n in lens])
-                # H2D on its own stream: the copy of sub-batch j+1 runs under the kernels of sub-batch j
-                x = self._dev_in[off - len(ch) * N: off].view(len(ch), 1, N)
-                with torch.cuda.stream(self._copy_stream):
-                    x.copy_(buf, non_blocking=True)
-                    landed = torch.cuda.Event()
-                    landed.record(self._copy_stream)
-                main.wait_event(landed)
-                out = self.model.encode(input_values=x, padding_mask=None, num_quantizers=self.num_quantizers,
-                                        valid_lengths=lens)
-                hc = self._pinned_codes[coff: coff + len(ch) * K * T].view(len(ch), K, T)
-                coff += len(ch) * K * T
-                hc.copy_(out.audio_codes, non_blocking=True)
-                host_codes.append(hc)
-            torch.cuda.current_stream(self.model.device).synchronize()
-            result: List[np.ndarray] = []
-            for ch, hc in zip(chunks, host_codes):
-                arr = hc.numpy()
-                for j, i in enumerate(ch):
-                    result.append(arr[j, :, : int(np.ceil(original_lengths[i] / frame_rate))].copy())
-            return result
+            self._copy_stream.wait_stream(main)          # earlier readers of the landing buffer are done before it is rewritten
+            zero_to = [min(N, -(-n // FRAME_SIZE) * FRAME_SIZE) for n in original_lengths]
+
+            def lander(b0, b1):
+                def land():
+                    self._fill(buf[b0:b1], audio_arrays[b0:b1], zero_to[b0:b1])
+                    with torch.cuda.stream(self._copy_stream):
+                        x[b0:b1].copy_(buf[b0:b1], non_blocking=True)
+                        landed = torch.cuda.Event()
+                        landed.record(self._copy_stream)
+                    main.wait_event(landed)
+                return land
+            groups = [(g[0], g[-1] + 1, lander(g[0], g[-1] + 1)) for g in self._front_groups(B, self.first_items)]
+            out = self.model.encode(input_values=x, padding_mask=None, num_quantizers=self.num_quantizers,
+                                    valid_lengths=original_lengths, staged_groups=groups)
+            hc = self._pinned_codes[: B * K * T].view(B, K, T)
+            hc.copy_(out.audio_codes, non_blocking=True)
+            main.synchronize()
+            arr = hc.numpy()
+            return [arr[i, :, : int(np.ceil(n / frame_rate))].copy() for i, n in enumerate(original_lengths)]
+
+    @staticmethod
+    def _front_groups(B: int, first_items: int) -> List[List[int]]:
+        """Item groups of the phased encode: a small first group gets the GPU going, every later group is twice as large
+        (its staging is hidden behind the front end of the groups before it)."""
+        bounds = [0, min(B, max(1, int(first_items)))]
+        while bounds[-1] < B:
+            bounds.append(min(B, bounds[-1] + 2 * (bounds[-1] - bounds[-2])))
+        return [list(range(a, b)) for a, b in zip(bounds[:-1], bounds[1:])]
+
+    def _encode_sub_batched(self, audio_arrays, original_lengths, K, frame_rate) -> List[np.ndarray]:
+        """Ragged path for kernel generations without the phased call: the batch goes through the GPU as independent
+        sub-batches (staging of sub-batch j+1 overlaps the encode of sub-batch j)."""
+        B = len(audio_arrays)
+        chunks = self._sub_batches(B, self.chunk_items, self.first_items)
+        # a sub-batch is padded to whole frames (but never beyond the full batch length): every item then sees the
+        # same zeros behind its last kept frame as in the reference's single padded batch
+        n_full = max(original_lengths)
+        n_max = [min(n_full, -(-max(original_lengths[i] for i in ch) // FRAME_SIZE) * FRAME_SIZE) for ch in chunks]
+        total = sum(len(ch) * n for ch, n in zip(chunks, n_max))
+        t_max = [-(-n // FRAME_SIZE) for n in n_max]
+        total_codes = sum(len(ch) * K * t for ch, t in zip(chunks, t_max))
+        self._grow_pinned(total, total_codes)
+        off = coff = 0
+        host_codes = []
+        dev = self.model.device
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream(dev)
+        self._copy_stream.wait_stream(main)
+        for ch, N, T in zip(chunks, n_max, t_max):
+            buf = self._pinned_view(off, len(ch), N)
+            off += len(ch) * N
+            lens = [original_lengths[i] for i in ch]
+            self._fill(buf, [audio_arrays[i] for i in ch], [min(N, -(-n // FRAME_SIZE) * FRAME_SIZE) for n in lens])
+            # H2D on its own stream: the copy of sub-batch j+1 runs under the kernels of sub-batch j
+            x = self._dev_in[off - len(ch) * N: off].view(len(ch), 1, N)
+            with torch.cuda.stream(self._copy_stream):
+                x.copy_(buf, non_blocking=True)
+                landed = torch.cuda.Event()
+                landed.record(self._copy_stream)
+            main.wait_event(landed)
+            out = self.model.encode(input_values=x, padding_mask=None, num_quantizers=self.num_quantizers,
+                                    valid_lengths=lens)
+            hc = self._pinned_codes[coff: coff + len(ch) * K * T].view(len(ch), K, T)
+            coff += len(ch) * K * T
+            hc.copy_(out.audio_codes, non_blocking=True)
+            host_codes.append(hc)
+        torch.cuda.current_stream(self.model.device).synchronize()
+        result: List[np.ndarray] = []
+        for ch, hc in zip(chunks, host_codes):
+            arr = hc.numpy()
+            for j, i in enumerate(ch):
+                result.append(arr[j, :, : int(np.ceil(original_lengths[i] / frame_rate))].copy())
+        return result
 
     # -- SURVEY.md section 8(f): the callers and data formats either side of the path ---------------------------------
     def encode_native_rate_batch(self, audio_arrays: List[np.ndarray], sample_rate: int) -> List[np.ndarray]:
