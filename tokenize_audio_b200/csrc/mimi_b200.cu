@@ -170,12 +170,15 @@ struct mimi_b200 {
   f0::Consts f0_consts;
   int num_sms = 148;
   long long item_tiles[6] = {0, 0, 0, 0, 0, 0};   // sum over items of ceil(rows_at_level / 128) for the call in flight
+  const int* tile_ptr[6] = {};                 // ragged call in flight: compact 128-row tile lists per level (device), or nullptr
+  int tile_cnt[6] = {};
+  int exp_no_tile_list = 0;                    // debug_set key 13: walk the mt_max x B grid and skip (the old schedule)
   int phase = 0, front_b0 = 0, front_b1 = 0;   // mimi_b200_encode_phase: which part of the pipeline the call in flight runs
   int exp_raw_h1 = 0;                          // debug_set key 12: h1 crosses HBM as raw fp32 (front_fused raw_out + tc_gemm4 for D1)
   int exp_linear_k = 0;                        // debug_set key 11: k-blocks in linear order (no tap grouping)
   int exp_no_flat = 0;                         // debug_set key 10: never flatten the linears' row dimension across items
   int num_clusters = 74;                       // co-resident CTA pairs of the cta_group::2 GEMM (tc_gemm5.cuh, mode 6)
-  int exp_pair_n128 = 0;                       // pair tiles of 128 instead of 256 columns (debug_set key 9)
+  int exp_pair_n128 = 0;                       // pair tiles of 128 columns for layers with N >= this (debug_set key 9; 0 = never)
   PFN_cuTensorMapEncodeTiled_v12000 encode_tiled = nullptr;
   TcWeight tc_conv[MIMI_B200_NUM_CONVS];       // convs 1..13 (conv 0 is a direct SIMT conv)
   TcWeight tc_qkv[MIMI_B200_NUM_LAYERS], tc_o[MIMI_B200_NUM_LAYERS], tc_fc1[MIMI_B200_NUM_LAYERS], tc_fc2[MIMI_B200_NUM_LAYERS];
@@ -255,16 +258,22 @@ static void free_weights(mimi_b200* h) {
   h->loaded = false;
 }
 
-static int stage_ints(mimi_b200* h, const std::vector<int>& v, int* d_dst, cudaStream_t st) {
-  if (v.size() > h->stage_cap) {
-    CUDA_TRY(h, cudaDeviceSynchronize());
-    for (int i = 0; i < kStageSlots; ++i) {
-      if (h->stage[i]) cudaFreeHost(h->stage[i]);
-      h->stage[i] = nullptr;
-    }
-    h->stage_cap = std::max<size_t>(4096, v.size() * 2);
-    for (int i = 0; i < kStageSlots; ++i) CUDA_TRY(h, cudaMallocHost((void**)&h->stage[i], h->stage_cap * sizeof(int)));
+// pinned staging slots for the small integer tables (lengths, tile lists) of a call; growing them costs a device
+// synchronisation and four pinned allocations, so workspace_bytes() pre-sizes them for the batch it is asked about
+static int ensure_stage(mimi_b200* h, size_t ints) {
+  if (ints <= h->stage_cap) return MIMI_B200_OK;
+  CUDA_TRY(h, cudaDeviceSynchronize());
+  for (int i = 0; i < kStageSlots; ++i) {
+    if (h->stage[i]) cudaFreeHost(h->stage[i]);
+    h->stage[i] = nullptr;
   }
+  h->stage_cap = std::max<size_t>(4096, ints + ints / 4);
+  for (int i = 0; i < kStageSlots; ++i) CUDA_TRY(h, cudaMallocHost((void**)&h->stage[i], h->stage_cap * sizeof(int)));
+  return MIMI_B200_OK;
+}
+
+static int stage_ints(mimi_b200* h, const std::vector<int>& v, int* d_dst, cudaStream_t st) {
+  if (int rc = ensure_stage(h, v.size())) return rc;
   const int s = h->stage_next;
   h->stage_next = (s + 1) % kStageSlots;
   CUDA_TRY(h, cudaEventSynchronize(h->stage_ev[s]));
@@ -468,10 +477,11 @@ int mimi_b200_debug_set(mimi_b200_t* h, int key, int value) {
   else if (key == 6) h->use_planes = value != 0;
   else if (key == 7) h->exp_prefetch = value != 0;
   else if (key == 8) h->att_variant = (value >= 2 && value <= 4) ? value : 2;
-  else if (key == 9) h->exp_pair_n128 = value != 0;
+  else if (key == 9) h->exp_pair_n128 = std::max(value, 0);
   else if (key == 10) h->exp_no_flat = value != 0;
   else if (key == 11) h->exp_linear_k = value != 0;
   else if (key == 12) h->exp_raw_h1 = value != 0;
+  else if (key == 13) h->exp_no_tile_list = value != 0;
   else return fail(h, MIMI_B200_ERR_ARG, "debug_set: unknown key");
   return MIMI_B200_OK;
 }
@@ -608,6 +618,10 @@ int mimi_b200_workspace_bytes(mimi_b200_t* h, int B, int64_t N, int K, size_t* o
   // in the unfused tensor-core modes
   const bool simt = h->mode == 0 || h->dbg_last_conv != MIMI_B200_NUM_CONVS - 1;
   *out_bytes = (simt ? make_plan(B, N, K).bytes : h->mode == 5 ? make_plan_r(B, N, K).bytes : make_plan_tc(B, N, K, h->mode < 3).bytes) + 256;
+  if (!simt && h->mode != 5) {
+    const PlanTC pt = make_plan_tc(B, N, K, h->mode < 3);
+    return ensure_stage(h, (pt.bytes - (size_t)pt.ints) / sizeof(int));     // lengths + tile lists of a batch this size
+  }
   return MIMI_B200_OK;
 }
 
@@ -682,9 +696,11 @@ static int encode_impl(mimi_b200_t* h, const float* d_input, int B, int64_t N, c
   for (int l = 0; l < 6; ++l) maxlen[l] = p.rows[l];
   int total_frames = B * p.rows[5];
   for (int l = 0; l < 6; ++l) h->item_tiles[l] = (long long)B * ((p.rows[l] + 127) / 128);
+  for (int l = 0; l < 6; ++l) { h->tile_ptr[l] = nullptr; h->tile_cnt[l] = 0; }
   if (h_valid_len) {
     for (int l = 0; l < 6; ++l) h->item_tiles[l] = 0;
     std::vector<int> v((size_t)7 * B + 1);
+    v.reserve((pt.bytes - (size_t)pt.ints) / sizeof(int));
     int mx[6] = {0, 0, 0, 0, 0, 0};
     int acc = 0;
     for (int b = 0; b < B; ++b) {
@@ -702,6 +718,20 @@ static int encode_impl(mimi_b200_t* h, const float* d_input, int B, int64_t N, c
     }
     v[(size_t)7 * B] = acc;
     total_frames = acc;
+    for (int l = 0; l < 6; ++l) { h->tile_ptr[l] = nullptr; h->tile_cnt[l] = 0; }
+    if (use_tc && !use_r5 && !h->exp_no_tile_list && B < 2048) {
+      // compact lists of the 128-row tiles that exist at levels 1..5 (the outputs of every conv), m-tile major so that
+      // neighbouring CTAs work on the same stretch of time; the persistent GEMMs deal them out round-robin
+      for (int l = 1; l < 6; ++l) {
+        const size_t off = v.size();
+        const int mt_max = (mx[l] + 127) / 128;
+        for (int mt = 0; mt < mt_max; ++mt)
+          for (int b = 0; b < B; ++b)
+            if (mt * 128 < v[(size_t)l * B + b]) v.push_back((b << 20) | mt);
+        h->tile_ptr[l] = dints + off;
+        h->tile_cnt[l] = (int)(v.size() - off);
+      }
+    }
     if (h->phase <= MIMI_B200_PHASE_BEGIN) {       // the later phases of a phased call find the lengths in the workspace
       int rc = stage_ints(h, v, dints, st);
       if (rc) return rc;

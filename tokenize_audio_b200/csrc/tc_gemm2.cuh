@@ -40,7 +40,28 @@ struct Sched {
   // second fetch an L2 hit. In linear order they are s * cp k-blocks (x 148 CTAs x 64 KB: more than the L2) apart and
   // the activations are read from DRAM G times (ncu: 2.4 GB instead of 1.2 GB for D2).
   int G, s, cp;
+  // Compact list of the 128-row tiles that exist (ragged batches): entry = item << 20 | m-tile, m-tile major. Without it
+  // (nullptr) the tiles are the mt_max x B grid and the ones past an item's end are skipped -- which leaves the CTAs of a
+  // static round-robin with unequal numbers of real tiles (ncu: SMs idle 20-30 % of a launch on a ragged batch).
+  const int* tiles;
+  int ntiles;
 };
+
+__device__ __forceinline__ int sched_tiles(const Sched& sc) { return sc.tiles ? sc.ntiles : sc.mt_max * sc.B; }
+// 128-row tile t -> (item, first row, rows of the item); false when the tile lies past the item's end
+__device__ __forceinline__ bool sched_tile(const Sched& sc, const Epilogue& ep, int t, int& b, int& m0, int& Lout) {
+  if (sc.tiles) {
+    const int e = __ldg(sc.tiles + t);
+    b = e >> 20;
+    m0 = (e & 0xFFFFF) * kBM;
+  } else {
+    b = t % sc.B;
+    m0 = (t / sc.B) * kBM;
+  }
+  const int Lin = ep.len_in ? __ldg(ep.len_in + b) : ep.uniform_len_in;
+  Lout = (Lin + ep.conv_stride - 1) / ep.conv_stride;
+  return m0 < Lout;
+}
 
 // i-th k-block to visit -> linear k-block index (tau * cp + channel panel)
 __device__ __forceinline__ int kblock_order(const Sched& sc, int i) {
@@ -204,16 +225,10 @@ __device__ __forceinline__ void epilogue_role(const Epilogue& ep, const Sched& s
   constexpr int HALF = BN / (EPIW / 4);            // columns per epilogue thread
   constexpr int PC = PC_;
   constexpr int STG_WARP = 32 * PC * 4;
-  const int vtiles = sc.mt_max * sc.B * sc.ntn;
+  const int vtiles = sched_tiles(sc) * sc.ntn;
   auto decode = [&](int id, int& b, int& m0, int& n0, int& Lout) {
-    const int nt = id % sc.ntn;
-    const int t = id / sc.ntn;
-    b = t % sc.B;
-    m0 = (t / sc.B) * kBM;
-    n0 = nt * BN;
-    const int Lin = ep.len_in ? __ldg(ep.len_in + b) : ep.uniform_len_in;
-    Lout = (Lin + ep.conv_stride - 1) / ep.conv_stride;
-    return m0 < Lout;
+    n0 = (id % sc.ntn) * BN;
+    return sched_tile(sc, ep, id / sc.ntn, b, m0, Lout);
   };
   // ---- epilogue warps --------------------------------------------------------------------------------------
   const int ew = warp - EW0;                     // EW0 = index of the first epilogue warp (a multiple of 4 or 2)
@@ -269,7 +284,7 @@ tc2_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   const int nkb = K / kBK;
   const int ckb = ep.chunk_kb > 0 ? ep.chunk_kb : kChunkKB;
   const int nchunks = (nkb + ckb - 1) / ckb;
-  const int vtiles = sc.mt_max * sc.B * sc.ntn;
+  const int vtiles = sched_tiles(sc) * sc.ntn;
 
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmA_hi); tc::prefetch_tmap(&tmA_lo); tc::prefetch_tmap(&tmW_hi); tc::prefetch_tmap(&tmW_lo);
@@ -291,14 +306,8 @@ tc2_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
 
   // virtual tile id -> (n-tile, item, m-tile); returns false for tiles past the item's length
   auto decode = [&](int id, int& b, int& m0, int& n0, int& Lout) {
-    const int nt = id % sc.ntn;
-    const int t = id / sc.ntn;
-    b = t % sc.B;
-    m0 = (t / sc.B) * kBM;
-    n0 = nt * BN;
-    const int Lin = ep.len_in ? __ldg(ep.len_in + b) : ep.uniform_len_in;
-    Lout = (Lin + ep.conv_stride - 1) / ep.conv_stride;
-    return m0 < Lout;
+    n0 = (id % sc.ntn) * BN;
+    return sched_tile(sc, ep, id / sc.ntn, b, m0, Lout);
   };
 
   if (warp == 0) {
@@ -449,7 +458,7 @@ tc2p_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   const int nkb = nplanes * gm.G;
   const int ckb = ep.chunk_kb > 0 ? ep.chunk_kb : kChunkKB;
   const int nchunks = (nkb + ckb - 1) / ckb;
-  const int vtiles = sc.mt_max * sc.B * sc.ntn;
+  const int vtiles = sched_tiles(sc) * sc.ntn;
   const uint32_t a_bytes = (uint32_t)(2 * (128 + gm.G - 1) * 128);
 
   if (warp == 0 && lane == 0) {
@@ -472,14 +481,8 @@ tc2p_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   const uint32_t tmem_base = *tmem_base_ptr;
 
   auto decode = [&](int id, int& b, int& m0, int& n0, int& Lout) {
-    const int nt = id % sc.ntn;
-    const int t = id / sc.ntn;
-    b = t % sc.B;
-    m0 = (t / sc.B) * kBM;
-    n0 = nt * BN;
-    const int Lin = ep.len_in ? __ldg(ep.len_in + b) : ep.uniform_len_in;
-    Lout = (Lin + ep.conv_stride - 1) / ep.conv_stride;
-    return m0 < Lout;
+    n0 = (id % sc.ntn) * BN;
+    return sched_tile(sc, ep, id / sc.ntn, b, m0, Lout);
   };
 
   if (warp == 0) {

@@ -73,7 +73,7 @@ tc4_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int nkb = K / kBK;
   const int ckb = ep.chunk_kb > 0 ? ep.chunk_kb : kChunkKB;
   const int nchunks = (nkb + ckb - 1) / ckb;
-  const int vtiles = sc.mt_max * sc.B * sc.ntn;
+  const int vtiles = tc2::sched_tiles(sc) * sc.ntn;
 
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmA); tc::prefetch_tmap(&tmW_hi); tc::prefetch_tmap(&tmW_lo);
@@ -91,14 +91,8 @@ tc4_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t tmem_base = *tmem_base_ptr;
 
   auto decode = [&](int id, int& b, int& m0, int& n0, int& Lout) {
-    const int nt = id % sc.ntn;
-    const int t = id / sc.ntn;
-    b = t % sc.B;
-    m0 = (t / sc.B) * kBM;
-    n0 = nt * BN;
-    const int Lin = ep.len_in ? __ldg(ep.len_in + b) : ep.uniform_len_in;
-    Lout = (Lin + ep.conv_stride - 1) / ep.conv_stride;
-    return m0 < Lout;
+    n0 = (id % sc.ntn) * BN;
+    return tc2::sched_tile(sc, ep, id / sc.ntn, b, m0, Lout);
   };
 
   if (warp < 4) {

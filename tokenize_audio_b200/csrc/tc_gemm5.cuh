@@ -145,7 +145,7 @@ tcp_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   const int nkb = K / kBK;
   const int ckb = ep.chunk_kb > 0 ? ep.chunk_kb : kChunkKB;
   const int nchunks = (nkb + ckb - 1) / ckb;
-  const int ntiles = sc.mt_max * sc.B;               // 128-row tiles (m-tile major, item minor)
+  const int ntiles = tc2::sched_tiles(sc);           // 128-row tiles (m-tile major, item minor; compact list if given)
   const int npairs = ((ntiles + 1) >> 1) * sc.ntn;
 
   if (warp == 0 && lane == 0) {
@@ -175,11 +175,7 @@ tcp_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     n0 = nt * BNP;
     b = 0; m0 = 0; Lout = 0;
     if (t >= ntiles) return false;
-    b = t % sc.B;
-    m0 = (t / sc.B) * kBM;
-    const int Lin = ep.len_in ? __ldg(ep.len_in + b) : ep.uniform_len_in;
-    Lout = (Lin + ep.conv_stride - 1) / ep.conv_stride;
-    return m0 < Lout;
+    return tc2::sched_tile(sc, ep, t, b, m0, Lout);
   };
   // this CTA's tile of the pair, and whether the pair has any work (identical decision in every role of both CTAs)
   auto decode_pair = [&](int pid, int& b, int& m0, int& n0, int& Lout, bool& mine) {

@@ -132,7 +132,9 @@ static PlanTC make_plan_tc(int B, long long N, int K, bool level0) {
   p.s_zp = split(4, 512, 0, 3);          // rows: [z0, z0, z0..z(T-1), z(T-1)] = T + 3
   p.e = raw(5, 512);   p.s_e = split(5, 512, 0, 0);  p.rp = raw(5, 512);
   p.ints = off * (long long)sizeof(float);
-  p.bytes = (size_t)p.ints + sizeof(int) * (size_t)(7 * B + 1 + 64);
+  long long tile_ints = 0;                 // compact tile lists of levels 1..5 (ragged calls)
+  for (int l = 1; l < 6; ++l) tile_ints += (long long)B * ((p.rows[l] + 127) / 128);
+  p.bytes = (size_t)p.ints + sizeof(int) * (size_t)(7 * B + 1 + 64 + tile_ints);
   return p;
 }
 
@@ -241,10 +243,12 @@ static void tc_korder(const mimi_b200* h, tc2::Sched& sc, int k, int s, int cin)
 
 // persistent second-generation kernel: one CTA per SM over mt_max * B * (N / BN) virtual tiles
 static void launch_tc2(mimi_b200* h, const CUtensorMap& ahi, const CUtensorMap& alo, const TcWeight& w, const tc::Epilogue& ep,
-                       int B, int mt_max, cudaStream_t st, int k = 1, int s = 1, int cin = 0) {
+                       int B, int mt_max, cudaStream_t st, int k = 1, int s = 1, int cin = 0, const int* tiles = nullptr,
+                       int ntiles = 0) {
   tc2::Sched sc{B, mt_max, w.N / w.BN};
   tc_korder(h, sc, k, s, cin);
-  const long long vt = (long long)mt_max * B * sc.ntn;
+  sc.tiles = tiles; sc.ntiles = ntiles;
+  const long long vt = (tiles ? (long long)ntiles : (long long)mt_max * B) * sc.ntn;
   const int grid = (int)std::min<long long>(vt, h->num_sms);
   if (grid <= 0) return;
   if (w.BN == 128)
@@ -258,11 +262,15 @@ static void launch_tc2(mimi_b200* h, const CUtensorMap& ahi, const CUtensorMap& 
 // fifth-generation kernel: CTA pairs (cta_group::2), pair tiles of 2 x 128 rows x BNP columns
 static bool tcp_applies(const mimi_b200* h, const TcWeight& w) { return h->mode == 6 && w.N % 128 == 0 && w.BN == 128; }
 static void launch_tcp(mimi_b200* h, const CUtensorMap& ahi, const CUtensorMap& alo, const TcWeight& w, const tc::Epilogue& ep,
-                       int B, int mt_max, cudaStream_t st, int k = 1, int s = 1, int cin = 0) {
-  const int bnp = (w.N % 256 == 0 && !h->exp_pair_n128) ? 256 : 128;
+                       int B, int mt_max, cudaStream_t st, int k = 1, int s = 1, int cin = 0, const int* tiles = nullptr,
+                       int ntiles = 0) {
+  // 256-column pair tiles unless the layer is so deep (K) and narrow in rows that a tile is a large share of a cluster's
+  // whole job: exp_pair_n128 = N threshold from which 128-column tiles are used (0 = never)
+  const int bnp = (w.N % 256 == 0 && !(h->exp_pair_n128 > 0 && w.N >= h->exp_pair_n128)) ? 256 : 128;
   tcp::Sched sc{B, mt_max, w.N / bnp};
   tc_korder(h, sc, k, s, cin);
-  const long long npairs = (((long long)mt_max * B + 1) / 2) * sc.ntn;
+  sc.tiles = tiles; sc.ntiles = ntiles;
+  const long long npairs = (((tiles ? (long long)ntiles : (long long)mt_max * B) + 1) / 2) * sc.ntn;
   const int ncl = (int)std::min<long long>(npairs, h->num_clusters);
   if (ncl <= 0) return;
   if (bnp == 256)
@@ -304,11 +312,16 @@ static int tc_gemm(TcCtx& c, int slot, const SplitBuf& a, int k, int s, int pad,
   if (lout_max <= 0) return MIMI_B200_OK;
   int nb = c.B;
   if (flat) { ep.len_in = nullptr; ep.uniform_len_in = c.B * rows_lvl; lout_max = c.B * rows_lvl; nb = 1; }
+  // ragged call: the compact list of the output level's tiles (the output of a strided conv lives one level up)
+  const int out_level = a.level + (s > 1 ? 1 : 0);
+  const int* tiles = (!flat && out_level < 6) ? c.h->tile_ptr[out_level] : nullptr;
+  const int ntiles = tiles ? c.h->tile_cnt[out_level] : 0;
   if (o.raw_in) {
     if (flat || planes || v3) return fail(c.h, MIMI_B200_ERR_ARG, "tc: raw input only for the k-block ring kernels");
     tc2::Sched sc{nb, (lout_max + tc::kBM - 1) / tc::kBM, w.N / w.BN};
     tc_korder(c.h, sc, k, s, a.C);
-    const long long vt = (long long)sc.mt_max * nb * sc.ntn;
+    sc.tiles = tiles; sc.ntiles = ntiles;
+    const long long vt = (tiles ? (long long)ntiles : (long long)sc.mt_max * nb) * sc.ntn;
     const int grid = (int)std::min<long long>(vt, c.h->num_sms);
     if (w.BN == 128)
       tc4::tc4_gemm_kernel<128><<<grid, tc4::kThreads, tc4::Cfg<128>::SMEM, c.st>>>(*ahi, w.map_hi, w.map_lo, w.K, 1, ep, sc);
@@ -328,9 +341,9 @@ static int tc_gemm(TcCtx& c, int slot, const SplitBuf& a, int k, int s, int pad,
     else
       tc2::tc2p_gemm_kernel<64><<<grid, tc2::threads(64), tc2::CfgP<64>::SMEM, c.st>>>(m4[2], m4[3], w.map_hi, w.map_lo, ep, sc, gm);
   } else if (tcp_applies(c.h, w)) {
-    launch_tcp(c.h, *ahi, *alo, w, ep, nb, (lout_max + tc::kBM - 1) / tc::kBM, c.st, k, s, a.C);
+    launch_tcp(c.h, *ahi, *alo, w, ep, nb, (lout_max + tc::kBM - 1) / tc::kBM, c.st, k, s, a.C, tiles, ntiles);
   } else if (c.h->mode >= 2) {
-    launch_tc2(c.h, *ahi, *alo, w, ep, nb, (lout_max + tc::kBM - 1) / tc::kBM, c.st, k, s, a.C);
+    launch_tc2(c.h, *ahi, *alo, w, ep, nb, (lout_max + tc::kBM - 1) / tc::kBM, c.st, k, s, a.C, tiles, ntiles);
   } else {
     dim3 grid((lout_max + tc::kBM - 1) / tc::kBM, w.N / w.BN, nb);
     if (w.BN == 128)
