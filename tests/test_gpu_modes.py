@@ -2,7 +2,8 @@
 
 mode 0 = all-fp32 FFMA (the exact-fp32 baseline), 2 = persistent tcgen05 3xTF32 GEMM + SIMT RVQ + SIMT attention,
 3 = + fused 24 kHz front end, tensor-core attention and RVQ, 4 = experimental third-generation GEMM, 5 = raw fp32
-activations split inside the GEMM, 6 = default: mode 3 with the CTA-pair (cta_group::2) GEMM.
+activations split inside the GEMM, 6 = mode 3 with the CTA-pair (cta_group::2) GEMM, 7 = default: mode 6 with bf16 lo
+parts (A_lo * W_hi on kind::f16).
 Tolerances as in test_gpu_parity.py: codes >= 99.9 % identical to the oracle, latent relative L2 <= 2e-5.
 """
 import ctypes as C
@@ -34,7 +35,7 @@ def case(state_dict):
     return x, lens, ref, np.stack(taps["latent"])
 
 
-@pytest.mark.parametrize("mode", [0, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("mode", [0, 2, 3, 4, 5, 6, 7])
 def test_every_mode_matches_the_oracle(b200_model, case, mode):
     x, lens, ref, lat_ref = case
     b200_model.set_mode(mode)
@@ -76,6 +77,7 @@ def test_tensor_core_attention_matches_simt_attention(b200_model):
         x[i, 0, :n] = synth.synth_speech(1300 + i, n)
     xd = torch.from_numpy(x).cuda()
     res = {}
+    b200_model.set_mode(6)            # the SIMT kernels write fp32 lo parts: compare inside the fp32-lo generation
     try:
         for variant in (2, 4):
             b200_model.debug_set(8, variant)
@@ -83,6 +85,7 @@ def test_tensor_core_attention_matches_simt_attention(b200_model):
             res[variant] = (out.audio_codes.cpu().numpy(), lat.cpu().numpy())
     finally:
         b200_model.debug_set(8, 4)
+        b200_model.set_mode(True)
     for i, n in enumerate(lens):
         t = -(-n // 1920)
         a, b = res[2][1][i, :, :t], res[4][1][i, :, :t]

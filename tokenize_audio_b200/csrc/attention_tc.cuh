@@ -53,6 +53,7 @@ struct Params {
   int uniform_len;
   int B;
   int mt_max;                  // query tiles per item at the longest item
+  int lo_bf16;                 // 1: out_lo is a bf16 array (mode 7)
 };
 
 // exp(x) for x <= 0 through ex2.approx; the scaling by log2(e) is done in two pieces so that the argument carries no
@@ -357,8 +358,8 @@ __global__ void __launch_bounds__(kThreads, 1) swa_attention_tc_kernel(const Par
       const long long o = (long long)b * p.out_stride + (long long)qi * kHidden + h * kHeadDim + cs * kCols;
 #pragma unroll
       for (int q = 0; q < kCols / 4; ++q)
-        store_split4(p.out_hi + o + 4 * q, p.out_lo + o + 4 * q,
-                     make_float4(oacc[4 * q] * inv, oacc[4 * q + 1] * inv, oacc[4 * q + 2] * inv, oacc[4 * q + 3] * inv));
+        store_split4_any(p.out_hi, p.out_lo, o + 4 * q,
+                         make_float4(oacc[4 * q] * inv, oacc[4 * q + 1] * inv, oacc[4 * q + 2] * inv, oacc[4 * q + 3] * inv), p.lo_bf16);
     }
     ++uc;
   }

@@ -66,6 +66,26 @@ __device__ __forceinline__ void store_split4(float* hi, float* lo, float4 v) {
   *reinterpret_cast<float4*>(lo) = l4;
 }
 
+// lo part of the split as bf16 (mode 7): lo = x - hi is a correction of relative size 2^-11, so 8 mantissa bits keep
+// the pair (hi, lo) accurate to 2^-20 of x; the A_lo * W_hi product then runs on kind::f16 at twice the TF32 rate
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {      // a -> low half, b -> high half (round to nearest)
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+// hi: 4 floats at `hi`; lo: 4 bf16 at element offset of the same index in a bf16 array
+__device__ __forceinline__ void store_split4_lob(float* hi, void* lo_bf16_elem, float4 v) {
+  float4 h4, l4;
+  split_tf32(v.x, h4.x, l4.x); split_tf32(v.y, h4.y, l4.y); split_tf32(v.z, h4.z, l4.z); split_tf32(v.w, h4.w, l4.w);
+  *reinterpret_cast<float4*>(hi) = h4;
+  *reinterpret_cast<uint2*>(lo_bf16_elem) = make_uint2(pack_bf16x2(l4.x, l4.y), pack_bf16x2(l4.z, l4.w));
+}
+// element `idx` of a lo array that is fp32 (lob = 0) or bf16 (lob = 1) and starts at `lo`
+__device__ __forceinline__ void store_split4_any(float* hi, float* lo, long long idx, float4 v, int lob) {
+  if (lob) store_split4_lob(hi + idx, reinterpret_cast<uint16_t*>(lo) + idx, v);
+  else store_split4(hi + idx, lo + idx, v);
+}
+
 // explicit shared-space 16-byte accesses (a pointer into dynamic shared memory that went through integer
 // arithmetic is otherwise compiled as a generic LD/ST, which the compiler cannot reorder against global
 // stores and which pays the generic-address check)

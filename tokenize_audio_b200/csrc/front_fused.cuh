@@ -55,6 +55,7 @@ struct Params {
   float* out_lo;
   long long split_item_stride;
   int split_front;
+  int lo_bf16;               // 1: out_lo is a bf16 array (mode 7)
   int raw_out;               // 1: store the raw fp32 result (pre-ELU, unsplit) to out_hi only (mode 5: the consumer
                              //    applies ELU and the hi/lo split itself)
 };
@@ -316,7 +317,14 @@ front_fused_kernel(const __grid_constant__ CUtensorMap tmW1_hi, const __grid_con
             const int r = i8 * 4 + (lane >> 3);
             const int mm = wq * 32 + r;
             const int tt = t0 - 2 + mm;
-            if (mm >= 2 && tt < L) *reinterpret_cast<float4*>(outp + obase + (long long)tt * 64 + (lane & 7) * 4) = tv[i8];
+            if (mm >= 2 && tt < L) {
+              const long long o = obase + (long long)tt * 64 + (lane & 7) * 4;
+              if (pass == 1 && p.lo_bf16)
+                *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(outp) + o) =
+                    make_uint2(pack_bf16x2(tv[i8].x, tv[i8].y), pack_bf16x2(tv[i8].z, tv[i8].w));
+              else
+                *reinterpret_cast<float4*>(outp + o) = tv[i8];
+            }
           }
           __syncwarp();
           if (pass == 0) {

@@ -71,6 +71,9 @@ struct TcWeight {
   float* lo = nullptr;
   CUtensorMap map_hi, map_lo;              // box 32 x BN
   CUtensorMap map64_hi, map64_lo;          // box 32 x 64 (tc_gemm3 when BN would be 32... or N % 128 != 0)
+  // bf16-lo generation (mode 7): hib = bf16(hi), SWIZZLE_64B boxes of 32 x {BN, 64, 32} rows, plus 32-row fp32 boxes
+  uint16_t* hib = nullptr;
+  CUtensorMap map_hib, map64_hib, map32_hib, map32_hi, map32_lo;
   int N = 0, K = 0, BN = 0;
 };
 // hi/lo activation pair, channels-last with `front` zero halo rows before row 0 of every item
@@ -153,7 +156,8 @@ struct mimi_b200 {
   Plan last;
   void* last_ws = nullptr;
   // tensor-core path
-  int mode = 6;                                // 6 = mode 3 with the CTA-pair GEMM (tc_gemm5.cuh) where N % 128 == 0 (default),
+  int mode = 7;                                // 7 = mode 6 with bf16 lo parts and A_lo * W_hi on kind::f16 (default),
+                                               // 6 = mode 3 with the CTA-pair GEMM (tc_gemm5.cuh) where N % 128 == 0 (default),
                                                // 5 = raw fp32 activations split inside the GEMM (tc_gemm4.cuh),
                                                // 4 = mode 3 with the experimental third-generation GEMM (tc_gemm3.cuh),
                                                // 3 = mode 2 + fused 24 kHz front end (front_fused.cuh),
@@ -172,6 +176,7 @@ struct mimi_b200 {
   long long item_tiles[6] = {0, 0, 0, 0, 0, 0};   // sum over items of ceil(rows_at_level / 128) for the call in flight
   const int* tile_ptr[6] = {};                 // ragged call in flight: compact 128-row tile lists per level (device), or nullptr
   int tile_cnt[6] = {};
+  int exp_full_lo = 0;                         // debug_set key 14: mode 7 keeps full-size (fp32-sized) lo buffers
   int exp_no_tile_list = 0;                    // debug_set key 13: walk the mt_max x B grid and skip (the old schedule)
   int phase = 0, front_b0 = 0, front_b1 = 0;   // mimi_b200_encode_phase: which part of the pipeline the call in flight runs
   int exp_raw_h1 = 0;                          // debug_set key 12: h1 crosses HBM as raw fp32 (front_fused raw_out + tc_gemm4 for D1)
@@ -210,6 +215,8 @@ static int fail(mimi_b200* h, int code, const std::string& msg) {
 // record "launch `id` just ended" on the stream (profiling only)
 static void mark(mimi_b200* h, int id, cudaStream_t st) {
   if (h->sync_debug && id >= 0 && h->sync_err.empty()) {
+    static const bool trace = getenv("MIMI_B200_TRACE") != nullptr;    // with MIMI_B200_SYNC: name every launch as it is awaited
+    if (trace) { fprintf(stderr, "[mimi_b200] waiting for launch kind %d (#%lld)\n", id, (long long)h->launches); fflush(stderr); }
     cudaError_t e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) h->sync_err = "launch kind " + std::to_string(id) + " (#" + std::to_string(h->launches) + "): " + cudaGetErrorString(e);
   }
@@ -428,6 +435,9 @@ int mimi_b200_create(mimi_b200_t** out, int device_ordinal) {
   cudaFuncSetAttribute(tc4::tc4_gemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc4::Cfg<32>::SMEM);
   cudaFuncSetAttribute(tcp::tcp_gemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcp::Cfg<256>::SMEM);
   cudaFuncSetAttribute(tcp::tcp_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcp::Cfg<128>::SMEM);
+  cudaFuncSetAttribute(tcp::tcp_gemm_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcp::Cfg<256, 1>::SMEM);
+  cudaFuncSetAttribute(tcp::tcp_gemm_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcp::Cfg<128, 1>::SMEM);
+  cudaFuncSetAttribute(tcp::tcp_gemm_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcp::Cfg<64, 1>::SMEM);
   {
     // how many CTA pairs of the widest instance fit at once (one per TPC unless the device says otherwise)
     cudaLaunchConfig_t cfg{};
@@ -471,7 +481,7 @@ int mimi_b200_debug_set(mimi_b200_t* h, int key, int value) {
   if (key == 0) h->dbg_layers = std::min(std::max(value, 0), MIMI_B200_NUM_LAYERS);
   else if (key == 1) h->dbg_last_conv = std::min(std::max(value, 0), MIMI_B200_NUM_CONVS - 1);
   else if (key == 2) { h->prof_on = value != 0; h->prof_n = 0; }
-  else if (key == 3) h->mode = std::min(std::max(value, 0), 6);
+  else if (key == 3) h->mode = std::min(std::max(value, 0), 7);
   else if (key == 4) h->exp_single_acc = value != 0;
   else if (key == 5) h->exp_chunk_kb = std::max(value, 0);
   else if (key == 6) h->use_planes = value != 0;
@@ -482,6 +492,7 @@ int mimi_b200_debug_set(mimi_b200_t* h, int key, int value) {
   else if (key == 11) h->exp_linear_k = value != 0;
   else if (key == 12) h->exp_raw_h1 = value != 0;
   else if (key == 13) h->exp_no_tile_list = value != 0;
+  else if (key == 14) h->exp_full_lo = value != 0;
   else return fail(h, MIMI_B200_ERR_ARG, "debug_set: unknown key");
   return MIMI_B200_OK;
 }
@@ -617,9 +628,9 @@ int mimi_b200_workspace_bytes(mimi_b200_t* h, int B, int64_t N, int K, size_t* o
   // sized for the compute mode in force (debug_set key 3): the fp32 FFMA plan only in mode 0, level-0 buffers only
   // in the unfused tensor-core modes
   const bool simt = h->mode == 0 || h->dbg_last_conv != MIMI_B200_NUM_CONVS - 1;
-  *out_bytes = (simt ? make_plan(B, N, K).bytes : h->mode == 5 ? make_plan_r(B, N, K).bytes : make_plan_tc(B, N, K, h->mode < 3).bytes) + 256;
+  *out_bytes = (simt ? make_plan(B, N, K).bytes : h->mode == 5 ? make_plan_r(B, N, K).bytes : make_plan_tc(B, N, K, h->mode < 3, h->mode == 7 && !h->exp_full_lo).bytes) + 256;
   if (!simt && h->mode != 5) {
-    const PlanTC pt = make_plan_tc(B, N, K, h->mode < 3);
+    const PlanTC pt = make_plan_tc(B, N, K, h->mode < 3, h->mode == 7 && !h->exp_full_lo);
     return ensure_stage(h, (pt.bytes - (size_t)pt.ints) / sizeof(int));     // lengths + tile lists of a batch this size
   }
   return MIMI_B200_OK;
@@ -640,7 +651,7 @@ int mimi_b200_encode_phase(mimi_b200_t* h, int phase, int b0, int b1, const floa
                            size_t workspace_bytes, void* stream) {
   if (!h) return MIMI_B200_ERR_ARG;
   if (phase < MIMI_B200_PHASE_BEGIN || phase > MIMI_B200_PHASE_FINISH) return fail(h, MIMI_B200_ERR_ARG, "encode_phase: bad phase");
-  if (h->mode < 3 || h->mode == 5 || h->dbg_last_conv != MIMI_B200_NUM_CONVS - 1)
+  if (h->mode < 3 || h->mode == 5 || h->dbg_last_conv != MIMI_B200_NUM_CONVS - 1)  // modes 3, 4, 6, 7
     return fail(h, MIMI_B200_ERR_STATE, "encode_phase: needs the fused front end (modes 3, 4, 6)");
   if (phase == MIMI_B200_PHASE_FRONT && (b0 < 0 || b1 > B || b0 > b1)) return fail(h, MIMI_B200_ERR_ARG, "encode_phase: bad item range");
   h->phase = phase; h->front_b0 = b0; h->front_b1 = b1;
@@ -669,7 +680,7 @@ static int encode_impl(mimi_b200_t* h, const float* d_input, int B, int64_t N, c
 
   const bool use_tc = h->mode >= 1 && h->dbg_last_conv == MIMI_B200_NUM_CONVS - 1;
   const Plan p = make_plan(B, N, K);
-  const PlanTC pt = make_plan_tc(B, N, K, h->mode < 3);
+  const PlanTC pt = make_plan_tc(B, N, K, h->mode < 3, h->mode == 7 && !h->exp_full_lo);
   const PlanR pr = make_plan_r(B, N, K);
   const bool use_r5 = use_tc && h->mode == 5;
   const size_t need = use_r5 ? pr.bytes : use_tc ? pt.bytes : p.bytes;
@@ -965,6 +976,11 @@ __global__ void debug_split_kernel(const float* __restrict__ x, float* __restric
   if (i < n) split_tf32(x[i], hi[i], lo[i]);
 }
 
+__global__ void debug_split_lob_kernel(const float* __restrict__ x, float* __restrict__ hi, uint16_t* __restrict__ lo, long long n) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i < n) store_split4_lob(hi + i, lo + i, *reinterpret_cast<const float4*>(x + i));
+}
+
 int mimi_b200_debug_tc_gemm(mimi_b200_t* h, const float* d_a, const float* h_w, const float* d_bias_opt, int M, int N,
                             int K, int act, float* d_out, void* stream) {
   if (!h || !d_a || !h_w || !d_out) return fail(h, MIMI_B200_ERR_ARG, "debug_tc_gemm: NULL argument");
@@ -980,16 +996,20 @@ int mimi_b200_debug_tc_gemm(mimi_b200_t* h, const float* d_a, const float* h_w, 
   const long long n = (long long)M * K;
   CUDA_TRY(h, cudaMalloc((void**)&hi, n * sizeof(float)));
   CUDA_TRY(h, cudaMalloc((void**)&lo, n * sizeof(float)));
-  debug_split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_a, hi, lo, n);
+  const bool lob = h->mode == 7;
+  if (lob) debug_split_lob_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(d_a, hi, reinterpret_cast<uint16_t*>(lo), n);
+  else debug_split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_a, hi, lo, n);
   CUtensorMap ma_hi, ma_lo;
   const cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)M, 1};
   const cuuint64_t strides[2] = {(cuuint64_t)K * sizeof(float), (cuuint64_t)n * sizeof(float)};
+  const cuuint64_t strides_b[2] = {(cuuint64_t)K * 2, (cuuint64_t)n * 2};
   if ((rc = tc_make_map(h, &ma_hi, hi, 3, dims, strides, tc::kBM))) return rc;
-  if ((rc = tc_make_map(h, &ma_lo, lo, 3, dims, strides, tc::kBM))) return rc;
+  if (lob) { if ((rc = tc_make_map_bf16(h, &ma_lo, lo, 3, dims, strides_b, tc::kBM))) return rc; }
+  else if ((rc = tc_make_map(h, &ma_lo, lo, 3, dims, strides, tc::kBM))) return rc;
   tc::Epilogue ep{};
   ep.bias = d_bias_opt; ep.out_raw = d_out; ep.raw_item_stride = (long long)M * N; ep.act = act;
   ep.uniform_len_in = M; ep.conv_stride = 1; ep.N = N;
-  ep.single_acc = h->exp_single_acc; ep.chunk_kb = h->exp_chunk_kb;
+  ep.single_acc = h->exp_single_acc; ep.chunk_kb = h->exp_chunk_kb; ep.lo_bf16 = lob;
   if (tcp_applies(h, w)) {
     launch_tcp(h, ma_hi, ma_lo, w, ep, 1, (M + tc::kBM - 1) / tc::kBM, st);
   } else if (h->mode == 4) {
@@ -1006,7 +1026,8 @@ int mimi_b200_debug_tc_gemm(mimi_b200_t* h, const float* d_a, const float* h_w, 
     else return fail(h, MIMI_B200_ERR_ARG, "debug_tc_gemm: mode 1 has no BN=32 kernel");
   }
   h->launches += 2;
-  cudaError_t e = cudaStreamSynchronize(st);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   cudaFree(hi);
   cudaFree(lo);
   if (e != cudaSuccess) return fail(h, MIMI_B200_ERR_CUDA, std::string("debug_tc_gemm: ") + cudaGetErrorString(e));

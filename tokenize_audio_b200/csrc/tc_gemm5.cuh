@@ -51,12 +51,19 @@ __device__ unsigned* g_tcp_marks = nullptr;
 #define TCP_MARK(slot, v)
 #endif
 
-template <int BNP>
+// LOB = 1 (mode 7): the activations' lo parts are bf16 arrays. The stage then holds A_hi (fp32, 16 KB), A_lo (bf16, 8 KB,
+// SWIZZLE_64B rows of 64 B), W_hi, W_lo (fp32) and W_hib = bf16(W_hi) (SWIZZLE_64B); A_hi*W_hi and A_hi*W_lo stay on
+// kind::tf32, A_lo*W_hib runs on kind::f16 (two K = 16 steps per k-block instead of four K = 8 steps): 2.5 tensor passes
+// instead of 3, and 6 instead of 8 bytes per activation element on every HBM / L2 / shared-memory hop.
+template <int BNP, int LOB = 0>
 struct Cfg {
   static constexpr int WB = BNP / 2;                                 // weight rows staged by each CTA
   static constexpr int A_BYTES = kBM * kBK * 4;                      // 16 KB
+  static constexpr int ALO_BYTES = LOB ? A_BYTES / 2 : A_BYTES;
   static constexpr int W_BYTES = WB * kBK * 4;
-  static constexpr int STAGE = 2 * A_BYTES + 2 * W_BYTES;            // per CTA
+  static constexpr int WHB_BYTES = LOB ? W_BYTES / 2 : 0;
+  static constexpr int OFF_ALO = A_BYTES, OFF_WHI = A_BYTES + ALO_BYTES, OFF_WLO = OFF_WHI + W_BYTES, OFF_WHB = OFF_WLO + W_BYTES;
+  static constexpr int STAGE = OFF_WHB + WHB_BYTES;                  // per CTA
   static constexpr int PC = 16;
   static constexpr int STG_WARP = 32 * PC * 4;
   static constexpr int STG = kEpiWarps * STG_WARP;
@@ -66,8 +73,10 @@ struct Cfg {
   static constexpr int SMEM = 1024 + STAGES * STAGE + STG + BAR_BYTES;
   static constexpr int TMEM_COLS = 2 * BNP;
   static constexpr int HALF = BNP / (kEpiWarps / 4);                 // accumulator columns per epilogue thread
-  static_assert(BNP == 128 || BNP == 256, "BNP");
+  static_assert(BNP == 64 || BNP == 128 || BNP == 256, "BNP");
+  static_assert(BNP >= 128 || LOB, "64-column pair tiles only exist in the bf16-lo generation");
   static_assert(STAGES >= 3, "ring too shallow");
+  static_assert(STAGE % 1024 == 0 && OFF_WHI % 1024 == 0 && OFF_WLO % 1024 == 0 && OFF_WHB % 512 == 0, "operand alignment");
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -112,6 +121,21 @@ __device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint32_t a_lo32,
       ::"r"(tmem_d), "r"(a_lo32), "r"(b_lo32), "r"(idesc), "r"(accumulate), "r"(tc::kDescHi)
       : "memory");
 }
+// the same for bf16 operands in SWIZZLE_64B K-major tiles (rows of 64 B, 8-row groups 512 B apart): kind::f16, K = 16
+constexpr uint32_t kDescHi64 = (uint32_t)(512 >> 4) | (1u << 14) | (4u << 29);
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint32_t a_lo32, uint32_t b_lo32, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo32), "r"(b_lo32), "r"(idesc), "r"(accumulate), "r"(kDescHi64)
+      : "memory");
+}
 // arrive (once every MMA issued so far has completed) on the barrier at this offset in BOTH CTAs of the pair
 __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
   const uint16_t mask = 3;
@@ -119,16 +143,14 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
                ::"r"(tc::smem_u32(bar)), "h"(mask) : "memory");
 }
 
-template <int BNP>
+template <int BNP, int LOB = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 tcp_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-                const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo, int K,
-                const Epilogue ep, const Sched sc) {
-  using C = Cfg<BNP>;
+                const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
+                const __grid_constant__ CUtensorMap tmW_hib, int K, const Epilogue ep, const Sched sc) {
+  using C = Cfg<BNP, LOB>;
   constexpr int STAGES = C::STAGES;
   constexpr int STAGE = C::STAGE;
-  constexpr int A_BYTES = C::A_BYTES;
-  constexpr int W_BYTES = C::W_BYTES;
   constexpr int HALF = C::HALF;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -150,6 +172,7 @@ tcp_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
 
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmA_hi); tc::prefetch_tmap(&tmA_lo); tc::prefetch_tmap(&tmW_hi); tc::prefetch_tmap(&tmW_lo);
+    if (LOB) tc::prefetch_tmap(&tmW_hib);
     for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < 2; ++s) {
       tc::mbar_init(&acc_full[s], 1);
@@ -209,9 +232,10 @@ tcp_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
             const uint32_t fb = full_leader + 8u * s;
             const int kx = tc2::kblock_order(sc, kb) * kBK;
             tma_load_3d_pair(st, &tmA_hi, fb, kx, m0, b);
-            tma_load_3d_pair(st + A_BYTES, &tmA_lo, fb, kx, m0, b);
-            tma_load_2d_pair(st + 2 * A_BYTES, &tmW_hi, fb, kx, wrow);
-            tma_load_2d_pair(st + 2 * A_BYTES + W_BYTES, &tmW_lo, fb, kx, wrow);
+            tma_load_3d_pair(st + C::OFF_ALO, &tmA_lo, fb, kx, m0, b);          // bf16 map in the LOB generation
+            tma_load_2d_pair(st + C::OFF_WHI, &tmW_hi, fb, kx, wrow);
+            tma_load_2d_pair(st + C::OFF_WLO, &tmW_lo, fb, kx, wrow);
+            if (LOB) tma_load_2d_pair(st + C::OFF_WHB, &tmW_hib, fb, kx, wrow);
           }
         }
       }
@@ -238,14 +262,20 @@ tcp_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
             if (lane == 0) TCP_MARK(2, kbc + 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t d_ahi = tc::desc_lo(smem_base_u32 + s * STAGE);
-            constexpr uint32_t kAlo = A_BYTES >> 4, kWhi = (2 * A_BYTES) >> 4, kWlo = (2 * A_BYTES + W_BYTES) >> 4;
+            constexpr uint32_t kAlo = C::OFF_ALO >> 4, kWhi = C::OFF_WHI >> 4, kWlo = C::OFF_WLO >> 4, kWhb = C::OFF_WHB >> 4;
             const bool first_in_chunk = kb == c * ckb;
             if (tc::elect_one()) {
 #pragma unroll
               for (int k = 0; k < kBK / kUmmaK; ++k) {
                 umma_tf32_pair(tmem_acc, d_ahi + 2 * k, d_ahi + kWhi + 2 * k, idesc, !(first_in_chunk && k == 0));
                 umma_tf32_pair(tmem_acc, d_ahi + 2 * k, d_ahi + kWlo + 2 * k, idesc, 1u);
-                umma_tf32_pair(tmem_acc, d_ahi + kAlo + 2 * k, d_ahi + kWhi + 2 * k, idesc, 1u);
+                if (!LOB) umma_tf32_pair(tmem_acc, d_ahi + kAlo + 2 * k, d_ahi + kWhi + 2 * k, idesc, 1u);
+              }
+              if (LOB) {
+                constexpr uint32_t idesc_b = make_idesc_bf16(2 * kBM, BNP);
+#pragma unroll
+                for (int k = 0; k < 2; ++k)     // 32 bf16 = two K = 16 steps of 32 B
+                  umma_bf16_pair(tmem_acc, d_ahi + kAlo + 2 * k, d_ahi + kWhb + 2 * k, idesc_b, 1u);
               }
               umma_commit_pair(&empty_bar[s]);
               if (kb + 1 == kb_end) umma_commit_pair(&acc_full[buf]);

@@ -27,6 +27,19 @@ static int tc_make_map(mimi_b200* h, CUtensorMap* out, const float* base, int ra
   return MIMI_B200_OK;
 }
 
+// bf16 tensor map, SWIZZLE_64B, inner box = 32 elements (64 B): the lo parts and bf16(W_hi) of the bf16-lo generation
+static int tc_make_map_bf16(mimi_b200* h, CUtensorMap* out, const void* base, int rank, const cuuint64_t* dims,
+                            const cuuint64_t* strides_bytes, int box_rows) {
+  cuuint32_t box[3] = {(cuuint32_t)tc::kBK, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = h->encode_tiled(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims,
+                               strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(h, MIMI_B200_ERR_CUDA, "cuTensorMapEncodeTiled (bf16) failed with CUresult " + std::to_string((int)r));
+  return MIMI_B200_OK;
+}
+
 // activation "plane" map for tc_gemm3: dims {C, stride, q, item}, element (c, ph, q, b) = row q*stride + ph, channel c of
 // item b (row 0 = first padded row); box {32, 1, box_rows, 1}, SWIZZLE_128B
 static int tc_make_map4(mimi_b200* h, CUtensorMap* out, const float* base, int C, int stride, long long q_rows, int B,
@@ -59,6 +72,25 @@ static int tc_make_weight(mimi_b200* h, TcWeight* w, const std::vector<float>& w
   if (N % 64 == 0) {   // tc_gemm3 has no BN = 32 instance: an extra 64-row box for it
     if ((rc = tc_make_map(h, &w->map64_hi, w->hi, 2, dims, strides, 64))) return rc;
     if ((rc = tc_make_map(h, &w->map64_lo, w->lo, 2, dims, strides, 64))) return rc;
+  }
+  {
+    // bf16-lo generation: bf16(W_hi) (round to nearest even; W_hi has 11 significant bits, bf16 keeps 8)
+    std::vector<uint16_t> hb(hi.size());
+    for (size_t i = 0; i < hi.size(); ++i) {
+      uint32_t u;
+      memcpy(&u, &hi[i], 4);
+      u += 0x7FFFu + ((u >> 16) & 1u);
+      hb[i] = (uint16_t)(u >> 16);
+    }
+    CUDA_TRY(h, cudaMalloc((void**)&w->hib, hb.size() * sizeof(uint16_t)));
+    h->allocs.push_back(w->hib);
+    CUDA_TRY(h, cudaMemcpy(w->hib, hb.data(), hb.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    const cuuint64_t strides_b[1] = {(cuuint64_t)K * 2};
+    if ((rc = tc_make_map_bf16(h, &w->map_hib, w->hib, 2, dims, strides_b, w->BN))) return rc;
+    if (N % 64 == 0 && (rc = tc_make_map_bf16(h, &w->map64_hib, w->hib, 2, dims, strides_b, 64))) return rc;
+    if ((rc = tc_make_map_bf16(h, &w->map32_hib, w->hib, 2, dims, strides_b, 32))) return rc;
+    if ((rc = tc_make_map(h, &w->map32_hi, w->hi, 2, dims, strides, 32))) return rc;
+    if ((rc = tc_make_map(h, &w->map32_lo, w->lo, 2, dims, strides, 32))) return rc;
   }
   return MIMI_B200_OK;
 }
@@ -100,7 +132,8 @@ static int tc_load_weights(mimi_b200* h, const mimi_b200_weights_t* w) {
 
 // `level0` = also lay out the level-0 buffers the unfused modes (1, 2) need; the default path keeps the 24 kHz
 // activations on chip, which saves 27.6 MB of workspace per audio-second
-static PlanTC make_plan_tc(int B, long long N, int K, bool level0) {
+// `lob` = the lo arrays are bf16 (mode 7): half the bytes
+static PlanTC make_plan_tc(int B, long long N, int K, bool level0, bool lob = false) {
   PlanTC p;
   p.B = B; p.K = K; p.N = N;
   long long L = N;
@@ -114,7 +147,7 @@ static PlanTC make_plan_tc(int B, long long N, int K, bool level0) {
     s.level = level; s.C = C; s.front = front; s.back = back;
     s.item_stride = (long long)(front + p.rows[level] + back) * C;
     s.hi = take((long long)B * s.item_stride + 64);
-    s.lo = take((long long)B * s.item_stride + 64);
+    s.lo = take(lob ? ((long long)B * s.item_stride + 64 + 1) / 2 : (long long)B * s.item_stride + 64);
     return s;
   };
   p.a0 = p.r1 = 0;
@@ -213,7 +246,10 @@ static int tc_amaps(TcCtx& c, int slot, const SplitBuf& a, int k, int s, int pad
     if (a.front < pad) return fail(c.h, MIMI_B200_ERR_ARG, "tc: halo smaller than conv padding");
     int rc;
     if ((rc = tc_make_map(c.h, mh, c.ws + a.hi + base_off, 3, dims, strides, tc::kBM))) return rc;
-    if ((rc = tc_make_map(c.h, ml, c.ws + a.lo + base_off, 3, dims, strides, tc::kBM))) return rc;
+    if (c.h->mode == 7) {   // lo is a bf16 array with the element indexing of hi
+      const cuuint64_t strides_b[2] = {strides[0] / 2, strides[1] / 2};
+      if ((rc = tc_make_map_bf16(c.h, ml, reinterpret_cast<const uint16_t*>(c.ws + a.lo) + base_off, 3, dims, strides_b, tc::kBM))) return rc;
+    } else if ((rc = tc_make_map(c.h, ml, c.ws + a.lo + base_off, 3, dims, strides, tc::kBM))) return rc;
     *c.built |= 1ull << slot;
   }
   *hi = mh;
@@ -260,23 +296,37 @@ static void launch_tc2(mimi_b200* h, const CUtensorMap& ahi, const CUtensorMap& 
 }
 
 // fifth-generation kernel: CTA pairs (cta_group::2), pair tiles of 2 x 128 rows x BNP columns
-static bool tcp_applies(const mimi_b200* h, const TcWeight& w) { return h->mode == 6 && w.N % 128 == 0 && w.BN == 128; }
+static bool tcp_applies(const mimi_b200* h, const TcWeight& w) {
+  return (h->mode == 6 && w.N % 128 == 0 && w.BN == 128) || (h->mode == 7 && w.N % 64 == 0);
+}
 static void launch_tcp(mimi_b200* h, const CUtensorMap& ahi, const CUtensorMap& alo, const TcWeight& w, const tc::Epilogue& ep,
                        int B, int mt_max, cudaStream_t st, int k = 1, int s = 1, int cin = 0, const int* tiles = nullptr,
                        int ntiles = 0) {
   // 256-column pair tiles unless the layer is so deep (K) and narrow in rows that a tile is a large share of a cluster's
   // whole job: exp_pair_n128 = N threshold from which 128-column tiles are used (0 = never)
-  const int bnp = (w.N % 256 == 0 && !(h->exp_pair_n128 > 0 && w.N >= h->exp_pair_n128)) ? 256 : 128;
+  const int bnp = (w.N % 256 == 0 && !(h->exp_pair_n128 > 0 && w.N >= h->exp_pair_n128)) ? 256
+                  : (w.N % 128 == 0)                                                       ? 128
+                                                                                           : 64;    // mode 7 only
   tcp::Sched sc{B, mt_max, w.N / bnp};
   tc_korder(h, sc, k, s, cin);
   sc.tiles = tiles; sc.ntiles = ntiles;
   const long long npairs = (((tiles ? (long long)ntiles : (long long)mt_max * B) + 1) / 2) * sc.ntn;
   const int ncl = (int)std::min<long long>(npairs, h->num_clusters);
   if (ncl <= 0) return;
+  if (h->mode == 7) {
+    // bf16-lo generation: every layer with N % 64 == 0 (alo is a bf16 map); box rows of the weight maps = bnp / 2
+    if (bnp == 256)
+      tcp::tcp_gemm_kernel<256, 1><<<2 * ncl, tcp::kThreads, tcp::Cfg<256, 1>::SMEM, st>>>(ahi, alo, w.map_hi, w.map_lo, w.map_hib, w.K, ep, sc);
+    else if (bnp == 128)
+      tcp::tcp_gemm_kernel<128, 1><<<2 * ncl, tcp::kThreads, tcp::Cfg<128, 1>::SMEM, st>>>(ahi, alo, w.map64_hi, w.map64_lo, w.map64_hib, w.K, ep, sc);
+    else
+      tcp::tcp_gemm_kernel<64, 1><<<2 * ncl, tcp::kThreads, tcp::Cfg<64, 1>::SMEM, st>>>(ahi, alo, w.map32_hi, w.map32_lo, w.map32_hib, w.K, ep, sc);
+    return;
+  }
   if (bnp == 256)
-    tcp::tcp_gemm_kernel<256><<<2 * ncl, tcp::kThreads, tcp::Cfg<256>::SMEM, st>>>(ahi, alo, w.map_hi, w.map_lo, w.K, ep, sc);
+    tcp::tcp_gemm_kernel<256><<<2 * ncl, tcp::kThreads, tcp::Cfg<256>::SMEM, st>>>(ahi, alo, w.map_hi, w.map_lo, w.map_hi, w.K, ep, sc);
   else
-    tcp::tcp_gemm_kernel<128><<<2 * ncl, tcp::kThreads, tcp::Cfg<128>::SMEM, st>>>(ahi, alo, w.map64_hi, w.map64_lo, w.K, ep, sc);
+    tcp::tcp_gemm_kernel<128><<<2 * ncl, tcp::kThreads, tcp::Cfg<128>::SMEM, st>>>(ahi, alo, w.map64_hi, w.map64_lo, w.map64_hi, w.K, ep, sc);
 }
 
 static int tc_gemm(TcCtx& c, int slot, const SplitBuf& a, int k, int s, int pad, const TcWeight& w, const TcOut& o, int prof_id) {
@@ -304,7 +354,7 @@ static int tc_gemm(TcCtx& c, int slot, const SplitBuf& a, int k, int s, int pad,
     ep.out_hi = c.ws + o.split->hi; ep.out_lo = c.ws + o.split->lo;
     ep.split_item_stride = o.split->item_stride; ep.split_front = o.split->front;
   }
-  ep.act = o.act; ep.elu_split = o.elu_split;
+  ep.act = o.act; ep.elu_split = o.elu_split; ep.lo_bf16 = c.h->mode == 7;
   ep.single_acc = c.h->exp_single_acc; ep.chunk_kb = c.h->exp_chunk_kb;
   ep.prefetch_next = c.h->exp_prefetch && w.N / w.BN == 1;      // with several n-tiles the rows are in L2 already
   ep.len_in = c.dlen[a.level]; ep.uniform_len_in = c.maxlen[a.level]; ep.conv_stride = s; ep.N = w.N;
@@ -364,7 +414,7 @@ static int tc_zero_halo(TcCtx& c, const SplitBuf& s) {
   const int per = (s.front + s.back) * s.C;
   dim3 grid((per + 255) / 256, c.B);
   tc::zero_halo_kernel<<<grid, 256, 0, c.st>>>(c.ws + s.hi, c.ws + s.lo, s.item_stride, s.C, s.front, s.back,
-                                               c.dlen[s.level], c.maxlen[s.level]);
+                                               c.dlen[s.level], c.maxlen[s.level], c.h->mode == 7);
   c.h->launches++;
   mark(c.h, 25, c.st);
   return MIMI_B200_OK;
@@ -375,7 +425,7 @@ static int encode_tc(mimi_b200* h, const float* d_input, int B, long long N, int
                      const int* const* dlen, const int* maxlen, const int* dprefix, int total_frames,
                      int64_t* d_codes, float* d_latent_opt, cudaStream_t st) {
   int rc;
-  const MapKey key{ws, B, N, h->mode < 3 ? 1 : 0};
+  const MapKey key{ws, B, N, h->mode < 3 ? 1 : h->mode == 7 ? 3 : 0};   // 2 = the raw-fp32 plan of mode 5 (tc5_host.inl)
   auto it = h->amap_cache.find(key);
   TcCtx c{h, &p, ws, B, st, dlen, maxlen, nullptr, nullptr, nullptr, nullptr};
   if (it == h->amap_cache.end()) {
@@ -417,7 +467,7 @@ static int encode_tc(mimi_b200* h, const float* d_input, int B, long long N, int
       fp.mt_max = (maxlen[0] + f0::kAdv - 1) / f0::kAdv;
       fp.out_hi = ws + p.s_h1.hi + (long long)b0 * p.s_h1.item_stride; fp.out_lo = ws + p.s_h1.lo + (long long)b0 * p.s_h1.item_stride;
       fp.split_item_stride = p.s_h1.item_stride; fp.split_front = p.s_h1.front;
-      fp.raw_out = raw_h1;
+      fp.raw_out = raw_h1; fp.lo_bf16 = h->mode == 7;
       const long long vt = (long long)fp.mt_max * nb;
       const int grid = (int)std::min<long long>(vt, h->num_sms);
       f0::front_fused_kernel<<<grid, f0::kThreads, f0::kSmem, st>>>(h->tc_conv[1].map_hi, h->tc_conv[1].map_lo, h->tc_conv[2].map_hi,
@@ -489,17 +539,17 @@ static int encode_tc(mimi_b200* h, const float* d_input, int B, long long N, int
   for (int l = 0; l < h->dbg_layers && T25 > 0; ++l) {
     const LayerDev& d = h->layer[l];
     dim3 lgrid((T25 + 7) / 8, B);
-    layernorm512_kernel<<<lgrid, 256, 0, st>>>(ws + p.z, ws + p.s_y.hi, d.ln1_w, d.ln1_b, rstride(4, 512), dlen[4], T25, ws + p.s_y.lo);
+    layernorm512_kernel<<<lgrid, 256, 0, st>>>(ws + p.z, ws + p.s_y.hi, d.ln1_w, d.ln1_b, rstride(4, 512), dlen[4], T25, ws + p.s_y.lo, h->mode == 7);
     h->launches++; mark(h, 14, st);
     TcOut o;
     o.raw = ws + p.qkv; o.raw_item_stride = rstride(4, 1536);
     if ((rc = tc_gemm(c, 0, p.s_y, 1, 1, 0, h->tc_qkv[l], o, 15))) return rc;
-    if (h->mode >= 3 && h->att_variant == 4) {
+    if (h->mode >= 3 && (h->att_variant == 4 || h->mode == 7)) {
       // tensor-core attention: persistent CTAs over (128-query tile, head, item) units
       atc::Params ap{};
       ap.qkv = ws + p.qkv; ap.item_stride = rstride(4, 1536); ap.out_hi = ws + p.s_att.hi; ap.out_lo = ws + p.s_att.lo;
       ap.out_stride = rstride(4, 512); ap.rope_cos = h->rope_cos; ap.rope_sin = h->rope_sin; ap.len = dlen[4];
-      ap.uniform_len = T25; ap.B = B; ap.mt_max = (T25 + atc::kQT - 1) / atc::kQT;
+      ap.uniform_len = T25; ap.B = B; ap.mt_max = (T25 + atc::kQT - 1) / atc::kQT; ap.lo_bf16 = h->mode == 7;
       const long long units = (long long)ap.mt_max * B * kHeads;
       atc::swa_attention_tc_kernel<<<(int)std::min<long long>(units, h->num_sms), atc::kThreads, atc::kSmem, st>>>(ap);
     } else if (h->mode >= 2) {
@@ -523,7 +573,7 @@ static int encode_tc(mimi_b200* h, const float* d_input, int B, long long N, int
     o = TcOut{};   // o_proj + LayerScale + residual, in place on z
     o.raw = ws + p.z; o.res = ws + p.z; o.raw_item_stride = rstride(4, 512); o.scale = d.ls1;
     if ((rc = tc_gemm(c, 1, p.s_att, 1, 1, 0, h->tc_o[l], o, 17))) return rc;
-    layernorm512_kernel<<<lgrid, 256, 0, st>>>(ws + p.z, ws + p.s_y.hi, d.ln2_w, d.ln2_b, rstride(4, 512), dlen[4], T25, ws + p.s_y.lo);
+    layernorm512_kernel<<<lgrid, 256, 0, st>>>(ws + p.z, ws + p.s_y.hi, d.ln2_w, d.ln2_b, rstride(4, 512), dlen[4], T25, ws + p.s_y.lo, h->mode == 7);
     h->launches++; mark(h, 14, st);
     o = TcOut{};   // fc1 + GELU(erf) -> split
     o.split = &p.s_ffn; o.act = 1;
@@ -537,7 +587,7 @@ static int encode_tc(mimi_b200* h, const float* d_input, int B, long long N, int
   if (T25 > 0) {
     dim3 pgrid((T25 + 3 + 7) / 8, B);
     tc::pad_replicate_split_kernel<<<pgrid, 256, 0, st>>>(ws + p.z, rstride(4, 512), ws + p.s_zp.hi, ws + p.s_zp.lo,
-                                                          p.s_zp.item_stride, dlen[4], T25);
+                                                          p.s_zp.item_stride, dlen[4], T25, h->mode == 7);
     h->launches++; mark(h, 26, st);
     TcOut o;
     o.raw = ws + p.e; o.raw_item_stride = rstride(5, 512); o.split = &p.s_e;

@@ -268,7 +268,7 @@ class MimiB200Model:
     @property
     def supports_phased(self) -> bool:
         """mimi_b200_encode_phase needs the fused front end (kernel generations 3, 4, 6)."""
-        return self._mode in (3, 4, 6)
+        return self._mode in (3, 4, 6, 7)
 
     def debug_set(self, key: int, value: int) -> None:
         if key == 3:
@@ -292,10 +292,11 @@ class MimiB200Model:
                      "rvq_input_proj", "rvq_fused", "latent_transpose", "code_fill", "halo_zero", "pad_split",
                      "front_fused"])
 
-    DEFAULT_MODE = 6
+    DEFAULT_MODE = 7
 
     def set_mode(self, tensor_cores) -> None:
-        """True / 6 (default): fused 24 kHz front end + CTA-pair (cta_group::2) tcgen05 3xTF32 GEMM for every layer with
+        """True / 7 (default): mode 6 with the lo parts of the activations stored as bf16 and the A_lo * W_hi product on
+        kind::f16 (2.5 tensor passes instead of 3, 6 instead of 8 bytes per activation element); 6: fused 24 kHz front end + CTA-pair (cta_group::2) tcgen05 3xTF32 GEMM for every layer with
         N % 128 == 0, the single-CTA persistent kernel for the rest; 3: the single-CTA kernel everywhere; 5: activations
         stored as raw fp32 and split inside the GEMM; 4: the same with the experimental third-generation GEMM (256-row tiles, plane-staged
         activations, single accumulator); 2: mode 3 without the front-end fusion; 1: the first-generation tcgen05 kernel
