@@ -77,6 +77,9 @@ def load_library(path: str | None = None) -> C.CDLL:
     global _lib
     if _lib is not None and path is None:
         return _lib
+    alt = os.environ.get("MIMI_B200_LIB")        # A/B of two builds on one box (tools/ab.sh): an explicit library file
+    if path is None and alt:
+        path = alt
     p = path or _build.LIB_PATH
     if path is None:
         try:
@@ -93,7 +96,7 @@ def load_library(path: str | None = None) -> C.CDLL:
         fn.argtypes = args
     if lib.mimi_b200_abi_version() != 1:
         raise MimiB200Error("libmimi_b200.so ABI version mismatch")
-    if path is None:
+    if path is None or path == alt:
         _lib = lib
     return lib
 
