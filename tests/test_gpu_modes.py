@@ -35,7 +35,7 @@ def case(state_dict):
     return x, lens, ref, np.stack(taps["latent"])
 
 
-@pytest.mark.parametrize("mode", [0, 2, 3, 4, 5, 6, 7])
+@pytest.mark.parametrize("mode", [0, 2, 3, 4, 5, 6, 7, 8])
 def test_every_mode_matches_the_oracle(b200_model, case, mode):
     x, lens, ref, lat_ref = case
     b200_model.set_mode(mode)

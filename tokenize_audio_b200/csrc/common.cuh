@@ -86,6 +86,16 @@ __device__ __forceinline__ void store_split4_any(float* hi, float* lo, long long
   else store_split4(hi + idx, lo + idx, v);
 }
 
+// the same with an optional third array hib = bf16(hi) (mode 8: both cross terms of the consuming GEMM run on kind::f16)
+__device__ __forceinline__ void store_split4_x(float* hi, float* lo, float* hib, long long idx, float4 v, int lob) {
+  if (!hib) { store_split4_any(hi, lo, idx, v, lob); return; }
+  float4 h4, l4;
+  split_tf32(v.x, h4.x, l4.x); split_tf32(v.y, h4.y, l4.y); split_tf32(v.z, h4.z, l4.z); split_tf32(v.w, h4.w, l4.w);
+  *reinterpret_cast<float4*>(hi + idx) = h4;
+  *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(lo) + idx) = make_uint2(pack_bf16x2(l4.x, l4.y), pack_bf16x2(l4.z, l4.w));
+  *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(hib) + idx) = make_uint2(pack_bf16x2(h4.x, h4.y), pack_bf16x2(h4.z, h4.w));
+}
+
 // explicit shared-space 16-byte accesses (a pointer into dynamic shared memory that went through integer
 // arithmetic is otherwise compiled as a generic LD/ST, which the compiler cannot reorder against global
 // stores and which pays the generic-address check)

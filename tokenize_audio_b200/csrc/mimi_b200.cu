@@ -73,11 +73,13 @@ struct TcWeight {
   CUtensorMap map64_hi, map64_lo;          // box 32 x 64 (tc_gemm3 when BN would be 32... or N % 128 != 0)
   // bf16-lo generation (mode 7): hib = bf16(hi), SWIZZLE_64B boxes of 32 x {BN, 64, 32} rows, plus 32-row fp32 boxes
   uint16_t* hib = nullptr;
+  uint16_t* lob = nullptr;                 // bf16(lo), mode 8
   CUtensorMap map_hib, map64_hib, map32_hib, map32_hi, map32_lo;
+  CUtensorMap map_lob, map64_lob, map32_lob;
   int N = 0, K = 0, BN = 0;
 };
 // hi/lo activation pair, channels-last with `front` zero halo rows before row 0 of every item
-struct SplitBuf { long long hi = 0, lo = 0, item_stride = 0; int front = 0, back = 0, C = 0, level = 0; };
+struct SplitBuf { long long hi = 0, lo = 0, item_stride = 0; int front = 0, back = 0, C = 0, level = 0; long long hib = -1; };   // hib: bf16(hi), mode 8, levels >= 2
 constexpr int kHalo = 8;     // >= max(k - stride) = 8 (front) and >= max(stride) - 1 = 7 (back)
 
 struct PlanTC {
@@ -102,7 +104,7 @@ struct PlanR {
   size_t bytes = 0;
 };
 
-struct MapSet { std::vector<CUtensorMap> maps, maps3; uint64_t built = 0, built3 = 0; };
+struct MapSet { std::vector<CUtensorMap> maps, maps3, mapsb; uint64_t built = 0, built3 = 0; };   // mapsb: hib maps, one per slot
 struct MapKey {
   const void* ws; int B; long long N; int layout;     // layout: which workspace plan the offsets come from
   bool operator<(const MapKey& o) const {
@@ -156,7 +158,8 @@ struct mimi_b200 {
   Plan last;
   void* last_ws = nullptr;
   // tensor-core path
-  int mode = 7;                                // 7 = mode 6 with bf16 lo parts and A_lo * W_hi on kind::f16 (default),
+  int mode = 7;                                // 8 = mode 7 + bf16(hi) copies at levels >= 2: both cross terms on kind::f16,
+                                               // 7 = mode 6 with bf16 lo parts and A_lo * W_hi on kind::f16 (default),
                                                // 6 = mode 3 with the CTA-pair GEMM (tc_gemm5.cuh) where N % 128 == 0 (default),
                                                // 5 = raw fp32 activations split inside the GEMM (tc_gemm4.cuh),
                                                // 4 = mode 3 with the experimental third-generation GEMM (tc_gemm3.cuh),
@@ -438,6 +441,9 @@ int mimi_b200_create(mimi_b200_t** out, int device_ordinal) {
   cudaFuncSetAttribute(tcp::tcp_gemm_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcp::Cfg<256, 1>::SMEM);
   cudaFuncSetAttribute(tcp::tcp_gemm_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcp::Cfg<128, 1>::SMEM);
   cudaFuncSetAttribute(tcp::tcp_gemm_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcp::Cfg<64, 1>::SMEM);
+  cudaFuncSetAttribute(tcp::tcp_gemm_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcp::Cfg<256, 2>::SMEM);
+  cudaFuncSetAttribute(tcp::tcp_gemm_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcp::Cfg<128, 2>::SMEM);
+  cudaFuncSetAttribute(tcp::tcp_gemm_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcp::Cfg<64, 2>::SMEM);
   {
     // how many CTA pairs of the widest instance fit at once (one per TPC unless the device says otherwise)
     cudaLaunchConfig_t cfg{};
@@ -481,7 +487,7 @@ int mimi_b200_debug_set(mimi_b200_t* h, int key, int value) {
   if (key == 0) h->dbg_layers = std::min(std::max(value, 0), MIMI_B200_NUM_LAYERS);
   else if (key == 1) h->dbg_last_conv = std::min(std::max(value, 0), MIMI_B200_NUM_CONVS - 1);
   else if (key == 2) { h->prof_on = value != 0; h->prof_n = 0; }
-  else if (key == 3) h->mode = std::min(std::max(value, 0), 7);
+  else if (key == 3) h->mode = std::min(std::max(value, 0), 8);
   else if (key == 4) h->exp_single_acc = value != 0;
   else if (key == 5) h->exp_chunk_kb = std::max(value, 0);
   else if (key == 6) h->use_planes = value != 0;
@@ -628,9 +634,9 @@ int mimi_b200_workspace_bytes(mimi_b200_t* h, int B, int64_t N, int K, size_t* o
   // sized for the compute mode in force (debug_set key 3): the fp32 FFMA plan only in mode 0, level-0 buffers only
   // in the unfused tensor-core modes
   const bool simt = h->mode == 0 || h->dbg_last_conv != MIMI_B200_NUM_CONVS - 1;
-  *out_bytes = (simt ? make_plan(B, N, K).bytes : h->mode == 5 ? make_plan_r(B, N, K).bytes : make_plan_tc(B, N, K, h->mode < 3, h->mode == 7 && !h->exp_full_lo).bytes) + 256;
+  *out_bytes = (simt ? make_plan(B, N, K).bytes : h->mode == 5 ? make_plan_r(B, N, K).bytes : make_plan_tc(B, N, K, h->mode < 3, h->mode >= 7 && !h->exp_full_lo, h->mode == 8).bytes) + 256;
   if (!simt && h->mode != 5) {
-    const PlanTC pt = make_plan_tc(B, N, K, h->mode < 3, h->mode == 7 && !h->exp_full_lo);
+    const PlanTC pt = make_plan_tc(B, N, K, h->mode < 3, h->mode >= 7 && !h->exp_full_lo, h->mode == 8);
     return ensure_stage(h, (pt.bytes - (size_t)pt.ints) / sizeof(int));     // lengths + tile lists of a batch this size
   }
   return MIMI_B200_OK;
@@ -651,7 +657,7 @@ int mimi_b200_encode_phase(mimi_b200_t* h, int phase, int b0, int b1, const floa
                            size_t workspace_bytes, void* stream) {
   if (!h) return MIMI_B200_ERR_ARG;
   if (phase < MIMI_B200_PHASE_BEGIN || phase > MIMI_B200_PHASE_FINISH) return fail(h, MIMI_B200_ERR_ARG, "encode_phase: bad phase");
-  if (h->mode < 3 || h->mode == 5 || h->dbg_last_conv != MIMI_B200_NUM_CONVS - 1)  // modes 3, 4, 6, 7
+  if (h->mode < 3 || h->mode == 5 || h->dbg_last_conv != MIMI_B200_NUM_CONVS - 1)  // modes 3, 4, 6, 7, 8
     return fail(h, MIMI_B200_ERR_STATE, "encode_phase: needs the fused front end (modes 3, 4, 6)");
   if (phase == MIMI_B200_PHASE_FRONT && (b0 < 0 || b1 > B || b0 > b1)) return fail(h, MIMI_B200_ERR_ARG, "encode_phase: bad item range");
   h->phase = phase; h->front_b0 = b0; h->front_b1 = b1;
@@ -680,7 +686,7 @@ static int encode_impl(mimi_b200_t* h, const float* d_input, int B, int64_t N, c
 
   const bool use_tc = h->mode >= 1 && h->dbg_last_conv == MIMI_B200_NUM_CONVS - 1;
   const Plan p = make_plan(B, N, K);
-  const PlanTC pt = make_plan_tc(B, N, K, h->mode < 3, h->mode == 7 && !h->exp_full_lo);
+  const PlanTC pt = make_plan_tc(B, N, K, h->mode < 3, h->mode >= 7 && !h->exp_full_lo, h->mode == 8);
   const PlanR pr = make_plan_r(B, N, K);
   const bool use_r5 = use_tc && h->mode == 5;
   const size_t need = use_r5 ? pr.bytes : use_tc ? pt.bytes : p.bytes;
@@ -976,9 +982,10 @@ __global__ void debug_split_kernel(const float* __restrict__ x, float* __restric
   if (i < n) split_tf32(x[i], hi[i], lo[i]);
 }
 
-__global__ void debug_split_lob_kernel(const float* __restrict__ x, float* __restrict__ hi, uint16_t* __restrict__ lo, long long n) {
+__global__ void debug_split_lob_kernel(const float* __restrict__ x, float* __restrict__ hi, uint16_t* __restrict__ lo, long long n,
+                                       float* __restrict__ hib) {
   const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  if (i < n) store_split4_lob(hi + i, lo + i, *reinterpret_cast<const float4*>(x + i));
+  if (i < n) store_split4_x(hi, reinterpret_cast<float*>(lo), hib, i, *reinterpret_cast<const float4*>(x + i), 1);
 }
 
 int mimi_b200_debug_tc_gemm(mimi_b200_t* h, const float* d_a, const float* h_w, const float* d_bias_opt, int M, int N,
@@ -996,14 +1003,18 @@ int mimi_b200_debug_tc_gemm(mimi_b200_t* h, const float* d_a, const float* h_w, 
   const long long n = (long long)M * K;
   CUDA_TRY(h, cudaMalloc((void**)&hi, n * sizeof(float)));
   CUDA_TRY(h, cudaMalloc((void**)&lo, n * sizeof(float)));
-  const bool lob = h->mode == 7;
-  if (lob) debug_split_lob_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(d_a, hi, reinterpret_cast<uint16_t*>(lo), n);
+  const bool lob = h->mode >= 7;
+  float* hib = nullptr;
+  if (h->mode == 8) CUDA_TRY(h, cudaMalloc((void**)&hib, n * sizeof(uint16_t)));
+  if (lob) debug_split_lob_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(d_a, hi, reinterpret_cast<uint16_t*>(lo), n, hib);
   else debug_split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_a, hi, lo, n);
   CUtensorMap ma_hi, ma_lo;
   const cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)M, 1};
   const cuuint64_t strides[2] = {(cuuint64_t)K * sizeof(float), (cuuint64_t)n * sizeof(float)};
   const cuuint64_t strides_b[2] = {(cuuint64_t)K * 2, (cuuint64_t)n * 2};
   if ((rc = tc_make_map(h, &ma_hi, hi, 3, dims, strides, tc::kBM))) return rc;
+  CUtensorMap ma_hib;
+  if (hib && (rc = tc_make_map_bf16(h, &ma_hib, hib, 3, dims, strides_b, tc::kBM))) return rc;
   if (lob) { if ((rc = tc_make_map_bf16(h, &ma_lo, lo, 3, dims, strides_b, tc::kBM))) return rc; }
   else if ((rc = tc_make_map(h, &ma_lo, lo, 3, dims, strides, tc::kBM))) return rc;
   tc::Epilogue ep{};
@@ -1011,7 +1022,7 @@ int mimi_b200_debug_tc_gemm(mimi_b200_t* h, const float* d_a, const float* h_w, 
   ep.uniform_len_in = M; ep.conv_stride = 1; ep.N = N;
   ep.single_acc = h->exp_single_acc; ep.chunk_kb = h->exp_chunk_kb; ep.lo_bf16 = lob;
   if (tcp_applies(h, w)) {
-    launch_tcp(h, ma_hi, ma_lo, w, ep, 1, (M + tc::kBM - 1) / tc::kBM, st);
+    launch_tcp(h, ma_hi, ma_lo, w, ep, 1, (M + tc::kBM - 1) / tc::kBM, st, 1, 1, 0, nullptr, 0, hib ? &ma_hib : nullptr);
   } else if (h->mode == 4) {
     CUtensorMap m4[4];
     for (int i = 0; i < 4; ++i)
@@ -1030,6 +1041,7 @@ int mimi_b200_debug_tc_gemm(mimi_b200_t* h, const float* d_a, const float* h_w, 
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   cudaFree(hi);
   cudaFree(lo);
+  if (hib) cudaFree(hib);
   if (e != cudaSuccess) return fail(h, MIMI_B200_ERR_CUDA, std::string("debug_tc_gemm: ") + cudaGetErrorString(e));
   return MIMI_B200_OK;
 }

@@ -47,6 +47,7 @@ struct Epilogue {
   int chunk_kb;                 // experiment (tc_gemm2 only): k-blocks per accumulation chunk (0 -> kChunkKB)
   int prefetch_next;            // tc_gemm2: L2-prefetch the next tile's activation boxes
   int lo_bf16;                  // 1: out_lo is a bf16 array (mode 7), same element indexing as out_hi
+  float* out_hib;               // mode 8: bf16(hi) array of the split output (same indexing), or nullptr
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -331,7 +332,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 // Zero the halo rows of one split buffer pair: rows [0, front) and [front + L_b, front + L_b + back) of every
 // item (the causal left pad and the right "extra" pad of the consuming conv).
 __global__ void zero_halo_kernel(float* hi, float* lo, long long item_stride, int C, int front, int back,
-                                 const int* __restrict__ len, int uniform_len, int lob = 0) {
+                                 const int* __restrict__ len, int uniform_len, int lob = 0, float* hib = nullptr) {
   const int b = blockIdx.y;
   const int L = len ? len[b] : uniform_len;
   const int per = (front + back) * C;
@@ -343,6 +344,7 @@ __global__ void zero_halo_kernel(float* hi, float* lo, long long item_stride, in
     hi[o] = 0.f;
     if (lob) reinterpret_cast<uint16_t*>(lo)[o] = 0;
     else lo[o] = 0.f;
+    if (hib) reinterpret_cast<uint16_t*>(hib)[o] = 0;
   }
 }
 
@@ -352,7 +354,8 @@ __global__ void zero_halo_kernel(float* hi, float* lo, long long item_stride, in
 __global__ void __launch_bounds__(256) pad_replicate_split_kernel(const float* __restrict__ z, long long z_item_stride,
                                                                   float* __restrict__ hi, float* __restrict__ lo,
                                                                   long long split_item_stride,
-                                                                  const int* __restrict__ len, int uniform_len, int lob = 0) {
+                                                                  const int* __restrict__ len, int uniform_len, int lob = 0,
+                                                                  float* __restrict__ hib = nullptr) {
   const int b = blockIdx.y;
   const int T = len ? len[b] : uniform_len;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -364,7 +367,7 @@ __global__ void __launch_bounds__(256) pad_replicate_split_kernel(const float* _
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int c = (i * 32 + lane) * 4;
-    store_split4_any(hi, lo, o + c, ld_nc_f4(zr + c), lob);
+    store_split4_x(hi, lo, hib, o + c, ld_nc_f4(zr + c), lob);
   }
 }
 

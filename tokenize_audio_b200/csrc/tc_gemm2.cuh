@@ -208,7 +208,7 @@ __device__ __forceinline__ void finish_tile(const Epilogue& ep, float (&acc)[HAL
         if (ep.out_raw) *reinterpret_cast<float4*>(ep.out_raw + raw_base + o) = v;
         if (ep.out_hi) {
           if (ep.elu_split) { v.x = elu_fast(v.x); v.y = elu_fast(v.y); v.z = elu_fast(v.z); v.w = elu_fast(v.w); }
-          store_split4_any(ep.out_hi, ep.out_lo, split_base + o, v, ep.lo_bf16);
+          store_split4_x(ep.out_hi, ep.out_lo, ep.out_hib, split_base + o, v, ep.lo_bf16);
         }
       }
     }

@@ -91,6 +91,19 @@ static int tc_make_weight(mimi_b200* h, TcWeight* w, const std::vector<float>& w
     if ((rc = tc_make_map_bf16(h, &w->map32_hib, w->hib, 2, dims, strides_b, 32))) return rc;
     if ((rc = tc_make_map(h, &w->map32_hi, w->hi, 2, dims, strides, 32))) return rc;
     if ((rc = tc_make_map(h, &w->map32_lo, w->lo, 2, dims, strides, 32))) return rc;
+    // mode 8: bf16(W_lo)
+    for (size_t i = 0; i < lo.size(); ++i) {
+      uint32_t u;
+      memcpy(&u, &lo[i], 4);
+      u += 0x7FFFu + ((u >> 16) & 1u);
+      hb[i] = (uint16_t)(u >> 16);
+    }
+    CUDA_TRY(h, cudaMalloc((void**)&w->lob, hb.size() * sizeof(uint16_t)));
+    h->allocs.push_back(w->lob);
+    CUDA_TRY(h, cudaMemcpy(w->lob, hb.data(), hb.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    if ((rc = tc_make_map_bf16(h, &w->map_lob, w->lob, 2, dims, strides_b, w->BN))) return rc;
+    if (N % 64 == 0 && (rc = tc_make_map_bf16(h, &w->map64_lob, w->lob, 2, dims, strides_b, 64))) return rc;
+    if ((rc = tc_make_map_bf16(h, &w->map32_lob, w->lob, 2, dims, strides_b, 32))) return rc;
   }
   return MIMI_B200_OK;
 }
@@ -133,7 +146,7 @@ static int tc_load_weights(mimi_b200* h, const mimi_b200_weights_t* w) {
 // `level0` = also lay out the level-0 buffers the unfused modes (1, 2) need; the default path keeps the 24 kHz
 // activations on chip, which saves 27.6 MB of workspace per audio-second
 // `lob` = the lo arrays are bf16 (mode 7): half the bytes
-static PlanTC make_plan_tc(int B, long long N, int K, bool level0, bool lob = false) {
+static PlanTC make_plan_tc(int B, long long N, int K, bool level0, bool lob = false, bool hibf = false) {
   PlanTC p;
   p.B = B; p.K = K; p.N = N;
   long long L = N;
@@ -148,6 +161,8 @@ static PlanTC make_plan_tc(int B, long long N, int K, bool level0, bool lob = fa
     s.item_stride = (long long)(front + p.rows[level] + back) * C;
     s.hi = take((long long)B * s.item_stride + 64);
     s.lo = take(lob ? ((long long)B * s.item_stride + 64 + 1) / 2 : (long long)B * s.item_stride + 64);
+    // mode 8: the tensor-bound layers (levels >= 2) also get bf16(hi); the HBM-bound level-0/1 edges stay at 6 bytes
+    s.hib = (hibf && level >= 2) ? take(((long long)B * s.item_stride + 64 + 1) / 2) : -1;
     return s;
   };
   p.a0 = p.r1 = 0;
@@ -182,6 +197,7 @@ struct TcCtx {
   const int* maxlen;          // [6]
   std::vector<CUtensorMap>* maps;   // 2 maps (hi, lo) per GEMM site, indexed by a fixed slot id
   uint64_t* built;                  // bit `slot` set once that site's maps are encoded
+  std::vector<CUtensorMap>* mapsb;  // mode 8: one bf16(hi) map per GEMM site
   std::vector<CUtensorMap>* maps3;  // 4 plane maps per GEMM site (tc_gemm3)
   uint64_t* built3;
 };
@@ -231,7 +247,7 @@ static int tc_amaps3(TcCtx& c, int slot, const SplitBuf& a, int k, int s, int pa
 // activation maps for a conv/linear that reads SplitBuf `a` with kernel k, stride s, left pad `pad`. `flat`: the
 // items' rows are one contiguous [B * rows][C] matrix (k = 1, no halo) seen as a single item.
 static int tc_amaps(TcCtx& c, int slot, const SplitBuf& a, int k, int s, int pad, bool flat, const CUtensorMap** hi,
-                    const CUtensorMap** lo) {
+                    const CUtensorMap** lo, const CUtensorMap** hib = nullptr) {
   if (flat) slot += kTcSlots;
   CUtensorMap* mh = &(*c.maps)[2 * slot];
   CUtensorMap* ml = mh + 1;
@@ -246,14 +262,19 @@ static int tc_amaps(TcCtx& c, int slot, const SplitBuf& a, int k, int s, int pad
     if (a.front < pad) return fail(c.h, MIMI_B200_ERR_ARG, "tc: halo smaller than conv padding");
     int rc;
     if ((rc = tc_make_map(c.h, mh, c.ws + a.hi + base_off, 3, dims, strides, tc::kBM))) return rc;
-    if (c.h->mode == 7) {   // lo is a bf16 array with the element indexing of hi
+    if (c.h->mode >= 7) {   // lo is a bf16 array with the element indexing of hi
       const cuuint64_t strides_b[2] = {strides[0] / 2, strides[1] / 2};
       if ((rc = tc_make_map_bf16(c.h, ml, reinterpret_cast<const uint16_t*>(c.ws + a.lo) + base_off, 3, dims, strides_b, tc::kBM))) return rc;
     } else if ((rc = tc_make_map(c.h, ml, c.ws + a.lo + base_off, 3, dims, strides, tc::kBM))) return rc;
+    if (a.hib >= 0) {
+      const cuuint64_t strides_b[2] = {strides[0] / 2, strides[1] / 2};
+      if ((rc = tc_make_map_bf16(c.h, &(*c.mapsb)[slot], reinterpret_cast<const uint16_t*>(c.ws + a.hib) + base_off, 3, dims, strides_b, tc::kBM))) return rc;
+    }
     *c.built |= 1ull << slot;
   }
   *hi = mh;
   *lo = ml;
+  if (hib) *hib = a.hib >= 0 ? &(*c.mapsb)[slot] : nullptr;
   return MIMI_B200_OK;
 }
 
@@ -297,11 +318,11 @@ static void launch_tc2(mimi_b200* h, const CUtensorMap& ahi, const CUtensorMap& 
 
 // fifth-generation kernel: CTA pairs (cta_group::2), pair tiles of 2 x 128 rows x BNP columns
 static bool tcp_applies(const mimi_b200* h, const TcWeight& w) {
-  return (h->mode == 6 && w.N % 128 == 0 && w.BN == 128) || (h->mode == 7 && w.N % 64 == 0);
+  return (h->mode == 6 && w.N % 128 == 0 && w.BN == 128) || (h->mode >= 7 && w.N % 64 == 0);
 }
 static void launch_tcp(mimi_b200* h, const CUtensorMap& ahi, const CUtensorMap& alo, const TcWeight& w, const tc::Epilogue& ep,
                        int B, int mt_max, cudaStream_t st, int k = 1, int s = 1, int cin = 0, const int* tiles = nullptr,
-                       int ntiles = 0) {
+                       int ntiles = 0, const CUtensorMap* ahib = nullptr) {
   // 256-column pair tiles unless the layer is so deep (K) and narrow in rows that a tile is a large share of a cluster's
   // whole job: exp_pair_n128 = N threshold from which 128-column tiles are used (0 = never)
   const int bnp = (w.N % 256 == 0 && !(h->exp_pair_n128 > 0 && w.N >= h->exp_pair_n128)) ? 256
@@ -313,24 +334,32 @@ static void launch_tcp(mimi_b200* h, const CUtensorMap& ahi, const CUtensorMap& 
   const long long npairs = (((tiles ? (long long)ntiles : (long long)mt_max * B) + 1) / 2) * sc.ntn;
   const int ncl = (int)std::min<long long>(npairs, h->num_clusters);
   if (ncl <= 0) return;
-  if (h->mode == 7) {
-    // bf16-lo generation: every layer with N % 64 == 0 (alo is a bf16 map); box rows of the weight maps = bnp / 2
-    if (bnp == 256)
-      tcp::tcp_gemm_kernel<256, 1><<<2 * ncl, tcp::kThreads, tcp::Cfg<256, 1>::SMEM, st>>>(ahi, alo, w.map_hi, w.map_lo, w.map_hib, w.K, ep, sc);
-    else if (bnp == 128)
-      tcp::tcp_gemm_kernel<128, 1><<<2 * ncl, tcp::kThreads, tcp::Cfg<128, 1>::SMEM, st>>>(ahi, alo, w.map64_hi, w.map64_lo, w.map64_hib, w.K, ep, sc);
-    else
-      tcp::tcp_gemm_kernel<64, 1><<<2 * ncl, tcp::kThreads, tcp::Cfg<64, 1>::SMEM, st>>>(ahi, alo, w.map32_hi, w.map32_lo, w.map32_hib, w.K, ep, sc);
+  if (h->mode >= 7) {
+    // bf16-lo generations: every layer with N % 64 == 0 (alo is a bf16 map); box rows of the weight maps = bnp / 2.
+    // With a bf16(hi) map of the input (mode 8, levels >= 2) both cross terms run on kind::f16 (LOB = 2).
+    const CUtensorMap &whi = bnp == 256 ? w.map_hi : bnp == 128 ? w.map64_hi : w.map32_hi;
+    const CUtensorMap &wlo = bnp == 256 ? w.map_lo : bnp == 128 ? w.map64_lo : w.map32_lo;
+    const CUtensorMap &whb = bnp == 256 ? w.map_hib : bnp == 128 ? w.map64_hib : w.map32_hib;
+    const CUtensorMap &wlb = bnp == 256 ? w.map_lob : bnp == 128 ? w.map64_lob : w.map32_lob;
+    if (ahib) {
+      if (bnp == 256) tcp::tcp_gemm_kernel<256, 2><<<2 * ncl, tcp::kThreads, tcp::Cfg<256, 2>::SMEM, st>>>(ahi, alo, whi, wlo, whb, *ahib, wlb, w.K, ep, sc);
+      else if (bnp == 128) tcp::tcp_gemm_kernel<128, 2><<<2 * ncl, tcp::kThreads, tcp::Cfg<128, 2>::SMEM, st>>>(ahi, alo, whi, wlo, whb, *ahib, wlb, w.K, ep, sc);
+      else tcp::tcp_gemm_kernel<64, 2><<<2 * ncl, tcp::kThreads, tcp::Cfg<64, 2>::SMEM, st>>>(ahi, alo, whi, wlo, whb, *ahib, wlb, w.K, ep, sc);
+    } else {
+      if (bnp == 256) tcp::tcp_gemm_kernel<256, 1><<<2 * ncl, tcp::kThreads, tcp::Cfg<256, 1>::SMEM, st>>>(ahi, alo, whi, wlo, whb, ahi, wlb, w.K, ep, sc);
+      else if (bnp == 128) tcp::tcp_gemm_kernel<128, 1><<<2 * ncl, tcp::kThreads, tcp::Cfg<128, 1>::SMEM, st>>>(ahi, alo, whi, wlo, whb, ahi, wlb, w.K, ep, sc);
+      else tcp::tcp_gemm_kernel<64, 1><<<2 * ncl, tcp::kThreads, tcp::Cfg<64, 1>::SMEM, st>>>(ahi, alo, whi, wlo, whb, ahi, wlb, w.K, ep, sc);
+    }
     return;
   }
   if (bnp == 256)
-    tcp::tcp_gemm_kernel<256><<<2 * ncl, tcp::kThreads, tcp::Cfg<256>::SMEM, st>>>(ahi, alo, w.map_hi, w.map_lo, w.map_hi, w.K, ep, sc);
+    tcp::tcp_gemm_kernel<256><<<2 * ncl, tcp::kThreads, tcp::Cfg<256>::SMEM, st>>>(ahi, alo, w.map_hi, w.map_lo, w.map_hi, ahi, w.map_hi, w.K, ep, sc);
   else
-    tcp::tcp_gemm_kernel<128><<<2 * ncl, tcp::kThreads, tcp::Cfg<128>::SMEM, st>>>(ahi, alo, w.map64_hi, w.map64_lo, w.map64_hi, w.K, ep, sc);
+    tcp::tcp_gemm_kernel<128><<<2 * ncl, tcp::kThreads, tcp::Cfg<128>::SMEM, st>>>(ahi, alo, w.map64_hi, w.map64_lo, w.map64_hi, ahi, w.map64_hi, w.K, ep, sc);
 }
 
 static int tc_gemm(TcCtx& c, int slot, const SplitBuf& a, int k, int s, int pad, const TcWeight& w, const TcOut& o, int prof_id) {
-  const CUtensorMap *ahi = nullptr, *alo = nullptr, *m4 = nullptr;
+  const CUtensorMap *ahi = nullptr, *alo = nullptr, *ahib = nullptr, *m4 = nullptr;
   int rc;
   if (slot < 0 || slot >= kTcSlots) return fail(c.h, MIMI_B200_ERR_ARG, "tc: bad map slot");
   const bool v3 = c.h->mode == 4;
@@ -345,7 +374,7 @@ static int tc_gemm(TcCtx& c, int slot, const SplitBuf& a, int k, int s, int pad,
                     (!o.split || (o.split->front == 0 && o.split->back == 0 && o.split->level == a.level)) &&
                     ((long long)c.B * rows_lvl + 127) / 128 < c.h->item_tiles[a.level];
   if (v3 || planes) { if ((rc = tc_amaps3(c, slot, a, k, s, pad, &m4))) return rc; }
-  else if ((rc = tc_amaps(c, slot, a, k, s, pad, flat, &ahi, &alo))) return rc;
+  else if ((rc = tc_amaps(c, slot, a, k, s, pad, flat, &ahi, &alo, &ahib))) return rc;
   if (w.K != k * a.C) return fail(c.h, MIMI_B200_ERR_ARG, "tc: weight K mismatch");
   tc::Epilogue ep{};
   ep.bias = o.bias; ep.scale = o.scale; ep.res = o.res; ep.out_raw = o.raw; ep.raw_item_stride = o.raw_item_stride;
@@ -353,8 +382,9 @@ static int tc_gemm(TcCtx& c, int slot, const SplitBuf& a, int k, int s, int pad,
     if (o.split->C != w.N) return fail(c.h, MIMI_B200_ERR_ARG, "tc: split output width mismatch");
     ep.out_hi = c.ws + o.split->hi; ep.out_lo = c.ws + o.split->lo;
     ep.split_item_stride = o.split->item_stride; ep.split_front = o.split->front;
+    ep.out_hib = o.split->hib >= 0 ? c.ws + o.split->hib : nullptr;
   }
-  ep.act = o.act; ep.elu_split = o.elu_split; ep.lo_bf16 = c.h->mode == 7;
+  ep.act = o.act; ep.elu_split = o.elu_split; ep.lo_bf16 = c.h->mode >= 7;
   ep.single_acc = c.h->exp_single_acc; ep.chunk_kb = c.h->exp_chunk_kb;
   ep.prefetch_next = c.h->exp_prefetch && w.N / w.BN == 1;      // with several n-tiles the rows are in L2 already
   ep.len_in = c.dlen[a.level]; ep.uniform_len_in = c.maxlen[a.level]; ep.conv_stride = s; ep.N = w.N;
@@ -391,7 +421,7 @@ static int tc_gemm(TcCtx& c, int slot, const SplitBuf& a, int k, int s, int pad,
     else
       tc2::tc2p_gemm_kernel<64><<<grid, tc2::threads(64), tc2::CfgP<64>::SMEM, c.st>>>(m4[2], m4[3], w.map_hi, w.map_lo, ep, sc, gm);
   } else if (tcp_applies(c.h, w)) {
-    launch_tcp(c.h, *ahi, *alo, w, ep, nb, (lout_max + tc::kBM - 1) / tc::kBM, c.st, k, s, a.C, tiles, ntiles);
+    launch_tcp(c.h, *ahi, *alo, w, ep, nb, (lout_max + tc::kBM - 1) / tc::kBM, c.st, k, s, a.C, tiles, ntiles, ahib);
   } else if (c.h->mode >= 2) {
     launch_tc2(c.h, *ahi, *alo, w, ep, nb, (lout_max + tc::kBM - 1) / tc::kBM, c.st, k, s, a.C, tiles, ntiles);
   } else {
@@ -414,7 +444,8 @@ static int tc_zero_halo(TcCtx& c, const SplitBuf& s) {
   const int per = (s.front + s.back) * s.C;
   dim3 grid((per + 255) / 256, c.B);
   tc::zero_halo_kernel<<<grid, 256, 0, c.st>>>(c.ws + s.hi, c.ws + s.lo, s.item_stride, s.C, s.front, s.back,
-                                               c.dlen[s.level], c.maxlen[s.level], c.h->mode == 7);
+                                               c.dlen[s.level], c.maxlen[s.level], c.h->mode >= 7,
+                                               s.hib >= 0 ? c.ws + s.hib : nullptr);
   c.h->launches++;
   mark(c.h, 25, c.st);
   return MIMI_B200_OK;
@@ -425,17 +456,19 @@ static int encode_tc(mimi_b200* h, const float* d_input, int B, long long N, int
                      const int* const* dlen, const int* maxlen, const int* dprefix, int total_frames,
                      int64_t* d_codes, float* d_latent_opt, cudaStream_t st) {
   int rc;
-  const MapKey key{ws, B, N, h->mode < 3 ? 1 : h->mode == 7 ? 3 : 0};   // 2 = the raw-fp32 plan of mode 5 (tc5_host.inl)
+  const MapKey key{ws, B, N, h->mode < 3 ? 1 : h->mode == 7 ? 3 : h->mode == 8 ? 4 : 0};   // 2 = the raw-fp32 plan of mode 5 (tc5_host.inl)
   auto it = h->amap_cache.find(key);
-  TcCtx c{h, &p, ws, B, st, dlen, maxlen, nullptr, nullptr, nullptr, nullptr};
+  TcCtx c{h, &p, ws, B, st, dlen, maxlen, nullptr, nullptr, nullptr, nullptr, nullptr};
   if (it == h->amap_cache.end()) {
     if (h->amap_cache.size() >= 64) h->amap_cache.clear();
     it = h->amap_cache.emplace(key, MapSet()).first;
     it->second.maps.resize(4 * kTcSlots);
+    it->second.mapsb.resize(2 * kTcSlots);
     it->second.maps3.resize(4 * kTcSlots);
   }
   c.maps = &it->second.maps;
   c.built = &it->second.built;
+  c.mapsb = &it->second.mapsb;
   c.maps3 = &it->second.maps3;
   c.built3 = &it->second.built3;
   auto rstride = [&](int level, int C) { return (long long)p.rows[level] * C; };
@@ -467,7 +500,7 @@ static int encode_tc(mimi_b200* h, const float* d_input, int B, long long N, int
       fp.mt_max = (maxlen[0] + f0::kAdv - 1) / f0::kAdv;
       fp.out_hi = ws + p.s_h1.hi + (long long)b0 * p.s_h1.item_stride; fp.out_lo = ws + p.s_h1.lo + (long long)b0 * p.s_h1.item_stride;
       fp.split_item_stride = p.s_h1.item_stride; fp.split_front = p.s_h1.front;
-      fp.raw_out = raw_h1; fp.lo_bf16 = h->mode == 7;
+      fp.raw_out = raw_h1; fp.lo_bf16 = h->mode >= 7;
       const long long vt = (long long)fp.mt_max * nb;
       const int grid = (int)std::min<long long>(vt, h->num_sms);
       f0::front_fused_kernel<<<grid, f0::kThreads, f0::kSmem, st>>>(h->tc_conv[1].map_hi, h->tc_conv[1].map_lo, h->tc_conv[2].map_hi,
@@ -539,17 +572,18 @@ static int encode_tc(mimi_b200* h, const float* d_input, int B, long long N, int
   for (int l = 0; l < h->dbg_layers && T25 > 0; ++l) {
     const LayerDev& d = h->layer[l];
     dim3 lgrid((T25 + 7) / 8, B);
-    layernorm512_kernel<<<lgrid, 256, 0, st>>>(ws + p.z, ws + p.s_y.hi, d.ln1_w, d.ln1_b, rstride(4, 512), dlen[4], T25, ws + p.s_y.lo, h->mode == 7);
+    layernorm512_kernel<<<lgrid, 256, 0, st>>>(ws + p.z, ws + p.s_y.hi, d.ln1_w, d.ln1_b, rstride(4, 512), dlen[4], T25, ws + p.s_y.lo, h->mode >= 7, p.s_y.hib >= 0 ? ws + p.s_y.hib : nullptr);
     h->launches++; mark(h, 14, st);
     TcOut o;
     o.raw = ws + p.qkv; o.raw_item_stride = rstride(4, 1536);
     if ((rc = tc_gemm(c, 0, p.s_y, 1, 1, 0, h->tc_qkv[l], o, 15))) return rc;
-    if (h->mode >= 3 && (h->att_variant == 4 || h->mode == 7)) {
+    if (h->mode >= 3 && (h->att_variant == 4 || h->mode >= 7)) {
       // tensor-core attention: persistent CTAs over (128-query tile, head, item) units
       atc::Params ap{};
       ap.qkv = ws + p.qkv; ap.item_stride = rstride(4, 1536); ap.out_hi = ws + p.s_att.hi; ap.out_lo = ws + p.s_att.lo;
       ap.out_stride = rstride(4, 512); ap.rope_cos = h->rope_cos; ap.rope_sin = h->rope_sin; ap.len = dlen[4];
-      ap.uniform_len = T25; ap.B = B; ap.mt_max = (T25 + atc::kQT - 1) / atc::kQT; ap.lo_bf16 = h->mode == 7;
+      ap.uniform_len = T25; ap.B = B; ap.mt_max = (T25 + atc::kQT - 1) / atc::kQT; ap.lo_bf16 = h->mode >= 7;
+      ap.out_hib = p.s_att.hib >= 0 ? ws + p.s_att.hib : nullptr;
       const long long units = (long long)ap.mt_max * B * kHeads;
       atc::swa_attention_tc_kernel<<<(int)std::min<long long>(units, h->num_sms), atc::kThreads, atc::kSmem, st>>>(ap);
     } else if (h->mode >= 2) {
@@ -573,7 +607,7 @@ static int encode_tc(mimi_b200* h, const float* d_input, int B, long long N, int
     o = TcOut{};   // o_proj + LayerScale + residual, in place on z
     o.raw = ws + p.z; o.res = ws + p.z; o.raw_item_stride = rstride(4, 512); o.scale = d.ls1;
     if ((rc = tc_gemm(c, 1, p.s_att, 1, 1, 0, h->tc_o[l], o, 17))) return rc;
-    layernorm512_kernel<<<lgrid, 256, 0, st>>>(ws + p.z, ws + p.s_y.hi, d.ln2_w, d.ln2_b, rstride(4, 512), dlen[4], T25, ws + p.s_y.lo, h->mode == 7);
+    layernorm512_kernel<<<lgrid, 256, 0, st>>>(ws + p.z, ws + p.s_y.hi, d.ln2_w, d.ln2_b, rstride(4, 512), dlen[4], T25, ws + p.s_y.lo, h->mode >= 7, p.s_y.hib >= 0 ? ws + p.s_y.hib : nullptr);
     h->launches++; mark(h, 14, st);
     o = TcOut{};   // fc1 + GELU(erf) -> split
     o.split = &p.s_ffn; o.act = 1;
@@ -587,7 +621,8 @@ static int encode_tc(mimi_b200* h, const float* d_input, int B, long long N, int
   if (T25 > 0) {
     dim3 pgrid((T25 + 3 + 7) / 8, B);
     tc::pad_replicate_split_kernel<<<pgrid, 256, 0, st>>>(ws + p.z, rstride(4, 512), ws + p.s_zp.hi, ws + p.s_zp.lo,
-                                                          p.s_zp.item_stride, dlen[4], T25, h->mode == 7);
+                                                          p.s_zp.item_stride, dlen[4], T25, h->mode >= 7,
+                                                          p.s_zp.hib >= 0 ? ws + p.s_zp.hib : nullptr);
     h->launches++; mark(h, 26, st);
     TcOut o;
     o.raw = ws + p.e; o.raw_item_stride = rstride(5, 512); o.split = &p.s_e;

@@ -11,7 +11,7 @@ __global__ void __launch_bounds__(256) layernorm512_kernel(const float* __restri
                                                            const float* __restrict__ gamma,
                                                            const float* __restrict__ beta,
                                                            long long item_stride, const int* __restrict__ len,
-                                                           int uniform_len, float* __restrict__ y_lo, int lob = 0) {
+                                                           int uniform_len, float* __restrict__ y_lo, int lob = 0, float* __restrict__ y_hib = nullptr) {
   // y_lo != nullptr: write the hi/lo TF32 split of the result into (y, y_lo) for a tensor-core consumer
   const int b = blockIdx.y;
   const int L = len ? len[b] : uniform_len;
@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(256) layernorm512_kernel(const float* __restri
     o.y = v[i].y * rstd * g.y + bt.y;
     o.z = v[i].z * rstd * g.z + bt.z;
     o.w = v[i].w * rstd * g.w + bt.w;
-    if (y_lo) store_split4_any(y, y_lo, (long long)b * item_stride + (long long)t * kHidden + c, o, lob);
+    if (y_lo) store_split4_x(y, y_lo, y_hib, (long long)b * item_stride + (long long)t * kHidden + c, o, lob);
     else *reinterpret_cast<float4*>(yr + c) = o;
   }
 }

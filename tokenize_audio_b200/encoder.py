@@ -268,7 +268,7 @@ class MimiB200Model:
     @property
     def supports_phased(self) -> bool:
         """mimi_b200_encode_phase needs the fused front end (kernel generations 3, 4, 6)."""
-        return self._mode in (3, 4, 6, 7)
+        return self._mode in (3, 4, 6, 7, 8)
 
     def debug_set(self, key: int, value: int) -> None:
         if key == 3:

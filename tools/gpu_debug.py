@@ -30,7 +30,7 @@ def main():
     xd = torch.from_numpy(x).cuda()
     if any(a.startswith("--tc") for a in sys.argv):
         # tensor-core path: raw taps that exist there (down convs 3/6/9, stream z), then the tail
-        mode = 1 if "--tc1" in sys.argv else 2 if "--tc2" in sys.argv else 4 if "--tc4" in sys.argv else 5 if "--tc5" in sys.argv else 6 if "--tc6" in sys.argv else 7 if "--tc7" in sys.argv else 3
+        mode = 1 if "--tc1" in sys.argv else 2 if "--tc2" in sys.argv else 4 if "--tc4" in sys.argv else 5 if "--tc5" in sys.argv else 6 if "--tc6" in sys.argv else 7 if "--tc7" in sys.argv else 8 if "--tc8" in sys.argv else 3
         m.set_mode(mode)
         for a in sys.argv:
             if a.startswith("--dbg="):          # --dbg=KEY:VALUE
