@@ -61,8 +61,9 @@ MMAC_PER_AUDIO_S = {
 HBM_BYTES_PER_AUDIO_S = {
     "conv0": 24000 * 4 + 24000 * 64 * 4,
     "layernorm": 25 * 512 * 4 * 2 * 16,
-    # fused 24 kHz front end: waveform in, TF32 hi/lo split of the 64-channel activation out
-    "front_fused": 24000 * 4 + 24000 * 64 * 8,
+    # fused 24 kHz front end: waveform in, TF32 hi (fp32) + lo (bf16) split of the 64-channel activation out
+    # (8 bytes per element in the kernel generations with fp32 lo parts, --mode <= 6)
+    "front_fused": 24000 * 4 + 24000 * 64 * 6,
 }
 HBM_BOUND_KINDS = ("conv0", "layernorm", "front_fused")
 
@@ -368,6 +369,8 @@ def main():
     ap.add_argument("--prefetch", type=int, default=None, help="debug: next-tile L2 prefetch in the GEMM producer on/off")
     args = ap.parse_args()
     select_workload(args.workload)
+    if args.mode is not None and args.mode <= 6:
+        HBM_BYTES_PER_AUDIO_S["front_fused"] = 24000 * 4 + 24000 * 64 * 8      # fp32 lo parts
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -495,7 +495,7 @@ int mimi_b200_debug_set(mimi_b200_t* h, int key, int value) {
   else if (key == 8) h->att_variant = (value >= 2 && value <= 4) ? value : 2;
   else if (key == 9) h->exp_pair_n128 = std::max(value, 0);
   else if (key == 10) h->exp_no_flat = value != 0;
-  else if (key == 11) h->exp_linear_k = value != 0;
+  else if (key == 11) h->exp_linear_k = value;           // 1: linear order, 2: tap-grouped with the channel panels innermost
   else if (key == 12) h->exp_raw_h1 = value != 0;
   else if (key == 13) h->exp_no_tile_list = value != 0;
   else if (key == 14) h->exp_full_lo = value != 0;

@@ -66,6 +66,14 @@ __device__ __forceinline__ bool sched_tile(const Sched& sc, const Epilogue& ep, 
 // i-th k-block to visit -> linear k-block index (tau * cp + channel panel)
 __device__ __forceinline__ int kblock_order(const Sched& sc, int i) {
   if (sc.G <= 1) return i;
+  if (sc.G >= 16) {
+    // variant (G + 16): channel panels innermost -- the cp 128-byte pieces of one input row are fetched back to back
+    // (DRAM page locality), the tap that re-reads the same rows follows cp k-blocks later (still an L2 hit)
+    const int G = sc.G - 16;
+    const int cb = i % sc.cp, t = i / sc.cp;
+    const int dq = t % G, ph = t / G;
+    return (ph + sc.s * dq) * sc.cp + cb;
+  }
   const int dq = i % sc.G, t = i / sc.G;
   const int cb = t % sc.cp, ph = t / sc.cp;
   return (ph + sc.s * dq) * sc.cp + cb;

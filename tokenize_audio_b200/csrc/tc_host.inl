@@ -294,8 +294,8 @@ struct TcOut {
 // k-block order of a conv with k taps, stride s over C_in channels (tc2::Sched): taps grouped by tau mod s
 static void tc_korder(const mimi_b200* h, tc2::Sched& sc, int k, int s, int cin) {
   sc.G = 0; sc.s = 0; sc.cp = 0;
-  if (h->exp_linear_k || s <= 1 || k <= s || k % s || cin % 32) return;   // s = 1 (k = 3): taps are 1 row apart, L2 hits anyway
-  sc.G = k / s; sc.s = s; sc.cp = cin / 32;
+  if (h->exp_linear_k == 1 || s <= 1 || k <= s || k % s || cin % 32) return;   // s = 1 (k = 3): taps are 1 row apart, L2 hits anyway
+  sc.G = k / s + (h->exp_linear_k == 2 ? 16 : 0); sc.s = s; sc.cp = cin / 32;
 }
 
 // persistent second-generation kernel: one CTA per SM over mt_max * B * (N / BN) virtual tiles
