@@ -93,6 +93,29 @@ def test_tensor_core_attention_matches_simt_attention(b200_model):
         assert (res[2][0][i, :, :t] == res[4][0][i, :, :t]).mean() >= 0.999
 
 
+def test_fused_level1_residual_block_matches_the_two_launches(b200_model):
+    """debug knob 15: conv a + conv b of the level-1 residual block in one kernel (tc_gemm6.cuh) vs the default two
+    launches, ragged batch. Same products in the same order per output element except conv b's K split, so the latents
+    agree to fp32 round-off and the codes are identical up to near-ties."""
+    lens = [289234, 61111, 1000]
+    x = np.zeros((3, 1, lens[0]), np.float32)
+    for i, n in enumerate(lens):
+        x[i, 0, :n] = synth.synth_speech(1500 + i, n)
+    xd = torch.from_numpy(x).cuda()
+    res = {}
+    try:
+        for fuse in (0, 1):
+            b200_model.debug_set(15, fuse)
+            out, lat = b200_model.encode(xd, num_quantizers=32, valid_lengths=lens, return_latent=True)
+            res[fuse] = (out.audio_codes.cpu().numpy(), lat.cpu().numpy())
+    finally:
+        b200_model.debug_set(15, 0)
+    for i, n in enumerate(lens):
+        t = -(-n // 1920)
+        assert _rel(res[1][1][i, :, :t], res[0][1][i, :, :t]) <= 2e-6
+        assert (res[1][0][i, :, :t] == res[0][0][i, :, :t]).mean() >= 0.999
+
+
 def test_wrapper_staging_schedules_are_invisible(b200_model):
     """encode_audio_batch (ragged mode) returns the same codes whether the batch is staged group by group under the
     running front end (mimi_b200_encode_phase, any group sizes), as independent sub-batches, or in one plain call."""

@@ -30,6 +30,7 @@
 #include "rvq_tc.cuh"
 #include "tc_gemm4.cuh"
 #include "tc_gemm5.cuh"
+#include "tc_gemm6.cuh"
 #include "transformer.cuh"
 #include "attention_tc.cuh"
 
@@ -179,6 +180,8 @@ struct mimi_b200 {
   long long item_tiles[6] = {0, 0, 0, 0, 0, 0};   // sum over items of ceil(rows_at_level / 128) for the call in flight
   const int* tile_ptr[6] = {};                 // ragged call in flight: compact 128-row tile lists per level (device), or nullptr
   int tile_cnt[6] = {};
+  int exp_fuse_res = 0;                        // debug_set key 15: level-1 residual block as one kernel (tc_gemm6.cuh, mode 7);
+                                               // correct, saves a launch and the intermediate buffer, but not faster (2.9 vs 3.1 ms)
   int exp_full_lo = 0;                         // debug_set key 14: mode 7 keeps full-size (fp32-sized) lo buffers
   int exp_no_tile_list = 0;                    // debug_set key 13: walk the mt_max x B grid and skip (the old schedule)
   int phase = 0, front_b0 = 0, front_b1 = 0;   // mimi_b200_encode_phase: which part of the pipeline the call in flight runs
@@ -441,6 +444,7 @@ int mimi_b200_create(mimi_b200_t** out, int device_ordinal) {
   cudaFuncSetAttribute(tcp::tcp_gemm_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcp::Cfg<256, 1>::SMEM);
   cudaFuncSetAttribute(tcp::tcp_gemm_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcp::Cfg<128, 1>::SMEM);
   cudaFuncSetAttribute(tcp::tcp_gemm_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcp::Cfg<64, 1>::SMEM);
+  cudaFuncSetAttribute(tcr::tcr_resblock_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tcr::kSmem);
   cudaFuncSetAttribute(tcp::tcp_gemm_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcp::Cfg<256, 2>::SMEM);
   cudaFuncSetAttribute(tcp::tcp_gemm_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcp::Cfg<128, 2>::SMEM);
   cudaFuncSetAttribute(tcp::tcp_gemm_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcp::Cfg<64, 2>::SMEM);
@@ -499,6 +503,7 @@ int mimi_b200_debug_set(mimi_b200_t* h, int key, int value) {
   else if (key == 12) h->exp_raw_h1 = value != 0;
   else if (key == 13) h->exp_no_tile_list = value != 0;
   else if (key == 14) h->exp_full_lo = value != 0;
+  else if (key == 15) h->exp_fuse_res = value != 0;
   else return fail(h, MIMI_B200_ERR_ARG, "debug_set: unknown key");
   return MIMI_B200_OK;
 }

@@ -439,6 +439,34 @@ static int tc_gemm(TcCtx& c, int slot, const SplitBuf& a, int k, int s, int pad,
   return MIMI_B200_OK;
 }
 
+// level-1 residual block fused (tc_gemm6.cuh): conv a (128 -> 64, k3) over split buffer `a`, conv b (64 -> 128, k1) + skip
+static int tc_resblock1(TcCtx& c, int slot, const SplitBuf& a, const TcWeight& wa, const TcWeight& wb, const float* bias_a,
+                        const float* bias_b, const float* res, long long raw_item_stride, const SplitBuf& out, int prof_id) {
+  const CUtensorMap *ahi = nullptr, *alo = nullptr;
+  int rc;
+  if (wa.N != tcr::kNA || wb.N != tcr::kNB || wb.K != tcr::kNA || wa.K != 3 * a.C || out.C != wb.N)
+    return fail(c.h, MIMI_B200_ERR_ARG, "tc: fused residual block geometry");
+  if ((rc = tc_amaps(c, slot, a, 3, 1, 2, false, &ahi, &alo))) return rc;
+  tc::Epilogue ep{};
+  ep.bias = bias_b; ep.res = res; ep.raw_item_stride = raw_item_stride;
+  ep.out_hi = c.ws + out.hi; ep.out_lo = c.ws + out.lo; ep.split_item_stride = out.item_stride; ep.split_front = out.front;
+  ep.elu_split = 1; ep.lo_bf16 = 1;
+  ep.len_in = c.dlen[a.level]; ep.uniform_len_in = c.maxlen[a.level]; ep.conv_stride = 1; ep.N = wb.N;
+  const int lout_max = c.maxlen[a.level];
+  if (lout_max <= 0) return MIMI_B200_OK;
+  tc2::Sched sc{c.B, (lout_max + tc::kBM - 1) / tc::kBM, 1};
+  sc.tiles = c.h->tile_ptr[a.level]; sc.ntiles = sc.tiles ? c.h->tile_cnt[a.level] : 0;
+  const long long npairs = ((sc.tiles ? (long long)sc.ntiles : (long long)sc.mt_max * c.B) + 1) / 2;
+  const int ncl = (int)std::min<long long>(npairs, c.h->num_clusters);
+  if (ncl <= 0) return MIMI_B200_OK;
+  tcr::tcr_resblock_kernel<<<2 * ncl, tcr::kThreads, tcr::kSmem, c.st>>>(*ahi, *alo, wa.map32_hi, wa.map32_lo, wa.map32_hib,
+                                                                        wb.map64_hi, wb.map64_lo, wb.map64_hib, wa.K, bias_a, ep, sc);
+  c.h->launches++;
+  mark(c.h, prof_id, c.st);
+  CUDA_TRY(c.h, cudaGetLastError());
+  return MIMI_B200_OK;
+}
+
 static int tc_zero_halo(TcCtx& c, const SplitBuf& s) {
   if (s.front + s.back == 0 || c.B == 0) return MIMI_B200_OK;
   const int per = (s.front + s.back) * s.C;
@@ -552,6 +580,12 @@ static int encode_tc(mimi_b200* h, const float* d_input, int B, long long N, int
     o.raw = ws + L.d_raw; o.raw_item_stride = rstride(s + 1, L.C); o.split = L.s_d; o.elu_split = 1; o.bias = h->conv_b[id];
     o.raw_in = (s == 0) ? raw_h1 : 0;
     if ((rc = tc_gemm(c, id, *L.in, gd.k, gd.stride, gd.k - gd.stride, h->tc_conv[id], o, id))) return rc;
+    if (s == 0 && h->mode == 7 && h->exp_fuse_res && !h->use_planes) {
+      // level 1: both convs of the residual block in one kernel (the 64-channel intermediate stays in shared memory)
+      if ((rc = tc_resblock1(c, ia, *L.s_d, h->tc_conv[ia], h->tc_conv[ib], h->conv_b[ia], h->conv_b[ib], ws + L.d_raw,
+                             rstride(s + 1, L.C), *L.s_h, ib))) return rc;
+      continue;
+    }
     o = TcOut{};   // resblock conv a: C -> C/2, k3
     o.split = L.s_r; o.elu_split = 1; o.bias = h->conv_b[ia];
     if ((rc = tc_gemm(c, ia, *L.s_d, 3, 1, 2, h->tc_conv[ia], o, ia))) return rc;
