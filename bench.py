@@ -68,6 +68,27 @@ HBM_BYTES_PER_AUDIO_S = {
 HBM_BOUND_KINDS = ("conv0", "layernorm", "front_fused")
 
 
+# stdout carries exactly ONE line, the JSON result: everything else a library prints there (NCCL's version banner, a
+# stray warning) is sent to stderr by pointing fd 1 at fd 2 for the whole run and writing the line to the saved fd
+_REAL_STDOUT = None
+
+
+def guard_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: str):
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        print(line, flush=True)
+    else:
+        os.write(_REAL_STDOUT, (line + "\n").encode())
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -172,7 +193,7 @@ def run_reference(args, rank, world):
     try:
         enc = reference_encoder(sd)
     except Exception as e:  # transformers missing on this box
-        print(json.dumps({"impl": "reference", "unavailable": f"transformers MimiModel not importable: {e}"}))
+        emit(json.dumps({"impl": "reference", "unavailable": f"transformers MimiModel not importable: {e}"}))
         return
     cores = os.cpu_count() or 1
 
@@ -186,7 +207,7 @@ def run_reference(args, rank, world):
     audio = sum(step(i) for i in range(args.steps))
     dt = time.perf_counter() - t0
     val = audio / dt
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": "audio_seconds_encoded_per_sec", "value": val, "unit": "x_realtime",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -339,7 +360,7 @@ def run_b200(args, rank, world, local_rank):
         except Exception as e:
             cpu = {"value": None, "unit": "x_realtime", "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {e}"}
 
-    print(json.dumps({
+    emit(json.dumps({
         "metric": "audio_seconds_encoded_per_sec", "value": value, "unit": "x_realtime", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": red["ms_max"] / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -368,6 +389,7 @@ def main():
     ap.add_argument("--dbg", action="append", default=[], help="debug: KEY=VALUE for mimi_b200_debug_set (A/B knobs)")
     ap.add_argument("--prefetch", type=int, default=None, help="debug: next-tile L2 prefetch in the GEMM producer on/off")
     args = ap.parse_args()
+    guard_stdout()
     select_workload(args.workload)
     if args.mode is not None and args.mode <= 6:
         HBM_BYTES_PER_AUDIO_S["front_fused"] = 24000 * 4 + 24000 * 64 * 8      # fp32 lo parts
