@@ -105,6 +105,13 @@ __device__ __forceinline__ void cluster_sync() {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// The same without release semantics, for "this TMEM buffer is drained": nothing in generic memory has to become visible
+// to the waiter (the tcgen05 loads are ordered by tcgen05.fence::before_thread_sync), and a cluster-scope release makes
+// the arriving lane wait for every global store its warp still has in flight from the previous tile's finish -- 17 % of
+// the warp samples of D1 sat in that fence (ERRBAR + the arrive, profiles/r01_final3_ncu.md).
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 // TMA loads of a CTA pair: destination in the executing CTA, completion bytes on a barrier that may live in the peer
 __device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1, int c2) {
   asm volatile(
@@ -329,7 +336,7 @@ tcp_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         tc2::drain_add<HALF>(tmem_base + lane_off + buf * BNP + (uint32_t)col0, acc);
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(acc_empty_leader + 8u * buf);
+        if (lane == 0) mbar_arrive_cluster_relaxed(acc_empty_leader + 8u * buf);
       }
       if (mine) tc2::finish_tile<HALF, C::PC>(ep, acc, b, m0 + quarter * 32, n0 + col0, Lout, stg, lane);
       if (threadIdx.x == 32 * kEW0) TCP_MARK(5, pid + 1);

@@ -222,7 +222,7 @@ tcr_resblock_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         tc2::drain_add<16>(tmem_base + lane_off + buf * kNA + (uint32_t)(cs * 16), acc);
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
-        if (lane == 0) tcp::mbar_arrive_cluster(acc_empty_leader + 8u * buf);
+        if (lane == 0) tcp::mbar_arrive_cluster_relaxed(acc_empty_leader + 8u * buf);
       }
       // ---- conv a result -> bias, ELU, split -> K-major operand of conv b: channels 16cs .. 16cs+15 of row `row` ----------
       {
