@@ -340,7 +340,8 @@ def run_b200(args, rank, world, local_rank):
     # measured DRAM traffic (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum per audio-second of the profiled
     # launches, profiles/traffic.json) per average launch of this kernel
     have = [k for k in grp["kinds"] if traffic_tab.get(k, {}).get("dram_bytes_per_audio_s") is not None]
-    traffic = (sum(traffic_tab[k]["dram_bytes_per_audio_s"] for k in have) * audio_per_step * args.steps / kcnt) if have else None
+    # (a layer kind that runs once per transformer layer has 8 launches per step, each over the whole batch)
+    traffic = (sum(traffic_tab[k]["dram_bytes_per_audio_s"] * prof[k][1] for k in have) * audio_per_step / kcnt) if have else None
     roof.update({"traffic": traffic, "kernel": kind, "share_of_step": kms / sum(v[0] for v in prof.values()),
                  "avg_launch_ms": 1e3 * per_launch_s, "launches_per_step": kcnt / args.steps, "peak_source": peaks["src"]})
     if len(grp["kinds"]) > 1:
