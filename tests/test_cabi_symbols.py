@@ -50,3 +50,13 @@ def test_no_cpu_fallback_without_gpu():
     from tokenize_audio_b200.encoder import MimiB200Model
     with pytest.raises(_lib.MimiB200Error):
         MimiB200Model({}, device="cuda")
+
+
+def test_phase_constants_match_the_header():
+    """tokenize_audio_b200/_lib.py mirrors the MIMI_B200_PHASE_* values of include/mimi_b200.h."""
+    import os
+    import re
+    from tokenize_audio_b200 import _lib
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "mimi_b200.h")).read()
+    vals = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define MIMI_B200_PHASE_(\w+) (\d+)", hdr)}
+    assert vals == {"BEGIN": _lib.PHASE_BEGIN, "FRONT": _lib.PHASE_FRONT, "FINISH": _lib.PHASE_FINISH}
