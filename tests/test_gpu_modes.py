@@ -196,3 +196,67 @@ def test_front_door_and_string_outputs(b200_model):
         assert s_ == utils.codes_to_chars(w, 2048)
         assert len(s_) == w.size
     assert enc.encode_native_rate_batch([], 16000) == [] and enc.encode_to_strings([]) == []
+
+
+def test_item_ranges_on_two_streams_are_bit_identical(b200_model):
+    """encode() splits a batch of >= 8 items into two contiguous item ranges on side streams (the other range's kernels
+    fill the SMs a persistent grid's last tiles leave idle). Items are independent and a tile's arithmetic does not depend
+    on which items share its CTA pair, so codes and latents are bit-identical to the single-stream call."""
+    rng = np.random.default_rng(11)
+    lens = [int(v) for v in rng.integers(2000, 90000, size=13)]
+    x = np.zeros((13, 1, max(lens)), np.float32)
+    for i, n in enumerate(lens):
+        x[i, 0, :n] = synth.synth_speech(1700 + i, n)
+    xd = torch.from_numpy(x).cuda()
+    res = {}
+    keep = b200_model.streams
+    try:
+        for n_streams in (1, 2):
+            b200_model.streams = n_streams
+            for ragged in (False, True):
+                out, lat = b200_model.encode(xd, num_quantizers=32, valid_lengths=lens if ragged else None, return_latent=True)
+                torch.cuda.synchronize()
+                res[(n_streams, ragged)] = (out.audio_codes.cpu().numpy(), lat.cpu().numpy())
+    finally:
+        b200_model.streams = keep
+    for ragged in (False, True):
+        for i, n in enumerate(lens):
+            t = -(-n // 1920) if ragged else res[(1, ragged)][0].shape[2]
+            assert np.array_equal(res[(1, ragged)][0][i, :, :t], res[(2, ragged)][0][i, :, :t])
+            assert np.array_equal(res[(1, ragged)][1][i, :, :t], res[(2, ragged)][1][i, :, :t])
+
+
+def test_nothing_is_read_before_it_is_written(b200_model):
+    """The whole workspace is filled with NaN before each call: a plain encode, the phased wrapper (several front-end
+    groups) and the independent sub-batches must still return the clean result -- i.e. no kernel reads an activation,
+    halo row, length or tile-list entry that this call has not written. (Caught a wrong bf16 `lo` offset of the per-group
+    front-end launches that stale data from earlier calls had been masking.)"""
+    from tokenize_audio_b200.encoder import MimiEncoder
+    rng = np.random.default_rng(7)
+    clips = [synth.synth_speech(1000 + i, int(n)) for i, n in enumerate(rng.integers(3000, 60000, size=21))]
+    lens = [len(c) for c in clips]
+    x = np.zeros((21, 1, max(lens)), np.float32)
+    for i, c in enumerate(clips):
+        x[i, 0, : len(c)] = c
+    xd = torch.from_numpy(x).cuda()
+    clean = b200_model.encode(xd, num_quantizers=8, valid_lengths=lens).audio_codes.cpu().numpy()
+
+    def poison():
+        for w in b200_model._workspaces.values():
+            if w is not None:
+                w.view(torch.float32)[: w.numel() // 4].fill_(float("nan"))
+        torch.cuda.synchronize()
+
+    poison()
+    assert np.array_equal(b200_model.encode(xd, num_quantizers=8, valid_lengths=lens).audio_codes.cpu().numpy(), clean)
+    poison()
+    strict = b200_model.encode(xd, num_quantizers=8).audio_codes.cpu().numpy()
+    for i, n in enumerate(lens):
+        assert np.array_equal(strict[i, :, : -(-n // 1920)], clean[i, :, : -(-n // 1920)])
+    for kw, phased in ((dict(first_items=1), True), (dict(first_items=4), True), (dict(chunk_items=4), False)):
+        w = MimiEncoder(b200_model, num_quantizers=8, **kw)
+        w.phased = phased
+        poison()
+        res = w.encode_audio_batch(clips)
+        for i, a in enumerate(res):
+            assert np.array_equal(a, clean[i, :, : a.shape[1]]), f"{kw}: item {i}"

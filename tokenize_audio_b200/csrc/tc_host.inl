@@ -526,7 +526,9 @@ static int encode_tc(mimi_b200* h, const float* d_input, int B, long long N, int
       fp.x = d_input + (long long)b0 * N; fp.x_stride = N; fp.len = dlen[0] ? dlen[0] + b0 : nullptr; fp.uniform_len = maxlen[0];
       fp.B = nb;
       fp.mt_max = (maxlen[0] + f0::kAdv - 1) / f0::kAdv;
-      fp.out_hi = ws + p.s_h1.hi + (long long)b0 * p.s_h1.item_stride; fp.out_lo = ws + p.s_h1.lo + (long long)b0 * p.s_h1.item_stride;
+      // (the lo array is bf16 in modes >= 7: the same ELEMENT offset is half as many floats)
+      fp.out_hi = ws + p.s_h1.hi + (long long)b0 * p.s_h1.item_stride;
+      fp.out_lo = ws + p.s_h1.lo + (long long)b0 * p.s_h1.item_stride / (h->mode >= 7 ? 2 : 1);
       fp.split_item_stride = p.s_h1.item_stride; fp.split_front = p.s_h1.front;
       fp.raw_out = raw_h1; fp.lo_bf16 = h->mode >= 7;
       const long long vt = (long long)fp.mt_max * nb;

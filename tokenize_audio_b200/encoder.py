@@ -66,8 +66,14 @@ class MimiB200Model:
         self.device = torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
         self._lib = _lib.load_library()
         self._lock = threading.Lock()
-        self._workspace: Optional[torch.Tensor] = None
+        self._workspaces: Dict[int, Optional[torch.Tensor]] = {}
         self._mode = self.DEFAULT_MODE
+        # encode() runs a batch of >= min_split_batch items as `streams` contiguous item ranges on side streams: every
+        # kernel is a persistent one-CTA-per-SM grid whose last tiles leave SMs idle, the other range's kernels fill them
+        # (+4-5 % on C2 / C3 / C4; three ranges are slower than one)
+        self.streams = 2
+        self.min_split_batch = 8
+        self._side_streams = []
         self.ragged_from_mask = False     # True: use padding_mask row sums as valid lengths (ragged mode)
         h = C.c_void_p()
         rc = self._lib.mimi_b200_create(C.byref(h), self.device.index)
@@ -165,11 +171,14 @@ class MimiB200Model:
             return torch.div(input_length + (FRAME_SIZE - 1), FRAME_SIZE, rounding_mode="floor")
         return int(self._lib.mimi_b200_encoded_frames(int(input_length)))
 
-    def _ws(self, nbytes: int) -> torch.Tensor:
-        if self._workspace is None or self._workspace.numel() < nbytes:
-            self._workspace = None
-            self._workspace = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
-        return self._workspace
+    def _ws(self, nbytes: int, slot: int = 0) -> torch.Tensor:
+        """Workspace `slot` (one per concurrent encode: slot 0 for plain calls, more when a wrapper runs item ranges on
+        several streams), grown on demand."""
+        w = self._workspaces.get(slot)
+        if w is None or w.numel() < nbytes:
+            self._workspaces[slot] = None
+            w = self._workspaces[slot] = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+        return w
 
     def reserve_workspace(self, batch: int, num_samples: int, num_quantizers: int = NUM_QUANTIZERS) -> int:
         """Pre-size the activation workspace for the largest ``[batch, 1, num_samples]`` input that will be
@@ -179,14 +188,14 @@ class MimiB200Model:
             nbytes = C.c_size_t()
             rc = self._lib.mimi_b200_workspace_bytes(self._h, int(batch), int(num_samples), int(num_quantizers), C.byref(nbytes))
             _lib.check(self._lib, self._h, rc, "mimi_b200_workspace_bytes")
-            self._ws(nbytes.value)
+            self._ws(nbytes.value + (1 << 20))       # + rounding slack for the per-stream split of encode()
         return int(nbytes.value)
 
     def encode(self, input_values: torch.Tensor, padding_mask: Optional[torch.Tensor] = None,
                num_quantizers: Optional[float] = None, encoder_past_key_values=None, padding_cache=None,
                use_streaming: Optional[bool] = None, return_dict: Optional[bool] = None,
                valid_lengths: Optional[Sequence[int]] = None, return_latent: bool = False,
-               staged_groups=None):
+               staged_groups=None, workspace_slot: int = 0):
         """Same contract as ``MimiModel.encode``. Extras (keyword-only in spirit): ``valid_lengths`` switches
         on ragged mode (skip work past each item's last kept frame), ``return_latent`` also returns the
         pre-quantisation latent ``[B,512,T]`` for parity checks. ``staged_groups`` = iterable of ``(b0, b1, land)``
@@ -234,10 +243,12 @@ class MimiB200Model:
                 nbytes = C.c_size_t()
                 rc = self._lib.mimi_b200_workspace_bytes(self._h, B, N, K, C.byref(nbytes))
                 _lib.check(self._lib, self._h, rc, "mimi_b200_workspace_bytes")
-                ws = self._ws(nbytes.value)
+                ws = self._ws(nbytes.value, workspace_slot)
                 stream = torch.cuda.current_stream(self.device).cuda_stream
                 lat_ptr = latent.data_ptr() if latent is not None else None
-                if staged_groups is None:
+                if staged_groups is None and self.streams > 1 and B >= self.min_split_batch and workspace_slot == 0:
+                    self._encode_multi_stream(x, B, N, vl, K, codes, latent)
+                elif staged_groups is None:
                     rc = self._lib.mimi_b200_encode(self._h, x.data_ptr(), B, N, vl, K, codes.data_ptr(), lat_ptr,
                                                     ws.data_ptr(), ws.numel(), stream)
                     _lib.check(self._lib, self._h, rc, "mimi_b200_encode")
@@ -263,6 +274,38 @@ class MimiB200Model:
         if return_dict is False:
             return tuple(out)
         return out
+
+    def _encode_multi_stream(self, x, B, N, vl, K, codes, latent) -> None:
+        """The batch as ``self.streams`` contiguous item ranges, each encoded on its own stream with its own workspace.
+        Items are independent, so the results are those of one call; the point is that every kernel is a persistent grid
+        with one CTA per SM whose last tiles leave SMs idle (15-30 % of a GEMM launch): the CTAs of the other range's
+        kernel fill them."""
+        n = self.streams
+        dev = self.device
+        main = torch.cuda.current_stream(dev)
+        if len(self._side_streams) < n:
+            self._side_streams = [torch.cuda.Stream(device=dev) for _ in range(n)]
+        bounds = [B * j // n for j in range(n + 1)]
+        sizes = []
+        for j in range(n):
+            nb = C.c_size_t()
+            rc = self._lib.mimi_b200_workspace_bytes(self._h, bounds[j + 1] - bounds[j], N, K, C.byref(nb))
+            _lib.check(self._lib, self._h, rc, "mimi_b200_workspace_bytes")
+            sizes.append((int(nb.value) + 1023) // 1024 * 1024)
+        ws = self._ws(sum(sizes))
+        off = 0
+        for j in range(n):
+            b0, b1 = bounds[j], bounds[j + 1]
+            st = self._side_streams[j]
+            st.wait_stream(main)
+            sub_vl = None if vl is None else (C.c_int64 * (b1 - b0))(*list(vl)[b0:b1])
+            rc = self._lib.mimi_b200_encode(
+                self._h, x[b0:].data_ptr(), b1 - b0, N, sub_vl, K, codes[b0:].data_ptr(),
+                latent[b0:].data_ptr() if latent is not None else None, ws.data_ptr() + off, sizes[j], st.cuda_stream)
+            _lib.check(self._lib, self._h, rc, "mimi_b200_encode")
+            off += sizes[j]
+        for j in range(n):
+            main.wait_stream(self._side_streams[j])
 
     # -- parity helpers --------------------------------------------------------------------------------
     @property
@@ -379,11 +422,15 @@ class MimiEncoder:
         # phased=True: one padded batch staged group by group under the running front end (mimi_b200_encode_phase);
         # False: independent sub-batches (the only choice for kernel generations without the fused front end)
         self.phased = True
+        # two phased item ranges on two streams: measured SLOWER end to end (23.4k vs 27k x RT: the second range's front end
+        # competes with the first range's main pipeline), kept as an experiment
+        self.two_ranges = False
         self.pack_threads = min(8, os.cpu_count() or 1)      # memcpy threads of mimi_b200_host_pack (1: torch copies)
         self._pinned: Optional[torch.Tensor] = None
         self._dev_in: Optional[torch.Tensor] = None
         self._pinned_codes: Optional[torch.Tensor] = None
         self._copy_stream: Optional[torch.cuda.Stream] = None
+        self._range_streams: List[torch.cuda.Stream] = []
         self._pool = None
         if stage_threads > 1:
             from concurrent.futures import ThreadPoolExecutor
@@ -479,9 +526,9 @@ class MimiEncoder:
     def encode_audio_batch(self, audio_arrays: List[np.ndarray], sample_rate: int = 24000) -> List[np.ndarray]:
         """REF/emilia-mimi/process_shard.py:88-140: pad to the longest, encode, trim item i to
         ceil(len_i / 1920) frames. With ``ragged=True`` (default) the padded tails are not computed and the
-        batch goes through the GPU as sub-batches of ``chunk_items`` items (staging of sub-batch j+1 overlaps
-        the encode of sub-batch j); the kept frames are the same either way. One device->host copy per
-        sub-batch instead of one per item."""
+        batch is staged group by group under the running front end (``mimi_b200_encode_phase``), as one or two item
+        ranges on their own streams; the kept frames are the same either way. One device->host copy per item range
+        instead of one per item."""
         if len(audio_arrays) == 0:
             return []
         if len(audio_arrays) == 1:
@@ -513,21 +560,37 @@ class MimiEncoder:
             main = torch.cuda.current_stream(dev)
             self._copy_stream.wait_stream(main)          # earlier readers of the landing buffer are done before it is rewritten
             zero_to = [min(N, -(-n // FRAME_SIZE) * FRAME_SIZE) for n in original_lengths]
-
-            def lander(b0, b1):
-                def land():
-                    self._fill(buf[b0:b1], audio_arrays[b0:b1], zero_to[b0:b1])
-                    with torch.cuda.stream(self._copy_stream):
-                        x[b0:b1].copy_(buf[b0:b1], non_blocking=True)
-                        landed = torch.cuda.Event()
-                        landed.record(self._copy_stream)
-                    main.wait_event(landed)
-                return land
-            groups = [(g[0], g[-1] + 1, lander(g[0], g[-1] + 1)) for g in self._front_groups(B, self.first_items)]
-            out = self.model.encode(input_values=x, padding_mask=None, num_quantizers=self.num_quantizers,
-                                    valid_lengths=original_lengths, staged_groups=groups)
+            # the batch as one or two contiguous item ranges, each a phased encode on its own stream and workspace: the
+            # second range's staging and front end run under the first range's main pipeline, and two kernels in flight
+            # fill the SMs that a persistent grid's last tiles leave idle
+            n_ranges = 2 if (self.two_ranges and self.model.streams > 1 and B >= 2 * self.model.min_split_batch) else 1
+            bounds = [B * j // n_ranges for j in range(n_ranges + 1)]
+            if len(self._range_streams) < n_ranges:
+                self._range_streams = [torch.cuda.Stream(device=dev) for _ in range(n_ranges)]
             hc = self._pinned_codes[: B * K * T].view(B, K, T)
-            hc.copy_(out.audio_codes, non_blocking=True)
+            for j in range(n_ranges):
+                r0, r1 = bounds[j], bounds[j + 1]
+                st = main if n_ranges == 1 else self._range_streams[j]
+                if st is not main:
+                    st.wait_stream(main)
+
+                def lander(b0, b1, st=st):
+                    def land():
+                        self._fill(buf[b0:b1], audio_arrays[b0:b1], zero_to[b0:b1])
+                        with torch.cuda.stream(self._copy_stream):
+                            x[b0:b1].copy_(buf[b0:b1], non_blocking=True)
+                            landed = torch.cuda.Event()
+                            landed.record(self._copy_stream)
+                        st.wait_event(landed)
+                    return land
+                groups = [(g[0], g[-1] + 1, lander(r0 + g[0], r0 + g[-1] + 1))
+                          for g in self._front_groups(r1 - r0, self.first_items)]
+                with torch.cuda.stream(st):
+                    out = self.model.encode(input_values=x[r0:r1], padding_mask=None, num_quantizers=self.num_quantizers,
+                                            valid_lengths=original_lengths[r0:r1], staged_groups=groups, workspace_slot=j)
+                    hc[r0:r1].copy_(out.audio_codes, non_blocking=True)
+                if st is not main:
+                    main.wait_stream(st)
             main.synchronize()
             arr = hc.numpy()
             return [arr[i, :, : int(np.ceil(n / frame_rate))].copy() for i, n in enumerate(original_lengths)]
