@@ -74,6 +74,7 @@ class MimiB200Model:
         self.streams = 2
         self.min_split_batch = 8
         self._side_streams = []
+        self._last_split = False
         self.ragged_from_mask = False     # True: use padding_mask row sums as valid lengths (ragged mode)
         h = C.c_void_p()
         rc = self._lib.mimi_b200_create(C.byref(h), self.device.index)
@@ -238,6 +239,7 @@ class MimiB200Model:
         codes = torch.empty((B, K, T), dtype=torch.int64, device=self.device)
         latent = torch.empty((B, 512, T), dtype=torch.float32, device=self.device) if return_latent else None
         self._last_B = B
+        self._last_split = False
         if B > 0 and N > 0:
             with self._lock, torch.cuda.device(self.device):
                 nbytes = C.c_size_t()
@@ -248,6 +250,7 @@ class MimiB200Model:
                 lat_ptr = latent.data_ptr() if latent is not None else None
                 if staged_groups is None and self.streams > 1 and B >= self.min_split_batch and workspace_slot == 0:
                     self._encode_multi_stream(x, B, N, vl, K, codes, latent)
+                    self._last_split = True
                 elif staged_groups is None:
                     rc = self._lib.mimi_b200_encode(self._h, x.data_ptr(), B, N, vl, K, codes.data_ptr(), lat_ptr,
                                                     ws.data_ptr(), ws.numel(), stream)
@@ -319,7 +322,10 @@ class MimiB200Model:
         _lib.check(self._lib, self._h, self._lib.mimi_b200_debug_set(self._h, key, value), "mimi_b200_debug_set")
 
     def debug_tap(self, which: int) -> torch.Tensor:
-        """Channels-last ``[B, rows, C]`` copy of an internal activation of the last encode call."""
+        """Channels-last ``[B, rows, C]`` copy of an internal activation of the last encode call (which must have run as
+        one item range: batches of ``min_split_batch`` items or more need ``model.streams = 1`` for that)."""
+        if self._last_split:
+            raise _lib.MimiB200Error("debug_tap: the last encode ran as several item ranges; set model.streams = 1 first")
         rows, ch = C.c_int64(), C.c_int()
         rc = self._lib.mimi_b200_debug_tap(self._h, which, None, 0, C.byref(rows), C.byref(ch), None)
         _lib.check(self._lib, self._h, rc, "mimi_b200_debug_tap")

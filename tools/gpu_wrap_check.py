@@ -1,3 +1,7 @@
+#!/usr/bin/env python3
+"""Diagnostic behind tests/test_gpu_modes.py::test_nothing_is_read_before_it_is_written: the workspace is re-allocated and
+filled with NaN before a plain encode and before phased wrapper calls with several front-end groups; prints the items whose
+codes differ from the clean result (run under gpurun)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
