@@ -15,9 +15,10 @@ clips, lengths, batches = bench.make_workload(0)
 nmax = max(len(c) for cl in clips for c in cl)
 model.reserve_workspace(64, nmax, 8)
 audio = sum(len(c) for cl in clips for c in cl) / 24000
-for chunk_items, threads, first, phased in [(16, 1, None, False), (16, 1, 16, True), (16, 8, 16, True), (16, 8, 8, True), (16, 8, 4, True), (16, 16, 8, True), (16, 8, 64, True)]:
+for chunk_items, threads, first, phased, two in [(16, 8, 8, True, False), (16, 8, 8, True, True), (16, 8, 4, True, True), (16, 8, 16, True, False), (16, 8, 8, True, False)]:
     w = MimiEncoder(model, ragged=True, num_quantizers=8, chunk_items=chunk_items, stage_threads=threads, first_items=first)
     w.phased = phased
+    w.two_ranges = two
     w.pack_threads = threads
     w.reserve(64, nmax)
     for i in range(3):
@@ -29,4 +30,4 @@ for chunk_items, threads, first, phased in [(16, 1, None, False), (16, 1, 16, Tr
         for i in range(8):
             w.encode_audio_batch(clips[i])
         best = min(best, time.perf_counter() - t)
-    print(f"phased={phased} chunk_items={chunk_items} threads={threads} first={first}: {1e3*best/8:.2f} ms/step  {audio/best:.0f} x RT", flush=True)
+    print(f"two_ranges={two} phased={phased} chunk_items={chunk_items} threads={threads} first={first}: {1e3*best/8:.2f} ms/step  {audio/best:.0f} x RT", flush=True)
