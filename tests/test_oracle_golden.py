@@ -31,6 +31,31 @@ def test_oracle_matches_reference_codes_and_latent(state_dict, name):
     np.testing.assert_allclose(np.stack(taps["seanet.out"])[0][:, :8], g["seanet_out_first"], rtol=0, atol=2e-4)
 
 
+@pytest.mark.parametrize("name,variant", [("mimi_c3_k8", None), ("mimi_c4_k32", None), ("mimi_ties_k32", "ties"),
+                                          ("mimi_heavy_k32", "heavy")])
+def test_oracle_matches_reference_at_full_sizes_and_on_adversarial_weights(state_dict, name, variant):
+    """BASELINE configs 3 and 4 at full length (30 s K=8, 15 s K=32), a codebook full of exact ties, and a heavy-tailed
+    second weight draw: the oracle against the real transformers.MimiModel outputs."""
+    g = load_golden(name)
+    sd = synth.variant_state_dict(variant) if variant else state_dict
+    assert synth.state_dict_digest(sd) == str(g["weights_digest"])
+    x = golden_input(g)
+    K = int(g["num_quantizers"])
+    taps = {}
+    codes = O.encode(sd, x, K, taps=taps)
+    ref = g["codes"].astype(np.int64)
+    assert (codes == ref).mean() >= 0.999
+    for b, k, t in np.argwhere(codes != ref):
+        first_bad = int(np.argmax(codes[b, :, t] != ref[b, :, t]))
+        assert k > first_bad or g["margins"][b, k, t] < 1e-3
+    lat = np.stack(taps["latent"])
+    assert np.linalg.norm(lat - g["latent"]) / np.linalg.norm(g["latent"]) < 1e-5
+    if variant == "ties":
+        assert ref.max() < 1024                       # every winner has a twin at index + 1024: the lower one is returned
+        assert (ref[:, [4, 8] + list(range(21, 32))] == 5).mean() > 0.9     # all-zero rows 5, 700, 1029, 1724: index 5
+        assert codes.max() < 1024
+
+
 def test_encoded_length_known_answers():
     g = load_golden("encoded_length")
     for n, t in zip(g["lengths"].tolist(), g["frames"].tolist()):

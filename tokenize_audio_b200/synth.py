@@ -186,3 +186,73 @@ def synth_speech(seed: int, n_samples: int, sr: int = SAMPLE_RATE) -> np.ndarray
     level = 10.0 ** (g.uniform(-20.0, -3.0) / 20.0)
     x = x / peak * level + 10.0 ** (-70.0 / 20.0) * g.standard_normal(n) * (pause > 0.5)
     return x.astype(np.float32)
+
+
+def variant_state_dict(kind: str) -> Dict[str, np.ndarray]:
+    """Adversarial weight draws for the parity tests (same key names / shapes as :func:`synth_state_dict`).
+
+    ``"ties"``  seed-0 weights whose codebooks are full of EXACT ties: in every codebook rows 1024..2047 are bitwise
+                copies of rows 0..1023 (embed_sum and cluster_usage both), so every winner has an identical twin at
+                index + 1024 and ``argmin`` must return the lower one (TF/models/mimi/modeling_mimi.py:1200-1201,
+                lowest index among equal minima); acoustic stages 3, 7 and 20..31 additionally hold all-zero rows
+                (dead entries, embed == 0) at indices 5, 700, 1029, 1724 in a codebook scaled x3, where the zero
+                vector is the nearest centroid for most frames and index 5 must win.
+    ``"heavy"`` seed-1 weights with heavy tails: Student-t (3 degrees of freedom) conv / linear weights at the variance
+                of the Gaussian draw, LayerScale 0.01 (the kyutai/mimi initial value), three x50 outlier output channels
+                in each strided conv D1..D3 and four x50 outlier rows in every fc1 -- wide dynamic range inside one
+                GEMM row, which is where a split-precision scheme loses bits first.
+    """
+    if kind == "ties":
+        sd = synth_state_dict(0)
+        half = CODEBOOK_SIZE // 2
+        for which, n_layers in (("semantic", NUM_SEMANTIC), ("acoustic", NUM_QUANTIZERS - NUM_SEMANTIC)):
+            for s in range(n_layers):
+                p = f"quantizer.{which}_residual_vector_quantizer.layers.{s}.codebook"
+                es, us = sd[f"{p}.embed_sum"].copy(), sd[f"{p}.cluster_usage"].copy()
+                if which == "acoustic" and (s in (3, 7) or s >= 20):
+                    es *= np.float32(3.0)
+                    es[[5, 700]] = np.float32(0.0)
+                    us[[5, 700]] = np.float32(1.0)
+                es[half:] = es[:half]
+                us[half:] = us[:half]
+                sd[f"{p}.embed_sum"], sd[f"{p}.cluster_usage"] = es, us
+        return sd
+    if kind == "heavy":
+        seed = 1
+        sd = synth_state_dict(seed)
+
+        def student(g, *shape):
+            return (g.standard_t(3.0, size=shape) / math.sqrt(3.0)).astype(np.float32)
+
+        for li, (name, cin, cout, k, _s) in enumerate(SEANET_CONVS):
+            g = _rng(seed, 11, li)
+            gain = 1.0 if li == 0 else 1.45
+            if name.endswith("block.3"):
+                gain = 0.8
+            w = student(g, cout, cin, k) * np.float32(gain / math.sqrt(cin * k))
+            if li == 0:
+                w *= np.float32(8.0)
+            if li in (3, 6, 9):
+                w[g.choice(cout, size=3, replace=False)] *= np.float32(50.0)
+            if li == 13:
+                w *= np.float32(HEAVY_OUT_GAIN)     # bring the SEANet output back to O(1) after the outlier channels
+            sd[f"{name}.conv.weight"] = w
+        for l in range(N_LAYERS):
+            g = _rng(seed, 12, l)
+            p = f"encoder_transformer.layers.{l}"
+            for nm in ("q_proj", "k_proj", "v_proj", "o_proj"):
+                sd[f"{p}.self_attn.{nm}.weight"] = student(g, HIDDEN, HIDDEN) * np.float32(1.0 / math.sqrt(HIDDEN))
+            sd[f"{p}.self_attn.q_proj.weight"] *= np.float32(2.0)
+            w1 = student(g, FFN, HIDDEN) * np.float32(1.0 / math.sqrt(HIDDEN))
+            w1[g.choice(FFN, size=4, replace=False)] *= np.float32(50.0)
+            sd[f"{p}.mlp.fc1.weight"] = w1
+            sd[f"{p}.mlp.fc2.weight"] = student(g, HIDDEN, FFN) * np.float32(1.0 / math.sqrt(FFN))
+            for nm in ("self_attn_layer_scale", "mlp_layer_scale"):
+                sd[f"{p}.{nm}.scale"] = np.full(HIDDEN, 0.01, np.float32)
+        return sd
+    raise ValueError(f"unknown weight variant '{kind}'")
+
+
+# the x50 outlier channels of the "heavy" variant lift the SEANet output rms to ~175 (intermediate activations reach 1e4);
+# the last conv is scaled by this constant (measured once, like RVQ_SIGMA0) so that the transformer stream and the RVQ see O(1)
+HEAVY_OUT_GAIN = 0.0085
