@@ -144,16 +144,29 @@ int mimi_b200_encode_phase(mimi_b200_t* h, int phase, int b0, int b1, const floa
 int mimi_b200_debug_tap(mimi_b200_t* h, int which, float* d_out, size_t out_capacity_floats,
                         int64_t* rows_per_item, int* channels, void* stream);
 
-/* Debug knobs (parity bisection only): key 0 = number of transformer layers to run (default 8),
-   key 1 = index of the last SEANet conv to run (default 13; smaller values stop the pipeline there and
-   leave d_codes untouched), key 2 = per-launch CUDA-event profiling on/off (resets the profile), key 3 =
-   compute mode: 3 (default) = mode 2 plus the fused 24 kHz front end (front_fused.cuh: L0 + ResBlock 1 in one
-   kernel); 2 = every GEMM-shaped layer on the persistent tcgen05 3xTF32 kernel (tc_gemm2.cuh),
-   1 = first-generation tcgen05 kernel for the wide layers (level 0 on FFMA), 0 = all-fp32 FFMA;
-   key 4 / key 5 = accuracy experiments on the persistent kernel: cross terms into the main accumulator (0/1),
-   k-blocks per accumulation chunk (0 = default 4); key 6 = plane-staged activations for k = G*stride convs
-   (tc2p_gemm_kernel; default 0); key 7 = next-tile L2 prefetch in the GEMM producer (default 0); key 8 = attention
-   kernel variant (2 = 8 warps x 4 queries, default; 3 = 16 warps x 2 queries). */
+/* Debug knobs (parity bisection and A/B measurements only; MimiB200Model.debug_set):
+     0  number of transformer layers to run (default 8)
+     1  index of the last SEANet conv to run (default 13; smaller values stop the pipeline there, on the fp32 FFMA path,
+        and leave d_codes untouched)
+     2  per-launch CUDA-event profiling on/off (resets the profile)
+     3  kernel generation ("mode"), default 7:
+          0  every layer on fp32 FFMA (exact-fp32 bisection baseline)
+          7  fused 24 kHz front end (front_fused.cuh) + CTA-pair tcgen05 GEMM (tc_gemm5.cuh; hi*hi and hi*lo on
+             kind::tf32, lo*hi on kind::f16 with bf16 lo parts) + tcgen05 attention + tensor-core RVQ
+          the other values (1..6, 8) are earlier / experimental generations kept for A/B, see DESIGN.md section 7
+     4  accuracy experiment: cross terms into the main accumulator (single-CTA GEMM generations)
+     5  accuracy experiment: k-blocks per accumulation chunk (0 = default 4)
+     6  plane-staged activations for k = G*stride convs (default 0)
+     7  next-tile L2 prefetch in the GEMM producer (default 0)
+     8  attention kernel: 4 = tcgen05 (default), 2 / 3 = fp32 SIMT variants (modes < 7 only)
+     9  pair tiles of 128 columns for layers with N >= value (0 = never, default)
+    10  1 = never flatten the row dimension of the linears across items
+    11  1 = k-blocks in linear order, 2 = tap-grouped with the channel panels innermost (default 0: grouped by tau mod s)
+    12  1 = the 24 kHz activation crosses HBM as raw fp32 (front end stores raw, D1 splits in shared memory)
+    13  1 = walk the mt_max x B tile grid instead of the compact tile lists of a ragged call
+    14  1 = full-size (fp32-sized) lo buffers in mode 7
+    15  1 = level-1 residual block as one kernel (tc_gemm6.cuh)
+    16  1 = first-draft one-thread-per-output resampler instead of resample_poly_kernel */
 int mimi_b200_debug_set(mimi_b200_t* h, int key, int value);
 
 /* Read and reset the per-launch profile gathered since profiling was switched on: for launch kind
@@ -201,6 +214,12 @@ int64_t mimi_b200_utf8_bytes_per_frame(int K, uint32_t unicode_offset, int codeb
 int mimi_b200_codes_to_utf8(mimi_b200_t* h, const int64_t* d_codes, int B, int K, int64_t T,
                             const int64_t* h_frames, uint32_t unicode_offset, int codebook_size,
                             uint8_t* d_out, int64_t out_stride, int64_t* h_out_len_opt, void* stream);
+
+/*
+ * codes int64 -> uint16, n elements of any shape (the `codes.astype(np.uint16)` storage format of
+ * REF/yodas2-mimi/process_shard.py:519-523, done before the device->host copy: 2 instead of 8 bytes per code cross PCIe).
+ */
+int mimi_b200_codes_pack_u16(mimi_b200_t* h, const int64_t* d_codes, int64_t n, uint16_t* d_out, void* stream);
 
 /*
  * Host-side staging helper of the wrapper (no device work): gathers n ragged fp32 clips into the rows of a (pinned)

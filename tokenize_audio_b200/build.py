@@ -17,7 +17,7 @@ NVCC_FLAGS = [
 def _sources():
     out = [os.path.join(HERE, "..", "include", "mimi_b200.h")]
     for f in sorted(os.listdir(CSRC)):
-        if f.endswith((".cu", ".cuh", ".h")):
+        if f.endswith((".cu", ".cuh", ".h", ".inl")):
             out.append(os.path.join(CSRC, f))
     return out
 
@@ -36,13 +36,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libmimi_b200.so (and there is no CPU fallback)")
-    tmp = LIB_PATH + ".tmp"
+    tmp = f"{LIB_PATH}.{os.getpid()}.tmp"       # pid-unique: two ranks building at once never share a half-written file
     extra = os.environ.get("MIMI_B200_NVCC_EXTRA", "").split()       # e.g. -DMIMI_TCP_DEBUG for tools/gpu_tcp_hang.py
     cmd = [nvcc, *NVCC_FLAGS, *extra, "-o", tmp, os.path.join(CSRC, "mimi_b200.cu")]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
+        if os.path.exists(tmp):
+            os.remove(tmp)
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
     os.replace(tmp, LIB_PATH)
     if verbose:

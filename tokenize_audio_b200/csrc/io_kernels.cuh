@@ -33,6 +33,116 @@ __global__ void __launch_bounds__(256) resample_kernel(const float* __restrict__
   y[(long long)b * out_stride + m] = acc;
 }
 
+// ---- polyphase form for small L*M (16 k, 48 k, 8 k, 32 k, 12 k -> 24 k) ----------------------------------------------
+// With n = (q + v)*M + r and m = q*L + phi the sum above is
+//     y[q*L + phi] = sum_r sum_v  xs_r[q + v] * g[r][v][phi],   xs_r[k] = x[k*M + r],  g[r][v][phi] = h[c + phi*M - (v*M + r)*L]
+// i.e. L*M plain stride-1 FIRs over the M de-interleaved input phases. A CTA stages the de-interleaved window of kQB output
+// blocks q in shared memory (coalesced loads, skewed by one word per 32 so that lanes 8 words apart hit different banks);
+// thread t owns Q = 8 consecutive blocks q and all L phases: per (r, v) it loads ONE new input sample and L taps (warp
+// broadcast) for L*Q FMAs out of a register sliding window -- 6 FMAs per shared-memory word at L = 3, so the FP32 pipe is
+// the bound, not the LSU. Results go back through shared memory and leave as coalesced float4 rows.
+// FP32 roofline, not HBM: 16 k -> 24 k spends 80 FMAs (68 on non-zero taps; zero taps pad each sub-filter to a multiple of 8) per
+// output sample for 6.7 bytes of traffic, i.e. 24 FLOP/B against the B200's ~11 FLOP/B fp32 ridge.
+namespace rsp {
+constexpr int kQ = 8;                 // output blocks per thread
+constexpr int kThreads = 128;
+constexpr int kQB = kQ * kThreads;    // output blocks per CTA
+__host__ __device__ inline int skew(int k) { return k + (k >> 5); }
+// floats of shared memory: taps [M][V][4] + de-interleaved window M * skew(kQB + V + kQ)
+__host__ __device__ inline size_t smem_floats(int L, int M, int V) {
+  const size_t xs = (size_t)M * (size_t)(skew(kQB + V + kQ) + 1);
+  const size_t out = (size_t)kQB * L;
+  return (size_t)M * V * 4 + (xs > out ? xs : out);
+}
+}  // namespace rsp
+
+template <int L, int M>
+__global__ void __launch_bounds__(rsp::kThreads) resample_poly_kernel(const float* __restrict__ x, long long in_stride,
+                                                                      const int* __restrict__ in_len,
+                                                                      const int* __restrict__ out_len,
+                                                                      const float* __restrict__ g,   // [M][V][4]
+                                                                      int V, int Vh, float* __restrict__ y,
+                                                                      long long out_stride) {
+  static_assert(L >= 1 && L <= 4, "phases per block");
+  extern __shared__ float sm[];
+  float* sg = sm;                                    // taps
+  float* sx = sm + (size_t)M * V * 4;                // window, later the output tile
+  const int xs_stride = rsp::skew(rsp::kQB + V + rsp::kQ) + 1;
+  const int b = blockIdx.y;
+  const long long q0 = (long long)blockIdx.x * rsp::kQB;
+  const int tid = threadIdx.x;
+  const int n_in = in_len[b], n_out = out_len[b];
+  const float* xb = x + (long long)b * in_stride;
+  for (int i = tid; i < M * V * 4; i += rsp::kThreads) sg[i] = g[i];
+  // window: input blocks k in [q0 - Vh, q0 - Vh + kQB + V), sample n = k*M + r; consecutive threads read consecutive n
+  const long long n_base = (q0 - Vh) * M;
+  const int span = (rsp::kQB + V) * M;
+  for (int t = tid; t < span; t += rsp::kThreads) {
+    const long long n = n_base + t;
+    const int k = t / M, r = t - k * M;
+    sx[r * xs_stride + rsp::skew(k)] = (n >= 0 && n < n_in) ? __ldg(xb + n) : 0.f;
+  }
+  __syncthreads();
+  float acc[L][rsp::kQ];
+#pragma unroll
+  for (int p = 0; p < L; ++p)
+#pragma unroll
+    for (int i = 0; i < rsp::kQ; ++i) acc[p][i] = 0.f;
+  const int kb = tid * rsp::kQ;                      // first window slot of this thread's block 0 at v = -Vh
+#pragma unroll
+  for (int r = 0; r < M; ++r) {
+    const float* xr = sx + r * xs_stride;
+    const float4* gr = reinterpret_cast<const float4*>(sg) + (size_t)r * V;
+    float w[rsp::kQ];
+#pragma unroll
+    for (int i = 0; i < rsp::kQ - 1; ++i) w[i] = xr[rsp::skew(kb + i)];
+    for (int v0 = 0; v0 < V; v0 += rsp::kQ) {        // V is a multiple of kQ (zero taps pad it)
+#pragma unroll
+      for (int s = 0; s < rsp::kQ; ++s) {
+        w[(s + rsp::kQ - 1) % rsp::kQ] = xr[rsp::skew(kb + v0 + s + rsp::kQ - 1)];
+        const float4 t4 = gr[v0 + s];
+        const float tp[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+        for (int p = 0; p < L; ++p)
+#pragma unroll
+          for (int i = 0; i < rsp::kQ; ++i) acc[p][i] = fmaf(w[(s + i) % rsp::kQ], tp[p], acc[p][i]);
+      }
+    }
+  }
+  __syncthreads();                                   // everyone is done with the window: reuse it as the output tile
+#pragma unroll
+  for (int i = 0; i < rsp::kQ; ++i)
+#pragma unroll
+    for (int p = 0; p < L; ++p) sx[(kb + i) * L + p] = acc[p][i];
+  __syncthreads();
+  const long long m0 = q0 * L;
+  float* yb = y + (long long)b * out_stride;
+  const int tile = rsp::kQB * L;
+  if ((out_stride & 3) == 0 && ((reinterpret_cast<uintptr_t>(yb) & 15) == 0)) {
+    for (int t = tid * 4; t < tile; t += rsp::kThreads * 4) {
+      const long long m = m0 + t;
+      if (m + 3 < out_stride) {
+        float4 o = *reinterpret_cast<const float4*>(sx + t);
+        if (m + 3 >= n_out) {
+          if (m >= n_out) o.x = 0.f;
+          if (m + 1 >= n_out) o.y = 0.f;
+          if (m + 2 >= n_out) o.z = 0.f;
+          o.w = 0.f;
+        }
+        *reinterpret_cast<float4*>(yb + m) = o;
+      } else {
+        for (int e = 0; e < 4; ++e)
+          if (m + e < out_stride) yb[m + e] = (m + e < n_out) ? sx[t + e] : 0.f;
+      }
+    }
+  } else {
+    for (int t = tid; t < tile; t += rsp::kThreads) {
+      const long long m = m0 + t;
+      if (m < out_stride) yb[m] = (m < n_out) ? sx[t] : 0.f;
+    }
+  }
+}
+
 // One thread per (item, frame, codebook): code point = offset + k*codebook_size + code, written as the
 // 1..4-byte UTF-8 form. byte_off[k] / bytes_per_frame are fixed per call because the host checked that no
 // codebook's code-point range straddles a UTF-8 length boundary.
@@ -73,6 +183,24 @@ __global__ void __launch_bounds__(256) codes_to_utf8_kernel(const Utf8Params p) 
     o[1] = (unsigned char)(0x80u | ((cp >> 12) & 0x3Fu));
     o[2] = (unsigned char)(0x80u | ((cp >> 6) & 0x3Fu));
     o[3] = (unsigned char)(0x80u | (cp & 0x3Fu));
+  }
+}
+
+// codes int64 -> uint16 (the `codes.astype(np.uint16)` of REF/yodas2-mimi/process_shard.py:519-523, before the D2H copy: a
+// quarter of the bytes cross PCIe). Grid-stride, 4 codes per thread: 32 B in, 8 B out.
+__global__ void __launch_bounds__(256) codes_pack_u16_kernel(const long long* __restrict__ codes, long long n,
+                                                             unsigned short* __restrict__ out) {
+  const long long stride = (long long)gridDim.x * blockDim.x * 4;
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+    if (i + 3 < n && (reinterpret_cast<uintptr_t>(out + i) & 7) == 0 && (reinterpret_cast<uintptr_t>(codes + i) & 15) == 0) {
+      const longlong2 a = *reinterpret_cast<const longlong2*>(codes + i);
+      const longlong2 b = *reinterpret_cast<const longlong2*>(codes + i + 2);
+      ushort4 o;
+      o.x = (unsigned short)a.x; o.y = (unsigned short)a.y; o.z = (unsigned short)b.x; o.w = (unsigned short)b.y;
+      *reinterpret_cast<ushort4*>(out + i) = o;
+    } else {
+      for (int e = 0; e < 4 && i + e < n; ++e) out[i + e] = (unsigned short)codes[i + e];
+    }
   }
 }
 

@@ -143,8 +143,10 @@ struct mimi_b200 {
   // scratch for resample / utf8 length arrays (device)
   int* dev_ints = nullptr;
   size_t dev_ints_cap = 0;
+  cudaEvent_t dev_ints_ev = nullptr;           // recorded behind the last kernel that reads dev_ints: the next call's upload
+                                               // (possibly on another stream) waits for it before overwriting the table
   // resampler taps cache: key (sr_in << 32 | sr_out)
-  struct Taps { float* d; int c, L, M; };
+  struct Taps { float* d; int c, L, M; float* g; int V, Vh; };   // g: polyphase table [M][V][4] (resample_poly_kernel) or nullptr
   std::map<unsigned long long, Taps> taps;
   // debug knobs and last plan
   int dbg_layers = MIMI_B200_NUM_LAYERS;
@@ -182,6 +184,7 @@ struct mimi_b200 {
   int tile_cnt[6] = {};
   int exp_fuse_res = 0;                        // debug_set key 15: level-1 residual block as one kernel (tc_gemm6.cuh, mode 7);
                                                // correct, saves a launch and the intermediate buffer, but not faster (2.9 vs 3.1 ms)
+  int exp_resample_simple = 0;                 // debug_set key 16: first-draft one-thread-per-output resampler (A/B of resample_poly_kernel)
   int exp_full_lo = 0;                         // debug_set key 14: mode 7 keeps full-size (fp32-sized) lo buffers
   int exp_no_tile_list = 0;                    // debug_set key 13: walk the mt_max x B grid and skip (the old schedule)
   int phase = 0, front_b0 = 0, front_b1 = 0;   // mimi_b200_encode_phase: which part of the pipeline the call in flight runs
@@ -203,6 +206,13 @@ struct mimi_b200 {
 };
 
 static std::string g_create_err;
+
+// create / load_weights / destroy switch to the handle's device and restore the caller's current device on return
+struct DeviceGuard {
+  int prev = -1;
+  DeviceGuard() { if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); } }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
 
 #define CUDA_TRY(h, expr)                                                                     \
   do {                                                                                        \
@@ -389,6 +399,12 @@ static void design_taps(int sr_in, int sr_out, std::vector<float>& taps, int& c,
 #include "tc_host.inl"
 #include "tc5_host.inl"
 
+// ratios the register-tiled polyphase resampler is instantiated for (16 k, 48 k, 8 k, 32 k, 12 k, 96 k -> 24 k, identity)
+static bool resample_poly_supported(int L, int M) {
+  return (L == 3 && M == 2) || (L == 1 && M == 2) || (L == 3 && M == 1) || (L == 3 && M == 4) || (L == 2 && M == 1) ||
+         (L == 1 && M == 4) || (L == 1 && M == 1);
+}
+
 static int utf8_len(unsigned cp) { return cp < 0x80u ? 1 : cp < 0x800u ? 2 : cp < 0x10000u ? 3 : 4; }
 
 // =====================================================================================================
@@ -419,12 +435,14 @@ int mimi_b200_create(mimi_b200_t** out, int device_ordinal) {
     return fail(nullptr, MIMI_B200_ERR_CUDA, cudaGetErrorString(e));
   if (prop.major != 10)
     return fail(nullptr, MIMI_B200_ERR_CUDA, "create: this library is built for sm_100a (B200) only");
+  DeviceGuard guard;
   mimi_b200* h = new mimi_b200();
   h->device = device_ordinal;
   h->num_sms = prop.multiProcessorCount;
   h->sync_debug = getenv("MIMI_B200_SYNC") != nullptr;
   if ((e = cudaSetDevice(device_ordinal)) != cudaSuccess) { delete h; return fail(nullptr, MIMI_B200_ERR_CUDA, cudaGetErrorString(e)); }
   for (int i = 0; i < kStageSlots; ++i) cudaEventCreateWithFlags(&h->stage_ev[i], cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&h->dev_ints_ev, cudaEventDisableTiming);
   cudaFuncSetAttribute(swa_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttSmemBytes);
   cudaFuncSetAttribute(swa_attention2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAtt2SmemBytes);
   cudaFuncSetAttribute(swa_attention3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAtt2SmemBytes);
@@ -473,6 +491,7 @@ int mimi_b200_create(mimi_b200_t** out, int device_ordinal) {
 
 void mimi_b200_destroy(mimi_b200_t* h) {
   if (!h) return;
+  DeviceGuard guard;
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   free_weights(h);
@@ -481,8 +500,9 @@ void mimi_b200_destroy(mimi_b200_t* h) {
     if (h->stage_ev[i]) cudaEventDestroy(h->stage_ev[i]);
   }
   if (h->dev_ints) cudaFree(h->dev_ints);
+  if (h->dev_ints_ev) cudaEventDestroy(h->dev_ints_ev);
   for (cudaEvent_t e : h->prof_pool) cudaEventDestroy(e);
-  for (auto& kv : h->taps) cudaFree(kv.second.d);
+  for (auto& kv : h->taps) { cudaFree(kv.second.d); if (kv.second.g) cudaFree(kv.second.g); }
   delete h;
 }
 
@@ -504,6 +524,7 @@ int mimi_b200_debug_set(mimi_b200_t* h, int key, int value) {
   else if (key == 13) h->exp_no_tile_list = value != 0;
   else if (key == 14) h->exp_full_lo = value != 0;
   else if (key == 15) h->exp_fuse_res = value != 0;
+  else if (key == 16) h->exp_resample_simple = value != 0;
   else return fail(h, MIMI_B200_ERR_ARG, "debug_set: unknown key");
   return MIMI_B200_OK;
 }
@@ -527,6 +548,7 @@ int mimi_b200_profile_read(mimi_b200_t* h, int max_ids, double* sum_ms, int64_t*
 
 int mimi_b200_load_weights(mimi_b200_t* h, const mimi_b200_weights_t* w) {
   if (!h || !w) return fail(h, MIMI_B200_ERR_ARG, "load_weights: NULL argument");
+  DeviceGuard guard;
   CUDA_TRY(h, cudaSetDevice(h->device));
   free_weights(h);
   for (int i = 0; i < MIMI_B200_NUM_CONVS; ++i)
@@ -1217,17 +1239,46 @@ int mimi_b200_resample(mimi_b200_t* h, const float* d_in, int64_t in_stride, con
     float* d = nullptr;
     CUDA_TRY(h, cudaMalloc((void**)&d, taps.size() * sizeof(float)));
     CUDA_TRY(h, cudaMemcpy(d, taps.data(), taps.size() * sizeof(float), cudaMemcpyHostToDevice));
-    tp = {d, c, L, M};
+    tp = {d, c, L, M, nullptr, 0, 0};
+    if (resample_poly_supported(L, M)) {
+      // polyphase table g[r][v + Vh][phi] = h[c + phi*M - (v*M + r)*L] (zero outside the prototype), V padded to 8
+      const int Vh = (c + L * M + L * M - 1) / (L * M);
+      const int V = (2 * Vh + 1 + rsp::kQ - 1) / rsp::kQ * rsp::kQ;
+      std::vector<float> g((size_t)M * V * 4, 0.f);
+      for (int r = 0; r < M; ++r)
+        for (int vv = 0; vv < V; ++vv)
+          for (int phi = 0; phi < L; ++phi) {
+            const long long idx = (long long)c + (long long)phi * M - ((long long)(vv - Vh) * M + r) * L;
+            if (idx >= 0 && idx <= 2ll * c) g[((size_t)r * V + vv) * 4 + phi] = taps[(size_t)idx];
+          }
+      CUDA_TRY(h, cudaMalloc((void**)&tp.g, g.size() * sizeof(float)));
+      CUDA_TRY(h, cudaMemcpy(tp.g, g.data(), g.size() * sizeof(float), cudaMemcpyHostToDevice));
+      tp.V = V; tp.Vh = Vh;
+    }
     h->taps[key] = tp;
   } else {
     tp = it->second;
   }
   int rc;
   if ((rc = ensure_dev_ints(h, v.size()))) return rc;
+  CUDA_TRY(h, cudaStreamWaitEvent(st, h->dev_ints_ev, 0));      // the previous reader of the table (any stream) is done
   if ((rc = stage_ints(h, v, h->dev_ints, st))) return rc;
-  dim3 grid((unsigned)((out_stride + 255) / 256), B);
-  resample_kernel<<<grid, 256, 0, st>>>(d_in, in_stride, h->dev_ints, h->dev_ints + B, tp.d, tp.c, tp.L, tp.M, d_out, out_stride);
+  if (tp.g && !h->exp_resample_simple) {
+    const long long qblocks = (out_stride + tp.L - 1) / tp.L;
+    dim3 grid((unsigned)((qblocks + rsp::kQB - 1) / rsp::kQB), B);
+    const size_t smem = rsp::smem_floats(tp.L, tp.M, tp.V) * sizeof(float);
+#define MIMI_RSP(LL, MM)                                                                                                  \
+  if (tp.L == LL && tp.M == MM)                                                                                           \
+    resample_poly_kernel<LL, MM><<<grid, rsp::kThreads, smem, st>>>(d_in, in_stride, h->dev_ints, h->dev_ints + B, tp.g, tp.V, \
+                                                                     tp.Vh, d_out, out_stride);
+    MIMI_RSP(3, 2) MIMI_RSP(1, 2) MIMI_RSP(3, 1) MIMI_RSP(3, 4) MIMI_RSP(2, 1) MIMI_RSP(1, 4) MIMI_RSP(1, 1)
+#undef MIMI_RSP
+  } else {
+    dim3 grid((unsigned)((out_stride + 255) / 256), B);
+    resample_kernel<<<grid, 256, 0, st>>>(d_in, in_stride, h->dev_ints, h->dev_ints + B, tp.d, tp.c, tp.L, tp.M, d_out, out_stride);
+  }
   h->launches++;
+  CUDA_TRY(h, cudaEventRecord(h->dev_ints_ev, st));
   CUDA_TRY(h, cudaGetLastError());
   return MIMI_B200_OK;
 }
@@ -1270,6 +1321,7 @@ int mimi_b200_codes_to_utf8(mimi_b200_t* h, const int64_t* d_codes, int B, int K
     }
     int rc;
     if ((rc = ensure_dev_ints(h, v.size()))) return rc;
+    CUDA_TRY(h, cudaStreamWaitEvent(st, h->dev_ints_ev, 0));
     if ((rc = stage_ints(h, v, h->dev_ints, st))) return rc;
     p.frames = h->dev_ints;
   }
@@ -1280,6 +1332,22 @@ int mimi_b200_codes_to_utf8(mimi_b200_t* h, const int64_t* d_codes, int B, int K
   if (!d_codes || !d_out) return fail(h, MIMI_B200_ERR_ARG, "codes_to_utf8: NULL device pointer");
   dim3 grid((unsigned)((maxfr * K + 255) / 256), B);
   codes_to_utf8_kernel<<<grid, 256, 0, st>>>(p);
+  h->launches++;
+  if (h_frames) CUDA_TRY(h, cudaEventRecord(h->dev_ints_ev, st));
+  CUDA_TRY(h, cudaGetLastError());
+  return MIMI_B200_OK;
+}
+
+int mimi_b200_codes_pack_u16(mimi_b200_t* h, const int64_t* d_codes, int64_t n, uint16_t* d_out, void* stream) {
+  if (!h) return MIMI_B200_ERR_ARG;
+  if (n < 0) return fail(h, MIMI_B200_ERR_ARG, "codes_pack_u16: bad count");
+  if (n == 0) return MIMI_B200_OK;
+  if (!d_codes || !d_out) return fail(h, MIMI_B200_ERR_ARG, "codes_pack_u16: NULL device pointer");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long quads = (n + 3) / 4;
+  const unsigned blocks = (unsigned)std::min<long long>((quads + 255) / 256, 148 * 16);
+  codes_pack_u16_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const long long*>(d_codes), n, d_out);
   h->launches++;
   CUDA_TRY(h, cudaGetLastError());
   return MIMI_B200_OK;

@@ -181,7 +181,7 @@ class MimiB200Model:
             w = self._workspaces[slot] = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
         return w
 
-    def reserve_workspace(self, batch: int, num_samples: int, num_quantizers: int = NUM_QUANTIZERS) -> int:
+    def reserve_workspace(self, batch: int, num_samples: int, num_quantizers: int = NUM_QUANTIZERS, slot: int = 0) -> int:
         """Pre-size the activation workspace for the largest ``[batch, 1, num_samples]`` input that will be
         encoded, so no later call has to grow it (a multi-GB device allocation in the middle of a shard).
         Returns the size in bytes."""
@@ -189,21 +189,22 @@ class MimiB200Model:
             nbytes = C.c_size_t()
             rc = self._lib.mimi_b200_workspace_bytes(self._h, int(batch), int(num_samples), int(num_quantizers), C.byref(nbytes))
             _lib.check(self._lib, self._h, rc, "mimi_b200_workspace_bytes")
-            self._ws(nbytes.value + (1 << 20))       # + rounding slack for the per-stream split of encode()
+            self._ws(nbytes.value + (1 << 20), slot)       # + rounding slack for the per-stream split of encode()
         return int(nbytes.value)
 
     def encode(self, input_values: torch.Tensor, padding_mask: Optional[torch.Tensor] = None,
                num_quantizers: Optional[float] = None, encoder_past_key_values=None, padding_cache=None,
                use_streaming: Optional[bool] = None, return_dict: Optional[bool] = None,
                valid_lengths: Optional[Sequence[int]] = None, return_latent: bool = False,
-               staged_groups=None, workspace_slot: int = 0):
+               staged_groups=None, workspace_slot: int = 0, on_front_done=None):
         """Same contract as ``MimiModel.encode``. Extras (keyword-only in spirit): ``valid_lengths`` switches
         on ragged mode (skip work past each item's last kept frame), ``return_latent`` also returns the
         pre-quantisation latent ``[B,512,T]`` for parity checks. ``staged_groups`` = iterable of ``(b0, b1, land)``
         partitioning ``[0, B)`` in order: ``input_values`` is a device buffer still being filled, and ``land()`` is
         called right before the front end of items ``[b0, b1)`` is launched -- it stages those items (fill, H2D, make the
         current stream wait for the copy). The GPU then works on the first groups while the host stages the later
-        ones (``mimi_b200_encode_phase``); the result is that of a plain call on the complete buffer."""
+        ones (``mimi_b200_encode_phase``); the result is that of a plain call on the complete buffer. ``on_front_done()``
+        is called once the last reader of ``input_values`` (the front end) has been queued."""
         if encoder_past_key_values is not None or padding_cache is not None or use_streaming:
             raise NotImplementedError("streaming / cache arguments are not supported (the reference scripts never pass them)")
         K = NUM_QUANTIZERS if num_quantizers is None else num_quantizers
@@ -270,6 +271,8 @@ class MimiB200Model:
                         nxt = b1
                     if nxt != B:
                         raise ValueError("staged_groups must partition [0, B) in order")
+                    if on_front_done is not None:
+                        on_front_done()         # every reader of input_values has been queued: the caller may record an event
                     phase(_lib.PHASE_FINISH, 0, 0)
         out = MimiEncoderOutput(codes, None, None)
         if return_latent:
@@ -400,12 +403,46 @@ class EncodecFeatureExtractorLite:
         return {"input_values": iv, "padding_mask": pm}
 
 
+class _Staging:
+    """One slot of the wrapper's double-buffered staging: pinned input rows, their device landing buffer, a pinned
+    result buffer, and the events that say when each may be reused."""
+
+    def __init__(self):
+        self.pinned: Optional[torch.Tensor] = None         # fp32 samples (pinned host)
+        self.dev_in: Optional[torch.Tensor] = None         # same size, device
+        self.pinned_out: Optional[torch.Tensor] = None     # bytes (pinned host): codes int64 / uint16 or UTF-8
+        self.h2d_done: Optional[torch.cuda.Event] = None   # last H2D copy out of `pinned` has completed
+        self.front_done: Optional[torch.cuda.Event] = None  # last reader of `dev_in` (the front end) has completed
+        self.pending: Optional["PendingBatch"] = None      # result not collected yet: `pinned_out` is still in use
+
+
+class PendingBatch:
+    """Handle returned by :meth:`MimiEncoder.submit`; pass it to :meth:`MimiEncoder.result`."""
+
+    def __init__(self, slot, done, view, lengths, frames, fmt, extra=None):
+        self._slot, self._done, self._view = slot, done, view
+        self.lengths, self.frames, self.format, self._extra = lengths, frames, fmt, extra
+        self._consumed = False
+
+    def ready(self) -> bool:
+        return self._done is None or self._done.query()
+
+
 class MimiEncoder:
     """Same methods as the reference's ``MimiEncoder`` wrapper (REF/emilia-mimi/process_shard.py:50-140).
 
     ``model`` may be a :class:`MimiB200Model`, a state dict, a checkpoint path, or a loaded
     ``transformers.MimiModel`` whose weights are taken over. ``num_quantizers=None`` returns all 32
-    codebooks like the reference (whose callers then slice ``[:8]``); pass 8 to compute only those."""
+    codebooks like the reference (whose callers then slice ``[:8]``); pass 8 to compute only those.
+
+    Thread safety: every public method takes the wrapper's lock, so one instance may be shared by the worker threads of
+    REF/yodas2-mimi/process_shard.py:690-717 (calls are serialised; the staging buffers are shared state).
+
+    Pipelined use: ``submit()`` stages a batch and queues its GPU work without waiting, ``result()`` collects it;
+    ``encode_stream(batches)`` keeps two batches in flight so that the staging of batch i+1 and the device->host copy of
+    batch i-1 run under the kernels of batch i. ``encode_audio_batch`` is ``result(submit(...))``."""
+
+    DEPTH = 2
 
     def __init__(self, model, device: str = "cuda", ragged: bool = True, num_quantizers: Optional[int] = None,
                  chunk_items: int = 16, stage_threads: int = 1, first_items: Optional[int] = None):
@@ -428,36 +465,59 @@ class MimiEncoder:
         # phased=True: one padded batch staged group by group under the running front end (mimi_b200_encode_phase);
         # False: independent sub-batches (the only choice for kernel generations without the fused front end)
         self.phased = True
-        # two phased item ranges on two streams: measured SLOWER end to end (23.4k vs 27k x RT: the second range's front end
-        # competes with the first range's main pipeline), kept as an experiment
-        self.two_ranges = False
-        self.pack_threads = min(8, os.cpu_count() or 1)      # memcpy threads of mimi_b200_host_pack (1: torch copies)
-        self._pinned: Optional[torch.Tensor] = None
-        self._dev_in: Optional[torch.Tensor] = None
-        self._pinned_codes: Optional[torch.Tensor] = None
+        # memcpy threads of mimi_b200_host_pack (1: torch copies). With one process per GPU every rank has its own pool:
+        # never more threads than this rank's share of the host cores (8 ranks x 8 threads on 32 cores cost 9 % at 8 GPUs)
+        ranks_here = int(os.environ.get("LOCAL_WORLD_SIZE") or os.environ.get("WORLD_SIZE") or 1)
+        self.pack_threads = max(1, min(8, (os.cpu_count() or 1) // max(1, ranks_here)))
+        # every staging slot encodes on its own stream with its own workspace: the kernels of two batches in flight
+        # interleave on the GPU, and the SMs that the last tiles of one batch's persistent kernels leave idle run the other's
+        # (what MimiB200Model.encode does with two item ranges of ONE resident batch). Costs a second workspace.
+        self.slot_streams = True
+        self._slot_stream: List[Optional[torch.cuda.Stream]] = [None] * self.DEPTH
+        self._lock = threading.RLock()
+        self._slots = [_Staging() for _ in range(self.DEPTH)]
+        self._cur = 0
         self._copy_stream: Optional[torch.cuda.Stream] = None
-        self._range_streams: List[torch.cuda.Stream] = []
         self._pool = None
         if stage_threads > 1:
             from concurrent.futures import ThreadPoolExecutor
             self._pool = ThreadPoolExecutor(max_workers=int(stage_threads), thread_name_prefix="mimi-stage")
 
+    # -- staging buffers -------------------------------------------------------------------------------------------
     def reserve(self, batch: int, max_samples: int) -> None:
         """Pre-size the pinned staging buffers (and the model workspace) for batches of up to ``batch`` items
         of up to ``max_samples`` samples, so that no later call has to pin fresh host memory (tens of ms)."""
         K = NUM_QUANTIZERS if self.num_quantizers is None else int(self.num_quantizers)
-        self._grow_pinned(batch * max_samples, batch * K * (-(-max_samples // FRAME_SIZE)))
-        self.model.reserve_workspace(batch, max_samples, K)
+        with self._lock:
+            for j, slot in enumerate(self._slots):
+                self._grow(slot, batch * max_samples, batch * K * (-(-max_samples // FRAME_SIZE)) * 8)
+                if j == 0 or self.slot_streams:
+                    self.model.reserve_workspace(batch, max_samples, K, slot=j)
 
-    def _grow_pinned(self, samples: int, codes: int) -> None:
-        if self._pinned is None or self._pinned.numel() < samples:
-            self._pinned = self._dev_in = None
-            self._pinned = torch.empty(max(int(samples * 1.25), 1), dtype=torch.float32).pin_memory()
+    def _grow(self, slot: _Staging, samples: int, out_bytes: int) -> None:
+        if slot.pinned is None or slot.pinned.numel() < samples:
+            if slot.h2d_done is not None:
+                slot.h2d_done.synchronize()
+            if slot.front_done is not None:
+                slot.front_done.synchronize()
+            slot.pinned = slot.dev_in = None
+            slot.pinned = torch.empty(max(int(samples * 1.25), 1), dtype=torch.float32).pin_memory()
             # device-side landing buffer of the same size: no allocator traffic on the hot path
-            self._dev_in = torch.empty(self._pinned.numel(), dtype=torch.float32, device=self.model.device)
-        if self._pinned_codes is None or self._pinned_codes.numel() < codes:
-            self._pinned_codes = None
-            self._pinned_codes = torch.empty(max(int(codes * 1.25), 1), dtype=torch.int64).pin_memory()
+            slot.dev_in = torch.empty(slot.pinned.numel(), dtype=torch.float32, device=self.model.device)
+        if slot.pinned_out is None or slot.pinned_out.numel() < out_bytes:
+            slot.pinned_out = None
+            slot.pinned_out = torch.empty(max(int(out_bytes * 1.25), 16), dtype=torch.uint8).pin_memory()
+
+    def _next_slot(self) -> _Staging:
+        slot = self._slots[self._cur]
+        slot.index = self._cur
+        self._cur = (self._cur + 1) % self.DEPTH
+        if slot.pending is not None and not slot.pending._consumed:
+            raise _lib.MimiB200Error(f"more than {self.DEPTH} batches in flight: collect an earlier submit() with result() first")
+        slot.pending = None
+        if slot.h2d_done is not None:
+            slot.h2d_done.synchronize()       # the previous user's copies have left the pinned rows
+        return slot
 
     @staticmethod
     def _sub_batches(B: int, chunk_items: int, first_items: Optional[int] = None) -> List[List[int]]:
@@ -472,9 +532,6 @@ class MimiEncoder:
     def _check_rate(self, sample_rate: int) -> None:
         if sample_rate != self.feature_extractor.sampling_rate:
             self.feature_extractor(raw_audio=np.zeros(1, np.float32), sampling_rate=sample_rate)   # raises ValueError
-
-    def _pinned_view(self, offset: int, B: int, N: int) -> torch.Tensor:
-        return self._pinned[offset: offset + B * N].view(B, 1, N)
 
     def _fill(self, buf: torch.Tensor, audio_arrays: Sequence[np.ndarray], zero_to: Sequence[int]) -> None:
         """fp32 cast + right zero-padding of every item into the pinned ``[B,1,N]`` view (what
@@ -509,97 +566,172 @@ class MimiEncoder:
         else:
             list(self._pool.map(one, range(len(audio_arrays))))
 
-    def _stage(self, audio_arrays: Sequence[np.ndarray], sample_rate: int) -> torch.Tensor:
+    def _streams(self):
+        dev = self.model.device
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        return torch.cuda.current_stream(dev), self._copy_stream
+
+    def _land(self, slot: _Staging, buf: torch.Tensor, x: torch.Tensor, audio_arrays, zero_to, b0: int, b1: int,
+              consumer: torch.cuda.Stream) -> None:
+        """Stage items [b0, b1): fill their pinned rows, copy them to the device on the copy stream, make ``consumer``
+        wait for the copy."""
+        self._fill(buf[b0:b1], audio_arrays[b0:b1], zero_to[b0:b1])
+        with torch.cuda.stream(self._copy_stream):
+            x[b0:b1].copy_(buf[b0:b1], non_blocking=True)
+            landed = torch.cuda.Event()
+            landed.record(self._copy_stream)
+        slot.h2d_done = landed
+        consumer.wait_event(landed)
+
+    def _stage(self, slot: _Staging, audio_arrays: Sequence[np.ndarray], sample_rate: int) -> torch.Tensor:
         """One pinned staging buffer and one H2D copy -> ``input_values [B,1,N]`` on the device. The
         ``padding_mask`` is never shipped: the model ignores it and the lengths are known here."""
         self._check_rate(sample_rate)
         B = len(audio_arrays)
         N = max(len(a) for a in audio_arrays)
-        self._grow_pinned(B * N, 0)
-        buf = self._pinned_view(0, B, N)
-        self._fill(buf, audio_arrays, [N] * B)
-        x = self._dev_in[: B * N].view(B, 1, N)
-        x.copy_(buf, non_blocking=True)
+        self._grow(slot, B * N, 0)
+        main, copy = self._streams()
+        if slot.front_done is not None:
+            copy.wait_event(slot.front_done)     # the previous reader of the landing buffer is done
+        buf = slot.pinned[: B * N].view(B, 1, N)
+        x = slot.dev_in[: B * N].view(B, 1, N)
+        self._land(slot, buf, x, list(audio_arrays), [N] * B, 0, B, main)
         return x
 
+    # -- the reference's two methods ------------------------------------------------------------------------------------
     def encode_audio_chunk(self, audio_array: np.ndarray, sample_rate: int = 24000) -> np.ndarray:
         """REF/emilia-mimi/process_shard.py:63-86: one utterance -> codes ``[K, T]`` (numpy int64)."""
-        with torch.no_grad():
-            x = self._stage([audio_array], sample_rate)
-            out = self.model.encode(x, None, num_quantizers=self.num_quantizers)
-            return out.audio_codes.cpu().numpy()[0]
+        with self._lock:
+            return self.result(self.submit([audio_array], sample_rate))[0]
 
-    def encode_audio_batch(self, audio_arrays: List[np.ndarray], sample_rate: int = 24000) -> List[np.ndarray]:
+    def encode_audio_batch(self, audio_arrays: List[np.ndarray], sample_rate: int = 24000,
+                           dtype=np.int64) -> List[np.ndarray]:
         """REF/emilia-mimi/process_shard.py:88-140: pad to the longest, encode, trim item i to
         ceil(len_i / 1920) frames. With ``ragged=True`` (default) the padded tails are not computed and the
-        batch is staged group by group under the running front end (``mimi_b200_encode_phase``), as one or two item
-        ranges on their own streams; the kept frames are the same either way. One device->host copy per item range
-        instead of one per item."""
+        batch is staged group by group under the running front end (``mimi_b200_encode_phase``); the kept frames are the
+        same either way. One device->host copy per batch instead of one per item. ``dtype=np.uint16`` returns the
+        storage format of REF/yodas2-mimi/process_shard.py:519-523 (cast on the GPU, a quarter of the D2H bytes)."""
         if len(audio_arrays) == 0:
             return []
-        if len(audio_arrays) == 1:
-            return [self.encode_audio_chunk(audio_arrays[0], sample_rate)]
-        frame_rate = sample_rate / 12.5
-        original_lengths = [len(a) for a in audio_arrays]
-        with torch.no_grad():
-            if not self.ragged:
-                x = self._stage(audio_arrays, sample_rate)
-                out = self.model.encode(input_values=x, padding_mask=None, num_quantizers=self.num_quantizers)
-                codes = out.audio_codes.cpu().numpy()
-                return [codes[i, :, : int(np.ceil(n / frame_rate))] for i, n in enumerate(original_lengths)]
+        fmt = "uint16" if np.dtype(dtype) == np.uint16 else "int64"
+        with self._lock:            # submit + result as one step: concurrent callers never exceed the staging depth
+            return self.result(self.submit(audio_arrays, sample_rate, fmt))
+
+    # -- pipelined API ---------------------------------------------------------------------------------------------
+    def submit(self, audio_arrays: List[np.ndarray], sample_rate: int = 24000, fmt: str = "int64",
+               num_codebooks: Optional[int] = None, codebook_size: int = 2048, unicode_offset: int = 0xE000) -> PendingBatch:
+        """Stage ``audio_arrays`` (host numpy clips at 24 kHz), queue the encode and the device->host copy of the result on
+        the current stream, and return without waiting. ``fmt``: ``"int64"`` (``encode_audio_batch``'s arrays),
+        ``"uint16"`` or ``"utf8"`` (``codes_to_chars`` strings of the first ``num_codebooks`` codebooks). At most
+        ``DEPTH`` batches may be uncollected."""
+        from . import utils
+        if fmt not in ("int64", "uint16", "utf8"):
+            raise ValueError(f"unknown result format '{fmt}'")
+        with self._lock, torch.no_grad():
             self._check_rate(sample_rate)
             B = len(audio_arrays)
+            lengths = [len(a) for a in audio_arrays]
             K = NUM_QUANTIZERS if self.num_quantizers is None else int(self.num_quantizers)
-            if not (self.phased and self.model.supports_phased):
-                return self._encode_sub_batched(audio_arrays, original_lengths, K, frame_rate)
-            # One padded [B,1,N] batch, exactly the reference's, staged group by group: the 24 kHz front end (the only
-            # part where items are independent) starts on group g as soon as its samples have landed while the host is
-            # still filling group g+1; everything after the front end runs once over the whole batch.
-            N = max(original_lengths)
+            if fmt == "utf8":
+                K = int(num_codebooks) if num_codebooks is not None else min(K, 8)
+                utils.validate_unicode_offset(unicode_offset, K, codebook_size)
+            if B == 0:
+                return PendingBatch(None, None, None, [], [], fmt)
+            slot = self._next_slot()
+            caller, copy = self._streams()
+            main, ws_slot = caller, 0
+            if self.slot_streams:
+                if self._slot_stream[slot.index] is None:
+                    self._slot_stream[slot.index] = torch.cuda.Stream(device=self.model.device)
+                main, ws_slot = self._slot_stream[slot.index], slot.index
+                main.wait_stream(caller)
+            frames = [-(-n // FRAME_SIZE) for n in lengths]
+            N = max(lengths)
             T = -(-N // FRAME_SIZE)
-            self._grow_pinned(B * N, B * K * T)
-            buf = self._pinned_view(0, B, N)
-            x = self._dev_in[: B * N].view(B, 1, N)
-            dev = self.model.device
-            if self._copy_stream is None:
-                self._copy_stream = torch.cuda.Stream(device=dev)
-            main = torch.cuda.current_stream(dev)
-            self._copy_stream.wait_stream(main)          # earlier readers of the landing buffer are done before it is rewritten
-            zero_to = [min(N, -(-n // FRAME_SIZE) * FRAME_SIZE) for n in original_lengths]
-            # the batch as one or two contiguous item ranges, each a phased encode on its own stream and workspace: the
-            # second range's staging and front end run under the first range's main pipeline, and two kernels in flight
-            # fill the SMs that a persistent grid's last tiles leave idle
-            n_ranges = 2 if (self.two_ranges and self.model.streams > 1 and B >= 2 * self.model.min_split_batch) else 1
-            bounds = [B * j // n_ranges for j in range(n_ranges + 1)]
-            if len(self._range_streams) < n_ranges:
-                self._range_streams = [torch.cuda.Stream(device=dev) for _ in range(n_ranges)]
-            hc = self._pinned_codes[: B * K * T].view(B, K, T)
-            for j in range(n_ranges):
-                r0, r1 = bounds[j], bounds[j + 1]
-                st = main if n_ranges == 1 else self._range_streams[j]
-                if st is not main:
-                    st.wait_stream(main)
+            phased = self.ragged and B > 1 and self.phased and self.model.supports_phased
+            if self.ragged and B > 1 and not phased:
+                # kernel generations without the phased call: independent sub-batches, synchronous
+                arrs = self._encode_sub_batched(slot, audio_arrays, lengths, K)
+                if fmt == "uint16":
+                    arrs = [a.astype(np.uint16) for a in arrs]
+                elif fmt == "utf8":
+                    arrs = [utils.codes_to_chars(a[:K], codebook_size, unicode_offset=unicode_offset) for a in arrs]
+                p = PendingBatch(None, None, None, lengths, frames, fmt, extra=arrs)
+                return p
+            with torch.cuda.stream(main):
+                if not phased:
+                    x = self._stage(slot, audio_arrays, sample_rate)
+                    out = self.model.encode(x, None, num_quantizers=K, workspace_slot=ws_slot)     # B == 1 or strict mode: all T frames
+                    slot.front_done = torch.cuda.Event()
+                    slot.front_done.record(main)
+                else:
+                    # One padded [B,1,N] batch, exactly the reference's, staged group by group: the 24 kHz front end (the only
+                    # part where items are independent) starts on group g as soon as its samples have landed while the host
+                    # is still filling group g+1; everything after the front end runs once over the whole batch.
+                    self._grow(slot, B * N, 0)
+                    buf = slot.pinned[: B * N].view(B, 1, N)
+                    x = slot.dev_in[: B * N].view(B, 1, N)
+                    if slot.front_done is not None:
+                        copy.wait_event(slot.front_done)     # the previous reader of this landing buffer is done
+                    zero_to = [min(N, f * FRAME_SIZE) for f in frames]
+                    arrs = list(audio_arrays)
+                    groups = [(g[0], g[-1] + 1, (lambda b0=g[0], b1=g[-1] + 1: self._land(slot, buf, x, arrs, zero_to, b0, b1, main)))
+                              for g in self._front_groups(B, self.first_items)]
+                    out = self.model.encode(input_values=x, padding_mask=None, num_quantizers=K, valid_lengths=lengths,
+                                            staged_groups=groups, on_front_done=lambda: self._mark_front_done(slot, main),
+                                            workspace_slot=ws_slot)
+                codes = out.audio_codes
+                # result -> pinned host memory, asynchronously on the encode stream
+                if fmt == "int64":
+                    dev_res, shape, dt = codes, (B, K, T), torch.int64
+                elif fmt == "uint16":
+                    dev_res, shape, dt = utils.codes_to_uint16(codes), (B, K, T), torch.uint16
+                else:
+                    dev_res, blens = utils.codes_to_utf8_device(codes[:, :K], frames, codebook_size, unicode_offset)
+                    shape, dt = tuple(dev_res.shape), torch.uint8
+                nbytes = dev_res.numel() * dev_res.element_size()
+                self._grow(slot, 0, nbytes)
+                view = slot.pinned_out[:nbytes].view(dt).view(shape)
+                view.copy_(dev_res, non_blocking=True)
+                done = torch.cuda.Event()
+                done.record(main)
+            p = PendingBatch(slot, done, view, lengths, frames, fmt, extra=blens if fmt == "utf8" else None)
+            slot.pending = p
+            return p
 
-                def lander(b0, b1, st=st):
-                    def land():
-                        self._fill(buf[b0:b1], audio_arrays[b0:b1], zero_to[b0:b1])
-                        with torch.cuda.stream(self._copy_stream):
-                            x[b0:b1].copy_(buf[b0:b1], non_blocking=True)
-                            landed = torch.cuda.Event()
-                            landed.record(self._copy_stream)
-                        st.wait_event(landed)
-                    return land
-                groups = [(g[0], g[-1] + 1, lander(r0 + g[0], r0 + g[-1] + 1))
-                          for g in self._front_groups(r1 - r0, self.first_items)]
-                with torch.cuda.stream(st):
-                    out = self.model.encode(input_values=x[r0:r1], padding_mask=None, num_quantizers=self.num_quantizers,
-                                            valid_lengths=original_lengths[r0:r1], staged_groups=groups, workspace_slot=j)
-                    hc[r0:r1].copy_(out.audio_codes, non_blocking=True)
-                if st is not main:
-                    main.wait_stream(st)
-            main.synchronize()
-            arr = hc.numpy()
-            return [arr[i, :, : int(np.ceil(n / frame_rate))].copy() for i, n in enumerate(original_lengths)]
+    def _mark_front_done(self, slot: _Staging, stream: torch.cuda.Stream) -> None:
+        slot.front_done = torch.cuda.Event()
+        slot.front_done.record(stream)
+
+    def result(self, pending: PendingBatch):
+        """Wait for a submitted batch and return what ``encode_audio_batch`` returns for it (a list of ``[K, T_i]`` arrays,
+        or of strings for ``fmt="utf8"``). The arrays are copies: the staging slot is free again afterwards."""
+        with self._lock:
+            if pending._consumed:
+                raise _lib.MimiB200Error("result() was already collected for this batch")
+            pending._consumed = True
+            if pending._done is None:
+                return pending._extra if pending._extra is not None else []
+            pending._done.synchronize()
+            if pending.format == "utf8":
+                host = pending._view.numpy()
+                return [host[i, : pending._extra[i]].tobytes().decode("utf-8") for i in range(len(pending.lengths))]
+            arr = pending._view.numpy()
+            return [arr[i, :, :f].copy() for i, f in enumerate(pending.frames)]
+
+    def encode_stream(self, batches, sample_rate: int = 24000, fmt: str = "int64", **kw):
+        """Generator over the results of ``batches`` (an iterable of lists of clips), in order, with two batches in flight:
+        the host stages batch i+1 and copies batch i-1's codes back while the GPU encodes batch i. Each yielded item is
+        what ``encode_audio_batch`` would return for that batch."""
+        from collections import deque
+        queue = deque()
+        for batch in batches:
+            queue.append(self.submit(batch, sample_rate, fmt, **kw))
+            if len(queue) >= self.DEPTH:
+                yield self.result(queue.popleft())
+        while queue:
+            yield self.result(queue.popleft())
 
     @staticmethod
     def _front_groups(B: int, first_items: int) -> List[List[int]]:
@@ -610,9 +742,9 @@ class MimiEncoder:
             bounds.append(min(B, bounds[-1] + 2 * (bounds[-1] - bounds[-2])))
         return [list(range(a, b)) for a, b in zip(bounds[:-1], bounds[1:])]
 
-    def _encode_sub_batched(self, audio_arrays, original_lengths, K, frame_rate) -> List[np.ndarray]:
+    def _encode_sub_batched(self, slot: _Staging, audio_arrays, original_lengths, K) -> List[np.ndarray]:
         """Ragged path for kernel generations without the phased call: the batch goes through the GPU as independent
-        sub-batches (staging of sub-batch j+1 overlaps the encode of sub-batch j)."""
+        sub-batches (staging of sub-batch j+1 overlaps the encode of sub-batch j). Synchronous."""
         B = len(audio_arrays)
         chunks = self._sub_batches(B, self.chunk_items, self.first_items)
         # a sub-batch is padded to whole frames (but never beyond the full batch length): every item then sees the
@@ -622,38 +754,31 @@ class MimiEncoder:
         total = sum(len(ch) * n for ch, n in zip(chunks, n_max))
         t_max = [-(-n // FRAME_SIZE) for n in n_max]
         total_codes = sum(len(ch) * K * t for ch, t in zip(chunks, t_max))
-        self._grow_pinned(total, total_codes)
+        self._grow(slot, total, total_codes * 8)
         off = coff = 0
         host_codes = []
-        dev = self.model.device
-        if self._copy_stream is None:
-            self._copy_stream = torch.cuda.Stream(device=dev)
-        main = torch.cuda.current_stream(dev)
-        self._copy_stream.wait_stream(main)
+        main, copy = self._streams()
+        copy.wait_stream(main)
+        pinned_codes = slot.pinned_out[: total_codes * 8].view(torch.int64)
         for ch, N, T in zip(chunks, n_max, t_max):
-            buf = self._pinned_view(off, len(ch), N)
+            buf = slot.pinned[off: off + len(ch) * N].view(len(ch), 1, N)
+            x = slot.dev_in[off: off + len(ch) * N].view(len(ch), 1, N)
             off += len(ch) * N
             lens = [original_lengths[i] for i in ch]
-            self._fill(buf, [audio_arrays[i] for i in ch], [min(N, -(-n // FRAME_SIZE) * FRAME_SIZE) for n in lens])
             # H2D on its own stream: the copy of sub-batch j+1 runs under the kernels of sub-batch j
-            x = self._dev_in[off - len(ch) * N: off].view(len(ch), 1, N)
-            with torch.cuda.stream(self._copy_stream):
-                x.copy_(buf, non_blocking=True)
-                landed = torch.cuda.Event()
-                landed.record(self._copy_stream)
-            main.wait_event(landed)
-            out = self.model.encode(input_values=x, padding_mask=None, num_quantizers=self.num_quantizers,
-                                    valid_lengths=lens)
-            hc = self._pinned_codes[coff: coff + len(ch) * K * T].view(len(ch), K, T)
+            self._land(slot, buf, x, [audio_arrays[i] for i in ch], [min(N, -(-n // FRAME_SIZE) * FRAME_SIZE) for n in lens],
+                       0, len(ch), main)
+            out = self.model.encode(input_values=x, padding_mask=None, num_quantizers=K, valid_lengths=lens)
+            hc = pinned_codes[coff: coff + len(ch) * K * T].view(len(ch), K, T)
             coff += len(ch) * K * T
             hc.copy_(out.audio_codes, non_blocking=True)
             host_codes.append(hc)
-        torch.cuda.current_stream(self.model.device).synchronize()
+        main.synchronize()
         result: List[np.ndarray] = []
         for ch, hc in zip(chunks, host_codes):
             arr = hc.numpy()
             for j, i in enumerate(ch):
-                result.append(arr[j, :, : int(np.ceil(original_lengths[i] / frame_rate))].copy())
+                result.append(arr[j, :, : -(-original_lengths[i] // FRAME_SIZE)].copy())
         return result
 
     # -- the callers and data formats either side of the path ---------------------------------
@@ -662,14 +787,18 @@ class MimiEncoder:
         calling the wrapper (REF/librispeech-mimi/process_librispeech_train.py:189-192, REF/*/utils.py:84-87) --
         clips at their native rate go to the GPU as they are (16 kHz audio is 1.5x fewer H2D bytes), are resampled
         to 24 kHz by the polyphase kernel straight into the zero-padded ``[B,1,N]`` layout, and encoded ragged.
-        Returns what ``encode_audio_batch`` returns for the resampled clips."""
+        Returns what ``encode_audio_batch`` returns for the resampled clips.
+
+        The resampling filter is NOT the reference's soxr_hq (``utils.resample_audio`` explains; parity unpinned): use
+        this entry point for throughput, and host-side ``librosa`` + ``encode_audio_batch`` where the reference's exact
+        tokens are required."""
         from . import utils
         if len(audio_arrays) == 0:
             return []
         if sample_rate == self.feature_extractor.sampling_rate:
             return self.encode_audio_batch(audio_arrays, sample_rate)
         K = self.num_quantizers
-        with torch.no_grad():
+        with self._lock, torch.no_grad():
             x, lens = utils.resample_batch(audio_arrays, sample_rate, self.feature_extractor.sampling_rate,
                                            device=self.model.device)
             out = self.model.encode(x, None, num_quantizers=K, valid_lengths=lens if self.ragged else None)
@@ -677,18 +806,37 @@ class MimiEncoder:
         return [codes[i, :, : -(-n // FRAME_SIZE)].copy() for i, n in enumerate(lens)]
 
     def encode_to_strings(self, audio_arrays: List[np.ndarray], sample_rate: int = 24000, num_codebooks: int = 8,
-                          codebook_size: int = 2048, unicode_offset: int = 0xE000) -> List[str]:
+                          codebook_size: int = 2048, unicode_offset: int = 0xE000,
+                          audio_tags: Optional[Sequence[str]] = None) -> List[str]:
         """Codes -> storage format on the GPU (8f rank 2): the ``audio_codes[:8]`` + ``codes_to_chars`` step every
         script performs per item on the host (REF/emilia-mimi/process_shard.py:505-506), as one UTF-8 kernel and
-        one device->host copy per batch. Returns the unicode strings ``codes_to_chars`` would build."""
-        from . import utils
+        one device->host copy per batch. Returns the unicode strings ``codes_to_chars`` would build;
+        ``audio_tags=("<|audio_start|>", "<|audio_end|>")`` wraps each one the way the pretraining-data builders do
+        (REF/pretraining-data/prepare_pretraining_data.py:255-271). ``num_codebooks=1`` gives the semantic-only strings of
+        REF/yodas2-mimi/build_yodas2_mm_semantic.py:169-195 (every 8th character of the 8-codebook string)."""
         if len(audio_arrays) == 0:
             return []
-        self._check_rate(sample_rate)
-        lens = [len(a) for a in audio_arrays]
-        with torch.no_grad():
-            x = self._stage(audio_arrays, sample_rate)
-            out = self.model.encode(x, None, num_quantizers=num_codebooks, valid_lengths=lens if self.ragged else None)
-            frames = [-(-n // FRAME_SIZE) for n in lens]
-            raw = utils.codes_to_utf8_batch(out.audio_codes, frames, codebook_size, unicode_offset)
-        return [r.decode("utf-8") for r in raw]
+        with self._lock:
+            strs = self.result(self.submit(audio_arrays, sample_rate, "utf8", num_codebooks=num_codebooks,
+                                           codebook_size=codebook_size, unicode_offset=unicode_offset))
+        if audio_tags is not None:
+            a, b = audio_tags
+            strs = [f"{a}{s}{b}" for s in strs]
+        return strs
+
+    def encode_long_audio(self, audio_array: np.ndarray, sample_rate: int = 24000,
+                          max_chunk_duration: Optional[float] = None) -> np.ndarray:
+        """Long-form audio (8f rank 3). ``max_chunk_duration=None``: the whole signal in ONE encode call -- exactly
+        ``MimiModel.encode`` on the unsplit waveform, i.e. one continuous stream (every conv halo and the 250-frame
+        attention window carry across what would have been piece boundaries). The engine takes items of up to 65 536
+        positions at 25 Hz (43 min) and needs ~33 MB of workspace per audio-second.
+        ``max_chunk_duration=s``: what REF/yodas2-mimi/process_shard.py:459-493 does -- pieces of at most ``s`` seconds
+        encoded independently (context reset at every cut) and concatenated along time; bit-identical to that loop."""
+        audio_array = np.asarray(audio_array)
+        if max_chunk_duration is None:
+            return self.encode_audio_chunk(audio_array, sample_rate)
+        max_samples = int(max_chunk_duration * sample_rate)
+        if max_samples <= 0:
+            raise ValueError("max_chunk_duration must be positive")
+        pieces = [audio_array[i:i + max_samples] for i in range(0, len(audio_array), max_samples)]
+        return np.concatenate([self.encode_audio_chunk(p, sample_rate) for p in pieces], axis=1)

@@ -5,6 +5,7 @@ with the array work done by libmimi_b200.so kernels: ``codes_to_chars``, ``chars
 from __future__ import annotations
 
 import ctypes as C
+import threading
 from typing import List, Optional, Sequence, Union
 
 import numpy as np
@@ -18,16 +19,38 @@ CODEBOOK_SIZE: int = 2048
 
 
 class _Engine:
-    """Weight-less engine handle for the resampler / UTF-8 kernels (one per device)."""
+    """Weight-less engine handle for the resampler / UTF-8 / pack kernels (one per device, shared by every caller).
+
+    The C handle is not re-entrant (include/mimi_b200.h): ``lock`` serialises the host side of every call on it, and the
+    library itself orders the device-side reuse of its small length tables across streams with an event. The pinned /
+    device staging buffers of :func:`resample_batch` live here too, so that no call pins fresh host memory."""
 
     _cache = {}
+    _cache_lock = threading.Lock()
 
     def __init__(self, device: torch.device):
         self.lib = _lib.load_library()
         self.device = device
+        self.lock = threading.RLock()
         h = C.c_void_p()
-        _lib.check(self.lib, None, self.lib.mimi_b200_create(C.byref(h), device.index), "mimi_b200_create")
+        with torch.cuda.device(device):
+            _lib.check(self.lib, None, self.lib.mimi_b200_create(C.byref(h), device.index), "mimi_b200_create")
         self.h = h
+        self._pinned_in: Optional[torch.Tensor] = None
+        self._dev_in: Optional[torch.Tensor] = None
+        self._staged = None          # event: the last H2D copy out of _pinned_in has completed
+
+    def staging(self, n: int) -> "tuple[torch.Tensor, torch.Tensor]":
+        """Persistent pinned + device fp32 staging buffers of at least ``n`` samples (call with ``lock`` held)."""
+        if self._pinned_in is None or self._pinned_in.numel() < n:
+            self._pinned_in = self._dev_in = None
+            cap = max(int(n * 1.25), 1 << 16)
+            self._pinned_in = torch.empty(cap, dtype=torch.float32).pin_memory()
+            self._dev_in = torch.empty(cap, dtype=torch.float32, device=self.device)
+            self._staged = None
+        if self._staged is not None:
+            self._staged.synchronize()          # the previous call's H2D copy has left the pinned buffer
+        return self._pinned_in, self._dev_in
 
     @classmethod
     def get(cls, device=None) -> "_Engine":
@@ -35,9 +58,10 @@ class _Engine:
             raise _lib.MimiB200Error("a CUDA device (B200) is required; there is no CPU fallback")
         dev = torch.device(device if device is not None else "cuda")
         dev = torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
-        if dev not in cls._cache:
-            cls._cache[dev] = cls(dev)
-        return cls._cache[dev]
+        with cls._cache_lock:
+            if dev not in cls._cache:
+                cls._cache[dev] = cls(dev)
+            return cls._cache[dev]
 
 
 def validate_unicode_offset(unicode_offset: int, num_codebooks: int, codebook_size: int) -> int:
@@ -51,10 +75,10 @@ def validate_unicode_offset(unicode_offset: int, num_codebooks: int, codebook_si
     return unicode_offset
 
 
-def codes_to_utf8_batch(codes: torch.Tensor, frames: Optional[Sequence[int]] = None, codebook_size: int = CODEBOOK_SIZE,
-                        unicode_offset: int = UNICODE_OFFSET) -> List[bytes]:
-    """codes ``[B,K,T]`` int64 on the GPU -> list of B UTF-8 byte strings (item i uses its first
-    ``frames[i]`` frames). One kernel + one device->host copy for the whole batch."""
+def codes_to_utf8_device(codes: torch.Tensor, frames: Optional[Sequence[int]] = None, codebook_size: int = CODEBOOK_SIZE,
+                         unicode_offset: int = UNICODE_OFFSET) -> "tuple[torch.Tensor, List[int]]":
+    """codes ``[B,K,T]`` int64 on the GPU -> (``[B, stride]`` uint8 device tensor of UTF-8 rows, byte length of each row);
+    asynchronous on the current stream. The codes must lie in ``[0, codebook_size)``."""
     if codes.dim() != 3:
         raise ValueError("codes must be [batch, num_codebooks, seq_length]")
     B, K, T = codes.shape
@@ -63,19 +87,39 @@ def codes_to_utf8_batch(codes: torch.Tensor, frames: Optional[Sequence[int]] = N
     bpf = eng.lib.mimi_b200_utf8_bytes_per_frame(K, unicode_offset, codebook_size)
     if bpf < 0:
         raise ValueError("unicode offset / codebook size not representable as fixed-width UTF-8 per codebook")
-    if B == 0:
-        return []
     codes = codes.to(torch.int64).contiguous()
     stride = max(int(T * bpf), 1)
     out = torch.empty((B, stride), dtype=torch.uint8, device=codes.device)
+    if B == 0:
+        return out, []
     fr = (C.c_int64 * B)(*[int(f) for f in frames]) if frames is not None else None
     lens = (C.c_int64 * B)()
-    with torch.cuda.device(codes.device):
+    with eng.lock, torch.cuda.device(codes.device):
         rc = eng.lib.mimi_b200_codes_to_utf8(eng.h, codes.data_ptr(), B, K, T, fr, unicode_offset, codebook_size,
                                              out.data_ptr(), stride, lens, torch.cuda.current_stream().cuda_stream)
-    _lib.check(eng.lib, eng.h, rc, "mimi_b200_codes_to_utf8")
+        _lib.check(eng.lib, eng.h, rc, "mimi_b200_codes_to_utf8")
+    return out, [int(v) for v in lens]
+
+
+def codes_to_utf8_batch(codes: torch.Tensor, frames: Optional[Sequence[int]] = None, codebook_size: int = CODEBOOK_SIZE,
+                        unicode_offset: int = UNICODE_OFFSET, validate: bool = True) -> List[bytes]:
+    """codes ``[B,K,T]`` int64 on the GPU -> list of B UTF-8 byte strings (item i uses its first
+    ``frames[i]`` frames). One kernel + one device->host copy for the whole batch.
+
+    The kernel's fixed bytes-per-frame layout relies on every code lying in ``[0, codebook_size)``; ``validate`` checks
+    that first (``ValueError`` otherwise -- the reference would silently emit characters of a neighbouring codebook or
+    raise in ``chr``). Codes that come straight out of the encoder are in range by construction and may skip the check."""
+    if codes.dim() != 3:
+        raise ValueError("codes must be [batch, num_codebooks, seq_length]")
+    if validate and codes.numel():
+        lo, hi = int(codes.min()), int(codes.max())
+        if lo < 0 or hi >= codebook_size:
+            raise ValueError(f"codes must lie in [0, {codebook_size}), got values in [{lo}, {hi}]")
+    out, lens = codes_to_utf8_device(codes, frames, codebook_size, unicode_offset)
+    if codes.shape[0] == 0:
+        return []
     host = out.cpu().numpy()
-    return [host[i, : lens[i]].tobytes() for i in range(B)]
+    return [host[i, : lens[i]].tobytes() for i in range(codes.shape[0])]
 
 
 def codes_to_chars(codes: Union[List[List[int]], np.ndarray, torch.Tensor], codebook_size: int,
@@ -119,34 +163,77 @@ def audio_to_str(audio_numpy: np.ndarray, mimi_model, device: str = "cuda") -> s
     return codes_to_chars(codes, codebook_size=CODEBOOK_SIZE)
 
 
+def codes_to_uint16(codes: torch.Tensor) -> torch.Tensor:
+    """int64 codes of any shape on the GPU -> uint16 tensor of the same shape: the ``codes.astype(np.uint16)`` storage
+    format of REF/yodas2-mimi/process_shard.py:519-523, cast before the device->host copy (2 instead of 8 bytes per code)."""
+    if not codes.is_cuda:
+        raise _lib.MimiB200Error("codes must live on the CUDA device (no CPU fallback)")
+    codes = codes.to(torch.int64).contiguous()
+    out = torch.empty(codes.shape, dtype=torch.uint16, device=codes.device)
+    eng = _Engine.get(codes.device)
+    with eng.lock, torch.cuda.device(codes.device):
+        rc = eng.lib.mimi_b200_codes_pack_u16(eng.h, codes.data_ptr(), codes.numel(), out.data_ptr(),
+                                              torch.cuda.current_stream().cuda_stream)
+        _lib.check(eng.lib, eng.h, rc, "mimi_b200_codes_pack_u16")
+    return out
+
+
 def resample_batch(audio: Sequence[np.ndarray], orig_sr: int, target_sr: int = 24000, device=None,
                    pad_to: Optional[int] = None) -> "tuple[torch.Tensor, List[int]]":
     """Resample a list of mono clips on the GPU into one zero-right-padded ``[B,1,N]`` device tensor
-    (exactly the ``input_values`` layout) and return it with the per-item output lengths."""
+    (exactly the ``input_values`` layout) and return it with the per-item output lengths.
+
+    NOT bit-compatible with the reference's ``librosa.resample`` (soxr_hq): see :func:`resample_audio`."""
     eng = _Engine.get(device)
     B = len(audio)
-    lens_in = [int(len(a)) for a in audio]
+    arrs = [np.ascontiguousarray(np.asarray(a, dtype=np.float32)) for a in audio]
+    for a in arrs:
+        if a.ndim != 1:
+            raise ValueError(f"Expected mono audio but example has shape {a.shape}")
+    lens_in = [int(a.shape[0]) for a in arrs]
     lens_out = [int(eng.lib.mimi_b200_resample_out_len(n, orig_sr, target_sr)) for n in lens_in]
     n_in, n_out = max(lens_in + [1]), max(lens_out + [1])
     if pad_to is not None:
         n_out = max(n_out, int(pad_to))
-    host = torch.zeros((B, n_in), dtype=torch.float32).pin_memory()
-    for i, a in enumerate(audio):
-        host[i, : lens_in[i]] = torch.from_numpy(np.asarray(a, dtype=np.float32))
-    d_in = host.to(eng.device, non_blocking=True)
     d_out = torch.empty((B, 1, n_out), dtype=torch.float32, device=eng.device)
-    hl = (C.c_int64 * B)(*lens_in)
-    with torch.cuda.device(eng.device):
-        rc = eng.lib.mimi_b200_resample(eng.h, d_in.data_ptr(), n_in, hl, B, int(orig_sr), int(target_sr),
+    if B == 0:
+        return d_out, lens_out
+    with eng.lock, torch.cuda.device(eng.device):
+        pinned, dev = eng.staging(B * n_in)
+        host = pinned[: B * n_in].view(B, n_in)
+        # native gather (memcpy threads, GIL released); rows are only read up to their length, no zero fill needed
+        src = (C.c_void_p * B)(*[a.ctypes.data for a in arrs])
+        ln = (C.c_int64 * B)(*lens_in)
+        rc = eng.lib.mimi_b200_host_pack(host.data_ptr(), n_in, src, ln, ln, B, 4)
+        _lib.check(eng.lib, None, rc, "mimi_b200_host_pack")
+        d_in = dev[: B * n_in].view(B, n_in)
+        d_in.copy_(host, non_blocking=True)
+        eng._staged = torch.cuda.Event()
+        eng._staged.record()
+        rc = eng.lib.mimi_b200_resample(eng.h, d_in.data_ptr(), n_in, ln, B, int(orig_sr), int(target_sr),
                                         d_out.data_ptr(), n_out, torch.cuda.current_stream().cuda_stream)
-    _lib.check(eng.lib, eng.h, rc, "mimi_b200_resample")
+        _lib.check(eng.lib, eng.h, rc, "mimi_b200_resample")
     return d_out, lens_out
 
 
-def resample_audio(audio: np.ndarray, orig_sr: int, target_sr: int) -> np.ndarray:
+def resample_audio(audio: np.ndarray, orig_sr: int, target_sr: int, backend: str = "b200") -> np.ndarray:
     """REF/emilia-mimi/utils.py:84-87: no-op when the rates agree, else band-limited resampling to
-    ``ceil(n * target_sr / orig_sr)`` samples (librosa ``fix=True``), here by the GPU polyphase FIR."""
+    ``ceil(n * target_sr / orig_sr)`` samples (librosa ``fix=True``).
+
+    **Not bit-compatible with the reference.** The reference calls ``librosa.resample``, whose default backend is libsoxr
+    "HQ"; that library is not available offline and nothing in the reference pins its output, so parity of this function
+    is UNPINNED. ``backend="b200"`` (default) runs the GPU polyphase FIR -- a Kaiser-windowed sinc, 32
+    zero crossings, roll-off 0.945, > 120 dB stop band -- which is a different (equally band-limited) filter: the 24 kHz
+    waveform differs from soxr_hq's in the last octave below Nyquist, and Mimi codes computed from it differ on the frames
+    where that matters (``bench.py --workload c1`` reports the code agreement between this filter and two other
+    high-quality resamplers as a yardstick). For runs that must reproduce the reference's tokens exactly, pass
+    ``backend="librosa"`` (needs librosa + soxr installed; host CPU) and feed the result to the encoder at 24 kHz."""
     if orig_sr == target_sr:
         return audio
+    if backend == "librosa":
+        import librosa                      # ImportError if absent: there is no silent substitute
+        return librosa.resample(audio, orig_sr=orig_sr, target_sr=target_sr)
+    if backend != "b200":
+        raise ValueError(f"unknown resampler backend '{backend}'")
     out, lens = resample_batch([np.asarray(audio)], orig_sr, target_sr)
     return out[0, 0, : lens[0]].cpu().numpy()
