@@ -68,7 +68,7 @@ HBM_BYTES_PER_AUDIO_S = {
     "conv0": 24000 * 4 + 24000 * 64 * 4,
     "layernorm": 25 * 512 * 4 * 2 * 16,
     # fused 24 kHz front end: waveform in, hi/lo split of the 64-channel activation out
-    "front_fused": 24000 * 4 + 24000 * 64 * 6,
+    "front_fused": 24000 * 4 + 24000 * 64 * 4,
 }
 HBM_BOUND_KINDS = ("conv0", "layernorm", "front_fused")
 
@@ -671,6 +671,12 @@ def run_b200(args, rank, world, local_rank):
                     t = min(min(a.shape[1], b.shape[1]) for a, b in zip(ours, theirs))
                     eq = np.stack([a[:, :t] == b[:, :t] for a, b in zip(ours, theirs)])
                     ra[nm] = {"codes_equal_frac": float(eq.mean()), "per_codebook": [round(float(v), 4) for v in eq.mean(axis=(0, 2))]}
+                # the same measure between the two stand-ins themselves: how far apart two "good" resamplers are on this audio
+                ta = [wrapper.encode_audio_chunk(y) for y in alt["torchaudio_sinc_interp_kaiser"]]
+                sp = [wrapper.encode_audio_chunk(y) for y in alt["scipy_resample_poly"]]
+                t = min(min(a.shape[1], b.shape[1]) for a, b in zip(ta, sp))
+                eq = np.stack([a[:, :t] == b[:, :t] for a, b in zip(ta, sp)])
+                ra["torchaudio_vs_scipy"] = {"codes_equal_frac": float(eq.mean()), "per_codebook": [round(float(v), 4) for v in eq.mean(axis=(0, 2))]}
                 extras["resampler_filter_sensitivity"] = {
                     "what": "code agreement of encode(resample_b200(x16k)) with encode(other_resampler(x16k)), 8 x 10 s clips; "
                             "soxr_hq (the reference's filter) is not installed, these two stand in as a yardstick",
@@ -720,8 +726,10 @@ def main():
     select_workload(args.workload)
     if args.mode is not None and args.mode <= 6:
         HBM_BYTES_PER_AUDIO_S["front_fused"] = 24000 * 4 + 24000 * 64 * 8      # fp32 lo parts
-    if args.mode == 9:
-        HBM_BYTES_PER_AUDIO_S["front_fused"] = 24000 * 4 + 24000 * 64 * 4      # fp16 hi + fp16 lo
+    if args.mode is None or args.mode == 9:
+        HBM_BYTES_PER_AUDIO_S["front_fused"] = 24000 * 4 + 24000 * 64 * 4      # fp16 hi + fp16 lo (default generation)
+    elif args.mode >= 7:
+        HBM_BYTES_PER_AUDIO_S["front_fused"] = 24000 * 4 + 24000 * 64 * 6      # TF32 hi (fp32) + bf16 lo
     if args.impl == "reference":
         run_reference(args, rank, world)
         return

@@ -149,10 +149,13 @@ int mimi_b200_debug_tap(mimi_b200_t* h, int which, float* d_out, size_t out_capa
      1  index of the last SEANet conv to run (default 13; smaller values stop the pipeline there, on the fp32 FFMA path,
         and leave d_codes untouched)
      2  per-launch CUDA-event profiling on/off (resets the profile)
-     3  kernel generation ("mode"), default 7:
+     3  kernel generation ("mode"), default 9:
           0  every layer on fp32 FFMA (exact-fp32 bisection baseline)
           7  fused 24 kHz front end (front_fused.cuh) + CTA-pair tcgen05 GEMM (tc_gemm5.cuh; hi*hi and hi*lo on
-             kind::tf32, lo*hi on kind::f16 with bf16 lo parts) + tcgen05 attention + tensor-core RVQ
+             kind::tf32, lo*hi on kind::f16 with bf16 lo parts) + tcgen05 attention + tensor-core RVQ; fp32 range
+          9  mode 7 with every GEMM operand as an fp16 hi/lo pair (activations: hi + lo/2048, weights row-scaled by a power
+             of two): hi*hi + hi*lo + lo*hi all on kind::f16, 3 tensor passes instead of 5 pass units, 4 instead of 6
+             bytes per activation element; saturates at 65504 (see mimi_b200_range_overflow)
           the other values (1..6, 8) are earlier / experimental generations kept for A/B, see DESIGN.md section 7
      4  accuracy experiment: cross terms into the main accumulator (single-CTA GEMM generations)
      5  accuracy experiment: k-blocks per accumulation chunk (0 = default 4)
@@ -230,6 +233,15 @@ int mimi_b200_codes_pack_u16(mimi_b200_t* h, const int64_t* d_codes, int64_t n, 
  */
 int mimi_b200_host_pack(float* h_dst, int64_t dst_stride, const float* const* h_src, const int64_t* h_len,
                         const int64_t* h_zero_to, int n, int n_threads);
+
+/*
+ * Range guard of the default (fp16 split, "mode 9") kernel generation: activations are carried as fp16 hi/lo pairs, which
+ * saturate at 65504 (MimiModel itself runs fp32 and has no such limit). Kernels clamp and raise a device flag; every mode-9
+ * encode copies the flag to the host behind its last kernel. Returns the flag as of the last COMPLETED encode on this handle's
+ * device (synchronise the encode's stream first); reset != 0 also clears it (synchronises the device). A caller that sees 1
+ * re-encodes with debug_set(3, 7), the TF32 generation, which has fp32's range -- MimiEncoder does that by itself.
+ */
+int mimi_b200_range_overflow(mimi_b200_t* h, int reset);
 
 /* Number of kernels this handle has launched since creation (bench.py reports it as gpu_launches). */
 int64_t mimi_b200_launch_count(const mimi_b200_t* h);

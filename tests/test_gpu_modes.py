@@ -2,8 +2,8 @@
 
 mode 0 = all-fp32 FFMA (the exact-fp32 baseline), 2 = persistent tcgen05 3xTF32 GEMM + SIMT RVQ + SIMT attention,
 3 = + fused 24 kHz front end, tensor-core attention and RVQ, 4 = experimental third-generation GEMM, 5 = raw fp32
-activations split inside the GEMM, 6 = mode 3 with the CTA-pair (cta_group::2) GEMM, 7 = default: mode 6 with bf16 lo
-parts (A_lo * W_hi on kind::f16).
+activations split inside the GEMM, 6 = mode 3 with the CTA-pair (cta_group::2) GEMM, 7 = mode 6 with bf16 lo
+parts (A_lo * W_hi on kind::f16), 9 = default: every GEMM operand an fp16 hi/lo pair, all products on kind::f16.
 Tolerances as in test_gpu_parity.py: codes >= 99.9 % identical to the oracle, latent relative L2 <= 2e-5.
 """
 import ctypes as C
@@ -35,7 +35,7 @@ def case(state_dict):
     return x, lens, ref, np.stack(taps["latent"])
 
 
-@pytest.mark.parametrize("mode", [0, 2, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("mode", [0, 2, 3, 4, 5, 6, 7, 8, 9])
 def test_every_mode_matches_the_oracle(b200_model, case, mode):
     x, lens, ref, lat_ref = case
     b200_model.set_mode(mode)
@@ -103,6 +103,7 @@ def test_fused_level1_residual_block_matches_the_two_launches(b200_model):
         x[i, 0, :n] = synth.synth_speech(1500 + i, n)
     xd = torch.from_numpy(x).cuda()
     res = {}
+    b200_model.set_mode(7)            # the fused block belongs to the TF32 / bf16-lo generation
     try:
         for fuse in (0, 1):
             b200_model.debug_set(15, fuse)
@@ -110,6 +111,7 @@ def test_fused_level1_residual_block_matches_the_two_launches(b200_model):
             res[fuse] = (out.audio_codes.cpu().numpy(), lat.cpu().numpy())
     finally:
         b200_model.debug_set(15, 0)
+        b200_model.set_mode(True)
     for i, n in enumerate(lens):
         t = -(-n // 1920)
         assert _rel(res[1][1][i, :, :t], res[0][1][i, :, :t]) <= 2e-6

@@ -165,3 +165,31 @@ def test_native_rate_front_door(b200_model):
     assert [g.shape for g in got] == [w.shape for w in want]
     agree = np.mean([np.mean(g == w) for g, w in zip(got, want)])
     assert agree >= 0.99          # inputs agree to fp32 rounding (2e-6), so only near-ties may flip
+
+
+def test_fp16_range_overflow_falls_back_to_the_tf32_generation(b200_model):
+    """The default generation carries activations as fp16 pairs (max 65504). Audio scaled far beyond [-1, 1] drives the
+    SEANet activations past that: the kernels clamp and raise the range flag, and the wrapper re-encodes the batch with the
+    range-safe TF32 generation -- the result is exactly what a mode-7 wrapper returns, and later batches are unaffected."""
+    from tokenize_audio_b200.encoder import MimiB200Model
+    loud = [synth.synth_speech(3300 + i, n) * np.float32(3e5) for i, n in enumerate((30000, 20000, 9000))]
+    normal = [synth.synth_speech(3310 + i, n) for i, n in enumerate((25000, 12000))]
+    b200_model.range_overflow(reset=True)
+    b200_model.set_mode(MimiB200Model.RANGE_SAFE_MODE)
+    try:
+        safe = MimiEncoder(b200_model, num_quantizers=8)
+        want_loud, want_normal = safe.encode_audio_batch(loud), safe.encode_audio_batch(normal)
+    finally:
+        b200_model.set_mode(True)
+    enc = MimiEncoder(b200_model, num_quantizers=8)
+    got_normal = enc.encode_audio_batch(normal)
+    assert enc.range_fallbacks == 0 and not b200_model.range_overflow()
+    got = list(enc.encode_stream([loud, normal, normal]))
+    assert enc.range_fallbacks >= 1
+    assert all(np.array_equal(a, b) for a, b in zip(got[0], want_loud))
+    for res in got[1:]:
+        for a, b, c in zip(res, want_normal, got_normal):
+            assert np.array_equal(a, b) or np.array_equal(a, c)      # redone range-safely (suspect) or plain mode 9
+    assert not b200_model.range_overflow()
+    after = enc.encode_audio_batch(normal)
+    assert all(np.array_equal(a, b) for a, b in zip(after, got_normal))

@@ -63,6 +63,7 @@ SYMBOLS = {
     "mimi_b200_codes_to_utf8": (C.c_int, [c_void_p, c_void_p, C.c_int, C.c_int, C.c_int64, c_void_p,
                                           C.c_uint32, C.c_int, c_void_p, C.c_int64, c_void_p, c_void_p]),
     "mimi_b200_codes_pack_u16": (C.c_int, [c_void_p, c_void_p, C.c_int64, c_void_p, c_void_p]),
+    "mimi_b200_range_overflow": (C.c_int, [c_void_p, C.c_int]),
     "mimi_b200_launch_count": (C.c_int64, [c_void_p]),
 }
 

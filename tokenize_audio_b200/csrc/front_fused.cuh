@@ -55,7 +55,7 @@ struct Params {
   float* out_lo;
   long long split_item_stride;
   int split_front;
-  int lo_bf16;               // 1: out_lo is a bf16 array (mode 7)
+  int lo_bf16;               // 1: out_lo is a bf16 array (mode 7); 3: out_hi and out_lo are fp16 arrays (mode 9, split_f16)
   int raw_out;               // 1: store the raw fp32 result (pre-ELU, unsplit) to out_hi only (mode 5: the consumer
                              //    applies ELU and the hi/lo split itself)
 };
@@ -296,6 +296,8 @@ front_fused_kernel(const __grid_constant__ CUtensorMap tmW1_hi, const __grid_con
           if (p.raw_out) {
             h4 = make_float4(v[0], v[1], v[2], v[3]);
             lq[q] = h4;
+          } else if (p.lo_bf16 == 3) {
+            split_f16(v[0], h4.x, lq[q].x); split_f16(v[1], h4.y, lq[q].y); split_f16(v[2], h4.z, lq[q].z); split_f16(v[3], h4.w, lq[q].w);
           } else {
             split_tf32(v[0], h4.x, lq[q].x); split_tf32(v[1], h4.y, lq[q].y); split_tf32(v[2], h4.z, lq[q].z); split_tf32(v[3], h4.w, lq[q].w);
           }
@@ -319,7 +321,10 @@ front_fused_kernel(const __grid_constant__ CUtensorMap tmW1_hi, const __grid_con
             const int tt = t0 - 2 + mm;
             if (mm >= 2 && tt < L) {
               const long long o = obase + (long long)tt * 64 + (lane & 7) * 4;
-              if (pass == 1 && p.lo_bf16)
+              if (p.lo_bf16 == 3)
+                *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(outp) + o) =
+                    make_uint2(pack_f16x2(tv[i8].x, tv[i8].y), pack_f16x2(tv[i8].z, tv[i8].w));
+              else if (pass == 1 && p.lo_bf16)
                 *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(outp) + o) =
                     make_uint2(pack_bf16x2(tv[i8].x, tv[i8].y), pack_bf16x2(tv[i8].z, tv[i8].w));
               else

@@ -77,10 +77,17 @@ struct TcWeight {
   uint16_t* lob = nullptr;                 // bf16(lo), mode 8
   CUtensorMap map_hib, map64_hib, map32_hib, map32_hi, map32_lo;
   CUtensorMap map_lob, map64_lob, map32_lob;
+  // fp16 generation (mode 9): rows scaled by 2^e_n so that max |W'[n,:]| lies in [2^13, 2^14); h16 = fp16(W'), l16 = fp16(W' - h16),
+  // s16 = fp16(h16 / 2048) (the factor of the activations' scaled lo parts); wscale[n] = 2^-e_n undoes the scaling in the epilogue.
+  // One array [3][N][K] (hi | lo | hs); SWIZZLE_64B boxes of 32 x {128, 64, 32} rows.
+  uint16_t* f16 = nullptr;
+  float* wscale = nullptr;
+  CUtensorMap map_f16[3][3];               // [hi, lo, hs][box rows 128, 64, 32]
   int N = 0, K = 0, BN = 0;
 };
 // hi/lo activation pair, channels-last with `front` zero halo rows before row 0 of every item
 struct SplitBuf { long long hi = 0, lo = 0, item_stride = 0; int front = 0, back = 0, C = 0, level = 0; long long hib = -1; };   // hib: bf16(hi), mode 8, levels >= 2
+// (mode 9: hi and lo are both fp16 arrays of item_stride ELEMENTS per item, starting at float offsets hi / lo)
 constexpr int kHalo = 8;     // >= max(k - stride) = 8 (front) and >= max(stride) - 1 = 7 (back)
 
 struct PlanTC {
@@ -143,6 +150,7 @@ struct mimi_b200 {
   // scratch for resample / utf8 length arrays (device)
   int* dev_ints = nullptr;
   size_t dev_ints_cap = 0;
+  int* range_flag = nullptr;                   // pinned host copy of g_f16_overflow, refreshed behind every mode-9 encode
   cudaEvent_t dev_ints_ev = nullptr;           // recorded behind the last kernel that reads dev_ints: the next call's upload
                                                // (possibly on another stream) waits for it before overwriting the table
   // resampler taps cache: key (sr_in << 32 | sr_out)
@@ -161,8 +169,9 @@ struct mimi_b200 {
   Plan last;
   void* last_ws = nullptr;
   // tensor-core path
-  int mode = 7;                                // 8 = mode 7 + bf16(hi) copies at levels >= 2: both cross terms on kind::f16,
-                                               // 7 = mode 6 with bf16 lo parts and A_lo * W_hi on kind::f16 (default),
+  int mode = 9;                                // 9 = mode 7 with fp16 hi/lo operands, all three products on kind::f16 (default),
+                                               // 8 = mode 7 + bf16(hi) copies at levels >= 2: both cross terms on kind::f16,
+                                               // 7 = mode 6 with bf16 lo parts and A_lo * W_hi on kind::f16 (the range-safe fallback of mode 9),
                                                // 6 = mode 3 with the CTA-pair GEMM (tc_gemm5.cuh) where N % 128 == 0 (default),
                                                // 5 = raw fp32 activations split inside the GEMM (tc_gemm4.cuh),
                                                // 4 = mode 3 with the experimental third-generation GEMM (tc_gemm3.cuh),
@@ -416,6 +425,20 @@ const char* mimi_b200_last_error(const mimi_b200_t* h) { return h ? h->err.c_str
 
 int64_t mimi_b200_launch_count(const mimi_b200_t* h) { return h ? h->launches : 0; }
 
+int mimi_b200_range_overflow(mimi_b200_t* h, int reset) {
+  if (!h || !h->range_flag) return 0;
+  const int v = *h->range_flag;
+  if (reset) {
+    DeviceGuard guard;
+    cudaSetDevice(h->device);
+    const int zero = 0;
+    cudaDeviceSynchronize();
+    cudaMemcpyToSymbol(g_f16_overflow, &zero, sizeof(int));
+    *h->range_flag = 0;
+  }
+  return v;
+}
+
 int64_t mimi_b200_encoded_frames(int64_t n) {
   for (int l = 0; l < 5; ++l) n = (n + kLevelStride[l] - 1) / kLevelStride[l];
   return n;
@@ -443,6 +466,8 @@ int mimi_b200_create(mimi_b200_t** out, int device_ordinal) {
   if ((e = cudaSetDevice(device_ordinal)) != cudaSuccess) { delete h; return fail(nullptr, MIMI_B200_ERR_CUDA, cudaGetErrorString(e)); }
   for (int i = 0; i < kStageSlots; ++i) cudaEventCreateWithFlags(&h->stage_ev[i], cudaEventDisableTiming);
   cudaEventCreateWithFlags(&h->dev_ints_ev, cudaEventDisableTiming);
+  if (cudaMallocHost((void**)&h->range_flag, sizeof(int)) == cudaSuccess) *h->range_flag = 0;
+  else { h->range_flag = nullptr; cudaGetLastError(); }
   cudaFuncSetAttribute(swa_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttSmemBytes);
   cudaFuncSetAttribute(swa_attention2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAtt2SmemBytes);
   cudaFuncSetAttribute(swa_attention3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAtt2SmemBytes);
@@ -466,6 +491,9 @@ int mimi_b200_create(mimi_b200_t** out, int device_ordinal) {
   cudaFuncSetAttribute(tcp::tcp_gemm_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcp::Cfg<256, 2>::SMEM);
   cudaFuncSetAttribute(tcp::tcp_gemm_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcp::Cfg<128, 2>::SMEM);
   cudaFuncSetAttribute(tcp::tcp_gemm_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcp::Cfg<64, 2>::SMEM);
+  cudaFuncSetAttribute(tcp::tcp_gemm_kernel<256, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcp::Cfg<256, 3>::SMEM);
+  cudaFuncSetAttribute(tcp::tcp_gemm_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcp::Cfg<128, 3>::SMEM);
+  cudaFuncSetAttribute(tcp::tcp_gemm_kernel<64, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcp::Cfg<64, 3>::SMEM);
   {
     // how many CTA pairs of the widest instance fit at once (one per TPC unless the device says otherwise)
     cudaLaunchConfig_t cfg{};
@@ -501,6 +529,7 @@ void mimi_b200_destroy(mimi_b200_t* h) {
   }
   if (h->dev_ints) cudaFree(h->dev_ints);
   if (h->dev_ints_ev) cudaEventDestroy(h->dev_ints_ev);
+  if (h->range_flag) cudaFreeHost(h->range_flag);
   for (cudaEvent_t e : h->prof_pool) cudaEventDestroy(e);
   for (auto& kv : h->taps) { cudaFree(kv.second.d); if (kv.second.g) cudaFree(kv.second.g); }
   delete h;
@@ -511,7 +540,7 @@ int mimi_b200_debug_set(mimi_b200_t* h, int key, int value) {
   if (key == 0) h->dbg_layers = std::min(std::max(value, 0), MIMI_B200_NUM_LAYERS);
   else if (key == 1) h->dbg_last_conv = std::min(std::max(value, 0), MIMI_B200_NUM_CONVS - 1);
   else if (key == 2) { h->prof_on = value != 0; h->prof_n = 0; }
-  else if (key == 3) h->mode = std::min(std::max(value, 0), 8);
+  else if (key == 3) h->mode = std::min(std::max(value, 0), 9);
   else if (key == 4) h->exp_single_acc = value != 0;
   else if (key == 5) h->exp_chunk_kb = std::max(value, 0);
   else if (key == 6) h->use_planes = value != 0;
@@ -661,9 +690,9 @@ int mimi_b200_workspace_bytes(mimi_b200_t* h, int B, int64_t N, int K, size_t* o
   // sized for the compute mode in force (debug_set key 3): the fp32 FFMA plan only in mode 0, level-0 buffers only
   // in the unfused tensor-core modes
   const bool simt = h->mode == 0 || h->dbg_last_conv != MIMI_B200_NUM_CONVS - 1;
-  *out_bytes = (simt ? make_plan(B, N, K).bytes : h->mode == 5 ? make_plan_r(B, N, K).bytes : make_plan_tc(B, N, K, h->mode < 3, h->mode >= 7 && !h->exp_full_lo, h->mode == 8).bytes) + 256;
+  *out_bytes = (simt ? make_plan(B, N, K).bytes : h->mode == 5 ? make_plan_r(B, N, K).bytes : make_plan_tc(B, N, K, h->mode < 3, h->mode >= 7 && !h->exp_full_lo, h->mode == 8, h->mode == 9).bytes) + 256;
   if (!simt && h->mode != 5) {
-    const PlanTC pt = make_plan_tc(B, N, K, h->mode < 3, h->mode >= 7 && !h->exp_full_lo, h->mode == 8);
+    const PlanTC pt = make_plan_tc(B, N, K, h->mode < 3, h->mode >= 7 && !h->exp_full_lo, h->mode == 8, h->mode == 9);
     return ensure_stage(h, (pt.bytes - (size_t)pt.ints) / sizeof(int));     // lengths + tile lists of a batch this size
   }
   return MIMI_B200_OK;
@@ -713,7 +742,7 @@ static int encode_impl(mimi_b200_t* h, const float* d_input, int B, int64_t N, c
 
   const bool use_tc = h->mode >= 1 && h->dbg_last_conv == MIMI_B200_NUM_CONVS - 1;
   const Plan p = make_plan(B, N, K);
-  const PlanTC pt = make_plan_tc(B, N, K, h->mode < 3, h->mode >= 7 && !h->exp_full_lo, h->mode == 8);
+  const PlanTC pt = make_plan_tc(B, N, K, h->mode < 3, h->mode >= 7 && !h->exp_full_lo, h->mode == 8, h->mode == 9);
   const PlanR pr = make_plan_r(B, N, K);
   const bool use_r5 = use_tc && h->mode == 5;
   const size_t need = use_r5 ? pr.bytes : use_tc ? pt.bytes : p.bytes;
@@ -1010,9 +1039,9 @@ __global__ void debug_split_kernel(const float* __restrict__ x, float* __restric
 }
 
 __global__ void debug_split_lob_kernel(const float* __restrict__ x, float* __restrict__ hi, uint16_t* __restrict__ lo, long long n,
-                                       float* __restrict__ hib) {
+                                       float* __restrict__ hib, int lob) {
   const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  if (i < n) store_split4_x(hi, reinterpret_cast<float*>(lo), hib, i, *reinterpret_cast<const float4*>(x + i), 1);
+  if (i < n) store_split4_x(hi, reinterpret_cast<float*>(lo), hib, i, *reinterpret_cast<const float4*>(x + i), lob);
 }
 
 int mimi_b200_debug_tc_gemm(mimi_b200_t* h, const float* d_a, const float* h_w, const float* d_bias_opt, int M, int N,
@@ -1033,13 +1062,15 @@ int mimi_b200_debug_tc_gemm(mimi_b200_t* h, const float* d_a, const float* h_w, 
   const bool lob = h->mode >= 7;
   float* hib = nullptr;
   if (h->mode == 8) CUDA_TRY(h, cudaMalloc((void**)&hib, n * sizeof(uint16_t)));
-  if (lob) debug_split_lob_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(d_a, hi, reinterpret_cast<uint16_t*>(lo), n, hib);
+  const bool f16 = h->mode == 9;
+  if (lob) debug_split_lob_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(d_a, hi, reinterpret_cast<uint16_t*>(lo), n, hib, f16 ? 3 : 1);
   else debug_split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_a, hi, lo, n);
   CUtensorMap ma_hi, ma_lo;
   const cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)M, 1};
   const cuuint64_t strides[2] = {(cuuint64_t)K * sizeof(float), (cuuint64_t)n * sizeof(float)};
   const cuuint64_t strides_b[2] = {(cuuint64_t)K * 2, (cuuint64_t)n * 2};
-  if ((rc = tc_make_map(h, &ma_hi, hi, 3, dims, strides, tc::kBM))) return rc;
+  if (f16) { if ((rc = tc_make_map_bf16(h, &ma_hi, hi, 3, dims, strides_b, tc::kBM))) return rc; }
+  else if ((rc = tc_make_map(h, &ma_hi, hi, 3, dims, strides, tc::kBM))) return rc;
   CUtensorMap ma_hib;
   if (hib && (rc = tc_make_map_bf16(h, &ma_hib, hib, 3, dims, strides_b, tc::kBM))) return rc;
   if (lob) { if ((rc = tc_make_map_bf16(h, &ma_lo, lo, 3, dims, strides_b, tc::kBM))) return rc; }
@@ -1047,7 +1078,9 @@ int mimi_b200_debug_tc_gemm(mimi_b200_t* h, const float* d_a, const float* h_w, 
   tc::Epilogue ep{};
   ep.bias = d_bias_opt; ep.out_raw = d_out; ep.raw_item_stride = (long long)M * N; ep.act = act;
   ep.uniform_len_in = M; ep.conv_stride = 1; ep.N = N;
-  ep.single_acc = h->exp_single_acc; ep.chunk_kb = h->exp_chunk_kb; ep.lo_bf16 = lob;
+  ep.single_acc = h->exp_single_acc; ep.chunk_kb = h->exp_chunk_kb; ep.lo_bf16 = f16 ? 3 : lob;
+  ep.wscale = f16 ? w.wscale : nullptr;
+  if (f16 && !tcp_applies(h, w)) return fail(h, MIMI_B200_ERR_ARG, "debug_tc_gemm: mode 9 needs N % 64 == 0");
   if (tcp_applies(h, w)) {
     launch_tcp(h, ma_hi, ma_lo, w, ep, 1, (M + tc::kBM - 1) / tc::kBM, st, 1, 1, 0, nullptr, 0, hib ? &ma_hib : nullptr);
   } else if (h->mode == 4) {

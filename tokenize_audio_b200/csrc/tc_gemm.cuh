@@ -46,7 +46,14 @@ struct Epilogue {
   int single_acc;               // experiment (tc_gemm2 only): cross terms accumulate into the main accumulator
   int chunk_kb;                 // experiment (tc_gemm2 only): k-blocks per accumulation chunk (0 -> kChunkKB)
   int prefetch_next;            // tc_gemm2: L2-prefetch the next tile's activation boxes
-  int lo_bf16;                  // 1: out_lo is a bf16 array (mode 7), same element indexing as out_hi
+  int lo_bf16;                  // 1: out_lo is a bf16 array (mode 7), same element indexing as out_hi; 3: out_hi and out_lo are
+                                //    fp16 arrays in the split_f16 format (mode 9)
+  const float* wscale;          // [N] per-column power-of-two factor that undoes the weight scaling of mode 9, or nullptr
+  // Flattened linears (the B items as one [B * flat_rows][C] matrix, see tc_host.inl): rows past an item's length hold
+  // whatever an earlier call left there. They are computed (rows are independent) but neither stored nor allowed to raise
+  // the fp16 range flag: row r belongs to item r / flat_rows and is real iff r % flat_rows < flat_len[item].
+  const int* flat_len;          // device [B] or nullptr (every row real)
+  int flat_rows;                // 0: not a flattened launch
   float* out_hib;               // mode 8: bf16(hi) array of the split output (same indexing), or nullptr
 };
 
@@ -341,7 +348,8 @@ __global__ void zero_halo_kernel(float* hi, float* lo, long long item_stride, in
     const int c = i - r * C;
     if (r >= front) r = front + L + (r - front);
     const long long o = (long long)b * item_stride + (long long)r * C + c;
-    hi[o] = 0.f;
+    if (lob == 3) reinterpret_cast<uint16_t*>(hi)[o] = 0;
+    else hi[o] = 0.f;
     if (lob) reinterpret_cast<uint16_t*>(lo)[o] = 0;
     else lo[o] = 0.f;
     if (hib) reinterpret_cast<uint16_t*>(hib)[o] = 0;

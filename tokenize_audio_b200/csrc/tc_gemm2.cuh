@@ -170,6 +170,16 @@ __device__ __forceinline__ void finish_tile(const Epilogue& ep, float (&acc)[HAL
   const int cj = lane % LPR;                     //                  float4 index inside the PC-wide piece
   const long long raw_base = (long long)b * ep.raw_item_stride + ncol0;
   const long long split_base = (long long)b * ep.split_item_stride + (long long)ep.split_front * ep.N + ncol0;
+  // rows of this thread's coalesced phase that exist (bit `it`): inside the tile's item, and -- in a flattened launch -- inside
+  // the length of the item the row falls into
+  uint32_t live = 0;
+#pragma unroll
+  for (int it = 0; it < IT; ++it) {
+    const int row = row_base + it * RPI + rr;
+    bool ok = row < Lout;
+    if (ok && ep.flat_rows > 0 && ep.flat_len) ok = (row % ep.flat_rows) < __ldg(ep.flat_len + row / ep.flat_rows);
+    live |= (uint32_t)ok << it;
+  }
 #pragma unroll
   for (int p = 0; p < NP; ++p) {
     float4 resv[IT];
@@ -178,7 +188,7 @@ __device__ __forceinline__ void finish_tile(const Epilogue& ep, float (&acc)[HAL
       for (int it = 0; it < IT; ++it) {
         const int row = row_base + it * RPI + rr;
         resv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row < Lout) resv[it] = *reinterpret_cast<const float4*>(ep.res + raw_base + (long long)row * ep.N + p * PC + cj * 4);
+        if ((live >> it) & 1u) resv[it] = *reinterpret_cast<const float4*>(ep.res + raw_base + (long long)row * ep.N + p * PC + cj * 4);
       }
     }
     const int wkey = (LPR == 8) ? (lane & 7) : ((lane >> 1) & (LPR - 1));
@@ -186,6 +196,10 @@ __device__ __forceinline__ void finish_tile(const Epilogue& ep, float (&acc)[HAL
     for (int j = 0; j < LPR; ++j) {
       float4 v = make_float4(acc[p * PC + 4 * j], acc[p * PC + 4 * j + 1], acc[p * PC + 4 * j + 2], acc[p * PC + 4 * j + 3]);
       const int c = ncol0 + p * PC + 4 * j;
+      if (ep.wscale) {
+        const float4 t = ld_nc_f4(ep.wscale + c);
+        v.x *= t.x; v.y *= t.y; v.z *= t.z; v.w *= t.w;
+      }
       if (ep.bias) {
         const float4 t = ld_nc_f4(ep.bias + c);
         v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
@@ -210,7 +224,7 @@ __device__ __forceinline__ void finish_tile(const Epilogue& ep, float (&acc)[HAL
       const int r = it * RPI + rr;
       float4 v = tv[it];
       const int row = row_base + r;
-      if (row < Lout) {
+      if ((live >> it) & 1u) {
         const long long o = (long long)row * ep.N + p * PC + cj * 4;
         if (ep.res) { v.x += resv[it].x; v.y += resv[it].y; v.z += resv[it].z; v.w += resv[it].w; }
         if (ep.out_raw) *reinterpret_cast<float4*>(ep.out_raw + raw_base + o) = v;

@@ -58,17 +58,22 @@ __device__ unsigned* g_tcp_marks = nullptr;
 // LOB = 2 (mode 8, inputs that also carry hib = bf16(hi)): BOTH cross terms on kind::f16 -- A_hib * W_lob and
 // A_lob * W_hib -- 2 tensor passes instead of 3; the stage holds A_hi (fp32), A_hib, A_lob (bf16), W_hi (fp32), W_hib,
 // W_lob (bf16): the same bytes as LOB = 1.
+// LOB = 3 (mode 9, the fp16 generation): every operand is an fp16 array in SWIZZLE_64B tiles -- A_hi16, A_lo16 (= (x - hi) * 2048),
+// W_hi16, W_lo16 and W_hs16 = W_hi16 / 2048 of the row-scaled weights (common.cuh: split_f16) -- and all three products
+// A_hi*W_hi + A_hi*W_lo + A_lo*W_hs run on kind::f16: 6 MMAs of K = 16 per k-block instead of 8 of K = 8 plus 2 of K = 16
+// (3 tensor passes at the 16-bit rate instead of 5 pass units), and the stage shrinks from 64 KB to 40 KB.
 template <int BNP, int LOB = 0>
 struct Cfg {
   static constexpr int WB = BNP / 2;                                 // weight rows staged by each CTA
   static constexpr int A_BYTES = kBM * kBK * 4;                      // 16 KB
   static constexpr int W_BYTES = WB * kBK * 4;
   // LOB 0: [A_hi | A_lo | W_hi | W_lo]   LOB 1: [A_hi | A_lob | W_hi | W_lo | W_hib]   LOB 2: [A_hi | A_lob | A_hib | W_hi | W_hib | W_lob]
-  static constexpr int OFF_ALO = A_BYTES;
+  // LOB 3: [A_hi16 | A_lo16 | W_hi16 | W_lo16 | W_hs16]
+  static constexpr int OFF_ALO = LOB == 3 ? A_BYTES / 2 : A_BYTES;
   static constexpr int OFF_AHB = OFF_ALO + (LOB ? A_BYTES / 2 : A_BYTES);              // LOB 2 only
   static constexpr int OFF_WHI = OFF_AHB + (LOB == 2 ? A_BYTES / 2 : 0);
-  static constexpr int OFF_WLO = OFF_WHI + W_BYTES;                                     // fp32 W_lo (LOB 0, 1)
-  static constexpr int OFF_WHB = OFF_WLO + (LOB == 2 ? 0 : W_BYTES);                    // bf16(W_hi) (LOB 1, 2)
+  static constexpr int OFF_WLO = OFF_WHI + (LOB == 3 ? W_BYTES / 2 : W_BYTES);          // fp32 W_lo (LOB 0, 1), W_lo16 (LOB 3)
+  static constexpr int OFF_WHB = OFF_WLO + (LOB == 2 ? 0 : LOB == 3 ? W_BYTES / 2 : W_BYTES);   // bf16(W_hi) (LOB 1, 2), W_hs16 (LOB 3)
   static constexpr int OFF_WLB = OFF_WHB + (LOB ? W_BYTES / 2 : 0);                     // bf16(W_lo) (LOB 2)
   static constexpr int STAGE = OFF_WLB + (LOB == 2 ? W_BYTES / 2 : 0);                  // per CTA
   static constexpr int PC = 16;
@@ -78,13 +83,13 @@ struct Cfg {
   static constexpr int STAGES_RAW = (kSmemMax - 1024 - STG - BAR_BYTES) / STAGE;
   static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
   static constexpr int SMEM = 1024 + STAGES * STAGE + STG + BAR_BYTES;
-  static constexpr int TMEM_COLS = 2 * BNP;
+  static constexpr int TMEM_COLS = 2 * BNP < 32 ? 32 : 2 * BNP;
   static constexpr int HALF = BNP / (kEpiWarps / 4);                 // accumulator columns per epilogue thread
   static_assert(BNP == 64 || BNP == 128 || BNP == 256, "BNP");
   static_assert(BNP >= 128 || LOB, "64-column pair tiles only exist in the bf16-lo generations");
   static_assert(STAGES >= 3, "ring too shallow");
-  static_assert(STAGE % 1024 == 0 && OFF_WHI % 1024 == 0 && OFF_WLO % 1024 == 0 && OFF_WHB % 512 == 0 && OFF_WLB % 512 == 0 &&
-                    OFF_AHB % 1024 == 0, "operand alignment");
+  static_assert(STAGE % 1024 == 0 && OFF_WHI % 1024 == 0 && OFF_WLO % (LOB == 3 ? 512 : 1024) == 0 && OFF_WHB % 512 == 0 &&
+                    OFF_WLB % 512 == 0 && OFF_AHB % 1024 == 0 && OFF_ALO % 512 == 0, "operand alignment");
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -140,6 +145,10 @@ __device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint32_t a_lo32,
 constexpr uint32_t kDescHi64 = (uint32_t)(512 >> 4) | (1u << 14) | (4u << 29);
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+// kind::f16 with fp16 A and B (format 0), fp32 accumulator
+__host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 __device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint32_t a_lo32, uint32_t b_lo32, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -286,7 +295,19 @@ tcp_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
             constexpr uint32_t kAlo = C::OFF_ALO >> 4, kWhi = C::OFF_WHI >> 4, kWlo = C::OFF_WLO >> 4, kWhb = C::OFF_WHB >> 4;
             constexpr uint32_t kAhb = C::OFF_AHB >> 4, kWlb = C::OFF_WLB >> 4;
             const bool first_in_chunk = kb == c * ckb;
-            if (tc::elect_one()) {
+            if (LOB == 3) {
+              if (tc::elect_one()) {
+                constexpr uint32_t idesc_h = make_idesc_f16(2 * kBM, BNP);
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {   // 32 fp16 = two K = 16 steps of 32 B
+                  umma_bf16_pair(tmem_acc, d_ahi + 2 * k, d_ahi + kWhi + 2 * k, idesc_h, !(first_in_chunk && k == 0));
+                  umma_bf16_pair(tmem_acc, d_ahi + 2 * k, d_ahi + kWlo + 2 * k, idesc_h, 1u);
+                  umma_bf16_pair(tmem_acc, d_ahi + kAlo + 2 * k, d_ahi + kWhb + 2 * k, idesc_h, 1u);
+                }
+                umma_commit_pair(&empty_bar[s]);
+                if (kb + 1 == kb_end) umma_commit_pair(&acc_full[buf]);
+              }
+            } else if (tc::elect_one()) {
 #pragma unroll
               for (int k = 0; k < kBK / kUmmaK; ++k) {
                 umma_tf32_pair(tmem_acc, d_ahi + 2 * k, d_ahi + kWhi + 2 * k, idesc, !(first_in_chunk && k == 0));

@@ -105,6 +105,42 @@ static int tc_make_weight(mimi_b200* h, TcWeight* w, const std::vector<float>& w
     if (N % 64 == 0 && (rc = tc_make_map_bf16(h, &w->map64_lob, w->lob, 2, dims, strides_b, 64))) return rc;
     if ((rc = tc_make_map_bf16(h, &w->map32_lob, w->lob, 2, dims, strides_b, 32))) return rc;
   }
+  {
+    // fp16 generation (mode 9): per-row power-of-two scaling, then W' = h16 + l16 with s16 = h16 / 2048
+    const size_t nk = (size_t)N * K;
+    std::vector<uint16_t> f((size_t)3 * nk);
+    std::vector<float> ws(N);
+    auto bits = [](float v) { const __half hh = __float2half_rn(v); uint16_t u; memcpy(&u, &hh, 2); return u; };
+    for (int n = 0; n < N; ++n) {
+      float mx = 0.f;
+      for (int k = 0; k < K; ++k) mx = std::max(mx, std::fabs(w_nk[(size_t)n * K + k]));
+      int e = 0;
+      if (mx > 0.f && std::isfinite(mx)) {
+        int ex;
+        std::frexp(mx, &ex);                 // mx = m * 2^ex, m in [0.5, 1)  ->  mx * 2^(14 - ex) in [2^13, 2^14)
+        e = 14 - ex;
+      }
+      ws[n] = std::ldexp(1.0f, -e);
+      for (int k = 0; k < K; ++k) {
+        const float v = std::ldexp(w_nk[(size_t)n * K + k], e);
+        const float vh = __half2float(__float2half_rn(v));
+        f[(size_t)n * K + k] = bits(vh);
+        f[nk + (size_t)n * K + k] = bits(v - vh);
+        f[2 * nk + (size_t)n * K + k] = bits(vh * (1.0f / 2048.0f));
+      }
+    }
+    CUDA_TRY(h, cudaMalloc((void**)&w->f16, f.size() * sizeof(uint16_t)));
+    h->allocs.push_back(w->f16);
+    CUDA_TRY(h, cudaMemcpy(w->f16, f.data(), f.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    if ((rc = dev_upload(h, &w->wscale, ws))) return rc;
+    const cuuint64_t strides_b[1] = {(cuuint64_t)K * 2};
+    const int rows[3] = {128, 64, 32};
+    for (int part = 0; part < 3; ++part)
+      for (int r = 0; r < 3; ++r) {
+        if (rows[r] > N) continue;
+        if ((rc = tc_make_map_bf16(h, &w->map_f16[part][r], w->f16 + (size_t)part * nk, 2, dims, strides_b, rows[r]))) return rc;
+      }
+  }
   return MIMI_B200_OK;
 }
 
@@ -146,7 +182,8 @@ static int tc_load_weights(mimi_b200* h, const mimi_b200_weights_t* w) {
 // `level0` = also lay out the level-0 buffers the unfused modes (1, 2) need; the default path keeps the 24 kHz
 // activations on chip, which saves 27.6 MB of workspace per audio-second
 // `lob` = the lo arrays are bf16 (mode 7): half the bytes
-static PlanTC make_plan_tc(int B, long long N, int K, bool level0, bool lob = false, bool hibf = false) {
+// `f16` = both arrays of every split buffer are fp16 (mode 9): 4 bytes per element
+static PlanTC make_plan_tc(int B, long long N, int K, bool level0, bool lob = false, bool hibf = false, bool f16 = false) {
   PlanTC p;
   p.B = B; p.K = K; p.N = N;
   long long L = N;
@@ -159,8 +196,8 @@ static PlanTC make_plan_tc(int B, long long N, int K, bool level0, bool lob = fa
     SplitBuf s;
     s.level = level; s.C = C; s.front = front; s.back = back;
     s.item_stride = (long long)(front + p.rows[level] + back) * C;
-    s.hi = take((long long)B * s.item_stride + 64);
-    s.lo = take(lob ? ((long long)B * s.item_stride + 64 + 1) / 2 : (long long)B * s.item_stride + 64);
+    s.hi = take(f16 ? ((long long)B * s.item_stride + 64 + 1) / 2 : (long long)B * s.item_stride + 64);
+    s.lo = take(lob || f16 ? ((long long)B * s.item_stride + 64 + 1) / 2 : (long long)B * s.item_stride + 64);
     // mode 8: the tensor-bound layers (levels >= 2) also get bf16(hi); the HBM-bound level-0/1 edges stay at 6 bytes
     s.hib = (hibf && level >= 2) ? take(((long long)B * s.item_stride + 64 + 1) / 2) : -1;
     return s;
@@ -261,8 +298,11 @@ static int tc_amaps(TcCtx& c, int slot, const SplitBuf& a, int k, int s, int pad
     const long long base_off = (long long)(a.front - pad) * a.C;
     if (a.front < pad) return fail(c.h, MIMI_B200_ERR_ARG, "tc: halo smaller than conv padding");
     int rc;
-    if ((rc = tc_make_map(c.h, mh, c.ws + a.hi + base_off, 3, dims, strides, tc::kBM))) return rc;
-    if (c.h->mode >= 7) {   // lo is a bf16 array with the element indexing of hi
+    if (c.h->mode == 9) {   // hi is an fp16 array too
+      const cuuint64_t strides_h[2] = {strides[0] / 2, strides[1] / 2};
+      if ((rc = tc_make_map_bf16(c.h, mh, reinterpret_cast<const uint16_t*>(c.ws + a.hi) + base_off, 3, dims, strides_h, tc::kBM))) return rc;
+    } else if ((rc = tc_make_map(c.h, mh, c.ws + a.hi + base_off, 3, dims, strides, tc::kBM))) return rc;
+    if (c.h->mode >= 7) {   // lo is a bf16 (mode 9: fp16) array with the element indexing of hi
       const cuuint64_t strides_b[2] = {strides[0] / 2, strides[1] / 2};
       if ((rc = tc_make_map_bf16(c.h, ml, reinterpret_cast<const uint16_t*>(c.ws + a.lo) + base_off, 3, dims, strides_b, tc::kBM))) return rc;
     } else if ((rc = tc_make_map(c.h, ml, c.ws + a.lo + base_off, 3, dims, strides, tc::kBM))) return rc;
@@ -334,6 +374,15 @@ static void launch_tcp(mimi_b200* h, const CUtensorMap& ahi, const CUtensorMap& 
   const long long npairs = (((tiles ? (long long)ntiles : (long long)mt_max * B) + 1) / 2) * sc.ntn;
   const int ncl = (int)std::min<long long>(npairs, h->num_clusters);
   if (ncl <= 0) return;
+  if (h->mode == 9) {
+    // fp16 generation: all five operand tiles are 16-bit SWIZZLE_64B boxes; weight boxes of bnp / 2 rows
+    const int r = bnp == 256 ? 0 : bnp == 128 ? 1 : 2;
+    const CUtensorMap &whi = w.map_f16[0][r], &wlo = w.map_f16[1][r], &whs = w.map_f16[2][r];
+    if (bnp == 256) tcp::tcp_gemm_kernel<256, 3><<<2 * ncl, tcp::kThreads, tcp::Cfg<256, 3>::SMEM, st>>>(ahi, alo, whi, wlo, whs, ahi, whs, w.K, ep, sc);
+    else if (bnp == 128) tcp::tcp_gemm_kernel<128, 3><<<2 * ncl, tcp::kThreads, tcp::Cfg<128, 3>::SMEM, st>>>(ahi, alo, whi, wlo, whs, ahi, whs, w.K, ep, sc);
+    else tcp::tcp_gemm_kernel<64, 3><<<2 * ncl, tcp::kThreads, tcp::Cfg<64, 3>::SMEM, st>>>(ahi, alo, whi, wlo, whs, ahi, whs, w.K, ep, sc);
+    return;
+  }
   if (h->mode >= 7) {
     // bf16-lo generations: every layer with N % 64 == 0 (alo is a bf16 map); box rows of the weight maps = bnp / 2.
     // With a bf16(hi) map of the input (mode 8, levels >= 2) both cross terms run on kind::f16 (LOB = 2).
@@ -384,14 +433,18 @@ static int tc_gemm(TcCtx& c, int slot, const SplitBuf& a, int k, int s, int pad,
     ep.split_item_stride = o.split->item_stride; ep.split_front = o.split->front;
     ep.out_hib = o.split->hib >= 0 ? c.ws + o.split->hib : nullptr;
   }
-  ep.act = o.act; ep.elu_split = o.elu_split; ep.lo_bf16 = c.h->mode >= 7;
+  ep.act = o.act; ep.elu_split = o.elu_split; ep.lo_bf16 = c.h->mode == 9 ? 3 : c.h->mode >= 7;
+  ep.wscale = c.h->mode == 9 ? w.wscale : nullptr;
   ep.single_acc = c.h->exp_single_acc; ep.chunk_kb = c.h->exp_chunk_kb;
   ep.prefetch_next = c.h->exp_prefetch && w.N / w.BN == 1;      // with several n-tiles the rows are in L2 already
   ep.len_in = c.dlen[a.level]; ep.uniform_len_in = c.maxlen[a.level]; ep.conv_stride = s; ep.N = w.N;
   int lout_max = (c.maxlen[a.level] + s - 1) / s;
   if (lout_max <= 0) return MIMI_B200_OK;
   int nb = c.B;
-  if (flat) { ep.len_in = nullptr; ep.uniform_len_in = c.B * rows_lvl; lout_max = c.B * rows_lvl; nb = 1; }
+  if (flat) {
+    ep.flat_len = c.dlen[a.level]; ep.flat_rows = rows_lvl;      // rows past an item's length: computed, not stored
+    ep.len_in = nullptr; ep.uniform_len_in = c.B * rows_lvl; lout_max = c.B * rows_lvl; nb = 1;
+  }
   // ragged call: the compact list of the output level's tiles (the output of a strided conv lives one level up)
   const int out_level = a.level + (s > 1 ? 1 : 0);
   const int* tiles = (!flat && out_level < 6) ? c.h->tile_ptr[out_level] : nullptr;
@@ -472,7 +525,7 @@ static int tc_zero_halo(TcCtx& c, const SplitBuf& s) {
   const int per = (s.front + s.back) * s.C;
   dim3 grid((per + 255) / 256, c.B);
   tc::zero_halo_kernel<<<grid, 256, 0, c.st>>>(c.ws + s.hi, c.ws + s.lo, s.item_stride, s.C, s.front, s.back,
-                                               c.dlen[s.level], c.maxlen[s.level], c.h->mode >= 7,
+                                               c.dlen[s.level], c.maxlen[s.level], c.h->mode == 9 ? 3 : c.h->mode >= 7,
                                                s.hib >= 0 ? c.ws + s.hib : nullptr);
   c.h->launches++;
   mark(c.h, 25, c.st);
@@ -484,7 +537,7 @@ static int encode_tc(mimi_b200* h, const float* d_input, int B, long long N, int
                      const int* const* dlen, const int* maxlen, const int* dprefix, int total_frames,
                      int64_t* d_codes, float* d_latent_opt, cudaStream_t st) {
   int rc;
-  const MapKey key{ws, B, N, h->mode < 3 ? 1 : h->mode == 7 ? 3 : h->mode == 8 ? 4 : 0};   // 2 = the raw-fp32 plan of mode 5 (tc5_host.inl)
+  const MapKey key{ws, B, N, h->mode < 3 ? 1 : h->mode == 7 ? 3 : h->mode == 8 ? 4 : h->mode == 9 ? 5 : 0};   // 2 = the raw-fp32 plan of mode 5 (tc5_host.inl)
   auto it = h->amap_cache.find(key);
   TcCtx c{h, &p, ws, B, st, dlen, maxlen, nullptr, nullptr, nullptr, nullptr, nullptr};
   if (it == h->amap_cache.end()) {
@@ -512,7 +565,7 @@ static int encode_tc(mimi_b200* h, const float* d_input, int B, long long N, int
 
   // the 24 kHz activation h1 (64 channels, the largest tensor of the pipeline) crosses HBM once as raw fp32 instead of as
   // an ELU'd hi/lo pair: the front end stores it raw, the first strided conv splits it in shared memory (tc_gemm4.cuh)
-  const int raw_h1 = h->mode >= 3 && h->mode != 4 && h->exp_raw_h1;
+  const int raw_h1 = h->mode >= 3 && h->mode != 4 && h->mode != 9 && h->exp_raw_h1;
   // ---- level 0 on CUDA cores: L0 (1->64 k7), R1a (64->32 k3), R1b (32->64 k1 + skip) ---------------------
   if (h->mode >= 3 && h->phase == MIMI_B200_PHASE_FINISH) {
     // phased call: the front end already ran, item group by item group (mimi_b200_encode_phase)
@@ -527,10 +580,10 @@ static int encode_tc(mimi_b200* h, const float* d_input, int B, long long N, int
       fp.B = nb;
       fp.mt_max = (maxlen[0] + f0::kAdv - 1) / f0::kAdv;
       // (the lo array is bf16 in modes >= 7: the same ELEMENT offset is half as many floats)
-      fp.out_hi = ws + p.s_h1.hi + (long long)b0 * p.s_h1.item_stride;
+      fp.out_hi = ws + p.s_h1.hi + (long long)b0 * p.s_h1.item_stride / (h->mode == 9 ? 2 : 1);
       fp.out_lo = ws + p.s_h1.lo + (long long)b0 * p.s_h1.item_stride / (h->mode >= 7 ? 2 : 1);
       fp.split_item_stride = p.s_h1.item_stride; fp.split_front = p.s_h1.front;
-      fp.raw_out = raw_h1; fp.lo_bf16 = h->mode >= 7;
+      fp.raw_out = raw_h1; fp.lo_bf16 = h->mode == 9 ? 3 : h->mode >= 7;
       const long long vt = (long long)fp.mt_max * nb;
       const int grid = (int)std::min<long long>(vt, h->num_sms);
       f0::front_fused_kernel<<<grid, f0::kThreads, f0::kSmem, st>>>(h->tc_conv[1].map_hi, h->tc_conv[1].map_lo, h->tc_conv[2].map_hi,
@@ -608,7 +661,7 @@ static int encode_tc(mimi_b200* h, const float* d_input, int B, long long N, int
   for (int l = 0; l < h->dbg_layers && T25 > 0; ++l) {
     const LayerDev& d = h->layer[l];
     dim3 lgrid((T25 + 7) / 8, B);
-    layernorm512_kernel<<<lgrid, 256, 0, st>>>(ws + p.z, ws + p.s_y.hi, d.ln1_w, d.ln1_b, rstride(4, 512), dlen[4], T25, ws + p.s_y.lo, h->mode >= 7, p.s_y.hib >= 0 ? ws + p.s_y.hib : nullptr);
+    layernorm512_kernel<<<lgrid, 256, 0, st>>>(ws + p.z, ws + p.s_y.hi, d.ln1_w, d.ln1_b, rstride(4, 512), dlen[4], T25, ws + p.s_y.lo, h->mode == 9 ? 3 : h->mode >= 7, p.s_y.hib >= 0 ? ws + p.s_y.hib : nullptr);
     h->launches++; mark(h, 14, st);
     TcOut o;
     o.raw = ws + p.qkv; o.raw_item_stride = rstride(4, 1536);
@@ -618,7 +671,7 @@ static int encode_tc(mimi_b200* h, const float* d_input, int B, long long N, int
       atc::Params ap{};
       ap.qkv = ws + p.qkv; ap.item_stride = rstride(4, 1536); ap.out_hi = ws + p.s_att.hi; ap.out_lo = ws + p.s_att.lo;
       ap.out_stride = rstride(4, 512); ap.rope_cos = h->rope_cos; ap.rope_sin = h->rope_sin; ap.len = dlen[4];
-      ap.uniform_len = T25; ap.B = B; ap.mt_max = (T25 + atc::kQT - 1) / atc::kQT; ap.lo_bf16 = h->mode >= 7;
+      ap.uniform_len = T25; ap.B = B; ap.mt_max = (T25 + atc::kQT - 1) / atc::kQT; ap.lo_bf16 = h->mode == 9 ? 3 : h->mode >= 7;
       ap.out_hib = p.s_att.hib >= 0 ? ws + p.s_att.hib : nullptr;
       const long long units = (long long)ap.mt_max * B * kHeads;
       atc::swa_attention_tc_kernel<<<(int)std::min<long long>(units, h->num_sms), atc::kThreads, atc::kSmem, st>>>(ap);
@@ -643,7 +696,7 @@ static int encode_tc(mimi_b200* h, const float* d_input, int B, long long N, int
     o = TcOut{};   // o_proj + LayerScale + residual, in place on z
     o.raw = ws + p.z; o.res = ws + p.z; o.raw_item_stride = rstride(4, 512); o.scale = d.ls1;
     if ((rc = tc_gemm(c, 1, p.s_att, 1, 1, 0, h->tc_o[l], o, 17))) return rc;
-    layernorm512_kernel<<<lgrid, 256, 0, st>>>(ws + p.z, ws + p.s_y.hi, d.ln2_w, d.ln2_b, rstride(4, 512), dlen[4], T25, ws + p.s_y.lo, h->mode >= 7, p.s_y.hib >= 0 ? ws + p.s_y.hib : nullptr);
+    layernorm512_kernel<<<lgrid, 256, 0, st>>>(ws + p.z, ws + p.s_y.hi, d.ln2_w, d.ln2_b, rstride(4, 512), dlen[4], T25, ws + p.s_y.lo, h->mode == 9 ? 3 : h->mode >= 7, p.s_y.hib >= 0 ? ws + p.s_y.hib : nullptr);
     h->launches++; mark(h, 14, st);
     o = TcOut{};   // fc1 + GELU(erf) -> split
     o.split = &p.s_ffn; o.act = 1;
@@ -657,7 +710,7 @@ static int encode_tc(mimi_b200* h, const float* d_input, int B, long long N, int
   if (T25 > 0) {
     dim3 pgrid((T25 + 3 + 7) / 8, B);
     tc::pad_replicate_split_kernel<<<pgrid, 256, 0, st>>>(ws + p.z, rstride(4, 512), ws + p.s_zp.hi, ws + p.s_zp.lo,
-                                                          p.s_zp.item_stride, dlen[4], T25, h->mode >= 7,
+                                                          p.s_zp.item_stride, dlen[4], T25, h->mode == 9 ? 3 : h->mode >= 7,
                                                           p.s_zp.hib >= 0 ? ws + p.s_zp.hib : nullptr);
     h->launches++; mark(h, 26, st);
     TcOut o;
@@ -694,6 +747,8 @@ static int encode_tc(mimi_b200* h, const float* d_input, int B, long long N, int
       h->launches++; mark(h, 22, st);
     }
   }
+  if (h->mode == 9 && h->range_flag)    // the fp16 generation's saturation flag rides behind the call on its stream
+    CUDA_TRY(h, cudaMemcpyFromSymbolAsync(h->range_flag, g_f16_overflow, sizeof(int), 0, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(h, cudaGetLastError());
   return MIMI_B200_OK;
 }

@@ -317,7 +317,7 @@ class MimiB200Model:
     @property
     def supports_phased(self) -> bool:
         """mimi_b200_encode_phase needs the fused front end (kernel generations 3, 4, 6)."""
-        return self._mode in (3, 4, 6, 7, 8)
+        return self._mode in (3, 4, 6, 7, 8, 9)
 
     def debug_set(self, key: int, value: int) -> None:
         if key == 3:
@@ -344,10 +344,21 @@ class MimiB200Model:
                      "rvq_input_proj", "rvq_fused", "latent_transpose", "code_fill", "halo_zero", "pad_split",
                      "front_fused"])
 
-    DEFAULT_MODE = 7
+    DEFAULT_MODE = 9
+    RANGE_SAFE_MODE = 7
+
+    def range_overflow(self, reset: bool = False) -> bool:
+        """True if an encode of the fp16 generation (mode 9, the default) that has COMPLETED on this device had to clamp an
+        activation to fp16's range (|x| > 65504) -- its codes are then not the reference's. Synchronise the stream of the
+        encode before asking. ``reset=True`` also clears the flag (synchronises the device). ``MimiEncoder`` checks this for
+        every batch and re-encodes with the range-safe TF32 generation (mode 7); callers of :meth:`encode` do the same with
+        ``set_mode(MimiB200Model.RANGE_SAFE_MODE)``."""
+        with torch.cuda.device(self.device):
+            return bool(self._lib.mimi_b200_range_overflow(self._h, 1 if reset else 0))
 
     def set_mode(self, tensor_cores) -> None:
-        """True / 7 (default): mode 6 with the lo parts of the activations stored as bf16 and the A_lo * W_hi product on
+        """True / 9 (default): mode 7 with every GEMM operand as an fp16 hi/lo pair, all three products on kind::f16 (3 tensor
+        passes, 4 bytes per activation element; fp16 range, see range_overflow); 7: mode 6 with the lo parts of the activations stored as bf16 and the A_lo * W_hi product on
         kind::f16 (2.5 tensor passes instead of 3, 6 instead of 8 bytes per activation element); 6: fused 24 kHz front end + CTA-pair (cta_group::2) tcgen05 3xTF32 GEMM for every layer with
         N % 128 == 0, the single-CTA persistent kernel for the rest; 3: the single-CTA kernel everywhere; 5: activations
         stored as raw fp32 and split inside the GEMM; 4: the same with the experimental third-generation GEMM (256-row tiles, plane-staged
@@ -423,6 +434,7 @@ class PendingBatch:
         self._slot, self._done, self._view = slot, done, view
         self.lengths, self.frames, self.format, self._extra = lengths, frames, fmt, extra
         self._consumed = False
+        self._redo = None          # (audio_arrays, sample_rate, kwargs, serial): what result() needs to re-encode range-safely
 
     def ready(self) -> bool:
         return self._done is None or self._done.query()
@@ -475,6 +487,10 @@ class MimiEncoder:
         self.slot_streams = True
         self._slot_stream: List[Optional[torch.cuda.Stream]] = [None] * self.DEPTH
         self._lock = threading.RLock()
+        self._spare = _Staging()          # staging of the (rare) range-safe re-encode
+        self._serial = 0
+        self._suspect_upto = -1           # batches submitted up to this serial ran while the fp16 range flag was up
+        self.range_fallbacks = 0          # batches re-encoded with the range-safe generation so far
         self._slots = [_Staging() for _ in range(self.DEPTH)]
         self._cur = 0
         self._copy_stream: Optional[torch.cuda.Stream] = None
@@ -620,7 +636,8 @@ class MimiEncoder:
 
     # -- pipelined API ---------------------------------------------------------------------------------------------
     def submit(self, audio_arrays: List[np.ndarray], sample_rate: int = 24000, fmt: str = "int64",
-               num_codebooks: Optional[int] = None, codebook_size: int = 2048, unicode_offset: int = 0xE000) -> PendingBatch:
+               num_codebooks: Optional[int] = None, codebook_size: int = 2048, unicode_offset: int = 0xE000,
+               _slot: Optional[_Staging] = None) -> PendingBatch:
         """Stage ``audio_arrays`` (host numpy clips at 24 kHz), queue the encode and the device->host copy of the result on
         the current stream, and return without waiting. ``fmt``: ``"int64"`` (``encode_audio_batch``'s arrays),
         ``"uint16"`` or ``"utf8"`` (``codes_to_chars`` strings of the first ``num_codebooks`` codebooks). At most
@@ -638,10 +655,10 @@ class MimiEncoder:
                 utils.validate_unicode_offset(unicode_offset, K, codebook_size)
             if B == 0:
                 return PendingBatch(None, None, None, [], [], fmt)
-            slot = self._next_slot()
+            slot = self._next_slot() if _slot is None else _slot
             caller, copy = self._streams()
             main, ws_slot = caller, 0
-            if self.slot_streams:
+            if self.slot_streams and _slot is None:
                 if self._slot_stream[slot.index] is None:
                     self._slot_stream[slot.index] = torch.cuda.Stream(device=self.model.device)
                 main, ws_slot = self._slot_stream[slot.index], slot.index
@@ -697,7 +714,11 @@ class MimiEncoder:
                 done = torch.cuda.Event()
                 done.record(main)
             p = PendingBatch(slot, done, view, lengths, frames, fmt, extra=blens if fmt == "utf8" else None)
-            slot.pending = p
+            self._serial += 1
+            p._redo = (list(audio_arrays), sample_rate,
+                       dict(num_codebooks=num_codebooks, codebook_size=codebook_size, unicode_offset=unicode_offset), self._serial)
+            if _slot is None:
+                slot.pending = p
             return p
 
     def _mark_front_done(self, slot: _Staging, stream: torch.cuda.Stream) -> None:
@@ -714,11 +735,32 @@ class MimiEncoder:
             if pending._done is None:
                 return pending._extra if pending._extra is not None else []
             pending._done.synchronize()
+            if self.model._mode == MimiB200Model.DEFAULT_MODE and pending._redo is not None and (
+                    pending._redo[3] <= self._suspect_upto or self.model.range_overflow()):
+                return self._redo_range_safe(pending)
             if pending.format == "utf8":
                 host = pending._view.numpy()
                 return [host[i, : pending._extra[i]].tobytes().decode("utf-8") for i in range(len(pending.lengths))]
             arr = pending._view.numpy()
             return [arr[i, :, :f].copy() for i, f in enumerate(pending.frames)]
+
+    def _redo_range_safe(self, pending: PendingBatch):
+        """An activation left fp16's range somewhere in this batch (or in one that was in flight with it): encode it again
+        with the TF32 generation, which has fp32's range. Rare by construction (|x| > 65504); costs a device synchronisation."""
+        audio, sample_rate, kw, serial = pending._redo
+        if self.model.range_overflow():
+            self._suspect_upto = self._serial           # everything submitted so far ran under the raised flag
+            self.model.range_overflow(reset=True)
+        torch.cuda.synchronize(self.model.device)
+        self.range_fallbacks += 1
+        self.model.set_mode(MimiB200Model.RANGE_SAFE_MODE)
+        try:
+            p2 = self.submit(audio, sample_rate, pending.format, _slot=self._spare, **kw)
+            p2._redo = None
+            return self.result(p2)
+        finally:
+            torch.cuda.synchronize(self.model.device)
+            self.model.set_mode(MimiB200Model.DEFAULT_MODE)
 
     def encode_stream(self, batches, sample_rate: int = 24000, fmt: str = "int64", **kw):
         """Generator over the results of ``batches`` (an iterable of lists of clips), in order, with two batches in flight:
