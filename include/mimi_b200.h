@@ -14,6 +14,8 @@
  *   mimi_b200_codes_to_utf8   <- utils.codes_to_chars        REF/emilia-mimi/utils.py:18-37,
  *                                REF/pretraining-data/converter.py:17-37
  *   mimi_b200_encoded_frames  <- MimiModel.get_encoded_length modeling_mimi.py:1490-1503
+ *   mimi_b200_decode          <- MimiModel.decode            modeling_mimi.py:1613-1679, called by utils.str_to_audio,
+ *                                REF/emilia-mimi/utils.py:72-81 (round-trip spot checks)
  *
  * Conventions: plain pointers and sizes only, no C++/torch types, no exceptions across the boundary.
  * Every function returns an int status (MIMI_B200_OK == 0). `d_` pointers are device memory on the
@@ -87,6 +89,26 @@ typedef struct {
      (modeling_mimi.py:538-560); NULL = computed by the library */
   const float* rope_inv_freq;
 } mimi_b200_weights_t;
+
+/* Decode-side tensors of MimiModel.state_dict(), host fp32. */
+typedef struct {
+  const float* semantic_output_proj_weight;     /* quantizer.semantic_residual_vector_quantizer.output_proj.weight [512,256,1] */
+  const float* acoustic_output_proj_weight;     /* quantizer.acoustic_residual_vector_quantizer.output_proj.weight [512,256,1] */
+  const float* upsample_weight;                 /* upsample.conv.weight [512,1,4] (depthwise ConvTranspose1d, stride 2) */
+  mimi_b200_layer_weights_t layer[MIMI_B200_NUM_LAYERS];   /* decoder_transformer.layers.{l}.* */
+  const float* conv_in_weight;                  /* decoder.layers.0.conv.weight [1024,512,7] */
+  const float* conv_in_bias;                    /* [1024] */
+  /* the four upsampling stages, ratios 8, 6, 5, 4: decoder.layers.{2,5,8,11}.conv (ConvTranspose1d weight [C_in,C_out,2r],
+     bias [C_out]) and their residual blocks decoder.layers.{3,6,9,12}.block.{1,3}.conv (weight [C_out,C_in,k], bias) */
+  const float* up_weight[4];
+  const float* up_bias[4];
+  const float* res_a_weight[4];
+  const float* res_a_bias[4];
+  const float* res_b_weight[4];
+  const float* res_b_bias[4];
+  const float* conv_out_weight;                 /* decoder.layers.14.conv.weight [1,64,3] */
+  const float* conv_out_bias;                   /* [1] */
+} mimi_b200_decoder_weights_t;
 
 /* Library / ABI identification. */
 int mimi_b200_abi_version(void);
@@ -217,6 +239,17 @@ int64_t mimi_b200_utf8_bytes_per_frame(int K, uint32_t unicode_offset, int codeb
 int mimi_b200_codes_to_utf8(mimi_b200_t* h, const int64_t* d_codes, int B, int K, int64_t T,
                             const int64_t* h_frames, uint32_t unicode_offset, int codebook_size,
                             uint8_t* d_out, int64_t out_stride, int64_t* h_out_len_opt, void* stream);
+
+/*
+ * Decode direction: d_codes [B,K,T] int64 (K = 1..32 codebooks, as MimiModel.decode accepts) -> d_audio [B,1,1920*T] fp32
+ * at 24 kHz. Needs load_weights (codebooks) and load_decoder_weights. Runs on the exact-fp32 FFMA kernels: this is the
+ * reference's round-trip spot-check path (REF/emilia-mimi/utils.py:72-81), not a throughput path. Codes outside [0, 2048)
+ * contribute nothing (the caller validates them; F.embedding would raise).
+ */
+int mimi_b200_load_decoder_weights(mimi_b200_t* h, const mimi_b200_decoder_weights_t* host_weights);
+int mimi_b200_decode_workspace_bytes(mimi_b200_t* h, int B, int64_t T, size_t* out_bytes);
+int mimi_b200_decode(mimi_b200_t* h, const int64_t* d_codes, int B, int K, int64_t T, float* d_audio, void* d_workspace,
+                     size_t workspace_bytes, void* stream);
 
 /*
  * codes int64 -> uint16, n elements of any shape (the `codes.astype(np.uint16)` storage format of

@@ -158,7 +158,8 @@ def sliding_window_attention(q: np.ndarray, k: np.ndarray, v: np.ndarray, window
     return out
 
 
-def encoder_transformer(sd: Dict[str, np.ndarray], z: np.ndarray, taps: Optional[dict] = None) -> np.ndarray:
+def encoder_transformer(sd: Dict[str, np.ndarray], z: np.ndarray, taps: Optional[dict] = None,
+                        prefix: str = "encoder_transformer") -> np.ndarray:
     """MimiTransformerModel.forward TF:1015-1140 over MimiTransformerLayer.forward TF:939-993.
     ``z`` [T25, 512] -> [T25, 512]. Pre-LN blocks, LayerScale on both branches (TF:499-511),
     no linear biases, no final norm, positions arange(T25), no padding information."""
@@ -166,7 +167,7 @@ def encoder_transformer(sd: Dict[str, np.ndarray], z: np.ndarray, taps: Optional
     cos, sin = rope_tables(T)
     z = z.astype(F32, copy=True)
     for l in range(8):
-        p = f"encoder_transformer.layers.{l}"
+        p = f"{prefix}.layers.{l}"
         y = layer_norm(z, sd[f"{p}.input_layernorm.weight"], sd[f"{p}.input_layernorm.bias"])
         def heads(w):
             return (y @ sd[w].T.astype(F32)).reshape(T, N_HEADS, HEAD_DIM).transpose(1, 0, 2)
@@ -273,4 +274,69 @@ def encode(sd: Dict[str, np.ndarray], input_values: np.ndarray, num_quantizers: 
             for k_, v_ in t.items():
                 taps.setdefault(k_, []).append(v_)
         out.append(rvq_encode(sd, e, K, margins))
+    return np.stack(out, axis=0)
+
+
+# ---- decode direction: MimiModel.decode TF:1613-1679 / _decode_frame TF:1594-1611 -----------------
+
+def conv_transpose1d_causal(x: np.ndarray, w: np.ndarray, b: Optional[np.ndarray], stride: int, groups: int = 1) -> np.ndarray:
+    """MimiConvTranspose1d.forward TF:403-409 with the causal trimming of TF:383-391 (trim_right_ratio = 1: the last
+    k - stride outputs are dropped, none on the left). ``x`` [C_in, L], ``w`` [C_in, C_out/groups, k] (nn.ConvTranspose1d
+    layout) -> [C_out, L * stride].  full[o, i*stride + tau] += x[c, i] * w[c, o, tau]."""
+    cin, cog, k = w.shape
+    L = x.shape[1]
+    full_len = (L - 1) * stride + k
+    x = x.astype(F32, copy=False)
+    if groups == 1:
+        full = np.zeros((cog, full_len), F32)
+        for tau in range(k):
+            full[:, tau: tau + (L - 1) * stride + 1: stride] += w[:, :, tau].T.astype(F32) @ x
+    else:                                   # depthwise (groups == C_in == C_out): TF:1433-1441
+        assert groups == cin and cog == 1
+        full = np.zeros((cin, full_len), F32)
+        for tau in range(k):
+            full[:, tau: tau + (L - 1) * stride + 1: stride] += w[:, 0, tau:tau + 1].astype(F32) * x
+    if b is not None:
+        full += b.astype(F32)[:, None]
+    return full[:, : full_len - (k - stride)]
+
+
+def rvq_decode(sd: Dict[str, np.ndarray], codes: np.ndarray) -> np.ndarray:
+    """MimiSplitResidualVectorQuantizer.decode TF:1340-1350 over MimiResidualVectorQuantizer.decode TF:1282-1297:
+    codes [K, T] -> [512, T]: per RVQ the sum of the codebook rows, then that RVQ's output_proj (1x1 conv, no bias)."""
+    out = np.zeros((512, codes.shape[1]), F32)
+    for which, lo, hi in (("semantic", 0, 1), ("acoustic", 1, codes.shape[0])):
+        if hi <= lo:
+            continue
+        p = f"quantizer.{which}_residual_vector_quantizer"
+        q = np.zeros((codes.shape[1], 256), F32)
+        for s in range(lo, hi):
+            q = q + codebook_embed(sd, f"{p}.layers.{s - lo}")[codes[s]]
+        out = out + (sd[f"{p}.output_proj.weight"][:, :, 0].astype(F32) @ q.T)
+    return out.astype(F32)
+
+
+def seanet_decoder(sd: Dict[str, np.ndarray], z: np.ndarray) -> np.ndarray:
+    """MimiDecoder.forward TF:1169-1174 (layers built at TF:1146-1167): conv k7, then per ratio (8, 6, 5, 4)
+    ELU -> ConvTranspose1d(k = 2r, stride r) -> residual block, then ELU -> conv k3 to one channel. [512, T25] -> [1, 960*T25]."""
+    def conv(name, h, stride=1):
+        return conv1d_causal(h, sd[f"{name}.conv.weight"], sd[f"{name}.conv.bias"], stride)
+    h = conv("decoder.layers.0", z)
+    for up, res, r in (("decoder.layers.2", "decoder.layers.3", 8), ("decoder.layers.5", "decoder.layers.6", 6),
+                       ("decoder.layers.8", "decoder.layers.9", 5), ("decoder.layers.11", "decoder.layers.12", 4)):
+        h = conv_transpose1d_causal(elu(h), sd[f"{up}.conv.weight"], sd[f"{up}.conv.bias"], r)
+        t = conv(f"{res}.block.1", elu(h))
+        t = conv(f"{res}.block.3", elu(t))
+        h = h + t
+    return conv("decoder.layers.14", elu(h))
+
+
+def decode(sd: Dict[str, np.ndarray], audio_codes: np.ndarray) -> np.ndarray:
+    """MimiModel.decode: ``audio_codes`` [B, K, T] int -> audio_values [B, 1, 1920*T] fp32."""
+    out = []
+    for b in range(audio_codes.shape[0]):
+        e = rvq_decode(sd, np.asarray(audio_codes[b]))
+        u = conv_transpose1d_causal(e, sd["upsample.conv.weight"], None, 2, groups=512)          # TF:1596
+        z = encoder_transformer(sd, u.T, prefix="decoder_transformer").T                           # TF:1597-1604
+        out.append(seanet_decoder(sd, z))
     return np.stack(out, axis=0)

@@ -147,6 +147,31 @@ def main():
                             weights_digest=digest)
         print("audio_to_str", len(s), "chars")
 
+    if not only or "mimi_decode" in only:
+        # decode direction (MimiModel.decode, modeling_mimi.py:1613-1679) on the seed-0 encode weights + seed-0 decode weights:
+        # random codes, K = 8 (what str_to_audio passes) and K = 32, T25 = 2T beyond the attention window for the first
+        sd_full = {**synth.synth_state_dict(0), **synth.decoder_state_dict(0)}
+        mfull = MimiModel(MimiConfig()).eval()
+        missing, unexpected = mfull.load_state_dict({k: torch.from_numpy(v) for k, v in sd_full.items()}, strict=False)
+        assert not missing and not unexpected, (missing, unexpected)
+        g = np.random.Generator(np.random.PCG64(11))
+        cases = {"weights_digest": synth.state_dict_digest(sd_full)}
+        for tag, B, K, T in (("k8", 2, 8, 140), ("k32", 1, 32, 9), ("k1", 1, 1, 5)):
+            codes = g.integers(0, 2048, size=(B, K, T), dtype=np.int64)
+            with torch.no_grad():
+                audio = mfull.decode(torch.from_numpy(codes)).audio_values.numpy()
+            assert audio.shape == (B, 1, 1920 * T)
+            cases[f"{tag}_codes"] = codes.astype(np.int16)
+            cases[f"{tag}_audio"] = audio.astype(np.float32)
+        # str_to_audio (REF/emilia-mimi/utils.py:72-81): string -> chars_to_codes -> decode(codes[None]).audio_values[0]
+        spec = importlib.util.spec_from_file_location("ref_converter", "/root/reference/pretraining-data/converter.py")
+        conv = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(conv)
+        s8 = conv.codes_to_chars(cases["k8_codes"][0].astype(np.int64), 2048, copy_before_conversion=True, unicode_offset=0xE000)
+        cases["k8_item0_utf8"] = np.frombuffer(s8.encode("utf-8"), np.uint8)
+        np.savez_compressed(os.path.join(HERE, "mimi_decode.npz"), **cases)
+        print("mimi_decode", {k: getattr(v, "shape", v) for k, v in cases.items()})
+
     if only and not ({"encoded_length", "codes_to_chars"} & only):
         return
     # get_encoded_length known answers (TF:1490-1503)

@@ -84,3 +84,18 @@ def test_error_behaviour(state_dict):
         O.encode(state_dict, x, 0)
     with pytest.raises(ValueError, match="channels must be 1 or 2"):
         O.encode(state_dict, np.zeros((1, 3, 1920), np.float32), 8)
+
+
+@pytest.mark.parametrize("tag", ["k8", "k32", "k1"])
+def test_oracle_decode_matches_transformers(state_dict, tag):
+    """Decode direction: the oracle's MimiModel.decode restatement against waveforms from the real transformers model."""
+    g = load_golden("mimi_decode")
+    sd = {**state_dict, **synth.decoder_state_dict(0)}
+    assert synth.state_dict_digest(sd) == str(g["weights_digest"])
+    codes = g[f"{tag}_codes"].astype(np.int64)
+    if tag == "k8":
+        codes = codes[:1, :, :40]            # the oracle is exact-causal: a prefix of frames gives a prefix of samples
+    audio = O.decode(sd, codes)
+    ref = g[f"{tag}_audio"][: codes.shape[0], :, : 1920 * codes.shape[2]]
+    assert audio.shape == ref.shape and audio.dtype == np.float32
+    assert np.linalg.norm(audio - ref) / np.linalg.norm(ref) < 1e-5

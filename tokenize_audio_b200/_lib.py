@@ -33,6 +33,25 @@ class Weights(C.Structure):
     ]
 
 
+class DecoderWeights(C.Structure):
+    _fields_ = [
+        ("semantic_output_proj_weight", c_void_p),
+        ("acoustic_output_proj_weight", c_void_p),
+        ("upsample_weight", c_void_p),
+        ("layer", LayerWeights * 8),
+        ("conv_in_weight", c_void_p),
+        ("conv_in_bias", c_void_p),
+        ("up_weight", c_void_p * 4),
+        ("up_bias", c_void_p * 4),
+        ("res_a_weight", c_void_p * 4),
+        ("res_a_bias", c_void_p * 4),
+        ("res_b_weight", c_void_p * 4),
+        ("res_b_bias", c_void_p * 4),
+        ("conv_out_weight", c_void_p),
+        ("conv_out_bias", c_void_p),
+    ]
+
+
 PHASE_BEGIN, PHASE_FRONT, PHASE_FINISH = 1, 2, 3      # MIMI_B200_PHASE_* (include/mimi_b200.h)
 
 # every symbol include/mimi_b200.h declares: name -> (restype, argtypes)
@@ -62,6 +81,9 @@ SYMBOLS = {
     "mimi_b200_utf8_bytes_per_frame": (C.c_int64, [C.c_int, C.c_uint32, C.c_int]),
     "mimi_b200_codes_to_utf8": (C.c_int, [c_void_p, c_void_p, C.c_int, C.c_int, C.c_int64, c_void_p,
                                           C.c_uint32, C.c_int, c_void_p, C.c_int64, c_void_p, c_void_p]),
+    "mimi_b200_load_decoder_weights": (C.c_int, [c_void_p, C.POINTER(DecoderWeights)]),
+    "mimi_b200_decode_workspace_bytes": (C.c_int, [c_void_p, C.c_int, C.c_int64, C.POINTER(C.c_size_t)]),
+    "mimi_b200_decode": (C.c_int, [c_void_p, c_void_p, C.c_int, C.c_int, C.c_int64, c_void_p, c_void_p, C.c_size_t, c_void_p]),
     "mimi_b200_codes_pack_u16": (C.c_int, [c_void_p, c_void_p, C.c_int64, c_void_p, c_void_p]),
     "mimi_b200_range_overflow": (C.c_int, [c_void_p, C.c_int]),
     "mimi_b200_launch_count": (C.c_int64, [c_void_p]),

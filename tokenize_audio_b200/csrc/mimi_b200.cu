@@ -33,6 +33,7 @@
 #include "tc_gemm6.cuh"
 #include "transformer.cuh"
 #include "attention_tc.cuh"
+#include "decode_kernels.cuh"
 
 using namespace mimi;
 
@@ -212,6 +213,13 @@ struct mimi_b200 {
   PlanTC last_tc;
   PlanR last_r;
   bool last_was_tc = false;
+  // decode direction (decode_host.inl): fp32 weights in the [K][N] layout of the FFMA GEMM
+  bool dec_loaded = false;
+  std::vector<void*> dec_allocs;
+  float *dec_proj_wt = nullptr, *dec_up_w = nullptr, *dec_in_wt = nullptr, *dec_in_b = nullptr, *dec_out_wt = nullptr, *dec_out_b = nullptr;
+  float *dec_up_wt[4] = {}, *dec_up_b[4] = {}, *dec_ra_wt[4] = {}, *dec_ra_b[4] = {}, *dec_rb_wt[4] = {}, *dec_rb_b[4] = {};
+  LayerDev dlayer[MIMI_B200_NUM_LAYERS] = {};
+  int* dec_bad = nullptr;
 };
 
 static std::string g_create_err;
@@ -407,6 +415,7 @@ static void design_taps(int sr_in, int sr_out, std::vector<float>& taps, int& c,
 
 #include "tc_host.inl"
 #include "tc5_host.inl"
+#include "decode_host.inl"
 
 // ratios the register-tiled polyphase resampler is instantiated for (16 k, 48 k, 8 k, 32 k, 12 k, 96 k -> 24 k, identity)
 static bool resample_poly_supported(int L, int M) {
@@ -530,6 +539,8 @@ void mimi_b200_destroy(mimi_b200_t* h) {
   if (h->dev_ints) cudaFree(h->dev_ints);
   if (h->dev_ints_ev) cudaEventDestroy(h->dev_ints_ev);
   if (h->range_flag) cudaFreeHost(h->range_flag);
+  for (void* p : h->dec_allocs) cudaFree(p);
+  if (h->dec_bad) cudaFree(h->dec_bad);
   for (cudaEvent_t e : h->prof_pool) cudaEventDestroy(e);
   for (auto& kv : h->taps) { cudaFree(kv.second.d); if (kv.second.g) cudaFree(kv.second.g); }
   delete h;
@@ -1369,6 +1380,32 @@ int mimi_b200_codes_to_utf8(mimi_b200_t* h, const int64_t* d_codes, int B, int K
   if (h_frames) CUDA_TRY(h, cudaEventRecord(h->dev_ints_ev, st));
   CUDA_TRY(h, cudaGetLastError());
   return MIMI_B200_OK;
+}
+
+int mimi_b200_load_decoder_weights(mimi_b200_t* h, const mimi_b200_decoder_weights_t* w) {
+  if (!h || !w) return fail(h, MIMI_B200_ERR_ARG, "load_decoder_weights: NULL argument");
+  DeviceGuard guard;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  return dec_load_weights(h, w);
+}
+
+int mimi_b200_decode_workspace_bytes(mimi_b200_t* h, int B, int64_t T, size_t* out_bytes) {
+  if (!h || !out_bytes) return fail(h, MIMI_B200_ERR_ARG, "decode_workspace_bytes: NULL argument");
+  if (B < 0 || T < 0 || 2 * T > kRopeMaxPos) return fail(h, MIMI_B200_ERR_ARG, "decode_workspace_bytes: bad B / T");
+  *out_bytes = make_plan_dec(B, T).bytes + 256;
+  return MIMI_B200_OK;
+}
+
+int mimi_b200_decode(mimi_b200_t* h, const int64_t* d_codes, int B, int K, int64_t T, float* d_audio, void* d_workspace,
+                     size_t workspace_bytes, void* stream) {
+  if (!h) return MIMI_B200_ERR_ARG;
+  if (!h->loaded || !h->dec_loaded) return fail(h, MIMI_B200_ERR_STATE, "decode: encoder codebooks and decoder weights must be loaded first");
+  if (K < 1 || K > MIMI_B200_MAX_QUANTIZERS) return fail(h, MIMI_B200_ERR_ARG, "decode: audio_codes must hold 1..32 codebooks");
+  if (B < 0 || T < 0 || 2 * T > kRopeMaxPos) return fail(h, MIMI_B200_ERR_ARG, "decode: bad B / T");
+  if (B == 0 || T == 0) return MIMI_B200_OK;
+  if (!d_codes || !d_audio || !d_workspace) return fail(h, MIMI_B200_ERR_ARG, "decode: NULL device pointer");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  return decode_impl(h, d_codes, B, K, T, d_audio, d_workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
 int mimi_b200_codes_pack_u16(mimi_b200_t* h, const int64_t* d_codes, int64_t n, uint16_t* d_out, void* stream) {

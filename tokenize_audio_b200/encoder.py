@@ -30,6 +30,17 @@ NUM_QUANTIZERS = 32
 NUM_SEMANTIC_QUANTIZERS = 1
 
 
+class MimiDecoderOutput(tuple):
+    """Tuple-compatible stand-in for transformers' ``MimiDecoderOutput`` (modeling_mimi.py:196-211):
+    ``out.audio_values``, ``out[0]``, ``out.decoder_past_key_values``."""
+
+    def __new__(cls, audio_values, decoder_past_key_values=None):
+        return super().__new__(cls, (audio_values, decoder_past_key_values))
+
+    audio_values = property(lambda self: self[0])
+    decoder_past_key_values = property(lambda self: self[1])
+
+
 class MimiEncoderOutput(tuple):
     """Tuple-compatible stand-in for transformers' ``MimiEncoderOutput`` (modeling_mimi.py:60-75):
     ``out.audio_codes``, ``out[0]``, ``out.encoder_past_key_values``, ``out.padding_cache``."""
@@ -66,7 +77,7 @@ class MimiB200Model:
         self.device = torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
         self._lib = _lib.load_library()
         self._lock = threading.Lock()
-        self._workspaces: Dict[int, Optional[torch.Tensor]] = {}
+        self._workspaces: Dict[object, Optional[torch.Tensor]] = {}
         self._mode = self.DEFAULT_MODE
         # encode() runs a batch of >= min_split_batch items as `streams` contiguous item ranges on side streams: every
         # kernel is a persistent one-CTA-per-SM grid whose last tiles leave SMs idle, the other range's kernels fill them
@@ -81,6 +92,7 @@ class MimiB200Model:
         _lib.check(self._lib, None, rc, "mimi_b200_create")
         self._h = h
         self._load(state_dict)
+        self.has_decoder = self._load_decoder(state_dict)
 
     # -- construction helpers ---------------------------------------------------------------------
     @classmethod
@@ -144,6 +156,96 @@ class MimiB200Model:
             rc = self._lib.mimi_b200_load_weights(self._h, C.byref(w))
         _lib.check(self._lib, self._h, rc, "mimi_b200_load_weights")
         del keep
+
+    def _load_decoder(self, sd) -> bool:
+        """Decode-side tensors (output projections, upsample, decoder transformer, SEANet decoder) when the state dict has
+        them -- a full ``kyutai/mimi`` checkpoint does; an encode-only dict leaves :meth:`decode` unavailable."""
+        from .synth import SEANET_DECODER_UPS
+        if "decoder.layers.0.conv.weight" not in sd:
+            return False
+        keep: List[np.ndarray] = []
+
+        def ptr(name: str, shape) -> C.c_void_p:
+            if name not in sd:
+                raise KeyError(f"state dict is missing '{name}'")
+            a = _as_f32(sd[name])
+            if tuple(a.shape) != tuple(shape):
+                raise ValueError(f"'{name}' has shape {tuple(a.shape)}, expected {tuple(shape)}")
+            keep.append(a)
+            return C.c_void_p(a.ctypes.data)
+
+        w = _lib.DecoderWeights()
+        w.semantic_output_proj_weight = ptr("quantizer.semantic_residual_vector_quantizer.output_proj.weight", (512, 256, 1))
+        w.acoustic_output_proj_weight = ptr("quantizer.acoustic_residual_vector_quantizer.output_proj.weight", (512, 256, 1))
+        w.upsample_weight = ptr("upsample.conv.weight", (512, 1, 4))
+        for l in range(8):
+            p = f"decoder_transformer.layers.{l}"
+            lw = w.layer[l]
+            lw.input_layernorm_weight = ptr(f"{p}.input_layernorm.weight", (512,))
+            lw.input_layernorm_bias = ptr(f"{p}.input_layernorm.bias", (512,))
+            lw.q_proj_weight = ptr(f"{p}.self_attn.q_proj.weight", (512, 512))
+            lw.k_proj_weight = ptr(f"{p}.self_attn.k_proj.weight", (512, 512))
+            lw.v_proj_weight = ptr(f"{p}.self_attn.v_proj.weight", (512, 512))
+            lw.o_proj_weight = ptr(f"{p}.self_attn.o_proj.weight", (512, 512))
+            lw.self_attn_layer_scale = ptr(f"{p}.self_attn_layer_scale.scale", (512,))
+            lw.post_attention_layernorm_weight = ptr(f"{p}.post_attention_layernorm.weight", (512,))
+            lw.post_attention_layernorm_bias = ptr(f"{p}.post_attention_layernorm.bias", (512,))
+            lw.fc1_weight = ptr(f"{p}.mlp.fc1.weight", (2048, 512))
+            lw.fc2_weight = ptr(f"{p}.mlp.fc2.weight", (512, 2048))
+            lw.mlp_layer_scale = ptr(f"{p}.mlp_layer_scale.scale", (512,))
+        w.conv_in_weight = ptr("decoder.layers.0.conv.weight", (1024, 512, 7))
+        w.conv_in_bias = ptr("decoder.layers.0.conv.bias", (1024,))
+        for i, (name, cin, cout, r, res) in enumerate(SEANET_DECODER_UPS):
+            w.up_weight[i] = ptr(f"{name}.conv.weight", (cin, cout, 2 * r))
+            w.up_bias[i] = ptr(f"{name}.conv.bias", (cout,))
+            w.res_a_weight[i] = ptr(f"{res}.block.1.conv.weight", (cout // 2, cout, 3))
+            w.res_a_bias[i] = ptr(f"{res}.block.1.conv.bias", (cout // 2,))
+            w.res_b_weight[i] = ptr(f"{res}.block.3.conv.weight", (cout, cout // 2, 1))
+            w.res_b_bias[i] = ptr(f"{res}.block.3.conv.bias", (cout,))
+        w.conv_out_weight = ptr("decoder.layers.14.conv.weight", (1, 64, 3))
+        w.conv_out_bias = ptr("decoder.layers.14.conv.bias", (1,))
+        with torch.cuda.device(self.device):
+            rc = self._lib.mimi_b200_load_decoder_weights(self._h, C.byref(w))
+        _lib.check(self._lib, self._h, rc, "mimi_b200_load_decoder_weights")
+        del keep
+        return True
+
+    def decode(self, audio_codes: torch.Tensor, padding_mask: Optional[torch.Tensor] = None, decoder_past_key_values=None,
+               return_dict: Optional[bool] = None):
+        """Same contract as ``MimiModel.decode`` (modeling_mimi.py:1613-1679): ``audio_codes`` ``[B, K, T]`` (K = 1..32) ->
+        ``MimiDecoderOutput`` with ``audio_values`` ``[B, 1, 1920*T]`` fp32, truncated to ``padding_mask.shape[-1]`` when a
+        shorter mask is given. Runs on the exact-fp32 FFMA kernels (the reference's round-trip spot-check path,
+        REF/emilia-mimi/utils.py:72-81)."""
+        if decoder_past_key_values is not None:
+            raise NotImplementedError("decoder_past_key_values (streaming decode) is not supported")
+        if not self.has_decoder:
+            raise _lib.MimiB200Error("this model was built from an encode-only state dict: decode() needs the decoder tensors")
+        if audio_codes.dim() != 3:
+            raise ValueError(f"audio_codes must be [batch, num_quantizers, codes_length], got {tuple(audio_codes.shape)}")
+        if not audio_codes.is_cuda or audio_codes.device != self.device:
+            raise _lib.MimiB200Error(f"audio_codes must live on {self.device} (no CPU fallback)")
+        B, K, T = audio_codes.shape
+        if K < 1 or K > NUM_QUANTIZERS:
+            raise ValueError(f"audio_codes must hold between 1 and {NUM_QUANTIZERS} codebooks, got {K}")
+        codes = audio_codes.detach().to(torch.int64).contiguous()
+        if codes.numel():
+            lo, hi = int(codes.min()), int(codes.max())
+            if lo < 0 or hi >= 2048:      # F.embedding in the reference raises IndexError here
+                raise IndexError(f"audio_codes must lie in [0, 2048), got values in [{lo}, {hi}]")
+        audio = torch.empty((B, 1, FRAME_SIZE * T), dtype=torch.float32, device=self.device)
+        if B > 0 and T > 0:
+            with self._lock, torch.cuda.device(self.device):
+                nbytes = C.c_size_t()
+                rc = self._lib.mimi_b200_decode_workspace_bytes(self._h, B, T, C.byref(nbytes))
+                _lib.check(self._lib, self._h, rc, "mimi_b200_decode_workspace_bytes")
+                ws = self._ws(nbytes.value, "decode")
+                rc = self._lib.mimi_b200_decode(self._h, codes.data_ptr(), B, K, T, audio.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                torch.cuda.current_stream(self.device).cuda_stream)
+                _lib.check(self._lib, self._h, rc, "mimi_b200_decode")
+        if padding_mask is not None and padding_mask.shape[-1] < audio.shape[-1]:
+            audio = audio[..., : padding_mask.shape[-1]]
+        out = MimiDecoderOutput(audio, None)
+        return tuple(out) if return_dict is False else out
 
     # -- nn.Module-flavoured no-ops so reference scripts keep working -----------------------------------
     def to(self, device):

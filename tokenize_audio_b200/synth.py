@@ -188,6 +188,57 @@ def synth_speech(seed: int, n_samples: int, sr: int = SAMPLE_RATE) -> np.ndarray
     return x.astype(np.float32)
 
 
+# (state-dict prefix, C_in, C_out, ratio) of the four ConvTranspose1d stages of the SEANet decoder and the index of the
+# residual block that follows each (MimiDecoder.__init__, TF/models/mimi/modeling_mimi.py:1143-1167)
+SEANET_DECODER_UPS = (
+    ("decoder.layers.2", 1024, 512, 8, "decoder.layers.3"),
+    ("decoder.layers.5", 512, 256, 6, "decoder.layers.6"),
+    ("decoder.layers.8", 256, 128, 5, "decoder.layers.9"),
+    ("decoder.layers.11", 128, 64, 4, "decoder.layers.12"),
+)
+
+
+def decoder_state_dict(seed: int = 0) -> Dict[str, np.ndarray]:
+    """Seeded DECODE-side tensors of ``MimiModel.state_dict()`` (output projections, upsample, decoder transformer, SEANet
+    decoder) for the decode direction. Kept apart from :func:`synth_state_dict` so that the
+    encode-side digest the golden fixtures were made with never moves; merge the two dicts to get a full model."""
+    sd: Dict[str, np.ndarray] = {}
+    g = _rng(seed, 21)
+    for which in ("semantic", "acoustic"):
+        sd[f"quantizer.{which}_residual_vector_quantizer.output_proj.weight"] = \
+            _randn(g, HIDDEN, CODEBOOK_DIM, 1) * np.float32(1.0 / math.sqrt(CODEBOOK_DIM))
+    sd["upsample.conv.weight"] = (np.float32(0.5) + _randn(g, HIDDEN, 1, 4) * np.float32(0.3)).astype(np.float32)
+    for l in range(N_LAYERS):
+        g = _rng(seed, 22, l)
+        p = f"decoder_transformer.layers.{l}"
+        for nm in ("q_proj", "k_proj", "v_proj", "o_proj"):
+            sd[f"{p}.self_attn.{nm}.weight"] = _randn(g, HIDDEN, HIDDEN) * np.float32(1.0 / math.sqrt(HIDDEN))
+        sd[f"{p}.self_attn.q_proj.weight"] *= np.float32(2.0)
+        sd[f"{p}.mlp.fc1.weight"] = _randn(g, FFN, HIDDEN) * np.float32(1.0 / math.sqrt(HIDDEN))
+        sd[f"{p}.mlp.fc2.weight"] = _randn(g, HIDDEN, FFN) * np.float32(1.0 / math.sqrt(FFN))
+        for nm in ("input_layernorm", "post_attention_layernorm"):
+            sd[f"{p}.{nm}.weight"] = np.float32(1.0) + _randn(g, HIDDEN) * np.float32(0.1)
+            sd[f"{p}.{nm}.bias"] = _randn(g, HIDDEN) * np.float32(0.1)
+        for nm in ("self_attn_layer_scale", "mlp_layer_scale"):
+            sd[f"{p}.{nm}.scale"] = g.uniform(0.05, 0.5, size=HIDDEN).astype(np.float32)
+    g = _rng(seed, 23)
+    sd["decoder.layers.0.conv.weight"] = _randn(g, 1024, HIDDEN, 7) * np.float32(0.5 / math.sqrt(HIDDEN * 7))
+    sd["decoder.layers.0.conv.bias"] = _randn(g, 1024) * np.float32(0.05)
+    for si, (name, cin, cout, r, res) in enumerate(SEANET_DECODER_UPS):
+        g = _rng(seed, 24, si)
+        # ConvTranspose1d weight layout [C_in, C_out, k]; every output sample sums two taps of every input channel
+        sd[f"{name}.conv.weight"] = _randn(g, cin, cout, 2 * r) * np.float32(1.45 / math.sqrt(2 * cin))
+        sd[f"{name}.conv.bias"] = _randn(g, cout) * np.float32(0.05)
+        sd[f"{res}.block.1.conv.weight"] = _randn(g, cout // 2, cout, 3) * np.float32(1.45 / math.sqrt(cout * 3))
+        sd[f"{res}.block.1.conv.bias"] = _randn(g, cout // 2) * np.float32(0.05)
+        sd[f"{res}.block.3.conv.weight"] = _randn(g, cout, cout // 2, 1) * np.float32(0.8 / math.sqrt(cout // 2))
+        sd[f"{res}.block.3.conv.bias"] = _randn(g, cout) * np.float32(0.05)
+    g = _rng(seed, 25)
+    sd["decoder.layers.14.conv.weight"] = _randn(g, 1, 64, 3) * np.float32(0.15 / math.sqrt(64 * 3))
+    sd["decoder.layers.14.conv.bias"] = _randn(g, 1) * np.float32(0.01)
+    return sd
+
+
 def variant_state_dict(kind: str) -> Dict[str, np.ndarray]:
     """Adversarial weight draws for the parity tests (same key names / shapes as :func:`synth_state_dict`).
 

@@ -1,6 +1,6 @@
 """Drop-in counterparts of the reference's ``utils.py`` (REF/emilia-mimi/utils.py, six identical copies)
 with the array work done by libmimi_b200.so kernels: ``codes_to_chars``, ``chars_to_codes``,
-``audio_to_str``, ``resample_audio``. Same names, argument meaning and error behaviour.
+``audio_to_str``, ``str_to_audio``, ``resample_audio``. Same names, argument meaning and error behaviour.
 """
 from __future__ import annotations
 
@@ -161,6 +161,15 @@ def audio_to_str(audio_numpy: np.ndarray, mimi_model, device: str = "cuda") -> s
         audio_codes = mimi_model.encode(audio_tensor)
     codes = audio_codes[0][0][:NUM_CODEBOOKS, :]
     return codes_to_chars(codes, codebook_size=CODEBOOK_SIZE)
+
+
+def str_to_audio(audio_str: str, mimi_model, device: str = "cuda") -> np.ndarray:
+    """REF/emilia-mimi/utils.py:72-81: unicode string -> 8 codebooks -> ``mimi_model.decode`` -> waveform ``[1, 1920*T]``."""
+    codes = chars_to_codes(audio_str, num_codebooks=NUM_CODEBOOKS, codebook_size=CODEBOOK_SIZE, return_tensors="pt")
+    codes = codes.to(device).unsqueeze(0)
+    with torch.no_grad():
+        audio_decoded = mimi_model.decode(codes).audio_values[0]
+    return audio_decoded.cpu().numpy()
 
 
 def codes_to_uint16(codes: torch.Tensor) -> torch.Tensor:
