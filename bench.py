@@ -571,7 +571,7 @@ def run_b200(args, rank, world, local_rank):
     groups = {}
     cur_mode = args.mode if args.mode is not None else model.DEFAULT_MODE
     default_gen = cur_mode >= 7
-    fn256 = "tcp_gemm_kernel<256,%d>" % (3 if cur_mode == 9 else 2 if cur_mode == 8 else 1)
+    fn256 = "tcp_gemm_kernel<256,%d>" % (3 if cur_mode == 9 else 1)
     for k, (kms_, kcnt_) in prof.items():
         g = fn256 if (default_gen and k in tcp256) else k
         e = groups.setdefault(g, {"ms": 0.0, "count": 0, "kinds": []})
@@ -609,9 +609,8 @@ def run_b200(args, rank, world, local_rank):
         roof["layers"] = sorted(grp["kinds"])
         roof["traffic_covers"] = sorted(have)
     if roof["bound"] == "tensor":
-        passes = {9: "fp16 hi/lo split of both operands (hi*hi + hi*lo + lo*hi, all on kind::f16: 3 bf16-rate tensor passes per MAC)",
-                  8: "hi*hi on TF32, both cross terms on bf16 (4 bf16-rate pass units per MAC)"}.get(
-                      cur_mode, "hi*hi + hi*lo on TF32, lo*hi on bf16 (5 bf16-rate pass units per MAC)")
+        passes = ("fp16 hi/lo split of both operands (hi*hi + hi*lo + lo*hi, all on kind::f16: 3 bf16-rate tensor passes per MAC)"
+                  if cur_mode == 9 else "hi*hi + hi*lo on TF32, lo*hi on bf16 (5 bf16-rate pass units per MAC)")
         roof["precision"] = (f"fp32-equivalent split precision on tcgen05: {passes}; achieved counts algorithmic FLOPs once; "
                              "peak is the measured dense bf16 figure")
     else:
@@ -711,7 +710,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference", "reference-cuda"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["resample", "utf8"], help="c2 = the metric's config (default)")
-    ap.add_argument("--mode", type=int, default=None, help="debug: kernel generation (see MimiB200Model.set_mode)")
+    ap.add_argument("--mode", type=int, default=None, help="debug: kernel generation 0 / 7 / 9 (see MimiB200Model.set_mode)")
     ap.add_argument("--streams", type=int, default=0, help="debug: item ranges on side streams inside encode()")
     ap.add_argument("--dbg", action="append", default=[], help="debug: KEY=VALUE for mimi_b200_debug_set (A/B knobs)")
     args = ap.parse_args()
@@ -724,11 +723,7 @@ def main():
             run_byte_kernel(args, local_rank)
         return
     select_workload(args.workload)
-    if args.mode is not None and args.mode <= 6:
-        HBM_BYTES_PER_AUDIO_S["front_fused"] = 24000 * 4 + 24000 * 64 * 8      # fp32 lo parts
-    if args.mode is None or args.mode == 9:
-        HBM_BYTES_PER_AUDIO_S["front_fused"] = 24000 * 4 + 24000 * 64 * 4      # fp16 hi + fp16 lo (default generation)
-    elif args.mode >= 7:
+    if args.mode == 7:
         HBM_BYTES_PER_AUDIO_S["front_fused"] = 24000 * 4 + 24000 * 64 * 6      # TF32 hi (fp32) + bf16 lo
     if args.impl == "reference":
         run_reference(args, rank, world)

@@ -151,7 +151,7 @@ int mimi_b200_encode(mimi_b200_t* h, const float* d_input, int B, int64_t N,
  *   MIMI_B200_PHASE_FINISH  the rest of the pipeline for the whole batch.
  * Every phase takes the arguments of mimi_b200_encode, identical from call to call; BEGIN, FRONT over a partition of
  * [0, B), FINISH on one stream is exactly mimi_b200_encode. This is what MimiEncoder.encode_audio_batch
- * (REF/emilia-mimi/process_shard.py:88-140) does with its pinned staging buffer. Needs the default kernel generation.
+ * (REF/emilia-mimi/process_shard.py:88-140) does with its pinned staging buffer. Needs a tensor-core generation (7 or 9).
  */
 #define MIMI_B200_PHASE_BEGIN 1
 #define MIMI_B200_PHASE_FRONT 2
@@ -172,25 +172,18 @@ int mimi_b200_debug_tap(mimi_b200_t* h, int which, float* d_out, size_t out_capa
         and leave d_codes untouched)
      2  per-launch CUDA-event profiling on/off (resets the profile)
      3  kernel generation ("mode"), default 9:
-          0  every layer on fp32 FFMA (exact-fp32 bisection baseline)
-          7  fused 24 kHz front end (front_fused.cuh) + CTA-pair tcgen05 GEMM (tc_gemm5.cuh; hi*hi and hi*lo on
-             kind::tf32, lo*hi on kind::f16 with bf16 lo parts) + tcgen05 attention + tensor-core RVQ; fp32 range
-          9  mode 7 with every GEMM operand as an fp16 hi/lo pair (activations: hi + lo/2048, weights row-scaled by a power
-             of two): hi*hi + hi*lo + lo*hi all on kind::f16, 3 tensor passes instead of 5 pass units, 4 instead of 6
-             bytes per activation element; saturates at 65504 (see mimi_b200_range_overflow)
-          the other values (1..6, 8) are earlier / experimental generations kept for A/B, see DESIGN.md section 7
-     4  accuracy experiment: cross terms into the main accumulator (single-CTA GEMM generations)
-     5  accuracy experiment: k-blocks per accumulation chunk (0 = default 4)
-     6  plane-staged activations for k = G*stride convs (default 0)
-     7  next-tile L2 prefetch in the GEMM producer (default 0)
-     8  attention kernel: 4 = tcgen05 (default), 2 / 3 = fp32 SIMT variants (modes < 7 only)
+          9  fused 24 kHz front end (front_fused.cuh) + CTA-pair tcgen05 GEMM (tc_gemm5.cuh) with every operand as an fp16
+             hi/lo pair (activations: hi + lo/2048, weights row-scaled by a power of two): hi*hi + hi*lo + lo*hi all on
+             kind::f16, 3 tensor passes, 4 bytes per activation element; + tcgen05 attention + tensor-core RVQ.
+             fp16 ends at 65504 (see mimi_b200_range_overflow)
+          7  the same with TF32 hi (fp32) and bf16 lo operands: hi*hi and hi*lo on kind::tf32, lo*hi on kind::f16 (5 pass
+             units, 6 bytes per element); fp32 range -- the fallback of mode 9
+          0  every layer on fp32 FFMA (exact-fp32 bisection baseline; also what the decode direction runs on)
+     5  k-blocks per accumulation chunk of the GEMM (0 = default 4, i.e. K = 128 inside TMEM between drains)
      9  pair tiles of 128 columns for layers with N >= value (0 = never, default)
     10  1 = never flatten the row dimension of the linears across items
     11  1 = k-blocks in linear order, 2 = tap-grouped with the channel panels innermost (default 0: grouped by tau mod s)
-    12  1 = the 24 kHz activation crosses HBM as raw fp32 (front end stores raw, D1 splits in shared memory)
     13  1 = walk the mt_max x B tile grid instead of the compact tile lists of a ragged call
-    14  1 = full-size (fp32-sized) lo buffers in mode 7
-    15  1 = level-1 residual block as one kernel (tc_gemm6.cuh)
     16  1 = first-draft one-thread-per-output resampler instead of resample_poly_kernel */
 int mimi_b200_debug_set(mimi_b200_t* h, int key, int value);
 
@@ -202,13 +195,12 @@ int mimi_b200_debug_set(mimi_b200_t* h, int key, int value);
 int mimi_b200_profile_read(mimi_b200_t* h, int max_ids, double* sum_ms, int64_t* count);
 
 /* Unit-test hook for the tensor-core GEMM kernel: d_out[M][N] = act(d_a[M][K] * h_w[N][K]^T + bias) through the
-   encoder's own TF32 hi/lo split + TMA + tcgen05 path (N % 32 == 0 in mode 2, N % 64 == 0 in mode 1;
-   K % 32 == 0; act 1 = GELU(erf)). Uses the kernel generation selected by debug_set key 3. Synchronises
-   the stream. */
+   encoder's own operand split + TMA + tcgen05 path (N % 64 == 0, K % 32 == 0; act 1 = GELU(erf)), in the tensor-core
+   generation selected by debug_set key 3 (7 or 9). Synchronises the stream. */
 int mimi_b200_debug_tc_gemm(mimi_b200_t* h, const float* d_a, const float* h_w, const float* d_bias_opt, int M,
                             int N, int K, int act, float* d_out, void* stream);
 
-/* Hardware probe (unit test only): one 128 x 64 single-pass TF32 tile whose SWIZZLE_128B A-operand
+/* Hardware probe (unit test only; the fused front end relies on the property): one 128 x 64 single-pass TF32 tile whose SWIZZLE_128B A-operand
    descriptor starts `shift` rows (0..8) into the staged tile: d_out[m][n] = sum_k d_a[m + shift][k] * h_w[n][k].
    d_a has 136 rows of K floats (K % 32 == 0), h_w 64 rows. base_mode 1 also sets the descriptor's
    base-offset field to (start >> 7) & 7. Synchronises the stream. */

@@ -1,5 +1,5 @@
-"""Unit test of the tcgen05 3xTF32 GEMM kernel (through the C-ABI debug hook) against float64 matmul.
-Tolerance: relative L2 error <= 1e-6 (fp32-equivalent), far inside the 3e-5 the codes tolerate."""
+"""Unit test of the CTA-pair tcgen05 GEMM kernel in both split-precision generations (through the C-ABI debug hook) against
+float64 matmul. Tolerance: relative L2 error <= 3e-6 (fp32-equivalent), far inside the 3e-5 the codes tolerate."""
 import ctypes as C
 
 import numpy as np
@@ -20,16 +20,14 @@ def engine():
     lib.mimi_b200_destroy(h)
 
 
-@pytest.mark.parametrize("mode", [9, 8, 7, 6, 4, 2, 1])
+@pytest.mark.parametrize("mode", [9, 7])
 @pytest.mark.parametrize("M,N,K,act,bias", [
     (128, 128, 32, 0, False), (300, 128, 512, 0, True), (77, 64, 384, 0, True), (1000, 256, 1280, 0, False),
     (60, 2048, 512, 1, False), (130, 512, 2048, 0, True), (257, 1024, 8192, 0, True), (64, 1536, 512, 0, False),
-    (40000, 128, 64, 0, True), (25000, 64, 96, 0, False), (30000, 32, 192, 0, True), (129, 32, 32, 1, True),
+    (40000, 128, 64, 0, True), (25000, 64, 96, 0, False),
 ])
 def test_tc_gemm_matches_float64(engine, M, N, K, act, bias, mode):
     lib, h = engine
-    if mode in (1, 4, 7, 8, 9) and N % 64:
-        pytest.skip("only the second-generation kernel has a BN=32 instance")
     _lib.check(lib, h, lib.mimi_b200_debug_set(h, 3, mode), "debug_set")
     g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
     a = torch.randn(M, K, generator=g) * 2.0
@@ -48,7 +46,6 @@ def test_tc_gemm_matches_float64(engine, M, N, K, act, bias, mode):
     if act:
         ref = torch.nn.functional.gelu(ref)
     err = (out.cpu().double() - ref).norm() / ref.norm()
-    # modes 4 / 6 fold the cross terms into the main accumulator; mode 7 keeps lo and W_hi of the A_lo * W_hi term in bf16
-    # mode 9: fp16 hi/lo split of both operands (22 significant bits each)
-    tol = 3e-6 if mode >= 7 else 1.5e-6 if mode in (4, 6) else 1e-6
+    # mode 7 keeps lo and the W_hi of the A_lo * W_hi term in bf16; mode 9: fp16 hi/lo split of both operands (22 bits each)
+    tol = 3e-6
     assert err <= tol, f"relative error {err:.2e}"

@@ -54,7 +54,6 @@ struct Params {
   int B;
   int mt_max;                  // query tiles per item at the longest item
   int lo_bf16;                 // 1: out_lo is a bf16 array (mode 7)
-  float* out_hib;              // mode 8: bf16(hi) array, or nullptr
 };
 
 // exp(x) for x <= 0 through ex2.approx; the scaling by log2(e) is done in two pieces so that the argument carries no
@@ -359,7 +358,7 @@ __global__ void __launch_bounds__(kThreads, 1) swa_attention_tc_kernel(const Par
       const long long o = (long long)b * p.out_stride + (long long)qi * kHidden + h * kHeadDim + cs * kCols;
 #pragma unroll
       for (int q = 0; q < kCols / 4; ++q)
-        store_split4_x(p.out_hi, p.out_lo, p.out_hib, o + 4 * q,
+        store_split4_x(p.out_hi, p.out_lo, o + 4 * q,
                          make_float4(oacc[4 * q] * inv, oacc[4 * q + 1] * inv, oacc[4 * q + 2] * inv, oacc[4 * q + 3] * inv), p.lo_bf16);
     }
     ++uc;

@@ -60,13 +60,6 @@ __host__ __device__ __forceinline__ void split_tf32(float x, float& hi, float& l
 #endif
   lo = x - hi;
 }
-__device__ __forceinline__ void store_split4(float* hi, float* lo, float4 v) {
-  float4 h4, l4;
-  split_tf32(v.x, h4.x, l4.x); split_tf32(v.y, h4.y, l4.y); split_tf32(v.z, h4.z, l4.z); split_tf32(v.w, h4.w, l4.w);
-  *reinterpret_cast<float4*>(hi) = h4;
-  *reinterpret_cast<float4*>(lo) = l4;
-}
-
 // lo part of the split as bf16 (mode 7): lo = x - hi is a correction of relative size 2^-11, so 8 mantissa bits keep
 // the pair (hi, lo) accurate to 2^-20 of x; the A_lo * W_hi product then runs on kind::f16 at twice the TF32 rate
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {      // a -> low half, b -> high half (round to nearest)
@@ -81,12 +74,6 @@ __device__ __forceinline__ void store_split4_lob(float* hi, void* lo_bf16_elem, 
   *reinterpret_cast<float4*>(hi) = h4;
   *reinterpret_cast<uint2*>(lo_bf16_elem) = make_uint2(pack_bf16x2(l4.x, l4.y), pack_bf16x2(l4.z, l4.w));
 }
-// element `idx` of a lo array that is fp32 (lob = 0) or bf16 (lob = 1) and starts at `lo`
-__device__ __forceinline__ void store_split4_any(float* hi, float* lo, long long idx, float4 v, int lob) {
-  if (lob) store_split4_lob(hi + idx, reinterpret_cast<uint16_t*>(lo) + idx, v);
-  else store_split4(hi + idx, lo + idx, v);
-}
-
 // fp16 generation (mode 9, lob = 3): x = hi + lo / 2048 with hi = fp16(x) (11 significant bits) and lo = fp16((x - hi) * 2048)
 // (the next 11 bits; the scaling keeps the correction in fp16's normal range however small x is), 4 bytes per element.
 // Every product of the consuming GEMM -- hi*W_hi, hi*W_lo, lo*(W_hi / 2048) -- then runs on kind::f16 at the full 16-bit
@@ -119,15 +106,10 @@ __device__ __forceinline__ void store_split4_f16(float* hi, float* lo, long long
                  pack_f16x2((v.z - f23.x) * kF16LoScale, (v.w - f23.y) * kF16LoScale));
 }
 
-// the same with an optional third array hib = bf16(hi) (mode 8: both cross terms of the consuming GEMM run on kind::f16)
-__device__ __forceinline__ void store_split4_x(float* hi, float* lo, float* hib, long long idx, float4 v, int lob) {
-  if (lob == 3) { store_split4_f16(hi, lo, idx, v); return; }
-  if (!hib) { store_split4_any(hi, lo, idx, v, lob); return; }
-  float4 h4, l4;
-  split_tf32(v.x, h4.x, l4.x); split_tf32(v.y, h4.y, l4.y); split_tf32(v.z, h4.z, l4.z); split_tf32(v.w, h4.w, l4.w);
-  *reinterpret_cast<float4*>(hi + idx) = h4;
-  *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(lo) + idx) = make_uint2(pack_bf16x2(l4.x, l4.y), pack_bf16x2(l4.z, l4.w));
-  *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(hib) + idx) = make_uint2(pack_bf16x2(h4.x, h4.y), pack_bf16x2(h4.z, h4.w));
+// one entry point for every producer of a split activation: lob = 1 -> TF32 hi (fp32) + bf16 lo (mode 7), lob = 3 -> fp16 pair
+__device__ __forceinline__ void store_split4_x(float* hi, float* lo, long long idx, float4 v, int lob) {
+  if (lob == 3) store_split4_f16(hi, lo, idx, v);
+  else store_split4_lob(hi + idx, reinterpret_cast<uint16_t*>(lo) + idx, v);
 }
 
 // explicit shared-space 16-byte accesses (a pointer into dynamic shared memory that went through integer

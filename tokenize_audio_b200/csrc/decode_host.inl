@@ -162,7 +162,7 @@ static int decode_impl(mimi_b200* h, const int64_t* d_codes, int B, int K, int64
     if ((rc = gemm(ws + p.y, s512, 512, 1, 0, d.qkv_wt, nullptr, 1536, ws + p.qkv, (long long)T25 * 1536, T25, 0))) return rc;
     dim3 agrid((T25 + kAttQT - 1) / kAttQT, kHeads, B);
     swa_attention_kernel<<<agrid, 256, kAttSmemBytes, st>>>(ws + p.qkv, (long long)T25 * 1536, ws + p.att, s512, h->rope_cos, h->rope_sin,
-                                                            nullptr, T25, nullptr);
+                                                            nullptr, T25);
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
     if ((rc = gemm(ws + p.att, s512, 512, 1, 0, d.o_wt, nullptr, 512, ws + p.z, s512, T25, 0, ws + p.z, d.ls1))) return rc;

@@ -56,8 +56,6 @@ struct Params {
   long long split_item_stride;
   int split_front;
   int lo_bf16;               // 1: out_lo is a bf16 array (mode 7); 3: out_hi and out_lo are fp16 arrays (mode 9, split_f16)
-  int raw_out;               // 1: store the raw fp32 result (pre-ELU, unsplit) to out_hi only (mode 5: the consumer
-                             //    applies ELU and the hi/lo split itself)
 };
 
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -291,12 +289,9 @@ front_fused_kernel(const __grid_constant__ CUtensorMap tmW1_hi, const __grid_con
             const int c = q * 4 + j;
             const float bias = ch == 0 ? cst.b2[c] : cst.b2[32 + c];
             const float pre = (__uint_as_float(rm[c]) + __uint_as_float(rs[c])) + bias + a0[c];
-            v[j] = p.raw_out ? pre : elu_fast(pre);
+            v[j] = elu_fast(pre);
           }
-          if (p.raw_out) {
-            h4 = make_float4(v[0], v[1], v[2], v[3]);
-            lq[q] = h4;
-          } else if (p.lo_bf16 == 3) {
+          if (p.lo_bf16 == 3) {
             split_f16(v[0], h4.x, lq[q].x); split_f16(v[1], h4.y, lq[q].y); split_f16(v[2], h4.z, lq[q].z); split_f16(v[3], h4.w, lq[q].w);
           } else {
             split_tf32(v[0], h4.x, lq[q].x); split_tf32(v[1], h4.y, lq[q].y); split_tf32(v[2], h4.z, lq[q].z); split_tf32(v[3], h4.w, lq[q].w);
@@ -304,8 +299,7 @@ front_fused_kernel(const __grid_constant__ CUtensorMap tmW1_hi, const __grid_con
           sts128(stg + (uint32_t)(lane * 8 + (q ^ key)) * 16u, h4);
         }
         // hi piece, then lo piece, through the same 4 KB of this warp's own (dead) operand rows
-        const int npass = p.raw_out ? 1 : 2;
-        for (int pass = 0; pass < npass; ++pass) {
+        for (int pass = 0; pass < 2; ++pass) {
           __syncwarp();
           float4 tv[8];
 #pragma unroll

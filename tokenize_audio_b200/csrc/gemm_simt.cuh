@@ -8,8 +8,8 @@
 // Linears are the k=1, stride=1 case. The epilogue fuses bias, GELU(erf), LayerScale and the residual
 // add; ELU on the conv INPUT (modeling_mimi.py:437-451) is applied while staging A.
 //
-// This is the exact-fp32 path (FFMA): used for the narrow early layers and as the accuracy baseline for
-// the tensor-core path.
+// This is the exact-fp32 path (FFMA): the accuracy baseline of the tensor-core generations (mode 0) and the engine of the
+// decode direction.
 #pragma once
 #include "common.cuh"
 
@@ -31,13 +31,6 @@ struct GemmParams {
   int replicate;              // 1: clamp rows (replicate padding) instead of zero fill
   int elu_in;                 // 1: ELU applied to A while loading
   int act;                    // 0 none, 1 GELU(erf) after bias
-  // optional hi/lo split output for a tensor-core consumer (out may then be nullptr): row j of item b at
-  // b*split_item_stride + (split_front + j)*N; ELU applied first when elu_split
-  float* out_hi;
-  float* out_lo;
-  long long split_item_stride;
-  int split_front;
-  int elu_split;
 };
 
 template <int BM, int BN, int TN>
@@ -182,12 +175,7 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmParams p) {
         const float4 rv = *reinterpret_cast<const float4*>(p.res + o);   // may alias out: plain load
         v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
       }
-      if (p.out) *reinterpret_cast<float4*>(p.out + o) = v;
-      if (p.out_hi) {
-        if (p.elu_split) { v.x = elu1(v.x); v.y = elu1(v.y); v.z = elu1(v.z); v.w = elu1(v.w); }
-        const long long so = (long long)b * p.split_item_stride + (long long)(p.split_front + j) * p.N + c;
-        store_split4(p.out_hi + so, p.out_lo + so, v);
-      }
+      *reinterpret_cast<float4*>(p.out + o) = v;
     }
   }
 }
@@ -198,11 +186,7 @@ __global__ void __launch_bounds__(256) conv0_kernel(const float* __restrict__ x,
                                                     const float* __restrict__ w,     // [64][7]
                                                     const float* __restrict__ bias,  // [64]
                                                     float* __restrict__ out, long long out_item_stride,
-                                                    const int* __restrict__ len_in, int uniform_len,
-                                                    float* __restrict__ out_hi, float* __restrict__ out_lo,
-                                                    long long split_item_stride, int split_front) {
-  // out_hi != nullptr: also write the TF32 hi/lo split of ELU(out) (the input of ResBlock-1's first conv) at
-  // row split_front + t of the halo'd split buffers
+                                                    const int* __restrict__ len_in, int uniform_len) {
   constexpr int TT = 128;                     // time steps per CTA
   __shared__ float xs[TT + 6];
   const int b = blockIdx.y;
@@ -240,11 +224,6 @@ __global__ void __launch_bounds__(256) conv0_kernel(const float* __restrict__ x,
     }
     float4 o = make_float4(v[0] + br[0], v[1] + br[1], v[2] + br[2], v[3] + br[3]);
     *reinterpret_cast<float4*>(ob + (long long)t * 64 + cg * 4) = o;
-    if (out_hi) {
-      o.x = elu1(o.x); o.y = elu1(o.y); o.z = elu1(o.z); o.w = elu1(o.w);
-      const long long so = (long long)b * split_item_stride + (long long)(split_front + t) * 64 + cg * 4;
-      store_split4(out_hi + so, out_lo + so, o);
-    }
   }
 }
 

@@ -26,11 +26,8 @@
 #include "tc_gemm.cuh"
 #include "tc_gemm2.cuh"
 #include "front_fused.cuh"
-#include "tc_gemm3.cuh"
 #include "rvq_tc.cuh"
-#include "tc_gemm4.cuh"
 #include "tc_gemm5.cuh"
-#include "tc_gemm6.cuh"
 #include "transformer.cuh"
 #include "attention_tc.cuh"
 #include "decode_kernels.cuh"
@@ -67,18 +64,15 @@ struct Plan {
 struct TapInfo { long long off; int level; int C; };
 
 // ---- tensor-core (tcgen05 3xTF32) path ---------------------------------------------------------------
-// A weight matrix [N][K] (K-major) pre-split into TF32 hi / lo parts with its two TMA maps (box 32 x BN)
+// A weight matrix [N][K] (K-major) in the operand formats of the two tensor-core generations, with its TMA maps
 struct TcWeight {
+  // mode 7: TF32 hi / lo (fp32, SWIZZLE_128B boxes of 32 floats) and bf16(hi) (SWIZZLE_64B)
   float* hi = nullptr;
   float* lo = nullptr;
-  CUtensorMap map_hi, map_lo;              // box 32 x BN
-  CUtensorMap map64_hi, map64_lo;          // box 32 x 64 (tc_gemm3 when BN would be 32... or N % 128 != 0)
-  // bf16-lo generation (mode 7): hib = bf16(hi), SWIZZLE_64B boxes of 32 x {BN, 64, 32} rows, plus 32-row fp32 boxes
   uint16_t* hib = nullptr;
-  uint16_t* lob = nullptr;                 // bf16(lo), mode 8
-  CUtensorMap map_hib, map64_hib, map32_hib, map32_hi, map32_lo;
-  CUtensorMap map_lob, map64_lob, map32_lob;
-  // fp16 generation (mode 9): rows scaled by 2^e_n so that max |W'[n,:]| lies in [2^13, 2^14); h16 = fp16(W'), l16 = fp16(W' - h16),
+  CUtensorMap map_hi, map_lo;              // box 32 x BN rows (the fused front end's resident W1 / W2)
+  CUtensorMap m_hi[3], m_lo[3], m_hib[3];  // box rows 128, 64, 32 (the pair GEMM stages bnp / 2 rows per CTA)
+  // mode 9: rows scaled by 2^e_n so that max |W'[n,:]| lies in [2^13, 2^14); h16 = fp16(W'), l16 = fp16(W' - h16),
   // s16 = fp16(h16 / 2048) (the factor of the activations' scaled lo parts); wscale[n] = 2^-e_n undoes the scaling in the epilogue.
   // One array [3][N][K] (hi | lo | hs); SWIZZLE_64B boxes of 32 x {128, 64, 32} rows.
   uint16_t* f16 = nullptr;
@@ -87,35 +81,23 @@ struct TcWeight {
   int N = 0, K = 0, BN = 0;
 };
 // hi/lo activation pair, channels-last with `front` zero halo rows before row 0 of every item
-struct SplitBuf { long long hi = 0, lo = 0, item_stride = 0; int front = 0, back = 0, C = 0, level = 0; long long hib = -1; };   // hib: bf16(hi), mode 8, levels >= 2
-// (mode 9: hi and lo are both fp16 arrays of item_stride ELEMENTS per item, starting at float offsets hi / lo)
+// (mode 7: hi fp32, lo bf16; mode 9: both fp16 -- item_stride counts ELEMENTS per item, hi / lo are float offsets of the arrays)
+struct SplitBuf { long long hi = 0, lo = 0, item_stride = 0; int front = 0, back = 0, C = 0, level = 0; };
 constexpr int kHalo = 8;     // >= max(k - stride) = 8 (front) and >= max(stride) - 1 = 7 (back)
 
 struct PlanTC {
   int B = 0, K = 0;
   long long N = 0;
   int rows[6] = {0, 0, 0, 0, 0, 0};
-  long long a0, r1, d1, d2, d3, z, qkv, e, rp;                 // raw fp32 buffers (float offsets)
-  SplitBuf s_a0, s_r1;                                         // mode 2: level 0 on tensor cores too
+  long long d1, d2, d3, z, qkv, e, rp;                         // raw fp32 buffers (float offsets)
   SplitBuf s_h1, s_d1, s_r2, s_h2, s_d2, s_r3, s_h3, s_d3, s_r4, s_h4, s_d4, s_y, s_att, s_ffn, s_zp, s_e;
   long long ints;
   size_t bytes = 0;
 };
 
-// mode 5: one fp32 buffer per activation (front/back zero halo rows where a conv pads)
-struct RawBuf { long long off = 0, item_stride = 0; int front = 0, back = 0, C = 0, level = 0; };
-struct PlanR {
-  int B = 0, K = 0;
-  long long N = 0;
-  int rows[6] = {0, 0, 0, 0, 0, 0};
-  RawBuf h1, d1, r2, h2, d2, r3, h3, d3, r4, h4, d4, z, y, qkv, att, ffn, zp, e, rp;
-  long long ints = 0;
-  size_t bytes = 0;
-};
-
-struct MapSet { std::vector<CUtensorMap> maps, maps3, mapsb; uint64_t built = 0, built3 = 0; };   // mapsb: hib maps, one per slot
+struct MapSet { std::vector<CUtensorMap> maps; uint64_t built = 0; };
 struct MapKey {
-  const void* ws; int B; long long N; int layout;     // layout: which workspace plan the offsets come from
+  const void* ws; int B; long long N; int layout;     // layout: the kernel generation whose workspace plan the offsets come from
   bool operator<(const MapKey& o) const {
     if (ws != o.ws) return ws < o.ws;
     if (B != o.B) return B < o.B;
@@ -170,35 +152,20 @@ struct mimi_b200 {
   Plan last;
   void* last_ws = nullptr;
   // tensor-core path
-  int mode = 9;                                // 9 = mode 7 with fp16 hi/lo operands, all three products on kind::f16 (default),
-                                               // 8 = mode 7 + bf16(hi) copies at levels >= 2: both cross terms on kind::f16,
-                                               // 7 = mode 6 with bf16 lo parts and A_lo * W_hi on kind::f16 (the range-safe fallback of mode 9),
-                                               // 6 = mode 3 with the CTA-pair GEMM (tc_gemm5.cuh) where N % 128 == 0 (default),
-                                               // 5 = raw fp32 activations split inside the GEMM (tc_gemm4.cuh),
-                                               // 4 = mode 3 with the experimental third-generation GEMM (tc_gemm3.cuh),
-                                               // 3 = mode 2 + fused 24 kHz front end (front_fused.cuh),
-                                               // 2 = persistent tcgen05 3xTF32 kernel for every GEMM-shaped layer,
-                                               // 1 = first-generation tcgen05 kernel (level 0 on FFMA), 0 = all-fp32 SIMT
+  int mode = 9;                                // 9 = fused front end + CTA-pair tcgen05 GEMM with fp16 hi/lo operands (3 kind::f16 passes) +
+                                               //     tcgen05 attention + tensor-core RVQ (default);
+                                               // 7 = the same with TF32 hi (fp32) + bf16 lo operands: fp32 range, the fallback of mode 9;
+                                               // 0 = every layer on fp32 FFMA (exact baseline for accuracy bisection)
   int last_mode = 0;
-  int exp_single_acc = 0, exp_chunk_kb = 0;    // accuracy experiments (debug_set keys 4, 5)
-  int att_variant = 4;                         // 4 = tcgen05 attention (attention_tc.cuh, default in modes >= 3), 2 = SIMT, 8 warps x
-                                               // 4 queries, 3 = SIMT, 16 warps x 2 queries (12 % slower than 2: bound by
-                                               // shared-memory reads per FMA, not by latency) (debug_set key 8)
-  int exp_prefetch = 0;                        // L2 prefetch of the next tile's activation boxes (debug_set key 7)
-  int use_planes = 0;                          // plane-staged activations for k = G*stride convs (debug_set key 6); off:
-                                               // fewer L2 bytes but not faster (shared-memory bandwidth binds)
+  int exp_chunk_kb = 0;                        // k-blocks per accumulation chunk (debug_set key 5; 0 = default 4)
   f0::Consts f0_consts;
   int num_sms = 148;
   long long item_tiles[6] = {0, 0, 0, 0, 0, 0};   // sum over items of ceil(rows_at_level / 128) for the call in flight
   const int* tile_ptr[6] = {};                 // ragged call in flight: compact 128-row tile lists per level (device), or nullptr
   int tile_cnt[6] = {};
-  int exp_fuse_res = 0;                        // debug_set key 15: level-1 residual block as one kernel (tc_gemm6.cuh, mode 7);
-                                               // correct, saves a launch and the intermediate buffer, but not faster (2.9 vs 3.1 ms)
   int exp_resample_simple = 0;                 // debug_set key 16: first-draft one-thread-per-output resampler (A/B of resample_poly_kernel)
-  int exp_full_lo = 0;                         // debug_set key 14: mode 7 keeps full-size (fp32-sized) lo buffers
   int exp_no_tile_list = 0;                    // debug_set key 13: walk the mt_max x B grid and skip (the old schedule)
   int phase = 0, front_b0 = 0, front_b1 = 0;   // mimi_b200_encode_phase: which part of the pipeline the call in flight runs
-  int exp_raw_h1 = 0;                          // debug_set key 12: h1 crosses HBM as raw fp32 (front_fused raw_out + tc_gemm4 for D1)
   int exp_linear_k = 0;                        // debug_set key 11: k-blocks in linear order (no tap grouping)
   int exp_no_flat = 0;                         // debug_set key 10: never flatten the linears' row dimension across items
   int num_clusters = 74;                       // co-resident CTA pairs of the cta_group::2 GEMM (tc_gemm5.cuh, mode 6)
@@ -211,7 +178,6 @@ struct mimi_b200 {
   CUtensorMap map_embed_hi, map_embed_lo;
   std::map<MapKey, MapSet> amap_cache;   // activation maps per (workspace, B, N)
   PlanTC last_tc;
-  PlanR last_r;
   bool last_was_tc = false;
   // decode direction (decode_host.inl): fp32 weights in the [K][N] layout of the FFMA GEMM
   bool dec_loaded = false;
@@ -414,7 +380,6 @@ static void design_taps(int sr_in, int sr_out, std::vector<float>& taps, int& c,
 }
 
 #include "tc_host.inl"
-#include "tc5_host.inl"
 #include "decode_host.inl"
 
 // ratios the register-tiled polyphase resampler is instantiated for (16 k, 48 k, 8 k, 32 k, 12 k, 96 k -> 24 k, identity)
@@ -478,46 +443,26 @@ int mimi_b200_create(mimi_b200_t** out, int device_ordinal) {
   if (cudaMallocHost((void**)&h->range_flag, sizeof(int)) == cudaSuccess) *h->range_flag = 0;
   else { h->range_flag = nullptr; cudaGetLastError(); }
   cudaFuncSetAttribute(swa_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttSmemBytes);
-  cudaFuncSetAttribute(swa_attention2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAtt2SmemBytes);
-  cudaFuncSetAttribute(swa_attention3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAtt2SmemBytes);
   cudaFuncSetAttribute(rvq_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRvqSmemBytes);
-  cudaFuncSetAttribute(tc::tc_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::smem_bytes(128));
-  cudaFuncSetAttribute(tc::tc_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::smem_bytes(64));
-  cudaFuncSetAttribute(tc2::tc2_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::Cfg<128>::SMEM);
-  cudaFuncSetAttribute(tc2::tc2_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::Cfg<64>::SMEM);
-  cudaFuncSetAttribute(tc2::tc2_gemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::Cfg<32>::SMEM);
-  cudaFuncSetAttribute(tc2::tc2p_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::CfgP<128>::SMEM);
-  cudaFuncSetAttribute(tc2::tc2p_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::CfgP<64>::SMEM);
-  cudaFuncSetAttribute(tc4::tc4_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc4::Cfg<128>::SMEM);
-  cudaFuncSetAttribute(tc4::tc4_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc4::Cfg<64>::SMEM);
-  cudaFuncSetAttribute(tc4::tc4_gemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc4::Cfg<32>::SMEM);
-  cudaFuncSetAttribute(tcp::tcp_gemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcp::Cfg<256>::SMEM);
-  cudaFuncSetAttribute(tcp::tcp_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcp::Cfg<128>::SMEM);
   cudaFuncSetAttribute(tcp::tcp_gemm_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcp::Cfg<256, 1>::SMEM);
   cudaFuncSetAttribute(tcp::tcp_gemm_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcp::Cfg<128, 1>::SMEM);
   cudaFuncSetAttribute(tcp::tcp_gemm_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcp::Cfg<64, 1>::SMEM);
-  cudaFuncSetAttribute(tcr::tcr_resblock_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tcr::kSmem);
-  cudaFuncSetAttribute(tcp::tcp_gemm_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcp::Cfg<256, 2>::SMEM);
-  cudaFuncSetAttribute(tcp::tcp_gemm_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcp::Cfg<128, 2>::SMEM);
-  cudaFuncSetAttribute(tcp::tcp_gemm_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcp::Cfg<64, 2>::SMEM);
   cudaFuncSetAttribute(tcp::tcp_gemm_kernel<256, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcp::Cfg<256, 3>::SMEM);
   cudaFuncSetAttribute(tcp::tcp_gemm_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcp::Cfg<128, 3>::SMEM);
   cudaFuncSetAttribute(tcp::tcp_gemm_kernel<64, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcp::Cfg<64, 3>::SMEM);
   {
     // how many CTA pairs of the widest instance fit at once (one per TPC unless the device says otherwise)
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(2 * (h->num_sms / 2)); cfg.blockDim = dim3(tcp::kThreads); cfg.dynamicSmemBytes = tcp::Cfg<256>::SMEM;
+    cfg.gridDim = dim3(2 * (h->num_sms / 2)); cfg.blockDim = dim3(tcp::kThreads); cfg.dynamicSmemBytes = tcp::Cfg<256, 1>::SMEM;
     cudaLaunchAttribute at{};
     at.id = cudaLaunchAttributeClusterDimension; at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
     cfg.attrs = &at; cfg.numAttrs = 1;
     int ncl = 0;
-    if (cudaOccupancyMaxActiveClusters(&ncl, tcp::tcp_gemm_kernel<256>, &cfg) == cudaSuccess && ncl > 0)
+    if (cudaOccupancyMaxActiveClusters(&ncl, tcp::tcp_gemm_kernel<256, 1>, &cfg) == cudaSuccess && ncl > 0)
       h->num_clusters = std::min(ncl, h->num_sms / 2);
     else { cudaGetLastError(); h->num_clusters = h->num_sms / 2; }
   }
   cudaFuncSetAttribute(atc::swa_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, atc::kSmem);
-  cudaFuncSetAttribute(tc3::tc3_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc3::Cfg<128>::SMEM);
-  cudaFuncSetAttribute(tc3::tc3_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc3::Cfg<64>::SMEM);
   cudaFuncSetAttribute(rvqtc::rvq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, rvqtc::kSmem);
   cudaFuncSetAttribute(f0::front_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, f0::kSmem);
   cudaFuncSetAttribute(tc2::tc_shift_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 40960);
@@ -551,19 +496,15 @@ int mimi_b200_debug_set(mimi_b200_t* h, int key, int value) {
   if (key == 0) h->dbg_layers = std::min(std::max(value, 0), MIMI_B200_NUM_LAYERS);
   else if (key == 1) h->dbg_last_conv = std::min(std::max(value, 0), MIMI_B200_NUM_CONVS - 1);
   else if (key == 2) { h->prof_on = value != 0; h->prof_n = 0; }
-  else if (key == 3) h->mode = std::min(std::max(value, 0), 9);
-  else if (key == 4) h->exp_single_acc = value != 0;
+  else if (key == 3) {
+    if (value != 0 && value != 7 && value != 9) return fail(h, MIMI_B200_ERR_ARG, "debug_set: kernel generation must be 0, 7 or 9");
+    h->mode = value;
+  }
   else if (key == 5) h->exp_chunk_kb = std::max(value, 0);
-  else if (key == 6) h->use_planes = value != 0;
-  else if (key == 7) h->exp_prefetch = value != 0;
-  else if (key == 8) h->att_variant = (value >= 2 && value <= 4) ? value : 2;
   else if (key == 9) h->exp_pair_n128 = std::max(value, 0);
   else if (key == 10) h->exp_no_flat = value != 0;
   else if (key == 11) h->exp_linear_k = value;           // 1: linear order, 2: tap-grouped with the channel panels innermost
-  else if (key == 12) h->exp_raw_h1 = value != 0;
   else if (key == 13) h->exp_no_tile_list = value != 0;
-  else if (key == 14) h->exp_full_lo = value != 0;
-  else if (key == 15) h->exp_fuse_res = value != 0;
   else if (key == 16) h->exp_resample_simple = value != 0;
   else return fail(h, MIMI_B200_ERR_ARG, "debug_set: unknown key");
   return MIMI_B200_OK;
@@ -698,15 +639,12 @@ int mimi_b200_workspace_bytes(mimi_b200_t* h, int B, int64_t N, int K, size_t* o
   if (!h || !out_bytes) return fail(h, MIMI_B200_ERR_ARG, "workspace_bytes: NULL argument");
   if (B < 0 || N < 0 || N > (1ll << 30) || K < 1 || K > MIMI_B200_MAX_QUANTIZERS)
     return fail(h, MIMI_B200_ERR_ARG, "workspace_bytes: bad B/N/K");
-  // sized for the compute mode in force (debug_set key 3): the fp32 FFMA plan only in mode 0, level-0 buffers only
-  // in the unfused tensor-core modes
+  // sized for the kernel generation in force (debug_set key 3)
   const bool simt = h->mode == 0 || h->dbg_last_conv != MIMI_B200_NUM_CONVS - 1;
-  *out_bytes = (simt ? make_plan(B, N, K).bytes : h->mode == 5 ? make_plan_r(B, N, K).bytes : make_plan_tc(B, N, K, h->mode < 3, h->mode >= 7 && !h->exp_full_lo, h->mode == 8, h->mode == 9).bytes) + 256;
-  if (!simt && h->mode != 5) {
-    const PlanTC pt = make_plan_tc(B, N, K, h->mode < 3, h->mode >= 7 && !h->exp_full_lo, h->mode == 8, h->mode == 9);
-    return ensure_stage(h, (pt.bytes - (size_t)pt.ints) / sizeof(int));     // lengths + tile lists of a batch this size
-  }
-  return MIMI_B200_OK;
+  if (simt) { *out_bytes = make_plan(B, N, K).bytes + 256; return MIMI_B200_OK; }
+  const PlanTC pt = make_plan_tc(B, N, K, h->mode == 9);
+  *out_bytes = pt.bytes + 256;
+  return ensure_stage(h, (pt.bytes - (size_t)pt.ints) / sizeof(int));     // lengths + tile lists of a batch this size
 }
 
 static int encode_impl(mimi_b200_t* h, const float* d_input, int B, int64_t N, const int64_t* h_valid_len, int K,
@@ -724,8 +662,8 @@ int mimi_b200_encode_phase(mimi_b200_t* h, int phase, int b0, int b1, const floa
                            size_t workspace_bytes, void* stream) {
   if (!h) return MIMI_B200_ERR_ARG;
   if (phase < MIMI_B200_PHASE_BEGIN || phase > MIMI_B200_PHASE_FINISH) return fail(h, MIMI_B200_ERR_ARG, "encode_phase: bad phase");
-  if (h->mode < 3 || h->mode == 5 || h->dbg_last_conv != MIMI_B200_NUM_CONVS - 1)  // modes 3, 4, 6, 7, 8
-    return fail(h, MIMI_B200_ERR_STATE, "encode_phase: needs the fused front end (modes 3, 4, 6)");
+  if (h->mode == 0 || h->dbg_last_conv != MIMI_B200_NUM_CONVS - 1)
+    return fail(h, MIMI_B200_ERR_STATE, "encode_phase: needs a tensor-core generation (mode 7 or 9)");
   if (phase == MIMI_B200_PHASE_FRONT && (b0 < 0 || b1 > B || b0 > b1)) return fail(h, MIMI_B200_ERR_ARG, "encode_phase: bad item range");
   h->phase = phase; h->front_b0 = b0; h->front_b1 = b1;
   const int rc = encode_impl(h, d_input, B, N, h_valid_len, K, d_codes, d_latent_opt, d_workspace, workspace_bytes, stream);
@@ -753,20 +691,17 @@ static int encode_impl(mimi_b200_t* h, const float* d_input, int B, int64_t N, c
 
   const bool use_tc = h->mode >= 1 && h->dbg_last_conv == MIMI_B200_NUM_CONVS - 1;
   const Plan p = make_plan(B, N, K);
-  const PlanTC pt = make_plan_tc(B, N, K, h->mode < 3, h->mode >= 7 && !h->exp_full_lo, h->mode == 8, h->mode == 9);
-  const PlanR pr = make_plan_r(B, N, K);
-  const bool use_r5 = use_tc && h->mode == 5;
-  const size_t need = use_r5 ? pr.bytes : use_tc ? pt.bytes : p.bytes;
+  const PlanTC pt = make_plan_tc(B, N, K, h->mode == 9);
+  const size_t need = use_tc ? pt.bytes : p.bytes;
   // align the workspace base to 256 bytes
   uintptr_t base = (reinterpret_cast<uintptr_t>(d_workspace) + 255) & ~uintptr_t(255);
   if (base + need > reinterpret_cast<uintptr_t>(d_workspace) + workspace_bytes)
     return fail(h, MIMI_B200_ERR_WORKSPACE, "encode: workspace too small, need " + std::to_string(need + 256));
   if (p.rows[4] > kRopeMaxPos) return fail(h, MIMI_B200_ERR_ARG, "encode: more than 16384 25-Hz positions per item");
   float* ws = reinterpret_cast<float*>(base);
-  int* dints = reinterpret_cast<int*>(base + (use_r5 ? pr.ints : use_tc ? pt.ints : p.ints));
+  int* dints = reinterpret_cast<int*>(base + (use_tc ? pt.ints : p.ints));
   h->last = p;
   h->last_tc = pt;
-  h->last_r = pr;
   h->last_was_tc = use_tc;
   h->last_mode = h->mode;
   h->last_ws = ws;
@@ -803,7 +738,7 @@ static int encode_impl(mimi_b200_t* h, const float* d_input, int B, int64_t N, c
     v[(size_t)7 * B] = acc;
     total_frames = acc;
     for (int l = 0; l < 6; ++l) { h->tile_ptr[l] = nullptr; h->tile_cnt[l] = 0; }
-    if (use_tc && !use_r5 && !h->exp_no_tile_list && B < 2048) {
+    if (use_tc && !h->exp_no_tile_list && B < 2048) {
       // compact lists of the 128-row tiles that exist at levels 1..5 (the outputs of every conv), m-tile major so that
       // neighbouring CTAs work on the same stretch of time; the persistent GEMMs deal them out round-robin
       for (int l = 1; l < 6; ++l) {
@@ -829,11 +764,6 @@ static int encode_impl(mimi_b200_t* h, const float* d_input, int B, int64_t N, c
     }
   }
 
-  if (use_r5) {
-    int rc5 = encode_tc5(h, d_input, B, N, K, pr, ws, dlen, maxlen, dprefix, total_frames, d_codes, d_latent_opt, st);
-    if (rc5 == MIMI_B200_OK && !h->sync_err.empty()) return fail(h, MIMI_B200_ERR_CUDA, h->sync_err);
-    return rc5;
-  }
   if (use_tc) {
     int rc_tc = encode_tc(h, d_input, B, N, K, pt, ws, dlen, maxlen, dprefix, total_frames, d_codes, d_latent_opt, st);
     if (rc_tc == MIMI_B200_OK && !h->sync_err.empty()) return fail(h, MIMI_B200_ERR_CUDA, h->sync_err);
@@ -847,8 +777,7 @@ static int encode_impl(mimi_b200_t* h, const float* d_input, int B, int64_t N, c
   {
     dim3 grid((maxlen[0] + 127) / 128, B);
     if (maxlen[0] > 0) {
-      conv0_kernel<<<grid, 256, 0, st>>>(d_input, N, h->conv_wt[0], h->conv_b[0], ws + p.a0, istride(0, 64), dlen[0], maxlen[0],
-                                         nullptr, nullptr, 0, 0);
+      conv0_kernel<<<grid, 256, 0, st>>>(d_input, N, h->conv_wt[0], h->conv_b[0], ws + p.a0, istride(0, 64), dlen[0], maxlen[0]);
       h->launches++; mark(h, 0, st);
       CUDA_TRY(h, cudaGetLastError());
     }
@@ -910,7 +839,7 @@ static int encode_impl(mimi_b200_t* h, const float* d_input, int B, int64_t N, c
     if ((rc = launch_gemm(h, g, B, T25, st, 15))) return rc;
     dim3 agrid((T25 + kAttQT - 1) / kAttQT, kHeads, B);
     swa_attention_kernel<<<agrid, 256, kAttSmemBytes, st>>>(ws + p.qkv, istride(4, 1536), ws + p.att, istride(4, 512),
-                                                            h->rope_cos, h->rope_sin, dlen[4], T25, nullptr);
+                                                            h->rope_cos, h->rope_sin, dlen[4], T25);
     h->launches++; mark(h, 16, st);
     CUDA_TRY(h, cudaGetLastError());
     g = GemmParams{};   // o_proj + LayerScale + residual (in place on z)
@@ -973,37 +902,10 @@ int mimi_b200_debug_tap(mimi_b200_t* h, int which, float* d_out, size_t cap, int
   if (!h || !h->last_ws) return fail(h, MIMI_B200_ERR_STATE, "debug_tap: no encode call yet");
   const Plan& p = h->last;
   TapInfo t{};
-  if (h->last_was_tc && h->last_mode == 5) {
-    const PlanR& q = h->last_r;
-    const RawBuf* rb = nullptr;
-    switch (which) {
-      case 3: rb = &q.d1; break;
-      case 6: rb = &q.d2; break;
-      case 9: rb = &q.d3; break;
-      case 13: rb = &q.z; break;
-      case 200: rb = &q.e; break;
-      case 201: rb = &q.rp; break;
-      default:
-        if (which >= 100 && which < 100 + MIMI_B200_NUM_LAYERS) rb = &q.z;
-        else return fail(h, MIMI_B200_ERR_ARG, "debug_tap: tap not materialised in mode 5");
-    }
-    const size_t row_floats = (size_t)q.rows[rb->level] * rb->C;
-    if (rows_per_item) *rows_per_item = q.rows[rb->level];
-    if (channels) *channels = rb->C;
-    if (!d_out) return MIMI_B200_OK;
-    if (cap < row_floats * q.B) return fail(h, MIMI_B200_ERR_ARG, "debug_tap: output too small");
-    CUDA_TRY(h, cudaMemcpy2DAsync(d_out, row_floats * sizeof(float),
-                                  static_cast<float*>(h->last_ws) + rb->off + (long long)rb->front * rb->C,
-                                  (size_t)rb->item_stride * sizeof(float), row_floats * sizeof(float), (size_t)q.B,
-                                  cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
-    return MIMI_B200_OK;
-  }
   if (h->last_was_tc) {
     const PlanTC& q = h->last_tc;
-    if (h->last_mode >= 3 && which < 3) return fail(h, MIMI_B200_ERR_ARG, "debug_tap: level-0 activations stay on chip in mode 3");
+    if (which < 3) return fail(h, MIMI_B200_ERR_ARG, "debug_tap: level-0 activations stay on chip in the tensor-core generations");
     switch (which) {
-      case 0: t = {q.a0, 0, 64}; break;
-      case 1: t = {q.r1, 0, 32}; break;
       case 3: t = {q.d1, 1, 128}; break;
       case 6: t = {q.d2, 2, 256}; break;
       case 9: t = {q.d3, 3, 512}; break;
@@ -1043,76 +945,51 @@ int mimi_b200_debug_tap(mimi_b200_t* h, int which, float* d_out, size_t cap, int
 }
 
 // Unit-test hook for the tensor-core GEMM: out[M][N] = epilogue(A[M][K] * W[N][K]^T) through the same split /
-// TMA / tcgen05 path the encoder uses (A is split on the device, W on the host).
-__global__ void debug_split_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, long long n) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) split_tf32(x[i], hi[i], lo[i]);
-}
-
-__global__ void debug_split_lob_kernel(const float* __restrict__ x, float* __restrict__ hi, uint16_t* __restrict__ lo, long long n,
-                                       float* __restrict__ hib, int lob) {
+// TMA / tcgen05 path the encoder uses (A is split on the device, W on the host), in the generation selected by key 3.
+__global__ void debug_split_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, long long n, int lob) {
   const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  if (i < n) store_split4_x(hi, reinterpret_cast<float*>(lo), hib, i, *reinterpret_cast<const float4*>(x + i), lob);
+  if (i < n) store_split4_x(hi, lo, i, *reinterpret_cast<const float4*>(x + i), lob);
 }
 
 int mimi_b200_debug_tc_gemm(mimi_b200_t* h, const float* d_a, const float* h_w, const float* d_bias_opt, int M, int N,
                             int K, int act, float* d_out, void* stream) {
   if (!h || !d_a || !h_w || !d_out) return fail(h, MIMI_B200_ERR_ARG, "debug_tc_gemm: NULL argument");
-  if (M <= 0 || N % 32 || K % 32 || ((h->mode < 2 || h->mode == 4) && N % 64))
-    return fail(h, MIMI_B200_ERR_ARG, "debug_tc_gemm: need N % 32 == 0 (mode 2) / N % 64 == 0 (mode 1) and K % 32 == 0");
+  if (h->mode != 7 && h->mode != 9) return fail(h, MIMI_B200_ERR_STATE, "debug_tc_gemm: needs a tensor-core generation (mode 7 or 9)");
+  if (M <= 0 || N % 64 || K % 32) return fail(h, MIMI_B200_ERR_ARG, "debug_tc_gemm: need N % 64 == 0 and K % 32 == 0");
   CUDA_TRY(h, cudaSetDevice(h->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int rc;
   if ((rc = tc_init_driver(h))) return rc;
+  const size_t mark = h->allocs.size();          // the test weight is freed again below
   TcWeight w;
   if ((rc = tc_make_weight(h, &w, std::vector<float>(h_w, h_w + (size_t)N * K), N, K))) return rc;
+  const bool f16 = h->mode == 9;
   float *hi = nullptr, *lo = nullptr;
   const long long n = (long long)M * K;
   CUDA_TRY(h, cudaMalloc((void**)&hi, n * sizeof(float)));
   CUDA_TRY(h, cudaMalloc((void**)&lo, n * sizeof(float)));
-  const bool lob = h->mode >= 7;
-  float* hib = nullptr;
-  if (h->mode == 8) CUDA_TRY(h, cudaMalloc((void**)&hib, n * sizeof(uint16_t)));
-  const bool f16 = h->mode == 9;
-  if (lob) debug_split_lob_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(d_a, hi, reinterpret_cast<uint16_t*>(lo), n, hib, f16 ? 3 : 1);
-  else debug_split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_a, hi, lo, n);
+  debug_split_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(d_a, hi, lo, n, f16 ? 3 : 1);
   CUtensorMap ma_hi, ma_lo;
   const cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)M, 1};
   const cuuint64_t strides[2] = {(cuuint64_t)K * sizeof(float), (cuuint64_t)n * sizeof(float)};
   const cuuint64_t strides_b[2] = {(cuuint64_t)K * 2, (cuuint64_t)n * 2};
   if (f16) { if ((rc = tc_make_map_bf16(h, &ma_hi, hi, 3, dims, strides_b, tc::kBM))) return rc; }
   else if ((rc = tc_make_map(h, &ma_hi, hi, 3, dims, strides, tc::kBM))) return rc;
-  CUtensorMap ma_hib;
-  if (hib && (rc = tc_make_map_bf16(h, &ma_hib, hib, 3, dims, strides_b, tc::kBM))) return rc;
-  if (lob) { if ((rc = tc_make_map_bf16(h, &ma_lo, lo, 3, dims, strides_b, tc::kBM))) return rc; }
-  else if ((rc = tc_make_map(h, &ma_lo, lo, 3, dims, strides, tc::kBM))) return rc;
+  if ((rc = tc_make_map_bf16(h, &ma_lo, lo, 3, dims, strides_b, tc::kBM))) return rc;
   tc::Epilogue ep{};
   ep.bias = d_bias_opt; ep.out_raw = d_out; ep.raw_item_stride = (long long)M * N; ep.act = act;
   ep.uniform_len_in = M; ep.conv_stride = 1; ep.N = N;
-  ep.single_acc = h->exp_single_acc; ep.chunk_kb = h->exp_chunk_kb; ep.lo_bf16 = f16 ? 3 : lob;
+  ep.chunk_kb = h->exp_chunk_kb; ep.lo_bf16 = f16 ? 3 : 1;
   ep.wscale = f16 ? w.wscale : nullptr;
-  if (f16 && !tcp_applies(h, w)) return fail(h, MIMI_B200_ERR_ARG, "debug_tc_gemm: mode 9 needs N % 64 == 0");
-  if (tcp_applies(h, w)) {
-    launch_tcp(h, ma_hi, ma_lo, w, ep, 1, (M + tc::kBM - 1) / tc::kBM, st, 1, 1, 0, nullptr, 0, hib ? &ma_hib : nullptr);
-  } else if (h->mode == 4) {
-    CUtensorMap m4[4];
-    for (int i = 0; i < 4; ++i)
-      if ((rc = tc_make_map4(h, &m4[i], (i & 1) ? lo : hi, K, 1, M, 1, n, 128))) return rc;
-    if ((rc = launch_tc3(h, m4, w, ep, 1, M, K, 1, 1, st))) return rc;
-  } else if (h->mode >= 2) {
-    launch_tc2(h, ma_hi, ma_lo, w, ep, 1, (M + tc::kBM - 1) / tc::kBM, st);
-  } else {
-    dim3 grid((M + tc::kBM - 1) / tc::kBM, N / w.BN, 1);
-    if (w.BN == 128) tc::tc_gemm_kernel<128><<<grid, tc::kThreads, tc::smem_bytes(128), st>>>(ma_hi, ma_lo, w.map_hi, w.map_lo, K, ep);
-    else if (w.BN == 64) tc::tc_gemm_kernel<64><<<grid, tc::kThreads, tc::smem_bytes(64), st>>>(ma_hi, ma_lo, w.map_hi, w.map_lo, K, ep);
-    else return fail(h, MIMI_B200_ERR_ARG, "debug_tc_gemm: mode 1 has no BN=32 kernel");
-  }
+  rc = launch_tcp(h, ma_hi, ma_lo, w, ep, 1, (M + tc::kBM - 1) / tc::kBM, st);
   h->launches += 2;
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   cudaFree(hi);
   cudaFree(lo);
-  if (hib) cudaFree(hib);
+  for (size_t i = mark; i < h->allocs.size(); ++i) cudaFree(h->allocs[i]);
+  h->allocs.resize(mark);
+  if (rc) return rc;
   if (e != cudaSuccess) return fail(h, MIMI_B200_ERR_CUDA, std::string("debug_tc_gemm: ") + cudaGetErrorString(e));
   return MIMI_B200_OK;
 }

@@ -20,12 +20,6 @@ namespace tc {
 constexpr int kBM = 128;
 constexpr int kBK = 32;                       // fp32 elements per k-block = one 128-byte swizzle row
 constexpr int kUmmaK = 8;                     // tf32 MMA K
-constexpr int kThreads = 192;
-constexpr int kSmemBudget = 196608;           // operand ring bytes (192 KB)
-
-__host__ __device__ constexpr int stage_bytes(int bn) { return 2 * kBM * kBK * 4 + 2 * bn * kBK * 4; }
-__host__ __device__ constexpr int num_stages(int bn) { return kSmemBudget / stage_bytes(bn); }
-__host__ __device__ constexpr int smem_bytes(int bn) { return num_stages(bn) * stage_bytes(bn) + 1024 + 256; }
 
 struct Epilogue {
   const float* bias;            // [N] or nullptr
@@ -43,9 +37,7 @@ struct Epilogue {
   int uniform_len_in;
   int conv_stride;              // Lout = ceil(len_in / conv_stride)
   int N;
-  int single_acc;               // experiment (tc_gemm2 only): cross terms accumulate into the main accumulator
-  int chunk_kb;                 // experiment (tc_gemm2 only): k-blocks per accumulation chunk (0 -> kChunkKB)
-  int prefetch_next;            // tc_gemm2: L2-prefetch the next tile's activation boxes
+  int chunk_kb;                 // experiment: k-blocks per accumulation chunk (0 -> kChunkKB)
   int lo_bf16;                  // 1: out_lo is a bf16 array (mode 7), same element indexing as out_hi; 3: out_hi and out_lo are
                                 //    fp16 arrays in the split_f16 format (mode 9)
   const float* wscale;          // [N] per-column power-of-two factor that undoes the weight scaling of mode 9, or nullptr
@@ -54,7 +46,6 @@ struct Epilogue {
   // the fp16 range flag: row r belongs to item r / flat_rows and is real iff r % flat_rows < flat_len[item].
   const int* flat_len;          // device [B] or nullptr (every row real)
   int flat_rows;                // 0: not a flattened launch
-  float* out_hib;               // mode 8: bf16(hi) array of the split output (same indexing), or nullptr
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -167,179 +158,14 @@ constexpr int kChunkKB = 4;                   // k-blocks (of 32) accumulated in
 
 // Accuracy note. The tensor core adds into its fp32 accumulator with truncation, so a long K loop drifts by
 // ~0.3 ulp per MMA (measured: 3e-6 relative at K=512 growing to 1e-4 by K=8192, far above the 3e-5 the codes
-// tolerate). Hence: (1) only hi*hi goes to the main accumulator, and only for kChunkKB k-blocks (16 MMAs) at
-// a time -- the epilogue warps drain each chunk from TMEM (double-buffered) and add it to per-thread fp32
-// running sums with round-to-nearest FADDs while the next chunk is being computed; (2) the two small cross
-// terms lo*hi + hi*lo (2^-11 of the main term, so their own drift is irrelevant) accumulate over the whole K
-// in a third TMEM region that is drained once.
-template <int BN>
-__global__ void __launch_bounds__(kThreads, 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-               const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo, int K,
-               const Epilogue ep) {
-  constexpr int STAGES = num_stages(BN);
-  constexpr int A_BYTES = kBM * kBK * 4;           // 16 KB
-  constexpr int W_BYTES = BN * kBK * 4;
-  constexpr int STAGE = stage_bytes(BN);
-  constexpr int TMEM_COLS = (BN == 128) ? 512 : 256;   // main[0] | main[1] | small  (3*BN, power of two)
-  static_assert(BN == 64 || BN == 128, "BN");
-
-  const int b = blockIdx.z;
-  const int Lin = ep.len_in ? ep.len_in[b] : ep.uniform_len_in;
-  const int Lout = (Lin + ep.conv_stride - 1) / ep.conv_stride;
-  const int m0 = blockIdx.x * kBM;
-  if (m0 >= Lout) return;                          // whole CTA leaves before any barrier exists
-  const int n0 = blockIdx.y * BN;
-
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* acc_full = empty_bar + STAGES;         // [2] chunk accumulator ready (MMA -> epilogue)
-  uint64_t* acc_empty = acc_full + 2;              // [2] chunk accumulator drained (epilogue -> MMA)
-  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nkb = K / kBK;
-  const int nchunks = (nkb + kChunkKB - 1) / kChunkKB;
-
-  if (warp == 0 && lane == 0) {
-    prefetch_tmap(&tmA_hi); prefetch_tmap(&tmA_lo); prefetch_tmap(&tmW_hi); prefetch_tmap(&tmW_lo);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_ptr)), "r"(TMEM_COLS));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = *tmem_base_ptr;
-  const uint32_t tmem_small = tmem_base + 2 * BN;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-        mbar_wait(&empty_bar[s], ph ^ 1u);
-        uint8_t* st = smem + s * STAGE;
-        mbar_expect_tx(&full_bar[s], STAGE);
-        tma_load_3d(st, &tmA_hi, &full_bar[s], kb * kBK, m0, b);
-        tma_load_3d(st + A_BYTES, &tmA_lo, &full_bar[s], kb * kBK, m0, b);
-        tma_load_2d(st + 2 * A_BYTES, &tmW_hi, &full_bar[s], kb * kBK, n0);
-        tma_load_2d(st + 2 * A_BYTES + W_BYTES, &tmW_lo, &full_bar[s], kb * kBK, n0);
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(kBM, BN);
-      for (int c = 0; c < nchunks; ++c) {
-        const int buf = c & 1;
-        mbar_wait(&acc_empty[buf], ((uint32_t)(c >> 1) & 1u) ^ 1u);      // drained two chunks ago
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t tmem_main = tmem_base + buf * BN;
-        const int kb_end = min(nkb, (c + 1) * kChunkKB);
-        for (int kb = c * kChunkKB; kb < kb_end; ++kb) {
-          const int s = kb % STAGES;
-          const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-          mbar_wait(&full_bar[s], ph);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t a_hi = smem_u32(smem + s * STAGE);
-          const uint32_t a_lo = a_hi + A_BYTES;
-          const uint32_t w_hi = a_hi + 2 * A_BYTES;
-          const uint32_t w_lo = w_hi + W_BYTES;
-          const bool first_in_chunk = kb == c * kChunkKB;
-#pragma unroll
-          for (int k = 0; k < kBK / kUmmaK; ++k)
-            umma_tf32(tmem_main, make_smem_desc(a_hi + k * 32), make_smem_desc(w_hi + k * 32), idesc, !(first_in_chunk && k == 0));
-#pragma unroll
-          for (int k = 0; k < kBK / kUmmaK; ++k)
-            umma_tf32(tmem_small, make_smem_desc(a_lo + k * 32), make_smem_desc(w_hi + k * 32), idesc, (kb | k) != 0);
-#pragma unroll
-          for (int k = 0; k < kBK / kUmmaK; ++k)
-            umma_tf32(tmem_small, make_smem_desc(a_hi + k * 32), make_smem_desc(w_lo + k * 32), idesc, 1u);
-          umma_commit(&empty_bar[s]);             // frees the smem slot once these MMAs have read it
-        }
-        umma_commit(&acc_full[buf]);              // chunk (and, after the last one, the small terms) complete
-      }
-    }
-  } else {
-    // ---- epilogue warps: warp w may touch TMEM lanes [32*(w%4), +32); thread = one output row -------------
-    const int quarter = warp & 3;
-    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-    float acc[BN];
-#pragma unroll
-    for (int i = 0; i < BN; ++i) acc[i] = 0.f;
-    for (int c = 0; c < nchunks; ++c) {
-      const int buf = c & 1;
-      mbar_wait(&acc_full[buf], (uint32_t)(c >> 1) & 1u);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t taddr = tmem_base + lane_off + (uint32_t)(buf * BN);
-#pragma unroll
-      for (int c0 = 0; c0 < BN; c0 += 16) {
-        uint32_t r[16];
-        tmem_ld16(taddr + (uint32_t)c0, r);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-        for (int i = 0; i < 16; ++i) acc[c0 + i] += __uint_as_float(r[i]);
-      }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[buf]);
-    }
-    // the last acc_full commit also covers every small-term MMA
-#pragma unroll
-    for (int c0 = 0; c0 < BN; c0 += 16) {
-      uint32_t r[16];
-      tmem_ld16(tmem_small + lane_off + (uint32_t)c0, r);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-      for (int i = 0; i < 16; ++i) acc[c0 + i] += __uint_as_float(r[i]);
-    }
-    // ---- all TMEM traffic is done: per-thread math (may diverge freely) and stores --------------------------
-    const int row = m0 + quarter * 32 + lane;
-    if (row < Lout) {
-      const long long raw_off = (long long)b * ep.raw_item_stride + (long long)row * ep.N + n0;
-      const long long split_off = (long long)b * ep.split_item_stride + (long long)(ep.split_front + row) * ep.N + n0;
-#pragma unroll
-      for (int c0 = 0; c0 < BN; c0 += 4) {
-        float4 v = make_float4(acc[c0], acc[c0 + 1], acc[c0 + 2], acc[c0 + 3]);
-        if (ep.bias) {
-          const float4 t = ld_nc_f4(ep.bias + n0 + c0);
-          v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
-        }
-        if (ep.act == 1) { v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w); }
-        if (ep.scale) {
-          const float4 t = ld_nc_f4(ep.scale + n0 + c0);
-          v.x *= t.x; v.y *= t.y; v.z *= t.z; v.w *= t.w;
-        }
-        if (ep.res) {
-          const float4 t = *reinterpret_cast<const float4*>(ep.res + raw_off + c0);
-          v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
-        }
-        if (ep.out_raw) *reinterpret_cast<float4*>(ep.out_raw + raw_off + c0) = v;
-        if (ep.out_hi) {
-          if (ep.elu_split) { v.x = elu1(v.x); v.y = elu1(v.y); v.z = elu1(v.z); v.w = elu1(v.w); }
-          store_split4(ep.out_hi + split_off + c0, ep.out_lo + split_off + c0, v);
-        }
-      }
-    }
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  if (warp == 1) {
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
-  }
-}
+// tolerate). Hence the GEMM kernels accumulate only kChunkKB k-blocks at a time inside TMEM: the epilogue warps drain each
+// chunk (double-buffered) and add it to per-thread fp32 running sums with round-to-nearest FADDs while the next chunk is
+// being computed.
 
 // Zero the halo rows of one split buffer pair: rows [0, front) and [front + L_b, front + L_b + back) of every
 // item (the causal left pad and the right "extra" pad of the consuming conv).
 __global__ void zero_halo_kernel(float* hi, float* lo, long long item_stride, int C, int front, int back,
-                                 const int* __restrict__ len, int uniform_len, int lob = 0, float* hib = nullptr) {
+                                 const int* __restrict__ len, int uniform_len, int lob) {
   const int b = blockIdx.y;
   const int L = len ? len[b] : uniform_len;
   const int per = (front + back) * C;
@@ -350,9 +176,7 @@ __global__ void zero_halo_kernel(float* hi, float* lo, long long item_stride, in
     const long long o = (long long)b * item_stride + (long long)r * C + c;
     if (lob == 3) reinterpret_cast<uint16_t*>(hi)[o] = 0;
     else hi[o] = 0.f;
-    if (lob) reinterpret_cast<uint16_t*>(lo)[o] = 0;
-    else lo[o] = 0.f;
-    if (hib) reinterpret_cast<uint16_t*>(hib)[o] = 0;
+    reinterpret_cast<uint16_t*>(lo)[o] = 0;
   }
 }
 
@@ -362,8 +186,7 @@ __global__ void zero_halo_kernel(float* hi, float* lo, long long item_stride, in
 __global__ void __launch_bounds__(256) pad_replicate_split_kernel(const float* __restrict__ z, long long z_item_stride,
                                                                   float* __restrict__ hi, float* __restrict__ lo,
                                                                   long long split_item_stride,
-                                                                  const int* __restrict__ len, int uniform_len, int lob = 0,
-                                                                  float* __restrict__ hib = nullptr) {
+                                                                  const int* __restrict__ len, int uniform_len, int lob) {
   const int b = blockIdx.y;
   const int T = len ? len[b] : uniform_len;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -375,7 +198,7 @@ __global__ void __launch_bounds__(256) pad_replicate_split_kernel(const float* _
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int c = (i * 32 + lane) * 4;
-    store_split4_x(hi, lo, hib, o + c, ld_nc_f4(zr + c), lob);
+    store_split4_x(hi, lo, o + c, ld_nc_f4(zr + c), lob);
   }
 }
 

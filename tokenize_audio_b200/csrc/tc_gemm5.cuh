@@ -51,31 +51,25 @@ __device__ unsigned* g_tcp_marks = nullptr;
 #define TCP_MARK(slot, v)
 #endif
 
-// LOB = 1 (mode 7): the activations' lo parts are bf16 arrays. The stage then holds A_hi (fp32, 16 KB), A_lo (bf16, 8 KB,
-// SWIZZLE_64B rows of 64 B), W_hi, W_lo (fp32) and W_hib = bf16(W_hi) (SWIZZLE_64B); A_hi*W_hi and A_hi*W_lo stay on
-// kind::tf32, A_lo*W_hib runs on kind::f16 (two K = 16 steps per k-block instead of four K = 8 steps): 2.5 tensor passes
-// instead of 3, and 6 instead of 8 bytes per activation element on every HBM / L2 / shared-memory hop.
-// LOB = 2 (mode 8, inputs that also carry hib = bf16(hi)): BOTH cross terms on kind::f16 -- A_hib * W_lob and
-// A_lob * W_hib -- 2 tensor passes instead of 3; the stage holds A_hi (fp32), A_hib, A_lob (bf16), W_hi (fp32), W_hib,
-// W_lob (bf16): the same bytes as LOB = 1.
-// LOB = 3 (mode 9, the fp16 generation): every operand is an fp16 array in SWIZZLE_64B tiles -- A_hi16, A_lo16 (= (x - hi) * 2048),
-// W_hi16, W_lo16 and W_hs16 = W_hi16 / 2048 of the row-scaled weights (common.cuh: split_f16) -- and all three products
-// A_hi*W_hi + A_hi*W_lo + A_lo*W_hs run on kind::f16: 6 MMAs of K = 16 per k-block instead of 8 of K = 8 plus 2 of K = 16
-// (3 tensor passes at the 16-bit rate instead of 5 pass units), and the stage shrinks from 64 KB to 40 KB.
-template <int BNP, int LOB = 0>
+// LOB = 1 (mode 7, TF32 generation): the stage holds A_hi (fp32, SWIZZLE_128B, 16 KB), A_lo (bf16, SWIZZLE_64B rows of 64 B,
+// 8 KB), W_hi, W_lo (fp32) and W_hib = bf16(W_hi) (SWIZZLE_64B); A_hi*W_hi and A_hi*W_lo run on kind::tf32 (four K = 8 steps per
+// k-block each), A_lo*W_hib on kind::f16 (two K = 16 steps): 5 bf16-rate pass units per MAC, 6 bytes per activation element.
+// LOB = 3 (mode 9, the fp16 generation, default): every operand is an fp16 array in SWIZZLE_64B tiles -- A_hi16, A_lo16
+// (= (x - hi) * 2048), W_hi16, W_lo16 and W_hs16 = W_hi16 / 2048 of the row-scaled weights (common.cuh: split_f16) -- and all
+// three products A_hi*W_hi + A_hi*W_lo + A_lo*W_hs run on kind::f16: 6 MMAs of K = 16 per k-block (3 tensor passes at the
+// 16-bit rate), and the stage shrinks from 64 KB to 40 KB.
+template <int BNP, int LOB>
 struct Cfg {
+  static_assert(LOB == 1 || LOB == 3, "LOB");
   static constexpr int WB = BNP / 2;                                 // weight rows staged by each CTA
-  static constexpr int A_BYTES = kBM * kBK * 4;                      // 16 KB
+  static constexpr int A_BYTES = kBM * kBK * 4;                      // 16 KB (fp32 tile)
   static constexpr int W_BYTES = WB * kBK * 4;
-  // LOB 0: [A_hi | A_lo | W_hi | W_lo]   LOB 1: [A_hi | A_lob | W_hi | W_lo | W_hib]   LOB 2: [A_hi | A_lob | A_hib | W_hi | W_hib | W_lob]
-  // LOB 3: [A_hi16 | A_lo16 | W_hi16 | W_lo16 | W_hs16]
+  // LOB 1: [A_hi | A_lob | W_hi | W_lo | W_hib]      LOB 3: [A_hi16 | A_lo16 | W_hi16 | W_lo16 | W_hs16]
   static constexpr int OFF_ALO = LOB == 3 ? A_BYTES / 2 : A_BYTES;
-  static constexpr int OFF_AHB = OFF_ALO + (LOB ? A_BYTES / 2 : A_BYTES);              // LOB 2 only
-  static constexpr int OFF_WHI = OFF_AHB + (LOB == 2 ? A_BYTES / 2 : 0);
-  static constexpr int OFF_WLO = OFF_WHI + (LOB == 3 ? W_BYTES / 2 : W_BYTES);          // fp32 W_lo (LOB 0, 1), W_lo16 (LOB 3)
-  static constexpr int OFF_WHB = OFF_WLO + (LOB == 2 ? 0 : LOB == 3 ? W_BYTES / 2 : W_BYTES);   // bf16(W_hi) (LOB 1, 2), W_hs16 (LOB 3)
-  static constexpr int OFF_WLB = OFF_WHB + (LOB ? W_BYTES / 2 : 0);                     // bf16(W_lo) (LOB 2)
-  static constexpr int STAGE = OFF_WLB + (LOB == 2 ? W_BYTES / 2 : 0);                  // per CTA
+  static constexpr int OFF_WHI = OFF_ALO + A_BYTES / 2;
+  static constexpr int OFF_WLO = OFF_WHI + (LOB == 3 ? W_BYTES / 2 : W_BYTES);          // fp32 W_lo (LOB 1), W_lo16 (LOB 3)
+  static constexpr int OFF_W3 = OFF_WLO + (LOB == 3 ? W_BYTES / 2 : W_BYTES);           // bf16(W_hi) (LOB 1), W_hs16 (LOB 3)
+  static constexpr int STAGE = OFF_W3 + W_BYTES / 2;                                    // per CTA
   static constexpr int PC = 16;
   static constexpr int STG_WARP = 32 * PC * 4;
   static constexpr int STG = kEpiWarps * STG_WARP;
@@ -83,13 +77,12 @@ struct Cfg {
   static constexpr int STAGES_RAW = (kSmemMax - 1024 - STG - BAR_BYTES) / STAGE;
   static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
   static constexpr int SMEM = 1024 + STAGES * STAGE + STG + BAR_BYTES;
-  static constexpr int TMEM_COLS = 2 * BNP < 32 ? 32 : 2 * BNP;
+  static constexpr int TMEM_COLS = 2 * BNP;
   static constexpr int HALF = BNP / (kEpiWarps / 4);                 // accumulator columns per epilogue thread
   static_assert(BNP == 64 || BNP == 128 || BNP == 256, "BNP");
-  static_assert(BNP >= 128 || LOB, "64-column pair tiles only exist in the bf16-lo generations");
   static_assert(STAGES >= 3, "ring too shallow");
-  static_assert(STAGE % 1024 == 0 && OFF_WHI % 1024 == 0 && OFF_WLO % (LOB == 3 ? 512 : 1024) == 0 && OFF_WHB % 512 == 0 &&
-                    OFF_WLB % 512 == 0 && OFF_AHB % 1024 == 0 && OFF_ALO % 512 == 0, "operand alignment");
+  static_assert(STAGE % 1024 == 0 && OFF_WHI % 1024 == 0 && OFF_WLO % 512 == 0 && OFF_W3 % 512 == 0 && OFF_ALO % 512 == 0,
+                "operand alignment");
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -167,12 +160,11 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
                ::"r"(tc::smem_u32(bar)), "h"(mask) : "memory");
 }
 
-template <int BNP, int LOB = 0>
+template <int BNP, int LOB>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 tcp_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                 const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
-                const __grid_constant__ CUtensorMap tmW_hib, const __grid_constant__ CUtensorMap tmA_hib,
-                const __grid_constant__ CUtensorMap tmW_lob, int K, const Epilogue ep, const Sched sc) {
+                const __grid_constant__ CUtensorMap tmW_3, int K, const Epilogue ep, const Sched sc) {
   using C = Cfg<BNP, LOB>;
   constexpr int STAGES = C::STAGES;
   constexpr int STAGE = C::STAGE;
@@ -197,8 +189,7 @@ tcp_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
 
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmA_hi); tc::prefetch_tmap(&tmA_lo); tc::prefetch_tmap(&tmW_hi); tc::prefetch_tmap(&tmW_lo);
-    if (LOB) tc::prefetch_tmap(&tmW_hib);
-    if (LOB == 2) { tc::prefetch_tmap(&tmA_hib); tc::prefetch_tmap(&tmW_lob); }
+    tc::prefetch_tmap(&tmW_3);
     for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < 2; ++s) {
       tc::mbar_init(&acc_full[s], 1);
@@ -258,14 +249,10 @@ tcp_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
             const uint32_t fb = full_leader + 8u * s;
             const int kx = tc2::kblock_order(sc, kb) * kBK;
             tma_load_3d_pair(st, &tmA_hi, fb, kx, m0, b);
-            tma_load_3d_pair(st + C::OFF_ALO, &tmA_lo, fb, kx, m0, b);          // bf16 map in the LOB generation
+            tma_load_3d_pair(st + C::OFF_ALO, &tmA_lo, fb, kx, m0, b);
             tma_load_2d_pair(st + C::OFF_WHI, &tmW_hi, fb, kx, wrow);
-            if (LOB != 2) tma_load_2d_pair(st + C::OFF_WLO, &tmW_lo, fb, kx, wrow);
-            if (LOB) tma_load_2d_pair(st + C::OFF_WHB, &tmW_hib, fb, kx, wrow);
-            if (LOB == 2) {
-              tma_load_3d_pair(st + C::OFF_AHB, &tmA_hib, fb, kx, m0, b);
-              tma_load_2d_pair(st + C::OFF_WLB, &tmW_lob, fb, kx, wrow);
-            }
+            tma_load_2d_pair(st + C::OFF_WLO, &tmW_lo, fb, kx, wrow);
+            tma_load_2d_pair(st + C::OFF_W3, &tmW_3, fb, kx, wrow);
           }
         }
       }
@@ -292,35 +279,27 @@ tcp_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
             if (lane == 0) TCP_MARK(2, kbc + 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t d_ahi = tc::desc_lo(smem_base_u32 + s * STAGE);
-            constexpr uint32_t kAlo = C::OFF_ALO >> 4, kWhi = C::OFF_WHI >> 4, kWlo = C::OFF_WLO >> 4, kWhb = C::OFF_WHB >> 4;
-            constexpr uint32_t kAhb = C::OFF_AHB >> 4, kWlb = C::OFF_WLB >> 4;
+            constexpr uint32_t kAlo = C::OFF_ALO >> 4, kWhi = C::OFF_WHI >> 4, kWlo = C::OFF_WLO >> 4, kW3 = C::OFF_W3 >> 4;
             const bool first_in_chunk = kb == c * ckb;
-            if (LOB == 3) {
-              if (tc::elect_one()) {
+            if (tc::elect_one()) {
+              if (LOB == 3) {
                 constexpr uint32_t idesc_h = make_idesc_f16(2 * kBM, BNP);
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {   // 32 fp16 = two K = 16 steps of 32 B
                   umma_bf16_pair(tmem_acc, d_ahi + 2 * k, d_ahi + kWhi + 2 * k, idesc_h, !(first_in_chunk && k == 0));
                   umma_bf16_pair(tmem_acc, d_ahi + 2 * k, d_ahi + kWlo + 2 * k, idesc_h, 1u);
-                  umma_bf16_pair(tmem_acc, d_ahi + kAlo + 2 * k, d_ahi + kWhb + 2 * k, idesc_h, 1u);
+                  umma_bf16_pair(tmem_acc, d_ahi + kAlo + 2 * k, d_ahi + kW3 + 2 * k, idesc_h, 1u);
                 }
-                umma_commit_pair(&empty_bar[s]);
-                if (kb + 1 == kb_end) umma_commit_pair(&acc_full[buf]);
-              }
-            } else if (tc::elect_one()) {
+              } else {
 #pragma unroll
-              for (int k = 0; k < kBK / kUmmaK; ++k) {
-                umma_tf32_pair(tmem_acc, d_ahi + 2 * k, d_ahi + kWhi + 2 * k, idesc, !(first_in_chunk && k == 0));
-                if (LOB != 2) umma_tf32_pair(tmem_acc, d_ahi + 2 * k, d_ahi + kWlo + 2 * k, idesc, 1u);
-                if (!LOB) umma_tf32_pair(tmem_acc, d_ahi + kAlo + 2 * k, d_ahi + kWhi + 2 * k, idesc, 1u);
-              }
-              if (LOB) {
+                for (int k = 0; k < kBK / kUmmaK; ++k) {
+                  umma_tf32_pair(tmem_acc, d_ahi + 2 * k, d_ahi + kWhi + 2 * k, idesc, !(first_in_chunk && k == 0));
+                  umma_tf32_pair(tmem_acc, d_ahi + 2 * k, d_ahi + kWlo + 2 * k, idesc, 1u);
+                }
                 constexpr uint32_t idesc_b = make_idesc_bf16(2 * kBM, BNP);
 #pragma unroll
-                for (int k = 0; k < 2; ++k) {   // 32 bf16 = two K = 16 steps of 32 B
-                  umma_bf16_pair(tmem_acc, d_ahi + kAlo + 2 * k, d_ahi + kWhb + 2 * k, idesc_b, 1u);
-                  if (LOB == 2) umma_bf16_pair(tmem_acc, d_ahi + kAhb + 2 * k, d_ahi + kWlb + 2 * k, idesc_b, 1u);
-                }
+                for (int k = 0; k < 2; ++k)     // 32 bf16 = two K = 16 steps of 32 B
+                  umma_bf16_pair(tmem_acc, d_ahi + kAlo + 2 * k, d_ahi + kW3 + 2 * k, idesc_b, 1u);
               }
               umma_commit_pair(&empty_bar[s]);
               if (kb + 1 == kb_end) umma_commit_pair(&acc_full[buf]);

@@ -1,6 +1,6 @@
-// Host side of the tensor-core path (included by mimi_b200.cu after the handle definition): TMA tensor
-// maps, TF32 hi/lo weight packs, the split-buffer workspace plan and the encode pipeline that runs the wide
-// layers on tcgen05 (tc_gemm.cuh) and the narrow / non-GEMM ones on the SIMT kernels.
+// Host side of the tensor-core generations (included by mimi_b200.cu after the handle definition): TMA tensor maps, the
+// split weight packs (TF32 hi/lo + bf16 for mode 7, row-scaled fp16 hi/lo/hs for mode 9), the split-buffer workspace plan and the
+// encode pipeline: fused front end -> CTA-pair tcgen05 GEMM for every other conv / linear -> tcgen05 attention and RVQ.
 
 static int tc_init_driver(mimi_b200* h) {
   if (h->encode_tiled) return MIMI_B200_OK;
@@ -40,24 +40,8 @@ static int tc_make_map_bf16(mimi_b200* h, CUtensorMap* out, const void* base, in
   return MIMI_B200_OK;
 }
 
-// activation "plane" map for tc_gemm3: dims {C, stride, q, item}, element (c, ph, q, b) = row q*stride + ph, channel c of
-// item b (row 0 = first padded row); box {32, 1, box_rows, 1}, SWIZZLE_128B
-static int tc_make_map4(mimi_b200* h, CUtensorMap* out, const float* base, int C, int stride, long long q_rows, int B,
-                        long long item_stride_floats, int box_rows) {
-  const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)stride, (cuuint64_t)std::max<long long>(q_rows, 1), (cuuint64_t)B};
-  const cuuint64_t strides[3] = {(cuuint64_t)C * sizeof(float), (cuuint64_t)stride * C * sizeof(float),
-                                 (cuuint64_t)item_stride_floats * sizeof(float)};
-  cuuint32_t box[4] = {(cuuint32_t)tc::kBK, 1, (cuuint32_t)box_rows, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = h->encode_tiled(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
-                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS)
-    return fail(h, MIMI_B200_ERR_CUDA, "cuTensorMapEncodeTiled (4-D plane map) failed with CUresult " + std::to_string((int)r));
-  return MIMI_B200_OK;
-}
-
-// w_nk: host [N][K] K-major. Splits into TF32 hi/lo, uploads, builds the two weight maps.
+// w_nk: host [N][K] K-major. Mode 7: TF32 hi / lo (fp32) and bf16(hi), uploaded with one map per box height (128, 64, 32
+// rows: the pair GEMM stages bnp / 2 weight rows per CTA); map_hi / map_lo (box BN) serve the fused front end.
 static int tc_make_weight(mimi_b200* h, TcWeight* w, const std::vector<float>& w_nk, int N, int K) {
   std::vector<float> hi(w_nk.size()), lo(w_nk.size());
   for (size_t i = 0; i < w_nk.size(); ++i) split_tf32(w_nk[i], hi[i], lo[i]);
@@ -67,14 +51,12 @@ static int tc_make_weight(mimi_b200* h, TcWeight* w, const std::vector<float>& w
   w->N = N; w->K = K; w->BN = (N % 128 == 0) ? 128 : (N % 64 == 0) ? 64 : 32;
   const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
   const cuuint64_t strides[1] = {(cuuint64_t)K * sizeof(float)};
+  const cuuint64_t strides_b[1] = {(cuuint64_t)K * 2};
   if ((rc = tc_make_map(h, &w->map_hi, w->hi, 2, dims, strides, w->BN))) return rc;
   if ((rc = tc_make_map(h, &w->map_lo, w->lo, 2, dims, strides, w->BN))) return rc;
-  if (N % 64 == 0) {   // tc_gemm3 has no BN = 32 instance: an extra 64-row box for it
-    if ((rc = tc_make_map(h, &w->map64_hi, w->hi, 2, dims, strides, 64))) return rc;
-    if ((rc = tc_make_map(h, &w->map64_lo, w->lo, 2, dims, strides, 64))) return rc;
-  }
+  const int rows[3] = {128, 64, 32};
   {
-    // bf16-lo generation: bf16(W_hi) (round to nearest even; W_hi has 11 significant bits, bf16 keeps 8)
+    // bf16(W_hi), round to nearest even (W_hi has 11 significant bits, bf16 keeps 8): the B operand of the A_lo * W_hi term
     std::vector<uint16_t> hb(hi.size());
     for (size_t i = 0; i < hi.size(); ++i) {
       uint32_t u;
@@ -85,25 +67,12 @@ static int tc_make_weight(mimi_b200* h, TcWeight* w, const std::vector<float>& w
     CUDA_TRY(h, cudaMalloc((void**)&w->hib, hb.size() * sizeof(uint16_t)));
     h->allocs.push_back(w->hib);
     CUDA_TRY(h, cudaMemcpy(w->hib, hb.data(), hb.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
-    const cuuint64_t strides_b[1] = {(cuuint64_t)K * 2};
-    if ((rc = tc_make_map_bf16(h, &w->map_hib, w->hib, 2, dims, strides_b, w->BN))) return rc;
-    if (N % 64 == 0 && (rc = tc_make_map_bf16(h, &w->map64_hib, w->hib, 2, dims, strides_b, 64))) return rc;
-    if ((rc = tc_make_map_bf16(h, &w->map32_hib, w->hib, 2, dims, strides_b, 32))) return rc;
-    if ((rc = tc_make_map(h, &w->map32_hi, w->hi, 2, dims, strides, 32))) return rc;
-    if ((rc = tc_make_map(h, &w->map32_lo, w->lo, 2, dims, strides, 32))) return rc;
-    // mode 8: bf16(W_lo)
-    for (size_t i = 0; i < lo.size(); ++i) {
-      uint32_t u;
-      memcpy(&u, &lo[i], 4);
-      u += 0x7FFFu + ((u >> 16) & 1u);
-      hb[i] = (uint16_t)(u >> 16);
+    for (int r = 0; r < 3; ++r) {
+      if (rows[r] > N) continue;
+      if ((rc = tc_make_map(h, &w->m_hi[r], w->hi, 2, dims, strides, rows[r]))) return rc;
+      if ((rc = tc_make_map(h, &w->m_lo[r], w->lo, 2, dims, strides, rows[r]))) return rc;
+      if ((rc = tc_make_map_bf16(h, &w->m_hib[r], w->hib, 2, dims, strides_b, rows[r]))) return rc;
     }
-    CUDA_TRY(h, cudaMalloc((void**)&w->lob, hb.size() * sizeof(uint16_t)));
-    h->allocs.push_back(w->lob);
-    CUDA_TRY(h, cudaMemcpy(w->lob, hb.data(), hb.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
-    if ((rc = tc_make_map_bf16(h, &w->map_lob, w->lob, 2, dims, strides_b, w->BN))) return rc;
-    if (N % 64 == 0 && (rc = tc_make_map_bf16(h, &w->map64_lob, w->lob, 2, dims, strides_b, 64))) return rc;
-    if ((rc = tc_make_map_bf16(h, &w->map32_lob, w->lob, 2, dims, strides_b, 32))) return rc;
   }
   {
     // fp16 generation (mode 9): per-row power-of-two scaling, then W' = h16 + l16 with s16 = h16 / 2048
@@ -133,8 +102,6 @@ static int tc_make_weight(mimi_b200* h, TcWeight* w, const std::vector<float>& w
     h->allocs.push_back(w->f16);
     CUDA_TRY(h, cudaMemcpy(w->f16, f.data(), f.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
     if ((rc = dev_upload(h, &w->wscale, ws))) return rc;
-    const cuuint64_t strides_b[1] = {(cuuint64_t)K * 2};
-    const int rows[3] = {128, 64, 32};
     for (int part = 0; part < 3; ++part)
       for (int r = 0; r < 3; ++r) {
         if (rows[r] > N) continue;
@@ -179,11 +146,10 @@ static int tc_load_weights(mimi_b200* h, const mimi_b200_weights_t* w) {
   return MIMI_B200_OK;
 }
 
-// `level0` = also lay out the level-0 buffers the unfused modes (1, 2) need; the default path keeps the 24 kHz
-// activations on chip, which saves 27.6 MB of workspace per audio-second
-// `lob` = the lo arrays are bf16 (mode 7): half the bytes
-// `f16` = both arrays of every split buffer are fp16 (mode 9): 4 bytes per element
-static PlanTC make_plan_tc(int B, long long N, int K, bool level0, bool lob = false, bool hibf = false, bool f16 = false) {
+// Workspace plan of the tensor-core generations: raw fp32 buffers where a skip or a non-GEMM consumer needs them, and a
+// hi / lo pair (with zero halo rows where a conv pads) for every GEMM operand. Mode 7: hi fp32 (TF32-rounded) + lo bf16,
+// 6 bytes per element; `f16` (mode 9): hi and lo both fp16, 4 bytes per element. The 24 kHz level stays on chip (front end).
+static PlanTC make_plan_tc(int B, long long N, int K, bool f16) {
   PlanTC p;
   p.B = B; p.K = K; p.N = N;
   long long L = N;
@@ -196,17 +162,11 @@ static PlanTC make_plan_tc(int B, long long N, int K, bool level0, bool lob = fa
     SplitBuf s;
     s.level = level; s.C = C; s.front = front; s.back = back;
     s.item_stride = (long long)(front + p.rows[level] + back) * C;
-    s.hi = take(f16 ? ((long long)B * s.item_stride + 64 + 1) / 2 : (long long)B * s.item_stride + 64);
-    s.lo = take(lob || f16 ? ((long long)B * s.item_stride + 64 + 1) / 2 : (long long)B * s.item_stride + 64);
-    // mode 8: the tensor-bound layers (levels >= 2) also get bf16(hi); the HBM-bound level-0/1 edges stay at 6 bytes
-    s.hib = (hibf && level >= 2) ? take(((long long)B * s.item_stride + 64 + 1) / 2) : -1;
+    const long long n = (long long)B * s.item_stride + 64;
+    s.hi = take(f16 ? (n + 1) / 2 : n);
+    s.lo = take((n + 1) / 2);
     return s;
   };
-  p.a0 = p.r1 = 0;
-  if (level0) {
-    p.a0 = raw(0, 64);   p.r1 = raw(0, 32);
-    p.s_a0 = split(0, 64, kHalo, 0);  p.s_r1 = split(0, 32, 0, 0);
-  }
   p.s_h1 = split(0, 64, kHalo, kHalo);
   p.d1 = raw(1, 128);  p.s_d1 = split(1, 128, kHalo, kHalo);  p.s_r2 = split(1, 64, 0, 0);  p.s_h2 = split(1, 128, kHalo, kHalo);
   p.d2 = raw(2, 256);  p.s_d2 = split(2, 256, kHalo, kHalo);  p.s_r3 = split(2, 128, 0, 0); p.s_h3 = split(2, 256, kHalo, kHalo);
@@ -234,57 +194,14 @@ struct TcCtx {
   const int* maxlen;          // [6]
   std::vector<CUtensorMap>* maps;   // 2 maps (hi, lo) per GEMM site, indexed by a fixed slot id
   uint64_t* built;                  // bit `slot` set once that site's maps are encoded
-  std::vector<CUtensorMap>* mapsb;  // mode 8: one bf16(hi) map per GEMM site
-  std::vector<CUtensorMap>* maps3;  // 4 plane maps per GEMM site (tc_gemm3)
-  uint64_t* built3;
 };
 constexpr int kTcSlots = 24;          // GEMM sites; slots [kTcSlots, 2*kTcSlots) hold the flattened-rows maps
 }  // namespace
 
-// third-generation kernel: 256-row tiles, plane-staged activations (4 maps per site: hi/lo x first/second box)
-static int launch_tc3(mimi_b200* h, const CUtensorMap* m4, const TcWeight& w, const tc::Epilogue& ep, int B, int lout_max,
-                      int C, int k, int s, cudaStream_t st) {
-  tc3::Geom gm{};
-  gm.G = k / s; gm.s = s; gm.cpanels = C / 32; gm.B = B; gm.mt_max = (lout_max + tc3::kBM - 1) / tc3::kBM;
-  const int bn = (w.N % 128 == 0) ? 128 : 64;
-  gm.ntn = w.N / bn; gm.chunk_kb = h->exp_chunk_kb;
-  const long long vt = (long long)gm.mt_max * B * gm.ntn;
-  const int grid = (int)std::min<long long>(vt, h->num_sms);
-  if (grid <= 0) return MIMI_B200_OK;
-  if (k % s || C % 32 || gm.G > 3) return fail(h, MIMI_B200_ERR_ARG, "tc3: unsupported conv geometry");
-  const CUtensorMap& wh = (bn == w.BN) ? w.map_hi : w.map64_hi;
-  const CUtensorMap& wl = (bn == w.BN) ? w.map_lo : w.map64_lo;
-  if (bn == 128)
-    tc3::tc3_gemm_kernel<128><<<grid, tc3::kThreads, tc3::Cfg<128>::SMEM, st>>>(m4[0], m4[1], m4[2], m4[3], wh, wl, ep, gm);
-  else
-    tc3::tc3_gemm_kernel<64><<<grid, tc3::kThreads, tc3::Cfg<64>::SMEM, st>>>(m4[0], m4[1], m4[2], m4[3], wh, wl, ep, gm);
-  return MIMI_B200_OK;
-}
-
-// plane maps of a conv/linear that reads SplitBuf `a` (kernel k, stride s, left pad `pad`): [hi box1, lo box1, hi box2, lo box2]
-static int tc_amaps3(TcCtx& c, int slot, const SplitBuf& a, int k, int s, int pad, const CUtensorMap** out4) {
-  CUtensorMap* m = &(*c.maps3)[4 * slot];
-  if (!((*c.built3 >> slot) & 1ull)) {
-    const PlanTC& p = *c.p;
-    const int G = k / s;
-    const long long rows_out = (p.rows[a.level] + s - 1) / s;
-    if (a.front < pad) return fail(c.h, MIMI_B200_ERR_ARG, "tc: halo smaller than conv padding");
-    const long long base_off = (long long)(a.front - pad) * a.C;
-    int rc;
-    for (int i = 0; i < 4; ++i) {
-      const float* base = c.ws + ((i & 1) ? a.lo : a.hi) + base_off;
-      if ((rc = tc_make_map4(c.h, &m[i], base, a.C, s, rows_out + G - 1, c.B, a.item_stride, (i < 2) ? 128 : 128 + G - 1))) return rc;
-    }
-    *c.built3 |= 1ull << slot;
-  }
-  *out4 = m;
-  return MIMI_B200_OK;
-}
-
 // activation maps for a conv/linear that reads SplitBuf `a` with kernel k, stride s, left pad `pad`. `flat`: the
 // items' rows are one contiguous [B * rows][C] matrix (k = 1, no halo) seen as a single item.
 static int tc_amaps(TcCtx& c, int slot, const SplitBuf& a, int k, int s, int pad, bool flat, const CUtensorMap** hi,
-                    const CUtensorMap** lo, const CUtensorMap** hib = nullptr) {
+                    const CUtensorMap** lo) {
   if (flat) slot += kTcSlots;
   CUtensorMap* mh = &(*c.maps)[2 * slot];
   CUtensorMap* ml = mh + 1;
@@ -295,26 +212,18 @@ static int tc_amaps(TcCtx& c, int slot, const SplitBuf& a, int k, int s, int pad
                                 (cuuint64_t)(flat ? 1 : c.B)};
     const cuuint64_t strides[2] = {(cuuint64_t)s * a.C * sizeof(float),
                                    (cuuint64_t)a.item_stride * (flat ? c.B : 1) * sizeof(float)};
+    const cuuint64_t strides_h[2] = {strides[0] / 2, strides[1] / 2};     // 16-bit arrays with the element indexing of hi
     const long long base_off = (long long)(a.front - pad) * a.C;
     if (a.front < pad) return fail(c.h, MIMI_B200_ERR_ARG, "tc: halo smaller than conv padding");
     int rc;
-    if (c.h->mode == 9) {   // hi is an fp16 array too
-      const cuuint64_t strides_h[2] = {strides[0] / 2, strides[1] / 2};
+    if (c.h->mode == 9) {
       if ((rc = tc_make_map_bf16(c.h, mh, reinterpret_cast<const uint16_t*>(c.ws + a.hi) + base_off, 3, dims, strides_h, tc::kBM))) return rc;
     } else if ((rc = tc_make_map(c.h, mh, c.ws + a.hi + base_off, 3, dims, strides, tc::kBM))) return rc;
-    if (c.h->mode >= 7) {   // lo is a bf16 (mode 9: fp16) array with the element indexing of hi
-      const cuuint64_t strides_b[2] = {strides[0] / 2, strides[1] / 2};
-      if ((rc = tc_make_map_bf16(c.h, ml, reinterpret_cast<const uint16_t*>(c.ws + a.lo) + base_off, 3, dims, strides_b, tc::kBM))) return rc;
-    } else if ((rc = tc_make_map(c.h, ml, c.ws + a.lo + base_off, 3, dims, strides, tc::kBM))) return rc;
-    if (a.hib >= 0) {
-      const cuuint64_t strides_b[2] = {strides[0] / 2, strides[1] / 2};
-      if ((rc = tc_make_map_bf16(c.h, &(*c.mapsb)[slot], reinterpret_cast<const uint16_t*>(c.ws + a.hib) + base_off, 3, dims, strides_b, tc::kBM))) return rc;
-    }
+    if ((rc = tc_make_map_bf16(c.h, ml, reinterpret_cast<const uint16_t*>(c.ws + a.lo) + base_off, 3, dims, strides_h, tc::kBM))) return rc;
     *c.built |= 1ull << slot;
   }
   *hi = mh;
   *lo = ml;
-  if (hib) *hib = a.hib >= 0 ? &(*c.mapsb)[slot] : nullptr;
   return MIMI_B200_OK;
 }
 
@@ -327,8 +236,6 @@ struct TcOut {
   const float* bias = nullptr;
   const float* scale = nullptr;
   int act = 0;
-  int raw_in = 0;                  // 1: the input buffer's `hi` array holds RAW fp32 (pre-ELU); the GEMM applies ELU and the
-                                   // hi/lo split itself in shared memory (tc_gemm4.cuh) -- half the HBM bytes on that edge
 };
 
 // k-block order of a conv with k taps, stride s over C_in channels (tc2::Sched): taps grouped by tau mod s
@@ -338,92 +245,50 @@ static void tc_korder(const mimi_b200* h, tc2::Sched& sc, int k, int s, int cin)
   sc.G = k / s + (h->exp_linear_k == 2 ? 16 : 0); sc.s = s; sc.cp = cin / 32;
 }
 
-// persistent second-generation kernel: one CTA per SM over mt_max * B * (N / BN) virtual tiles
-static void launch_tc2(mimi_b200* h, const CUtensorMap& ahi, const CUtensorMap& alo, const TcWeight& w, const tc::Epilogue& ep,
-                       int B, int mt_max, cudaStream_t st, int k = 1, int s = 1, int cin = 0, const int* tiles = nullptr,
-                       int ntiles = 0) {
-  tc2::Sched sc{B, mt_max, w.N / w.BN};
-  tc_korder(h, sc, k, s, cin);
-  sc.tiles = tiles; sc.ntiles = ntiles;
-  const long long vt = (tiles ? (long long)ntiles : (long long)mt_max * B) * sc.ntn;
-  const int grid = (int)std::min<long long>(vt, h->num_sms);
-  if (grid <= 0) return;
-  if (w.BN == 128)
-    tc2::tc2_gemm_kernel<128><<<grid, tc2::threads(128), tc2::Cfg<128>::SMEM, st>>>(ahi, alo, w.map_hi, w.map_lo, w.K, ep, sc);
-  else if (w.BN == 64)
-    tc2::tc2_gemm_kernel<64><<<grid, tc2::threads(64), tc2::Cfg<64>::SMEM, st>>>(ahi, alo, w.map_hi, w.map_lo, w.K, ep, sc);
-  else
-    tc2::tc2_gemm_kernel<32><<<grid, tc2::threads(32), tc2::Cfg<32>::SMEM, st>>>(ahi, alo, w.map_hi, w.map_lo, w.K, ep, sc);
-}
-
-// fifth-generation kernel: CTA pairs (cta_group::2), pair tiles of 2 x 128 rows x BNP columns
-static bool tcp_applies(const mimi_b200* h, const TcWeight& w) {
-  return (h->mode == 6 && w.N % 128 == 0 && w.BN == 128) || (h->mode >= 7 && w.N % 64 == 0);
-}
-static void launch_tcp(mimi_b200* h, const CUtensorMap& ahi, const CUtensorMap& alo, const TcWeight& w, const tc::Epilogue& ep,
-                       int B, int mt_max, cudaStream_t st, int k = 1, int s = 1, int cin = 0, const int* tiles = nullptr,
-                       int ntiles = 0, const CUtensorMap* ahib = nullptr) {
+// the CTA-pair GEMM (tc_gemm5.cuh): pair tiles of 2 x 128 rows x BNP columns. Every layer of the network has N % 64 == 0.
+static int launch_tcp(mimi_b200* h, const CUtensorMap& ahi, const CUtensorMap& alo, const TcWeight& w, const tc::Epilogue& ep,
+                      int B, int mt_max, cudaStream_t st, int k = 1, int s = 1, int cin = 0, const int* tiles = nullptr,
+                      int ntiles = 0) {
+  if (w.N % 64) return fail(h, MIMI_B200_ERR_ARG, "tc: the pair GEMM needs N % 64 == 0");
   // 256-column pair tiles unless the layer is so deep (K) and narrow in rows that a tile is a large share of a cluster's
   // whole job: exp_pair_n128 = N threshold from which 128-column tiles are used (0 = never)
-  const int bnp = (w.N % 256 == 0 && !(h->exp_pair_n128 > 0 && w.N >= h->exp_pair_n128)) ? 256
-                  : (w.N % 128 == 0)                                                       ? 128
-                                                                                           : 64;    // mode 7 only
+  const int bnp = (w.N % 256 == 0 && !(h->exp_pair_n128 > 0 && w.N >= h->exp_pair_n128)) ? 256 : (w.N % 128 == 0) ? 128 : 64;
   tcp::Sched sc{B, mt_max, w.N / bnp};
   tc_korder(h, sc, k, s, cin);
   sc.tiles = tiles; sc.ntiles = ntiles;
   const long long npairs = (((tiles ? (long long)ntiles : (long long)mt_max * B) + 1) / 2) * sc.ntn;
   const int ncl = (int)std::min<long long>(npairs, h->num_clusters);
-  if (ncl <= 0) return;
+  if (ncl <= 0) return MIMI_B200_OK;
+  const int r = bnp == 256 ? 0 : bnp == 128 ? 1 : 2;            // weight boxes of bnp / 2 rows
   if (h->mode == 9) {
-    // fp16 generation: all five operand tiles are 16-bit SWIZZLE_64B boxes; weight boxes of bnp / 2 rows
-    const int r = bnp == 256 ? 0 : bnp == 128 ? 1 : 2;
+    // fp16 generation: all five operand tiles are 16-bit SWIZZLE_64B boxes
     const CUtensorMap &whi = w.map_f16[0][r], &wlo = w.map_f16[1][r], &whs = w.map_f16[2][r];
-    if (bnp == 256) tcp::tcp_gemm_kernel<256, 3><<<2 * ncl, tcp::kThreads, tcp::Cfg<256, 3>::SMEM, st>>>(ahi, alo, whi, wlo, whs, ahi, whs, w.K, ep, sc);
-    else if (bnp == 128) tcp::tcp_gemm_kernel<128, 3><<<2 * ncl, tcp::kThreads, tcp::Cfg<128, 3>::SMEM, st>>>(ahi, alo, whi, wlo, whs, ahi, whs, w.K, ep, sc);
-    else tcp::tcp_gemm_kernel<64, 3><<<2 * ncl, tcp::kThreads, tcp::Cfg<64, 3>::SMEM, st>>>(ahi, alo, whi, wlo, whs, ahi, whs, w.K, ep, sc);
-    return;
+    if (bnp == 256) tcp::tcp_gemm_kernel<256, 3><<<2 * ncl, tcp::kThreads, tcp::Cfg<256, 3>::SMEM, st>>>(ahi, alo, whi, wlo, whs, w.K, ep, sc);
+    else if (bnp == 128) tcp::tcp_gemm_kernel<128, 3><<<2 * ncl, tcp::kThreads, tcp::Cfg<128, 3>::SMEM, st>>>(ahi, alo, whi, wlo, whs, w.K, ep, sc);
+    else tcp::tcp_gemm_kernel<64, 3><<<2 * ncl, tcp::kThreads, tcp::Cfg<64, 3>::SMEM, st>>>(ahi, alo, whi, wlo, whs, w.K, ep, sc);
+  } else {
+    // TF32 generation with bf16 lo parts (mode 7): alo is a bf16 map, the third weight tile is bf16(W_hi)
+    const CUtensorMap &whi = w.m_hi[r], &wlo = w.m_lo[r], &whb = w.m_hib[r];
+    if (bnp == 256) tcp::tcp_gemm_kernel<256, 1><<<2 * ncl, tcp::kThreads, tcp::Cfg<256, 1>::SMEM, st>>>(ahi, alo, whi, wlo, whb, w.K, ep, sc);
+    else if (bnp == 128) tcp::tcp_gemm_kernel<128, 1><<<2 * ncl, tcp::kThreads, tcp::Cfg<128, 1>::SMEM, st>>>(ahi, alo, whi, wlo, whb, w.K, ep, sc);
+    else tcp::tcp_gemm_kernel<64, 1><<<2 * ncl, tcp::kThreads, tcp::Cfg<64, 1>::SMEM, st>>>(ahi, alo, whi, wlo, whb, w.K, ep, sc);
   }
-  if (h->mode >= 7) {
-    // bf16-lo generations: every layer with N % 64 == 0 (alo is a bf16 map); box rows of the weight maps = bnp / 2.
-    // With a bf16(hi) map of the input (mode 8, levels >= 2) both cross terms run on kind::f16 (LOB = 2).
-    const CUtensorMap &whi = bnp == 256 ? w.map_hi : bnp == 128 ? w.map64_hi : w.map32_hi;
-    const CUtensorMap &wlo = bnp == 256 ? w.map_lo : bnp == 128 ? w.map64_lo : w.map32_lo;
-    const CUtensorMap &whb = bnp == 256 ? w.map_hib : bnp == 128 ? w.map64_hib : w.map32_hib;
-    const CUtensorMap &wlb = bnp == 256 ? w.map_lob : bnp == 128 ? w.map64_lob : w.map32_lob;
-    if (ahib) {
-      if (bnp == 256) tcp::tcp_gemm_kernel<256, 2><<<2 * ncl, tcp::kThreads, tcp::Cfg<256, 2>::SMEM, st>>>(ahi, alo, whi, wlo, whb, *ahib, wlb, w.K, ep, sc);
-      else if (bnp == 128) tcp::tcp_gemm_kernel<128, 2><<<2 * ncl, tcp::kThreads, tcp::Cfg<128, 2>::SMEM, st>>>(ahi, alo, whi, wlo, whb, *ahib, wlb, w.K, ep, sc);
-      else tcp::tcp_gemm_kernel<64, 2><<<2 * ncl, tcp::kThreads, tcp::Cfg<64, 2>::SMEM, st>>>(ahi, alo, whi, wlo, whb, *ahib, wlb, w.K, ep, sc);
-    } else {
-      if (bnp == 256) tcp::tcp_gemm_kernel<256, 1><<<2 * ncl, tcp::kThreads, tcp::Cfg<256, 1>::SMEM, st>>>(ahi, alo, whi, wlo, whb, ahi, wlb, w.K, ep, sc);
-      else if (bnp == 128) tcp::tcp_gemm_kernel<128, 1><<<2 * ncl, tcp::kThreads, tcp::Cfg<128, 1>::SMEM, st>>>(ahi, alo, whi, wlo, whb, ahi, wlb, w.K, ep, sc);
-      else tcp::tcp_gemm_kernel<64, 1><<<2 * ncl, tcp::kThreads, tcp::Cfg<64, 1>::SMEM, st>>>(ahi, alo, whi, wlo, whb, ahi, wlb, w.K, ep, sc);
-    }
-    return;
-  }
-  if (bnp == 256)
-    tcp::tcp_gemm_kernel<256><<<2 * ncl, tcp::kThreads, tcp::Cfg<256>::SMEM, st>>>(ahi, alo, w.map_hi, w.map_lo, w.map_hi, ahi, w.map_hi, w.K, ep, sc);
-  else
-    tcp::tcp_gemm_kernel<128><<<2 * ncl, tcp::kThreads, tcp::Cfg<128>::SMEM, st>>>(ahi, alo, w.map64_hi, w.map64_lo, w.map64_hi, ahi, w.map64_hi, w.K, ep, sc);
+  return MIMI_B200_OK;
 }
 
 static int tc_gemm(TcCtx& c, int slot, const SplitBuf& a, int k, int s, int pad, const TcWeight& w, const TcOut& o, int prof_id) {
-  const CUtensorMap *ahi = nullptr, *alo = nullptr, *ahib = nullptr, *m4 = nullptr;
+  const CUtensorMap *ahi = nullptr, *alo = nullptr;
   int rc;
   if (slot < 0 || slot >= kTcSlots) return fail(c.h, MIMI_B200_ERR_ARG, "tc: bad map slot");
-  const bool v3 = c.h->mode == 4;
-  const bool planes = !v3 && c.h->mode >= 2 && c.h->use_planes && s > 0 && k % s == 0 && k / s >= 2 && k / s <= 3 &&
-                      a.C % 32 == 0 && w.N % 64 == 0;
   // Linears (k = 1) over buffers without halo rows: the B items are one contiguous [B * rows][C] matrix. When whole
   // 128-row tiles of that matrix are fewer than the per-item tiles (each item rounds up on its own), run it as ONE item:
-  // rows past an item's length are computed and stored but never read (every consumer is row-wise and length-bound).
+  // rows past an item's length are computed but not stored (every consumer is row-wise and length-bound).
   const int rows_lvl = c.p->rows[a.level];
-  const bool flat = !c.h->exp_no_flat && !v3 && !planes && k == 1 && s == 1 && pad == 0 && a.front == 0 && a.back == 0 &&
+  const bool flat = !c.h->exp_no_flat && k == 1 && s == 1 && pad == 0 && a.front == 0 && a.back == 0 &&
                     c.B > 1 && (!o.raw && !o.res || o.raw_item_stride == (long long)rows_lvl * w.N) &&
                     (!o.split || (o.split->front == 0 && o.split->back == 0 && o.split->level == a.level)) &&
                     ((long long)c.B * rows_lvl + 127) / 128 < c.h->item_tiles[a.level];
-  if (v3 || planes) { if ((rc = tc_amaps3(c, slot, a, k, s, pad, &m4))) return rc; }
-  else if ((rc = tc_amaps(c, slot, a, k, s, pad, flat, &ahi, &alo, &ahib))) return rc;
+  if ((rc = tc_amaps(c, slot, a, k, s, pad, flat, &ahi, &alo))) return rc;
   if (w.K != k * a.C) return fail(c.h, MIMI_B200_ERR_ARG, "tc: weight K mismatch");
   tc::Epilogue ep{};
   ep.bias = o.bias; ep.scale = o.scale; ep.res = o.res; ep.out_raw = o.raw; ep.raw_item_stride = o.raw_item_stride;
@@ -431,12 +296,10 @@ static int tc_gemm(TcCtx& c, int slot, const SplitBuf& a, int k, int s, int pad,
     if (o.split->C != w.N) return fail(c.h, MIMI_B200_ERR_ARG, "tc: split output width mismatch");
     ep.out_hi = c.ws + o.split->hi; ep.out_lo = c.ws + o.split->lo;
     ep.split_item_stride = o.split->item_stride; ep.split_front = o.split->front;
-    ep.out_hib = o.split->hib >= 0 ? c.ws + o.split->hib : nullptr;
   }
-  ep.act = o.act; ep.elu_split = o.elu_split; ep.lo_bf16 = c.h->mode == 9 ? 3 : c.h->mode >= 7;
+  ep.act = o.act; ep.elu_split = o.elu_split; ep.lo_bf16 = c.h->mode == 9 ? 3 : 1;
   ep.wscale = c.h->mode == 9 ? w.wscale : nullptr;
-  ep.single_acc = c.h->exp_single_acc; ep.chunk_kb = c.h->exp_chunk_kb;
-  ep.prefetch_next = c.h->exp_prefetch && w.N / w.BN == 1;      // with several n-tiles the rows are in L2 already
+  ep.chunk_kb = c.h->exp_chunk_kb;
   ep.len_in = c.dlen[a.level]; ep.uniform_len_in = c.maxlen[a.level]; ep.conv_stride = s; ep.N = w.N;
   int lout_max = (c.maxlen[a.level] + s - 1) / s;
   if (lout_max <= 0) return MIMI_B200_OK;
@@ -449,71 +312,7 @@ static int tc_gemm(TcCtx& c, int slot, const SplitBuf& a, int k, int s, int pad,
   const int out_level = a.level + (s > 1 ? 1 : 0);
   const int* tiles = (!flat && out_level < 6) ? c.h->tile_ptr[out_level] : nullptr;
   const int ntiles = tiles ? c.h->tile_cnt[out_level] : 0;
-  if (o.raw_in) {
-    if (flat || planes || v3) return fail(c.h, MIMI_B200_ERR_ARG, "tc: raw input only for the k-block ring kernels");
-    tc2::Sched sc{nb, (lout_max + tc::kBM - 1) / tc::kBM, w.N / w.BN};
-    tc_korder(c.h, sc, k, s, a.C);
-    sc.tiles = tiles; sc.ntiles = ntiles;
-    const long long vt = (tiles ? (long long)ntiles : (long long)sc.mt_max * nb) * sc.ntn;
-    const int grid = (int)std::min<long long>(vt, c.h->num_sms);
-    if (w.BN == 128)
-      tc4::tc4_gemm_kernel<128><<<grid, tc4::kThreads, tc4::Cfg<128>::SMEM, c.st>>>(*ahi, w.map_hi, w.map_lo, w.K, 1, ep, sc);
-    else if (w.BN == 64)
-      tc4::tc4_gemm_kernel<64><<<grid, tc4::kThreads, tc4::Cfg<64>::SMEM, c.st>>>(*ahi, w.map_hi, w.map_lo, w.K, 1, ep, sc);
-    else
-      tc4::tc4_gemm_kernel<32><<<grid, tc4::kThreads, tc4::Cfg<32>::SMEM, c.st>>>(*ahi, w.map_hi, w.map_lo, w.K, 1, ep, sc);
-  } else if (v3) {
-    if ((rc = launch_tc3(c.h, m4, w, ep, nb, lout_max, a.C, k, s, c.st))) return rc;
-  } else if (planes) {
-    tc2::Sched sc{nb, (lout_max + tc::kBM - 1) / tc::kBM, w.N / w.BN};
-    tc2::PlaneGeom gm{k / s, s, a.C / 32};
-    const long long vt = (long long)sc.mt_max * nb * sc.ntn;
-    const int grid = (int)std::min<long long>(vt, c.h->num_sms);
-    if (w.BN == 128)
-      tc2::tc2p_gemm_kernel<128><<<grid, tc2::threads(128), tc2::CfgP<128>::SMEM, c.st>>>(m4[2], m4[3], w.map_hi, w.map_lo, ep, sc, gm);
-    else
-      tc2::tc2p_gemm_kernel<64><<<grid, tc2::threads(64), tc2::CfgP<64>::SMEM, c.st>>>(m4[2], m4[3], w.map_hi, w.map_lo, ep, sc, gm);
-  } else if (tcp_applies(c.h, w)) {
-    launch_tcp(c.h, *ahi, *alo, w, ep, nb, (lout_max + tc::kBM - 1) / tc::kBM, c.st, k, s, a.C, tiles, ntiles, ahib);
-  } else if (c.h->mode >= 2) {
-    launch_tc2(c.h, *ahi, *alo, w, ep, nb, (lout_max + tc::kBM - 1) / tc::kBM, c.st, k, s, a.C, tiles, ntiles);
-  } else {
-    dim3 grid((lout_max + tc::kBM - 1) / tc::kBM, w.N / w.BN, nb);
-    if (w.BN == 128)
-      tc::tc_gemm_kernel<128><<<grid, tc::kThreads, tc::smem_bytes(128), c.st>>>(*ahi, *alo, w.map_hi, w.map_lo, w.K, ep);
-    else if (w.BN == 64)
-      tc::tc_gemm_kernel<64><<<grid, tc::kThreads, tc::smem_bytes(64), c.st>>>(*ahi, *alo, w.map_hi, w.map_lo, w.K, ep);
-    else
-      return fail(c.h, MIMI_B200_ERR_ARG, "tc: mode 1 has no BN=32 kernel");
-  }
-  c.h->launches++;
-  mark(c.h, prof_id, c.st);
-  CUDA_TRY(c.h, cudaGetLastError());
-  return MIMI_B200_OK;
-}
-
-// level-1 residual block fused (tc_gemm6.cuh): conv a (128 -> 64, k3) over split buffer `a`, conv b (64 -> 128, k1) + skip
-static int tc_resblock1(TcCtx& c, int slot, const SplitBuf& a, const TcWeight& wa, const TcWeight& wb, const float* bias_a,
-                        const float* bias_b, const float* res, long long raw_item_stride, const SplitBuf& out, int prof_id) {
-  const CUtensorMap *ahi = nullptr, *alo = nullptr;
-  int rc;
-  if (wa.N != tcr::kNA || wb.N != tcr::kNB || wb.K != tcr::kNA || wa.K != 3 * a.C || out.C != wb.N)
-    return fail(c.h, MIMI_B200_ERR_ARG, "tc: fused residual block geometry");
-  if ((rc = tc_amaps(c, slot, a, 3, 1, 2, false, &ahi, &alo))) return rc;
-  tc::Epilogue ep{};
-  ep.bias = bias_b; ep.res = res; ep.raw_item_stride = raw_item_stride;
-  ep.out_hi = c.ws + out.hi; ep.out_lo = c.ws + out.lo; ep.split_item_stride = out.item_stride; ep.split_front = out.front;
-  ep.elu_split = 1; ep.lo_bf16 = 1;
-  ep.len_in = c.dlen[a.level]; ep.uniform_len_in = c.maxlen[a.level]; ep.conv_stride = 1; ep.N = wb.N;
-  const int lout_max = c.maxlen[a.level];
-  if (lout_max <= 0) return MIMI_B200_OK;
-  tc2::Sched sc{c.B, (lout_max + tc::kBM - 1) / tc::kBM, 1};
-  sc.tiles = c.h->tile_ptr[a.level]; sc.ntiles = sc.tiles ? c.h->tile_cnt[a.level] : 0;
-  const long long npairs = ((sc.tiles ? (long long)sc.ntiles : (long long)sc.mt_max * c.B) + 1) / 2;
-  const int ncl = (int)std::min<long long>(npairs, c.h->num_clusters);
-  if (ncl <= 0) return MIMI_B200_OK;
-  tcr::tcr_resblock_kernel<<<2 * ncl, tcr::kThreads, tcr::kSmem, c.st>>>(*ahi, *alo, wa.map32_hi, wa.map32_lo, wa.map32_hib,
-                                                                        wb.map64_hi, wb.map64_lo, wb.map64_hib, wa.K, bias_a, ep, sc);
+  if ((rc = launch_tcp(c.h, *ahi, *alo, w, ep, nb, (lout_max + tc::kBM - 1) / tc::kBM, c.st, k, s, a.C, tiles, ntiles))) return rc;
   c.h->launches++;
   mark(c.h, prof_id, c.st);
   CUDA_TRY(c.h, cudaGetLastError());
@@ -525,53 +324,40 @@ static int tc_zero_halo(TcCtx& c, const SplitBuf& s) {
   const int per = (s.front + s.back) * s.C;
   dim3 grid((per + 255) / 256, c.B);
   tc::zero_halo_kernel<<<grid, 256, 0, c.st>>>(c.ws + s.hi, c.ws + s.lo, s.item_stride, s.C, s.front, s.back,
-                                               c.dlen[s.level], c.maxlen[s.level], c.h->mode == 9 ? 3 : c.h->mode >= 7,
-                                               s.hib >= 0 ? c.ws + s.hib : nullptr);
+                                               c.dlen[s.level], c.maxlen[s.level], c.h->mode == 9 ? 3 : 1);
   c.h->launches++;
   mark(c.h, 25, c.st);
   return MIMI_B200_OK;
 }
 
-// The encode pipeline with the wide layers on tensor cores. Same contract as the SIMT pipeline.
+// The encode pipeline of the tensor-core generations (modes 7 and 9). Same contract as the fp32 FFMA pipeline in mimi_b200.cu.
 static int encode_tc(mimi_b200* h, const float* d_input, int B, long long N, int K, const PlanTC& p, float* ws,
                      const int* const* dlen, const int* maxlen, const int* dprefix, int total_frames,
                      int64_t* d_codes, float* d_latent_opt, cudaStream_t st) {
   int rc;
-  const MapKey key{ws, B, N, h->mode < 3 ? 1 : h->mode == 7 ? 3 : h->mode == 8 ? 4 : h->mode == 9 ? 5 : 0};   // 2 = the raw-fp32 plan of mode 5 (tc5_host.inl)
+  const int lob = h->mode == 9 ? 3 : 1;            // split format every producer writes (common.cuh: store_split4_x)
+  const MapKey key{ws, B, N, h->mode};             // one set of activation maps per (workspace, shape, generation)
   auto it = h->amap_cache.find(key);
-  TcCtx c{h, &p, ws, B, st, dlen, maxlen, nullptr, nullptr, nullptr, nullptr, nullptr};
+  TcCtx c{h, &p, ws, B, st, dlen, maxlen, nullptr, nullptr};
   if (it == h->amap_cache.end()) {
     if (h->amap_cache.size() >= 64) h->amap_cache.clear();
     it = h->amap_cache.emplace(key, MapSet()).first;
     it->second.maps.resize(4 * kTcSlots);
-    it->second.mapsb.resize(2 * kTcSlots);
-    it->second.maps3.resize(4 * kTcSlots);
   }
   c.maps = &it->second.maps;
   c.built = &it->second.built;
-  c.mapsb = &it->second.mapsb;
-  c.maps3 = &it->second.maps3;
-  c.built3 = &it->second.built3;
   auto rstride = [&](int level, int C) { return (long long)p.rows[level] * C; };
 
   // halo rows of every conv-consumed split buffer (producers only ever write rows [0, L))
   const SplitBuf* halos[] = {&p.s_h1, &p.s_d1, &p.s_h2, &p.s_d2, &p.s_h3, &p.s_d3, &p.s_h4, &p.s_d4};
-  if (h->phase <= MIMI_B200_PHASE_BEGIN) {
+  if (h->phase <= MIMI_B200_PHASE_BEGIN)
     for (const SplitBuf* s : halos)
       if ((rc = tc_zero_halo(c, *s))) return rc;
-    if (h->mode == 2 && (rc = tc_zero_halo(c, p.s_a0))) return rc;
-  }
   if (h->phase == MIMI_B200_PHASE_BEGIN) return MIMI_B200_OK;
 
-  // the 24 kHz activation h1 (64 channels, the largest tensor of the pipeline) crosses HBM once as raw fp32 instead of as
-  // an ELU'd hi/lo pair: the front end stores it raw, the first strided conv splits it in shared memory (tc_gemm4.cuh)
-  const int raw_h1 = h->mode >= 3 && h->mode != 4 && h->mode != 9 && h->exp_raw_h1;
-  // ---- level 0 on CUDA cores: L0 (1->64 k7), R1a (64->32 k3), R1b (32->64 k1 + skip) ---------------------
-  if (h->mode >= 3 && h->phase == MIMI_B200_PHASE_FINISH) {
-    // phased call: the front end already ran, item group by item group (mimi_b200_encode_phase)
-  } else if (h->mode >= 3) {
-    // fused front end: waveform -> L0 -> R1a -> R1b (+skip) -> ELU -> split, 24 kHz activations stay on chip.
-    // Items [b0, b1) only in a phased call (every item is independent here).
+  // ---- fused front end: waveform -> L0 -> R1a -> R1b (+skip) -> ELU -> split; the 24 kHz activations stay on chip ------------
+  // Items [b0, b1) only in a phased call (every item is independent here); PHASE_FINISH finds the front end already done.
+  if (h->phase != MIMI_B200_PHASE_FINISH) {
     const int b0 = h->phase == MIMI_B200_PHASE_FRONT ? h->front_b0 : 0;
     const int nb = (h->phase == MIMI_B200_PHASE_FRONT ? h->front_b1 : B) - b0;
     if (maxlen[0] > 0 && nb > 0) {
@@ -579,11 +365,11 @@ static int encode_tc(mimi_b200* h, const float* d_input, int B, long long N, int
       fp.x = d_input + (long long)b0 * N; fp.x_stride = N; fp.len = dlen[0] ? dlen[0] + b0 : nullptr; fp.uniform_len = maxlen[0];
       fp.B = nb;
       fp.mt_max = (maxlen[0] + f0::kAdv - 1) / f0::kAdv;
-      // (the lo array is bf16 in modes >= 7: the same ELEMENT offset is half as many floats)
+      // (16-bit arrays: the same ELEMENT offset is half as many floats)
       fp.out_hi = ws + p.s_h1.hi + (long long)b0 * p.s_h1.item_stride / (h->mode == 9 ? 2 : 1);
-      fp.out_lo = ws + p.s_h1.lo + (long long)b0 * p.s_h1.item_stride / (h->mode >= 7 ? 2 : 1);
+      fp.out_lo = ws + p.s_h1.lo + (long long)b0 * p.s_h1.item_stride / 2;
       fp.split_item_stride = p.s_h1.item_stride; fp.split_front = p.s_h1.front;
-      fp.raw_out = raw_h1; fp.lo_bf16 = h->mode == 9 ? 3 : h->mode >= 7;
+      fp.lo_bf16 = lob;
       const long long vt = (long long)fp.mt_max * nb;
       const int grid = (int)std::min<long long>(vt, h->num_sms);
       f0::front_fused_kernel<<<grid, f0::kThreads, f0::kSmem, st>>>(h->tc_conv[1].map_hi, h->tc_conv[1].map_lo, h->tc_conv[2].map_hi,
@@ -591,38 +377,10 @@ static int encode_tc(mimi_b200* h, const float* d_input, int B, long long N, int
       h->launches++; mark(h, 27, st);
       CUDA_TRY(h, cudaGetLastError());
     }
-  } else if (maxlen[0] > 0) {
-    dim3 grid((maxlen[0] + 127) / 128, B);
-    const bool sp = h->mode == 2;
-    conv0_kernel<<<grid, 256, 0, st>>>(d_input, N, h->conv_wt[0], h->conv_b[0], ws + p.a0, rstride(0, 64), dlen[0], maxlen[0],
-                                       sp ? ws + p.s_a0.hi : nullptr, sp ? ws + p.s_a0.lo : nullptr, p.s_a0.item_stride, p.s_a0.front);
-    h->launches++; mark(h, 0, st);
-    CUDA_TRY(h, cudaGetLastError());
   }
   if (h->phase == MIMI_B200_PHASE_FRONT) return MIMI_B200_OK;
-  if (h->mode >= 3) {
-  } else if (h->mode == 2) {
-    TcOut o;   // R1a: ELU -> 64 -> 32, k3 (ELU was applied by conv0's split store)
-    o.split = &p.s_r1; o.elu_split = 1; o.bias = h->conv_b[1];
-    if ((rc = tc_gemm(c, 16, p.s_a0, 3, 1, 2, h->tc_conv[1], o, 1))) return rc;
-    o = TcOut{};   // R1b: ELU -> 32 -> 64, k1, + skip (raw a0); only ELU(h) is needed downstream
-    o.res = ws + p.a0; o.raw_item_stride = rstride(0, 64); o.split = &p.s_h1; o.elu_split = 1; o.bias = h->conv_b[2];
-    if ((rc = tc_gemm(c, 17, p.s_r1, 1, 1, 0, h->tc_conv[2], o, 2))) return rc;
-  } else {
-    GemmParams g{};
-    g.A = ws + p.a0; g.Wt = h->conv_wt[1]; g.bias = h->conv_b[1]; g.out = ws + p.r1;
-    g.len_in = dlen[0]; g.uniform_len_in = maxlen[0]; g.a_item_stride = rstride(0, 64); g.out_item_stride = rstride(0, 32);
-    g.Cin = 64; g.stride = 1; g.pad_left = 2; g.K = 192; g.N = 32; g.elu_in = 1;
-    if ((rc = launch_gemm(h, g, B, maxlen[0], st, 1))) return rc;
-    g = GemmParams{};
-    g.A = ws + p.r1; g.Wt = h->conv_wt[2]; g.bias = h->conv_b[2]; g.res = ws + p.a0; g.out = nullptr;
-    g.len_in = dlen[0]; g.uniform_len_in = maxlen[0]; g.a_item_stride = rstride(0, 32); g.out_item_stride = rstride(0, 64);
-    g.Cin = 32; g.stride = 1; g.pad_left = 0; g.K = 32; g.N = 64; g.elu_in = 1;
-    g.out_hi = ws + p.s_h1.hi; g.out_lo = ws + p.s_h1.lo; g.split_item_stride = p.s_h1.item_stride;
-    g.split_front = p.s_h1.front; g.elu_split = 1;
-    if ((rc = launch_gemm(h, g, B, maxlen[0], st, 2))) return rc;
-  }
-  // ---- D1 .. R4b on tensor cores ----------------------------------------------------------------------------
+
+  // ---- D1 .. R4b ------------------------------------------------------------------------------------------------------
   struct Lvl { const SplitBuf* in; long long d_raw; const SplitBuf *s_d, *s_r, *s_h; int C; };   // C = channels after the down conv
   const Lvl lv[3] = {{&p.s_h1, p.d1, &p.s_d1, &p.s_r2, &p.s_h2, 128},
                      {&p.s_h2, p.d2, &p.s_d2, &p.s_r3, &p.s_h3, 256},
@@ -633,14 +391,7 @@ static int encode_tc(mimi_b200* h, const float* d_input, int B, long long N, int
     const ConvGeom& gd = kConv[id];
     TcOut o;   // down conv: raw (skip) + ELU'd split (resblock conv a)
     o.raw = ws + L.d_raw; o.raw_item_stride = rstride(s + 1, L.C); o.split = L.s_d; o.elu_split = 1; o.bias = h->conv_b[id];
-    o.raw_in = (s == 0) ? raw_h1 : 0;
     if ((rc = tc_gemm(c, id, *L.in, gd.k, gd.stride, gd.k - gd.stride, h->tc_conv[id], o, id))) return rc;
-    if (s == 0 && h->mode == 7 && h->exp_fuse_res && !h->use_planes) {
-      // level 1: both convs of the residual block in one kernel (the 64-channel intermediate stays in shared memory)
-      if ((rc = tc_resblock1(c, ia, *L.s_d, h->tc_conv[ia], h->tc_conv[ib], h->conv_b[ia], h->conv_b[ib], ws + L.d_raw,
-                             rstride(s + 1, L.C), *L.s_h, ib))) return rc;
-      continue;
-    }
     o = TcOut{};   // resblock conv a: C -> C/2, k3
     o.split = L.s_r; o.elu_split = 1; o.bias = h->conv_b[ia];
     if ((rc = tc_gemm(c, ia, *L.s_d, 3, 1, 2, h->tc_conv[ia], o, ia))) return rc;
@@ -661,42 +412,26 @@ static int encode_tc(mimi_b200* h, const float* d_input, int B, long long N, int
   for (int l = 0; l < h->dbg_layers && T25 > 0; ++l) {
     const LayerDev& d = h->layer[l];
     dim3 lgrid((T25 + 7) / 8, B);
-    layernorm512_kernel<<<lgrid, 256, 0, st>>>(ws + p.z, ws + p.s_y.hi, d.ln1_w, d.ln1_b, rstride(4, 512), dlen[4], T25, ws + p.s_y.lo, h->mode == 9 ? 3 : h->mode >= 7, p.s_y.hib >= 0 ? ws + p.s_y.hib : nullptr);
+    layernorm512_kernel<<<lgrid, 256, 0, st>>>(ws + p.z, ws + p.s_y.hi, d.ln1_w, d.ln1_b, rstride(4, 512), dlen[4], T25, ws + p.s_y.lo, lob);
     h->launches++; mark(h, 14, st);
     TcOut o;
     o.raw = ws + p.qkv; o.raw_item_stride = rstride(4, 1536);
     if ((rc = tc_gemm(c, 0, p.s_y, 1, 1, 0, h->tc_qkv[l], o, 15))) return rc;
-    if (h->mode >= 3 && (h->att_variant == 4 || h->mode >= 7)) {
+    {
       // tensor-core attention: persistent CTAs over (128-query tile, head, item) units
       atc::Params ap{};
       ap.qkv = ws + p.qkv; ap.item_stride = rstride(4, 1536); ap.out_hi = ws + p.s_att.hi; ap.out_lo = ws + p.s_att.lo;
       ap.out_stride = rstride(4, 512); ap.rope_cos = h->rope_cos; ap.rope_sin = h->rope_sin; ap.len = dlen[4];
-      ap.uniform_len = T25; ap.B = B; ap.mt_max = (T25 + atc::kQT - 1) / atc::kQT; ap.lo_bf16 = h->mode == 9 ? 3 : h->mode >= 7;
-      ap.out_hib = p.s_att.hib >= 0 ? ws + p.s_att.hib : nullptr;
+      ap.uniform_len = T25; ap.B = B; ap.mt_max = (T25 + atc::kQT - 1) / atc::kQT; ap.lo_bf16 = lob;
       const long long units = (long long)ap.mt_max * B * kHeads;
       atc::swa_attention_tc_kernel<<<(int)std::min<long long>(units, h->num_sms), atc::kThreads, atc::kSmem, st>>>(ap);
-    } else if (h->mode >= 2) {
-      const int ntiles = (T25 + kAttQT - 1) / kAttQT;
-      const int nsplit = std::max(1, std::min(ntiles, (4 * h->num_sms + kHeads * B - 1) / (kHeads * B)));
-      const int tps = (ntiles + nsplit - 1) / nsplit;
-      dim3 agrid((ntiles + tps - 1) / tps, kHeads, B);
-      if (h->att_variant == 3)
-        swa_attention3_kernel<<<agrid, 512, kAtt2SmemBytes, st>>>(ws + p.qkv, rstride(4, 1536), ws + p.s_att.hi, rstride(4, 512),
-                                                                  h->rope_cos, h->rope_sin, dlen[4], T25, ws + p.s_att.lo, tps);
-      else
-        swa_attention2_kernel<<<agrid, 256, kAtt2SmemBytes, st>>>(ws + p.qkv, rstride(4, 1536), ws + p.s_att.hi, rstride(4, 512),
-                                                                  h->rope_cos, h->rope_sin, dlen[4], T25, ws + p.s_att.lo, tps);
-    } else {
-      dim3 agrid((T25 + kAttQT - 1) / kAttQT, kHeads, B);
-      swa_attention_kernel<<<agrid, 256, kAttSmemBytes, st>>>(ws + p.qkv, rstride(4, 1536), ws + p.s_att.hi, rstride(4, 512),
-                                                              h->rope_cos, h->rope_sin, dlen[4], T25, ws + p.s_att.lo);
+      h->launches++; mark(h, 16, st);
+      CUDA_TRY(h, cudaGetLastError());
     }
-    h->launches++; mark(h, 16, st);
-    CUDA_TRY(h, cudaGetLastError());
     o = TcOut{};   // o_proj + LayerScale + residual, in place on z
     o.raw = ws + p.z; o.res = ws + p.z; o.raw_item_stride = rstride(4, 512); o.scale = d.ls1;
     if ((rc = tc_gemm(c, 1, p.s_att, 1, 1, 0, h->tc_o[l], o, 17))) return rc;
-    layernorm512_kernel<<<lgrid, 256, 0, st>>>(ws + p.z, ws + p.s_y.hi, d.ln2_w, d.ln2_b, rstride(4, 512), dlen[4], T25, ws + p.s_y.lo, h->mode == 9 ? 3 : h->mode >= 7, p.s_y.hib >= 0 ? ws + p.s_y.hib : nullptr);
+    layernorm512_kernel<<<lgrid, 256, 0, st>>>(ws + p.z, ws + p.s_y.hi, d.ln2_w, d.ln2_b, rstride(4, 512), dlen[4], T25, ws + p.s_y.lo, lob);
     h->launches++; mark(h, 14, st);
     o = TcOut{};   // fc1 + GELU(erf) -> split
     o.split = &p.s_ffn; o.act = 1;
@@ -710,8 +445,7 @@ static int encode_tc(mimi_b200* h, const float* d_input, int B, long long N, int
   if (T25 > 0) {
     dim3 pgrid((T25 + 3 + 7) / 8, B);
     tc::pad_replicate_split_kernel<<<pgrid, 256, 0, st>>>(ws + p.z, rstride(4, 512), ws + p.s_zp.hi, ws + p.s_zp.lo,
-                                                          p.s_zp.item_stride, dlen[4], T25, h->mode == 9 ? 3 : h->mode >= 7,
-                                                          p.s_zp.hib >= 0 ? ws + p.s_zp.hib : nullptr);
+                                                          p.s_zp.item_stride, dlen[4], T25, lob);
     h->launches++; mark(h, 26, st);
     TcOut o;
     o.raw = ws + p.e; o.raw_item_stride = rstride(5, 512); o.split = &p.s_e;
@@ -729,21 +463,14 @@ static int encode_tc(mimi_b200* h, const float* d_input, int B, long long N, int
     TcOut o;
     o.raw = ws + p.rp; o.raw_item_stride = rstride(5, 512);
     if ((rc = tc_gemm(c, 15, p.s_e, 1, 1, 0, h->tc_proj, o, 21))) return rc;
-    RvqParams r{};
-    r.rproj = ws + p.rp; r.item_stride = rstride(5, 512);
-    r.embed = h->embed; r.embed_t = h->embed_t; r.enorm = h->enorm;
-    r.codes = reinterpret_cast<long long*>(d_codes); r.K = K; r.T_out = p.rows[5];
-    r.len = dlen[5]; r.uniform_len = T; r.B = B; r.total_frames = total_frames; r.frame_prefix = dprefix;
-    if (total_frames > 0 && h->mode >= 3) {
+    if (total_frames > 0) {
       rvqtc::Params q{};
-      q.rproj = r.rproj; q.item_stride = r.item_stride; q.embed = h->embed; q.enorm = h->enorm; q.codes = r.codes;
-      q.K = K; q.T_out = r.T_out; q.len = r.len; q.uniform_len = r.uniform_len; q.B = B; q.total_frames = total_frames;
+      q.rproj = ws + p.rp; q.item_stride = rstride(5, 512); q.embed = h->embed; q.enorm = h->enorm;
+      q.codes = reinterpret_cast<long long*>(d_codes);
+      q.K = K; q.T_out = p.rows[5]; q.len = dlen[5]; q.uniform_len = T; q.B = B; q.total_frames = total_frames;
       q.frame_prefix = dprefix;
       rvqtc::rvq_tc_kernel<<<(total_frames + rvqtc::kFrames - 1) / rvqtc::kFrames, rvqtc::kThreads, rvqtc::kSmem, st>>>(
           h->map_embed_hi, h->map_embed_lo, q);
-      h->launches++; mark(h, 22, st);
-    } else if (total_frames > 0) {
-      rvq_encode_kernel<<<(total_frames + kRvqFM - 1) / kRvqFM, 256, kRvqSmemBytes, st>>>(r);
       h->launches++; mark(h, 22, st);
     }
   }

@@ -11,7 +11,7 @@ __global__ void __launch_bounds__(256) layernorm512_kernel(const float* __restri
                                                            const float* __restrict__ gamma,
                                                            const float* __restrict__ beta,
                                                            long long item_stride, const int* __restrict__ len,
-                                                           int uniform_len, float* __restrict__ y_lo, int lob = 0, float* __restrict__ y_hib = nullptr) {
+                                                           int uniform_len, float* __restrict__ y_lo, int lob = 0) {
   // y_lo != nullptr: write the hi/lo TF32 split of the result into (y, y_lo) for a tensor-core consumer
   const int b = blockIdx.y;
   const int L = len ? len[b] : uniform_len;
@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(256) layernorm512_kernel(const float* __restri
     o.y = v[i].y * rstd * g.y + bt.y;
     o.z = v[i].z * rstd * g.z + bt.z;
     o.w = v[i].w * rstd * g.w + bt.w;
-    if (y_lo) store_split4_x(y, y_lo, y_hib, (long long)b * item_stride + (long long)t * kHidden + c, o, lob);
+    if (y_lo) store_split4_x(y, y_lo, (long long)b * item_stride + (long long)t * kHidden + c, o, lob);
     else *reinterpret_cast<float4*>(yr + c) = o;
   }
 }
@@ -66,9 +66,7 @@ __global__ void __launch_bounds__(256) swa_attention_kernel(const float* __restr
                                                             float* __restrict__ out, long long out_stride,
                                                             const float* __restrict__ rope_cos,
                                                             const float* __restrict__ rope_sin,
-                                                            const int* __restrict__ len, int uniform_len,
-                                                            float* __restrict__ out_lo) {
-  // out_lo != nullptr: (out, out_lo) receive the hi/lo TF32 split of the result
+                                                            const int* __restrict__ len, int uniform_len) {
   extern __shared__ __align__(16) float smem[];
   float* Vs = smem;                                  // [281][64]  (float4 stores: 16-byte aligned)
   float* Qs = Vs + kAttKeys * kHeadDim;              // [32][64]
@@ -171,350 +169,10 @@ __global__ void __launch_bounds__(256) swa_attention_kernel(const float* __restr
       o1 = fmaf(pj, vr[lane + 32], o1);
     }
     float* orow = out + (long long)b * out_stride + (long long)i * kHidden + h * kHeadDim;
-    if (out_lo) {
-      float* lrow = out_lo + (long long)b * out_stride + (long long)i * kHidden + h * kHeadDim;
-      float hi, lo;
-      split_tf32(o0, hi, lo); orow[lane] = hi; lrow[lane] = lo;
-      split_tf32(o1, hi, lo); orow[lane + 32] = hi; lrow[lane + 32] = lo;
-    } else {
-      orow[lane] = o0;
-      orow[lane + 32] = o1;
-    }
+    orow[lane] = o0;
+    orow[lane + 32] = o1;
     __syncwarp();
   }
 }
-
-
-// Second-generation sliding-window attention (same arithmetic, ~4x fewer shared-memory reads):
-//   * one CTA walks a contiguous range of 32-query tiles of one (head, item) and keeps K (RoPE applied) and V
-//     in a 320-row RING in shared memory, so every K/V row is fetched from global memory once per range
-//     instead of once per 32 queries (a tile needs rows [q0-249, q0+31] = 281 <= 320 - 32);
-//   * each warp scores FOUR consecutive queries at a time: a K element read from shared memory feeds four
-//     FMAs (q rows for the four queries come as one broadcast LDS.128), and in the PV pass one V element feeds
-//     four FMAs (the four probabilities of a key are one broadcast LDS.128).
-// grid = (splits, heads, items); CTA (sp, h, b) handles query tiles [sp*tps, min((sp+1)*tps, ntiles)).
-constexpr int kAtt2Ring = 320;
-constexpr size_t kAtt2SmemBytes =
-    sizeof(float) * (size_t)(kAtt2Ring * kAttKPitch + kAtt2Ring * kHeadDim + 8 * kHeadDim * 4 + 8 * 256 * 4);
-
-__global__ void __launch_bounds__(256) swa_attention2_kernel(const float* __restrict__ qkv, long long item_stride,
-                                                             float* __restrict__ out, long long out_stride,
-                                                             const float* __restrict__ rope_cos,
-                                                             const float* __restrict__ rope_sin,
-                                                             const int* __restrict__ len, int uniform_len,
-                                                             float* __restrict__ out_lo, int tiles_per_split) {
-  extern __shared__ __align__(16) float smem[];
-  float* Vs = smem;                                   // [320][64]
-  float* Qt = Vs + kAtt2Ring * kHeadDim;              // [8 warps][64 d][4 queries]
-  float* Pt = Qt + 8 * kHeadDim * 4;                  // [8 warps][256 keys][4 queries]
-  float* Ks = Pt + 8 * 256 * 4;                       // [320][65]
-
-  const int b = blockIdx.z, h = blockIdx.y;
-  const int T = len ? len[b] : uniform_len;
-  const int ntiles = (T + kAttQT - 1) / kAttQT;
-  const int t_begin = blockIdx.x * tiles_per_split;
-  const int t_end = min(ntiles, t_begin + tiles_per_split);
-  if (t_begin >= t_end) return;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const float* base = qkv + (long long)b * item_stride;
-
-  // stage K (rotated) and V rows [r_lo, r_hi) into their ring slots
-  auto stage_kv = [&](int r_lo, int r_hi) {
-    for (int idx = tid; idx < (r_hi - r_lo) * 8; idx += 256) {
-      const int pos = r_lo + (idx >> 3), d4 = (idx & 7) * 4;
-      const int slot = pos % kAtt2Ring;
-      const float* row = base + (long long)pos * (3 * kHidden);
-      const float4 k_lo = ld_nc_f4(row + kHidden + h * kHeadDim + d4);
-      const float4 k_hi = ld_nc_f4(row + kHidden + h * kHeadDim + d4 + 32);
-      const float4 c = ld_nc_f4(rope_cos + (long long)pos * 32 + d4);
-      const float4 s = ld_nc_f4(rope_sin + (long long)pos * 32 + d4);
-      float* kd = Ks + slot * kAttKPitch + d4;
-      kd[0] = k_lo.x * c.x - k_hi.x * s.x;  kd[32] = k_hi.x * c.x + k_lo.x * s.x;
-      kd[1] = k_lo.y * c.y - k_hi.y * s.y;  kd[33] = k_hi.y * c.y + k_lo.y * s.y;
-      kd[2] = k_lo.z * c.z - k_hi.z * s.z;  kd[34] = k_hi.z * c.z + k_lo.z * s.z;
-      kd[3] = k_lo.w * c.w - k_hi.w * s.w;  kd[35] = k_hi.w * c.w + k_lo.w * s.w;
-      *reinterpret_cast<float4*>(Vs + slot * kHeadDim + d4) = ld_nc_f4(row + 2 * kHidden + h * kHeadDim + d4);
-      *reinterpret_cast<float4*>(Vs + slot * kHeadDim + d4 + 32) = ld_nc_f4(row + 2 * kHidden + h * kHeadDim + d4 + 32);
-    }
-  };
-
-  stage_kv(max(0, t_begin * kAttQT - (kWindow - 1)), t_begin * kAttQT);       // halo of the first tile
-  float* Qw = Qt + warp * kHeadDim * 4;
-  float* Pw = Pt + warp * 256 * 4;
-  for (int tile = t_begin; tile < t_end; ++tile) {
-    const int q0 = tile * kAttQT;
-    const int q1 = min(q0 + kAttQT, T);
-    stage_kv(q0, q1);
-    // this warp's four queries q0 + 4*warp + {0..3}: rotated, pre-scaled by 1/8, stored [d][query]
-    {
-      const int qq = lane >> 3, d4 = (lane & 7) * 4;         // 4 queries x 8 float4 pairs = 32 lanes
-      const int pos = q0 + 4 * warp + qq;
-      float4 lo4 = make_float4(0.f, 0.f, 0.f, 0.f), hi4 = lo4;
-      if (pos < T) {
-        const float* row = base + (long long)pos * (3 * kHidden);
-        const float4 q_lo = ld_nc_f4(row + h * kHeadDim + d4);
-        const float4 q_hi = ld_nc_f4(row + h * kHeadDim + d4 + 32);
-        const float4 c = ld_nc_f4(rope_cos + (long long)pos * 32 + d4);
-        const float4 s = ld_nc_f4(rope_sin + (long long)pos * 32 + d4);
-        lo4.x = (q_lo.x * c.x - q_hi.x * s.x) * 0.125f;  hi4.x = (q_hi.x * c.x + q_lo.x * s.x) * 0.125f;
-        lo4.y = (q_lo.y * c.y - q_hi.y * s.y) * 0.125f;  hi4.y = (q_hi.y * c.y + q_lo.y * s.y) * 0.125f;
-        lo4.z = (q_lo.z * c.z - q_hi.z * s.z) * 0.125f;  hi4.z = (q_hi.z * c.z + q_lo.z * s.z) * 0.125f;
-        lo4.w = (q_lo.w * c.w - q_hi.w * s.w) * 0.125f;  hi4.w = (q_hi.w * c.w + q_lo.w * s.w) * 0.125f;
-      }
-      Qw[(d4 + 0) * 4 + qq] = lo4.x;  Qw[(d4 + 32) * 4 + qq] = hi4.x;
-      Qw[(d4 + 1) * 4 + qq] = lo4.y;  Qw[(d4 + 33) * 4 + qq] = hi4.y;
-      Qw[(d4 + 2) * 4 + qq] = lo4.z;  Qw[(d4 + 34) * 4 + qq] = hi4.z;
-      Qw[(d4 + 3) * 4 + qq] = lo4.w;  Qw[(d4 + 35) * 4 + qq] = hi4.w;
-    }
-    __syncthreads();
-    const int i0 = q0 + 4 * warp;                       // first query of this warp's group
-    if (i0 < T) {
-      const int jlo = max(0, i0 - (kWindow - 1));       // first key visible to the group's first query
-      // lane owns keys jlo + lane + 32*u, u = 0..7 (covers the 253-key union of the four windows)
-      int slot0 = (jlo + lane) % kAtt2Ring;
-      float sc[4][8];
-#pragma unroll
-      for (int qq = 0; qq < 4; ++qq)
-#pragma unroll
-        for (int u = 0; u < 8; ++u) sc[qq][u] = 0.f;
-      int koff[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        int sl = slot0 + 32 * u;
-        if (sl >= kAtt2Ring) sl -= kAtt2Ring;
-        koff[u] = sl * kAttKPitch;
-      }
-#pragma unroll 4
-      for (int d = 0; d < kHeadDim; ++d) {
-        const float4 qv = *reinterpret_cast<const float4*>(Qw + d * 4);
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const float kv = Ks[koff[u] + d];
-          sc[0][u] = fmaf(qv.x, kv, sc[0][u]);
-          sc[1][u] = fmaf(qv.y, kv, sc[1][u]);
-          sc[2][u] = fmaf(qv.z, kv, sc[2][u]);
-          sc[3][u] = fmaf(qv.w, kv, sc[3][u]);
-        }
-      }
-      // masks, softmax (fp32) per query; probabilities to Pw[key][query]
-      float inv[4];
-#pragma unroll
-      for (int qq = 0; qq < 4; ++qq) {
-        const int i = i0 + qq;
-        float m = -INFINITY;
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int j = jlo + lane + 32 * u;
-          const bool vis = (j <= i) && (j > i - kWindow) && (i < T);
-          sc[qq][u] = vis ? sc[qq][u] : -INFINITY;
-          m = fmaxf(m, sc[qq][u]);
-        }
-        m = warp_max(m);
-        float sum = 0.f;
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const float e = (sc[qq][u] == -INFINITY) ? 0.f : expf(sc[qq][u] - m);
-          sc[qq][u] = e;
-          sum += e;
-        }
-        sum = warp_sum(sum);
-        inv[qq] = (i < T) ? 1.f / sum : 0.f;
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u)
-        *reinterpret_cast<float4*>(Pw + (lane + 32 * u) * 4) =
-            make_float4(sc[0][u] * inv[0], sc[1][u] * inv[1], sc[2][u] * inv[2], sc[3][u] * inv[3]);
-      __syncwarp();
-      // out[q][d] = sum_j P[j][q] * V[j][d]; lane owns d = lane and lane + 32
-      const int nkeys = min(i0 + 3, T - 1) - jlo + 1;   // keys jlo .. last query of the group
-      float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
-      int sl = jlo % kAtt2Ring;
-      for (int jj = 0; jj < nkeys; ++jj) {
-        const float4 pj = *reinterpret_cast<const float4*>(Pw + jj * 4);
-        const float v0 = Vs[sl * kHeadDim + lane], v1 = Vs[sl * kHeadDim + lane + 32];
-        o0[0] = fmaf(pj.x, v0, o0[0]); o1[0] = fmaf(pj.x, v1, o1[0]);
-        o0[1] = fmaf(pj.y, v0, o0[1]); o1[1] = fmaf(pj.y, v1, o1[1]);
-        o0[2] = fmaf(pj.z, v0, o0[2]); o1[2] = fmaf(pj.z, v1, o1[2]);
-        o0[3] = fmaf(pj.w, v0, o0[3]); o1[3] = fmaf(pj.w, v1, o1[3]);
-        if (++sl == kAtt2Ring) sl = 0;
-      }
-#pragma unroll
-      for (int qq = 0; qq < 4; ++qq) {
-        const int i = i0 + qq;
-        if (i >= T) break;
-        float* orow = out + (long long)b * out_stride + (long long)i * kHidden + h * kHeadDim;
-        if (out_lo) {
-          float* lrow = out_lo + (long long)b * out_stride + (long long)i * kHidden + h * kHeadDim;
-          float hi, lo;
-          split_tf32(o0[qq], hi, lo); orow[lane] = hi; lrow[lane] = lo;
-          split_tf32(o1[qq], hi, lo); orow[lane + 32] = hi; lrow[lane + 32] = lo;
-        } else {
-          orow[lane] = o0[qq];
-          orow[lane + 32] = o1[qq];
-        }
-      }
-    }
-    __syncthreads();                                    // ring slots of the next tile may overwrite old rows
-  }
-}
-
-// Third variant: 16 warps per CTA, TWO queries per warp. The per-tile arithmetic is the same; four warps per SM
-// sub-partition (instead of two) hide the shared-memory and FMA latencies the 8-warp version exposes (IPC 0.43).
-__global__ void __launch_bounds__(512) swa_attention3_kernel(const float* __restrict__ qkv, long long item_stride,
-                                                             float* __restrict__ out, long long out_stride,
-                                                             const float* __restrict__ rope_cos,
-                                                             const float* __restrict__ rope_sin,
-                                                             const int* __restrict__ len, int uniform_len,
-                                                             float* __restrict__ out_lo, int tiles_per_split) {
-  extern __shared__ __align__(16) float smem[];
-  float* Vs = smem;                                   // [320][64]
-  float* Qt = Vs + kAtt2Ring * kHeadDim;              // [16 warps][64 d][2 queries]
-  float* Pt = Qt + 16 * kHeadDim * 2;                 // [16 warps][256 keys][2 queries]
-  float* Ks = Pt + 16 * 256 * 2;                      // [320][65]
-
-  const int b = blockIdx.z, h = blockIdx.y;
-  const int T = len ? len[b] : uniform_len;
-  const int ntiles = (T + kAttQT - 1) / kAttQT;
-  const int t_begin = blockIdx.x * tiles_per_split;
-  const int t_end = min(ntiles, t_begin + tiles_per_split);
-  if (t_begin >= t_end) return;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const float* base = qkv + (long long)b * item_stride;
-
-  // stage K (rotated) and V rows [r_lo, r_hi) into their ring slots
-  auto stage_kv = [&](int r_lo, int r_hi) {
-    for (int idx = tid; idx < (r_hi - r_lo) * 8; idx += 512) {
-      const int pos = r_lo + (idx >> 3), d4 = (idx & 7) * 4;
-      const int slot = pos % kAtt2Ring;
-      const float* row = base + (long long)pos * (3 * kHidden);
-      const float4 k_lo = ld_nc_f4(row + kHidden + h * kHeadDim + d4);
-      const float4 k_hi = ld_nc_f4(row + kHidden + h * kHeadDim + d4 + 32);
-      const float4 c = ld_nc_f4(rope_cos + (long long)pos * 32 + d4);
-      const float4 s = ld_nc_f4(rope_sin + (long long)pos * 32 + d4);
-      float* kd = Ks + slot * kAttKPitch + d4;
-      kd[0] = k_lo.x * c.x - k_hi.x * s.x;  kd[32] = k_hi.x * c.x + k_lo.x * s.x;
-      kd[1] = k_lo.y * c.y - k_hi.y * s.y;  kd[33] = k_hi.y * c.y + k_lo.y * s.y;
-      kd[2] = k_lo.z * c.z - k_hi.z * s.z;  kd[34] = k_hi.z * c.z + k_lo.z * s.z;
-      kd[3] = k_lo.w * c.w - k_hi.w * s.w;  kd[35] = k_hi.w * c.w + k_lo.w * s.w;
-      *reinterpret_cast<float4*>(Vs + slot * kHeadDim + d4) = ld_nc_f4(row + 2 * kHidden + h * kHeadDim + d4);
-      *reinterpret_cast<float4*>(Vs + slot * kHeadDim + d4 + 32) = ld_nc_f4(row + 2 * kHidden + h * kHeadDim + d4 + 32);
-    }
-  };
-
-  stage_kv(max(0, t_begin * kAttQT - (kWindow - 1)), t_begin * kAttQT);       // halo of the first tile
-  float* Qw = Qt + warp * kHeadDim * 2;
-  float* Pw = Pt + warp * 256 * 2;
-  for (int tile = t_begin; tile < t_end; ++tile) {
-    const int q0 = tile * kAttQT;
-    const int q1 = min(q0 + kAttQT, T);
-    stage_kv(q0, q1);
-    // this warp's two queries q0 + 2*warp + {0,1}: rotated, pre-scaled by 1/8, stored [d][query]
-    if (lane < 16) {
-      const int qq = lane >> 3, d4 = (lane & 7) * 4;         // 2 queries x 8 float4 pairs = 16 lanes
-      const int pos = q0 + 2 * warp + qq;
-      float4 lo4 = make_float4(0.f, 0.f, 0.f, 0.f), hi4 = lo4;
-      if (pos < T) {
-        const float* row = base + (long long)pos * (3 * kHidden);
-        const float4 q_lo = ld_nc_f4(row + h * kHeadDim + d4);
-        const float4 q_hi = ld_nc_f4(row + h * kHeadDim + d4 + 32);
-        const float4 c = ld_nc_f4(rope_cos + (long long)pos * 32 + d4);
-        const float4 s = ld_nc_f4(rope_sin + (long long)pos * 32 + d4);
-        lo4.x = (q_lo.x * c.x - q_hi.x * s.x) * 0.125f;  hi4.x = (q_hi.x * c.x + q_lo.x * s.x) * 0.125f;
-        lo4.y = (q_lo.y * c.y - q_hi.y * s.y) * 0.125f;  hi4.y = (q_hi.y * c.y + q_lo.y * s.y) * 0.125f;
-        lo4.z = (q_lo.z * c.z - q_hi.z * s.z) * 0.125f;  hi4.z = (q_hi.z * c.z + q_lo.z * s.z) * 0.125f;
-        lo4.w = (q_lo.w * c.w - q_hi.w * s.w) * 0.125f;  hi4.w = (q_hi.w * c.w + q_lo.w * s.w) * 0.125f;
-      }
-      Qw[(d4 + 0) * 2 + qq] = lo4.x;  Qw[(d4 + 32) * 2 + qq] = hi4.x;
-      Qw[(d4 + 1) * 2 + qq] = lo4.y;  Qw[(d4 + 33) * 2 + qq] = hi4.y;
-      Qw[(d4 + 2) * 2 + qq] = lo4.z;  Qw[(d4 + 34) * 2 + qq] = hi4.z;
-      Qw[(d4 + 3) * 2 + qq] = lo4.w;  Qw[(d4 + 35) * 2 + qq] = hi4.w;
-    }
-    __syncthreads();
-    const int i0 = q0 + 2 * warp;                       // first query of this warp's pair
-    if (i0 < T) {
-      const int jlo = max(0, i0 - (kWindow - 1));       // first key visible to the group's first query
-      // lane owns keys jlo + lane + 32*u, u = 0..7 (covers the 251-key union of the two windows)
-      int slot0 = (jlo + lane) % kAtt2Ring;
-      float sc[2][8];
-#pragma unroll
-      for (int qq = 0; qq < 2; ++qq)
-#pragma unroll
-        for (int u = 0; u < 8; ++u) sc[qq][u] = 0.f;
-      int koff[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        int sl = slot0 + 32 * u;
-        if (sl >= kAtt2Ring) sl -= kAtt2Ring;
-        koff[u] = sl * kAttKPitch;
-      }
-#pragma unroll 4
-      for (int d = 0; d < kHeadDim; ++d) {
-        const float2 qv = *reinterpret_cast<const float2*>(Qw + d * 2);
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const float kv = Ks[koff[u] + d];
-          sc[0][u] = fmaf(qv.x, kv, sc[0][u]);
-          sc[1][u] = fmaf(qv.y, kv, sc[1][u]);
-        }
-      }
-      // masks, softmax (fp32) per query; probabilities to Pw[key][query]
-      float inv[2];
-#pragma unroll
-      for (int qq = 0; qq < 2; ++qq) {
-        const int i = i0 + qq;
-        float m = -INFINITY;
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int j = jlo + lane + 32 * u;
-          const bool vis = (j <= i) && (j > i - kWindow) && (i < T);
-          sc[qq][u] = vis ? sc[qq][u] : -INFINITY;
-          m = fmaxf(m, sc[qq][u]);
-        }
-        m = warp_max(m);
-        float sum = 0.f;
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const float e = (sc[qq][u] == -INFINITY) ? 0.f : expf(sc[qq][u] - m);
-          sc[qq][u] = e;
-          sum += e;
-        }
-        sum = warp_sum(sum);
-        inv[qq] = (i < T) ? 1.f / sum : 0.f;
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u)
-        *reinterpret_cast<float2*>(Pw + (lane + 32 * u) * 2) = make_float2(sc[0][u] * inv[0], sc[1][u] * inv[1]);
-      __syncwarp();
-      // out[q][d] = sum_j P[j][q] * V[j][d]; lane owns d = lane and lane + 32
-      const int nkeys = min(i0 + 1, T - 1) - jlo + 1;   // keys jlo .. last query of the pair
-      float o0[2] = {0.f, 0.f}, o1[2] = {0.f, 0.f};
-      int sl = jlo % kAtt2Ring;
-      for (int jj = 0; jj < nkeys; ++jj) {
-        const float2 pj = *reinterpret_cast<const float2*>(Pw + jj * 2);
-        const float v0 = Vs[sl * kHeadDim + lane], v1 = Vs[sl * kHeadDim + lane + 32];
-        o0[0] = fmaf(pj.x, v0, o0[0]); o1[0] = fmaf(pj.x, v1, o1[0]);
-        o0[1] = fmaf(pj.y, v0, o0[1]); o1[1] = fmaf(pj.y, v1, o1[1]);
-        if (++sl == kAtt2Ring) sl = 0;
-      }
-#pragma unroll
-      for (int qq = 0; qq < 2; ++qq) {
-        const int i = i0 + qq;
-        if (i >= T) break;
-        float* orow = out + (long long)b * out_stride + (long long)i * kHidden + h * kHeadDim;
-        if (out_lo) {
-          float* lrow = out_lo + (long long)b * out_stride + (long long)i * kHidden + h * kHeadDim;
-          float hi, lo;
-          split_tf32(o0[qq], hi, lo); orow[lane] = hi; lrow[lane] = lo;
-          split_tf32(o1[qq], hi, lo); orow[lane + 32] = hi; lrow[lane + 32] = lo;
-        } else {
-          orow[lane] = o0[qq];
-          orow[lane + 32] = o1[qq];
-        }
-      }
-    }
-    __syncthreads();                                    // ring slots of the next tile may overwrite old rows
-  }
-}
-
 
 }  // namespace mimi

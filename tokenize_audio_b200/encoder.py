@@ -418,8 +418,8 @@ class MimiB200Model:
     # -- parity helpers --------------------------------------------------------------------------------
     @property
     def supports_phased(self) -> bool:
-        """mimi_b200_encode_phase needs the fused front end (kernel generations 3, 4, 6)."""
-        return self._mode in (3, 4, 6, 7, 8, 9)
+        """mimi_b200_encode_phase needs the fused front end (the tensor-core generations 7 and 9)."""
+        return self._mode in (7, 9)
 
     def debug_set(self, key: int, value: int) -> None:
         if key == 3:
@@ -459,13 +459,10 @@ class MimiB200Model:
             return bool(self._lib.mimi_b200_range_overflow(self._h, 1 if reset else 0))
 
     def set_mode(self, tensor_cores) -> None:
-        """True / 9 (default): mode 7 with every GEMM operand as an fp16 hi/lo pair, all three products on kind::f16 (3 tensor
-        passes, 4 bytes per activation element; fp16 range, see range_overflow); 7: mode 6 with the lo parts of the activations stored as bf16 and the A_lo * W_hi product on
-        kind::f16 (2.5 tensor passes instead of 3, 6 instead of 8 bytes per activation element); 6: fused 24 kHz front end + CTA-pair (cta_group::2) tcgen05 3xTF32 GEMM for every layer with
-        N % 128 == 0, the single-CTA persistent kernel for the rest; 3: the single-CTA kernel everywhere; 5: activations
-        stored as raw fp32 and split inside the GEMM; 4: the same with the experimental third-generation GEMM (256-row tiles, plane-staged
-        activations, single accumulator); 2: mode 3 without the front-end fusion; 1: the first-generation tcgen05 kernel
-        for the wide layers (level 0 on FFMA); False / 0: all-fp32 FFMA."""
+        """True / 9 (default): fused 24 kHz front end + CTA-pair (cta_group::2) tcgen05 GEMM with every operand as an fp16 hi/lo
+        pair, all three products on kind::f16 (3 tensor passes, 4 bytes per activation element; fp16 range, see
+        range_overflow) + tcgen05 attention + tensor-core RVQ; 7: the same with TF32 hi (fp32) and bf16 lo operands (hi*hi and
+        hi*lo on kind::tf32, lo*hi on kind::f16: 5 pass units, fp32 range); False / 0: all-fp32 FFMA (bisection baseline)."""
         mode = (self.DEFAULT_MODE if tensor_cores else 0) if isinstance(tensor_cores, bool) else int(tensor_cores)
         self.debug_set(3, mode)
 
