@@ -43,7 +43,7 @@ const ConvGeom kConv[MIMI_B200_NUM_CONVS] = {
     {64, 128, 1, 1},  {128, 256, 10, 5}, {256, 128, 3, 1}, {128, 256, 1, 1},  {256, 512, 12, 6},
     {512, 256, 3, 1}, {256, 512, 1, 1}, {512, 1024, 16, 8}, {1024, 512, 3, 1}};
 const int kLevelStride[5] = {4, 5, 6, 8, 2};   // level l+1 = ceil(level l / stride)
-constexpr int kRopeMaxPos = 16384;             // 25 Hz positions (10.9 min); reference chunks are <= 60 s
+constexpr int kRopeMaxPos = 65536;             // 25 Hz positions (43.7 min of audio per item); reference chunks are <= 60 s
 constexpr int kStageSlots = 4;
 
 struct LayerDev {
@@ -697,7 +697,7 @@ static int encode_impl(mimi_b200_t* h, const float* d_input, int B, int64_t N, c
   uintptr_t base = (reinterpret_cast<uintptr_t>(d_workspace) + 255) & ~uintptr_t(255);
   if (base + need > reinterpret_cast<uintptr_t>(d_workspace) + workspace_bytes)
     return fail(h, MIMI_B200_ERR_WORKSPACE, "encode: workspace too small, need " + std::to_string(need + 256));
-  if (p.rows[4] > kRopeMaxPos) return fail(h, MIMI_B200_ERR_ARG, "encode: more than 16384 25-Hz positions per item");
+  if (p.rows[4] > kRopeMaxPos) return fail(h, MIMI_B200_ERR_ARG, "encode: more than 65536 25-Hz positions (43.7 min) per item");
   float* ws = reinterpret_cast<float*>(base);
   int* dints = reinterpret_cast<int*>(base + (use_tc ? pt.ints : p.ints));
   h->last = p;
