@@ -71,6 +71,12 @@ HBM_BYTES_PER_AUDIO_S = {
     "front_fused": 24000 * 4 + 24000 * 64 * 4,
 }
 HBM_BOUND_KINDS = ("conv0", "layernorm", "front_fused")
+# level-1 GEMM layers in the default generation (fp16 pairs: 4 B per split element, raw skip tensor fp32): operand in + outputs
+LEVEL1_HBM_BYTES_PER_AUDIO_S = {
+    "seanet_conv3": 24000 * 64 * 4 + 6000 * 128 * (4 + 4),             # D1: h1 pair in, d1 raw + ELU'd pair out
+    "seanet_conv4": 6000 * 128 * 4 + 6000 * 64 * 4,                    # R2a: d1 pair in, r2 pair out
+    "seanet_conv5": 6000 * 64 * 4 + 6000 * 128 * 4 + 6000 * 128 * 4,   # R2b: r2 pair in, d1 raw (skip) in, h2 pair out
+}
 
 
 # stdout carries exactly ONE line, the JSON result: everything else a library prints there (NCCL's version banner, a
@@ -566,14 +572,14 @@ def run_b200(args, rank, world, local_rank):
     # The profile is per launch KIND (layer); the ncu launch list is per kernel FUNCTION. In the default generation most
     # layers are launches of one function, the 256-column CTA-pair GEMM: group the kinds by the function that runs them so
     # that "dominant kernel" and its share of the step mean the same thing here and in profiles/*launches*.md.
-    tcp256 = ("seanet_conv6", "seanet_conv8", "seanet_conv9", "seanet_conv10", "seanet_conv11", "seanet_conv12", "seanet_conv13",
-              "qkv_gemm", "o_proj", "fc1_gelu", "fc2", "downsample_conv", "rvq_input_proj")
+    # (tc_host.inl: launch_tcp -- 256-column pair tiles for K > 2048, 64 for N = 64, 128 for the rest)
+    fn_of = {"seanet_conv9": 256, "seanet_conv12": 256, "seanet_conv13": 256, "seanet_conv4": 64}
+    gemm_kinds = {f"seanet_conv{i}" for i in range(3, 14)} | {"qkv_gemm", "o_proj", "fc1_gelu", "fc2", "downsample_conv", "rvq_input_proj"}
     groups = {}
     cur_mode = args.mode if args.mode is not None else model.DEFAULT_MODE
-    default_gen = cur_mode >= 7
-    fn256 = "tcp_gemm_kernel<256,%d>" % (3 if cur_mode == 9 else 1)
+    default_gen = cur_mode >= 7 and not any(kv.startswith("9=") for kv in args.dbg)
     for k, (kms_, kcnt_) in prof.items():
-        g = fn256 if (default_gen and k in tcp256) else k
+        g = "tcp_gemm_kernel<%d,%d>" % (fn_of.get(k, 128), 3 if cur_mode == 9 else 1) if (default_gen and k in gemm_kinds) else k
         e = groups.setdefault(g, {"ms": 0.0, "count": 0, "kinds": []})
         e["ms"] += kms_; e["count"] += kcnt_; e["kinds"].append(k)
     kind, grp = max(groups.items(), key=lambda kv: kv[1]["ms"])
@@ -615,6 +621,27 @@ def run_b200(args, rank, world, local_rank):
                              "peak is the measured dense bf16 figure")
     else:
         roof["note"] = "achieved = algorithmic bytes of the launch / CUDA-event duration; peak = measured copy bandwidth"
+    # every kernel function of the step with its own roofline reading (the headline `roofline` is the entry with the largest share);
+    # the level-1 layers of the 128-column GEMM are HBM-bound, so they are also given against the copy bandwidth
+    by_kernel = []
+    step_ms = sum(v[0] for v in prof.values())
+    for g, e in sorted(groups.items(), key=lambda kv: -kv[1]["ms"]):
+        if e["ms"] / step_ms < 0.01:
+            continue
+        row = {"kernel": g, "share_of_step": round(e["ms"] / step_ms, 4), "ms_per_step": round(e["ms"] / args.steps, 4)}
+        if all(k in MMAC_PER_AUDIO_S and k not in HBM_BOUND_KINDS for k in e["kinds"]):
+            tf = sum(2 * MMAC_PER_AUDIO_S[k] * 1e6 for k in e["kinds"]) * audio_per_step * args.steps / (e["ms"] / 1e3) / 1e12
+            row.update({"bound": "tensor", "achieved_tflops": round(tf, 1), "frac": round(tf / peaks["tflops"], 4)})
+        elif all(k in HBM_BYTES_PER_AUDIO_S for k in e["kinds"]):
+            gb = sum(HBM_BYTES_PER_AUDIO_S[k] for k in e["kinds"]) * audio_per_step * args.steps / (e["ms"] / 1e3) / 1e9
+            row.update({"bound": "hbm", "achieved_gbs": round(gb, 1), "frac": round(gb / peaks["hbm_gbs"], 4)})
+        by_kernel.append(row)
+    if cur_mode == 9:
+        for k, nbytes in LEVEL1_HBM_BYTES_PER_AUDIO_S.items():
+            if k in prof:
+                gb = nbytes * audio_per_step * args.steps / (prof[k][0] / 1e3) / 1e9
+                by_kernel.append({"kernel": f"tcp_gemm_kernel, layer {k} alone (HBM view)", "bound": "hbm", "achieved_gbs": round(gb, 1),
+                                  "frac": round(gb / peaks["hbm_gbs"], 4), "ms_per_step": round(prof[k][0] / args.steps, 4)})
     breakdown = {k: round(v[0] / args.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
 
     # ---- CPU baseline beside it (rank 0, N=1 only): the reference implementation on host cores -----------
@@ -698,7 +725,7 @@ def run_b200(args, rank, world, local_rank):
         "e2e_single_call": {"value": e2e1_value, "unit": "x_realtime", "latency_ms_median": 1e3 * float(np.median(lat)),
                             "api": "one synchronous wrapper call per batch (MimiEncoder.encode_audio_batch / encode_to_strings / encode_native_rate_batch)"},
         "gpu_launches": int(red["launches"]), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
-        "agreement": agreement, **extras, "ms_per_step_by_kernel": breakdown,
+        "agreement": agreement, **extras, "roofline_by_kernel": by_kernel, "ms_per_step_by_kernel": breakdown,
     }))
 
 

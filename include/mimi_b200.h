@@ -180,9 +180,9 @@ int mimi_b200_debug_tap(mimi_b200_t* h, int which, float* d_out, size_t out_capa
              units, 6 bytes per element); fp32 range -- the fallback of mode 9
           0  every layer on fp32 FFMA (exact-fp32 bisection baseline; also what the decode direction runs on)
      5  k-blocks per accumulation chunk of the GEMM (0 = default 4, i.e. K = 128 inside TMEM between drains)
-     9  pair tiles of 128 columns for layers with N >= value (0 = never, default)
+     9  1 = pair tiles of 256 columns wherever N allows (default 0: 256 columns only for K > 2048, 128 otherwise)
     10  1 = never flatten the row dimension of the linears across items
-    11  1 = k-blocks in linear order, 2 = tap-grouped with the channel panels innermost (default 0: grouped by tau mod s)
+    11  1 = k-blocks in linear order (default 0: taps grouped by tau mod s so that re-read input rows hit L2)
     13  1 = walk the mt_max x B tile grid instead of the compact tile lists of a ragged call
     16  1 = first-draft one-thread-per-output resampler instead of resample_poly_kernel */
 int mimi_b200_debug_set(mimi_b200_t* h, int key, int value);

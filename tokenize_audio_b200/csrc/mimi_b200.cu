@@ -76,7 +76,10 @@ struct TcWeight {
   // s16 = fp16(h16 / 2048) (the factor of the activations' scaled lo parts); wscale[n] = 2^-e_n undoes the scaling in the epilogue.
   // One array [3][N][K] (hi | lo | hs); SWIZZLE_64B boxes of 32 x {128, 64, 32} rows.
   uint16_t* f16 = nullptr;
-  float* wscale = nullptr;
+  // per-column affine of the epilogue, out = act(acc * cmul + cadd): cmul[0] (mode 7) = LayerScale or 1, cmul[1] (mode 9) = that
+  // times the weight unscaling 2^-e_n; cadd = bias * LayerScale or 0
+  float* cmul[2] = {nullptr, nullptr};
+  float* cadd = nullptr;
   CUtensorMap map_f16[3][3];               // [hi, lo, hs][box rows 128, 64, 32]
   int N = 0, K = 0, BN = 0;
 };
@@ -169,7 +172,7 @@ struct mimi_b200 {
   int exp_linear_k = 0;                        // debug_set key 11: k-blocks in linear order (no tap grouping)
   int exp_no_flat = 0;                         // debug_set key 10: never flatten the linears' row dimension across items
   int num_clusters = 74;                       // co-resident CTA pairs of the cta_group::2 GEMM (tc_gemm5.cuh, mode 6)
-  int exp_pair_n128 = 0;                       // pair tiles of 128 columns for layers with N >= this (debug_set key 9; 0 = never)
+  int exp_pair_n128 = 0;                       // debug_set key 9: 1 = 256-column pair tiles wherever N allows (default: only for K > 2048)
   PFN_cuTensorMapEncodeTiled_v12000 encode_tiled = nullptr;
   TcWeight tc_conv[MIMI_B200_NUM_CONVS];       // convs 1..13 (conv 0 is a direct SIMT conv)
   TcWeight tc_qkv[MIMI_B200_NUM_LAYERS], tc_o[MIMI_B200_NUM_LAYERS], tc_fc1[MIMI_B200_NUM_LAYERS], tc_fc2[MIMI_B200_NUM_LAYERS];
@@ -503,7 +506,7 @@ int mimi_b200_debug_set(mimi_b200_t* h, int key, int value) {
   else if (key == 5) h->exp_chunk_kb = std::max(value, 0);
   else if (key == 9) h->exp_pair_n128 = std::max(value, 0);
   else if (key == 10) h->exp_no_flat = value != 0;
-  else if (key == 11) h->exp_linear_k = value;           // 1: linear order, 2: tap-grouped with the channel panels innermost
+  else if (key == 11) h->exp_linear_k = value != 0;      // 1: k-blocks in linear order (no tap grouping)
   else if (key == 13) h->exp_no_tile_list = value != 0;
   else if (key == 16) h->exp_resample_simple = value != 0;
   else return fail(h, MIMI_B200_ERR_ARG, "debug_set: unknown key");
@@ -962,7 +965,12 @@ int mimi_b200_debug_tc_gemm(mimi_b200_t* h, const float* d_a, const float* h_w, 
   if ((rc = tc_init_driver(h))) return rc;
   const size_t mark = h->allocs.size();          // the test weight is freed again below
   TcWeight w;
-  if ((rc = tc_make_weight(h, &w, std::vector<float>(h_w, h_w + (size_t)N * K), N, K))) return rc;
+  std::vector<float> hbias;
+  if (d_bias_opt) {
+    hbias.resize(N);
+    CUDA_TRY(h, cudaMemcpy(hbias.data(), d_bias_opt, (size_t)N * sizeof(float), cudaMemcpyDeviceToHost));
+  }
+  if ((rc = tc_make_weight(h, &w, std::vector<float>(h_w, h_w + (size_t)N * K), N, K, d_bias_opt ? hbias.data() : nullptr))) return rc;
   const bool f16 = h->mode == 9;
   float *hi = nullptr, *lo = nullptr;
   const long long n = (long long)M * K;
@@ -977,10 +985,9 @@ int mimi_b200_debug_tc_gemm(mimi_b200_t* h, const float* d_a, const float* h_w, 
   else if ((rc = tc_make_map(h, &ma_hi, hi, 3, dims, strides, tc::kBM))) return rc;
   if ((rc = tc_make_map_bf16(h, &ma_lo, lo, 3, dims, strides_b, tc::kBM))) return rc;
   tc::Epilogue ep{};
-  ep.bias = d_bias_opt; ep.out_raw = d_out; ep.raw_item_stride = (long long)M * N; ep.act = act;
+  ep.cmul = w.cmul[f16 ? 1 : 0]; ep.cadd = w.cadd; ep.out_raw = d_out; ep.raw_item_stride = (long long)M * N; ep.act = act;
   ep.uniform_len_in = M; ep.conv_stride = 1; ep.N = N;
   ep.chunk_kb = h->exp_chunk_kb; ep.lo_bf16 = f16 ? 3 : 1;
-  ep.wscale = f16 ? w.wscale : nullptr;
   rc = launch_tcp(h, ma_hi, ma_lo, w, ep, 1, (M + tc::kBM - 1) / tc::kBM, st);
   h->launches += 2;
   cudaError_t e = cudaGetLastError();

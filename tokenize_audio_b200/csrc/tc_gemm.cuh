@@ -22,8 +22,8 @@ constexpr int kBK = 32;                       // fp32 elements per k-block = one
 constexpr int kUmmaK = 8;                     // tf32 MMA K
 
 struct Epilogue {
-  const float* bias;            // [N] or nullptr
-  const float* scale;           // [N] LayerScale or nullptr
+  const float* cmul;            // [N] per-column factor: the weight unscaling of mode 9 (a power of two) x LayerScale, 1 otherwise
+  const float* cadd;            // [N] per-column addend: bias x LayerScale, 0 otherwise:   out = act(acc * cmul + cadd) (+ res)
   const float* res;             // raw residual rows of N floats (may alias out_raw) or nullptr
   float* out_raw;               // raw output rows of N floats, or nullptr
   float* out_hi;                // split output (with halo rows), or nullptr
@@ -31,7 +31,7 @@ struct Epilogue {
   long long raw_item_stride;    // floats between items in res / out_raw
   long long split_item_stride;  // floats between items in out_hi / out_lo
   int split_front;              // halo rows in front of row 0 of each item in the split buffers
-  int act;                      // 1: GELU(erf) after bias
+  int act;                      // 1: GELU(erf) after the affine
   int elu_split;                // 1: ELU applied before the hi/lo split (next conv's input activation)
   const int* len_in;            // device [B] input rows per item or nullptr -> uniform_len_in
   int uniform_len_in;
@@ -40,7 +40,6 @@ struct Epilogue {
   int chunk_kb;                 // experiment: k-blocks per accumulation chunk (0 -> kChunkKB)
   int lo_bf16;                  // 1: out_lo is a bf16 array (mode 7), same element indexing as out_hi; 3: out_hi and out_lo are
                                 //    fp16 arrays in the split_f16 format (mode 9)
-  const float* wscale;          // [N] per-column power-of-two factor that undoes the weight scaling of mode 9, or nullptr
   // Flattened linears (the B items as one [B * flat_rows][C] matrix, see tc_host.inl): rows past an item's length hold
   // whatever an earlier call left there. They are computed (rows are independent) but neither stored nor allowed to raise
   // the fp16 range flag: row r belongs to item r / flat_rows and is real iff r % flat_rows < flat_len[item].

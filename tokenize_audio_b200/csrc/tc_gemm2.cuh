@@ -48,17 +48,10 @@ __device__ __forceinline__ bool sched_tile(const Sched& sc, const Epilogue& ep, 
   return m0 < Lout;
 }
 
-// i-th k-block to visit -> linear k-block index (tau * cp + channel panel)
+// i-th k-block to visit -> linear k-block index (tau * cp + channel panel), tau = ph + s * dq with dq fastest, then the
+// channel panel, then the tap phase ph. (The GEMM producer walks this order incrementally; this is the closed form.)
 __device__ __forceinline__ int kblock_order(const Sched& sc, int i) {
   if (sc.G <= 1) return i;
-  if (sc.G >= 16) {
-    // variant (G + 16): channel panels innermost -- the cp 128-byte pieces of one input row are fetched back to back
-    // (DRAM page locality), the tap that re-reads the same rows follows cp k-blocks later (still an L2 hit)
-    const int G = sc.G - 16;
-    const int cb = i % sc.cp, t = i / sc.cp;
-    const int dq = t % G, ph = t / G;
-    return (ph + sc.s * dq) * sc.cp + cb;
-  }
   const int dq = i % sc.G, t = i / sc.G;
   const int cb = t % sc.cp, ph = t / sc.cp;
   return (ph + sc.s * dq) * sc.cp + cb;
@@ -125,60 +118,69 @@ __device__ __forceinline__ void prefetch_residual(const Epilogue& ep, int b, int
   }
 }
 
-// Finish a tile: thread (lane) holds acc[0, HALF) = columns ncol0 + [0, HALF) of row row_base + lane. Bias / GELU /
-// LayerScale per thread = per row, transpose through the warp's staging tile `stg`, then row-contiguous float4 residual
-// loads and raw / hi / lo stores (128-byte segments).
-template <int HALF, int PC>
+// Finish a tile: thread (lane) holds acc[0, HALF) = columns ncol0 + [0, HALF) of row row_base + lane.
+//   phase 1 (thread = row): v = acc * cmul[c] + cadd[c] (the per-column affine the host folds weight unscaling, bias and
+//            LayerScale into), GELU(erf) for fc1, into the warp's swizzled staging tile;
+//   phase 2 (lane = one float4 of a row, 32 / LPR rows per instruction): + residual, raw store, ELU, split store -- row-contiguous
+//            64-byte (fp32) / 32-byte (16-bit) segments.
+// Everything that is uniform over the tile (which outputs exist, whether there is a residual / activation) is decided once per
+// PC-column piece, outside the unrolled loops, and the row offsets are computed once per tile: the first version re-tested
+// every flag and rebuilt every 64-bit address per float4 and spent 43 instructions per output element here (ncu, round 2).
+// LOB = 1: split as TF32 hi (fp32) + bf16 lo; LOB = 3: fp16 pair, with the fp16 range check folded into one half2 max per pair.
+template <int HALF, int PC, int LOB>
 __device__ __forceinline__ void finish_tile(const Epilogue& ep, float (&acc)[HALF], int b, int row_base, int ncol0, int Lout,
                                             uint32_t stg, int lane) {
   using G = EpiGeom<HALF, PC>;
   constexpr int NP = G::NP, LPR = G::LPR, RPI = G::RPI, IT = G::IT;
   const int rr = lane / LPR;                     // coalesced phase: row within an RPI-row group
   const int cj = lane % LPR;                     //                  float4 index inside the PC-wide piece
-  const long long raw_base = (long long)b * ep.raw_item_stride + ncol0;
-  const long long split_base = (long long)b * ep.split_item_stride + (long long)ep.split_front * ep.N + ncol0;
   // rows of this thread's coalesced phase that exist (bit `it`): inside the tile's item, and -- in a flattened launch -- inside
-  // the length of the item the row falls into
+  // the length of the item the row falls into; and their element offsets row * N + 4 cj
   uint32_t live = 0;
+  long long roff[IT];
 #pragma unroll
   for (int it = 0; it < IT; ++it) {
     const int row = row_base + it * RPI + rr;
     bool ok = row < Lout;
     if (ok && ep.flat_rows > 0 && ep.flat_len) ok = (row % ep.flat_rows) < __ldg(ep.flat_len + row / ep.flat_rows);
     live |= (uint32_t)ok << it;
+    roff[it] = (long long)row * ep.N + cj * 4;
   }
+  const float* __restrict__ cm = ep.cmul + ncol0;
+  const float* __restrict__ ca = ep.cadd + ncol0;
+  const long long raw_base = (long long)b * ep.raw_item_stride + ncol0;
+  const long long split_base = (long long)b * ep.split_item_stride + (long long)ep.split_front * ep.N + ncol0;
+  const float* resp = ep.res ? ep.res + raw_base : nullptr;
+  float* rawp = ep.out_raw ? ep.out_raw + raw_base : nullptr;
+  const bool do_split = ep.out_hi != nullptr, do_elu = ep.elu_split != 0, do_act = ep.act == 1;
+  const int wkey = (LPR == 8) ? (lane & 7) : ((lane >> 1) & (LPR - 1));
+  __half2 mx2 = __floats2half2_rn(0.f, 0.f);     // LOB 3: running max |hi| of everything this thread stores (range check)
 #pragma unroll
   for (int p = 0; p < NP; ++p) {
     float4 resv[IT];
-    if (ep.res) {
+    if (resp) {
 #pragma unroll
       for (int it = 0; it < IT; ++it) {
-        const int row = row_base + it * RPI + rr;
         resv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if ((live >> it) & 1u) resv[it] = *reinterpret_cast<const float4*>(ep.res + raw_base + (long long)row * ep.N + p * PC + cj * 4);
+        if ((live >> it) & 1u) resv[it] = *reinterpret_cast<const float4*>(resp + roff[it] + p * PC);
       }
     }
-    const int wkey = (LPR == 8) ? (lane & 7) : ((lane >> 1) & (LPR - 1));
+    // ---- phase 1: affine (+ GELU) -> staging tile ----
+    float4 v[LPR];
 #pragma unroll
     for (int j = 0; j < LPR; ++j) {
-      float4 v = make_float4(acc[p * PC + 4 * j], acc[p * PC + 4 * j + 1], acc[p * PC + 4 * j + 2], acc[p * PC + 4 * j + 3]);
-      const int c = ncol0 + p * PC + 4 * j;
-      if (ep.wscale) {
-        const float4 t = ld_nc_f4(ep.wscale + c);
-        v.x *= t.x; v.y *= t.y; v.z *= t.z; v.w *= t.w;
-      }
-      if (ep.bias) {
-        const float4 t = ld_nc_f4(ep.bias + c);
-        v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
-      }
-      if (ep.act == 1) { v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w); }
-      if (ep.scale) {
-        const float4 t = ld_nc_f4(ep.scale + c);
-        v.x *= t.x; v.y *= t.y; v.z *= t.z; v.w *= t.w;
-      }
-      sts128(stg + (uint32_t)(lane * LPR + (j ^ wkey)) * 16u, v);
+      const float4 m = ld_nc_f4(cm + p * PC + 4 * j), a = ld_nc_f4(ca + p * PC + 4 * j);
+      v[j] = make_float4(fmaf(acc[p * PC + 4 * j], m.x, a.x), fmaf(acc[p * PC + 4 * j + 1], m.y, a.y),
+                         fmaf(acc[p * PC + 4 * j + 2], m.z, a.z), fmaf(acc[p * PC + 4 * j + 3], m.w, a.w));
     }
+    if (do_act) {
+#pragma unroll
+      for (int j = 0; j < LPR; ++j) { v[j].x = gelu_erf(v[j].x); v[j].y = gelu_erf(v[j].y); v[j].z = gelu_erf(v[j].z); v[j].w = gelu_erf(v[j].w); }
+    }
+#pragma unroll
+    for (int j = 0; j < LPR; ++j) sts128(stg + (uint32_t)(lane * LPR + (j ^ wkey)) * 16u, v[j]);
     __syncwarp();
+    // ---- phase 2: transposed read, residual, raw store, ELU, split store ----
     float4 tv[IT];
 #pragma unroll
     for (int it = 0; it < IT; ++it) {
@@ -186,22 +188,44 @@ __device__ __forceinline__ void finish_tile(const Epilogue& ep, float (&acc)[HAL
       const int rkey = (LPR == 8) ? (r & 7) : ((r >> 1) & (LPR - 1));
       tv[it] = lds128(stg + (uint32_t)(r * LPR + (cj ^ rkey)) * 16u);
     }
+    if (resp) {
 #pragma unroll
-    for (int it = 0; it < IT; ++it) {
-      const int r = it * RPI + rr;
-      float4 v = tv[it];
-      const int row = row_base + r;
-      if ((live >> it) & 1u) {
-        const long long o = (long long)row * ep.N + p * PC + cj * 4;
-        if (ep.res) { v.x += resv[it].x; v.y += resv[it].y; v.z += resv[it].z; v.w += resv[it].w; }
-        if (ep.out_raw) *reinterpret_cast<float4*>(ep.out_raw + raw_base + o) = v;
-        if (ep.out_hi) {
-          if (ep.elu_split) { v.x = elu_fast(v.x); v.y = elu_fast(v.y); v.z = elu_fast(v.z); v.w = elu_fast(v.w); }
-          store_split4_x(ep.out_hi, ep.out_lo, split_base + o, v, ep.lo_bf16);
+      for (int it = 0; it < IT; ++it) { tv[it].x += resv[it].x; tv[it].y += resv[it].y; tv[it].z += resv[it].z; tv[it].w += resv[it].w; }
+    }
+    if (rawp) {
+#pragma unroll
+      for (int it = 0; it < IT; ++it)
+        if ((live >> it) & 1u) *reinterpret_cast<float4*>(rawp + roff[it] + p * PC) = tv[it];
+    }
+    if (do_split) {
+      if (do_elu) {
+#pragma unroll
+        for (int it = 0; it < IT; ++it) { tv[it].x = elu_fast(tv[it].x); tv[it].y = elu_fast(tv[it].y); tv[it].z = elu_fast(tv[it].z); tv[it].w = elu_fast(tv[it].w); }
+      }
+#pragma unroll
+      for (int it = 0; it < IT; ++it) {
+        const long long o = split_base + roff[it] + p * PC;
+        if (LOB == 3) {
+          const uint32_t h01 = pack_f16x2(tv[it].x, tv[it].y), h23 = pack_f16x2(tv[it].z, tv[it].w);
+          const __half2 g01 = *reinterpret_cast<const __half2*>(&h01), g23 = *reinterpret_cast<const __half2*>(&h23);
+          const float2 f01 = __half22float2(g01), f23 = __half22float2(g23);
+          const uint2 lo2 = make_uint2(pack_f16x2((tv[it].x - f01.x) * kF16LoScale, (tv[it].y - f01.y) * kF16LoScale),
+                                       pack_f16x2((tv[it].z - f23.x) * kF16LoScale, (tv[it].w - f23.y) * kF16LoScale));
+          if ((live >> it) & 1u) {
+            mx2 = __hmax2(mx2, __hmax2(__habs2(g01), __habs2(g23)));
+            *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(ep.out_hi) + o) = make_uint2(h01, h23);
+            *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(ep.out_lo) + o) = lo2;
+          }
+        } else if ((live >> it) & 1u) {
+          store_split4_lob(ep.out_hi + o, reinterpret_cast<uint16_t*>(ep.out_lo) + o, tv[it]);
         }
       }
     }
     __syncwarp();
+  }
+  if (LOB == 3) {
+    // |hi| is inf exactly when the fp32 value was beyond fp16's range (round-to-nearest keeps everything below 65520 finite)
+    if (__hisinf(__low2half(mx2)) || __hisinf(__high2half(mx2))) g_f16_overflow = 1;
   }
 }
 

@@ -17,7 +17,7 @@
 //             (each CTA drains its own TMEM: lanes = its 128 rows). setmaxnreg: 32 / 112 registers -- setmaxnreg only
 //             moves registers inside the CTA's launch allocation (640 x 96 = 128 x 32 + 512 x 112): asking for more
 //             blocks the last warps in setmaxnreg.inc forever.
-//   TMEM    = 2 chunk buffers x BNP columns. One accumulator per chunk: hi*hi, hi*lo and lo*hi all land in it and it is
+//   TMEM    = 2 (BNP = 256) or 4 chunk buffers x BNP columns. One accumulator per chunk: hi*hi, hi*lo and lo*hi all land in it and it is
 //             drained into fp32 registers every K = 128 (round-to-nearest adds), as in tc_gemm2.
 #pragma once
 #include "tc_gemm2.cuh"
@@ -77,7 +77,10 @@ struct Cfg {
   static constexpr int STAGES_RAW = (kSmemMax - 1024 - STG - BAR_BYTES) / STAGE;
   static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
   static constexpr int SMEM = 1024 + STAGES * STAGE + STG + BAR_BYTES;
-  static constexpr int TMEM_COLS = 2 * BNP;
+  // accumulator chunk buffers in TMEM: two for 256-column tiles (all 512 columns); four for the narrower tiles, so that the MMAs
+  // of the next tile (up to 4 chunks = K 512) run while the epilogue warps are busy finishing the previous one
+  static constexpr int NBUF = BNP == 256 ? 2 : 4;
+  static constexpr int TMEM_COLS = NBUF * BNP;
   static constexpr int HALF = BNP / (kEpiWarps / 4);                 // accumulator columns per epilogue thread
   static_assert(BNP == 64 || BNP == 128 || BNP == 256, "BNP");
   static_assert(STAGES >= 3, "ring too shallow");
@@ -174,9 +177,10 @@ tcp_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   uint8_t* stg_base = smem + STAGES * STAGE;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg_base + C::STG);   // used in the leader only
   uint64_t* empty_bar = full_bar + STAGES;                                // one per CTA (multicast commit)
-  uint64_t* acc_full = empty_bar + STAGES;                                // [2] one per CTA (multicast commit)
-  uint64_t* acc_empty = acc_full + 2;                                     // [2] leader only: both CTAs' epilogue warps arrive
-  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  constexpr uint32_t NBUF = C::NBUF;
+  uint64_t* acc_full = empty_bar + STAGES;                                // [NBUF] one per CTA (multicast commit)
+  uint64_t* acc_empty = acc_full + NBUF;                                  // [NBUF] leader only: both CTAs' epilogue warps arrive
+  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(acc_empty + NBUF);
 
   const int warp = tc::uniform_warp_idx(), lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -191,7 +195,7 @@ tcp_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     tc::prefetch_tmap(&tmA_hi); tc::prefetch_tmap(&tmA_lo); tc::prefetch_tmap(&tmW_hi); tc::prefetch_tmap(&tmW_lo);
     tc::prefetch_tmap(&tmW_3);
     for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) {
+    for (uint32_t s = 0; s < NBUF; ++s) {
       tc::mbar_init(&acc_full[s], 1);
       tc::mbar_init(&acc_empty[s], 2 * kEpiWarps);
     }
@@ -233,50 +237,54 @@ tcp_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       if (tc::elect_one()) {
         const uint32_t full_leader = mapa(tc::smem_u32(full_bar), 0);
         const uint32_t smem_u = tc::smem_u32(smem);
-        uint32_t kbc = 0;
+        // The producer is ONE thread; every instruction between two TMA issues is on the critical path of the narrow layers
+        // (a k-block of a 128-column pair tile is only 384 clocks of MMA work). Ring position and k-block order are therefore
+        // walked incrementally: no division or modulo per k-block (the first version spent ~200 instructions per k-block here and
+        // starved the tensor pipe of D1 / R2a: epilogue warps waited 15 % of their samples for accumulators).
+        uint32_t s = 0, ring_phase = 0;
         for (int pid = cid; pid < npairs; pid += ncl) {
           int b, m0, n0, Lout;
           bool mine;
           if (!decode_pair(pid, b, m0, n0, Lout, mine)) continue;
           const int wrow = n0 + (int)rank * C::WB;
-          for (int kb = 0; kb < nkb; ++kb, ++kbc) {
-            const uint32_t s = kbc % STAGES;
-            TCP_MARK(6, kbc | 0x80000000u);
-            tc::mbar_wait(&empty_bar[s], ((kbc / STAGES) & 1u) ^ 1u);
-            TCP_MARK(1, kbc + 1);
+          int dq = 0, cb = 0, ph = 0;                      // tap group, channel panel, tap phase of the next k-block (Sched::G > 1)
+          for (int kb = 0; kb < nkb; ++kb) {
+            int kx = kb * kBK;
+            if (sc.G > 1) {                                // i-th k-block visited = (ph + s * dq) * cp + cb, dq fastest (tc2::kblock_order)
+              kx = ((ph + sc.s * dq) * sc.cp + cb) * kBK;
+              if (++dq == sc.G) { dq = 0; if (++cb == sc.cp) { cb = 0; ++ph; } }
+            }
+            tc::mbar_wait(&empty_bar[s], ring_phase ^ 1u);
             if (rank == 0) tc::mbar_expect_tx(&full_bar[s], 2 * STAGE);
             const uint32_t st = smem_u + s * STAGE;
             const uint32_t fb = full_leader + 8u * s;
-            const int kx = tc2::kblock_order(sc, kb) * kBK;
             tma_load_3d_pair(st, &tmA_hi, fb, kx, m0, b);
             tma_load_3d_pair(st + C::OFF_ALO, &tmA_lo, fb, kx, m0, b);
             tma_load_2d_pair(st + C::OFF_WHI, &tmW_hi, fb, kx, wrow);
             tma_load_2d_pair(st + C::OFF_WLO, &tmW_lo, fb, kx, wrow);
             tma_load_2d_pair(st + C::OFF_W3, &tmW_3, fb, kx, wrow);
+            if (++s == STAGES) { s = 0; ring_phase ^= 1u; }
           }
         }
       }
     } else if (warp == 1 && rank == 0) {
       constexpr uint32_t idesc = tc::make_idesc(2 * kBM, BNP);
       const uint32_t smem_base_u32 = tc::smem_u32(smem);
-      uint32_t kbc = 0, cc = 0;
+      uint32_t s = 0, ring_phase = 0, cc = 0;
       for (int pid = cid; pid < npairs; pid += ncl) {
         int b, m0, n0, Lout;
         bool mine;
         if (!decode_pair(pid, b, m0, n0, Lout, mine)) continue;
         for (int c = 0; c < nchunks; ++c, ++cc) {
-          const uint32_t buf = cc & 1u;
+          const uint32_t buf = cc % NBUF;
           if (lane == 0) TCP_MARK(3, cc | 0x80000000u);
-          tc::mbar_wait(&acc_empty[buf], ((cc >> 1) & 1u) ^ 1u);         // drained (by both CTAs) two chunks ago
+          tc::mbar_wait(&acc_empty[buf], ((cc / NBUF) & 1u) ^ 1u);       // drained (by both CTAs) NBUF chunks ago
           if (lane == 0) TCP_MARK(3, cc + 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t tmem_acc = tmem_base + buf * BNP;
           const int kb_end = min(nkb, (c + 1) * ckb);
-          for (int kb = c * ckb; kb < kb_end; ++kb, ++kbc) {
-            const uint32_t s = kbc % STAGES;
-            if (lane == 0) TCP_MARK(7, kbc | 0x80000000u);
-            tc::mbar_wait(&full_bar[s], (kbc / STAGES) & 1u);
-            if (lane == 0) TCP_MARK(2, kbc + 1);
+          for (int kb = c * ckb; kb < kb_end; ++kb) {
+            tc::mbar_wait(&full_bar[s], ring_phase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t d_ahi = tc::desc_lo(smem_base_u32 + s * STAGE);
             constexpr uint32_t kAlo = C::OFF_ALO >> 4, kWhi = C::OFF_WHI >> 4, kWlo = C::OFF_WLO >> 4, kW3 = C::OFF_W3 >> 4;
@@ -305,6 +313,7 @@ tcp_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
               if (kb + 1 == kb_end) umma_commit_pair(&acc_full[buf]);
             }
             __syncwarp();
+            if (++s == STAGES) { s = 0; ring_phase ^= 1u; }
           }
         }
       }
@@ -328,9 +337,9 @@ tcp_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       for (int i = 0; i < HALF; ++i) acc[i] = 0.f;
       if (mine) tc2::prefetch_residual<HALF, C::PC>(ep, b, m0 + quarter * 32, n0 + col0, Lout, lane);
       for (int c = 0; c < nchunks; ++c, ++cc) {
-        const uint32_t buf = cc & 1u;
+        const uint32_t buf = cc % NBUF;
         if (threadIdx.x == 32 * kEW0) TCP_MARK(4, cc | 0x80000000u);
-        tc::mbar_wait(&acc_full[buf], (cc >> 1) & 1u);
+        tc::mbar_wait(&acc_full[buf], (cc / NBUF) & 1u);
         if (threadIdx.x == 32 * kEW0) TCP_MARK(4, cc + 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         tc2::drain_add<HALF>(tmem_base + lane_off + buf * BNP + (uint32_t)col0, acc);
@@ -338,7 +347,7 @@ tcp_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster_relaxed(acc_empty_leader + 8u * buf);
       }
-      if (mine) tc2::finish_tile<HALF, C::PC>(ep, acc, b, m0 + quarter * 32, n0 + col0, Lout, stg, lane);
+      if (mine) tc2::finish_tile<HALF, C::PC, LOB>(ep, acc, b, m0 + quarter * 32, n0 + col0, Lout, stg, lane);
       if (threadIdx.x == 32 * kEW0) TCP_MARK(5, pid + 1);
     }
   }

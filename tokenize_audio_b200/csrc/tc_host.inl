@@ -42,7 +42,10 @@ static int tc_make_map_bf16(mimi_b200* h, CUtensorMap* out, const void* base, in
 
 // w_nk: host [N][K] K-major. Mode 7: TF32 hi / lo (fp32) and bf16(hi), uploaded with one map per box height (128, 64, 32
 // rows: the pair GEMM stages bnp / 2 weight rows per CTA); map_hi / map_lo (box BN) serve the fused front end.
-static int tc_make_weight(mimi_b200* h, TcWeight* w, const std::vector<float>& w_nk, int N, int K) {
+// `bias` / `scale` (host [N] or nullptr): folded with the mode-9 weight unscaling into the per-column affine of the epilogue,
+//   out = act(acc * cmul + cadd):  cmul = unscale * scale,  cadd = bias * scale   (scale = LayerScale of o_proj / fc2)
+static int tc_make_weight(mimi_b200* h, TcWeight* w, const std::vector<float>& w_nk, int N, int K, const float* bias = nullptr,
+                          const float* scale = nullptr) {
   std::vector<float> hi(w_nk.size()), lo(w_nk.size());
   for (size_t i = 0; i < w_nk.size(); ++i) split_tf32(w_nk[i], hi[i], lo[i]);
   int rc;
@@ -101,7 +104,14 @@ static int tc_make_weight(mimi_b200* h, TcWeight* w, const std::vector<float>& w
     CUDA_TRY(h, cudaMalloc((void**)&w->f16, f.size() * sizeof(uint16_t)));
     h->allocs.push_back(w->f16);
     CUDA_TRY(h, cudaMemcpy(w->f16, f.data(), f.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
-    if ((rc = dev_upload(h, &w->wscale, ws))) return rc;
+    std::vector<float> cm7(N), cm9(N), ca(N);
+    for (int n = 0; n < N; ++n) {
+      const float ls = scale ? scale[n] : 1.0f;
+      cm7[n] = ls; cm9[n] = ws[n] * ls; ca[n] = (bias ? bias[n] : 0.0f) * ls;
+    }
+    if ((rc = dev_upload(h, &w->cmul[0], cm7))) return rc;
+    if ((rc = dev_upload(h, &w->cmul[1], cm9))) return rc;
+    if ((rc = dev_upload(h, &w->cadd, ca))) return rc;
     for (int part = 0; part < 3; ++part)
       for (int r = 0; r < 3; ++r) {
         if (rows[r] > N) continue;
@@ -125,7 +135,8 @@ static int tc_load_weights(mimi_b200* h, const mimi_b200_weights_t* w) {
   if ((rc = tc_init_driver(h))) return rc;
   for (int i = 1; i < MIMI_B200_NUM_CONVS; ++i) {
     const ConvGeom& g = kConv[i];
-    if ((rc = tc_make_weight(h, &h->tc_conv[i], pack_conv_nk(w->conv_weight[i], g.cout, g.cin, g.k), g.cout, g.cin * g.k))) return rc;
+    if ((rc = tc_make_weight(h, &h->tc_conv[i], pack_conv_nk(w->conv_weight[i], g.cout, g.cin, g.k), g.cout, g.cin * g.k,
+                             w->conv_bias[i]))) return rc;
   }
   for (int l = 0; l < MIMI_B200_NUM_LAYERS; ++l) {
     const mimi_b200_layer_weights_t& s = w->layer[l];
@@ -134,9 +145,11 @@ static int tc_load_weights(mimi_b200* h, const mimi_b200_weights_t* w) {
     std::memcpy(qkv.data() + 512 * 512, s.k_proj_weight, sizeof(float) * 512 * 512);
     std::memcpy(qkv.data() + 2 * 512 * 512, s.v_proj_weight, sizeof(float) * 512 * 512);
     if ((rc = tc_make_weight(h, &h->tc_qkv[l], qkv, 1536, 512))) return rc;
-    if ((rc = tc_make_weight(h, &h->tc_o[l], std::vector<float>(s.o_proj_weight, s.o_proj_weight + 512 * 512), 512, 512))) return rc;
+    if ((rc = tc_make_weight(h, &h->tc_o[l], std::vector<float>(s.o_proj_weight, s.o_proj_weight + 512 * 512), 512, 512, nullptr,
+                             s.self_attn_layer_scale))) return rc;
     if ((rc = tc_make_weight(h, &h->tc_fc1[l], std::vector<float>(s.fc1_weight, s.fc1_weight + 2048 * 512), 2048, 512))) return rc;
-    if ((rc = tc_make_weight(h, &h->tc_fc2[l], std::vector<float>(s.fc2_weight, s.fc2_weight + 512 * 2048), 512, 2048))) return rc;
+    if ((rc = tc_make_weight(h, &h->tc_fc2[l], std::vector<float>(s.fc2_weight, s.fc2_weight + 512 * 2048), 512, 2048, nullptr,
+                             s.mlp_layer_scale))) return rc;
   }
   if ((rc = tc_make_weight(h, &h->tc_down, pack_conv_nk(w->downsample_weight, 512, 512, 4), 512, 2048))) return rc;
   std::vector<float> pj((size_t)512 * 512);
@@ -233,16 +246,14 @@ struct TcOut {
   long long raw_item_stride = 0;
   const SplitBuf* split = nullptr; // split output
   int elu_split = 0;
-  const float* bias = nullptr;
-  const float* scale = nullptr;
-  int act = 0;
+  int act = 0;                     // (bias and LayerScale live in the weight's per-column affine)
 };
 
 // k-block order of a conv with k taps, stride s over C_in channels (tc2::Sched): taps grouped by tau mod s
 static void tc_korder(const mimi_b200* h, tc2::Sched& sc, int k, int s, int cin) {
   sc.G = 0; sc.s = 0; sc.cp = 0;
   if (h->exp_linear_k == 1 || s <= 1 || k <= s || k % s || cin % 32) return;   // s = 1 (k = 3): taps are 1 row apart, L2 hits anyway
-  sc.G = k / s + (h->exp_linear_k == 2 ? 16 : 0); sc.s = s; sc.cp = cin / 32;
+  sc.G = k / s; sc.s = s; sc.cp = cin / 32;
 }
 
 // the CTA-pair GEMM (tc_gemm5.cuh): pair tiles of 2 x 128 rows x BNP columns. Every layer of the network has N % 64 == 0.
@@ -250,9 +261,13 @@ static int launch_tcp(mimi_b200* h, const CUtensorMap& ahi, const CUtensorMap& a
                       int B, int mt_max, cudaStream_t st, int k = 1, int s = 1, int cin = 0, const int* tiles = nullptr,
                       int ntiles = 0) {
   if (w.N % 64) return fail(h, MIMI_B200_ERR_ARG, "tc: the pair GEMM needs N % 64 == 0");
-  // 256-column pair tiles unless the layer is so deep (K) and narrow in rows that a tile is a large share of a cluster's
-  // whole job: exp_pair_n128 = N threshold from which 128-column tiles are used (0 = never)
-  const int bnp = (w.N % 256 == 0 && !(h->exp_pair_n128 > 0 && w.N >= h->exp_pair_n128)) ? 256 : (w.N % 128 == 0) ? 128 : 64;
+  // Pair tiles of 256 columns for the deep layers (K > 2048: D3, D4, F -- the tensor pipe is the bound and a 256-wide tile reads
+  // every operand byte once per 256 x 256 MMA), 128 columns for everything else: those layers are bound by the tile finish, and
+  // a 128-column tile leaves TMEM room for four accumulator chunks, so the MMAs of the next tile run under the finish of the
+  // previous one (measured on C2: fc1 -17 %, QKV -9 %, o_proj -15 %, fc2 -8 %, D1 -13 %; D3 / D4 +6 / +11 % if forced to 128).
+  // debug_set key 9 = 1 restores 256 columns wherever N allows.
+  const bool wide = w.N % 256 == 0 && (w.K > 2048 || h->exp_pair_n128 == 1);
+  const int bnp = wide ? 256 : (w.N % 128 == 0) ? 128 : 64;
   tcp::Sched sc{B, mt_max, w.N / bnp};
   tc_korder(h, sc, k, s, cin);
   sc.tiles = tiles; sc.ntiles = ntiles;
@@ -291,14 +306,14 @@ static int tc_gemm(TcCtx& c, int slot, const SplitBuf& a, int k, int s, int pad,
   if ((rc = tc_amaps(c, slot, a, k, s, pad, flat, &ahi, &alo))) return rc;
   if (w.K != k * a.C) return fail(c.h, MIMI_B200_ERR_ARG, "tc: weight K mismatch");
   tc::Epilogue ep{};
-  ep.bias = o.bias; ep.scale = o.scale; ep.res = o.res; ep.out_raw = o.raw; ep.raw_item_stride = o.raw_item_stride;
+  ep.cmul = w.cmul[c.h->mode == 9 ? 1 : 0]; ep.cadd = w.cadd;
+  ep.res = o.res; ep.out_raw = o.raw; ep.raw_item_stride = o.raw_item_stride;
   if (o.split) {
     if (o.split->C != w.N) return fail(c.h, MIMI_B200_ERR_ARG, "tc: split output width mismatch");
     ep.out_hi = c.ws + o.split->hi; ep.out_lo = c.ws + o.split->lo;
     ep.split_item_stride = o.split->item_stride; ep.split_front = o.split->front;
   }
   ep.act = o.act; ep.elu_split = o.elu_split; ep.lo_bf16 = c.h->mode == 9 ? 3 : 1;
-  ep.wscale = c.h->mode == 9 ? w.wscale : nullptr;
   ep.chunk_kb = c.h->exp_chunk_kb;
   ep.len_in = c.dlen[a.level]; ep.uniform_len_in = c.maxlen[a.level]; ep.conv_stride = s; ep.N = w.N;
   int lout_max = (c.maxlen[a.level] + s - 1) / s;
@@ -390,21 +405,21 @@ static int encode_tc(mimi_b200* h, const float* d_input, int B, long long N, int
     const int id = 3 + 3 * s, ia = 4 + 3 * s, ib = 5 + 3 * s;
     const ConvGeom& gd = kConv[id];
     TcOut o;   // down conv: raw (skip) + ELU'd split (resblock conv a)
-    o.raw = ws + L.d_raw; o.raw_item_stride = rstride(s + 1, L.C); o.split = L.s_d; o.elu_split = 1; o.bias = h->conv_b[id];
+    o.raw = ws + L.d_raw; o.raw_item_stride = rstride(s + 1, L.C); o.split = L.s_d; o.elu_split = 1;
     if ((rc = tc_gemm(c, id, *L.in, gd.k, gd.stride, gd.k - gd.stride, h->tc_conv[id], o, id))) return rc;
     o = TcOut{};   // resblock conv a: C -> C/2, k3
-    o.split = L.s_r; o.elu_split = 1; o.bias = h->conv_b[ia];
+    o.split = L.s_r; o.elu_split = 1;
     if ((rc = tc_gemm(c, ia, *L.s_d, 3, 1, 2, h->tc_conv[ia], o, ia))) return rc;
     o = TcOut{};   // resblock conv b: C/2 -> C, k1, + skip; only ELU(h) is needed downstream
-    o.res = ws + L.d_raw; o.raw_item_stride = rstride(s + 1, L.C); o.split = L.s_h; o.elu_split = 1; o.bias = h->conv_b[ib];
+    o.res = ws + L.d_raw; o.raw_item_stride = rstride(s + 1, L.C); o.split = L.s_h; o.elu_split = 1;
     if ((rc = tc_gemm(c, ib, *L.s_r, 1, 1, 0, h->tc_conv[ib], o, ib))) return rc;
   }
   {
     TcOut o;   // D4: 512 -> 1024, k16 s8
-    o.split = &p.s_d4; o.elu_split = 1; o.bias = h->conv_b[12];
+    o.split = &p.s_d4; o.elu_split = 1;
     if ((rc = tc_gemm(c, 12, p.s_h4, 16, 8, 8, h->tc_conv[12], o, 12))) return rc;
     o = TcOut{};   // F: 1024 -> 512, k3 -> transformer stream z (raw)
-    o.raw = ws + p.z; o.raw_item_stride = rstride(4, 512); o.bias = h->conv_b[13];
+    o.raw = ws + p.z; o.raw_item_stride = rstride(4, 512);
     if ((rc = tc_gemm(c, 13, p.s_d4, 3, 1, 2, h->tc_conv[13], o, 13))) return rc;
   }
   // ---- encoder transformer -------------------------------------------------------------------------------------
@@ -429,7 +444,7 @@ static int encode_tc(mimi_b200* h, const float* d_input, int B, long long N, int
       CUDA_TRY(h, cudaGetLastError());
     }
     o = TcOut{};   // o_proj + LayerScale + residual, in place on z
-    o.raw = ws + p.z; o.res = ws + p.z; o.raw_item_stride = rstride(4, 512); o.scale = d.ls1;
+    o.raw = ws + p.z; o.res = ws + p.z; o.raw_item_stride = rstride(4, 512);
     if ((rc = tc_gemm(c, 1, p.s_att, 1, 1, 0, h->tc_o[l], o, 17))) return rc;
     layernorm512_kernel<<<lgrid, 256, 0, st>>>(ws + p.z, ws + p.s_y.hi, d.ln2_w, d.ln2_b, rstride(4, 512), dlen[4], T25, ws + p.s_y.lo, lob);
     h->launches++; mark(h, 14, st);
@@ -437,7 +452,7 @@ static int encode_tc(mimi_b200* h, const float* d_input, int B, long long N, int
     o.split = &p.s_ffn; o.act = 1;
     if ((rc = tc_gemm(c, 0, p.s_y, 1, 1, 0, h->tc_fc1[l], o, 18))) return rc;
     o = TcOut{};   // fc2 + LayerScale + residual, in place on z
-    o.raw = ws + p.z; o.res = ws + p.z; o.raw_item_stride = rstride(4, 512); o.scale = d.ls2;
+    o.raw = ws + p.z; o.res = ws + p.z; o.raw_item_stride = rstride(4, 512);
     if ((rc = tc_gemm(c, 2, p.s_ffn, 1, 1, 0, h->tc_fc2[l], o, 19))) return rc;
   }
   // ---- stride-2 downsample (replicate pad materialised as 3 extra rows), RVQ input projections ------------------
