@@ -606,7 +606,7 @@ class MimiEncoder:
         with self._lock:
             for j, slot in enumerate(self._slots):
                 self._grow(slot, batch * max_samples, batch * K * (-(-max_samples // FRAME_SIZE)) * 8)
-                if j == 0 or self.slot_streams:
+                if j == 0 or (self.slot_streams and self._two_workspaces_fit(batch, max_samples, K)):
                     self.model.reserve_workspace(batch, max_samples, K, slot=j)
 
     def _grow(self, slot: _Staging, samples: int, out_bytes: int) -> None:
@@ -757,7 +757,7 @@ class MimiEncoder:
             slot = self._next_slot() if _slot is None else _slot
             caller, copy = self._streams()
             main, ws_slot = caller, 0
-            if self.slot_streams and _slot is None:
+            if self.slot_streams and _slot is None and self._two_workspaces_fit(B, max(lengths), K):
                 if self._slot_stream[slot.index] is None:
                     self._slot_stream[slot.index] = torch.cuda.Stream(device=self.model.device)
                 main, ws_slot = self._slot_stream[slot.index], slot.index
@@ -819,6 +819,16 @@ class MimiEncoder:
             if _slot is None:
                 slot.pending = p
             return p
+
+    def _two_workspaces_fit(self, B: int, N: int, K: int) -> bool:
+        """One workspace per staging slot costs twice the activation memory (~23 MB per padded audio-second each): only when
+        both fit comfortably (a B = 64 x 60 s batch needs 90 GB per workspace -- that one runs on a single stream)."""
+        nbytes = C.c_size_t()
+        with self.model._lock, torch.cuda.device(self.model.device):
+            rc = self.model._lib.mimi_b200_workspace_bytes(self.model._h, int(B), int(N), int(K), C.byref(nbytes))
+        _lib.check(self.model._lib, self.model._h, rc, "mimi_b200_workspace_bytes")
+        total = torch.cuda.get_device_properties(self.model.device).total_memory
+        return 2 * nbytes.value <= 0.6 * total
 
     def _mark_front_done(self, slot: _Staging, stream: torch.cuda.Stream) -> None:
         slot.front_done = torch.cuda.Event()
