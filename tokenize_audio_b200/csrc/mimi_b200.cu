@@ -1236,8 +1236,6 @@ int mimi_b200_codes_to_utf8(mimi_b200_t* h, const int64_t* d_codes, int B, int K
   Utf8Params p{};
   p.codes = reinterpret_cast<const long long*>(d_codes); p.B = B; p.K = K; p.T = T; p.offset = off; p.codebook_size = cbs;
   p.bytes_per_frame = (int)bpf; p.out = d_out; p.out_stride = out_stride; p.frames = nullptr;
-  int o = 0;
-  for (int k = 0; k < K; ++k) { p.byte_off[k] = (unsigned char)o; o += utf8_len(off + (unsigned)k * cbs); }
   int64_t maxfr = T;
   if (h_frames) {
     std::vector<int> v(B);
@@ -1258,8 +1256,8 @@ int mimi_b200_codes_to_utf8(mimi_b200_t* h, const int64_t* d_codes, int B, int K
     for (int b = 0; b < B; ++b) h_out_len_opt[b] = (h_frames ? h_frames[b] : T) * bpf;
   if (maxfr == 0) return MIMI_B200_OK;
   if (!d_codes || !d_out) return fail(h, MIMI_B200_ERR_ARG, "codes_to_utf8: NULL device pointer");
-  dim3 grid((unsigned)((maxfr * K + 255) / 256), B);
-  codes_to_utf8_kernel<<<grid, 256, 0, st>>>(p);
+  dim3 grid((unsigned)((maxfr + kUtf8Frames - 1) / kUtf8Frames), B);
+  codes_to_utf8_kernel<<<grid, kUtf8Frames, (size_t)kUtf8Frames * bpf + 32, st>>>(p);
   h->launches++;
   if (h_frames) CUDA_TRY(h, cudaEventRecord(h->dev_ints_ev, st));
   CUDA_TRY(h, cudaGetLastError());
