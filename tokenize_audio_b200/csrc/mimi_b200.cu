@@ -6,6 +6,8 @@
 #include <cudaTypedefs.h>
 #include <cuda_runtime.h>
 
+#include <emmintrin.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -1067,9 +1069,34 @@ class PackPool {
   }
 
  private:
+  // Streaming (non-temporal) stores: the pinned rows are written once and then read by the DMA engine, never by this core,
+  // so a regular store would first read every destination line into the cache (read-for-ownership): 3 bytes of host memory
+  // traffic per byte staged instead of 2. With 8 ranks staging ~3 GB/s each on one NUMA node that traffic is what bounds the
+  // end-to-end rate at 8 GPUs.
+  static void stream_copy(float* dst, const float* src, size_t n) {
+    size_t i = 0;
+    while (i < n && (reinterpret_cast<uintptr_t>(dst + i) & 15)) { dst[i] = src ? src[i] : 0.f; ++i; }
+    if (src) {
+      for (; i + 16 <= n; i += 16) {
+        const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i));
+        const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i + 4));
+        const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i + 8));
+        const __m128i d = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i + 12));
+        _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i), a);
+        _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 4), b);
+        _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 8), c);
+        _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 12), d);
+      }
+    } else {
+      const __m128i z = _mm_setzero_si128();
+      for (; i + 4 <= n; i += 4) _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i), z);
+    }
+    for (; i < n; ++i) dst[i] = src ? src[i] : 0.f;
+  }
   static void exec(const PackJob& j) {
-    if (j.copy_floats) memcpy(j.dst, j.src, j.copy_floats * sizeof(float));
-    if (j.zero_floats) memset(j.dst + j.copy_floats, 0, j.zero_floats * sizeof(float));
+    if (j.copy_floats) stream_copy(j.dst, j.src, j.copy_floats);
+    if (j.zero_floats) stream_copy(j.dst + j.copy_floats, nullptr, j.zero_floats);
+    _mm_sfence();                     // the streamed lines are globally visible before the job counts as done
   }
   void work() {
     for (;;) {
