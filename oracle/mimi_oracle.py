@@ -1,10 +1,10 @@
 """ORACLE (test infrastructure, NOT product code): CPU/numpy restatement of the Mimi encode path.
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline leg may import this
-module; the product package ``tokenize_audio_b200`` never does (tests/test_no_oracle_in_product.py
-enforces it).
+module; the product package ``tokenize_audio_b200`` never does
+(tests/test_host_logic.py::test_product_never_imports_the_oracle enforces it).
 
-What it restates: ``transformers.MimiModel.encode`` (transformers 5.5.0, a third-party dependency
+What it restates: ``transformers.MimiModel.encode`` and ``MimiModel.decode`` (transformers 5.5.0, a third-party dependency
 of potsawee/tokenize-audio that is NOT vendored under /root/reference; call sites
 REF/emilia-mimi/process_shard.py:81-84,124-127 and REF/*/utils.py:64). ``TF`` below means
 ``transformers/models/mimi/modeling_mimi.py``. Every function cites the lines it follows.

@@ -105,7 +105,7 @@ def test_config5_codes_to_unicode_after_encode(b200_model):
 
 
 def test_sw128_descriptor_row_shift_property():
-    """The hardware property front_fused.cuh / tc_gemm3.cuh rely on: a SWIZZLE_128B K-major operand descriptor may
+    """The hardware property front_fused.cuh relies on: a SWIZZLE_128B K-major operand descriptor may
     start at any whole 128-byte row of a staged tile when its base-offset field is 0."""
     lib = _lib.load_library()
     h = C.c_void_p()

@@ -173,7 +173,7 @@ struct mimi_b200 {
   int phase = 0, front_b0 = 0, front_b1 = 0;   // mimi_b200_encode_phase: which part of the pipeline the call in flight runs
   int exp_linear_k = 0;                        // debug_set key 11: k-blocks in linear order (no tap grouping)
   int exp_no_flat = 0;                         // debug_set key 10: never flatten the linears' row dimension across items
-  int num_clusters = 74;                       // co-resident CTA pairs of the cta_group::2 GEMM (tc_gemm5.cuh, mode 6)
+  int num_clusters = 74;                       // co-resident CTA pairs of the cta_group::2 GEMM (tc_gemm5.cuh)
   int exp_pair_n128 = 0;                       // debug_set key 9: 1 = 256-column pair tiles wherever N allows (default: only for K > 2048)
   PFN_cuTensorMapEncodeTiled_v12000 encode_tiled = nullptr;
   TcWeight tc_conv[MIMI_B200_NUM_CONVS];       // convs 1..13 (conv 0 is a direct SIMT conv)
