@@ -51,6 +51,45 @@ def test_every_mode_matches_the_oracle(b200_model, case, mode):
         assert np.array_equal(rag[i, :, :t], codes[i, :, :t])          # ragged == strict on kept frames, every mode
 
 
+def test_front_end_and_attention_schedule_variants_agree(b200_model, case):
+    """The fp16 front end (front_f16.cuh, default) against round 1's front end with TF32 internals (debug knob 17), and the
+    attention kernel's compact reversed unit list against its grid walk (knob 18; ragged calls only): same codes, latents
+    within the tolerance of either against the oracle. The 13-sample and 127-sample items put item ends inside the first
+    front-end tile, right before a tile boundary (126) and right after it."""
+    x, lens, ref, lat_ref = case
+    xd = torch.from_numpy(x).cuda()
+    out = {}
+    for name, knob in (("default", None), ("front_tf32", 17), ("att_grid", 18)):
+        if knob is not None:
+            b200_model.debug_set(knob, 1)
+        try:
+            o, lat = b200_model.encode(xd, num_quantizers=32, return_latent=True)
+            rag = b200_model.encode(xd, num_quantizers=32, valid_lengths=lens).audio_codes.cpu().numpy()
+            out[name] = (o.audio_codes.cpu().numpy(), lat.cpu().numpy(), rag)
+        finally:
+            if knob is not None:
+                b200_model.debug_set(knob, 0)
+    for name, (codes, lat, rag) in out.items():
+        assert _rel(lat, lat_ref) <= 2e-5, name
+        assert (codes == ref).mean() >= 0.999, name
+        for i, n in enumerate(lens):
+            t = -(-n // 1920)
+            assert np.array_equal(rag[i, :, :t], codes[i, :, :t]), name
+    assert np.array_equal(out["default"][2], out["att_grid"][2])            # the schedule changes no arithmetic
+    assert (out["default"][0] == out["front_tf32"][0]).mean() >= 0.999
+    # tile-boundary lengths of the front end's item-major tile walk, ragged against strict
+    short = [13, 126, 127, 1920 * 2 + 5, 252, 1]
+    n = max(short)
+    xs = np.zeros((len(short), 1, n), np.float32)
+    for i, m in enumerate(short):
+        xs[i, 0, :m] = synth.synth_speech(850 + i, m)
+    a = b200_model.encode(torch.from_numpy(xs).cuda(), num_quantizers=8).audio_codes.cpu().numpy()
+    r = b200_model.encode(torch.from_numpy(xs).cuda(), num_quantizers=8, valid_lengths=short).audio_codes.cpu().numpy()
+    for i, m in enumerate(short):
+        t = -(-m // 1920)
+        assert np.array_equal(r[i, :, :t], a[i, :, :t])
+
+
 def test_tensor_core_rvq_matches_simt_rvq(b200_model):
     """mode 0 (fused SIMT RVQ, exact fp32 FFMA distances, on the all-fp32 pipeline) vs the default generation (tensor-core
     RVQ): the codes may differ only through near-ties (<= 0.1 % of slots)."""

@@ -51,6 +51,18 @@ def test_golden_vectors_from_transformers(b200_model, name):
     assert _rel(lat.cpu().numpy(), g["latent"]) <= LATENT_REL_TOL
 
 
+def _assert_flips_explained(codes, ref, mg, what=""):
+    """Every mismatch is an argmin near-tie of the ORACLE itself (its top-2 relative margin < NEAR_TIE: fp32 rounding decides
+    it in the reference too) or lies below such a flip in the same frame (the residual chain cascades); at most 2 % of the
+    frames may hold one."""
+    agree = codes == ref
+    for b, k, t in np.argwhere(~agree):
+        first_bad = int(np.argmax(~agree[b, :, t]))
+        assert k > first_bad or mg[b, k, t] < NEAR_TIE, f"{what}: unexplained flip item {b} cb {k} frame {t} margin {mg[b, k, t]:.2e}"
+    bad_frames = int((~agree).any(axis=1).sum())
+    assert bad_frames <= max(1, agree.shape[0] * agree.shape[2] // 50), f"{what}: {bad_frames} frames with flips"
+
+
 def test_against_oracle_with_flip_classification(b200_model, state_dict):
     N = 24000 + 4321
     x = np.stack([synth.synth_speech(11, N), synth.synth_speech(12, N)])[:, None, :]
@@ -128,8 +140,9 @@ def test_wrapper_chunk_and_batch(b200_model, state_dict):
     audio = [synth.synth_speech(70, 20000), synth.synth_speech(71, 33333), synth.synth_speech(72, 5000)]
     single = enc.encode_audio_chunk(audio[0])
     assert single.shape == (32, 11) and single.dtype == np.int64
-    ref0 = O.encode(state_dict, audio[0][None, None, :], 32)[0]
-    assert (single == ref0).mean() >= CODE_AGREEMENT
+    mg0 = []
+    ref0 = O.encode(state_dict, audio[0][None, None, :], 32, margins=mg0)[0]
+    _assert_flips_explained(single[None], ref0[None], np.stack(mg0).reshape(1, 32, -1), "chunk")
     batch = enc.encode_audio_batch(audio)
     assert [c.shape for c in batch] == [(32, 11), (32, 18), (32, 3)]
     # reference batch semantics: pad with zeros to the longest, encode, trim
@@ -137,9 +150,14 @@ def test_wrapper_chunk_and_batch(b200_model, state_dict):
     x = np.zeros((3, 1, n), np.float32)
     for i, a in enumerate(audio):
         x[i, 0, : len(a)] = a
-    ref = O.encode(state_dict, x, 32)
+    mgs = []
+    ref = O.encode(state_dict, x, 32, margins=mgs)
+    mg = np.stack(mgs).reshape(3, 32, -1)
+    # (item 1, frame 3, codebook 6 is an EXACT tie of the reference's fp32 distances: margin 0.0; which of the two codes comes
+    #  out depends on the last bit of the latent, and everything below it in that frame follows)
     for i, c in enumerate(batch):
-        assert (c == ref[i, :, : c.shape[1]]).mean() >= CODE_AGREEMENT
+        t = c.shape[1]
+        _assert_flips_explained(c[None], ref[i : i + 1, :, :t], mg[i : i + 1, :, :t], f"item {i}")
     assert enc.encode_audio_batch([]) == []
     enc_strict = MimiEncoder(b200_model, ragged=False)
     for a, b_ in zip(enc_strict.encode_audio_batch(audio), batch):

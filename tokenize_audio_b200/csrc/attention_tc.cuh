@@ -54,6 +54,12 @@ struct Params {
   int B;
   int mt_max;                  // query tiles per item at the longest item
   int lo_bf16;                 // 1: out_lo is a bf16 array (mode 7)
+  // Ragged call: the compact list of the query tiles that exist (item << 20 | tile, tile-major: the level-4 list of the GEMMs,
+  // tc_gemm2.cuh). Walked from its END: later tiles see more key chunks (2, 4, 6, 6, ...), so the expensive units are dealt
+  // first and the cheap ones level the tail; no unit past an item's end is ever visited (the mt_max x B grid walk left the SMs
+  // idle for 31 % of a launch on a C2 batch, ncu round 2).
+  const int* tiles;            // device [ntiles] or nullptr -> walk the mt_max x B grid
+  int ntiles;
 };
 
 // exp(x) for x <= 0 through ex2.approx; the scaling by log2(e) is done in two pieces so that the argument carries no
@@ -186,15 +192,21 @@ __global__ void __launch_bounds__(kThreads, 1) swa_attention_tc_kernel(const Par
   const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
   const uint32_t tS = tmem_base + lane_off + (uint32_t)(cs * kCols);  // + 64c: this thread's columns of chunk c
   const uint32_t tO = tmem_base + lane_off + 384u + (uint32_t)(cs * kCols);   // + 64 * buffer
-  const int units = p.mt_max * p.B * kHeads;
+  const int units = (p.tiles ? p.ntiles : p.mt_max * p.B) * kHeads;
   uint32_t kvc = 0, pvc = 0, uc = 0, job = 0;                         // K/V stage uses, P*V chunks, units, MMA jobs so far
 
   // unit u -> geometry; false when the tile lies past the item's end (same decision in every role)
   auto decode = [&](int u, int& b, int& h, int& q0, int& T, int& c_lo, int& c_hi) {
     h = u % kHeads;
     const int t = u / kHeads;
-    b = t % p.B;
-    q0 = (t / p.B) * kQT;
+    if (p.tiles) {
+      const int e = __ldg(p.tiles + (p.ntiles - 1 - t));
+      b = e >> 20;
+      q0 = (e & 0xFFFFF) * kQT;
+    } else {
+      b = t % p.B;
+      q0 = (t / p.B) * kQT;
+    }
     T = len_smem ? s_len[b] : p.len ? __ldg(p.len + b) : p.uniform_len;
     if (q0 >= T) return false;
     const int kbase = q0 - 256;

@@ -28,6 +28,7 @@
 #include "tc_gemm.cuh"
 #include "tc_gemm2.cuh"
 #include "front_fused.cuh"
+#include "front_f16.cuh"
 #include "rvq_tc.cuh"
 #include "tc_gemm5.cuh"
 #include "transformer.cuh"
@@ -84,6 +85,9 @@ struct TcWeight {
   float* cadd = nullptr;
   CUtensorMap map_f16[3][3];               // [hi, lo, hs][box rows 128, 64, 32]
   int N = 0, K = 0, BN = 0;
+  // host copies of the mode-9 pack (R1a / R1b only: the fused front end keeps them resident in its own shared-memory layout)
+  std::vector<uint16_t> h_f16;
+  std::vector<float> h_cmul9, h_cadd;
 };
 // hi/lo activation pair, channels-last with `front` zero halo rows before row 0 of every item
 // (mode 7: hi fp32, lo bf16; mode 9: both fp16 -- item_stride counts ELEMENTS per item, hi / lo are float offsets of the arrays)
@@ -164,6 +168,11 @@ struct mimi_b200 {
   int last_mode = 0;
   int exp_chunk_kb = 0;                        // k-blocks per accumulation chunk (debug_set key 5; 0 = default 4)
   f0::Consts f0_consts;
+  f1::Consts f1_consts;                        // the fp16 front end (front_f16.cuh): L0 weights, affines of R1a / R1b
+  uint4* f1_wimg = nullptr;                    //   and the shared-memory image of W1 / W2 (hi | lo | hs, swizzle applied)
+  int exp_front_tf32 = 0;                      // debug_set key 17: mode 9 runs round 1's front end (TF32 internals, front_fused.cuh)
+  int exp_att_grid = 0;                        // debug_set key 18: attention walks the mt_max x B grid (round 1's schedule)
+  std::vector<int> len0_host;                  // samples per item of the call in flight (the front end's tile count)
   int num_sms = 148;
   long long item_tiles[6] = {0, 0, 0, 0, 0, 0};   // sum over items of ceil(rows_at_level / 128) for the call in flight
   const int* tile_ptr[6] = {};                 // ragged call in flight: compact 128-row tile lists per level (device), or nullptr
@@ -470,6 +479,7 @@ int mimi_b200_create(mimi_b200_t** out, int device_ordinal) {
   cudaFuncSetAttribute(atc::swa_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, atc::kSmem);
   cudaFuncSetAttribute(rvqtc::rvq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, rvqtc::kSmem);
   cudaFuncSetAttribute(f0::front_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, f0::kSmem);
+  cudaFuncSetAttribute(f1::front_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, f1::kSmem);
   cudaFuncSetAttribute(tc2::tc_shift_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 40960);
   if ((e = cudaGetLastError()) != cudaSuccess) { delete h; return fail(nullptr, MIMI_B200_ERR_CUDA, cudaGetErrorString(e)); }
   *out = h;
@@ -511,6 +521,8 @@ int mimi_b200_debug_set(mimi_b200_t* h, int key, int value) {
   else if (key == 11) h->exp_linear_k = value != 0;      // 1: k-blocks in linear order (no tap grouping)
   else if (key == 13) h->exp_no_tile_list = value != 0;
   else if (key == 16) h->exp_resample_simple = value != 0;
+  else if (key == 17) h->exp_front_tf32 = value != 0;
+  else if (key == 18) h->exp_att_grid = value != 0;
   else return fail(h, MIMI_B200_ERR_ARG, "debug_set: unknown key");
   return MIMI_B200_OK;
 }
@@ -721,6 +733,7 @@ static int encode_impl(mimi_b200_t* h, const float* d_input, int B, int64_t N, c
   int total_frames = B * p.rows[5];
   for (int l = 0; l < 6; ++l) h->item_tiles[l] = (long long)B * ((p.rows[l] + 127) / 128);
   for (int l = 0; l < 6; ++l) { h->tile_ptr[l] = nullptr; h->tile_cnt[l] = 0; }
+  h->len0_host.assign((size_t)B, (int)N);
   if (h_valid_len) {
     for (int l = 0; l < 6; ++l) h->item_tiles[l] = 0;
     std::vector<int> v((size_t)7 * B + 1);
@@ -731,6 +744,7 @@ static int encode_impl(mimi_b200_t* h, const float* d_input, int B, int64_t N, c
       long long len = h_valid_len[b];
       if (len < 0 || len > N) return fail(h, MIMI_B200_ERR_ARG, "encode: valid_len out of range");
       long long L = std::min<long long>(N, (len + MIMI_B200_FRAME_SIZE - 1) / MIMI_B200_FRAME_SIZE * MIMI_B200_FRAME_SIZE);
+      h->len0_host[b] = (int)L;
       for (int l = 0; l < 6; ++l) {
         v[(size_t)l * B + b] = (int)L;
         mx[l] = std::max(mx[l], (int)L);

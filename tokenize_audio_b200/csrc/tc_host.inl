@@ -112,6 +112,7 @@ static int tc_make_weight(mimi_b200* h, TcWeight* w, const std::vector<float>& w
     if ((rc = dev_upload(h, &w->cmul[0], cm7))) return rc;
     if ((rc = dev_upload(h, &w->cmul[1], cm9))) return rc;
     if ((rc = dev_upload(h, &w->cadd, ca))) return rc;
+    if (nk <= 8192) { w->h_f16 = f; w->h_cmul9 = cm9; w->h_cadd = ca; }      // R1a / R1b: the front end builds its own image
     for (int part = 0; part < 3; ++part)
       for (int r = 0; r < 3; ++r) {
         if (rows[r] > N) continue;
@@ -128,6 +129,38 @@ static std::vector<float> pack_conv_nk(const float* w, int cout, int cin, int k)
     for (int ci = 0; ci < cin; ++ci)
       for (int tau = 0; tau < k; ++tau) t[((size_t)co * k + tau) * cin + ci] = w[((size_t)co * cin + ci) * k + tau];
   return t;
+}
+
+// The resident weights of the fp16 front end (front_f16.cuh) exactly as they sit in its shared memory: K-major rows of 128 bytes
+// (64 halfs), 16-byte chunk c of row n at chunk position c ^ (n & 7) (SWIZZLE_128B). W1 = R1a [32][tau * 64 + ci] as nine 4 KB
+// blocks [tap][hi | lo | hs]; W2 = R1b [64][32] as three 8 KB parts whose rows use their first 64 bytes.
+static int f1_make_image(mimi_b200* h, const mimi_b200_weights_t* w) {
+  const TcWeight &w1 = h->tc_conv[1], &w2 = h->tc_conv[2];
+  if (w1.N != 32 || w1.K != 192 || w2.N != 64 || w2.K != 32 || w1.h_f16.size() != (size_t)3 * 32 * 192 ||
+      w2.h_f16.size() != (size_t)3 * 64 * 32)
+    return fail(h, MIMI_B200_ERR_STATE, "front end: unexpected R1a / R1b geometry");
+  std::vector<uint16_t> img(f1::kWBytes / 2, 0);
+  auto put = [&](size_t byte_off, const uint16_t* src, int rows, int ld, int k0, int kcount) {
+    for (int n = 0; n < rows; ++n)
+      for (int ci = 0; ci < kcount; ++ci) {
+        const int chunk = ci / 8;
+        const size_t pos = byte_off + (size_t)n * 128 + (size_t)((chunk ^ (n & 7)) * 16) + (size_t)(ci % 8) * 2;
+        img[pos / 2] = src[(size_t)n * ld + k0 + ci];
+      }
+  };
+  for (int tau = 0; tau < 3; ++tau)
+    for (int part = 0; part < 3; ++part)
+      put((size_t)(tau * 3 + part) * f1::kWBlock, w1.h_f16.data() + (size_t)part * 32 * 192, 32, 192, tau * 64, 64);
+  for (int part = 0; part < 3; ++part)
+    put((size_t)f1::kW1Bytes + (size_t)part * f1::kW2Part, w2.h_f16.data() + (size_t)part * 64 * 32, 64, 32, 0, 32);
+  CUDA_TRY(h, cudaMalloc((void**)&h->f1_wimg, f1::kWBytes));      // (load_weights freed every earlier allocation)
+  h->allocs.push_back(h->f1_wimg);
+  CUDA_TRY(h, cudaMemcpy(h->f1_wimg, img.data(), f1::kWBytes, cudaMemcpyHostToDevice));
+  std::memcpy(h->f1_consts.w0, w->conv_weight[0], sizeof(float) * 64 * 7);
+  std::memcpy(h->f1_consts.b0, w->conv_bias[0], sizeof(float) * 64);
+  for (int n = 0; n < 32; ++n) { h->f1_consts.m1[n] = w1.h_cmul9[n]; h->f1_consts.a1[n] = w1.h_cadd[n]; }
+  for (int n = 0; n < 64; ++n) { h->f1_consts.m2[n] = w2.h_cmul9[n]; h->f1_consts.a2[n] = w2.h_cadd[n]; }
+  return MIMI_B200_OK;
 }
 
 static int tc_load_weights(mimi_b200* h, const mimi_b200_weights_t* w) {
@@ -156,7 +189,7 @@ static int tc_load_weights(mimi_b200* h, const mimi_b200_weights_t* w) {
   std::memcpy(pj.data(), w->semantic_input_proj_weight, sizeof(float) * 256 * 512);
   std::memcpy(pj.data() + 256 * 512, w->acoustic_input_proj_weight, sizeof(float) * 256 * 512);
   if ((rc = tc_make_weight(h, &h->tc_proj, pj, 512, 512))) return rc;
-  return MIMI_B200_OK;
+  return f1_make_image(h, w);
 }
 
 // Workspace plan of the tensor-core generations: raw fp32 buffers where a skip or a non-GEMM consumer needs them, and a
@@ -387,8 +420,23 @@ static int encode_tc(mimi_b200* h, const float* d_input, int B, long long N, int
       fp.lo_bf16 = lob;
       const long long vt = (long long)fp.mt_max * nb;
       const int grid = (int)std::min<long long>(vt, h->num_sms);
-      f0::front_fused_kernel<<<grid, f0::kThreads, f0::kSmem, st>>>(h->tc_conv[1].map_hi, h->tc_conv[1].map_lo, h->tc_conv[2].map_hi,
-                                                                    h->tc_conv[2].map_lo, h->f0_consts, fp);
+      if (h->mode == 9 && !h->exp_front_tf32) {
+        // fp16 generation: front_f16.cuh walks only the tiles that exist, item by item
+        f1::Params q{};
+        q.x = fp.x; q.x_stride = N; q.len = fp.len; q.uniform_len = fp.uniform_len; q.B = nb;
+        long long tiles = 0;
+        for (int b = b0; b < b0 + nb; ++b) tiles += (std::min<long long>(h->len0_host[b], N) + f1::kAdv - 1) / f1::kAdv;
+        if (tiles > 0x7fffffffll) return fail(h, MIMI_B200_ERR_ARG, "front end: too many tiles");
+        q.total_tiles = (int)tiles;
+        q.wimg = h->f1_wimg;
+        q.out_hi = reinterpret_cast<uint16_t*>(fp.out_hi); q.out_lo = reinterpret_cast<uint16_t*>(fp.out_lo);
+        q.split_item_stride = fp.split_item_stride; q.split_front = fp.split_front;
+        const int g1 = (int)std::min<long long>((tiles + 1) / 2, h->num_sms);
+        if (g1 > 0) f1::front_f16_kernel<<<g1, f1::kThreads, f1::kSmem, st>>>(h->f1_consts, q);
+      } else {
+        f0::front_fused_kernel<<<grid, f0::kThreads, f0::kSmem, st>>>(h->tc_conv[1].map_hi, h->tc_conv[1].map_lo, h->tc_conv[2].map_hi,
+                                                                      h->tc_conv[2].map_lo, h->f0_consts, fp);
+      }
       h->launches++; mark(h, 27, st);
       CUDA_TRY(h, cudaGetLastError());
     }
@@ -438,7 +486,8 @@ static int encode_tc(mimi_b200* h, const float* d_input, int B, long long N, int
       ap.qkv = ws + p.qkv; ap.item_stride = rstride(4, 1536); ap.out_hi = ws + p.s_att.hi; ap.out_lo = ws + p.s_att.lo;
       ap.out_stride = rstride(4, 512); ap.rope_cos = h->rope_cos; ap.rope_sin = h->rope_sin; ap.len = dlen[4];
       ap.uniform_len = T25; ap.B = B; ap.mt_max = (T25 + atc::kQT - 1) / atc::kQT; ap.lo_bf16 = lob;
-      const long long units = (long long)ap.mt_max * B * kHeads;
+      if (!h->exp_att_grid && h->tile_ptr[4]) { ap.tiles = h->tile_ptr[4]; ap.ntiles = h->tile_cnt[4]; }
+      const long long units = (ap.tiles ? (long long)ap.ntiles : (long long)ap.mt_max * B) * kHeads;
       atc::swa_attention_tc_kernel<<<(int)std::min<long long>(units, h->num_sms), atc::kThreads, atc::kSmem, st>>>(ap);
       h->launches++; mark(h, 16, st);
       CUDA_TRY(h, cudaGetLastError());
