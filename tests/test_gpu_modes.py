@@ -90,6 +90,26 @@ def test_front_end_and_attention_schedule_variants_agree(b200_model, case):
         assert np.array_equal(r[i, :, :t], a[i, :, :t])
 
 
+def test_fp16_rvq_matches_tf32_rvq(b200_model, case):
+    """The fp16-pair RVQ kernel (rvq_f16.cuh, default of generation 9) against the TF32 one (debug knob 19) on the same latents:
+    32 codebooks, strict and ragged; the codes may differ only through near-ties (<= 0.1 % of slots) and never on the first
+    codebook of this case."""
+    x, lens, ref, _ = case
+    xd = torch.from_numpy(x).cuda()
+    a = b200_model.encode(xd, num_quantizers=32).audio_codes.cpu().numpy()
+    ar = b200_model.encode(xd, num_quantizers=32, valid_lengths=lens).audio_codes.cpu().numpy()
+    b200_model.debug_set(19, 1)
+    try:
+        b = b200_model.encode(xd, num_quantizers=32).audio_codes.cpu().numpy()
+    finally:
+        b200_model.debug_set(19, 0)
+    assert (a == b).mean() >= 0.999 and np.array_equal(a[:, 0], b[:, 0])
+    assert (a == ref).mean() >= 0.999
+    for i, n in enumerate(lens):
+        t = -(-n // 1920)
+        assert np.array_equal(ar[i, :, :t], a[i, :, :t])
+
+
 def test_tensor_core_rvq_matches_simt_rvq(b200_model):
     """mode 0 (fused SIMT RVQ, exact fp32 FFMA distances, on the all-fp32 pipeline) vs the default generation (tensor-core
     RVQ): the codes may differ only through near-ties (<= 0.1 % of slots)."""

@@ -30,6 +30,7 @@
 #include "front_fused.cuh"
 #include "front_f16.cuh"
 #include "rvq_tc.cuh"
+#include "rvq_f16.cuh"
 #include "tc_gemm5.cuh"
 #include "transformer.cuh"
 #include "attention_tc.cuh"
@@ -190,6 +191,10 @@ struct mimi_b200 {
   TcWeight tc_down, tc_proj;
   float *embed_hi = nullptr, *embed_lo = nullptr;   // TF32 split of the materialised codebooks (rvq_tc.cuh)
   CUtensorMap map_embed_hi, map_embed_lo;
+  uint16_t* embed16 = nullptr;                      // fp16 pair of the row-scaled codebooks: [hi | lo][32 * 2048][256] (rvq_f16.cuh)
+  float* embed_m2s = nullptr;                       // [32][2048] -2 * 2^-s of each code's row scaling
+  CUtensorMap map_embed16_hi, map_embed16_lo;
+  int exp_rvq_tf32 = 0;                             // debug_set key 19: mode 9 runs the TF32 RVQ (rvq_tc.cuh)
   std::map<MapKey, MapSet> amap_cache;   // activation maps per (workspace, B, N)
   PlanTC last_tc;
   bool last_was_tc = false;
@@ -478,6 +483,7 @@ int mimi_b200_create(mimi_b200_t** out, int device_ordinal) {
   }
   cudaFuncSetAttribute(atc::swa_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, atc::kSmem);
   cudaFuncSetAttribute(rvqtc::rvq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, rvqtc::kSmem);
+  cudaFuncSetAttribute(rvq16::rvq_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, rvq16::kSmem);
   cudaFuncSetAttribute(f0::front_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, f0::kSmem);
   cudaFuncSetAttribute(f1::front_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, f1::kSmem);
   cudaFuncSetAttribute(tc2::tc_shift_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 40960);
@@ -523,6 +529,7 @@ int mimi_b200_debug_set(mimi_b200_t* h, int key, int value) {
   else if (key == 16) h->exp_resample_simple = value != 0;
   else if (key == 17) h->exp_front_tf32 = value != 0;
   else if (key == 18) h->exp_att_grid = value != 0;
+  else if (key == 19) h->exp_rvq_tf32 = value != 0;
   else return fail(h, MIMI_B200_ERR_ARG, "debug_set: unknown key");
   return MIMI_B200_OK;
 }
@@ -617,6 +624,30 @@ int mimi_b200_load_weights(mimi_b200_t* h, const mimi_b200_weights_t* w) {
     if ((rc = dev_upload(h, &h->embed, E))) return rc;
     if ((rc = dev_upload(h, &h->embed_t, Et))) return rc;
     if ((rc = dev_upload(h, &h->enorm, En))) return rc;
+    {
+      // fp16 generation: rows scaled by 2^s so that max |e'| lies in [2^13, 2^14), e' = hi16 + lo16; the distance's -2 carries 2^-s
+      const size_t tot = 32 * per;
+      std::vector<uint16_t> f(2 * tot);
+      std::vector<float> m2s((size_t)32 * kCodebookSize);
+      auto bits = [](float v) { const __half hh = __float2half_rn(v); uint16_t u; memcpy(&u, &hh, 2); return u; };
+      for (size_t r = 0; r < (size_t)32 * kCodebookSize; ++r) {
+        float mx = 0.f;
+        for (int k = 0; k < kCodeDim; ++k) mx = std::max(mx, std::fabs(E[r * kCodeDim + k]));
+        int e = 0;
+        if (mx > 0.f && std::isfinite(mx)) { int ex; std::frexp(mx, &ex); e = 14 - ex; }
+        m2s[r] = -2.0f * std::ldexp(1.0f, -e);
+        for (int k = 0; k < kCodeDim; ++k) {
+          const float v = std::ldexp(E[r * kCodeDim + k], e);
+          const float vh = __half2float(__float2half_rn(v));
+          f[r * kCodeDim + k] = bits(vh);
+          f[tot + r * kCodeDim + k] = bits(v - vh);
+        }
+      }
+      CUDA_TRY(h, cudaMalloc((void**)&h->embed16, f.size() * sizeof(uint16_t)));
+      h->allocs.push_back(h->embed16);
+      CUDA_TRY(h, cudaMemcpy(h->embed16, f.data(), f.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+      if ((rc = dev_upload(h, &h->embed_m2s, m2s))) return rc;
+    }
     for (size_t i = 0; i < E.size(); ++i) { float hi, lo; split_tf32(E[i], hi, lo); E[i] = hi; Et[i] = lo; }   // reuse as hi / lo
     if ((rc = dev_upload(h, &h->embed_hi, E))) return rc;
     if ((rc = dev_upload(h, &h->embed_lo, Et))) return rc;
@@ -646,6 +677,10 @@ int mimi_b200_load_weights(mimi_b200_t* h, const mimi_b200_weights_t* w) {
     const cuuint64_t strides[1] = {(cuuint64_t)kCodeDim * sizeof(float)};
     if ((rc = tc_make_map(h, &h->map_embed_hi, h->embed_hi, 2, dims, strides, rvqtc::kCodesPerBlock))) return rc;
     if ((rc = tc_make_map(h, &h->map_embed_lo, h->embed_lo, 2, dims, strides, rvqtc::kCodesPerBlock))) return rc;
+    const cuuint64_t strides16[1] = {(cuuint64_t)kCodeDim * sizeof(uint16_t)};
+    const size_t tot = (size_t)MIMI_B200_MAX_QUANTIZERS * kCodebookSize * kCodeDim;
+    if ((rc = tc_make_map16_sw128(h, &h->map_embed16_hi, h->embed16, dims, strides16, rvq16::kCodesPerBlock))) return rc;
+    if ((rc = tc_make_map16_sw128(h, &h->map_embed16_lo, h->embed16 + tot, dims, strides16, rvq16::kCodesPerBlock))) return rc;
   }
   h->amap_cache.clear();
   h->loaded = true;

@@ -40,6 +40,19 @@ static int tc_make_map_bf16(mimi_b200* h, CUtensorMap* out, const void* base, in
   return MIMI_B200_OK;
 }
 
+// 16-bit tensor map, SWIZZLE_128B, inner box = 64 elements (128 B): the fp16 codebooks of rvq_f16.cuh
+static int tc_make_map16_sw128(mimi_b200* h, CUtensorMap* out, const void* base, const cuuint64_t* dims,
+                               const cuuint64_t* strides_bytes, int box_rows) {
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = h->encode_tiled(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides_bytes, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(h, MIMI_B200_ERR_CUDA, "cuTensorMapEncodeTiled (16-bit, 128B swizzle) failed with CUresult " + std::to_string((int)r));
+  return MIMI_B200_OK;
+}
+
 // w_nk: host [N][K] K-major. Mode 7: TF32 hi / lo (fp32) and bf16(hi), uploaded with one map per box height (128, 64, 32
 // rows: the pair GEMM stages bnp / 2 weight rows per CTA); map_hi / map_lo (box BN) serve the fused front end.
 // `bias` / `scale` (host [N] or nullptr): folded with the mode-9 weight unscaling into the per-column affine of the epilogue,
@@ -527,7 +540,16 @@ static int encode_tc(mimi_b200* h, const float* d_input, int B, long long N, int
     TcOut o;
     o.raw = ws + p.rp; o.raw_item_stride = rstride(5, 512);
     if ((rc = tc_gemm(c, 15, p.s_e, 1, 1, 0, h->tc_proj, o, 21))) return rc;
-    if (total_frames > 0) {
+    if (total_frames > 0 && h->mode == 9 && !h->exp_rvq_tf32) {
+      rvq16::Params q{};
+      q.rproj = ws + p.rp; q.item_stride = rstride(5, 512); q.embed = h->embed; q.enorm = h->enorm; q.m2s = h->embed_m2s;
+      q.codes = reinterpret_cast<long long*>(d_codes);
+      q.K = K; q.T_out = p.rows[5]; q.len = dlen[5]; q.uniform_len = T; q.B = B; q.total_frames = total_frames;
+      q.frame_prefix = dprefix;
+      rvq16::rvq_f16_kernel<<<(total_frames + rvq16::kFrames - 1) / rvq16::kFrames, rvq16::kThreads, rvq16::kSmem, st>>>(
+          h->map_embed16_hi, h->map_embed16_lo, q);
+      h->launches++; mark(h, 22, st);
+    } else if (total_frames > 0) {
       rvqtc::Params q{};
       q.rproj = ws + p.rp; q.item_stride = rstride(5, 512); q.embed = h->embed; q.enorm = h->enorm;
       q.codes = reinterpret_cast<long long*>(d_codes);
