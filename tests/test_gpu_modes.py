@@ -90,6 +90,29 @@ def test_front_end_and_attention_schedule_variants_agree(b200_model, case):
         assert np.array_equal(r[i, :, :t], a[i, :, :t])
 
 
+def test_tap_group_gemm_matches_per_tap_gemm(b200_model, case):
+    """Convs run as tap groups (tc_gemm7.cuh: one activation tile per group of taps that share input rows, shifted
+    descriptors) against the per-k-block schedule of tc_gemm5.cuh (debug knob 20): both within tolerance of the oracle, the
+    same codes up to near-ties, ragged == strict on kept frames."""
+    x, lens, ref, lat_ref = case
+    xd = torch.from_numpy(x).cuda()
+    out, lat = b200_model.encode(xd, num_quantizers=32, return_latent=True)
+    a = out.audio_codes.cpu().numpy()
+    ar = b200_model.encode(xd, num_quantizers=32, valid_lengths=lens).audio_codes.cpu().numpy()
+    b200_model.debug_set(20, 1)
+    try:
+        out_b, lat_b = b200_model.encode(xd, num_quantizers=32, return_latent=True)
+        b = out_b.audio_codes.cpu().numpy()
+    finally:
+        b200_model.debug_set(20, 0)
+    assert _rel(lat.cpu().numpy(), lat_ref) <= 2e-5 and _rel(lat_b.cpu().numpy(), lat_ref) <= 2e-5
+    assert _rel(lat.cpu().numpy(), lat_b.cpu().numpy()) <= 1e-5
+    assert (a == ref).mean() >= 0.999 and (a == b).mean() >= 0.999
+    for i, n in enumerate(lens):
+        t = -(-n // 1920)
+        assert np.array_equal(ar[i, :, :t], a[i, :, :t])
+
+
 def test_fp16_rvq_matches_tf32_rvq(b200_model, case):
     """The fp16-pair RVQ kernel (rvq_f16.cuh, default of generation 9) against the TF32 one (debug knob 19) on the same latents:
     32 codebooks, strict and ragged; the codes may differ only through near-ties (<= 0.1 % of slots) and never on the first

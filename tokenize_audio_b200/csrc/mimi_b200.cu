@@ -32,6 +32,7 @@
 #include "rvq_tc.cuh"
 #include "rvq_f16.cuh"
 #include "tc_gemm5.cuh"
+#include "tc_gemm7.cuh"
 #include "transformer.cuh"
 #include "attention_tc.cuh"
 #include "decode_kernels.cuh"
@@ -172,6 +173,7 @@ struct mimi_b200 {
   f1::Consts f1_consts;                        // the fp16 front end (front_f16.cuh): L0 weights, affines of R1a / R1b
   uint4* f1_wimg = nullptr;                    //   and the shared-memory image of W1 / W2 (hi | lo | hs, swizzle applied)
   int exp_front_tf32 = 0;                      // debug_set key 17: mode 9 runs round 1's front end (TF32 internals, front_fused.cuh)
+  int exp_no_taps = 0;                         // debug_set key 20: convs never run as tap groups (tc_gemm7.cuh), i.e. round 2's schedule
   int exp_att_grid = 0;                        // debug_set key 18: attention walks the mt_max x B grid (round 1's schedule)
   std::vector<int> len0_host;                  // samples per item of the call in flight (the front end's tile count)
   int num_sms = 148;
@@ -481,6 +483,10 @@ int mimi_b200_create(mimi_b200_t** out, int device_ordinal) {
       h->num_clusters = std::min(ncl, h->num_sms / 2);
     else { cudaGetLastError(); h->num_clusters = h->num_sms / 2; }
   }
+  cudaFuncSetAttribute(tcg::tcp_taps_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcg::Cfg<128, 2>::SMEM);
+  cudaFuncSetAttribute(tcg::tcp_taps_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcg::Cfg<128, 3>::SMEM);
+  cudaFuncSetAttribute(tcg::tcp_taps_kernel<64, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcg::Cfg<64, 3>::SMEM);
+  cudaFuncSetAttribute(tcg::tcp_taps_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcg::Cfg<64, 2>::SMEM);
   cudaFuncSetAttribute(atc::swa_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, atc::kSmem);
   cudaFuncSetAttribute(rvqtc::rvq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, rvqtc::kSmem);
   cudaFuncSetAttribute(rvq16::rvq_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, rvq16::kSmem);
@@ -522,7 +528,7 @@ int mimi_b200_debug_set(mimi_b200_t* h, int key, int value) {
     h->mode = value;
   }
   else if (key == 5) h->exp_chunk_kb = std::max(value, 0);
-  else if (key == 9) h->exp_pair_n128 = std::max(value, 0);
+  else if (key == 9) { h->exp_pair_n128 = std::max(value, 0); h->amap_cache.clear(); }
   else if (key == 10) h->exp_no_flat = value != 0;
   else if (key == 11) h->exp_linear_k = value != 0;      // 1: k-blocks in linear order (no tap grouping)
   else if (key == 13) h->exp_no_tile_list = value != 0;
@@ -530,6 +536,7 @@ int mimi_b200_debug_set(mimi_b200_t* h, int key, int value) {
   else if (key == 17) h->exp_front_tf32 = value != 0;
   else if (key == 18) h->exp_att_grid = value != 0;
   else if (key == 19) h->exp_rvq_tf32 = value != 0;
+  else if (key == 20) { h->exp_no_taps = value != 0; h->amap_cache.clear(); }     // (the activation maps of a conv differ)
   else return fail(h, MIMI_B200_ERR_ARG, "debug_set: unknown key");
   return MIMI_B200_OK;
 }

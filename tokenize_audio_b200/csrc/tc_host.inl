@@ -259,15 +259,16 @@ constexpr int kTcSlots = 24;          // GEMM sites; slots [kTcSlots, 2*kTcSlots
 
 // activation maps for a conv/linear that reads SplitBuf `a` with kernel k, stride s, left pad `pad`. `flat`: the
 // items' rows are one contiguous [B * rows][C] matrix (k = 1, no halo) seen as a single item.
+// `extra`: box rows and row dimension grow by this many rows (tap-group launches, tc_gemm7.cuh).
 static int tc_amaps(TcCtx& c, int slot, const SplitBuf& a, int k, int s, int pad, bool flat, const CUtensorMap** hi,
-                    const CUtensorMap** lo) {
+                    const CUtensorMap** lo, int extra = 0) {
   if (flat) slot += kTcSlots;
   CUtensorMap* mh = &(*c.maps)[2 * slot];
   CUtensorMap* ml = mh + 1;
   if (!((*c.built >> slot) & 1ull)) {
     const PlanTC& p = *c.p;
     const int rows_out = (p.rows[a.level] + s - 1) / s;
-    const cuuint64_t dims[3] = {(cuuint64_t)k * a.C, (cuuint64_t)std::max(flat ? rows_out * c.B : rows_out, 1),
+    const cuuint64_t dims[3] = {(cuuint64_t)k * a.C, (cuuint64_t)std::max(flat ? rows_out * c.B : rows_out, 1) + extra,
                                 (cuuint64_t)(flat ? 1 : c.B)};
     const cuuint64_t strides[2] = {(cuuint64_t)s * a.C * sizeof(float),
                                    (cuuint64_t)a.item_stride * (flat ? c.B : 1) * sizeof(float)};
@@ -276,9 +277,9 @@ static int tc_amaps(TcCtx& c, int slot, const SplitBuf& a, int k, int s, int pad
     if (a.front < pad) return fail(c.h, MIMI_B200_ERR_ARG, "tc: halo smaller than conv padding");
     int rc;
     if (c.h->mode == 9) {
-      if ((rc = tc_make_map_bf16(c.h, mh, reinterpret_cast<const uint16_t*>(c.ws + a.hi) + base_off, 3, dims, strides_h, tc::kBM))) return rc;
+      if ((rc = tc_make_map_bf16(c.h, mh, reinterpret_cast<const uint16_t*>(c.ws + a.hi) + base_off, 3, dims, strides_h, tc::kBM + extra))) return rc;
     } else if ((rc = tc_make_map(c.h, mh, c.ws + a.hi + base_off, 3, dims, strides, tc::kBM))) return rc;
-    if ((rc = tc_make_map_bf16(c.h, ml, reinterpret_cast<const uint16_t*>(c.ws + a.lo) + base_off, 3, dims, strides_h, tc::kBM))) return rc;
+    if ((rc = tc_make_map_bf16(c.h, ml, reinterpret_cast<const uint16_t*>(c.ws + a.lo) + base_off, 3, dims, strides_h, tc::kBM + extra))) return rc;
     *c.built |= 1ull << slot;
   }
   *hi = mh;
@@ -303,9 +304,17 @@ static void tc_korder(const mimi_b200* h, tc2::Sched& sc, int k, int s, int cin)
 }
 
 // the CTA-pair GEMM (tc_gemm5.cuh): pair tiles of 2 x 128 rows x BNP columns. Every layer of the network has N % 64 == 0.
+// Taps per group of a conv the tap-group kernel (tc_gemm7.cuh) can run: 2 for k = 2 s, 3 for k = 3 with s = 1; 1 = tc_gemm5.
+static int tc_tap_group(const mimi_b200* h, const TcWeight& w, int k, int s, int cin) {
+  if (h->mode != 9 || h->exp_no_taps || k <= 1 || k % s || cin % 32) return 1;
+  if (w.N % 256 == 0 && (w.K > 2048 || h->exp_pair_n128 == 1)) return 1;      // 256-column pair tiles: no room for the wider stage
+  const int g = k / s;
+  return (g == 2 || (g == 3 && s == 1)) ? g : 1;
+}
+
 static int launch_tcp(mimi_b200* h, const CUtensorMap& ahi, const CUtensorMap& alo, const TcWeight& w, const tc::Epilogue& ep,
                       int B, int mt_max, cudaStream_t st, int k = 1, int s = 1, int cin = 0, const int* tiles = nullptr,
-                      int ntiles = 0) {
+                      int ntiles = 0, int tg = 1) {
   if (w.N % 64) return fail(h, MIMI_B200_ERR_ARG, "tc: the pair GEMM needs N % 64 == 0");
   // Pair tiles of 256 columns for the deep layers (K > 2048: D3, D4, F -- the tensor pipe is the bound and a 256-wide tile reads
   // every operand byte once per 256 x 256 MMA), 128 columns for everything else: those layers are bound by the tile finish, and
@@ -321,6 +330,17 @@ static int launch_tcp(mimi_b200* h, const CUtensorMap& ahi, const CUtensorMap& a
   const int ncl = (int)std::min<long long>(npairs, h->num_clusters);
   if (ncl <= 0) return MIMI_B200_OK;
   const int r = bnp == 256 ? 0 : bnp == 128 ? 1 : 2;            // weight boxes of bnp / 2 rows
+  if (tg > 1) {
+    // taps that share input rows: one activation tile of 128 + tg - 1 rows per (tap phase, channel panel) (tc_gemm7.cuh)
+    sc.G = tg; sc.s = s; sc.cp = cin / 32;
+    if (w.K != tg * sc.s * sc.cp * 32 || bnp == 256) return fail(h, MIMI_B200_ERR_ARG, "tc: tap-group launch with a wrong geometry");
+    const CUtensorMap &whi = w.map_f16[0][r], &wlo = w.map_f16[1][r], &whs = w.map_f16[2][r];
+    if (bnp == 128 && tg == 2) tcg::tcp_taps_kernel<128, 2><<<2 * ncl, tcg::kThreads, tcg::Cfg<128, 2>::SMEM, st>>>(ahi, alo, whi, wlo, whs, ep, sc);
+    else if (bnp == 128 && tg == 3) tcg::tcp_taps_kernel<128, 3><<<2 * ncl, tcg::kThreads, tcg::Cfg<128, 3>::SMEM, st>>>(ahi, alo, whi, wlo, whs, ep, sc);
+    else if (bnp == 64 && tg == 3) tcg::tcp_taps_kernel<64, 3><<<2 * ncl, tcg::kThreads, tcg::Cfg<64, 3>::SMEM, st>>>(ahi, alo, whi, wlo, whs, ep, sc);
+    else if (bnp == 64 && tg == 2) tcg::tcp_taps_kernel<64, 2><<<2 * ncl, tcg::kThreads, tcg::Cfg<64, 2>::SMEM, st>>>(ahi, alo, whi, wlo, whs, ep, sc);
+    return MIMI_B200_OK;
+  }
   if (h->mode == 9) {
     // fp16 generation: all five operand tiles are 16-bit SWIZZLE_64B boxes
     const CUtensorMap &whi = w.map_f16[0][r], &wlo = w.map_f16[1][r], &whs = w.map_f16[2][r];
@@ -349,7 +369,8 @@ static int tc_gemm(TcCtx& c, int slot, const SplitBuf& a, int k, int s, int pad,
                     c.B > 1 && (!o.raw && !o.res || o.raw_item_stride == (long long)rows_lvl * w.N) &&
                     (!o.split || (o.split->front == 0 && o.split->back == 0 && o.split->level == a.level)) &&
                     ((long long)c.B * rows_lvl + 127) / 128 < c.h->item_tiles[a.level];
-  if ((rc = tc_amaps(c, slot, a, k, s, pad, flat, &ahi, &alo))) return rc;
+  const int tg = flat ? 1 : tc_tap_group(c.h, w, k, s, a.C);
+  if ((rc = tc_amaps(c, slot, a, k, s, pad, flat, &ahi, &alo, tg - 1))) return rc;
   if (w.K != k * a.C) return fail(c.h, MIMI_B200_ERR_ARG, "tc: weight K mismatch");
   tc::Epilogue ep{};
   ep.cmul = w.cmul[c.h->mode == 9 ? 1 : 0]; ep.cadd = w.cadd;
@@ -373,7 +394,7 @@ static int tc_gemm(TcCtx& c, int slot, const SplitBuf& a, int k, int s, int pad,
   const int out_level = a.level + (s > 1 ? 1 : 0);
   const int* tiles = (!flat && out_level < 6) ? c.h->tile_ptr[out_level] : nullptr;
   const int ntiles = tiles ? c.h->tile_cnt[out_level] : 0;
-  if ((rc = launch_tcp(c.h, *ahi, *alo, w, ep, nb, (lout_max + tc::kBM - 1) / tc::kBM, c.st, k, s, a.C, tiles, ntiles))) return rc;
+  if ((rc = launch_tcp(c.h, *ahi, *alo, w, ep, nb, (lout_max + tc::kBM - 1) / tc::kBM, c.st, k, s, a.C, tiles, ntiles, tg))) return rc;
   c.h->launches++;
   mark(c.h, prof_id, c.st);
   CUDA_TRY(c.h, cudaGetLastError());
