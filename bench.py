@@ -573,13 +573,27 @@ def run_b200(args, rank, world, local_rank):
     # layers are launches of one function, the 256-column CTA-pair GEMM: group the kinds by the function that runs them so
     # that "dominant kernel" and its share of the step mean the same thing here and in profiles/*launches*.md.
     # (tc_host.inl: launch_tcp -- 256-column pair tiles for K > 2048, 64 for N = 64, 128 for the rest)
+    #  generation 9 also: convs whose taps share input rows run as tap groups, tcp_taps_kernel<BNP, taps per group> (tc_gemm7.cuh),
+    #  the front end is front_f16_kernel and the RVQ rvq_f16_kernel unless a debug knob says otherwise)
     fn_of = {"seanet_conv9": 256, "seanet_conv12": 256, "seanet_conv13": 256, "seanet_conv4": 64}
     gemm_kinds = {f"seanet_conv{i}" for i in range(3, 14)} | {"qkv_gemm", "o_proj", "fc1_gelu", "fc2", "downsample_conv", "rvq_input_proj"}
     groups = {}
     cur_mode = args.mode if args.mode is not None else model.DEFAULT_MODE
     default_gen = cur_mode >= 7 and not any(kv.startswith("9=") for kv in args.dbg)
+    knob_on = lambda key: any(kv.split("=")[0] == str(key) and kv.split("=")[1] != "0" for kv in args.dbg)
+    taps_of = {"seanet_conv3": (128, 2), "seanet_conv6": (128, 2), "downsample_conv": (128, 2), "seanet_conv7": (128, 3),
+               "seanet_conv10": (128, 3), "seanet_conv4": (64, 3)} if (cur_mode == 9 and default_gen and not knob_on(20)) else {}
+    renamed = {}
+    if cur_mode == 9:
+        if not knob_on(17):
+            renamed["front_fused"] = "front_f16_kernel"
+        if not knob_on(19):
+            renamed["rvq_fused"] = "rvq_f16_kernel"
     for k, (kms_, kcnt_) in prof.items():
-        g = "tcp_gemm_kernel<%d,%d>" % (fn_of.get(k, 128), 3 if cur_mode == 9 else 1) if (default_gen and k in gemm_kinds) else k
+        if k in taps_of:
+            g = "tcp_taps_kernel<%d,%d>" % taps_of[k]
+        else:
+            g = "tcp_gemm_kernel<%d,%d>" % (fn_of.get(k, 128), 3 if cur_mode == 9 else 1) if (default_gen and k in gemm_kinds) else renamed.get(k, k)
         e = groups.setdefault(g, {"ms": 0.0, "count": 0, "kinds": []})
         e["ms"] += kms_; e["count"] += kcnt_; e["kinds"].append(k)
     kind, grp = max(groups.items(), key=lambda kv: kv[1]["ms"])
@@ -640,7 +654,7 @@ def run_b200(args, rank, world, local_rank):
         for k, nbytes in LEVEL1_HBM_BYTES_PER_AUDIO_S.items():
             if k in prof:
                 gb = nbytes * audio_per_step * args.steps / (prof[k][0] / 1e3) / 1e9
-                by_kernel.append({"kernel": f"tcp_gemm_kernel, layer {k} alone (HBM view)", "bound": "hbm", "achieved_gbs": round(gb, 1),
+                by_kernel.append({"kernel": f"GEMM layer {k} alone (HBM view)", "bound": "hbm", "achieved_gbs": round(gb, 1),
                                   "frac": round(gb / peaks["hbm_gbs"], 4), "ms_per_step": round(prof[k][0] / args.steps, 4)})
     breakdown = {k: round(v[0] / args.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
 

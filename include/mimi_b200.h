@@ -188,6 +188,7 @@ int mimi_b200_debug_tap(mimi_b200_t* h, int which, float* d_out, size_t out_capa
     17  1 = generation 9 runs round 1's front end (front_fused.cuh: TF32 internals) instead of front_f16.cuh
     18  1 = the attention kernel walks the mt_max x B unit grid instead of the compact tile list of a ragged call
     19  1 = generation 9 runs the TF32 RVQ kernel (rvq_tc.cuh) instead of the fp16-pair one (rvq_f16.cuh)
+    21  1 = fc1's GELU through erff instead of gelu_fast (common.cuh; same function to <= 4e-7 absolute)
     20  1 = convs never run as tap groups (tc_gemm7.cuh): every k-block of the im2col view is fetched on its own (tc_gemm5.cuh) */
 int mimi_b200_debug_set(mimi_b200_t* h, int key, int value);
 

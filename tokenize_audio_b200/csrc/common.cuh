@@ -31,6 +31,29 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
 }
 
+// The same GELU for the tensor-core epilogues, 15 instructions instead of erff's 25 (fc1 is bound by its tile finish):
+// gelu(x) = x * Phi(x), Phi(-t) = 0.5 erfc(t / sqrt 2) = 2^q(t) with q a degree-10 polynomial fitted to log2(0.5 erfc(t / sqrt 2)) on
+// [0, 5.5] (max error 2e-7 in q), Phi(t) = 1 - Phi(-t). Beyond 5.5 Phi is 1.9e-8 / 1 - 1.9e-8 either way. Against the exact
+// function in double: absolute error <= 3.9e-7 over [-8, 8] (an erff-based fp32 GELU: 4.5e-7, both set by the rounding of the
+// result), relative error <= 1.2e-6 for x > -3 (<= 8e-7 on [-2, 2]).
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float t = fminf(fabsf(x), 5.5f);
+  float q = -1.725302567479048e-08f;
+  q = fmaf(q, t, 5.477549507304502e-07f);
+  q = fmaf(q, t, -7.4582894740160555e-06f);
+  q = fmaf(q, t, 5.484473149408586e-05f);
+  q = fmaf(q, t, -0.000200506707187742f);
+  q = fmaf(q, t, -0.00017614704847801477f);
+  q = fmaf(q, t, 0.007180649787187576f);
+  q = fmaf(q, t, -0.05261564627289772f);
+  q = fmaf(q, t, -0.4591561555862427f);
+  q = fmaf(q, t, -1.1511132717132568f);
+  q = fmaf(q, t, -0.9999998211860657f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(q));
+  return x * (x >= 0.f ? 1.f - e : e);
+}
+
 __device__ __forceinline__ float4 ld_nc_f4(const float* p) {
   return __ldg(reinterpret_cast<const float4*>(p));
 }

@@ -173,6 +173,7 @@ struct mimi_b200 {
   f1::Consts f1_consts;                        // the fp16 front end (front_f16.cuh): L0 weights, affines of R1a / R1b
   uint4* f1_wimg = nullptr;                    //   and the shared-memory image of W1 / W2 (hi | lo | hs, swizzle applied)
   int exp_front_tf32 = 0;                      // debug_set key 17: mode 9 runs round 1's front end (TF32 internals, front_fused.cuh)
+  int exp_gelu_erff = 0;                       // debug_set key 21: fc1's GELU through erff (25 instructions) instead of gelu_fast
   int exp_no_taps = 0;                         // debug_set key 20: convs never run as tap groups (tc_gemm7.cuh), i.e. round 2's schedule
   int exp_att_grid = 0;                        // debug_set key 18: attention walks the mt_max x B grid (round 1's schedule)
   std::vector<int> len0_host;                  // samples per item of the call in flight (the front end's tile count)
@@ -536,6 +537,7 @@ int mimi_b200_debug_set(mimi_b200_t* h, int key, int value) {
   else if (key == 17) h->exp_front_tf32 = value != 0;
   else if (key == 18) h->exp_att_grid = value != 0;
   else if (key == 19) h->exp_rvq_tf32 = value != 0;
+  else if (key == 21) h->exp_gelu_erff = value != 0;
   else if (key == 20) { h->exp_no_taps = value != 0; h->amap_cache.clear(); }     // (the activation maps of a conv differ)
   else return fail(h, MIMI_B200_ERR_ARG, "debug_set: unknown key");
   return MIMI_B200_OK;

@@ -31,7 +31,7 @@ struct Epilogue {
   long long raw_item_stride;    // floats between items in res / out_raw
   long long split_item_stride;  // floats between items in out_hi / out_lo
   int split_front;              // halo rows in front of row 0 of each item in the split buffers
-  int act;                      // 1: GELU(erf) after the affine
+  int act;                      // 1: GELU(erf) after the affine through erff; 2: the same function through gelu_fast (common.cuh)
   int elu_split;                // 1: ELU applied before the hi/lo split (next conv's input activation)
   const int* len_in;            // device [B] input rows per item or nullptr -> uniform_len_in
   int uniform_len_in;

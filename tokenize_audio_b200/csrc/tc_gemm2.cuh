@@ -152,7 +152,7 @@ __device__ __forceinline__ void finish_tile(const Epilogue& ep, float (&acc)[HAL
   const long long split_base = (long long)b * ep.split_item_stride + (long long)ep.split_front * ep.N + ncol0;
   const float* resp = ep.res ? ep.res + raw_base : nullptr;
   float* rawp = ep.out_raw ? ep.out_raw + raw_base : nullptr;
-  const bool do_split = ep.out_hi != nullptr, do_elu = ep.elu_split != 0, do_act = ep.act == 1;
+  const bool do_split = ep.out_hi != nullptr, do_elu = ep.elu_split != 0, do_act = ep.act == 1, do_act_fast = ep.act == 2;
   const int wkey = (LPR == 8) ? (lane & 7) : ((lane >> 1) & (LPR - 1));
   __half2 mx2 = __floats2half2_rn(0.f, 0.f);     // LOB 3: running max |hi| of everything this thread stores (range check)
 #pragma unroll
@@ -173,7 +173,10 @@ __device__ __forceinline__ void finish_tile(const Epilogue& ep, float (&acc)[HAL
       v[j] = make_float4(fmaf(acc[p * PC + 4 * j], m.x, a.x), fmaf(acc[p * PC + 4 * j + 1], m.y, a.y),
                          fmaf(acc[p * PC + 4 * j + 2], m.z, a.z), fmaf(acc[p * PC + 4 * j + 3], m.w, a.w));
     }
-    if (do_act) {
+    if (do_act_fast) {
+#pragma unroll
+      for (int j = 0; j < LPR; ++j) { v[j].x = gelu_fast(v[j].x); v[j].y = gelu_fast(v[j].y); v[j].z = gelu_fast(v[j].z); v[j].w = gelu_fast(v[j].w); }
+    } else if (do_act) {
 #pragma unroll
       for (int j = 0; j < LPR; ++j) { v[j].x = gelu_erf(v[j].x); v[j].y = gelu_erf(v[j].y); v[j].z = gelu_erf(v[j].z); v[j].w = gelu_erf(v[j].w); }
     }

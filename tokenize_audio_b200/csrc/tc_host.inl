@@ -380,7 +380,7 @@ static int tc_gemm(TcCtx& c, int slot, const SplitBuf& a, int k, int s, int pad,
     ep.out_hi = c.ws + o.split->hi; ep.out_lo = c.ws + o.split->lo;
     ep.split_item_stride = o.split->item_stride; ep.split_front = o.split->front;
   }
-  ep.act = o.act; ep.elu_split = o.elu_split; ep.lo_bf16 = c.h->mode == 9 ? 3 : 1;
+  ep.act = (o.act == 1 && !c.h->exp_gelu_erff) ? 2 : o.act; ep.elu_split = o.elu_split; ep.lo_bf16 = c.h->mode == 9 ? 3 : 1;
   ep.chunk_kb = c.h->exp_chunk_kb;
   ep.len_in = c.dlen[a.level]; ep.uniform_len_in = c.maxlen[a.level]; ep.conv_stride = s; ep.N = w.N;
   int lout_max = (c.maxlen[a.level] + s - 1) / s;
