@@ -30,6 +30,7 @@ constexpr int kAStage = 2 * kCodesPerBlock * 128;  // codebook stage: hi | lo = 
 constexpr int kAStages = 4;
 constexpr int kThreads = 320;
 constexpr int kMisc = 4096;                        // xn[64], candidates, barriers
+constexpr float kBandUp = 1.0f + 4.76837158203125e-07f;   // 1 + 2^-21, see the block loop
 constexpr int kSmem = 1024 + kRBytes + kAStages * kAStage + kMisc;
 
 struct Params {
@@ -205,12 +206,20 @@ rvq_f16_kernel(const __grid_constant__ CUtensorMap tmE_hi, const __grid_constant
       epi_sync();                                   // operand + xn complete for all frames
       if (lane == 0) tc::mbar_arrive(r_ready);
 
-      // ---- 16 code blocks: distances and running (min, lowest index) for this thread's code lane ---------------
-      float bd[32];
+      // ---- 16 code blocks: running (min, lowest index) for this thread's code lane ------------------------------------
+      // The reference takes the argmin of sqrt(d2) (torch.cdist), lowest index among EQUAL ROUNDED roots. A candidate that is
+      // smaller by more than 2^-21 relative has a strictly smaller rounded root for certain (the roots differ by 2^-22
+      // relative, two roundings move them by at most 2^-24 each), so the running minimum is kept on d2 itself and the square
+      // roots are only computed when a candidate falls inside that band below the current minimum -- never, in practice
+      // (exact duplicates are equal, not inside the band) -- and once per frame at the end. 9 instructions per candidate
+      // instead of 16: the block loop, not the codebook stream, bounded this kernel (ncu: 25 B/clk/SM of stream, issue-bound
+      // epilogue warps).
+      float bd[32];                                 // d2 of the running minimum
       int bi[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) { bd[i] = INFINITY; bi[i] = 0; }
       const long long cofs = (long long)stage * kCodebookSize + quarter * 32 + lane;
+      const uint32_t xn_s = tc::smem_u32(xn + fh * 32);
       for (int blk = 0; blk < kBlocks; ++blk, ++bc) {
         const uint32_t buf = bc & 1u;
         const float e2 = __ldg(p.enorm + cofs + blk * kCodesPerBlock);
@@ -225,14 +234,31 @@ rvq_f16_kernel(const __grid_constant__ CUtensorMap tmE_hi, const __grid_constant
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&acc_empty[buf]);
+        bool band = false;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float dot = fmaf(__uint_as_float(rs[i]), 1.0f / kF16LoScale, __uint_as_float(rm[i]));   // scaled by 2^s
-          const float d2 = fmaf(ms, dot, xn[fh * 32 + i] + e2);
-          const float d = sqrtf(fmaxf(d2, 0.f));
-          if (d < bd[i]) { bd[i] = d; bi[i] = code; }      // codes ascend per thread: strict '<' keeps the lowest index
+        for (int i4 = 0; i4 < 8; ++i4) {
+          const float4 x4 = lds128(xn_s + (uint32_t)i4 * 16u);
+          const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int i = i4 * 4 + j;
+            const float dot = fmaf(__uint_as_float(rs[i]), 1.0f / kF16LoScale, __uint_as_float(rm[i]));   // scaled by 2^s
+            const float d2 = fmaxf(fmaf(ms, dot, xv[j] + e2), 0.f);
+            if (d2 * kBandUp < bd[i]) { bd[i] = d2; bi[i] = code; }   // clearly smaller (codes ascend per thread: ties keep the lowest)
+            band |= d2 < bd[i];                                        // smaller, but within the band: decide on the roots below
+          }
+        }
+        if (__builtin_expect(band, 0)) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {     // (unrolled: a dynamic index would move the register arrays to local memory)
+            const float dot = fmaf(__uint_as_float(rs[i]), 1.0f / kF16LoScale, __uint_as_float(rm[i]));
+            const float d2 = fmaxf(fmaf(ms, dot, xn[fh * 32 + i] + e2), 0.f);
+            if (d2 < bd[i] && sqrtf(d2) < sqrtf(bd[i])) { bd[i] = d2; bi[i] = code; }
+          }
         }
       }
+#pragma unroll
+      for (int i = 0; i < 32; ++i) bd[i] = sqrtf(bd[i]);   // the cross-lane argmin below compares rounded roots, like the reference
       // ---- argmin over the 128 code lanes x 16 blocks: warp shuffles, then the 4 quarters through smem -----------
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
