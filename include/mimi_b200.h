@@ -162,7 +162,9 @@ int mimi_b200_encode_phase(mimi_b200_t* h, int phase, int b0, int b1, const floa
 
 /* Debug/parity taps: copy an internal activation of the LAST encode call into d_out (channels-last
    [B, rows, C] fp32). `which`: 0..13 = output of SEANet conv i (after residual add for block.3 convs),
-   100+l = transformer layer l output. Returns rows/C through the out params. */
+   100+l = transformer layer l output; 200 = the latent, 201 = the RVQ input projections [sem | aco] (in generation 9 the
+   acoustic half holds the last stage's residual after an encode with more than two codebooks: rvq_f16.cuh keeps the fp32
+   residual there). Returns rows/C through the out params. */
 int mimi_b200_debug_tap(mimi_b200_t* h, int which, float* d_out, size_t out_capacity_floats,
                         int64_t* rows_per_item, int* channels, void* stream);
 
@@ -172,10 +174,10 @@ int mimi_b200_debug_tap(mimi_b200_t* h, int which, float* d_out, size_t out_capa
         and leave d_codes untouched)
      2  per-launch CUDA-event profiling on/off (resets the profile)
      3  kernel generation ("mode"), default 9:
-          9  fused 24 kHz front end (front_fused.cuh) + CTA-pair tcgen05 GEMM (tc_gemm5.cuh) with every operand as an fp16
+          9  fused 24 kHz front end (front_f16.cuh) + CTA-pair tcgen05 GEMM (tc_gemm5.cuh; tc_gemm7.cuh for the convs whose taps
+             share input rows) + tcgen05 attention + tensor-core RVQ (rvq_f16.cuh), with every GEMM operand as an fp16
              hi/lo pair (activations: hi + lo/2048, weights row-scaled by a power of two): hi*hi + hi*lo + lo*hi all on
-             kind::f16, 3 tensor passes, 4 bytes per activation element; + tcgen05 attention + tensor-core RVQ.
-             fp16 ends at 65504 (see mimi_b200_range_overflow)
+             kind::f16, 3 tensor passes, 4 bytes per activation element. fp16 ends at 65504 (see mimi_b200_range_overflow)
           7  the same with TF32 hi (fp32) and bf16 lo operands: hi*hi and hi*lo on kind::tf32, lo*hi on kind::f16 (5 pass
              units, 6 bytes per element); fp32 range -- the fallback of mode 9
           0  every layer on fp32 FFMA (exact-fp32 bisection baseline; also what the decode direction runs on)

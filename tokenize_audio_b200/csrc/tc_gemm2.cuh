@@ -118,6 +118,12 @@ __device__ __forceinline__ void prefetch_residual(const Epilogue& ep, int b, int
   }
 }
 
+// streaming 8-byte store under a predicate (no branch)
+__device__ __forceinline__ void st_cs_v2_if(void* p, uint32_t a, uint32_t b, uint32_t pred) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\t@q st.global.cs.v2.b32 [%0], {%1, %2};\n\t}"
+               ::"l"(p), "r"(a), "r"(b), "r"(pred) : "memory");
+}
+
 // Finish a tile: thread (lane) holds acc[0, HALF) = columns ncol0 + [0, HALF) of row row_base + lane.
 //   phase 1 (thread = row): v = acc * cmul[c] + cadd[c] (the per-column affine the host folds weight unscaling, bias and
 //            LayerScale into), GELU(erf) for fc1, into the warp's swizzled staging tile;
@@ -137,21 +143,27 @@ __device__ __forceinline__ void finish_tile(const Epilogue& ep, float (&acc)[HAL
   // rows of this thread's coalesced phase that exist (bit `it`): inside the tile's item, and -- in a flattened launch -- inside
   // the length of the item the row falls into; and their element offsets row * N + 4 cj
   uint32_t live = 0;
-  long long roff[IT];
+  // addresses = a tile-uniform 64-bit base (item, first row of this warp's 32, first column) + a per-thread 32-bit offset inside
+  // the tile: one add per access instead of a 64-bit multiply-add chain (the first layout rebuilt row * N + column in 64 bits
+  // for every float4: 3.5 of the 33 instructions per output element of the k = 1 convs)
+  uint32_t toff[IT];
 #pragma unroll
   for (int it = 0; it < IT; ++it) {
     const int row = row_base + it * RPI + rr;
     bool ok = row < Lout;
     if (ok && ep.flat_rows > 0 && ep.flat_len) ok = (row % ep.flat_rows) < __ldg(ep.flat_len + row / ep.flat_rows);
     live |= (uint32_t)ok << it;
-    roff[it] = (long long)row * ep.N + cj * 4;
+    toff[it] = (uint32_t)((it * RPI + rr) * ep.N + cj * 4);
   }
   const float* __restrict__ cm = ep.cmul + ncol0;
   const float* __restrict__ ca = ep.cadd + ncol0;
-  const long long raw_base = (long long)b * ep.raw_item_stride + ncol0;
-  const long long split_base = (long long)b * ep.split_item_stride + (long long)ep.split_front * ep.N + ncol0;
+  const long long tile_off = (long long)row_base * ep.N + ncol0;
+  const long long raw_base = (long long)b * ep.raw_item_stride + tile_off;
+  const long long split_base = (long long)b * ep.split_item_stride + (long long)ep.split_front * ep.N + tile_off;
   const float* resp = ep.res ? ep.res + raw_base : nullptr;
   float* rawp = ep.out_raw ? ep.out_raw + raw_base : nullptr;
+  uint16_t* hi16 = reinterpret_cast<uint16_t*>(ep.out_hi) + split_base;
+  uint16_t* lo16 = reinterpret_cast<uint16_t*>(ep.out_lo) + split_base;
   const bool do_split = ep.out_hi != nullptr, do_elu = ep.elu_split != 0, do_act = ep.act == 1, do_act_fast = ep.act == 2;
   const int wkey = (LPR == 8) ? (lane & 7) : ((lane >> 1) & (LPR - 1));
   __half2 mx2 = __floats2half2_rn(0.f, 0.f);     // LOB 3: running max |hi| of everything this thread stores (range check)
@@ -162,7 +174,7 @@ __device__ __forceinline__ void finish_tile(const Epilogue& ep, float (&acc)[HAL
 #pragma unroll
       for (int it = 0; it < IT; ++it) {
         resv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if ((live >> it) & 1u) resv[it] = *reinterpret_cast<const float4*>(resp + roff[it] + p * PC);
+        if ((live >> it) & 1u) resv[it] = *reinterpret_cast<const float4*>(resp + (toff[it] + p * PC));
       }
     }
     // ---- phase 1: affine (+ GELU) -> staging tile ----
@@ -198,7 +210,7 @@ __device__ __forceinline__ void finish_tile(const Epilogue& ep, float (&acc)[HAL
     if (rawp) {
 #pragma unroll
       for (int it = 0; it < IT; ++it)
-        if ((live >> it) & 1u) __stcs(reinterpret_cast<float4*>(rawp + roff[it] + p * PC), tv[it]);   // streaming stores: the
+        if ((live >> it) & 1u) __stcs(reinterpret_cast<float4*>(rawp + (toff[it] + p * PC)), tv[it]);   // streaming stores: the
         // outputs are re-read only by the NEXT kernel, after more traffic than the L2 holds (D1 -4 %, R2b -6 %; an evict-first
         // residual LOAD was 15 % slower: it fights the L2 prefetch issued at tile start)
     }
@@ -209,20 +221,21 @@ __device__ __forceinline__ void finish_tile(const Epilogue& ep, float (&acc)[HAL
       }
 #pragma unroll
       for (int it = 0; it < IT; ++it) {
-        const long long o = split_base + roff[it] + p * PC;
+        const uint32_t o = toff[it] + p * PC;
         if (LOB == 3) {
           const uint32_t h01 = pack_f16x2(tv[it].x, tv[it].y), h23 = pack_f16x2(tv[it].z, tv[it].w);
           const __half2 g01 = *reinterpret_cast<const __half2*>(&h01), g23 = *reinterpret_cast<const __half2*>(&h23);
           const float2 f01 = __half22float2(g01), f23 = __half22float2(g23);
           const uint2 lo2 = make_uint2(pack_f16x2((tv[it].x - f01.x) * kF16LoScale, (tv[it].y - f01.y) * kF16LoScale),
                                        pack_f16x2((tv[it].z - f23.x) * kF16LoScale, (tv[it].w - f23.y) * kF16LoScale));
-          if ((live >> it) & 1u) {
-            mx2 = __hmax2(mx2, __hmax2(__habs2(g01), __habs2(g23)));
-            __stcs(reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(ep.out_hi) + o), make_uint2(h01, h23));
-            __stcs(reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(ep.out_lo) + o), lo2);
-          }
+          // predicated stores instead of a branch around split + stores (the compiler sank the whole split into the branch:
+          // BSSY / BRA / BSYNC per float4); a dead row's values never leave the registers and never reach the range check
+          const uint32_t lv = (live >> it) & 1u;
+          if (lv) mx2 = __hmax2(mx2, __hmax2(__habs2(g01), __habs2(g23)));
+          st_cs_v2_if(hi16 + o, h01, h23, lv);
+          st_cs_v2_if(lo16 + o, lo2.x, lo2.y, lv);
         } else if ((live >> it) & 1u) {
-          store_split4_lob(ep.out_hi + o, reinterpret_cast<uint16_t*>(ep.out_lo) + o, tv[it]);
+          store_split4_lob(ep.out_hi + split_base + o, lo16 + o, tv[it]);
         }
       }
     }
