@@ -104,3 +104,26 @@ def test_host_pack_gathers_and_zero_pads():
             assert bool((buf[i, 0, n:zto[i]] == 0).all()) and bool((buf[i, 0, zto[i]:] == 7).all())
     bad = (C.c_int64 * B)(*[N + 1] * B)
     assert lib.mimi_b200_host_pack(buf.data_ptr(), buf.stride(0), src, bad, z, B, 2) != 0
+
+
+def test_item_ranges_of_equal_work():
+    """encode() splits a batch into contiguous item ranges for its side streams: equal total length when the lengths are known
+    (every range non-empty, bounds monotone, the last one ends at B), equal item counts otherwise."""
+    from tokenize_audio_b200.encoder import MimiB200Model as M
+    assert M._range_bounds(64, 2, None) == [0, 32, 64]
+    assert M._range_bounds(8, 2, [1, 1, 1, 1, 10, 10, 10, 10]) == [0, 6, 8]
+    assert M._range_bounds(8, 2, [100, 1, 1, 1, 1, 1, 1, 1]) == [0, 1, 8]
+    assert M._range_bounds(8, 3, [5] * 8) == [0, 3, 5, 8]
+    assert M._range_bounds(2, 2, [0, 0]) == [0, 1, 2]
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        B = int(rng.integers(2, 70))
+        n = int(rng.integers(2, min(B, 4) + 1))
+        vl = rng.integers(0, 500000, size=B).tolist()
+        b = M._range_bounds(B, n, vl)
+        assert b[0] == 0 and b[-1] == B and len(b) == n + 1 and all(x < y for x, y in zip(b, b[1:]))
+        if n == 2 and sum(vl) > 0:
+            # no other split point is closer to half of the work
+            half = sum(vl) / 2
+            best = min(range(1, B), key=lambda k: abs(sum(max(v, 1) for v in vl[:k]) - sum(max(v, 1) for v in vl) / 2))
+            assert abs(sum(vl[:b[1]]) - half) <= abs(sum(vl[:best]) - half) + B

@@ -83,6 +83,7 @@ class MimiB200Model:
         # kernel is a persistent one-CTA-per-SM grid whose last tiles leave SMs idle, the other range's kernels fill them
         # (+4-5 % on C2 / C3 / C4; three ranges are slower than one)
         self.streams = 2
+        self.balance_ranges = True        # ranges of equal total length rather than equal item count (A/B switch)
         self.min_split_batch = 8
         self._side_streams = []
         self._last_split = False
@@ -383,6 +384,25 @@ class MimiB200Model:
             return tuple(out)
         return out
 
+    @staticmethod
+    def _range_bounds(B: int, n: int, vl) -> List[int]:
+        """Item ranges of (nearly) equal WORK: with ``valid_lengths`` the split points sit where the cumulative length crosses
+        j / n of the total (a length-bucketed batch that straddles two buckets has its short items first: equal item counts gave
+        the two streams 45 % / 55 % of the samples), without them equal item counts."""
+        if vl is None or n <= 1:
+            return [B * j // n for j in range(n + 1)]
+        cum, acc = [], 0
+        for v in vl:
+            acc += max(int(v), 1)
+            cum.append(acc)
+        bounds = [0]
+        for j in range(1, n):
+            target = acc * j / n
+            k = min(range(B), key=lambda i: abs(cum[i] - target)) + 1
+            bounds.append(min(max(k, bounds[-1] + 1), B - (n - j)))
+        bounds.append(B)
+        return bounds
+
     def _encode_multi_stream(self, x, B, N, vl, K, codes, latent) -> None:
         """The batch as ``self.streams`` contiguous item ranges, each encoded on its own stream with its own workspace.
         Items are independent, so the results are those of one call; the point is that every kernel is a persistent grid
@@ -393,7 +413,7 @@ class MimiB200Model:
         main = torch.cuda.current_stream(dev)
         if len(self._side_streams) < n:
             self._side_streams = [torch.cuda.Stream(device=dev) for _ in range(n)]
-        bounds = [B * j // n for j in range(n + 1)]
+        bounds = self._range_bounds(B, n, vl if self.balance_ranges else None)
         sizes = []
         for j in range(n):
             nb = C.c_size_t()

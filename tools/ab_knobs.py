@@ -1,6 +1,6 @@
 """A/B of debug knobs on one box (diagnostic): the resident C2 step (two item ranges on two streams, CUDA events) and the
 per-kernel profile of a single-stream pass, for the default build and for each `KEY=VALUE[,KEY=VALUE]` argument.
-Usage: python tools/ab_knobs.py 17=1 18=1 17=1,18=1"""
+Usage: python tools/ab_knobs.py 17=1 18=1 17=1,18=1 balance_ranges=0"""
 import json
 import os
 import sys
@@ -58,11 +58,18 @@ def measure(reps=3):
 
 settings = [""] + sys.argv[1:]
 for s in settings:
-    pairs = [tuple(int(v) for v in kv.split("=")) for kv in s.split(",") if kv]
+    # KEY=VALUE -> debug_set(KEY, VALUE); NAME=VALUE with a non-numeric NAME -> setattr(model, NAME, VALUE) for this measurement
+    pairs = [tuple(int(v) for v in kv.split("=")) for kv in s.split(",") if kv and kv.split("=")[0].isdigit()]
+    attrs = [(kv.split("=")[0], int(kv.split("=")[1])) for kv in s.split(",") if kv and not kv.split("=")[0].isdigit()]
+    old = [(a, getattr(model, a)) for a, _ in attrs]
     for k, v in pairs:
         model.debug_set(k, v)
+    for a, v in attrs:
+        setattr(model, a, type(getattr(model, a))(v))
     try:
         print(json.dumps({"knobs": s or "default", **measure()}), flush=True)
     finally:
         for k, v in pairs:
             model.debug_set(k, 0)
+        for a, v in old:
+            setattr(model, a, v)
