@@ -119,6 +119,8 @@ WORKLOADS = {
            "desc": "30 s long-form segments, batch 16, codes -> codes_to_chars UTF-8 strings on the GPU, 8 batches cycled"},
 }
 WORKLOAD = "c2"
+ORDER = "bucketed"            # --order file: batches in pool (file) order, no length bucketing (what the reference scripts do)
+STRICT = False                # --strict: every item encoded over the padded batch length (what the reference computes)
 DESC = WORKLOADS["c2"]["desc"]
 DUR = WORKLOADS["c2"]["dur"]
 SR_IN = SR
@@ -140,7 +142,12 @@ def make_workload(rank: int):
     """POOL utterance lengths (U(2,20) s for c2) -> 8 length-bucketed batches of BATCH (lists of numpy clips at SR_IN)."""
     rng = np.random.Generator(np.random.PCG64(SEED))
     lengths = [int(v) for v in rng.uniform(DUR[0], DUR[1], size=POOL) * SR_IN]
-    batches = sharding.bucket_batches(lengths, BATCH, bucket_width=2 * SR_IN)
+    if ORDER == "file":
+        # SURVEY.md section 8(d), C2: "the un-bucketed file-order variant the reference uses" -- consecutive items form a batch
+        # (REF/emilia-mimi/process_shard.py:479-510 batches files as they come), so every batch is padded to ~ the longest clip
+        batches = [list(range(i, min(i + BATCH, POOL))) for i in range(0, POOL, BATCH)]
+    else:
+        batches = sharding.bucket_batches(lengths, BATCH, bucket_width=2 * SR_IN)
     # 12 base clips per rank; utterance i = a crop of base clip i % 12 (content does not affect timing)
     top = int(DUR[1] * SR_IN)
     base = [synth.synth_speech(SEED + 100 * rank + j, top, sr=SR_IN) for j in range(12)]
@@ -151,8 +158,11 @@ def make_workload(rank: int):
 
 
 def bench_config(extra=None):
-    cfg = {"workload": WORKLOAD, "codebooks": K_CODEBOOKS, "batch": BATCH, "durations_s": DESC,
-           "mode": "ragged (padded tails skipped, kept frames identical)", "l2": "inputs+activations per step >> 126 MB L2",
+    desc = DESC.replace("length-bucketed", "in file order (not bucketed)") if ORDER == "file" else DESC
+    mode = ("strict (every item encoded over the padded batch length, exactly the reference's computation)" if STRICT
+            else "ragged (padded tails skipped, kept frames identical)")
+    cfg = {"workload": WORKLOAD, "codebooks": K_CODEBOOKS, "batch": BATCH, "durations_s": desc,
+           "mode": mode, "l2": "inputs+activations per step >> 126 MB L2",
            "weights": "synthetic seed 0 (kyutai/mimi architecture)"}
     if extra:
         cfg.update(extra)
@@ -323,7 +333,7 @@ def run_reference(args, rank, world, device="cpu"):
 
     n_s = len(samples[0])
     sample_txt = (f"{n_s} of the {BATCH} items of each step's batch (every {max(1, BATCH // REF_ITEMS_PER_STEP)}th item of the "
-                  f"length-sorted batch, one forward of batch {n_s})" if n_s < BATCH else f"the full {BATCH}-item batch per step")
+                  f"{'length-sorted' if ORDER == 'bucketed' else 'file-order'} batch, one forward of batch {n_s})" if n_s < BATCH else f"the full {BATCH}-item batch per step")
     if not cuda:
         val, dt = timed()
         emit(json.dumps({
@@ -445,7 +455,7 @@ def run_b200(args, rank, world, local_rank):
         model.debug_set(int(k), int(v))
     if args.streams:
         model.streams = args.streams
-    wrapper = MimiEncoder(model, device=str(dev), ragged=True, num_quantizers=K_CODEBOOKS)
+    wrapper = MimiEncoder(model, device=str(dev), ragged=not STRICT, num_quantizers=K_CODEBOOKS)
     clips, lengths, batches = make_workload(rank)
     peaks = load_peaks()
     native = SR_IN != SR
@@ -466,7 +476,7 @@ def run_b200(args, rank, world, local_rank):
     model.reserve_workspace(BATCH, max(x.shape[2] for x, _ in dev_batches), K_CODEBOOKS)
     wrapper.reserve(BATCH, max(x.shape[2] for x, _ in dev_batches))
     audio_s = [sum(l) / SR for _, l in dev_batches]
-    computed_s = [sum(min(x.shape[2], -(-n // 1920) * 1920) for n in l) / SR for x, l in dev_batches]
+    computed_s = [(x.shape[0] * x.shape[2] if STRICT else sum(min(x.shape[2], -(-n // 1920) * 1920) for n in l)) / SR for x, l in dev_batches]
 
     def barrier():
         if world > 1:
@@ -475,7 +485,7 @@ def run_b200(args, rank, world, local_rank):
 
     def resident_step(i):
         x, l = dev_batches[i % N_BATCHES]
-        codes = model.encode(x, num_quantizers=K_CODEBOOKS, valid_lengths=l if BATCH > 1 else None).audio_codes
+        codes = model.encode(x, num_quantizers=K_CODEBOOKS, valid_lengths=l if (BATCH > 1 and not STRICT) else None).audio_codes
         if STRINGS:
             return utils.codes_to_utf8_device(codes, [-(-n // 1920) for n in l])
         return codes
@@ -734,6 +744,8 @@ def run_b200(args, rank, world, local_rank):
         "config": bench_config(),
         "launch": (f"encode() runs the batch as {split_streams} item ranges on {split_streams} streams" if split_streams > 1 else "one stream"),
         "audio_s_per_step": total_audio / args.steps,
+        "computed_audio_s_per_step": total_computed / args.steps,
+        "padding_waste": sharding.padding_waste(lengths, batches),
         "audio_hours_per_sec": value / 3600.0,
         "e2e": {"value": e2e_value, "unit": "x_realtime", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "api": api},
         "e2e_single_call": {"value": e2e1_value, "unit": "x_realtime", "latency_ms_median": 1e3 * float(np.median(lat)),
@@ -744,6 +756,7 @@ def run_b200(args, rank, world, local_rank):
 
 
 def main():
+    global ORDER, STRICT
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=16)
@@ -751,6 +764,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference", "reference-cuda"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["resample", "utf8"], help="c2 = the metric's config (default)")
+    ap.add_argument("--order", default="bucketed", choices=["bucketed", "file"],
+                    help="c2 variant of SURVEY.md 8(d): 'file' = batches in pool order without length bucketing (the reference's own batching)")
+    ap.add_argument("--strict", action="store_true",
+                    help="c2 variant of SURVEY.md 8(d): encode every item over the padded batch length (no valid_lengths), as the reference does")
     ap.add_argument("--mode", type=int, default=None, help="debug: kernel generation 0 / 7 / 9 (see MimiB200Model.set_mode)")
     ap.add_argument("--streams", type=int, default=0, help="debug: item ranges on side streams inside encode()")
     ap.add_argument("--dbg", action="append", default=[], help="debug: KEY=VALUE for mimi_b200_debug_set (A/B knobs)")
@@ -764,6 +781,7 @@ def main():
             run_byte_kernel(args, local_rank)
         return
     select_workload(args.workload)
+    ORDER, STRICT = args.order, bool(args.strict)
     if args.mode == 7:
         HBM_BYTES_PER_AUDIO_S["front_fused"] = 24000 * 4 + 24000 * 64 * 6      # TF32 hi (fp32) + bf16 lo
     if args.impl == "reference":
