@@ -127,3 +127,36 @@ def test_item_ranges_of_equal_work():
             half = sum(vl) / 2
             best = min(range(1, B), key=lambda k: abs(sum(max(v, 1) for v in vl[:k]) - sum(max(v, 1) for v in vl) / 2))
             assert abs(sum(vl[:b[1]]) - half) <= abs(sum(vl[:best]) - half) + B
+
+
+def test_bench_c2_variants_keep_the_items_and_change_only_the_batching():
+    """bench.py --order file / --strict: the same 512 utterances, batched in pool order instead of
+    by length bucket; the strict variant's config says that every item runs over the padded length."""
+    import importlib
+    import sys
+    argv = sys.argv
+    sys.argv = ["bench.py"]
+    try:
+        bench = importlib.import_module("bench")
+    finally:
+        sys.argv = argv
+    bench.select_workload("c2")
+    keep = bench.ORDER, bench.STRICT, bench.synth.synth_speech
+    bench.synth.synth_speech = lambda seed, n, sr=24000: np.zeros(n, np.float32)     # the audio itself is irrelevant here
+    try:
+        got = {}
+        for order in ("bucketed", "file"):
+            bench.ORDER = order
+            clips, lengths, batches = bench.make_workload(0)
+            assert sorted(i for b in batches for i in b) == list(range(bench.POOL))
+            assert all(len(b) == bench.BATCH for b in batches)
+            assert [[len(c) for c in cl] for cl in clips] == [[lengths[i] for i in b] for b in batches]
+            got[order] = sharding.padding_waste(lengths, batches)
+        assert batches == [list(range(i, i + bench.BATCH)) for i in range(0, bench.POOL, bench.BATCH)]
+        assert got["bucketed"] < 0.2 < 0.4 < got["file"]
+        bench.STRICT = True
+        assert bench.bench_config()["mode"].startswith("strict") and "file order" in bench.bench_config()["durations_s"]
+        bench.ORDER, bench.STRICT = "bucketed", False
+        assert bench.bench_config()["mode"].startswith("ragged") and "length-bucketed" in bench.bench_config()["durations_s"]
+    finally:
+        bench.ORDER, bench.STRICT, bench.synth.synth_speech = keep

@@ -1000,7 +1000,7 @@ class MimiEncoder:
         """Long-form audio (8f rank 3). ``max_chunk_duration=None``: the whole signal in ONE encode call -- exactly
         ``MimiModel.encode`` on the unsplit waveform, i.e. one continuous stream (every conv halo and the 250-frame
         attention window carry across what would have been piece boundaries). The engine takes items of up to 65 536
-        positions at 25 Hz (43 min) and needs ~33 MB of workspace per audio-second.
+        positions at 25 Hz (43 min) and needs ~23 MB of workspace per audio-second (33 MB in the TF32 generation).
         ``max_chunk_duration=s``: what REF/yodas2-mimi/process_shard.py:459-493 does -- pieces of at most ``s`` seconds
         encoded independently (context reset at every cut) and concatenated along time; bit-identical to that loop."""
         audio_array = np.asarray(audio_array)
