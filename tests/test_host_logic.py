@@ -160,3 +160,25 @@ def test_bench_c2_variants_keep_the_items_and_change_only_the_batching():
         assert bench.bench_config()["mode"].startswith("ragged") and "length-bucketed" in bench.bench_config()["durations_s"]
     finally:
         bench.ORDER, bench.STRICT, bench.synth.synth_speech = keep
+
+
+def test_resample_audio_defaults_to_the_reference_resampler_when_it_exists(monkeypatch):
+    """the drop-in ``resample_audio`` must not silently swap soxr_hq for the GPU filter. backend=None -> librosa
+    when importable, else the GPU kernel with ONE RuntimeWarning; explicit names are taken as given; equal rates are a no-op."""
+    import importlib.util
+    import warnings
+    from tokenize_audio_b200 import utils
+    x = np.zeros(10, np.float32)
+    assert utils.resample_audio(x, 24000, 24000) is x
+    assert utils._resampler_backend("b200") == "b200" and utils._resampler_backend("librosa") == "librosa"
+    with pytest.raises(ValueError, match="unknown resampler backend"):
+        utils._resampler_backend("sox")
+    real = importlib.util.find_spec
+    monkeypatch.setattr(importlib.util, "find_spec", lambda name, *a, **k: object() if name == "librosa" else real(name, *a, **k))
+    assert utils._resampler_backend(None) == "librosa"
+    monkeypatch.setattr(importlib.util, "find_spec", lambda name, *a, **k: None if name == "librosa" else real(name, *a, **k))
+    monkeypatch.setattr(utils, "_warned_resampler", False)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        assert utils._resampler_backend(None) == "b200" and utils._resampler_backend(None) == "b200"
+    assert len([m for m in w if issubclass(m.category, RuntimeWarning)]) == 1

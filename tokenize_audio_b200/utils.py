@@ -225,24 +225,49 @@ def resample_batch(audio: Sequence[np.ndarray], orig_sr: int, target_sr: int = 2
     return d_out, lens_out
 
 
-def resample_audio(audio: np.ndarray, orig_sr: int, target_sr: int, backend: str = "b200") -> np.ndarray:
+_warned_resampler = False
+
+
+def _resampler_backend(backend: Optional[str]) -> str:
+    """``None`` -> "librosa" when it is importable (the reference's own resampler: identical tokens), else "b200" with a
+    one-time warning that the tokens of resampled audio will not be the reference's."""
+    global _warned_resampler
+    if backend is not None:
+        if backend not in ("librosa", "b200"):
+            raise ValueError(f"unknown resampler backend '{backend}'")
+        return backend
+    import importlib.util
+    if importlib.util.find_spec("librosa") is not None:
+        return "librosa"
+    if not _warned_resampler:
+        import warnings
+        warnings.warn("resample_audio: librosa is not installed, using the GPU polyphase resampler -- a different filter than "
+                      "the reference's soxr_hq, so Mimi codes of the resampled audio will differ from the reference pipeline's "
+                      "(pass backend='b200' to choose it explicitly and silence this warning)", RuntimeWarning, stacklevel=3)
+        _warned_resampler = True
+    return "b200"
+
+
+def resample_audio(audio: np.ndarray, orig_sr: int, target_sr: int, backend: Optional[str] = None) -> np.ndarray:
     """REF/emilia-mimi/utils.py:84-87: no-op when the rates agree, else band-limited resampling to
     ``ceil(n * target_sr / orig_sr)`` samples (librosa ``fix=True``).
 
     **Not bit-compatible with the reference.** The reference calls ``librosa.resample``, whose default backend is libsoxr
     "HQ"; that library is not available offline and nothing in the reference pins its output, so parity of this function
-    is UNPINNED. ``backend="b200"`` (default) runs the GPU polyphase FIR -- a Kaiser-windowed sinc, 32
+    is UNPINNED. ``backend="b200"`` runs the GPU polyphase FIR -- a Kaiser-windowed sinc, 32
     zero crossings, roll-off 0.945, > 120 dB stop band -- which is a different (equally band-limited) filter: the 24 kHz
     waveform differs from soxr_hq's in the last octave below Nyquist, and Mimi codes computed from it differ on the frames
     where that matters (``bench.py --workload c1`` reports the code agreement between this filter and two other
-    high-quality resamplers as a yardstick). For runs that must reproduce the reference's tokens exactly, pass
-    ``backend="librosa"`` (needs librosa + soxr installed; host CPU) and feed the result to the encoder at 24 kHz."""
+    high-quality resamplers as a yardstick). ``backend="librosa"`` is the reference's own call (host CPU; needs librosa +
+    soxr; ImportError if absent, there is no silent substitute). The default, ``backend=None``, keeps the drop-in
+    parity-safe: librosa when it is installed -- as it is wherever the reference scripts run -- and otherwise the GPU kernel
+    with a one-time ``RuntimeWarning``. The GPU resampler is thus opt-in (here, ``resample_batch`` and
+    ``MimiEncoder.encode_native_rate_batch``) wherever the reference's exact tokens are reachable."""
     if orig_sr == target_sr:
         return audio
+    backend = _resampler_backend(backend)
     if backend == "librosa":
-        import librosa                      # ImportError if absent: there is no silent substitute
+        import librosa
         return librosa.resample(audio, orig_sr=orig_sr, target_sr=target_sr)
-    if backend != "b200":
-        raise ValueError(f"unknown resampler backend '{backend}'")
     out, lens = resample_batch([np.asarray(audio)], orig_sr, target_sr)
     return out[0, 0, : lens[0]].cpu().numpy()
