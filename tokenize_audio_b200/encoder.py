@@ -1001,6 +1001,8 @@ class MimiEncoder:
         ``MimiModel.encode`` on the unsplit waveform, i.e. one continuous stream (every conv halo and the 250-frame
         attention window carry across what would have been piece boundaries). The engine takes items of up to 65 536
         positions at 25 Hz (43 min) and needs ~23 MB of workspace per audio-second (33 MB in the TF32 generation).
+        (The reference itself counts frames with a float32 division, modeling_mimi.py:279-280, exact only below 2^24 samples =
+        11.6 min; past that this engine keeps the exact integer ceil(L / stride), so only there can the two differ.)
         ``max_chunk_duration=s``: what REF/yodas2-mimi/process_shard.py:459-493 does -- pieces of at most ``s`` seconds
         encoded independently (context reset at every cut) and concatenated along time; bit-identical to that loop."""
         audio_array = np.asarray(audio_array)
