@@ -111,6 +111,9 @@ def load_library(path: str | None = None) -> C.CDLL:
         except Exception as e:  # stale-but-present library is still usable; a missing one is fatal
             if not os.path.exists(p):
                 raise MimiB200Error(f"libmimi_b200.so is missing and could not be built: {e}") from e
+            import warnings
+            warnings.warn(f"libmimi_b200.so is older than its sources and could not be rebuilt ({e}); loading the existing "
+                          "library", RuntimeWarning, stacklevel=2)
     if not os.path.exists(p):
         raise MimiB200Error(f"{p} not found: the CUDA extension is required (there is no CPU fallback)")
     lib = C.CDLL(p)
