@@ -42,3 +42,22 @@ def test_same_rate_is_identity_and_lengths():
     assert R.out_len(160000, 16000, 24000) == 240000
     assert R.out_len(1, 16000, 24000) == 2
     assert len(R.resample(np.zeros(0, np.float32), 16000, 24000)) == 0
+
+
+def test_response_against_the_soxr_hq_specification():
+    """The reference's resampler (soxr_hq, not installed) is specified as: flat to 0.9136 x Nyquist, >= 120 dB down from
+    1.0 x Nyquist. This pins what the stand-in filter actually does against that mask, so that the documentation cannot drift:
+    it is softer (droop before soxr's pass-band edge, -24 dB at Nyquist, 120 dB only from 1.08 x Nyquist)."""
+    for sr_in in (16000, 48000):
+        h, L, M, c = R.design_taps(sr_in, 24000)
+        nyq = min(sr_in, 24000) / 2.0
+        nfft = 1 << 20
+        H = np.abs(np.fft.rfft(h.astype(np.float64) / L, nfft))
+        f = np.fft.rfftfreq(nfft, 1.0 / (L * sr_in)) / nyq
+        db = 20 * np.log10(np.maximum(H, 1e-15))
+        at = lambda x: float(db[np.argmin(np.abs(f - x))])
+        assert abs(at(0.5)) < 1e-4 and -0.02 < at(0.84) < 0.0           # flat in the body of the band
+        assert -1.9 < at(0.9136) < -1.7                                  # soxr_hq is still flat here
+        assert abs(at(0.945) + 6.02) < 0.1                               # ROLLOFF is the -6 dB point
+        assert -25.0 < at(1.0) < -23.5                                   # soxr_hq: -120 dB here
+        assert db[f >= 1.08].max() <= -119.9                             # full rejection only from 1.08 x Nyquist

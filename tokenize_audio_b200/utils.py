@@ -255,9 +255,10 @@ def resample_audio(audio: np.ndarray, orig_sr: int, target_sr: int, backend: Opt
     **Not bit-compatible with the reference.** The reference calls ``librosa.resample``, whose default backend is libsoxr
     "HQ"; that library is not available offline and nothing in the reference pins its output, so parity of this function
     is UNPINNED. ``backend="b200"`` runs the GPU polyphase FIR -- a Kaiser-windowed sinc, 32
-    zero crossings, roll-off 0.945, > 120 dB stop band -- which is a different (equally band-limited) filter: the 24 kHz
-    waveform differs from soxr_hq's in the last octave below Nyquist, and Mimi codes computed from it differ on the frames
-    where that matters (``bench.py --workload c1`` reports the code agreement between this filter and two other
+    zero crossings, -6 dB at 0.945 x Nyquist -- which is a different and SOFTER filter than soxr_hq (flat to 0.9136 x Nyquist,
+    120 dB down from 1.0 x Nyquist): -1.8 dB at soxr_hq's pass-band edge, -24 dB at Nyquist, 120 dB only from 1.08 x Nyquist
+    (oracle/resample_oracle.py pins the response). The 24 kHz waveform therefore differs from soxr_hq's in the top sixth of
+    the input band, and Mimi codes computed from it differ on the frames where that matters (``bench.py --workload c1`` reports the code agreement between this filter and two other
     high-quality resamplers as a yardstick). ``backend="librosa"`` is the reference's own call (host CPU; needs librosa +
     soxr; ImportError if absent, there is no silent substitute). The default, ``backend=None``, keeps the drop-in
     parity-safe: librosa when it is installed -- as it is wherever the reference scripts run -- and otherwise the GPU kernel
